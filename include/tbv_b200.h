@@ -1,0 +1,227 @@
+/* tbv_b200.h — C-ABI of the B200-native TBV / CFEAR hot path (libtbv_b200.so).
+ *
+ * The reference (dan11003/tbv_slam_public @ 90f17c59) has no FFI layer: its seams for this path are C++ classes
+ * called in-process.  Every entry point below names the reference interface it replaces (paths relative to the
+ * reference root); INTEGRATION.md shows the few-line adapter a maintainer would add at each call site.
+ *
+ * Conventions
+ *   - plain C types only; caller-owned HOST buffers unless the name ends in _dev (then: device pointers);
+ *   - int status: 0 = TBV_OK, <0 = error (never exit(), never throws); tbv_last_error() gives the message;
+ *   - no global state: everything hangs off a tbv_ctx (one CUDA device, one stream); distinct contexts may be
+ *     used from distinct threads (the reference's odometry thread + loop-closure thread);
+ *   - poses are planar (x, y, theta[rad]) — the reference's Eigen::Affine3d are planar by construction
+ *     (vectorToAffine3d, cfear_radarodometry/src/cfear_radarodometry/registration.cpp:129-135);
+ *   - a "cell" (reference class `cell`, cfear_radarodometry/include/cfear_radarodometry/pointnormal.h:45-105)
+ *     crosses the boundary as 16 doubles, see tbv_cell.
+ */
+#ifndef TBV_B200_H_
+#define TBV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBV_OK 0
+#define TBV_ERR_INVALID (-1)   /* bad argument */
+#define TBV_ERR_CUDA (-2)      /* CUDA runtime error, see tbv_last_error */
+#define TBV_ERR_CAPACITY (-3)  /* an internal or caller buffer is too small */
+#define TBV_ERR_NO_GPU (-4)    /* no CUDA device: the product has no CPU fallback */
+
+typedef struct tbv_ctx tbv_ctx;
+
+/* ---- enums: values match the reference's enums ------------------------------------------------------------ */
+/* cost_metric  (cfear_radarodometry/include/cfear_radarodometry/registration.h:55) */
+enum { TBV_P2P = 0, TBV_P2L = 1, TBV_P2D = 2 };
+/* loss_type    (registration.h:60) */
+enum { TBV_LOSS_NONE = 0, TBV_LOSS_HUBER = 1, TBV_LOSS_CAUCHY = 2, TBV_LOSS_SOFTLONE = 3, TBV_LOSS_COMBINED = 4, TBV_LOSS_TUKEY = 5 };
+/* weightoption (registration.h:50) */
+enum { TBV_W_UNIFORM = 0, TBV_W_SIM_N = 1, TBV_W_SIM_DIRECTION = 2, TBV_W_SIM_SCALE = 3, TBV_W_COMBINED = 4 };
+
+/* ---- records ------------------------------------------------------------------------------------------------ */
+/* reference `cell` (pointnormal.h:66-73) */
+typedef struct tbv_cell {
+  double u[2];            /* u_ */
+  double cov[4];          /* cov_ row-major: c00 c01 c10 c11 */
+  double scale;           /* scale_ (planarity) */
+  double snormal[2];      /* snormal_ */
+  double orth_normal[2];  /* orth_normal */
+  double lambda_min, lambda_max;
+  double sum_intensity, avg_intensity;
+  double n_samples;       /* Nsamples_ */
+} tbv_cell;
+
+/* k-strongest / CA-CFAR filter parameters — radarDriver::Parameters (radar_driver.h:40-64); z_min, range_res,
+ * min_distance are float there and widened exactly as StructuredKStrongest's ctor does (radar_filters.h:86). */
+typedef struct tbv_filter_params {
+  float z_min;
+  int k_strongest;
+  float min_distance;
+  float range_res;
+} tbv_filter_params;
+
+typedef struct tbv_cfar_params {   /* AzimuthCACFAR ctor, cfar.h:28-42; max_distance = 400 at radar_driver.cpp:54 */
+  int window_size;
+  double false_alarm_rate;
+  int nb_guard_cells;
+  double range_resolution;
+  double static_threshold;
+  double min_distance;
+  double max_distance;
+} tbv_cfar_params;
+
+/* A filtered cloud in struct-of-arrays form; each array holds `capacity` entries per scan, scan b starts at
+ * b*capacity.  Order = the reference's: azimuth-major, ascending (intensity, range) inside an azimuth.
+ * Any array pointer may be NULL (not wanted). */
+typedef struct tbv_points {
+  int capacity;        /* entries per scan (>= n_az * k for the k-strongest filter) */
+  int* count;          /* [batch] out: points per scan */
+  uint16_t* azimuth;
+  uint16_t* range;
+  uint8_t* intensity;
+  float* x;
+  float* y;
+} tbv_points;
+
+/* n_scan_normal_reg configuration (n_scan_normal.h:33-35,53-55,72-75; registration.h:117-122) */
+typedef struct tbv_reg_params {
+  int cost;                 /* TBV_P2L ... */
+  int loss;                 /* TBV_LOSS_HUBER ... */
+  int weight_opt;           /* TBV_W_... */
+  double loss_limit;        /* 0.1 */
+  double cov_scale;         /* SetD2dPar */
+  double regularization;    /* SetD2dPar */
+  int max_itr_association;  /* SetParameters; default 8 */
+  int max_itr_solver;       /* SetParameters; default 20 */
+} tbv_reg_params;
+
+typedef struct tbv_reg_summary {
+  int success;              /* Register's bool */
+  int itrs;                 /* timing key "itrs": association iteration counter at exit */
+  int lm_iterations;        /* total LM iterations over all association rounds */
+  int num_residuals;        /* summary_.num_residuals of the last solve */
+  int last_n_iterations;    /* summary_.iterations.size() of the last solve */
+  int termination;          /* 0 convergence, 1 no_convergence, 2 failure (last solve) */
+  double score;             /* final_cost / num_residuals */
+  double final_cost;
+  double last_relative_decrease;
+} tbv_reg_summary;
+
+/* OdometryKeyframeFuser::Parameters subset on the path (odometrykeyframefuser.h:90-113) + filter + preset */
+typedef struct tbv_odom_params {
+  tbv_filter_params filter;
+  tbv_reg_params reg;       /* max_itr_* <= 0 -> class defaults (8, 20) */
+  int submap_scan_size;
+  int weight_intensity;
+  int use_guess, compensate, radar_ccw, use_keyframe;
+  double res;               /* cell radius / voxel leaf */
+  double min_keyframe_dist, min_keyframe_rot_deg;
+  double downsample_factor;
+} tbv_odom_params;
+
+typedef struct tbv_odom_out {   /* one per sequence per step */
+  double pose[3];
+  int n_points, n_cells, itrs, reg_ok, is_keyframe, n_keyframes;
+  int lm_iterations, num_residuals;
+  double score;
+} tbv_odom_out;
+
+/* ---- context -------------------------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`.  Returns NULL (and sets tbv_last_error) when no GPU is present. */
+tbv_ctx* tbv_create(int device);
+void tbv_destroy(tbv_ctx* ctx);
+const char* tbv_last_error(void);
+/* the cudaStream_t all work of this context is enqueued on (for event timing by the caller) */
+void* tbv_stream(tbv_ctx* ctx);
+int tbv_synchronize(tbv_ctx* ctx);
+/* number of kernel launches issued by this library since the context was created */
+long long tbv_launch_count(tbv_ctx* ctx);
+int tbv_version(void);
+
+/* ---- K1: k-strongest filter -------------------------------------------------------------------------------------
+ * Replaces StructuredKStrongest::StructuredKStrongest + FilterKstrongest + AxialNonMaxSupress +
+ * getPeaksFilteredPointCloud (cfear_radarodometry/src/cfear_radarodometry/radar_filters.cpp:198-337), as called by
+ * radarDriver::Process (radar_driver.cpp:57-61).  polar: batch scans of n_az rows x n_range u8, row_stride bytes
+ * between rows, scan b at polar + b*n_az*row_stride.  out_peaks may be NULL. */
+int tbv_filter_kstrongest(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_range, size_t row_stride, int batch,
+                          const tbv_filter_params* params, tbv_points* out_filtered, tbv_points* out_peaks);
+/* Same with the scans already resident in device memory; results stay on the device (tbv_cloud_* accessors). */
+int tbv_filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
+                              const tbv_filter_params* params, int want_peaks);
+/* copies the device-resident result of the last *_dev filter call to host arrays */
+int tbv_filter_fetch(tbv_ctx* ctx, tbv_points* out_filtered, tbv_points* out_peaks);
+
+/* MulRan-style input (radarDriver::Callback, radar_driver.cpp:74-90): MONO8 range-major image [n_range][n_az]
+ * rotated 90 deg CCW into the azimuth-major layout the filters expect.  Host in, host out. */
+int tbv_rotate90ccw(tbv_ctx* ctx, const uint8_t* src, int rows, int cols, uint8_t* dst);
+
+/* ---- K1b: CA-CFAR filter — AzimuthCACFAR::getFilteredPointCloud (cfar.cpp:35-83) -------------------------------- */
+int tbv_filter_cacfar(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_range, size_t row_stride, int batch,
+                      const tbv_cfar_params* params, tbv_points* out);
+
+/* ---- K2: motion compensation — CFEAR_Radarodometry::Compensate (utils.cpp:96-113) ------------------------------- */
+int tbv_compensate(tbv_ctx* ctx, float* x, float* y, int n, const double mot_xyt[3], int ccw);
+
+/* ---- K3: oriented surface points — MapPointNormal ctor / ComputeNormals / cell (pointnormal.cpp:7-90, 265-297) --- */
+/* returns TBV_OK and *n_cells (may exceed cell_capacity: then only cell_capacity records are written and the call
+ * returns TBV_ERR_CAPACITY); *n_samples (optional) = number of voxel-grid sample points examined */
+int tbv_build_cells(tbv_ctx* ctx, const float* x, const float* y, const float* intensity, int n, float radius,
+                    double downsample_factor, int weight_intensity, const double origin[2], tbv_cell* cells, int cell_capacity,
+                    int* n_cells, int* n_samples);
+
+/* ---- K4: one (target, source) pair: correspondences + robustified cost, J^T J, J^T r ----------------------------
+ * n_scan_normal_reg::AddScanPairCost (n_scan_normal.cpp:213-324) followed by one evaluation of the resulting
+ * residual blocks at x = T_src (what ceres::Problem::Evaluate / the first LM iteration computes).
+ * itr selects the search radius exactly like the reference's member itr_ (1 -> 2*radius_, else radius_ = 2.0).
+ * assoc (optional, n_src ints): target index matched to each source cell or -1. */
+int tbv_pair_normal_eq(tbv_ctx* ctx, const tbv_cell* tgt, int n_tgt, const double T_tgt[3], const tbv_cell* src, int n_src,
+                       const double T_src[3], const tbv_reg_params* params, int itr, double* cost, int* n_res, double H[9],
+                       double g[3], int32_t* assoc);
+
+/* ---- K5: registration — n_scan_normal_reg::Register (n_scan_normal.cpp:82-185) -----------------------------------
+ * scans[n_scans-1] is the moving scan (local frame), the others are fixed; T is [n_scans][3] in/out. */
+int tbv_register(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, double* T,
+                 const tbv_reg_params* params, tbv_reg_summary* summary);
+/* GetCost (n_scan_normal.cpp:186-211): residuals (optional) receives up to res_capacity corrected residuals */
+int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T,
+                 const tbv_reg_params* params, int itr, double* score, double* cost, int* n_res, double* residuals,
+                 int res_capacity);
+/* Batched independent two-scan registrations — loopclosure::Register (tbv_slam/src/tbv_slam/loopclosure.cpp:35-97):
+ * pair p registers `from` (moving, pose T_from[p]) against `to` (fixed, pose T_to[p]) with P2L / Huber 0.1 / uniform
+ * weights / SetParameters(4,10) unless params says otherwise.  Cell sets are given once (n_sets), pairs index them.
+ * Outputs per pair: T_revised (x,y,theta), T_align = T_revised^-1 * T_to, summary. */
+int tbv_register_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, const int* n_cells, int n_pairs, const int* from_set,
+                       const int* to_set, const double* T_from, const double* T_to, const tbv_reg_params* params,
+                       double* T_revised, double* T_align, tbv_reg_summary* summaries);
+
+/* ---- batched odometry: radarDriver::Process + OdometryKeyframeFuser::processFrame --------------------------------
+ * (radar_driver.cpp:48-73, odometrykeyframefuser.cpp:143-259) for n_seq independent sequences advanced in lock-step:
+ * one call consumes one polar scan per sequence and returns one pose per sequence.  All per-sequence state
+ * (keyframe window, T_prev, Tmot) lives on the device. */
+typedef struct tbv_odom tbv_odom;
+tbv_odom* tbv_odom_create(tbv_ctx* ctx, int n_seq, int n_az, int n_range, const tbv_odom_params* params);
+void tbv_odom_destroy(tbv_odom* od);
+int tbv_odom_reset(tbv_odom* od);
+/* host scans [n_seq][n_az][n_range] (pinned or pageable) -> out[n_seq]; includes H2D and D2H */
+int tbv_odom_step(tbv_odom* od, const uint8_t* polar_host, tbv_odom_out* out);
+/* scans already on the device; results stay on the device until tbv_odom_fetch */
+int tbv_odom_step_dev(tbv_odom* od, const uint8_t* polar_dev);
+int tbv_odom_fetch(tbv_odom* od, tbv_odom_out* out);
+/* Software-pipelined host path: enqueue the upload of the next step's scans on a copy stream while the previous
+ * step computes. tbv_odom_submit returns immediately; tbv_odom_collect blocks for the oldest submitted step. */
+int tbv_odom_submit(tbv_odom* od, const uint8_t* polar_host_pinned);
+int tbv_odom_collect(tbv_odom* od, tbv_odom_out* out);
+/* current cells of sequence `seq` (the scan processed last) and of its keyframe window, for parity checks */
+int tbv_odom_cells(tbv_odom* od, int seq, int keyframe /* -1 = current scan */, tbv_cell* cells, int capacity, int* n_cells,
+                   double pose[3]);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
+void* tbv_host_alloc(size_t bytes);
+void tbv_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBV_B200_H_ */

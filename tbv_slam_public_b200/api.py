@@ -1,0 +1,380 @@
+"""ctypes binding of libtbv_b200.so — the Python face of the C-ABI in include/tbv_b200.h.
+
+Class and method names follow the reference's C++ seams (StructuredKStrongest, MapPointNormal, n_scan_normal_reg,
+OdometryKeyframeFuser) so the parity tests read like tests of the reference classes.  There is no CPU fallback:
+a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtbv_b200.so")
+_LIB = None
+
+P2P, P2L, P2D = 0, 1, 2
+LOSS_NONE, HUBER, CAUCHY, SOFTLONE, COMBINED, TUKEY = 0, 1, 2, 3, 4, 5
+W_UNIFORM, W_SIM_N, W_SIM_DIR, W_SIM_SCALE, W_COMBINED = 0, 1, 2, 3, 4
+TBV_OK, TBV_ERR_INVALID, TBV_ERR_CUDA, TBV_ERR_CAPACITY, TBV_ERR_NO_GPU = 0, -1, -2, -3, -4
+
+
+class TbvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tbv error {code}: {msg}")
+        self.code = code
+
+
+class FilterParams(C.Structure):
+    _fields_ = [("z_min", C.c_float), ("k_strongest", C.c_int), ("min_distance", C.c_float), ("range_res", C.c_float)]
+
+
+class CfarParams(C.Structure):
+    _fields_ = [("window_size", C.c_int), ("false_alarm_rate", C.c_double), ("nb_guard_cells", C.c_int),
+                ("range_resolution", C.c_double), ("static_threshold", C.c_double), ("min_distance", C.c_double),
+                ("max_distance", C.c_double)]
+
+
+class Points(C.Structure):
+    _fields_ = [("capacity", C.c_int), ("count", C.POINTER(C.c_int)), ("azimuth", C.POINTER(C.c_uint16)),
+                ("range", C.POINTER(C.c_uint16)), ("intensity", C.POINTER(C.c_uint8)), ("x", C.POINTER(C.c_float)),
+                ("y", C.POINTER(C.c_float))]
+
+
+class RegParams(C.Structure):
+    _fields_ = [("cost", C.c_int), ("loss", C.c_int), ("weight_opt", C.c_int), ("loss_limit", C.c_double),
+                ("cov_scale", C.c_double), ("regularization", C.c_double), ("max_itr_association", C.c_int),
+                ("max_itr_solver", C.c_int)]
+
+
+class RegSummary(C.Structure):
+    _fields_ = [("success", C.c_int), ("itrs", C.c_int), ("lm_iterations", C.c_int), ("num_residuals", C.c_int),
+                ("last_n_iterations", C.c_int), ("termination", C.c_int), ("score", C.c_double), ("final_cost", C.c_double),
+                ("last_relative_decrease", C.c_double)]
+
+
+class OdomParams(C.Structure):
+    _fields_ = [("filter", FilterParams), ("reg", RegParams), ("submap_scan_size", C.c_int), ("weight_intensity", C.c_int),
+                ("use_guess", C.c_int), ("compensate", C.c_int), ("radar_ccw", C.c_int), ("use_keyframe", C.c_int),
+                ("res", C.c_double), ("min_keyframe_dist", C.c_double), ("min_keyframe_rot_deg", C.c_double),
+                ("downsample_factor", C.c_double)]
+
+
+class OdomOut(C.Structure):
+    _fields_ = [("pose", C.c_double * 3), ("n_points", C.c_int), ("n_cells", C.c_int), ("itrs", C.c_int), ("reg_ok", C.c_int),
+                ("is_keyframe", C.c_int), ("n_keyframes", C.c_int), ("lm_iterations", C.c_int), ("num_residuals", C.c_int),
+                ("score", C.c_double)]
+
+
+def default_reg_params(**kw) -> RegParams:
+    p = RegParams(P2L, HUBER, W_UNIFORM, 0.1, 1.0, 0.01, 0, 0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_odom_params(**kw) -> OdomParams:
+    """BASELINE config 2: CFEAR-3 filter (k=40, z_min=60, r=3), 4 keyframes, P2L, Huber 0.1, weight_opt 4, weight_intensity."""
+    p = OdomParams(FilterParams(60.0, 40, 2.5, 0.0438), RegParams(P2L, HUBER, W_COMBINED, 0.1, 1.0, 1.0, 0, 0), 4, 1, 1, 1, 0, 1,
+                   3.0, 1.5, 5.0, 1.0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m tbv_slam_public_b200.build` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.tbv_create.restype = C.c_void_p
+        L.tbv_create.argtypes = [C.c_int]
+        L.tbv_destroy.argtypes = [C.c_void_p]
+        L.tbv_last_error.restype = C.c_char_p
+        L.tbv_stream.restype = C.c_void_p
+        L.tbv_stream.argtypes = [C.c_void_p]
+        L.tbv_synchronize.argtypes = [C.c_void_p]
+        L.tbv_launch_count.restype = C.c_longlong
+        L.tbv_launch_count.argtypes = [C.c_void_p]
+        L.tbv_host_alloc.restype = C.c_void_p
+        L.tbv_host_alloc.argtypes = [C.c_size_t]
+        L.tbv_host_free.argtypes = [C.c_void_p]
+        L.tbv_filter_kstrongest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(FilterParams),
+                                            C.POINTER(Points), C.POINTER(Points)]
+        L.tbv_filter_kstrongest_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                                                C.POINTER(FilterParams), C.c_int]
+        L.tbv_filter_fetch.argtypes = [C.c_void_p, C.POINTER(Points), C.POINTER(Points)]
+        L.tbv_compensate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.tbv_rotate90ccw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        for name, argt, rest in _OPTIONAL:
+            if hasattr(L, name):
+                f = getattr(L, name)
+                if argt is not None:
+                    f.argtypes = argt
+                if rest is not None:
+                    f.restype = rest
+        _LIB = L
+    return _LIB
+
+
+_OPTIONAL = [
+    ("tbv_build_cells", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int, C.c_void_p,
+                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
+    ("tbv_pair_normal_eq", [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(RegParams),
+                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], None),
+    ("tbv_register", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RegParams), C.POINTER(RegSummary)], None),
+    ("tbv_get_cost", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RegParams), C.c_int, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_int], None),
+    ("tbv_register_batch", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.POINTER(RegParams), C.c_void_p, C.c_void_p, C.c_void_p], None),
+    ("tbv_odom_create", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(OdomParams)], C.c_void_p),
+    ("tbv_odom_destroy", [C.c_void_p], None),
+    ("tbv_odom_reset", [C.c_void_p], None),
+    ("tbv_odom_step", [C.c_void_p, C.c_void_p, C.c_void_p], None),
+    ("tbv_odom_step_dev", [C.c_void_p, C.c_void_p], None),
+    ("tbv_odom_fetch", [C.c_void_p, C.c_void_p], None),
+    ("tbv_odom_submit", [C.c_void_p, C.c_void_p], None),
+    ("tbv_odom_collect", [C.c_void_p, C.c_void_p], None),
+    ("tbv_odom_cells", [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
+    ("tbv_filter_cacfar", [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(CfarParams), C.POINTER(Points)], None),
+]
+
+
+def _check(rc):
+    if rc != 0:
+        raise TbvError(rc, lib().tbv_last_error().decode())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class _PointBufs:
+    """numpy storage behind a tbv_points."""
+
+    def __init__(self, batch, cap):
+        self.batch, self.cap = batch, cap
+        self.count = np.zeros(batch, np.int32)
+        self.az = np.zeros((batch, cap), np.uint16)
+        self.rg = np.zeros((batch, cap), np.uint16)
+        self.I = np.zeros((batch, cap), np.uint8)
+        self.x = np.zeros((batch, cap), np.float32)
+        self.y = np.zeros((batch, cap), np.float32)
+        self.c = Points(cap, self.count.ctypes.data_as(C.POINTER(C.c_int)), self.az.ctypes.data_as(C.POINTER(C.c_uint16)),
+                        self.rg.ctypes.data_as(C.POINTER(C.c_uint16)), self.I.ctypes.data_as(C.POINTER(C.c_uint8)),
+                        self.x.ctypes.data_as(C.POINTER(C.c_float)), self.y.ctypes.data_as(C.POINTER(C.c_float)))
+
+    def scan(self, b):
+        n = int(self.count[b])
+        return self.az[b, :n], self.rg[b, :n], self.I[b, :n], self.x[b, :n], self.y[b, :n]
+
+
+class Context:
+    """tbv_ctx: one CUDA device + one stream."""
+
+    def __init__(self, device: int = 0):
+        self.h = lib().tbv_create(device)
+        if not self.h:
+            raise TbvError(TBV_ERR_NO_GPU, lib().tbv_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tbv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return lib().tbv_stream(self.h)
+
+    def synchronize(self):
+        _check(lib().tbv_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return lib().tbv_launch_count(self.h)
+
+    # ---- radarDriver::Process (k-strongest branch) -----------------------------------------------------------
+    def StructuredKStrongest(self, polar: np.ndarray, z_min=60.0, k_strongest=40, min_distance=2.5, range_res=0.0438,
+                             peaks=True, n_range=None):
+        """polar: [n_az, width] or [batch, n_az, width] u8 (host); n_range <= width bins are used (row stride = width).
+        Returns (filtered, peaks) _PointBufs."""
+        polar = np.ascontiguousarray(polar, np.uint8)
+        if polar.ndim == 2:
+            polar = polar[None]
+        batch, n_az, width = polar.shape
+        n_range = n_range or width
+        stride = width
+        par = FilterParams(z_min, k_strongest, min_distance, range_res)
+        f = _PointBufs(batch, n_az * k_strongest)
+        p = _PointBufs(batch, n_az * k_strongest) if peaks else None
+        _check(lib().tbv_filter_kstrongest(self.h, _ptr(polar), n_az, n_range, stride, batch, C.byref(par), C.byref(f.c),
+                                           C.byref(p.c) if peaks else None))
+        return f, p
+
+    def filter_dev(self, polar_dev_ptr: int, n_az, n_range, batch, par: FilterParams, want_peaks=True, row_stride=None):
+        _check(lib().tbv_filter_kstrongest_dev(self.h, C.c_void_p(polar_dev_ptr), n_az, n_range, row_stride or n_range, batch,
+                                               C.byref(par), int(want_peaks)))
+
+    def filter_fetch(self, batch, n_az, k, peaks=True):
+        f = _PointBufs(batch, n_az * k)
+        p = _PointBufs(batch, n_az * k) if peaks else None
+        _check(lib().tbv_filter_fetch(self.h, C.byref(f.c), C.byref(p.c) if peaks else None))
+        return f, p
+
+    def AzimuthCACFAR(self, polar, window_size=40, false_alarm_rate=0.01, nb_guard_cells=10, range_res=0.0438,
+                      static_threshold=20.0, min_distance=2.5, max_distance=400.0, capacity=None):
+        polar = np.ascontiguousarray(polar, np.uint8)
+        if polar.ndim == 2:
+            polar = polar[None]
+        batch, n_az, n_range = polar.shape
+        par = CfarParams(window_size, false_alarm_rate, nb_guard_cells, range_res, static_threshold, min_distance, max_distance)
+        out = _PointBufs(batch, capacity or n_az * n_range)
+        _check(lib().tbv_filter_cacfar(self.h, _ptr(polar), n_az, n_range, n_range, batch, C.byref(par), C.byref(out.c)))
+        return out
+
+    def rotate90ccw(self, src):
+        src = np.ascontiguousarray(src, np.uint8)
+        H, W = src.shape
+        dst = np.zeros((W, H), np.uint8)
+        _check(lib().tbv_rotate90ccw(self.h, _ptr(src), H, W, _ptr(dst)))
+        return dst
+
+    # ---- CFEAR_Radarodometry::Compensate -------------------------------------------------------------------------
+    def Compensate(self, x, y, mot, ccw=False):
+        x = np.array(x, np.float32, copy=True)
+        y = np.array(y, np.float32, copy=True)
+        m = np.ascontiguousarray(mot, np.float64)
+        _check(lib().tbv_compensate(self.h, _ptr(x), _ptr(y), len(x), _ptr(m), int(ccw)))
+        return x, y
+
+    # ---- MapPointNormal ----------------------------------------------------------------------------------------------
+    def MapPointNormal(self, x, y, intensity, radius=3.0, downsample_factor=1.0, weight_intensity=True, origin=(0.0, 0.0),
+                       capacity=None):
+        """Returns (cells [n,16] float64, n_samples)."""
+        x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+        intensity = np.ascontiguousarray(intensity, np.float32)
+        cap = capacity or max(len(x), 1)
+        cells = np.zeros((cap, 16), np.float64)
+        o = np.ascontiguousarray(origin, np.float64)
+        nc, ns = C.c_int(0), C.c_int(0)
+        _check(lib().tbv_build_cells(self.h, _ptr(x), _ptr(y), _ptr(intensity), len(x), C.c_float(radius), C.c_double(downsample_factor),
+                                     int(weight_intensity), _ptr(o), _ptr(cells), cap, C.byref(nc), C.byref(ns)))
+        return cells[:nc.value].copy(), ns.value
+
+    # ---- n_scan_normal_reg ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _scan_ptrs(scans):
+        arrs = [np.ascontiguousarray(s, np.float64).reshape(-1, 16) for s in scans]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        ns = np.array([len(a) for a in arrs], np.int32)
+        return arrs, ptrs, ns
+
+    def pair_normal_eq(self, tgt, T_tgt, src, T_src, params: RegParams | None = None, itr=1):
+        params = params or default_reg_params()
+        tgt = np.ascontiguousarray(tgt, np.float64); src = np.ascontiguousarray(src, np.float64)
+        Tt = np.ascontiguousarray(T_tgt, np.float64); Ts = np.ascontiguousarray(T_src, np.float64)
+        H, g = np.zeros(9), np.zeros(3)
+        cost, nres = C.c_double(0), C.c_int(0)
+        assoc = np.zeros(max(len(src), 1), np.int32)
+        _check(lib().tbv_pair_normal_eq(self.h, _ptr(tgt), len(tgt), _ptr(Tt), _ptr(src), len(src), _ptr(Ts), C.byref(params), itr,
+                                        C.byref(cost), C.byref(nres), _ptr(H), _ptr(g), _ptr(assoc)))
+        return dict(n_res=nres.value, cost=cost.value, H=H.reshape(3, 3), g=g, assoc=assoc[:len(src)])
+
+    def Register(self, scans, T, params: RegParams | None = None):
+        params = params or default_reg_params()
+        arrs, ptrs, ns = self._scan_ptrs(scans)
+        Tio = np.array(T, np.float64, copy=True).reshape(len(scans), 3)
+        s = RegSummary()
+        _check(lib().tbv_register(self.h, len(scans), ptrs, _ptr(ns), _ptr(Tio), C.byref(params), C.byref(s)))
+        return Tio, s
+
+    def GetCost(self, scans, T, params: RegParams | None = None, itr=0):
+        params = params or default_reg_params()
+        arrs, ptrs, ns = self._scan_ptrs(scans)
+        Tio = np.ascontiguousarray(T, np.float64).reshape(len(scans), 3)
+        cap = int(2 * ns[-1] * (len(scans) - 1)) + 8
+        res = np.zeros(cap)
+        score, cost, n = C.c_double(0), C.c_double(0), C.c_int(0)
+        _check(lib().tbv_get_cost(self.h, len(scans), ptrs, _ptr(ns), _ptr(Tio), C.byref(params), itr, C.byref(score), C.byref(cost),
+                                  C.byref(n), _ptr(res), cap))
+        return n.value, score.value, cost.value, res[:max(n.value, 0)]
+
+    def RegisterBatch(self, sets, from_set, to_set, T_from, T_to, params: RegParams | None = None):
+        """loopclosure::Register for many candidates at once. Returns (T_revised [n,3], T_align [n,3], summaries)."""
+        params = params or default_reg_params(max_itr_association=4, max_itr_solver=10)
+        arrs, ptrs, ns = self._scan_ptrs(sets)
+        fs = np.ascontiguousarray(from_set, np.int32); ts = np.ascontiguousarray(to_set, np.int32)
+        Tf = np.ascontiguousarray(T_from, np.float64).reshape(-1, 3); Tt = np.ascontiguousarray(T_to, np.float64).reshape(-1, 3)
+        n = len(fs)
+        Tr, Ta = np.zeros((n, 3)), np.zeros((n, 3))
+        summ = (RegSummary * n)()
+        _check(lib().tbv_register_batch(self.h, len(arrs), ptrs, _ptr(ns), n, _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), C.byref(params),
+                                        _ptr(Tr), _ptr(Ta), C.cast(summ, C.c_void_p)))
+        return Tr, Ta, summ
+
+
+class OdometryKeyframeFuser:
+    """n_seq independent radarDriver + OdometryKeyframeFuser pipelines advanced in lock-step on one GPU."""
+
+    def __init__(self, ctx: Context, n_seq: int, n_az: int, n_range: int, params: OdomParams | None = None):
+        self.ctx, self.n_seq, self.n_az, self.n_range = ctx, n_seq, n_az, n_range
+        self.params = params or default_odom_params()
+        self.h = lib().tbv_odom_create(ctx.h, n_seq, n_az, n_range, C.byref(self.params))
+        if not self.h:
+            raise TbvError(TBV_ERR_INVALID, lib().tbv_last_error().decode())
+        self._out = (OdomOut * n_seq)()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tbv_odom_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().tbv_odom_reset(self.h))
+
+    def pointcloudCallback(self, polar_host: np.ndarray):
+        """One scan per sequence [n_seq, n_az, n_range] u8 from host memory -> list of OdomOut."""
+        polar_host = np.ascontiguousarray(polar_host, np.uint8)
+        assert polar_host.size == self.n_seq * self.n_az * self.n_range
+        _check(lib().tbv_odom_step(self.h, _ptr(polar_host), C.cast(self._out, C.c_void_p)))
+        return self._out
+
+    def step_dev(self, polar_dev_ptr: int):
+        _check(lib().tbv_odom_step_dev(self.h, C.c_void_p(polar_dev_ptr)))
+
+    def fetch(self):
+        _check(lib().tbv_odom_fetch(self.h, C.cast(self._out, C.c_void_p)))
+        return self._out
+
+    def submit(self, pinned_ptr: int):
+        _check(lib().tbv_odom_submit(self.h, C.c_void_p(pinned_ptr)))
+
+    def collect(self):
+        _check(lib().tbv_odom_collect(self.h, C.cast(self._out, C.c_void_p)))
+        return self._out
+
+    def cells(self, seq: int, keyframe: int = -1, capacity: int = 8192):
+        cells = np.zeros((capacity, 16))
+        n = C.c_int(0)
+        pose = np.zeros(3)
+        _check(lib().tbv_odom_cells(self.h, seq, keyframe, _ptr(cells), capacity, C.byref(n), _ptr(pose)))
+        return cells[:n.value].copy(), pose
+
+
+def poses(outs) -> np.ndarray:
+    return np.array([[o.pose[0], o.pose[1], o.pose[2]] for o in outs])

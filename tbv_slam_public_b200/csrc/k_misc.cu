@@ -1,0 +1,120 @@
+// k_misc.cu — context lifecycle, error string, pinned-memory helpers, 90-degree rotation of range-major scans.
+#include <mutex>
+
+#include "tbv_common.cuh"
+
+namespace tbv {
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+// dst(i, j) = src(j, W-1-i): cv::rotate(ROTATE_90_COUNTERCLOCKWISE) as used at radar_driver.cpp:80-84.
+// 32x32 shared-memory tile transpose so both the read and the write are coalesced.
+__global__ void k_rotate90ccw(const uint8_t* __restrict__ src, int H, int W, uint8_t* __restrict__ dst) {
+  __shared__ uint8_t tile[32][33];
+  const int j0 = blockIdx.y * 32, c0 = blockIdx.x * 32;  // src rows j, src cols c
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int j = j0 + dy, c = c0 + threadIdx.x;
+    if (j < H && c < W) tile[dy][threadIdx.x] = src[(size_t)j * W + c];
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int c = c0 + dy, j = j0 + threadIdx.x;  // dst row i = W-1-c, dst col j
+    if (j < H && c < W) dst[(size_t)(W - 1 - c) * H + j] = tile[threadIdx.x][dy];
+  }
+}
+}  // namespace tbv
+
+using namespace tbv;
+
+extern "C" {
+
+const char* tbv_last_error(void) { return g_err.c_str(); }
+int tbv_version(void) { return 100; }
+
+tbv_ctx* tbv_create(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s): libtbv_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range [0,%d)", device, n);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  tbv_ctx* ctx = new tbv_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    delete ctx;
+    return nullptr;
+  }
+  return ctx;
+}
+
+void tbv_destroy(tbv_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  FilterState& F = ctx->filt;
+  F.polar.release(); F.row_keys.release(); F.row_cnt.release(); F.cs_table.release(); F.filtered.release(); F.peaks.release();
+  cells_release(ctx);
+  reg_release(ctx);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void* tbv_stream(tbv_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int tbv_synchronize(tbv_ctx* ctx) {
+  TBV_REQUIRE(ctx, "null context");
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TBV_OK;
+}
+
+long long tbv_launch_count(tbv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* tbv_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    set_error("cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void tbv_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int tbv_rotate90ccw(tbv_ctx* ctx, const uint8_t* src, int rows, int cols, uint8_t* dst) {
+  TBV_REQUIRE(ctx && src && dst && rows > 0 && cols > 0, "bad arguments");
+  const size_t n = (size_t)rows * cols;
+  DevBuf<uint8_t> a, b;
+  int rc;
+  if ((rc = a.reserve(n)) || (rc = b.reserve(n))) { a.release(); b.release(); return rc; }
+  cudaError_t e = cudaMemcpyAsync(a.p, src, n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    k_rotate90ccw<<<grid, block, 0, ctx->stream>>>(a.p, rows, cols, b.p);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dst, b.p, n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  a.release(); b.release();
+  if (e != cudaSuccess) { set_error("tbv_rotate90ccw: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  return TBV_OK;
+}
+
+}  // extern "C"

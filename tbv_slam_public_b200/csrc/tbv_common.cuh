@@ -1,0 +1,111 @@
+// tbv_common.cuh — shared host/device plumbing of libtbv_b200.so (context, error handling, small device helpers).
+// Product code: never includes anything from oracle/.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tbv_b200.h"
+
+namespace tbv {
+
+void set_error(const char* fmt, ...);
+
+#define TBV_CUDA(call)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      tbv::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return TBV_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define TBV_REQUIRE(cond, msg)                   \
+  do {                                           \
+    if (!(cond)) {                               \
+      tbv::set_error("invalid argument: %s", msg); \
+      return TBV_ERR_INVALID;                    \
+    }                                            \
+  } while (0)
+
+// growable device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int reserve(size_t count) {
+    if (count <= n) return TBV_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      return TBV_ERR_CUDA;
+    }
+    n = count;
+    return TBV_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// A filtered cloud resident on the device, struct-of-arrays, `cap` entries per scan.
+struct DevCloud {
+  int cap = 0, batch = 0;
+  DevBuf<float> x, y;
+  DevBuf<uint8_t> inten;
+  DevBuf<uint16_t> az, rg;
+  DevBuf<int> count;
+  int reserve(int batch_, int cap_) {
+    batch = batch_;
+    cap = cap_;
+    const size_t n = (size_t)batch_ * cap_;
+    int rc;
+    if ((rc = x.reserve(n))) return rc;
+    if ((rc = y.reserve(n))) return rc;
+    if ((rc = inten.reserve(n))) return rc;
+    if ((rc = az.reserve(n))) return rc;
+    if ((rc = rg.reserve(n))) return rc;
+    return count.reserve(batch_);
+  }
+  void release() { x.release(); y.release(); inten.release(); az.release(); rg.release(); count.release(); }
+};
+
+struct FilterState {  // device-resident result of the last k-strongest call
+  int batch = 0, n_az = 0, n_range = 0, k = 0;
+  DevBuf<uint8_t> polar;       // staging for host-input calls
+  DevBuf<uint32_t> row_keys;   // [batch][n_az][k]  bit31 = peak, bits 16..23 intensity, bits 0..15 range
+  DevBuf<uint16_t> row_cnt;    // [batch][n_az]
+  DevBuf<double2> cs_table;    // [n_az] (cos theta, sin theta) computed on the host with glibc
+  int cs_n_az = 0;
+  DevCloud filtered, peaks;
+};
+
+}  // namespace tbv
+
+struct tbv_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  tbv::FilterState filt;
+  void* cells_scratch = nullptr;  // tbv::CellsScratch (k_cells.cu)
+  void* reg_scratch = nullptr;    // tbv::RegScratch (k_register.cu)
+};
+
+namespace tbv {
+// implemented in k_filter.cu
+int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
+                          const tbv_filter_params* params, int want_peaks);
+int compensate_clouds_dev(tbv_ctx* ctx, DevCloud& cloud, const double* mot_dev /*[batch][3]*/, int ccw);
+void cells_release(tbv_ctx* ctx);
+void reg_release(tbv_ctx* ctx);
+}  // namespace tbv
