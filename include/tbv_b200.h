@@ -119,12 +119,16 @@ typedef struct tbv_odom_params {
   double res;               /* cell radius / voxel leaf */
   double min_keyframe_dist, min_keyframe_rot_deg;
   double downsample_factor;
+  int cell_capacity;        /* cells kept per scan; <= 0 -> 1024 */
+  int sample_capacity;      /* voxel-grid sample points examined per scan; <= 0 -> 4096 */
 } tbv_odom_params;
 
 typedef struct tbv_odom_out {   /* one per sequence per step */
   double pose[3];
   int n_points, n_cells, itrs, reg_ok, is_keyframe, n_keyframes;
   int lm_iterations, num_residuals;
+  int status;               /* TBV_OK, or TBV_ERR_CAPACITY when a per-scan capacity was exceeded (results then unreliable) */
+  int reserved;
   double score;
 } tbv_odom_out;
 

@@ -59,13 +59,13 @@ class OdomParams(C.Structure):
     _fields_ = [("filter", FilterParams), ("reg", RegParams), ("submap_scan_size", C.c_int), ("weight_intensity", C.c_int),
                 ("use_guess", C.c_int), ("compensate", C.c_int), ("radar_ccw", C.c_int), ("use_keyframe", C.c_int),
                 ("res", C.c_double), ("min_keyframe_dist", C.c_double), ("min_keyframe_rot_deg", C.c_double),
-                ("downsample_factor", C.c_double)]
+                ("downsample_factor", C.c_double), ("cell_capacity", C.c_int), ("sample_capacity", C.c_int)]
 
 
 class OdomOut(C.Structure):
     _fields_ = [("pose", C.c_double * 3), ("n_points", C.c_int), ("n_cells", C.c_int), ("itrs", C.c_int), ("reg_ok", C.c_int),
                 ("is_keyframe", C.c_int), ("n_keyframes", C.c_int), ("lm_iterations", C.c_int), ("num_residuals", C.c_int),
-                ("score", C.c_double)]
+                ("status", C.c_int), ("reserved", C.c_int), ("score", C.c_double)]
 
 
 def default_reg_params(**kw) -> RegParams:
@@ -78,7 +78,7 @@ def default_reg_params(**kw) -> RegParams:
 def default_odom_params(**kw) -> OdomParams:
     """BASELINE config 2: CFEAR-3 filter (k=40, z_min=60, r=3), 4 keyframes, P2L, Huber 0.1, weight_opt 4, weight_intensity."""
     p = OdomParams(FilterParams(60.0, 40, 2.5, 0.0438), RegParams(P2L, HUBER, W_COMBINED, 0.1, 1.0, 1.0, 0, 0), 4, 1, 1, 1, 0, 1,
-                   3.0, 1.5, 5.0, 1.0)
+                   3.0, 1.5, 5.0, 1.0, 0, 0)
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -378,3 +378,26 @@ class OdometryKeyframeFuser:
 
 def poses(outs) -> np.ndarray:
     return np.array([[o.pose[0], o.pose[1], o.pose[2]] for o in outs])
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'ed byte buffer (tbv_host_alloc) exposed as a numpy u8 array: the source of pipelined uploads."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = lib().tbv_host_alloc(nbytes)
+        if not self.ptr:
+            raise TbvError(TBV_ERR_CUDA, lib().tbv_last_error().decode())
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().tbv_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,648 @@
+// k_cells.cu — K3: oriented surface points ("cells") from a filtered cloud.
+//
+// Replaces MapPointNormal::MapPointNormal / ComputeNormals (cfear_radarodometry/src/cfear_radarodometry/pointnormal.cpp:65-90,
+// 265-297), cell::cell (:7-36) and cell::ComputeNormal (:37-63), including the PCL VoxelGrid down-sampling and the
+// FLANN radius search they call.  No kd-tree: the voxel grid that produces the sample points doubles as the spatial
+// index (points are counting-sorted by voxel; the neighbours of a sample lie in at most a few contiguous runs of that
+// order).  Kernels, all batched over scans:
+//   C1 bounding box + voxel index per point + voxel histogram        (1 CTA / scan)
+//   C2 exclusive scan over voxels, list of non-empty voxels = samples (1 CTA / scan)
+//   C3 scatter points into voxel order
+//   C4 per sample: order its points by cloud index, float centroid    (1 warp / sample)
+//   C5 per sample: radius neighbours, sort by (d2, index), weighted mean / covariance in neighbour order,
+//      2x2 symmetric eigen-solve, validity, planarity                 (1 warp / sample)
+//   C6 ordered compaction of the valid cells                          (1 CTA / scan)
+// Arithmetic follows the reference operation by operation (float voxel / distance math, double statistics, no FMA
+// contraction: the library is built with -fmad=false).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+#include "tbv_cells.cuh"
+
+namespace tbv {
+
+constexpr int NB_CAP = 1024;      // neighbours sorted in shared memory per sample
+constexpr int C5_WARPS = 4;
+constexpr int C5_CHUNK = 64;
+
+struct GridInfo {
+  int min_bx, min_by, div_x, div_y, n_vox, ok;
+  float inv_leaf;
+};
+
+struct CellsScratch {
+  int batch = 0, cap_pts = 0, vox_cap = 0, max_samples = 0;
+  DevBuf<GridInfo> grid;
+  DevBuf<int> vox_idx, vox_start, vox_fill, sample_vox, sorted_raw, sorted, err;
+  DevBuf<float> cx, cy;
+  DevBuf<double> cand;          // [batch][CELL_FIELDS][max_samples]
+  DevBuf<uint8_t> cand_valid;   // [batch][max_samples]
+  void release() {
+    grid.release(); vox_idx.release(); vox_start.release(); vox_fill.release(); sample_vox.release(); sorted_raw.release();
+    sorted.release(); err.release(); cx.release(); cy.release(); cand.release(); cand_valid.release();
+  }
+};
+
+__device__ __forceinline__ float warp_min(float v) {
+  for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+// ---- C1 -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+c1_grid(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ count, int cap_pts, float leaf, int vox_cap,
+        GridInfo* __restrict__ grid, int* __restrict__ vox_idx, int* __restrict__ vox_cnt /*[batch][vox_cap+1]*/) {
+  __shared__ float s_mn[2][8], s_mx[2][8];
+  __shared__ GridInfo s_g;
+  const int scan = blockIdx.x;
+  const int n = min(count[scan], cap_pts);
+  const float* px = x + (size_t)scan * cap_pts;
+  const float* py = y + (size_t)scan * cap_pts;
+  float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = px[i], b = py[i];
+    mnx = fminf(mnx, a); mxx = fmaxf(mxx, a); mny = fminf(mny, b); mxy = fmaxf(mxy, b);
+  }
+  mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_mn[0][warp] = mnx; s_mn[1][warp] = mny; s_mx[0][warp] = mxx; s_mx[1][warp] = mxy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) {
+      mnx = fminf(mnx, s_mn[0][w]); mny = fminf(mny, s_mn[1][w]); mxx = fmaxf(mxx, s_mx[0][w]); mxy = fmaxf(mxy, s_mx[1][w]);
+    }
+    GridInfo g;
+    const float inv = 1.0f / leaf;  // PCL: inverse_leaf_size_ = 1 / leaf_size_
+    g.inv_leaf = inv;
+    g.ok = 0; g.min_bx = g.min_by = 0; g.div_x = g.div_y = 1; g.n_vox = 0;
+    if (n > 0) {
+      const long long dx = (long long)((mxx - mnx) * inv) + 1, dy = (long long)((mxy - mny) * inv) + 1;
+      g.min_bx = (int)floorf(mnx * inv);
+      g.min_by = (int)floorf(mny * inv);
+      const int max_bx = (int)floorf(mxx * inv), max_by = (int)floorf(mxy * inv);
+      g.div_x = max_bx - g.min_bx + 1;
+      g.div_y = max_by - g.min_by + 1;
+      const long long nv = (long long)g.div_x * (long long)g.div_y;
+      g.n_vox = nv > 0x7fffffffLL ? 0x7fffffff : (int)nv;
+      g.ok = (dx * dy <= 0x7fffffffLL) && (nv <= (long long)vox_cap);
+    }
+    s_g = g;
+    grid[scan] = g;
+  }
+  __syncthreads();
+  const GridInfo g = s_g;
+  if (!g.ok) return;
+  int* vi = vox_idx + (size_t)scan * cap_pts;
+  int* vc = vox_cnt + (size_t)scan * (vox_cap + 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // PCL voxel_grid.hpp: ijk = (int)(floor(p * inverse_leaf_size) - (float)min_b)
+    const int ijk0 = (int)(floorf(px[i] * g.inv_leaf) - (float)g.min_bx);
+    const int ijk1 = (int)(floorf(py[i] * g.inv_leaf) - (float)g.min_by);
+    const int idx = ijk0 + ijk1 * g.div_x;
+    vi[i] = idx;
+    atomicAdd(&vc[idx], 1);
+  }
+}
+
+// ---- C2 -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+c2_scan(const GridInfo* __restrict__ grid, int vox_cap, int max_samples, int* __restrict__ vox_cnt_start /* in: counts, out: starts */,
+        int* __restrict__ sample_vox, int* __restrict__ n_samples, int* __restrict__ err) {
+  __shared__ int s_a[32], s_b[32];
+  const int scan = blockIdx.x;
+  const GridInfo g = grid[scan];
+  if (!g.ok) {
+    if (threadIdx.x == 0) { n_samples[scan] = 0; if (g.n_vox > 0) err[scan] = TBV_ERR_CAPACITY; }
+    return;
+  }
+  int* vc = vox_cnt_start + (size_t)scan * (vox_cap + 1);
+  const int nv = g.n_vox;
+  const int chunk = (nv + blockDim.x - 1) / blockDim.x;
+  const int b0 = min(nv, (int)threadIdx.x * chunk), b1 = min(nv, b0 + chunk);
+  int sum = 0, ne = 0;
+  for (int v = b0; v < b1; v++) { const int c = vc[v]; sum += c; ne += (c > 0); }
+  // block exclusive scan of (sum, ne)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int is = sum, ie = ne;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int ts = __shfl_up_sync(0xffffffffu, is, d), te = __shfl_up_sync(0xffffffffu, ie, d);
+    if (lane >= d) { is += ts; ie += te; }
+  }
+  if (lane == 31) { s_a[warp] = is; s_b[warp] = ie; }
+  __syncthreads();
+  if (warp == 0) {
+    int a = s_a[lane], b = s_b[lane];
+    int ia = a, ib = b;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, ia, d), tb = __shfl_up_sync(0xffffffffu, ib, d);
+      if (lane >= d) { ia += ta; ib += tb; }
+    }
+    s_a[lane] = ia - a;
+    s_b[lane] = ib - b;
+    if (lane == 31) {
+      n_samples[scan] = min(ib, max_samples);
+      if (ib > max_samples) err[scan] = TBV_ERR_CAPACITY;
+    }
+  }
+  __syncthreads();
+  int off = s_a[warp] + is - sum, soff = s_b[warp] + ie - ne;
+  int* sv = sample_vox + (size_t)scan * max_samples;
+  for (int v = b0; v < b1; v++) {
+    const int c = vc[v];
+    vc[v] = off;
+    off += c;
+    if (c > 0) { if (soff < max_samples) sv[soff] = v; soff++; }
+  }
+  if (b1 == nv && b0 < nv) vc[nv] = off;          // total
+  if (nv == 0 && threadIdx.x == 0) vc[0] = 0;
+}
+
+// ---- C3 -------------------------------------------------------------------------------------------------------
+__global__ void c3_scatter(const GridInfo* __restrict__ grid, const int* __restrict__ count, int cap_pts, int vox_cap,
+                           const int* __restrict__ vox_idx, const int* __restrict__ vox_start, int* __restrict__ vox_fill,
+                           int* __restrict__ sorted_raw) {
+  const int scan = blockIdx.y;
+  if (!grid[scan].ok) return;
+  const int n = min(count[scan], cap_pts);
+  const int* vi = vox_idx + (size_t)scan * cap_pts;
+  const int* vs = vox_start + (size_t)scan * (vox_cap + 1);
+  int* vf = vox_fill + (size_t)scan * vox_cap;
+  int* sr = sorted_raw + (size_t)scan * cap_pts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int v = vi[i];
+    sr[vs[v] + atomicAdd(&vf[v], 1)] = i;
+  }
+}
+
+// ---- C4 -------------------------------------------------------------------------------------------------------
+// One warp per sample: order the voxel's points by cloud index ([DEV-1]: PCL's std::sort leaves the intra-voxel order
+// to libstdc++'s introsort; ascending index is used here and in the oracle's default mode), then accumulate the
+// centroid in float exactly like pcl::CentroidPoint (sum, then divide by (float)n).
+__global__ void __launch_bounds__(128)
+c4_centroids(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, int cap_pts, int vox_cap,
+             const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ sample_vox,
+             const int* __restrict__ vox_start, const int* __restrict__ sorted_raw, int* __restrict__ sorted,
+             float* __restrict__ cx, float* __restrict__ cy) {
+  const int scan = blockIdx.y;
+  if (!grid[scan].ok) return;
+  const int ns = n_samples[scan];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* px = x + (size_t)scan * cap_pts;
+  const float* py = y + (size_t)scan * cap_pts;
+  const int* vs = vox_start + (size_t)scan * (vox_cap + 1);
+  const int* sr = sorted_raw + (size_t)scan * cap_pts;
+  int* so = sorted + (size_t)scan * cap_pts;
+  for (int s = blockIdx.x * 4 + warp; s < ns; s += gridDim.x * 4) {
+    const int v = sample_vox[(size_t)scan * max_samples + s];
+    const int s0 = vs[v], n = vs[v + 1] - s0;
+    for (int e = lane; e < n; e += 32) {
+      const int my = sr[s0 + e];
+      int rank = 0;
+      for (int j = 0; j < n; j++) rank += (sr[s0 + j] < my);
+      so[s0 + rank] = my;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      float sx = 0.f, sy = 0.f;
+      for (int j = 0; j < n; j++) {
+        const int i = so[s0 + j];
+        sx += px[i];
+        sy += py[i];
+      }
+      const float fn = (float)n;
+      cx[(size_t)scan * max_samples + s] = sx / fn;
+      cy[(size_t)scan * max_samples + s] = sy / fn;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- C5 -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double eig_hypot(double x, double y) {  // Eigen 3.3 numext::hypot
+  double ax = fabs(x), ay = fabs(y), p, qp;
+  if (ax > ay) { p = ax; qp = ay / p; } else { p = ay; qp = ax / p; }
+  if (p == 0.0) return 0.0;
+  return p * sqrt(1.0 + qp * qp);
+}
+__device__ __forceinline__ void make_givens(double p, double q, double& c, double& s) {  // Eigen JacobiRotation::makeGivens
+  if (q == 0.0) { c = p < 0.0 ? -1.0 : 1.0; s = 0.0; }
+  else if (p == 0.0) { c = 0.0; s = q < 0.0 ? 1.0 : -1.0; }
+  else if (fabs(p) > fabs(q)) {
+    double t = q / p; double u = sqrt(1.0 + t * t); if (p < 0.0) u = -u;
+    c = 1.0 / u; s = -t * c;
+  } else {
+    double t = p / q; double u = sqrt(1.0 + t * t); if (q < 0.0) u = -u;
+    s = -1.0 / u; c = -t * s;
+  }
+}
+// Eigen 3.3.7 SelfAdjointEigenSolver<Matrix2d>::compute: scale, (trivial) tridiagonalisation, implicit QR with
+// Wilkinson shift, ascending sort.  evec[row][col].
+__device__ void self_adjoint_eig2(double m00, double m10, double m11, double eval[2], double evec[2][2]) {
+  double scale = fmax(fabs(m00), fmax(fabs(m10), fabs(m11)));
+  if (scale == 0.0) scale = 1.0;
+  double d0 = m00 / scale, d1 = m11 / scale, sub = m10 / scale;
+  double Q00 = 1, Q01 = 0, Q10 = 0, Q11 = 1;
+  const double precision = 2.0 * DBL_EPSILON, considerAsZero = DBL_MIN;
+  int iter = 0;
+  while (true) {
+    if (fabs(sub) <= (fabs(d0) + fabs(d1)) * precision || fabs(sub) <= considerAsZero) sub = 0.0;
+    if (sub == 0.0) break;
+    iter++;
+    if (iter > 60) break;
+    const double td = (d0 - d1) * 0.5, e = sub;
+    double mu = d1;
+    if (td == 0.0) mu -= fabs(e);
+    else if (e != 0.0) {
+      const double e2 = e * e;
+      const double h = eig_hypot(td, e);
+      if (e2 == 0.0) mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
+      else mu -= e2 / (td + (td > 0.0 ? h : -h));
+    }
+    const double xx = d0 - mu, z = sub;
+    double c, s;
+    make_givens(xx, z, c, s);
+    const double sdk = s * d0 + c * sub;
+    const double dkp1 = s * sub + c * d1;
+    d0 = c * (c * d0 - s * sub) - s * (c * sub - s * d1);
+    d1 = s * sdk + c * dkp1;
+    sub = c * sdk - s * dkp1;
+    double xi = Q00, yi = Q01;
+    Q00 = c * xi - s * yi; Q01 = s * xi + c * yi;
+    xi = Q10; yi = Q11;
+    Q10 = c * xi - s * yi; Q11 = s * xi + c * yi;
+  }
+  if (d1 < d0) {
+    double t = d0; d0 = d1; d1 = t;
+    t = Q00; Q00 = Q01; Q01 = t;
+    t = Q10; Q10 = Q11; Q11 = t;
+  }
+  eval[0] = d0 * scale; eval[1] = d1 * scale;
+  evec[0][0] = Q00; evec[0][1] = Q01; evec[1][0] = Q10; evec[1][1] = Q11;
+}
+
+__global__ void __launch_bounds__(C5_WARPS * 32)
+c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, int cap_pts, int vox_cap,
+         const float* __restrict__ x, const float* __restrict__ y, const uint8_t* __restrict__ inten_u8, const float* __restrict__ inten_f32,
+         const int* __restrict__ vox_start, const int* __restrict__ sorted, const float* __restrict__ cx, const float* __restrict__ cy,
+         float radius, int weight_intensity, double origin_x, double origin_y,
+         double* __restrict__ cand, uint8_t* __restrict__ cand_valid, int* __restrict__ err) {
+  __shared__ unsigned long long s_keys[C5_WARPS][NB_CAP];
+  __shared__ double s_t[C5_WARPS][4][C5_CHUNK];
+  __shared__ double s_u[C5_WARPS][2];
+  const int scan = blockIdx.y;
+  const GridInfo g = grid[scan];
+  if (!g.ok) return;
+  const int ns = n_samples[scan];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  const float* px = x + (size_t)scan * cap_pts;
+  const float* py = y + (size_t)scan * cap_pts;
+  const uint8_t* pi8 = inten_u8 ? inten_u8 + (size_t)scan * cap_pts : nullptr;
+  const float* pif = inten_f32 ? inten_f32 + (size_t)scan * cap_pts : nullptr;
+  const int* vs = vox_start + (size_t)scan * (vox_cap + 1);
+  const int* so = sorted + (size_t)scan * cap_pts;
+  unsigned long long* keys = s_keys[warp];
+  const float r2 = (float)((double)radius * (double)radius);  // pcl::KdTreeFLANN::radiusSearch: static_cast<float>(radius*radius)
+  const float eps = 1e-3f;
+  double* cnd = cand + (size_t)scan * CELL_FIELDS * max_samples;
+  uint8_t* cv = cand_valid + (size_t)scan * max_samples;
+
+  for (int s = blockIdx.x * C5_WARPS + warp; s < ns; s += gridDim.x * C5_WARPS) {
+    const float qx = cx[(size_t)scan * max_samples + s], qy = cy[(size_t)scan * max_samples + s];
+    // voxel window that certainly contains every point with d2 < r2
+    int ix0 = (int)(floorf((qx - radius - eps) * g.inv_leaf) - (float)g.min_bx);
+    int ix1 = (int)(floorf((qx + radius + eps) * g.inv_leaf) - (float)g.min_bx);
+    int iy0 = (int)(floorf((qy - radius - eps) * g.inv_leaf) - (float)g.min_by);
+    int iy1 = (int)(floorf((qy + radius + eps) * g.inv_leaf) - (float)g.min_by);
+    ix0 = max(ix0, 0); iy0 = max(iy0, 0); ix1 = min(ix1, g.div_x - 1); iy1 = min(iy1, g.div_y - 1);
+    int N = 0;
+    bool overflow = false;
+    for (int iy = iy0; iy <= iy1; iy++) {
+      const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
+      for (int base = a; base < b; base += 32) {
+        const int j = base + lane;
+        bool in = false;
+        unsigned long long key = 0;
+        if (j < b) {
+          const int i = so[j];
+          const float dx = qx - px[i], dy = qy - py[i];
+          float d = dx * dx;        // FLANN L2_Simple: result += diff*diff per dimension (z contributes +0)
+          d = d + dy * dy;
+          in = d < r2;
+          key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+        }
+        const unsigned bal = __ballot_sync(FULL, in);
+        if (in) {
+          const int pos = N + __popc(bal & ((1u << lane) - 1u));
+          if (pos < NB_CAP) keys[pos] = key;
+        }
+        N += __popc(bal);
+      }
+    }
+    if (N > NB_CAP) { overflow = true; }
+    bool valid = false;
+    if (N >= 6 && !overflow) {  // pointnormal.cpp:291
+      // ---- bitonic sort of the keys (ascending (d2, index): FLANN's DistanceIndex order) ---------------------
+      int P = 32;
+      while (P < N) P <<= 1;
+      for (int e = N + lane; e < P; e += 32) keys[e] = ~0ull;
+      __syncwarp();
+      for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+          for (int t = lane; t < (P >> 1); t += 32) {
+            const int lo = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));  // index with bit jj cleared
+            const int hi = lo | jj;
+            const unsigned long long a = keys[lo], b = keys[hi];
+            const bool up = ((lo & kk) == 0);
+            if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+          }
+          __syncwarp();
+        }
+      }
+      // ---- weights, mean, covariance in neighbour order (pointnormal.cpp:13-33) --------------------------------
+      double wsum = 0.0;
+      for (int e = lane; e < N; e += 32) {
+        const int i = (int)(keys[e] & 0xffffffffu);
+        const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
+        wsum += weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0;
+      }
+      for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(FULL, wsum, d);  // integer-valued terms: exact in any order
+      double u0 = 0.0, u1 = 0.0;
+      for (int base = 0; base < N; base += C5_CHUNK) {
+        const int m = min(C5_CHUNK, N - base);
+        for (int e = lane; e < m; e += 32) {
+          const int i = (int)(keys[base + e] & 0xffffffffu);
+          const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
+          const double w = (weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0) / wsum;
+          s_t[warp][0][e] = w * (double)px[i];
+          s_t[warp][1][e] = w * (double)py[i];
+        }
+        __syncwarp();
+        if (lane < 2) {
+          double acc = lane == 0 ? u0 : u1;
+          const double* t = s_t[warp][lane];
+          for (int e = 0; e < m; e++) acc += t[e];
+          if (lane == 0) u0 = acc; else u1 = acc;
+        }
+        __syncwarp();
+      }
+      if (lane == 0) s_u[warp][0] = u0;
+      if (lane == 1) s_u[warp][1] = u1;
+      __syncwarp();
+      u0 = s_u[warp][0]; u1 = s_u[warp][1];
+      double cacc = 0.0;  // lanes 0..3 hold c00, c01, c10, c11
+      for (int base = 0; base < N; base += C5_CHUNK) {
+        const int m = min(C5_CHUNK, N - base);
+        for (int e = lane; e < m; e += 32) {
+          const int i = (int)(keys[base + e] & 0xffffffffu);
+          const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
+          const double w = (weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0) / wsum;
+          const double d0 = (double)px[i] - u0, d1 = (double)py[i] - u1;
+          const double xw0 = w * d0, xw1 = w * d1;
+          s_t[warp][0][e] = d0 * xw0;
+          s_t[warp][1][e] = d0 * xw1;
+          s_t[warp][2][e] = d1 * xw0;
+          s_t[warp][3][e] = d1 * xw1;
+        }
+        __syncwarp();
+        if (lane < 4) {
+          const double* t = s_t[warp][lane];
+          for (int e = 0; e < m; e++) cacc += t[e];
+        }
+        __syncwarp();
+      }
+      const double c00 = __shfl_sync(FULL, cacc, 0), c01 = __shfl_sync(FULL, cacc, 1), c10 = __shfl_sync(FULL, cacc, 2),
+                   c11 = __shfl_sync(FULL, cacc, 3);
+      if (lane == 0) {
+        // ---- cell::ComputeNormal (pointnormal.cpp:37-63) ----------------------------------------------------------
+        double eval[2], evec[2][2];
+        self_adjoint_eig2(c00, c10, c11, eval, evec);
+        double n0 = evec[0][0], n1 = evec[1][0];
+        const double lambda_min = eval[0], lambda_max = eval[1];
+        const double condition_number = fabs(lambda_max / lambda_min);
+        const double determinant = lambda_max * lambda_min;
+        valid = (condition_number <= 10000) && (determinant > 0.00001) && lambda_min > 0 && lambda_max > 0;
+        const double scale = log(1.0 + condition_number / 2);
+        const double pox = origin_x - u0, poy = origin_y - u1;
+        if (n0 * pox + n1 * poy < 0) { n0 = -n0; n1 = -n1; }
+        const size_t st = max_samples;
+        cnd[CF_U0 * st + s] = u0; cnd[CF_U1 * st + s] = u1;
+        cnd[CF_C00 * st + s] = c00; cnd[CF_C01 * st + s] = c01; cnd[CF_C10 * st + s] = c10; cnd[CF_C11 * st + s] = c11;
+        cnd[CF_SCALE * st + s] = scale;
+        cnd[CF_N0 * st + s] = n0; cnd[CF_N1 * st + s] = n1;
+        cnd[CF_O0 * st + s] = evec[0][1]; cnd[CF_O1 * st + s] = evec[1][1];
+        cnd[CF_LMIN * st + s] = lambda_min; cnd[CF_LMAX * st + s] = lambda_max;
+        cnd[CF_SUMI * st + s] = wsum; cnd[CF_AVGI * st + s] = wsum / (double)N;
+        cnd[CF_NS * st + s] = (double)N;
+      }
+    }
+    if (lane == 0) {
+      cv[s] = valid ? 1 : 0;
+      if (overflow) err[scan] = TBV_ERR_CAPACITY;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- C6 -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+c6_compact(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, const double* __restrict__ cand,
+           const uint8_t* __restrict__ cand_valid, double* __restrict__ out, int out_cap, int* __restrict__ out_count, int* __restrict__ err) {
+  __shared__ int s_w[8];
+  __shared__ int s_running;
+  const int scan = blockIdx.x;
+  const int ns = grid[scan].ok ? n_samples[scan] : 0;
+  const double* cnd = cand + (size_t)scan * CELL_FIELDS * max_samples;
+  const uint8_t* cv = cand_valid + (size_t)scan * max_samples;
+  double* o = out + (size_t)scan * CELL_FIELDS * out_cap;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_running = 0;
+  __syncthreads();
+  for (int base = 0; base < ns; base += 256) {
+    const int s = base + threadIdx.x;
+    const bool v = s < ns && cv[s];
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_running;
+    for (int w = 0; w < warp; w++) off += s_w[w];
+    if (v) {
+      const int q = off + __popc(bal & ((1u << lane) - 1u));
+      if (q < out_cap)
+        for (int f = 0; f < CELL_FIELDS; f++) o[(size_t)f * out_cap + q] = cnd[(size_t)f * max_samples + s];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; w++) t += s_w[w];
+      s_running += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out_count[scan] = min(s_running, out_cap);
+    if (s_running > out_cap) err[scan] = TBV_ERR_CAPACITY;
+  }
+}
+
+// AoS <-> field-major conversion kernels
+__global__ void k_cells_aos_to_soa(const double* __restrict__ aos, int n, double* __restrict__ soa, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int f = 0; f < CELL_FIELDS; f++) soa[(size_t)f * cap + i] = aos[(size_t)i * CELL_FIELDS + f];
+}
+__global__ void k_cells_soa_to_aos(const double* __restrict__ soa, int cap, int n, double* __restrict__ aos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int f = 0; f < CELL_FIELDS; f++) aos[(size_t)i * CELL_FIELDS + f] = soa[(size_t)f * cap + i];
+}
+
+// --------------------------------------------------------------------------------------------------------------
+static CellsScratch* scratch(tbv_ctx* ctx) {
+  if (!ctx->cells_scratch) ctx->cells_scratch = new CellsScratch();
+  return (CellsScratch*)ctx->cells_scratch;
+}
+void cells_release(tbv_ctx* ctx) {
+  if (!ctx->cells_scratch) return;
+  CellsScratch* s = (CellsScratch*)ctx->cells_scratch;
+  s->release();
+  delete s;
+  ctx->cells_scratch = nullptr;
+}
+
+int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t* inten_u8, const float* inten_f32, const int* count_dev,
+                    int cap_pts, int batch, const CellsParams& par, int cell_cap, CellStore& out) {
+  TBV_REQUIRE(par.radius > 0.f && par.downsample_factor > 0.0, "radius and downsample_factor must be positive");
+  CellsScratch& S = *scratch(ctx);
+  const float leaf = (float)((double)par.radius / par.downsample_factor);  // pointnormal.cpp:279
+  // voxel grid scratch sized from the largest extent the caller vouches for
+  const double ext = par.max_extent > 0 ? par.max_extent : 400.0;
+  long long side = (long long)(2.0 * ext / leaf) + 4;
+  long long vox_cap_ll = side * side;
+  TBV_REQUIRE(vox_cap_ll <= (1ll << 24), "voxel grid too fine for the given extent (more than 2^24 voxels)");
+  const int vox_cap = (int)vox_cap_ll;
+  const int max_samples = par.max_samples > 0 ? par.max_samples : cell_cap;
+  int rc;
+  if ((rc = S.grid.reserve(batch)) || (rc = S.err.reserve(batch)) || (rc = S.vox_idx.reserve((size_t)batch * cap_pts)) ||
+      (rc = S.vox_start.reserve((size_t)batch * (vox_cap + 1))) || (rc = S.vox_fill.reserve((size_t)batch * vox_cap)) ||
+      (rc = S.sample_vox.reserve((size_t)batch * max_samples)) || (rc = S.sorted_raw.reserve((size_t)batch * cap_pts)) ||
+      (rc = S.sorted.reserve((size_t)batch * cap_pts)) || (rc = S.cx.reserve((size_t)batch * max_samples)) ||
+      (rc = S.cy.reserve((size_t)batch * max_samples)) || (rc = S.cand.reserve((size_t)batch * CELL_FIELDS * max_samples)) ||
+      (rc = S.cand_valid.reserve((size_t)batch * max_samples)))
+    return rc;
+  if ((rc = out.reserve(batch, cell_cap))) return rc;
+  cudaStream_t st = ctx->stream;
+  TBV_CUDA(cudaMemsetAsync(S.vox_start.p, 0, (size_t)batch * (vox_cap + 1) * sizeof(int), st));
+  TBV_CUDA(cudaMemsetAsync(S.vox_fill.p, 0, (size_t)batch * vox_cap * sizeof(int), st));
+  TBV_CUDA(cudaMemsetAsync(S.err.p, 0, (size_t)batch * sizeof(int), st));
+  c1_grid<<<batch, 256, 0, st>>>(x, y, count_dev, cap_pts, leaf, vox_cap, S.grid.p, S.vox_idx.p, S.vox_start.p);
+  c2_scan<<<batch, 1024, 0, st>>>(S.grid.p, vox_cap, max_samples, S.vox_start.p, S.sample_vox.p, out.n_samples.p, S.err.p);
+  {
+    dim3 g((cap_pts + 255) / 256 < 64 ? (cap_pts + 255) / 256 : 64, batch);
+    c3_scatter<<<g, 256, 0, st>>>(S.grid.p, count_dev, cap_pts, vox_cap, S.vox_idx.p, S.vox_start.p, S.vox_fill.p, S.sorted_raw.p);
+  }
+  {
+    const int gx = (max_samples + 3) / 4 < 512 ? (max_samples + 3) / 4 : 512;
+    c4_centroids<<<dim3(gx, batch), 128, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, S.sample_vox.p, S.vox_start.p,
+                                                  S.sorted_raw.p, S.sorted.p, S.cx.p, S.cy.p);
+    const int g5 = (max_samples + C5_WARPS - 1) / C5_WARPS < 512 ? (max_samples + C5_WARPS - 1) / C5_WARPS : 512;
+    c5_cells<<<dim3(g5, batch), C5_WARPS * 32, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, inten_u8, inten_f32,
+                                                        S.vox_start.p, S.sorted.p, S.cx.p, S.cy.p, par.radius, par.weight_intensity,
+                                                        par.origin[0], par.origin[1], S.cand.p, S.cand_valid.p, S.err.p);
+  }
+  c6_compact<<<batch, 256, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, S.cand.p, S.cand_valid.p, out.f64.p, cell_cap, out.count.p, S.err.p);
+  ctx->launches += 6;
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
+}
+
+int cells_errors(tbv_ctx* ctx, int batch, std::vector<int>& err) {
+  CellsScratch& S = *scratch(ctx);
+  err.resize(batch);
+  TBV_CUDA(cudaMemcpyAsync(err.data(), S.err.p, batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TBV_OK;
+}
+const int* cells_err_dev(tbv_ctx* ctx) { return scratch(ctx)->err.p; }
+
+int cells_upload(tbv_ctx* ctx, const tbv_cell* cells, int n, double* set_dev, int cap) {
+  if (n <= 0) return TBV_OK;
+  TBV_REQUIRE(n <= cap, "cell set larger than its device capacity");
+  double* tmp = nullptr;
+  TBV_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * sizeof(tbv_cell), ctx->stream));
+  TBV_CUDA(cudaMemcpyAsync(tmp, cells, (size_t)n * sizeof(tbv_cell), cudaMemcpyHostToDevice, ctx->stream));
+  k_cells_aos_to_soa<<<(n + 127) / 128, 128, 0, ctx->stream>>>(tmp, n, set_dev, cap);
+  ctx->launches++;
+  TBV_CUDA(cudaFreeAsync(tmp, ctx->stream));
+  return TBV_OK;
+}
+int cells_download(tbv_ctx* ctx, const double* set_dev, int cap, int n, tbv_cell* cells) {
+  if (n <= 0) return TBV_OK;
+  double* tmp = nullptr;
+  TBV_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * sizeof(tbv_cell), ctx->stream));
+  k_cells_soa_to_aos<<<(n + 127) / 128, 128, 0, ctx->stream>>>(set_dev, cap, n, tmp);
+  ctx->launches++;
+  TBV_CUDA(cudaMemcpyAsync(cells, tmp, (size_t)n * sizeof(tbv_cell), cudaMemcpyDeviceToHost, ctx->stream));
+  TBV_CUDA(cudaFreeAsync(tmp, ctx->stream));
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TBV_OK;
+}
+
+}  // namespace tbv
+
+using namespace tbv;
+
+extern "C" int tbv_build_cells(tbv_ctx* ctx, const float* x, const float* y, const float* intensity, int n, float radius,
+                               double downsample_factor, int weight_intensity, const double origin[2], tbv_cell* cells, int cell_capacity,
+                               int* n_cells, int* n_samples) {
+  TBV_REQUIRE(ctx && x && y && intensity && origin && cells && n_cells, "null pointer");
+  TBV_REQUIRE(n >= 0 && cell_capacity > 0, "bad sizes");
+  *n_cells = 0;
+  if (n_samples) *n_samples = 0;
+  if (n == 0) return TBV_OK;  // reference: exit(0) on an empty cloud (pointnormal.cpp:72-75); here: no cells
+  // extent from the data (host side: the points are host-resident anyway)
+  double ext = 1.0;
+  for (int i = 0; i < n; i++) {
+    ext = std::max(ext, (double)std::fabs(x[i]));
+    ext = std::max(ext, (double)std::fabs(y[i]));
+  }
+  DevBuf<float> dx, dy, di;
+  DevBuf<int> dc;
+  int rc;
+  auto cleanup = [&]() { dx.release(); dy.release(); di.release(); dc.release(); };
+  if ((rc = dx.reserve(n)) || (rc = dy.reserve(n)) || (rc = di.reserve(n)) || (rc = dc.reserve(1))) { cleanup(); return rc; }
+  cudaStream_t st = ctx->stream;
+  cudaMemcpyAsync(dx.p, x, n * sizeof(float), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dy.p, y, n * sizeof(float), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(di.p, intensity, n * sizeof(float), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dc.p, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+  CellsParams par;
+  par.radius = radius; par.downsample_factor = downsample_factor; par.weight_intensity = weight_intensity;
+  par.origin[0] = origin[0]; par.origin[1] = origin[1]; par.max_extent = ext + 1.0; par.max_samples = 0;
+  CellStore store;
+  // the number of samples is bounded by the number of points; candidates need that much room
+  const int work_cap = n;
+  rc = cells_build_dev(ctx, dx.p, dy.p, nullptr, di.p, dc.p, n, 1, par, work_cap, store);
+  if (rc) { cleanup(); store.release(); return rc; }
+  int h_cnt = 0, h_ns = 0;
+  std::vector<int> err;
+  cudaMemcpyAsync(&h_cnt, store.count.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(&h_ns, store.n_samples.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+  rc = cells_errors(ctx, 1, err);
+  if (rc) { cleanup(); store.release(); return rc; }
+  if (err[0]) { cleanup(); store.release(); set_error("tbv_build_cells: neighbourhood or grid capacity exceeded"); return TBV_ERR_CAPACITY; }
+  *n_cells = h_cnt;
+  if (n_samples) *n_samples = h_ns;
+  const int ncopy = h_cnt < cell_capacity ? h_cnt : cell_capacity;
+  rc = cells_download(ctx, store.set_ptr(0), store.cap, ncopy, cells);
+  cleanup();
+  store.release();
+  if (rc) return rc;
+  if (h_cnt > cell_capacity) { set_error("cell_capacity %d < %d cells", cell_capacity, h_cnt); return TBV_ERR_CAPACITY; }
+  return TBV_OK;
+}

@@ -1,0 +1,432 @@
+// k_odom.cu — the odometry pipeline: radarDriver::Process + OdometryKeyframeFuser::processFrame for n_seq independent
+// sequences advanced in lock-step, all state resident on the device.
+//
+// Replaces (per sequence, per frame) radarDriver::Process (cfear_radarodometry/src/cfear_radarodometry/radar_driver.cpp:48-73)
+// and OdometryKeyframeFuser::processFrame / KeyFrameBasedFuse / AccelerationVelocitySanityCheck / FormatScans /
+// AddToReference (cfear_radarodometry/src/cfear_radarodometry/odometrykeyframefuser.cpp:62-94, 143-259, 470-494).
+//
+// One step = K1/K2 (k-strongest, clouds) -> compensation with the previous frame-to-frame motion -> K3 (cells) -> problem
+// setup (Tguess = Tprev * Tmot, keyframe window) -> K4/K5 (registration) -> fuser update (sanity check, keyframe policy,
+// window rotation).  Nothing returns to the host between the stages; the host only uploads the scans and reads back one
+// tbv_odom_out per sequence.  Frame t of a sequence needs the pose of frame t-1, so the parallelism is ACROSS sequences
+// (the reference's own scaling model: one worker process per sequence).
+#include <cmath>
+
+#include "tbv_reg.cuh"
+
+namespace tbv {
+
+constexpr int MAX_KF = 16;  // largest supported submap_scan_size on the device path
+
+struct AffD {
+  double r00, r01, r10, r11, tx, ty;
+};
+__device__ __forceinline__ AffD aff_identity() { return AffD{1, 0, 0, 1, 0, 0}; }
+__device__ __forceinline__ AffD aff_from_vec(double x, double y, double th) {
+  const double c = cos(th), s = sin(th);
+  return AffD{c, -s, s, c, x, y};
+}
+__device__ __forceinline__ AffD aff_mul(const AffD& A, const AffD& B) {
+  AffD C;
+  C.r00 = A.r00 * B.r00 + A.r01 * B.r10;
+  C.r01 = A.r00 * B.r01 + A.r01 * B.r11;
+  C.r10 = A.r10 * B.r00 + A.r11 * B.r10;
+  C.r11 = A.r10 * B.r01 + A.r11 * B.r11;
+  C.tx = (A.r00 * B.tx + A.r01 * B.ty) + A.tx;
+  C.ty = (A.r10 * B.tx + A.r11 * B.ty) + A.ty;
+  return C;
+}
+__device__ __forceinline__ AffD aff_inv(const AffD& A) {
+  AffD I;
+  const double det = A.r00 * A.r11 - A.r01 * A.r10;
+  const double invdet = 1.0 / det;
+  I.r00 = A.r11 * invdet;
+  I.r01 = -A.r01 * invdet;
+  I.r10 = -A.r10 * invdet;
+  I.r11 = A.r00 * invdet;
+  I.tx = -(I.r00 * A.tx + I.r01 * A.ty);
+  I.ty = -(I.r10 * A.tx + I.r11 * A.ty);
+  return I;
+}
+__device__ __forceinline__ void aff_to_vec(const AffD& T, double v[3]) {  // utils.cpp:115-122
+  v[0] = T.tx; v[1] = T.ty; v[2] = atan2(T.r10, T.r11);
+}
+
+struct SeqState {
+  AffD T_prev, Tmot, Tcurrent, Tguess;
+  AffD kf_pose[MAX_KF];
+  int kf_slot[MAX_KF];  // store slot of keyframe i (0 = oldest)
+  int n_kf;
+  int frame;
+};
+
+struct OdomDevParams {
+  int K;  // submap_scan_size
+  int use_guess, use_keyframe;
+  double min_keyframe_dist, min_keyframe_rot_rad;
+};
+
+__global__ void k_odom_reset(SeqState* st, int n_seq) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seq) return;
+  SeqState z;
+  z.T_prev = z.Tmot = z.Tcurrent = z.Tguess = aff_identity();
+  for (int i = 0; i < MAX_KF; i++) { z.kf_pose[i] = aff_identity(); z.kf_slot[i] = i; }
+  z.n_kf = 0;
+  z.frame = 0;
+  st[s] = z;
+}
+
+// motion vector for Compensate: Affine3dToVectorXYeZ(TprevMot) (utils.cpp:109-113)
+__global__ void k_odom_motion(const SeqState* __restrict__ st, int n_seq, double* __restrict__ mot) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seq) return;
+  double v[3];
+  aff_to_vec(st[s].Tmot, v);
+  mot[3 * s + 0] = v[0]; mot[3 * s + 1] = v[1]; mot[3 * s + 2] = v[2];
+}
+
+// FormatScans (:478-494) + Tguess (:164-168) -> registration problems
+__global__ void k_odom_problems(SeqState* __restrict__ st, int n_seq, OdomDevParams P, RegProblem* __restrict__ problems,
+                                int* __restrict__ fixed_set, double* __restrict__ fixed_pose) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seq) return;
+  SeqState& S = st[s];
+  S.Tguess = P.use_guess ? aff_mul(S.T_prev, S.Tmot) : S.T_prev;
+  RegProblem pr;
+  pr.n_fixed = S.n_kf;
+  pr.fixed_first = s * P.K;
+  pr.src_set = s * (P.K + 1) + P.K;
+  pr.active = S.n_kf > 0 ? 1 : 0;
+  aff_to_vec(S.Tguess, pr.src_pose);
+  for (int i = 0; i < S.n_kf; i++) {
+    fixed_set[s * P.K + i] = s * (P.K + 1) + S.kf_slot[i];
+    double v[3];
+    aff_to_vec(S.kf_pose[i], v);
+    fixed_pose[(size_t)(s * P.K + i) * 3 + 0] = v[0];
+    fixed_pose[(size_t)(s * P.K + i) * 3 + 1] = v[1];
+    fixed_pose[(size_t)(s * P.K + i) * 3 + 2] = v[2];
+  }
+  problems[s] = pr;
+}
+
+// processFrame after Register (:186-249): one CTA per sequence (the CTA also copies the cells of a new keyframe)
+__global__ void __launch_bounds__(256)
+k_odom_update(SeqState* __restrict__ st, OdomDevParams P, const RegResult* __restrict__ results, const int* __restrict__ n_points,
+              const double* __restrict__ cur_cells, const int* __restrict__ cur_count, int cell_cap, double* __restrict__ kf_cells,
+              int* __restrict__ kf_count, const int* __restrict__ cells_err, tbv_odom_out* __restrict__ outs) {
+  __shared__ int s_fuse_slot;
+  const int s = blockIdx.x;
+  if (threadIdx.x == 0) {
+    SeqState& S = st[s];
+    const RegResult r = results[s];
+    tbv_odom_out o;
+    memset(&o, 0, sizeof(o));
+    int fuse_slot = -1;
+    if (S.n_kf == 0) {  // first frame: AddToReference (:470-476), pose stays identity
+      S.kf_pose[0] = aff_identity();
+      S.kf_slot[0] = 0;
+      S.n_kf = 1;
+      fuse_slot = 0;
+      o.reg_ok = 1;
+      o.is_keyframe = 1;
+    } else {
+      S.Tcurrent = r.pose_updated ? aff_from_vec(r.pose[0], r.pose[1], r.pose[2]) : S.Tguess;
+      const AffD Tmot_current = aff_mul(aff_inv(S.T_prev), S.Tcurrent);
+      {  // AccelerationVelocitySanityCheck (:76-94): Tsensor = 0.25 s, limits 200 m/s, 200 m/s^2
+        const double dt = 0.25, vel_limit = 200, acc_limit = 200;
+        const double vx = Tmot_current.tx / dt, vy = Tmot_current.ty / dt;
+        const double vel = sqrt(vx * vx + vy * vy);
+        const double ax = (Tmot_current.tx - S.Tmot.tx) / (dt * dt), ay = (Tmot_current.ty - S.Tmot.ty) / (dt * dt);
+        const double acc = sqrt(ax * ax + ay * ay);
+        if (acc > acc_limit || vel > vel_limit) S.Tcurrent = S.Tguess;
+      }
+      S.Tmot = aff_mul(aff_inv(S.T_prev), S.Tcurrent);
+      const AffD Tkeydiff = aff_mul(aff_inv(S.kf_pose[S.n_kf - 1]), S.Tcurrent);
+      bool fuse = true;
+      if (P.use_keyframe) {  // KeyFrameBasedFuse (:62-73)
+        const double yaw = atan2(Tkeydiff.r10, Tkeydiff.r11);
+        const double tnorm = sqrt(Tkeydiff.tx * Tkeydiff.tx + Tkeydiff.ty * Tkeydiff.ty);
+        fuse = tnorm > P.min_keyframe_dist || fabs(yaw) > P.min_keyframe_rot_rad;
+      }
+      if (fuse) {
+        if (S.n_kf < P.K) {
+          fuse_slot = S.kf_slot[S.n_kf];  // unused slot (kf_slot is a permutation of 0..K-1)
+          S.kf_pose[S.n_kf] = S.Tcurrent;
+          S.n_kf++;
+        } else {  // push_back + erase(begin): the oldest keyframe's slot is recycled
+          fuse_slot = S.kf_slot[0];
+          for (int i = 0; i + 1 < P.K; i++) { S.kf_slot[i] = S.kf_slot[i + 1]; S.kf_pose[i] = S.kf_pose[i + 1]; }
+          S.kf_slot[P.K - 1] = fuse_slot;
+          S.kf_pose[P.K - 1] = S.Tcurrent;
+        }
+        o.is_keyframe = 1;
+      }
+      S.T_prev = S.Tcurrent;
+      o.reg_ok = r.success;
+      o.itrs = r.itrs;
+      o.lm_iterations = r.lm_iterations;
+      o.num_residuals = r.num_residuals;
+      o.score = r.score;
+    }
+    S.frame++;
+    aff_to_vec(S.Tcurrent, o.pose);
+    o.n_points = n_points[s];
+    o.n_cells = cur_count[s];
+    o.n_keyframes = S.n_kf;
+    o.status = cells_err[s];
+    outs[s] = o;
+    s_fuse_slot = fuse_slot;
+  }
+  __syncthreads();
+  const int slot = s_fuse_slot;
+  if (slot < 0) return;
+  const int n = min(cur_count[s], cell_cap);
+  const double* src = cur_cells + (size_t)s * CELL_FIELDS * cell_cap;
+  double* dst = kf_cells + ((size_t)s * P.K + slot) * CELL_FIELDS * cell_cap;
+  for (int f = 0; f < CELL_FIELDS; f++)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[(size_t)f * cell_cap + i] = src[(size_t)f * cell_cap + i];
+  if (threadIdx.x == 0) kf_count[s * P.K + slot] = n;
+}
+
+}  // namespace tbv
+
+using namespace tbv;
+
+struct tbv_odom {
+  tbv_ctx* ctx = nullptr;
+  int n_seq = 0, n_az = 0, n_range = 0, K = 0, cell_cap = 0, sample_cap = 0;
+  tbv_odom_params par;
+  OdomDevParams dpar;
+  RegParamsDev rpar;
+  CellsParams cpar;
+  DevBuf<SeqState> state;
+  DevBuf<double> mot, fixed_pose;
+  DevBuf<RegProblem> problems;
+  DevBuf<int> fixed_set;
+  DevBuf<RegResult> results;
+  DevBuf<SetView> views;
+  DevBuf<tbv_odom_out> outs_dev;
+  CellStore cur, kf;
+  // host-input path: double-buffered uploads on a copy stream
+  DevBuf<uint8_t> polar[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t uploaded[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+  tbv_odom_out* outs_host[2] = {nullptr, nullptr};  // pinned
+  int n_submitted = 0, n_collected = 0;
+};
+
+static void odom_free(tbv_odom* od) {
+  if (!od) return;
+  cudaSetDevice(od->ctx->device);
+  cudaStreamSynchronize(od->ctx->stream);
+  if (od->copy_stream) cudaStreamSynchronize(od->copy_stream);
+  od->state.release(); od->mot.release(); od->fixed_pose.release(); od->problems.release(); od->fixed_set.release();
+  od->results.release(); od->views.release(); od->outs_dev.release(); od->cur.release(); od->kf.release();
+  for (int i = 0; i < 2; i++) {
+    od->polar[i].release();
+    if (od->uploaded[i]) cudaEventDestroy(od->uploaded[i]);
+    if (od->consumed[i]) cudaEventDestroy(od->consumed[i]);
+    if (od->done[i]) cudaEventDestroy(od->done[i]);
+    if (od->outs_host[i]) cudaFreeHost(od->outs_host[i]);
+  }
+  if (od->copy_stream) cudaStreamDestroy(od->copy_stream);
+  delete od;
+}
+
+static int odom_init(tbv_odom* od) {
+  tbv_ctx* ctx = od->ctx;
+  const int n_seq = od->n_seq, K = od->K;
+  int rc;
+  if ((rc = od->state.reserve(n_seq)) || (rc = od->mot.reserve((size_t)n_seq * 3)) || (rc = od->fixed_pose.reserve((size_t)n_seq * K * 3)) ||
+      (rc = od->problems.reserve(n_seq)) || (rc = od->fixed_set.reserve((size_t)n_seq * K)) || (rc = od->results.reserve(n_seq)) ||
+      (rc = od->views.reserve((size_t)n_seq * (K + 1))) || (rc = od->outs_dev.reserve(n_seq)) || (rc = od->cur.reserve(n_seq, od->cell_cap)) ||
+      (rc = od->kf.reserve(n_seq * K, od->cell_cap)))
+    return rc;
+  TBV_CUDA(cudaMemsetAsync(od->kf.count.p, 0, (size_t)n_seq * K * sizeof(int), ctx->stream));
+  TBV_CUDA(cudaMemsetAsync(od->cur.count.p, 0, (size_t)n_seq * sizeof(int), ctx->stream));
+  TBV_CUDA(cudaMemsetAsync(od->fixed_set.p, 0, (size_t)n_seq * K * sizeof(int), ctx->stream));
+  TBV_CUDA(cudaMemsetAsync(od->fixed_pose.p, 0, (size_t)n_seq * K * 3 * sizeof(double), ctx->stream));
+  std::vector<SetView> hv((size_t)n_seq * (K + 1));
+  for (int s = 0; s < n_seq; s++) {
+    for (int i = 0; i < K; i++) hv[(size_t)s * (K + 1) + i] = SetView{od->kf.set_ptr(s * K + i), od->cell_cap, od->kf.count.p + s * K + i, 0};
+    hv[(size_t)s * (K + 1) + K] = SetView{od->cur.set_ptr(s), od->cell_cap, od->cur.count.p + s, 0};
+  }
+  TBV_CUDA(cudaMemcpyAsync(od->views.p, hv.data(), hv.size() * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
+  k_odom_reset<<<(n_seq + 127) / 128, 128, 0, ctx->stream>>>(od->state.p, n_seq);
+  ctx->launches++;
+  TBV_CUDA(cudaGetLastError());
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TBV_OK;
+}
+
+// enqueue one step on ctx->stream; scans are on the device
+static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
+  tbv_ctx* ctx = od->ctx;
+  const int n_seq = od->n_seq;
+  cudaStream_t st = ctx->stream;
+  int rc = filter_kstrongest_dev(ctx, polar_dev, od->n_az, od->n_range, (size_t)od->n_range, n_seq, &od->par.filter, 1);
+  if (rc) return rc;
+  FilterState& F = ctx->filt;
+  if (od->par.compensate) {
+    k_odom_motion<<<(n_seq + 127) / 128, 128, 0, st>>>(od->state.p, n_seq, od->mot.p);
+    ctx->launches++;
+    if ((rc = compensate_clouds_dev(ctx, F.filtered, od->mot.p, od->par.radar_ccw))) return rc;
+    if ((rc = compensate_clouds_dev(ctx, F.peaks, od->mot.p, od->par.radar_ccw))) return rc;
+  }
+  if ((rc = cells_build_dev(ctx, F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, nullptr, F.filtered.count.p, F.filtered.cap, n_seq, od->cpar,
+                            od->cell_cap, od->cur)))
+    return rc;
+  k_odom_problems<<<(n_seq + 127) / 128, 128, 0, st>>>(od->state.p, n_seq, od->dpar, od->problems.p, od->fixed_set.p, od->fixed_pose.p);
+  ctx->launches++;
+  if ((rc = register_launch(ctx, REG_MODE_REGISTER, 0, od->views.p, od->problems.p, od->fixed_set.p, od->fixed_pose.p, n_seq, od->K, od->cell_cap,
+                            od->cell_cap, od->rpar, od->results.p, nullptr, false)))
+    return rc;
+  k_odom_update<<<n_seq, 256, 0, st>>>(od->state.p, od->dpar, od->results.p, F.filtered.count.p, od->cur.f64.p, od->cur.count.p, od->cell_cap,
+                                       od->kf.f64.p, od->kf.count.p, cells_err_dev(ctx), od->outs_dev.p);
+  ctx->launches++;
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
+}
+
+extern "C" {
+
+tbv_odom* tbv_odom_create(tbv_ctx* ctx, int n_seq, int n_az, int n_range, const tbv_odom_params* params) {
+  if (!ctx || !params || n_seq <= 0 || n_az <= 0 || n_range <= 0) { set_error("tbv_odom_create: bad arguments"); return nullptr; }
+  if (params->submap_scan_size < 1 || params->submap_scan_size > MAX_KF) { set_error("submap_scan_size must be in [1,%d]", MAX_KF); return nullptr; }
+  if (!(params->res > 0) || !(params->downsample_factor > 0)) { set_error("res and downsample_factor must be positive"); return nullptr; }
+  cudaSetDevice(ctx->device);
+  tbv_odom* od = new tbv_odom();
+  od->ctx = ctx; od->n_seq = n_seq; od->n_az = n_az; od->n_range = n_range; od->par = *params;
+  od->K = params->submap_scan_size;
+  od->cell_cap = params->cell_capacity > 0 ? params->cell_capacity : 1024;
+  od->sample_cap = params->sample_capacity > 0 ? params->sample_capacity : 4096;
+  od->dpar.K = od->K; od->dpar.use_guess = params->use_guess; od->dpar.use_keyframe = params->use_keyframe;
+  od->dpar.min_keyframe_dist = params->min_keyframe_dist;
+  od->dpar.min_keyframe_rot_rad = params->min_keyframe_rot_deg * M_PI / 180.0;  // odometrykeyframefuser.cpp:69
+  od->rpar = to_dev(params->reg);
+  od->cpar.radius = (float)params->res;  // MapPointNormal(cloud, par.res, ...) takes float radius (pointnormal.h:118)
+  od->cpar.downsample_factor = params->downsample_factor;
+  od->cpar.weight_intensity = params->weight_intensity;
+  od->cpar.origin[0] = od->cpar.origin[1] = 0.0;
+  od->cpar.max_extent = (double)n_range * (double)params->filter.range_res * 1.05 + 8.0;  // scan radius + compensation margin
+  od->cpar.max_samples = od->sample_cap;
+  if (odom_init(od) != TBV_OK) { odom_free(od); return nullptr; }
+  return od;
+}
+
+void tbv_odom_destroy(tbv_odom* od) { odom_free(od); }
+
+int tbv_odom_reset(tbv_odom* od) {
+  TBV_REQUIRE(od, "null handle");
+  tbv_ctx* ctx = od->ctx;
+  cudaSetDevice(ctx->device);
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (od->copy_stream) TBV_CUDA(cudaStreamSynchronize(od->copy_stream));
+  od->n_submitted = od->n_collected = 0;
+  TBV_CUDA(cudaMemsetAsync(od->kf.count.p, 0, (size_t)od->n_seq * od->K * sizeof(int), ctx->stream));
+  k_odom_reset<<<(od->n_seq + 127) / 128, 128, 0, ctx->stream>>>(od->state.p, od->n_seq);
+  ctx->launches++;
+  TBV_CUDA(cudaGetLastError());
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TBV_OK;
+}
+
+int tbv_odom_step_dev(tbv_odom* od, const uint8_t* polar_dev) {
+  TBV_REQUIRE(od && polar_dev, "null pointer");
+  cudaSetDevice(od->ctx->device);
+  return odom_enqueue(od, polar_dev);
+}
+
+int tbv_odom_fetch(tbv_odom* od, tbv_odom_out* out) {
+  TBV_REQUIRE(od && out, "null pointer");
+  TBV_CUDA(cudaMemcpyAsync(out, od->outs_dev.p, (size_t)od->n_seq * sizeof(tbv_odom_out), cudaMemcpyDeviceToHost, od->ctx->stream));
+  TBV_CUDA(cudaStreamSynchronize(od->ctx->stream));
+  return TBV_OK;
+}
+
+static int odom_pipeline_init(tbv_odom* od) {
+  if (od->copy_stream) return TBV_OK;
+  TBV_CUDA(cudaStreamCreateWithFlags(&od->copy_stream, cudaStreamNonBlocking));
+  const size_t bytes = (size_t)od->n_seq * od->n_az * od->n_range;
+  for (int i = 0; i < 2; i++) {
+    int rc = od->polar[i].reserve(bytes);
+    if (rc) return rc;
+    TBV_CUDA(cudaEventCreateWithFlags(&od->uploaded[i], cudaEventDisableTiming));
+    TBV_CUDA(cudaEventCreateWithFlags(&od->consumed[i], cudaEventDisableTiming));
+    TBV_CUDA(cudaEventCreateWithFlags(&od->done[i], cudaEventDisableTiming));
+    TBV_CUDA(cudaHostAlloc((void**)&od->outs_host[i], (size_t)od->n_seq * sizeof(tbv_odom_out), cudaHostAllocDefault));
+  }
+  return TBV_OK;
+}
+
+int tbv_odom_submit(tbv_odom* od, const uint8_t* polar_host) {
+  TBV_REQUIRE(od && polar_host, "null pointer");
+  TBV_REQUIRE(od->n_submitted - od->n_collected < 2, "two steps are already in flight: call tbv_odom_collect first");
+  cudaSetDevice(od->ctx->device);
+  int rc = odom_pipeline_init(od);
+  if (rc) return rc;
+  const int b = od->n_submitted & 1;
+  const size_t bytes = (size_t)od->n_seq * od->n_az * od->n_range;
+  // the buffer may still be read by the step submitted two calls ago
+  if (od->n_submitted >= 2) TBV_CUDA(cudaStreamWaitEvent(od->copy_stream, od->consumed[b], 0));
+  TBV_CUDA(cudaMemcpyAsync(od->polar[b].p, polar_host, bytes, cudaMemcpyHostToDevice, od->copy_stream));
+  TBV_CUDA(cudaEventRecord(od->uploaded[b], od->copy_stream));
+  TBV_CUDA(cudaStreamWaitEvent(od->ctx->stream, od->uploaded[b], 0));
+  rc = odom_enqueue(od, od->polar[b].p);
+  if (rc) return rc;
+  TBV_CUDA(cudaEventRecord(od->consumed[b], od->ctx->stream));
+  TBV_CUDA(cudaMemcpyAsync(od->outs_host[b], od->outs_dev.p, (size_t)od->n_seq * sizeof(tbv_odom_out), cudaMemcpyDeviceToHost, od->ctx->stream));
+  TBV_CUDA(cudaEventRecord(od->done[b], od->ctx->stream));
+  od->n_submitted++;
+  return TBV_OK;
+}
+
+int tbv_odom_collect(tbv_odom* od, tbv_odom_out* out) {
+  TBV_REQUIRE(od && out, "null pointer");
+  TBV_REQUIRE(od->n_collected < od->n_submitted, "nothing in flight");
+  const int b = od->n_collected & 1;
+  TBV_CUDA(cudaEventSynchronize(od->done[b]));
+  memcpy(out, od->outs_host[b], (size_t)od->n_seq * sizeof(tbv_odom_out));
+  od->n_collected++;
+  return TBV_OK;
+}
+
+int tbv_odom_step(tbv_odom* od, const uint8_t* polar_host, tbv_odom_out* out) {
+  TBV_REQUIRE(od && polar_host && out, "null pointer");
+  TBV_REQUIRE(od->n_submitted == od->n_collected, "steps are in flight: collect them before a synchronous step");
+  int rc = tbv_odom_submit(od, polar_host);
+  if (rc) return rc;
+  return tbv_odom_collect(od, out);
+}
+
+int tbv_odom_cells(tbv_odom* od, int seq, int keyframe, tbv_cell* cells, int capacity, int* n_cells, double pose[3]) {
+  TBV_REQUIRE(od && cells && n_cells && seq >= 0 && seq < od->n_seq && capacity > 0, "bad arguments");
+  tbv_ctx* ctx = od->ctx;
+  cudaSetDevice(ctx->device);
+  SeqState hs;
+  TBV_CUDA(cudaMemcpyAsync(&hs, od->state.p + seq, sizeof(SeqState), cudaMemcpyDeviceToHost, ctx->stream));
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  const double* set;
+  const int* cnt_dev;
+  AffD T;
+  if (keyframe < 0) {
+    set = od->cur.set_ptr(seq); cnt_dev = od->cur.count.p + seq; T = hs.Tcurrent;
+  } else {
+    TBV_REQUIRE(keyframe < hs.n_kf, "keyframe index outside the window");
+    const int slot = hs.kf_slot[keyframe];
+    set = od->kf.set_ptr(seq * od->K + slot); cnt_dev = od->kf.count.p + seq * od->K + slot; T = hs.kf_pose[keyframe];
+  }
+  int n = 0;
+  TBV_CUDA(cudaMemcpyAsync(&n, cnt_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_cells = n;
+  if (pose) { pose[0] = T.tx; pose[1] = T.ty; pose[2] = std::atan2(T.r10, T.r11); }
+  const int ncopy = n < capacity ? n : capacity;
+  int rc = cells_download(ctx, set, od->cell_cap, ncopy, cells);
+  if (rc) return rc;
+  if (n > capacity) { set_error("capacity %d < %d cells", capacity, n); return TBV_ERR_CAPACITY; }
+  return TBV_OK;
+}
+
+}  // extern "C"

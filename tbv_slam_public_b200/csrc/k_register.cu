@@ -1,0 +1,982 @@
+// k_register.cu — K4 (correspondences + robustified cost / J^T J / J^T r) and K5 (association loop + Ceres-style
+// Levenberg-Marquardt), one CTA per registration problem, everything on the device.
+//
+// Replaces n_scan_normal_reg::{Register, GetCost, AddScanPairCost, BuildOptimizationProblem, SolveOptimizationProblem}
+// (cfear_radarodometry/src/cfear_radarodometry/n_scan_normal.cpp:82-211, 213-324, 342-389, 441-450), the cost functors
+// P2LEfficientCost / P2PEfficientCost / P2DEfficientCost (include/cfear_radarodometry/n_scan_normal.h:180-255, 330-361),
+// Registration::{Weights, GetWeight, GetLoss} (registration.h:88-101, registration.cpp:67-96), MapPointNormal::GetClosestIdx
+// (pointnormal.cpp:238-254) and the ceres::Solve call (trust region / Levenberg-Marquardt, Ceres 2.1.0 defaults).
+//
+// Design
+//   * a "problem" = up to max_fixed fixed cell sets (keyframes) + one moving set; the CTA keeps the whole outer
+//     association loop and all LM iterations on chip: no host round trip per iteration, thousands of problems per launch
+//     (odometry: one per sequence; loop closure: one per candidate);
+//   * association: the fixed set's cell means are staged in shared memory as float2 (the reference searches a float
+//     kd-tree, pcl::PointXY); one warp per source cell scans them lane-strided and the warp takes the lexicographic
+//     (distance, index) minimum — the exhaustive 1-NN the kd-tree returns, lowest index on exact ties;
+//   * accepted correspondences are compacted IN ORDER (fixed scan major, source index ascending — the order the
+//     reference adds residual blocks in) into field-major arrays holding exactly what a cost functor captures
+//     (source mean, target mean and normal / sqrt-information pre-transformed to the world frame, loss weight);
+//   * one evaluation = every thread strides over the blocks, accumulates cost, g = J^T r (3) and H = J^T J (6 unique)
+//     of the loss-corrected residuals/Jacobians, fixed-shape warp-shuffle + cross-warp reduction (deterministic);
+//   * thread 0 runs the trust-region logic on the 3x3 system: Jacobi scaling, LM diagonal clamp, Cholesky, model
+//     cost change, step quality, radius update, the three tolerance tests — the same state machine as
+//     ceres::internal::TrustRegionMinimizer with max_consecutive_nonmonotonic_steps = 0.
+// fp64 throughout (fp32 only where the reference uses float: the NN search), built with -fmad=false.
+#include <cfloat>
+#include <cmath>
+
+#include "tbv_reg.cuh"
+
+namespace tbv {
+
+constexpr int RG_THREADS = 256;
+constexpr int RG_WARPS = RG_THREADS / 32;
+constexpr int NACC = 10;  // cost, g0..g2, H00,H01,H02,H11,H12,H22
+
+struct Aff {
+  double r00, r01, r10, r11, tx, ty;
+};
+__device__ __forceinline__ Aff vec_to_aff(double x, double y, double th) {  // registration.cpp:129-135
+  Aff T;
+  const double c = cos(th), s = sin(th);
+  T.r00 = c; T.r01 = -s; T.r10 = s; T.r11 = c; T.tx = x; T.ty = y;
+  return T;
+}
+__device__ __forceinline__ Aff aff_mul(const Aff& A, const Aff& B) {
+  Aff C;
+  C.r00 = A.r00 * B.r00 + A.r01 * B.r10;
+  C.r01 = A.r00 * B.r01 + A.r01 * B.r11;
+  C.r10 = A.r10 * B.r00 + A.r11 * B.r10;
+  C.r11 = A.r10 * B.r01 + A.r11 * B.r11;
+  C.tx = (A.r00 * B.tx + A.r01 * B.ty) + A.tx;
+  C.ty = (A.r10 * B.tx + A.r11 * B.ty) + A.ty;
+  return C;
+}
+__device__ __forceinline__ Aff aff_inv(const Aff& A) {
+  Aff I;
+  const double det = A.r00 * A.r11 - A.r01 * A.r10;
+  const double invdet = 1.0 / det;
+  I.r00 = A.r11 * invdet;
+  I.r01 = -A.r01 * invdet;
+  I.r10 = -A.r10 * invdet;
+  I.r11 = A.r00 * invdet;
+  I.tx = -(I.r00 * A.tx + I.r01 * A.ty);
+  I.ty = -(I.r10 * A.tx + I.r11 * A.ty);
+  return I;
+}
+
+// ---- Ceres 2.1.0 loss functions wrapped in ScaledLoss (registration.cpp:77-96, n_scan_normal.cpp:275) -------------------
+__device__ __forceinline__ void loss_huber(double a, double s, double rho[3]) {
+  const double b = a * a;
+  if (s > b) {
+    const double r = sqrt(s);
+    rho[0] = 2.0 * a * r - b;
+    rho[1] = fmax(DBL_MIN, a / r);
+    rho[2] = -rho[1] / (2.0 * s);
+  } else {
+    rho[0] = s; rho[1] = 1.0; rho[2] = 0.0;
+  }
+}
+__device__ __forceinline__ void loss_cauchy(double a, double s, double rho[3]) {
+  const double b = a * a, c = 1.0 / b;
+  const double sum = 1.0 + s * c;
+  const double inv = 1.0 / sum;
+  rho[0] = b * log(sum);
+  rho[1] = fmax(DBL_MIN, inv);
+  rho[2] = -c * (inv * inv);
+}
+__device__ void scaled_loss(int loss, double limit, double w, double s, double rho[3]) {
+  switch (loss) {
+    case TBV_LOSS_HUBER: loss_huber(limit, s, rho); break;
+    case TBV_LOSS_CAUCHY: loss_cauchy(limit, s, rho); break;
+    case TBV_LOSS_SOFTLONE: {
+      const double b = limit * limit, c = 1.0 / b;
+      const double sum = 1.0 + s * c;
+      const double tmp = sqrt(sum);
+      rho[0] = 2.0 * b * (tmp - 1.0);
+      rho[1] = fmax(DBL_MIN, 1.0 / tmp);
+      rho[2] = -(c * rho[1]) / (2.0 * sum);
+      break;
+    }
+    case TBV_LOSS_TUKEY: {
+      const double a2 = limit * limit;
+      if (s <= a2) {
+        const double value = 1.0 - s / a2;
+        const double value_sq = value * value;
+        rho[0] = a2 / 3.0 * (1.0 - value_sq * value);
+        rho[1] = value_sq;
+        rho[2] = -2.0 / a2 * value;
+      } else {
+        rho[0] = a2 / 3.0; rho[1] = 0.0; rho[2] = 0.0;
+      }
+      break;
+    }
+    case TBV_LOSS_COMBINED: {  // ComposedLoss(Huber(1), Cauchy(1))
+      double rg[3], rf[3];
+      loss_cauchy(1.0, s, rg);
+      loss_huber(1.0, rg[0], rf);
+      rho[0] = rf[0];
+      rho[1] = rf[1] * rg[1];
+      rho[2] = rf[2] * rg[1] * rg[1] + rf[1] * rg[2];
+      break;
+    }
+    default:  // ScaledLoss with a null inner loss
+      rho[0] = w * s; rho[1] = w; rho[2] = 0.0;
+      return;
+  }
+  rho[0] *= w; rho[1] *= w; rho[2] *= w;
+}
+
+// One residual block at x: loss-corrected residuals f[n] and Jacobian J[n][3], returns 0.5*rho(s).
+// blk points at field 0 of the block (stride = field stride).
+__device__ __forceinline__ double eval_block(int cost_type, int loss, double limit, const double* __restrict__ blk, size_t stride,
+                                             double x0, double x1, double cy, double sy, double f[2], double J[6], int& n, bool want_jac) {
+  const double sx = blk[0], sy_ = blk[stride], tx = blk[2 * stride], ty = blk[3 * stride];
+  const double a4 = blk[4 * stride], a5 = blk[5 * stride], w = blk[7 * stride];
+  const double mx = (cy * sx + (-sy) * sy_) + x0;
+  const double my = (sy * sx + cy * sy_) + x1;
+  const double dmx = (-sy) * sx + (-cy) * sy_;
+  const double dmy = cy * sx + (-sy) * sy_;
+  if (cost_type == TBV_P2L) {
+    n = 1;
+    const double v0 = mx - tx, v1 = my - ty;
+    f[0] = v0 * a4 + v1 * a5;
+    J[0] = a4; J[1] = a5; J[2] = dmx * a4 + dmy * a5;
+  } else if (cost_type == TBV_P2P) {
+    n = 2;
+    f[0] = tx - mx; f[1] = ty - my;
+    J[0] = -1.0; J[1] = 0.0; J[2] = -dmx; J[3] = 0.0; J[4] = -1.0; J[5] = -dmy;
+  } else {  // P2D: L = [a4 0; a5 a6]
+    n = 2;
+    const double a6 = blk[6 * stride];
+    const double e0 = mx - tx, e1 = my - ty;
+    f[0] = a4 * e0 + 0.0 * e1;
+    f[1] = a5 * e0 + a6 * e1;
+    J[0] = a4; J[1] = 0.0; J[2] = a4 * dmx + 0.0 * dmy;
+    J[3] = a5; J[4] = a6; J[5] = a5 * dmx + a6 * dmy;
+  }
+  double sq = 0.0;
+  for (int r = 0; r < n; r++) sq += f[r] * f[r];
+  double rho[3];
+  scaled_loss(loss, limit, w, sq, rho);
+  // ceres::internal::Corrector
+  const double sqrt_rho1 = sqrt(rho[1]);
+  double residual_scaling, alpha_sq_norm;
+  if (sq == 0.0 || rho[2] <= 0.0) {
+    residual_scaling = sqrt_rho1;
+    alpha_sq_norm = 0.0;
+  } else {
+    const double D = 1.0 + 2.0 * sq * rho[2] / rho[1];
+    const double alpha = 1.0 - sqrt(D);
+    residual_scaling = sqrt_rho1 / (1 - alpha);
+    alpha_sq_norm = alpha / sq;
+  }
+  if (want_jac) {
+    if (alpha_sq_norm == 0.0) {
+      for (int i = 0; i < n * 3; i++) J[i] *= sqrt_rho1;
+    } else {
+      for (int c = 0; c < 3; c++) {
+        double rtj = 0.0;
+        for (int r = 0; r < n; r++) rtj += J[r * 3 + c] * f[r];
+        for (int r = 0; r < n; r++) J[r * 3 + c] = sqrt_rho1 * (J[r * 3 + c] - alpha_sq_norm * f[r] * rtj);
+      }
+    }
+  }
+  for (int r = 0; r < n; r++) f[r] *= residual_scaling;
+  return 0.5 * rho[0];
+}
+
+// ---- LM state machine (thread 0) ----------------------------------------------------------------------------------------
+struct LMState {
+  double x[3], x_norm, x_cost;
+  double g[3], H[6];          // at x: unscaled gradient and J^T J (00 01 02 11 12 22)
+  double scal[3];             // jacobian_scaling
+  double radius, decrease_factor, diag[3];
+  bool reuse_diagonal;
+  double ev_minimum_cost, ev_current_cost, ev_reference_cost, ev_candidate_cost, ev_acc_ref, ev_acc_cand;
+  int num_consecutive_invalid;
+  // current iteration summary
+  int it_iteration;
+  bool it_successful;
+  double it_cost, it_gmax, it_gnorm, it_rel_dec;
+  // pushed summaries
+  int n_pushed;
+  double last_rel_dec, last_gmax, last_gnorm, min_pushed_cost, initial_cost;
+  int termination;            // 0 convergence, 1 no convergence, 2 failure
+  bool terminated;
+  double minimum_cost, params[3];
+  // pending step
+  double cand[3], model_cost_change;
+};
+
+__device__ void lm_gradient_norms(LMState& S) {
+  double gmax = 0.0, gn = 0.0;
+  for (int c = 0; c < 3; c++) {
+    const double pg = S.x[c] - (S.x[c] + (-S.g[c]));
+    gmax = fmax(gmax, fabs(pg));
+    gn += pg * pg;
+  }
+  S.it_gmax = gmax;
+  S.it_gnorm = sqrt(gn);
+}
+
+__device__ bool chol_solve3(const double H[3][3], const double b[3], double y[3]) {
+  double L[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < 3; j++) {
+    double d = H[j][j];
+    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    L[j][j] = sqrt(d);
+    for (int i = j + 1; i < 3; i++) {
+      double v = H[i][j];
+      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  double z[3];
+  for (int i = 0; i < 3; i++) {
+    double v = b[i];
+    for (int k = 0; k < i; k++) v -= L[i][k] * z[k];
+    z[i] = v / L[i][i];
+  }
+  for (int i = 2; i >= 0; i--) {
+    double v = z[i];
+    for (int k = i + 1; k < 3; k++) v -= L[k][i] * y[k];
+    y[i] = v / L[i][i];
+  }
+  return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
+}
+
+// after the evaluation at the initial point (acc = cost, g, H)
+__device__ void lm_begin(LMState& S, const double x0[3], const double* acc) {
+  for (int c = 0; c < 3; c++) { S.x[c] = x0[c]; S.params[c] = x0[c]; }
+  S.x_norm = sqrt(S.x[0] * S.x[0] + S.x[1] * S.x[1] + S.x[2] * S.x[2]);
+  S.radius = 1e4; S.decrease_factor = 2.0; S.reuse_diagonal = false;
+  S.diag[0] = S.diag[1] = S.diag[2] = 0.0;
+  S.ev_acc_ref = 0.0; S.ev_acc_cand = 0.0;
+  S.num_consecutive_invalid = 0;
+  S.n_pushed = 0; S.terminated = false; S.termination = 1;
+  S.it_iteration = 0; S.it_rel_dec = 0.0;
+  S.x_cost = acc[0];
+  for (int c = 0; c < 3; c++) S.g[c] = acc[1 + c];
+  for (int c = 0; c < 6; c++) S.H[c] = acc[4 + c];
+  const double hd[3] = {S.H[0], S.H[3], S.H[5]};
+  for (int c = 0; c < 3; c++) S.scal[c] = 1.0 / (1.0 + sqrt(hd[c]));
+  S.it_cost = S.x_cost;
+  lm_gradient_norms(S);
+  S.initial_cost = S.x_cost;
+  S.min_pushed_cost = S.x_cost;
+  S.it_successful = true;
+  S.minimum_cost = S.x_cost;
+  S.ev_minimum_cost = S.ev_current_cost = S.ev_reference_cost = S.ev_candidate_cost = S.x_cost;
+}
+
+// FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep (+ HandleInvalidStep loop).
+// Returns true when S.cand must be evaluated; false when the solve is over.
+__device__ bool lm_advance(LMState& S, int max_iterations) {
+  if (S.terminated) return false;
+  for (;;) {
+    // ---- Finalize
+    if (S.it_successful) {
+      if (S.x_cost < S.minimum_cost || S.it_iteration == 0) {
+        S.minimum_cost = fmin(S.minimum_cost, S.x_cost);
+        S.params[0] = S.x[0]; S.params[1] = S.x[1]; S.params[2] = S.x[2];
+      }
+    }
+    S.n_pushed++;
+    S.last_rel_dec = S.it_rel_dec; S.last_gmax = S.it_gmax; S.last_gnorm = S.it_gnorm;
+    S.min_pushed_cost = fmin(S.min_pushed_cost, S.it_cost);
+    if (S.it_iteration >= max_iterations) { S.termination = 1; S.terminated = true; return false; }
+    if (S.it_successful && S.it_gmax <= 1e-10) { S.termination = 0; S.terminated = true; return false; }
+    if (S.radius < 1e-32) { S.termination = 0; S.terminated = true; return false; }
+    // ---- next iteration
+    S.it_iteration++;
+    S.it_successful = false;
+    S.it_rel_dec = 0.0;
+    S.it_cost = 0.0;
+    const double hd[3] = {S.H[0], S.H[3], S.H[5]};
+    if (!S.reuse_diagonal)
+      for (int c = 0; c < 3; c++) S.diag[c] = fmin(fmax((S.scal[c] * S.scal[c]) * hd[c], 1e-6), 1e32);
+    double lmd[3];
+    for (int c = 0; c < 3; c++) lmd[c] = sqrt(S.diag[c] / S.radius);
+    const double Hf[3][3] = {{S.H[0], S.H[1], S.H[2]}, {S.H[1], S.H[3], S.H[4]}, {S.H[2], S.H[4], S.H[5]}};
+    double Hs[3][3], Hd[3][3], rhs[3];
+    for (int a = 0; a < 3; a++) {
+      rhs[a] = S.scal[a] * S.g[a];
+      for (int c = 0; c < 3; c++) { Hs[a][c] = (S.scal[a] * S.scal[c]) * Hf[a][c]; Hd[a][c] = Hs[a][c]; }
+      Hd[a][a] += lmd[a] * lmd[a];
+    }
+    double step[3];
+    const bool solved = chol_solve3(Hd, rhs, step);
+    S.reuse_diagonal = true;
+    bool valid = false;
+    if (solved) {
+      for (int c = 0; c < 3; c++) step[c] *= -1.0;
+      double lin = 0.0, quad = 0.0;
+      for (int a = 0; a < 3; a++) {
+        lin += step[a] * rhs[a];
+        double hv = 0.0;
+        for (int c = 0; c < 3; c++) hv += Hs[a][c] * step[c];
+        quad += step[a] * hv;
+      }
+      S.model_cost_change = -(lin + quad / 2.0);
+      valid = S.model_cost_change > 0.0;
+    }
+    if (valid) {
+      S.num_consecutive_invalid = 0;
+      for (int c = 0; c < 3; c++) S.cand[c] = S.x[c] + step[c] * S.scal[c];
+      return true;
+    }
+    // ---- HandleInvalidStep
+    S.num_consecutive_invalid++;
+    if (S.num_consecutive_invalid >= 5) { S.termination = 2; S.terminated = true; return false; }
+    S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = true;
+    S.it_cost = S.x_cost; S.it_rel_dec = 0.0;
+    S.it_gmax = S.last_gmax; S.it_gnorm = S.last_gnorm;
+  }
+}
+
+// after the evaluation at S.cand (acc = cost, g, H there)
+__device__ void lm_candidate(LMState& S, const double* acc) {
+  double candidate_cost = acc[0];
+  if (!isfinite(candidate_cost)) candidate_cost = DBL_MAX;
+  {
+    const double d0 = S.x[0] - S.cand[0], d1 = S.x[1] - S.cand[1], d2 = S.x[2] - S.cand[2];
+    const double step_norm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    const double tol = 1e-8 * (S.x_norm + 1e-8);
+    if (step_norm <= tol) { S.termination = 0; S.terminated = true; return; }
+  }
+  const double cost_change = S.x_cost - candidate_cost;
+  if (fabs(cost_change) <= 1e-6 * S.x_cost) { S.termination = 0; S.terminated = true; return; }
+  if (candidate_cost >= DBL_MAX) {
+    S.it_rel_dec = -DBL_MAX;
+  } else {
+    const double rd = (S.ev_current_cost - candidate_cost) / S.model_cost_change;
+    const double hist = (S.ev_reference_cost - candidate_cost) / (S.ev_acc_ref + S.model_cost_change);
+    S.it_rel_dec = fmax(rd, hist);
+  }
+  if (S.it_rel_dec > 1e-3) {
+    for (int c = 0; c < 3; c++) S.x[c] = S.cand[c];
+    S.x_norm = sqrt(S.x[0] * S.x[0] + S.x[1] * S.x[1] + S.x[2] * S.x[2]);
+    S.x_cost = acc[0];
+    for (int c = 0; c < 3; c++) S.g[c] = acc[1 + c];
+    for (int c = 0; c < 6; c++) S.H[c] = acc[4 + c];
+    S.it_cost = S.x_cost;
+    lm_gradient_norms(S);
+    S.it_successful = true;
+    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * S.it_rel_dec - 1.0, 3.0));
+    S.radius = fmin(1e16, S.radius);
+    S.decrease_factor = 2.0;
+    S.reuse_diagonal = false;
+    S.ev_current_cost = candidate_cost;
+    S.ev_acc_cand += S.model_cost_change;
+    S.ev_acc_ref += S.model_cost_change;
+    if (S.ev_current_cost < S.ev_minimum_cost) {
+      S.ev_minimum_cost = S.ev_current_cost; S.ev_candidate_cost = S.ev_current_cost; S.ev_acc_cand = 0.0;
+      S.ev_reference_cost = S.ev_candidate_cost; S.ev_acc_ref = S.ev_acc_cand;
+    } else if (S.ev_current_cost > S.ev_candidate_cost) {
+      S.ev_candidate_cost = S.ev_current_cost; S.ev_acc_cand = 0.0;
+    }
+  } else {
+    S.it_successful = false;
+    S.it_cost = candidate_cost;
+    S.it_gmax = S.last_gmax; S.it_gnorm = S.last_gnorm;
+    S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = true;
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------
+struct RegShared {
+  double acc[NACC];
+  double warp_acc[RG_WARPS][NACC];
+  double ex[3], cs[2];
+  int flag, n_blocks, warp_cnt[RG_WARPS], running;
+};
+
+__device__ __forceinline__ int set_count(const SetView& s) { return s.n_ptr ? min(*s.n_ptr, s.cap) : min(s.n_val, s.cap); }
+
+__global__ void __launch_bounds__(RG_THREADS)
+k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
+           const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
+           double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
+           double* __restrict__ residuals_all) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float2* s_tgt = reinterpret_cast<float2*>(s_raw);  // [tgt_cap] cell means of the fixed scan being searched
+  __shared__ RegShared sh;
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned FULL = 0xffffffffu;
+  const RegProblem prob = problems[p];
+  RegResult* out = results + p;
+  if (!prob.active) {
+    if (tid == 0) {
+      RegResult r;
+      memset(&r, 0, sizeof(r));
+      r.pose[0] = prob.src_pose[0]; r.pose[1] = prob.src_pose[1]; r.pose[2] = prob.src_pose[2];
+      *out = r;
+      if (n_blocks_all) n_blocks_all[p] = 0;
+    }
+    return;
+  }
+  const SetView src = sets[prob.src_set];
+  const int n_src = set_count(src);
+  const size_t bstride = (size_t)max_fixed * slot_cap;
+  int* assoc = assoc_all + (size_t)p * bstride;
+  double* blocks = blocks_all + (size_t)p * BLK_FIELDS * bstride;
+  const int nres_per_block = (P.cost == TBV_P2L) ? 1 : 2;
+
+  // ---- association at pose x with search radius R: fills assoc + compacted blocks, returns the block count in sh.n_blocks
+  auto associate = [&](const double x[3], double R) {
+    const Aff Tsrc = vec_to_aff(x[0], x[1], x[2]);
+    if (tid == 0) sh.running = 0;
+    for (int fi = 0; fi < prob.n_fixed; fi++) {
+      const SetView tgt = sets[fixed_set[prob.fixed_first + fi]];
+      const int n_tgt = set_count(tgt);
+      const double* fp = fixed_pose + (size_t)(prob.fixed_first + fi) * 3;
+      const Aff Ttar = vec_to_aff(fp[0], fp[1], fp[2]);
+      const Aff Tst = aff_mul(aff_inv(Ttar), Tsrc);
+      __syncthreads();  // previous users of s_tgt are done
+      for (int i = tid; i < n_tgt; i += RG_THREADS)
+        s_tgt[i] = make_float2((float)tgt.f[(size_t)CF_U0 * tgt.cap + i], (float)tgt.f[(size_t)CF_U1 * tgt.cap + i]);
+      __syncthreads();
+      // 1-NN: one warp per source cell
+      for (int j = warp; j < n_src; j += RG_WARPS) {
+        const double ux = src.f[(size_t)CF_U0 * src.cap + j], uy = src.f[(size_t)CF_U1 * src.cap + j];
+        const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
+        const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
+        const float qx = (float)qxd, qy = (float)qyd;
+        float bestd = FLT_MAX;
+        int best = 0x7fffffff;
+        for (int i = lane; i < n_tgt; i += 32) {
+          const float2 m = s_tgt[i];
+          const float dx = qx - m.x, dy = qy - m.y;
+          float dd = dx * dx;       // FLANN L2_Simple, no contraction (-fmad=false)
+          dd = dd + dy * dy;
+          if (dd < bestd) { bestd = dd; best = i; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const float od = __shfl_xor_sync(FULL, bestd, d);
+          const int oi = __shfl_xor_sync(FULL, best, d);
+          if (od < bestd || (od == bestd && oi < best)) { bestd = od; best = oi; }
+        }
+        if (lane == 0) {
+          int a = -1;
+          if (best != 0x7fffffff && (double)bestd < R * R) a = best;  // pointnormal.cpp:250
+          assoc[(size_t)fi * slot_cap + j] = a;
+        }
+      }
+      __syncthreads();
+      // gate + weights + block data, ordered compaction
+      for (int base = 0; base < n_src; base += RG_THREADS) {
+        const int j = base + tid;
+        bool ok = false;
+        int ti = -1;
+        double w = 0.0;
+        if (j < n_src) {
+          ti = assoc[(size_t)fi * slot_cap + j];
+          if (ti >= 0) {
+            const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
+            const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
+            const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
+            const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
+            const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
+            if (sim > P.angle_outlier) {
+              ok = true;
+              const double N1 = src.f[(size_t)CF_NS * src.cap + j], N2 = tgt.f[(size_t)CF_NS * tgt.cap + ti];
+              const double p1 = src.f[(size_t)CF_SCALE * src.cap + j], p2 = tgt.f[(size_t)CF_SCALE * tgt.cap + ti];
+              const double simN = 2 * fmin(N1, N2) / (N1 + N2);
+              const double simP = 2 * fmin(p1, p2) / (p1 + p2);
+              switch (P.weight_opt) {   // registration.cpp:67-75
+                case TBV_W_UNIFORM: w = 1.0; break;
+                case TBV_W_SIM_N: w = simN; break;
+                case TBV_W_SIM_DIRECTION: w = sim; break;
+                case TBV_W_SIM_SCALE: w = simP; break;
+                case TBV_W_COMBINED: w = simN + sim + simP; break;
+                default: w = 1.0;
+              }
+            } else {
+              assoc[(size_t)fi * slot_cap + j] = -1;
+            }
+          }
+        }
+        const unsigned bal = __ballot_sync(FULL, ok);
+        if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        if (ok) {
+          int q = sh.running + __popc(bal & ((1u << lane) - 1u));
+          for (int wv = 0; wv < warp; wv++) q += sh.warp_cnt[wv];
+          const double tu0 = tgt.f[(size_t)CF_U0 * tgt.cap + ti], tu1 = tgt.f[(size_t)CF_U1 * tgt.cap + ti];
+          blocks[0 * bstride + q] = src.f[(size_t)CF_U0 * src.cap + j];
+          blocks[1 * bstride + q] = src.f[(size_t)CF_U1 * src.cap + j];
+          blocks[2 * bstride + q] = (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx;
+          blocks[3 * bstride + q] = (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty;
+          if (P.cost == TBV_P2L) {
+            const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
+            blocks[4 * bstride + q] = Ttar.r00 * tn0 + Ttar.r01 * tn1;
+            blocks[5 * bstride + q] = Ttar.r10 * tn0 + Ttar.r11 * tn1;
+          } else if (P.cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
+            const double c00 = tgt.f[(size_t)CF_C00 * tgt.cap + ti], c01 = tgt.f[(size_t)CF_C01 * tgt.cap + ti];
+            const double c10 = tgt.f[(size_t)CF_C10 * tgt.cap + ti], c11 = tgt.f[(size_t)CF_C11 * tgt.cap + ti];
+            const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
+            const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
+            const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
+            const double M00 = RC00 * R00 + RC01 * R01, M01 = RC00 * R10 + RC01 * R11;
+            const double M10 = RC10 * R00 + RC11 * R01, M11 = RC10 * R10 + RC11 * R11;
+            const double t00 = (P.regularization + M00) * P.cov_scale, t01 = (0.0 + M01) * P.cov_scale;
+            const double t10 = (0.0 + M10) * P.cov_scale, t11 = (P.regularization + M11) * P.cov_scale;
+            const double det = t00 * t11 - t10 * t01;
+            const double invdet = 1.0 / det;
+            const double i00 = t11 * invdet, i10 = -t10 * invdet, i11 = t00 * invdet;
+            const double l00 = sqrt(i00);
+            const double l10 = i10 / l00;
+            const double l11 = sqrt(i11 - l10 * l10);
+            blocks[4 * bstride + q] = l00;
+            blocks[5 * bstride + q] = l10;
+            blocks[6 * bstride + q] = l11;
+          }
+          blocks[7 * bstride + q] = w;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int t = 0;
+          for (int wv = 0; wv < RG_WARPS; wv++) t += sh.warp_cnt[wv];
+          sh.running += t;
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    if (tid == 0) sh.n_blocks = sh.running;
+    __syncthreads();
+  };
+
+  // ---- evaluation at sh.ex (cos/sin in sh.cs): result in sh.acc
+  auto evaluate = [&](int nblk, bool write_residuals) {
+    double a[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) a[i] = 0.0;
+    const double x0 = sh.ex[0], x1 = sh.ex[1], cy = sh.cs[0], sy = sh.cs[1];
+    for (int q = tid; q < nblk; q += RG_THREADS) {
+      double f[2], J[6];
+      int n;
+      a[0] += eval_block(P.cost, P.loss, P.loss_limit, blocks + q, bstride, x0, x1, cy, sy, f, J, n, true);
+      for (int r = 0; r < n; r++) {
+        const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
+        a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
+        a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
+      }
+      if (write_residuals && residuals_all) {
+        double* ro = residuals_all + (size_t)p * 2 * bstride;
+        for (int r = 0; r < n; r++) ro[(size_t)q * n + r] = f[r];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NACC; i++) {
+      double v = a[i];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+      if (lane == 0) sh.warp_acc[warp][i] = v;
+    }
+    __syncthreads();
+    if (tid < NACC) {
+      double v = 0.0;
+      for (int wv = 0; wv < RG_WARPS; wv++) v += sh.warp_acc[wv][tid];
+      sh.acc[tid] = v;
+    }
+    __syncthreads();
+  };
+  auto set_eval_point = [&](const double x[3]) {  // thread 0
+    sh.ex[0] = x[0]; sh.ex[1] = x[1]; sh.ex[2] = x[2];
+    sh.cs[0] = cos(x[2]); sh.cs[1] = sin(x[2]);
+  };
+
+  // =========================================================================================================
+  if (mode == REG_MODE_EVAL) {
+    const double R = (eval_itr == 1) ? 2 * P.radius : P.radius;
+    associate(prob.src_pose, R);
+    const int nblk = sh.n_blocks;
+    if (tid == 0) set_eval_point(prob.src_pose);
+    __syncthreads();
+    evaluate(nblk, true);
+    if (tid == 0) {
+      RegResult r;
+      memset(&r, 0, sizeof(r));
+      r.pose[0] = prob.src_pose[0]; r.pose[1] = prob.src_pose[1]; r.pose[2] = prob.src_pose[2];
+      r.num_residuals = nblk * nres_per_block;
+      r.success = r.num_residuals > 1;
+      r.final_cost = sh.acc[0];
+      r.score = sh.acc[0] / (double)max(r.num_residuals, 1);
+      *out = r;
+      n_blocks_all[p] = nblk;
+      if (eval_out)
+        for (int i = 0; i < NACC; i++) eval_out[(size_t)p * NACC + i] = sh.acc[i];
+    }
+    return;
+  }
+
+  // ---- Register (n_scan_normal.cpp:82-185) — control state lives in thread 0, decisions are broadcast through sh.flag
+  LMState S;
+  double par[3] = {prob.src_pose[0], prob.src_pose[1], prob.src_pose[2]};  // parameters.back()
+  double prev_par[3] = {par[0], par[1], par[2]};
+  double tsrc[3] = {par[0], par[1], par[2]};  // Tsrc.back(): only rewritten after a usable solve (:118-121, :166-170)
+  double prev_score = DBL_MAX;
+  int total_lm = 0, itr = 1, pose_updated = 0;
+  bool success = true;
+  int num_residuals = 0, last_n_iterations = 0, termination = 1;
+  double final_cost = 0.0, last_rel_dec = 0.0;
+  for (itr = 1; itr <= P.max_itr_association && success; itr++) {
+    const double R = (itr == 1) ? 2 * P.radius : P.radius;
+    associate(par, R);  // every thread keeps an identical copy of par (broadcast below)
+    const int nblk = sh.n_blocks;
+    num_residuals = nblk * nres_per_block;
+    if (num_residuals <= 1) { success = false; break; }  // BuildOptimizationProblem fails (:371-374)
+    // ---- ceres::Solve
+    if (tid == 0) set_eval_point(par);
+    __syncthreads();
+    evaluate(nblk, false);
+    if (tid == 0) {
+      lm_begin(S, par, sh.acc);
+      const bool go = lm_advance(S, P.max_itr_solver);
+      if (go) set_eval_point(S.cand);
+      sh.flag = go ? 1 : 0;
+    }
+    __syncthreads();
+    while (sh.flag) {
+      evaluate(nblk, false);
+      if (tid == 0) {
+        lm_candidate(S, sh.acc);
+        const bool go = lm_advance(S, P.max_itr_solver);
+        if (go) set_eval_point(S.cand);
+        sh.flag = go ? 1 : 0;
+      }
+      __syncthreads();
+    }
+    // broadcast the outcome of this solve: parameters + the scalars the outer loop reads
+    if (tid == 0) {
+      sh.ex[0] = S.params[0]; sh.ex[1] = S.params[1]; sh.ex[2] = S.params[2];
+      sh.acc[0] = fmin(S.initial_cost, S.min_pushed_cost);  // SetSummaryFinalCost
+      sh.acc[1] = S.last_rel_dec;
+      sh.warp_cnt[0] = S.n_pushed;
+      sh.warp_cnt[1] = S.termination;
+    }
+    __syncthreads();
+    par[0] = sh.ex[0]; par[1] = sh.ex[1]; par[2] = sh.ex[2];
+    final_cost = sh.acc[0];
+    last_rel_dec = sh.acc[1];
+    last_n_iterations = sh.warp_cnt[0];
+    termination = sh.warp_cnt[1];
+    __syncthreads();
+    total_lm += last_n_iterations - 1;
+    success = termination != 2;  // IsSolutionUsable
+    if (success) { pose_updated = 1; tsrc[0] = par[0]; tsrc[1] = par[1]; tsrc[2] = par[2]; }
+    const double current_score = final_cost;
+    const double rel_improvement = (prev_score - current_score) / prev_score;
+    if (itr > 3) {  // min_itr_ = 3
+      if (prev_score < current_score) {
+        par[0] = prev_par[0]; par[1] = prev_par[1]; par[2] = prev_par[2];
+        break;
+      } else if (rel_improvement < 0.00001) {
+        break;
+      } else if (last_rel_dec < 0.00001 || last_n_iterations == 1) {
+        break;
+      }
+    }
+    prev_score = current_score;
+    prev_par[0] = par[0]; prev_par[1] = par[1]; prev_par[2] = par[2];
+  }
+  if (success && pose_updated) { tsrc[0] = par[0]; tsrc[1] = par[1]; tsrc[2] = par[2]; }
+  if (tid == 0) {
+    RegResult r;
+    memset(&r, 0, sizeof(r));
+    r.pose[0] = tsrc[0]; r.pose[1] = tsrc[1]; r.pose[2] = tsrc[2];
+    r.pose_updated = pose_updated;
+    r.success = success ? 1 : 0;
+    r.itrs = itr;
+    r.lm_iterations = total_lm;
+    r.num_residuals = num_residuals;
+    r.last_n_iterations = last_n_iterations;
+    r.termination = termination;
+    r.final_cost = final_cost;
+    r.last_relative_decrease = last_rel_dec;
+    r.score = success ? final_cost / (double)num_residuals : 0.0;
+    // Talign = Trevised^-1 * Tto (loopclosure.cpp:73), Trevised = vectorToAffine(parameters)
+    const double* fp = fixed_pose + (size_t)prob.fixed_first * 3;
+    const Aff Tal = aff_mul(aff_inv(vec_to_aff(tsrc[0], tsrc[1], tsrc[2])), vec_to_aff(fp[0], fp[1], fp[2]));
+    r.align[0] = Tal.tx; r.align[1] = Tal.ty; r.align[2] = atan2(Tal.r10, Tal.r11);
+    *out = r;
+    if (n_blocks_all) n_blocks_all[p] = sh.n_blocks;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+RegParamsDev to_dev(const tbv_reg_params& p) {
+  RegParamsDev d;
+  d.cost = p.cost; d.loss = p.loss; d.weight_opt = p.weight_opt; d.loss_limit = p.loss_limit; d.cov_scale = p.cov_scale;
+  d.regularization = p.regularization;
+  const bool both = p.max_itr_association > 0 && p.max_itr_solver > 0;            // SetParameters sets both (n_scan_normal.h:53-55)
+  d.max_itr_association = both ? p.max_itr_association : 8;                       // n_scan_normal.h:75
+  d.max_itr_solver = both ? p.max_itr_solver : 20;                                // n_scan_normal.cpp:9
+  d.angle_outlier = std::cos(M_PI / 6.0);                                         // n_scan_normal.cpp:216
+  d.radius = 2.0;                                                                 // registration.h:122
+  return d;
+}
+
+RegScratch* reg_scratch(tbv_ctx* ctx) {
+  if (!ctx->reg_scratch) ctx->reg_scratch = new RegScratch();
+  return (RegScratch*)ctx->reg_scratch;
+}
+void reg_release(tbv_ctx* ctx) {
+  if (!ctx->reg_scratch) return;
+  RegScratch* s = (RegScratch*)ctx->reg_scratch;
+  s->release();
+  delete s;
+  ctx->reg_scratch = nullptr;
+}
+int reg_scratch_reserve(tbv_ctx* ctx, int n_problems, int max_fixed, int slot_cap, bool want_residuals) {
+  RegScratch& S = *reg_scratch(ctx);
+  const size_t slots = (size_t)n_problems * max_fixed * slot_cap;
+  int rc;
+  if ((rc = S.assoc.reserve(slots)) || (rc = S.blocks.reserve(slots * BLK_FIELDS)) || (rc = S.n_blocks.reserve(n_problems))) return rc;
+  if (want_residuals && (rc = S.residuals.reserve(slots * 2))) return rc;
+  return TBV_OK;
+}
+
+int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_dev, const RegProblem* problems_dev, const int* fixed_set_dev,
+                    const double* fixed_pose_dev, int n_problems, int max_fixed, int slot_cap, int tgt_cap, const RegParamsDev& params,
+                    RegResult* results_dev, double* eval_out_dev, bool want_residuals) {
+  if (n_problems <= 0) return TBV_OK;
+  TBV_REQUIRE(max_fixed >= 1 && slot_cap >= 1 && tgt_cap >= 1, "bad registration capacities");
+  int rc = reg_scratch_reserve(ctx, n_problems, max_fixed, slot_cap, want_residuals);
+  if (rc) return rc;
+  RegScratch& S = *reg_scratch(ctx);
+  const size_t smem = (size_t)tgt_cap * sizeof(float2);
+  TBV_REQUIRE(smem <= 160 * 1024, "fixed scan too large for the shared-memory search (more than 20480 cells)");
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    TBV_CUDA(cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  k_register<<<n_problems, RG_THREADS, smem, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
+                                                            slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
+                                                            want_residuals ? S.residuals.p : nullptr);
+  ctx->launches++;
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// C-ABI entry points with host-resident cell records
+// --------------------------------------------------------------------------------------------------------------
+namespace {
+struct HostProblemSet {  // uploads n_sets cell sets and describes them as SetViews
+  tbv_ctx* ctx;
+  std::vector<DevBuf<double>> bufs;
+  DevBuf<SetView> views;
+  int max_n = 1;
+  ~HostProblemSet() {
+    for (auto& b : bufs) b.release();
+    views.release();
+  }
+  int upload(int n_sets, const tbv_cell* const* sets, const int* n_cells) {
+    bufs.resize(n_sets);
+    std::vector<SetView> hv(n_sets);
+    for (int i = 0; i < n_sets; i++) {
+      const int n = n_cells[i];
+      TBV_REQUIRE(n >= 0 && (n == 0 || sets[i]), "bad cell set");
+      const int cap = n > 0 ? n : 1;
+      int rc = bufs[i].reserve((size_t)CELL_FIELDS * cap);
+      if (rc) return rc;
+      if ((rc = cells_upload(ctx, sets[i], n, bufs[i].p, cap))) return rc;
+      hv[i] = SetView{bufs[i].p, cap, nullptr, n};
+      if (n > max_n) max_n = n;
+    }
+    int rc = views.reserve(n_sets);
+    if (rc) return rc;
+    TBV_CUDA(cudaMemcpyAsync(views.p, hv.data(), n_sets * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
+    TBV_CUDA(cudaStreamSynchronize(ctx->stream));  // hv goes out of scope
+    return TBV_OK;
+  }
+};
+
+template <typename T>
+int to_device(tbv_ctx* ctx, DevBuf<T>& d, const std::vector<T>& h) {
+  int rc = d.reserve(h.size() ? h.size() : 1);
+  if (rc) return rc;
+  if (!h.empty()) TBV_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return TBV_OK;
+}
+
+void fill_summary(const RegResult& r, tbv_reg_summary* s) {
+  if (!s) return;
+  s->success = r.success; s->itrs = r.itrs; s->lm_iterations = r.lm_iterations; s->num_residuals = r.num_residuals;
+  s->last_n_iterations = r.last_n_iterations; s->termination = r.termination; s->score = r.score; s->final_cost = r.final_cost;
+  s->last_relative_decrease = r.last_relative_decrease;
+}
+
+// one problem: scans[0..n-2] fixed, scans[n-1] moving
+int run_single(tbv_ctx* ctx, int mode, int eval_itr, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T,
+               const tbv_reg_params* params, RegResult* res, double* eval_out, std::vector<int>* assoc, std::vector<double>* residuals,
+               int* n_blocks) {
+  HostProblemSet hs;
+  hs.ctx = ctx;
+  int rc = hs.upload(n_scans, scans, n_cells);
+  if (rc) return rc;
+  const int n_fixed = n_scans - 1;
+  RegProblem pr;
+  pr.n_fixed = n_fixed; pr.fixed_first = 0; pr.src_set = n_scans - 1; pr.active = 1;
+  for (int c = 0; c < 3; c++) pr.src_pose[c] = T[3 * (n_scans - 1) + c];
+  std::vector<RegProblem> hp{pr};
+  std::vector<int> hfs(n_fixed);
+  std::vector<double> hfp((size_t)n_fixed * 3);
+  for (int i = 0; i < n_fixed; i++) {
+    hfs[i] = i;
+    for (int c = 0; c < 3; c++) hfp[3 * i + c] = T[3 * i + c];
+  }
+  DevBuf<RegProblem> dp; DevBuf<int> dfs; DevBuf<double> dfp, dev_eval; DevBuf<RegResult> dr;
+  auto cleanup = [&]() { dp.release(); dfs.release(); dfp.release(); dev_eval.release(); dr.release(); };
+  if ((rc = to_device(ctx, dp, hp)) || (rc = to_device(ctx, dfs, hfs)) || (rc = to_device(ctx, dfp, hfp)) || (rc = dr.reserve(1)) ||
+      (rc = dev_eval.reserve(NACC))) { cleanup(); return rc; }
+  const int slot_cap = n_cells[n_scans - 1] > 0 ? n_cells[n_scans - 1] : 1;
+  rc = register_launch(ctx, mode, eval_itr, hs.views.p, dp.p, dfs.p, dfp.p, 1, n_fixed, slot_cap, hs.max_n, to_dev(*params), dr.p, dev_eval.p,
+                       residuals != nullptr);
+  if (rc) { cleanup(); return rc; }
+  cudaError_t e = cudaMemcpyAsync(res, dr.p, sizeof(RegResult), cudaMemcpyDeviceToHost, ctx->stream);
+  double ev[NACC];
+  if (e == cudaSuccess && eval_out) e = cudaMemcpyAsync(ev, dev_eval.p, sizeof(ev), cudaMemcpyDeviceToHost, ctx->stream);
+  RegScratch& S = *reg_scratch(ctx);
+  int nb = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&nb, S.n_blocks.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && assoc) {
+    assoc->assign((size_t)n_fixed * slot_cap, -1);
+    e = cudaMemcpyAsync(assoc->data(), S.assoc.p, assoc->size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && residuals) {
+    const int nres = nb * (params->cost == TBV_P2L ? 1 : 2);
+    residuals->assign(nres, 0.0);
+    if (nres > 0) e = cudaMemcpy(residuals->data(), S.residuals.p, (size_t)nres * sizeof(double), cudaMemcpyDeviceToHost);
+  }
+  cleanup();
+  if (e != cudaSuccess) { set_error("registration: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  if (eval_out) memcpy(eval_out, ev, sizeof(ev));
+  if (n_blocks) *n_blocks = nb;
+  return TBV_OK;
+}
+}  // namespace
+
+}  // namespace tbv
+
+using namespace tbv;
+
+extern "C" {
+
+int tbv_pair_normal_eq(tbv_ctx* ctx, const tbv_cell* tgt, int n_tgt, const double T_tgt[3], const tbv_cell* src, int n_src,
+                       const double T_src[3], const tbv_reg_params* params, int itr, double* cost, int* n_res, double H[9], double g[3],
+                       int32_t* assoc) {
+  TBV_REQUIRE(ctx && T_tgt && T_src && params && n_tgt >= 0 && n_src >= 0, "bad arguments");
+  const tbv_cell* scans[2] = {tgt, src};
+  const int n_cells[2] = {n_tgt, n_src};
+  const double T[6] = {T_tgt[0], T_tgt[1], T_tgt[2], T_src[0], T_src[1], T_src[2]};
+  RegResult r;
+  double ev[NACC];
+  std::vector<int> a;
+  int rc = run_single(ctx, REG_MODE_EVAL, itr, 2, scans, n_cells, T, params, &r, ev, assoc ? &a : nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  if (cost) *cost = ev[0];
+  if (n_res) *n_res = r.num_residuals;
+  if (g) { g[0] = ev[1]; g[1] = ev[2]; g[2] = ev[3]; }
+  if (H) {
+    H[0] = ev[4]; H[1] = ev[5]; H[2] = ev[6];
+    H[3] = ev[5]; H[4] = ev[7]; H[5] = ev[8];
+    H[6] = ev[6]; H[7] = ev[8]; H[8] = ev[9];
+  }
+  if (assoc) for (int j = 0; j < n_src; j++) assoc[j] = a[j];
+  return TBV_OK;
+}
+
+int tbv_register(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, double* T, const tbv_reg_params* params,
+                 tbv_reg_summary* summary) {
+  TBV_REQUIRE(ctx && scans && n_cells && T && params && n_scans >= 2, "bad arguments");
+  RegResult r;
+  int rc = run_single(ctx, REG_MODE_REGISTER, 0, n_scans, scans, n_cells, T, params, &r, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  fill_summary(r, summary);
+  // Register writes Tsrc[i] = vectorToAffine(parameters[i]) for every scan after a successful solve; read back through
+  // Affine3dToVectorXYeZ the angles come out as atan2(sin, cos) (registration.cpp:129-135, utils.cpp:115-122)
+  if (r.pose_updated) {
+    for (int i = 0; i < n_scans; i++) {
+      double* t = T + 3 * i;
+      const double th = (i == n_scans - 1) ? r.pose[2] : t[2];
+      if (i == n_scans - 1) { t[0] = r.pose[0]; t[1] = r.pose[1]; }
+      t[2] = std::atan2(std::sin(th), std::cos(th));
+    }
+  }
+  return TBV_OK;
+}
+
+int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T, const tbv_reg_params* params,
+                 int itr, double* score, double* cost, int* n_res, double* residuals, int res_capacity) {
+  TBV_REQUIRE(ctx && scans && n_cells && T && params && n_scans >= 2, "bad arguments");
+  RegResult r;
+  double ev[NACC];
+  std::vector<double> res;
+  int rc = run_single(ctx, REG_MODE_EVAL, itr, n_scans, scans, n_cells, T, params, &r, ev, nullptr, residuals ? &res : nullptr, nullptr);
+  if (rc) return rc;
+  if (n_res) *n_res = r.num_residuals > 1 ? r.num_residuals : -1;  // GetCost returns false when <= 1 residual
+  if (cost) *cost = ev[0];
+  if (score) *score = r.score;
+  if (residuals)
+    for (int i = 0; i < (int)res.size() && i < res_capacity; i++) residuals[i] = res[i];
+  return TBV_OK;
+}
+
+int tbv_register_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, const int* n_cells, int n_pairs, const int* from_set,
+                       const int* to_set, const double* T_from, const double* T_to, const tbv_reg_params* params, double* T_revised,
+                       double* T_align, tbv_reg_summary* summaries) {
+  TBV_REQUIRE(ctx && sets && n_cells && from_set && to_set && T_from && T_to && params && n_sets >= 1 && n_pairs >= 0, "bad arguments");
+  if (n_pairs == 0) return TBV_OK;
+  HostProblemSet hs;
+  hs.ctx = ctx;
+  int rc = hs.upload(n_sets, sets, n_cells);
+  if (rc) return rc;
+  std::vector<RegProblem> hp(n_pairs);
+  std::vector<int> hfs(n_pairs);
+  std::vector<double> hfp((size_t)n_pairs * 3);
+  for (int p = 0; p < n_pairs; p++) {
+    TBV_REQUIRE(from_set[p] >= 0 && from_set[p] < n_sets && to_set[p] >= 0 && to_set[p] < n_sets, "pair indexes a missing set");
+    hp[p].n_fixed = 1; hp[p].fixed_first = p; hp[p].src_set = from_set[p]; hp[p].active = 1;
+    hfs[p] = to_set[p];
+    for (int c = 0; c < 3; c++) { hp[p].src_pose[c] = T_from[3 * p + c]; hfp[3 * p + c] = T_to[3 * p + c]; }
+  }
+  DevBuf<RegProblem> dp; DevBuf<int> dfs; DevBuf<double> dfp; DevBuf<RegResult> dr;
+  auto cleanup = [&]() { dp.release(); dfs.release(); dfp.release(); dr.release(); };
+  if ((rc = to_device(ctx, dp, hp)) || (rc = to_device(ctx, dfs, hfs)) || (rc = to_device(ctx, dfp, hfp)) || (rc = dr.reserve(n_pairs))) {
+    cleanup();
+    return rc;
+  }
+  rc = register_launch(ctx, REG_MODE_REGISTER, 0, hs.views.p, dp.p, dfs.p, dfp.p, n_pairs, 1, hs.max_n, hs.max_n, to_dev(*params), dr.p, nullptr,
+                       false);
+  if (rc) { cleanup(); return rc; }
+  std::vector<RegResult> hr(n_pairs);
+  cudaError_t e = cudaMemcpyAsync(hr.data(), dr.p, n_pairs * sizeof(RegResult), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e != cudaSuccess) { set_error("tbv_register_batch: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  for (int p = 0; p < n_pairs; p++) {
+    const RegResult& r = hr[p];
+    if (T_revised) {
+      // T_vek.back() read through Affine3dToVectorXYeZ; untouched input when no solve succeeded
+      T_revised[3 * p + 0] = r.pose_updated ? r.pose[0] : T_from[3 * p + 0];
+      T_revised[3 * p + 1] = r.pose_updated ? r.pose[1] : T_from[3 * p + 1];
+      const double th = r.pose_updated ? r.pose[2] : T_from[3 * p + 2];
+      T_revised[3 * p + 2] = std::atan2(std::sin(th), std::cos(th));
+    }
+    if (T_align) for (int c = 0; c < 3; c++) T_align[3 * p + c] = r.align[c];
+    if (summaries) fill_summary(r, summaries + p);
+  }
+  return TBV_OK;
+}
+
+}  // extern "C"

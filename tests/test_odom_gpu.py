@@ -1,0 +1,94 @@
+"""End-to-end odometry parity: radarDriver::Process + OdometryKeyframeFuser::processFrame on the GPU (batched over
+sequences, state on the device) vs the oracle run sequence by sequence on the same scans.
+
+Bar (north_star): poses within 1e-5 m / 1e-6 rad; point counts, cell counts, association iterations and the keyframe
+decisions identical.
+"""
+import numpy as np
+import pytest
+
+from tbv_slam_public_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, ANG_TOL = 1e-5, 1e-6
+
+
+def _ang(d):
+    return np.abs(np.arctan2(np.sin(d), np.cos(d)))
+
+
+def _run_pair(ctx, oracle, scans_per_seq, gkw, okw):
+    n_seq, n_frames = len(scans_per_seq), len(scans_per_seq[0])
+    n_az, n_range = scans_per_seq[0][0].shape
+    fuser = api.OdometryKeyframeFuser(ctx, n_seq, n_az, n_range, api.default_odom_params(**gkw))
+    refs = [oracle.Odometry(oracle.default_odom_params(**okw)) for _ in range(n_seq)]
+    for f in range(n_frames):
+        batch = np.stack([scans_per_seq[s][f] for s in range(n_seq)])
+        outs = fuser.pointcloudCallback(batch)
+        for s in range(n_seq):
+            r = refs[s].step(scans_per_seq[s][f])
+            g = outs[s]
+            assert g.status == 0
+            assert (g.n_points, g.n_cells, g.itrs, g.is_keyframe, g.n_keyframes, g.reg_ok) == \
+                   (r.n_points, r.n_cells, r.itrs, r.is_keyframe, r.n_keyframes, r.reg_ok), f"frame {f} seq {s}"
+            assert abs(g.pose[0] - r.pose[0]) < POS_TOL and abs(g.pose[1] - r.pose[1]) < POS_TOL, f"frame {f} seq {s}"
+            assert _ang(g.pose[2] - r.pose[2]) < ANG_TOL, f"frame {f} seq {s}"
+    # keyframe window parity at the end
+    for s in range(n_seq):
+        poses, nc = refs[s].keyframes()
+        for i in range(len(poses)):
+            cells, pose = fuser.cells(s, i)
+            assert len(cells) == nc[i]
+            assert np.abs(pose[:2] - poses[i][:2]).max() < POS_TOL and _ang(pose[2] - poses[i][2]) < ANG_TOL
+            ref_cells = refs[s].keyframe_cells(i)
+            assert np.allclose(cells[:, :2], ref_cells[:, :2], rtol=0, atol=1e-9)
+    fuser.close()
+
+
+def test_odometry_baseline_config(ctx, oracle):
+    """BASELINE config 2: CFEAR-3 filter, 4 keyframes, P2L, Huber 0.1, combined weights — two sequences in lock-step."""
+    a = synth.make_stream(14, s0=0.0)
+    b = synth.make_stream(14, s0=300.0, seed=99)
+    _run_pair(ctx, oracle, [list(a.scans), list(b.scans)], {}, {})
+
+
+def test_odometry_cfear1_p2l_one_keyframe(ctx, oracle, stream8):
+    g = dict(submap_scan_size=1, weight_intensity=0, res=3.5)
+    gp = api.default_odom_params(**g)
+    gp.filter.k_strongest = 12
+    gp.filter.z_min = 70.0
+    fuser_kw = dict(submap_scan_size=1, weight_intensity=0, res=3.5, filter=gp.filter)
+    _run_pair(ctx, oracle, [list(stream8.scans)], fuser_kw, dict(submap_scan_size=1, weight_intensity=0, res=3.5, k_strongest=12, z_min=70.0))
+
+
+def test_odometry_p2p_and_slow_motion_keyframes(ctx, oracle):
+    """P2P cost (the CFEAR-3 preset) on a slow stream: most frames are NOT keyframes, the window is reused."""
+    st = synth.make_stream(10, speed=2.0)
+    rp = api.default_reg_params(cost=api.P2P, weight_opt=api.W_COMBINED, regularization=1.0)
+    _run_pair(ctx, oracle, [list(st.scans)], dict(reg=rp), dict(cost_type=oracle.P2P))
+
+
+def test_pipelined_submit_collect_matches_sync(ctx):
+    st = synth.make_stream(6)
+    n_seq = 3
+    p = api.default_odom_params()
+    f1 = api.OdometryKeyframeFuser(ctx, n_seq, 400, 3768, p)
+    sync = []
+    for f in range(6):
+        batch = np.stack([st.scans[(f + s) % 6] for s in range(n_seq)])
+        sync.append(api.poses(f1.pointcloudCallback(batch)).copy())
+    f1.close()
+    f2 = api.OdometryKeyframeFuser(ctx, n_seq, 400, 3768, p)
+    bufs = [api.PinnedBuffer(n_seq * 400 * 3768) for _ in range(2)]
+    got = []
+    for f in range(6):
+        batch = np.stack([st.scans[(f + s) % 6] for s in range(n_seq)])
+        bufs[f & 1].array[:] = batch.reshape(-1)
+        f2.submit(bufs[f & 1].ptr)
+        if f >= 1:
+            got.append(api.poses(f2.collect()).copy())
+    got.append(api.poses(f2.collect()).copy())
+    f2.close()
+    for a, b in zip(sync, got):
+        assert np.array_equal(a, b)

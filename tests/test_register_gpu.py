@@ -1,0 +1,114 @@
+"""K4/K5 parity: correspondences + cost / J^T J / J^T r, GetCost, Register and batched loop registrations vs the oracle.
+
+Bar: associations bit-exact (index work); cost / gradient / Hessian within 1e-12 relative (the reduction order differs:
+the reference sums sequentially, the kernel in a fixed tree); registered poses within 1e-5 m / 1e-6 rad (north_star),
+with the same number of association and LM iterations.
+"""
+import numpy as np
+import pytest
+
+from tbv_slam_public_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, ANG_TOL = 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module")
+def cellsets(oracle, stream8):
+    sets = []
+    for i in range(6):
+        az, rg, I, x, y = oracle.kstrongest(stream8.scans[i])["filtered"]
+        c, _ = oracle.build_cells(x, y, I.astype(np.float32), radius=3.0, weight_intensity=True)
+        sets.append(c)
+    return sets
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _ang(a, b):
+    d = a - b
+    return abs(np.arctan2(np.sin(d), np.cos(d)))
+
+
+@pytest.mark.parametrize("cost", [api.P2L, api.P2P, api.P2D])
+@pytest.mark.parametrize("loss,wopt", [(api.HUBER, api.W_COMBINED), (api.CAUCHY, api.W_UNIFORM), (api.LOSS_NONE, api.W_SIM_N),
+                                       (api.TUKEY, api.W_SIM_DIR), (api.SOFTLONE, api.W_SIM_SCALE), (api.COMBINED, api.W_UNIFORM)])
+def test_pair_normal_eq(ctx, oracle, cellsets, cost, loss, wopt):
+    tgt, src = cellsets[0], cellsets[1]
+    Tt, Ts = (0.0, 0.0, 0.0), (2.4, 0.05, 0.003)
+    for itr in (1, 2):
+        kw = dict(cost=cost, loss=loss, weight_opt=wopt, loss_limit=0.1, cov_scale=1.0, regularization=0.1)
+        ref = oracle.pair_normal_eq(tgt, Tt, src, Ts, oracle.default_reg_params(**kw), itr=itr)
+        got = ctx.pair_normal_eq(tgt, Tt, src, Ts, api.default_reg_params(**kw), itr=itr)
+        assert np.array_equal(ref["assoc"], got["assoc"])
+        assert ref["n_res"] == got["n_res"] and ref["n_res"] > 50
+        assert abs(ref["cost"] - got["cost"]) <= 1e-12 * abs(ref["cost"])
+        assert _rel(got["g"], ref["g"]) < 1e-11
+        assert _rel(got["H"], ref["H"]) < 1e-12
+
+
+def test_get_cost(ctx, oracle, cellsets):
+    scans = [cellsets[0], cellsets[1], cellsets[2]]
+    T = [(0, 0, 0), (2.5, 0, 0), (5.05, -0.04, -0.006)]
+    for itr in (0, 1):
+        kw = dict(cost=api.P2L, loss=api.HUBER, loss_limit=0.3)
+        n, score, cost, res = oracle.get_cost(scans, T, oracle.default_reg_params(**kw), itr=itr)
+        gn, gscore, gcost, gres = ctx.GetCost(scans, T, api.default_reg_params(**kw), itr=itr)
+        assert n == gn and n > 100
+        assert abs(cost - gcost) <= 1e-12 * cost and abs(score - gscore) <= 1e-12 * score
+        assert np.allclose(res, gres, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("cost,loss,wopt", [(api.P2L, api.HUBER, api.W_COMBINED), (api.P2P, api.HUBER, api.W_COMBINED),
+                                            (api.P2D, api.CAUCHY, api.W_COMBINED), (api.P2L, api.CAUCHY, api.W_UNIFORM)])
+def test_register_multi_keyframe(ctx, oracle, stream8, cellsets, cost, loss, wopt):
+    """scan 4 against keyframes 0..3 placed at the ground-truth poses, perturbed initial guess."""
+    gt = stream8.gt
+    T = [tuple(gt[i]) for i in range(4)] + [(gt[4][0] + 0.4, gt[4][1] - 0.3, gt[4][2] + 0.02)]
+    scans = cellsets[:5]
+    kw = dict(cost=cost, loss=loss, weight_opt=wopt, loss_limit=0.1, cov_scale=1.0, regularization=0.1)
+    Tr, sr = oracle.register(scans, T, oracle.default_reg_params(**kw))
+    Tg, sg = ctx.Register(scans, T, api.default_reg_params(**kw))
+    assert sr.success == 1 and sg.success == 1
+    assert (sr.itrs, sr.lm_iterations, sr.num_residuals, sr.last_n_iterations, sr.termination) == \
+           (sg.itrs, sg.lm_iterations, sg.num_residuals, sg.last_n_iterations, sg.termination)
+    assert np.abs(Tr[-1, :2] - Tg[-1, :2]).max() < POS_TOL and _ang(Tr[-1, 2], Tg[-1, 2]) < ANG_TOL
+    assert abs(sr.score - sg.score) <= 1e-9 * abs(sr.score)
+    # the estimate is near the ground truth (sanity of the whole chain, not a parity statement)
+    assert np.abs(Tg[-1, :2] - gt[4][:2]).max() < 0.5
+
+
+def test_register_failure_and_empty(ctx, oracle, cellsets):
+    far = [(0, 0, 0), (500.0, 500.0, 1.0)]  # no correspondences -> BuildOptimizationProblem fails
+    Tr, sr = oracle.register(cellsets[:2], far)
+    Tg, sg = ctx.Register(cellsets[:2], far)
+    assert sr.success == 0 and sg.success == 0 and sr.itrs == sg.itrs
+    assert np.allclose(Tr, Tg, atol=1e-12)
+    empty = np.zeros((0, 16))
+    Tg, sg = ctx.Register([cellsets[0], empty], [(0, 0, 0), (1, 0, 0)])
+    assert sg.success == 0
+
+
+def test_register_batch_loop_candidates(ctx, oracle, stream8, cellsets):
+    """loopclosure::Register for a batch of (from, to) pairs with initial errors of the Scan-Context scale."""
+    rng = np.random.default_rng(3)
+    gt = stream8.gt
+    fs, ts, Tf, Tt = [], [], [], []
+    for _ in range(24):
+        a, b = rng.choice(6, 2, replace=False)
+        err = np.array([rng.uniform(-1.5, 1.5), rng.uniform(-1.5, 1.5), rng.uniform(-0.1, 0.1)])
+        fs.append(a); ts.append(b); Tf.append(gt[a] + err); Tt.append(gt[b])
+    Tr, Ta, summ = ctx.RegisterBatch(cellsets, fs, ts, Tf, Tt)
+    n_ok = 0
+    for p in range(24):
+        ok, Ta_ref, Tr_ref, itrs, score = oracle.loop_register(cellsets[fs[p]], cellsets[ts[p]], Tf[p], Tt[p])
+        assert bool(summ[p].success) == ok and summ[p].itrs == itrs
+        assert np.abs(Tr_ref[:2] - Tr[p, :2]).max() < POS_TOL and _ang(Tr_ref[2], Tr[p, 2]) < ANG_TOL
+        if ok:
+            n_ok += 1
+            assert np.abs(Ta_ref[:2] - Ta[p, :2]).max() < POS_TOL and _ang(Ta_ref[2], Ta[p, 2]) < ANG_TOL
+            assert abs(score - summ[p].score) <= 1e-9 * abs(score)
+    assert n_ok >= 20
