@@ -128,7 +128,7 @@ typedef struct tbv_odom_out {   /* one per sequence per step */
   int n_points, n_cells, itrs, reg_ok, is_keyframe, n_keyframes;
   int lm_iterations, num_residuals;
   int status;               /* TBV_OK, or TBV_ERR_CAPACITY when a per-scan capacity was exceeded (results then unreliable) */
-  int reserved;
+  int n_samples;            /* voxel-grid sample points examined for this scan */
   double score;
 } tbv_odom_out;
 
@@ -143,6 +143,11 @@ int tbv_synchronize(tbv_ctx* ctx);
 /* number of kernel launches issued by this library since the context was created */
 long long tbv_launch_count(tbv_ctx* ctx);
 int tbv_version(void);
+/* Per-launch device timing (the reference's CFEAR_Radarodometry::timing, statistics.h:38, keyed by kernel): after
+ * tbv_profile_begin every kernel launch of this context is followed by an event record; tbv_profile_end synchronises and
+ * returns, in launch order, the kernel names (static strings) and the milliseconds between consecutive events. */
+int tbv_profile_begin(tbv_ctx* ctx);
+int tbv_profile_end(tbv_ctx* ctx, int capacity, const char** names, float* ms, int* n);
 
 /* ---- K1: k-strongest filter -------------------------------------------------------------------------------------
  * Replaces StructuredKStrongest::StructuredKStrongest + FilterKstrongest + AxialNonMaxSupress +

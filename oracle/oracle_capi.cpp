@@ -339,6 +339,42 @@ double orc_odom_run(const orc_odom_params* p, const uint8_t* pool, int n_pool, i
   return std::chrono::duration<double>(clk::now() - t0).count();
 }
 
+// Same, timing only the frames after the first n_warm of every sequence (the GPU arm's warm-up steps): each thread sums the
+// wall time of its own timed frames; returns the maximum over threads (all threads are busy throughout), i.e. the time in
+// which n_seq * (n_frames - n_warm) scans were registered.  thread_seconds (optional, n_threads entries) receives the sums.
+double orc_odom_run_timed(const orc_odom_params* p, const uint8_t* pool, int n_pool, int n_az, int n_range, int n_seq, const int* first,
+                          int n_warm, int n_frames, int n_threads, double* poses, double* thread_seconds) {
+  using clk = std::chrono::steady_clock;
+  std::atomic<int> next(0);
+  const size_t scan_bytes = (size_t)n_az * n_range;
+  const int nt = std::max(1, n_threads);
+  std::vector<double> acc(nt, 0.0);
+  auto worker = [&](int tid) {
+    for (;;) {
+      const int s = next.fetch_add(1);
+      if (s >= n_seq) break;
+      OdomHandle h;
+      h.p = *p;
+      OdometryKeyframeFuser fuser(ToFuser(*p));
+      h.fuser = &fuser;
+      for (int f = 0; f < n_frames; f++) {
+        const int idx = (first[s] + f) % n_pool;
+        orc_odom_out o;
+        const auto t0 = clk::now();
+        OdomStep(&h, pool + scan_bytes * idx, n_az, n_range, n_range, &o);
+        if (f >= n_warm) acc[tid] += std::chrono::duration<double>(clk::now() - t0).count();
+        if (poses) std::memcpy(poses + ((size_t)s * n_frames + f) * 3, o.pose, 3 * sizeof(double));
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < nt; i++) th.emplace_back(worker, i);
+  for (auto& t : th) t.join();
+  double mx = 0.0;
+  for (int i = 0; i < nt; i++) { mx = std::max(mx, acc[i]); if (thread_seconds) thread_seconds[i] = acc[i]; }
+  return mx;
+}
+
 // ---- Ceres-restated pieces exposed for unit tests ------------------------------------------------
 void orc_loss(int loss, double loss_limit, double weight, double s, double rho[3]) { ceres_restated::ScaledLoss(loss, loss_limit, weight, s, rho); }
 

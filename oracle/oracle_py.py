@@ -115,6 +115,7 @@ def lib():
         L.orc_loop_register.restype = C.c_int
         L.orc_odom_create.restype = C.c_void_p
         L.orc_odom_run.restype = C.c_double
+        L.orc_odom_run_timed.restype = C.c_double
         L.orc_odom_keyframes.restype = C.c_int
         L.orc_odom_keyframe_cells.restype = C.c_int
         L.orc_rsc_create.restype = C.c_void_p
@@ -308,6 +309,16 @@ def odom_run(params: OdomParams, pool: np.ndarray, first, n_frames: int, n_threa
     poses = np.zeros((len(first), n_frames, 3))
     sec = lib().orc_odom_run(C.byref(params), _p(pool, C.c_uint8), pool.shape[0], pool.shape[1], pool.shape[2], len(first),
                              _p(first, C.c_int), n_frames, n_threads, _p(poses, C.c_double))
+    return sec, poses
+
+
+def odom_run_timed(params: OdomParams, pool: np.ndarray, first, n_warm: int, n_frames: int, n_threads: int):
+    """Like odom_run but times only frames >= n_warm of every sequence. Returns (max-over-threads timed seconds, poses)."""
+    pool = np.ascontiguousarray(pool, np.uint8)
+    first = np.ascontiguousarray(first, np.int32)
+    poses = np.zeros((len(first), n_frames, 3))
+    sec = lib().orc_odom_run_timed(C.byref(params), _p(pool, C.c_uint8), pool.shape[0], pool.shape[1], pool.shape[2], len(first),
+                                   _p(first, C.c_int), n_warm, n_frames, n_threads, _p(poses, C.c_double), None)
     return sec, poses
 
 

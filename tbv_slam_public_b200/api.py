@@ -65,7 +65,7 @@ class OdomParams(C.Structure):
 class OdomOut(C.Structure):
     _fields_ = [("pose", C.c_double * 3), ("n_points", C.c_int), ("n_cells", C.c_int), ("itrs", C.c_int), ("reg_ok", C.c_int),
                 ("is_keyframe", C.c_int), ("n_keyframes", C.c_int), ("lm_iterations", C.c_int), ("num_residuals", C.c_int),
-                ("status", C.c_int), ("reserved", C.c_int), ("score", C.c_double)]
+                ("status", C.c_int), ("n_samples", C.c_int), ("score", C.c_double)]
 
 
 def default_reg_params(**kw) -> RegParams:
@@ -100,6 +100,8 @@ def lib():
         L.tbv_synchronize.argtypes = [C.c_void_p]
         L.tbv_launch_count.restype = C.c_longlong
         L.tbv_launch_count.argtypes = [C.c_void_p]
+        L.tbv_profile_begin.argtypes = [C.c_void_p]
+        L.tbv_profile_end.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tbv_host_alloc.restype = C.c_void_p
         L.tbv_host_alloc.argtypes = [C.c_size_t]
         L.tbv_host_free.argtypes = [C.c_void_p]
@@ -201,6 +203,17 @@ class Context:
 
     def launch_count(self) -> int:
         return lib().tbv_launch_count(self.h)
+
+    def profile_begin(self):
+        _check(lib().tbv_profile_begin(self.h))
+
+    def profile_end(self, capacity=4096):
+        """-> list of (kernel name, ms) in launch order since profile_begin."""
+        names = (C.c_char_p * capacity)()
+        ms = (C.c_float * capacity)()
+        n = C.c_int(0)
+        _check(lib().tbv_profile_end(self.h, capacity, names, ms, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n.value, capacity))]
 
     # ---- radarDriver::Process (k-strongest branch) -----------------------------------------------------------
     def StructuredKStrongest(self, polar: np.ndarray, z_min=60.0, k_strongest=40, min_distance=2.5, range_res=0.0438,

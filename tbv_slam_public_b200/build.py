@@ -51,5 +51,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+
+
+def _exports():
+    """Every function include/tbv_b200.h declares — the C-ABI the library must export."""
+    import re
+    hdr = open(os.path.join(HERE, "..", "include", "tbv_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(tbv_[a-z0-9_]+)\s*\(", hdr)))
+
+
+EXPORTS = _exports()
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

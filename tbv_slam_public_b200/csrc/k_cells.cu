@@ -541,22 +541,27 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
   TBV_CUDA(cudaMemsetAsync(S.vox_fill.p, 0, (size_t)batch * vox_cap * sizeof(int), st));
   TBV_CUDA(cudaMemsetAsync(S.err.p, 0, (size_t)batch * sizeof(int), st));
   c1_grid<<<batch, 256, 0, st>>>(x, y, count_dev, cap_pts, leaf, vox_cap, S.grid.p, S.vox_idx.p, S.vox_start.p);
+  launched(ctx, "c1_grid");
   c2_scan<<<batch, 1024, 0, st>>>(S.grid.p, vox_cap, max_samples, S.vox_start.p, S.sample_vox.p, out.n_samples.p, S.err.p);
+  launched(ctx, "c2_scan");
   {
     dim3 g((cap_pts + 255) / 256 < 64 ? (cap_pts + 255) / 256 : 64, batch);
     c3_scatter<<<g, 256, 0, st>>>(S.grid.p, count_dev, cap_pts, vox_cap, S.vox_idx.p, S.vox_start.p, S.vox_fill.p, S.sorted_raw.p);
+    launched(ctx, "c3_scatter");
   }
   {
     const int gx = (max_samples + 3) / 4 < 512 ? (max_samples + 3) / 4 : 512;
     c4_centroids<<<dim3(gx, batch), 128, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, S.sample_vox.p, S.vox_start.p,
                                                   S.sorted_raw.p, S.sorted.p, S.cx.p, S.cy.p);
+    launched(ctx, "c4_centroids");
     const int g5 = (max_samples + C5_WARPS - 1) / C5_WARPS < 512 ? (max_samples + C5_WARPS - 1) / C5_WARPS : 512;
     c5_cells<<<dim3(g5, batch), C5_WARPS * 32, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, inten_u8, inten_f32,
                                                         S.vox_start.p, S.sorted.p, S.cx.p, S.cy.p, par.radius, par.weight_intensity,
                                                         par.origin[0], par.origin[1], S.cand.p, S.cand_valid.p, S.err.p);
+    launched(ctx, "c5_cells");
   }
   c6_compact<<<batch, 256, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, S.cand.p, S.cand_valid.p, out.f64.p, cell_cap, out.count.p, S.err.p);
-  ctx->launches += 6;
+  launched(ctx, "c6_compact");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
 }
@@ -577,7 +582,7 @@ int cells_upload(tbv_ctx* ctx, const tbv_cell* cells, int n, double* set_dev, in
   TBV_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * sizeof(tbv_cell), ctx->stream));
   TBV_CUDA(cudaMemcpyAsync(tmp, cells, (size_t)n * sizeof(tbv_cell), cudaMemcpyHostToDevice, ctx->stream));
   k_cells_aos_to_soa<<<(n + 127) / 128, 128, 0, ctx->stream>>>(tmp, n, set_dev, cap);
-  ctx->launches++;
+  launched(ctx, "cells_aos_to_soa");
   TBV_CUDA(cudaFreeAsync(tmp, ctx->stream));
   return TBV_OK;
 }
@@ -586,7 +591,7 @@ int cells_download(tbv_ctx* ctx, const double* set_dev, int cap, int n, tbv_cell
   double* tmp = nullptr;
   TBV_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * sizeof(tbv_cell), ctx->stream));
   k_cells_soa_to_aos<<<(n + 127) / 128, 128, 0, ctx->stream>>>(set_dev, cap, n, tmp);
-  ctx->launches++;
+  launched(ctx, "cells_soa_to_aos");
   TBV_CUDA(cudaMemcpyAsync(cells, tmp, (size_t)n * sizeof(tbv_cell), cudaMemcpyDeviceToHost, ctx->stream));
   TBV_CUDA(cudaFreeAsync(tmp, ctx->stream));
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));

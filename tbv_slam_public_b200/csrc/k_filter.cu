@@ -417,7 +417,7 @@ __global__ void k_compensate(float* __restrict__ x, float* __restrict__ y, const
 // --------------------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------------------
-static int ensure_cs_table(tbv_ctx* ctx, int n_az) {
+int ensure_cs_table(tbv_ctx* ctx, int n_az) {
   FilterState& F = ctx->filt;
   if (F.cs_n_az == n_az) return TBV_OK;
   int rc = F.cs_table.reserve(n_az);
@@ -469,7 +469,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   }
   k1_kstrongest<<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
                                                              F.row_keys.p, F.row_cnt.p);
-  ctx->launches++;
+  launched(ctx, "k1_kstrongest");
   TBV_CUDA(cudaGetLastError());
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
   const int min_range_bin = (int)std::ceil((double)p->min_distance / rr);   // radar_filters.cpp:315
@@ -478,7 +478,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
                                                     F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, F.filtered.az.p, F.filtered.rg.p,
                                                     F.filtered.count.p, want_peaks, F.peaks.x.p, F.peaks.y.p, F.peaks.inten.p, F.peaks.az.p,
                                                     F.peaks.rg.p, F.peaks.count.p);
-  ctx->launches++;
+  launched(ctx, "k2_make_clouds");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
 }
@@ -486,12 +486,12 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
 int compensate_clouds_dev(tbv_ctx* ctx, DevCloud& c, const double* mot_dev, int ccw) {
   dim3 grid((c.cap + 255) / 256 < 32 ? (c.cap + 255) / 256 : 32, c.batch);
   k_compensate<<<grid, 256, 0, ctx->stream>>>(c.x.p, c.y.p, c.count.p, c.cap, mot_dev, ccw);
-  ctx->launches++;
+  launched(ctx, "k_compensate");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
 }
 
-static int fetch_cloud(tbv_ctx* ctx, const DevCloud& d, int batch, tbv_points* out) {
+int fetch_cloud(tbv_ctx* ctx, const DevCloud& d, int batch, tbv_points* out) {
   if (!out) return TBV_OK;
   TBV_REQUIRE(out->capacity > 0 && out->count, "tbv_points needs capacity and count");
   std::vector<int> cnt(batch);
@@ -559,7 +559,7 @@ int tbv_compensate(tbv_ctx* ctx, float* x, float* y, int n, const double mot_xyt
   if (e == cudaSuccess) {
     dim3 grid((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024, 1);
     k_compensate<<<grid, 256, 0, ctx->stream>>>(dx.p, dy.p, nullptr, n, dm.p, ccw);
-    ctx->launches++;
+    launched(ctx, "k_compensate");
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(x, dx.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);

@@ -14,6 +14,19 @@ void set_error(const char* fmt, ...) {
   g_err = buf;
 }
 
+void prof_mark(tbv_ctx* ctx, const char* name) {
+  Prof& P = ctx->prof;
+  if ((int)P.ev.size() <= P.n) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    P.ev.push_back(e);
+    P.names.push_back(name);
+  }
+  P.names[P.n] = name;
+  cudaEventRecord(P.ev[P.n], ctx->stream);
+  P.n++;
+}
+
 // dst(i, j) = src(j, W-1-i): cv::rotate(ROTATE_90_COUNTERCLOCKWISE) as used at radar_driver.cpp:80-84.
 // 32x32 shared-memory tile transpose so both the read and the write are coalesced.
 __global__ void k_rotate90ccw(const uint8_t* __restrict__ src, int H, int W, uint8_t* __restrict__ dst) {
@@ -71,8 +84,36 @@ void tbv_destroy(tbv_ctx* ctx) {
   F.polar.release(); F.row_keys.release(); F.row_cnt.release(); F.cs_table.release(); F.filtered.release(); F.peaks.release();
   cells_release(ctx);
   reg_release(ctx);
+  for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+int tbv_profile_begin(tbv_ctx* ctx) {
+  TBV_REQUIRE(ctx, "null context");
+  ctx->prof.n = 0;
+  ctx->prof.on = true;
+  prof_mark(ctx, "begin");
+  return TBV_OK;
+}
+
+int tbv_profile_end(tbv_ctx* ctx, int capacity, const char** names, float* ms, int* n) {
+  TBV_REQUIRE(ctx && n, "null pointer");
+  Prof& P = ctx->prof;
+  P.on = false;
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  int m = 0;
+  for (int i = 1; i < P.n; i++) {
+    float t = 0.f;
+    TBV_CUDA(cudaEventElapsedTime(&t, P.ev[i - 1], P.ev[i]));
+    if (m < capacity) {
+      if (names) names[m] = P.names[i];
+      if (ms) ms[m] = t;
+    }
+    m++;
+  }
+  *n = m;
+  return TBV_OK;
 }
 
 void* tbv_stream(tbv_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -107,7 +148,7 @@ int tbv_rotate90ccw(tbv_ctx* ctx, const uint8_t* src, int rows, int cols, uint8_
   if (e == cudaSuccess) {
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
     k_rotate90ccw<<<grid, block, 0, ctx->stream>>>(a.p, rows, cols, b.p);
-    ctx->launches++;
+    launched(ctx, "k_rotate90ccw");
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(dst, b.p, n, cudaMemcpyDeviceToHost, ctx->stream);

@@ -114,7 +114,8 @@ __global__ void k_odom_problems(SeqState* __restrict__ st, int n_seq, OdomDevPar
 __global__ void __launch_bounds__(256)
 k_odom_update(SeqState* __restrict__ st, OdomDevParams P, const RegResult* __restrict__ results, const int* __restrict__ n_points,
               const double* __restrict__ cur_cells, const int* __restrict__ cur_count, int cell_cap, double* __restrict__ kf_cells,
-              int* __restrict__ kf_count, const int* __restrict__ cells_err, tbv_odom_out* __restrict__ outs) {
+              int* __restrict__ kf_count, const int* __restrict__ cells_err, const int* __restrict__ cur_samples,
+              tbv_odom_out* __restrict__ outs) {
   __shared__ int s_fuse_slot;
   const int s = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -175,6 +176,7 @@ k_odom_update(SeqState* __restrict__ st, OdomDevParams P, const RegResult* __res
     o.n_cells = cur_count[s];
     o.n_keyframes = S.n_kf;
     o.status = cells_err[s];
+    o.n_samples = cur_samples[s];
     outs[s] = o;
     s_fuse_slot = fuse_slot;
   }
@@ -254,7 +256,7 @@ static int odom_init(tbv_odom* od) {
   }
   TBV_CUDA(cudaMemcpyAsync(od->views.p, hv.data(), hv.size() * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
   k_odom_reset<<<(n_seq + 127) / 128, 128, 0, ctx->stream>>>(od->state.p, n_seq);
-  ctx->launches++;
+  launched(ctx, "k_odom_reset");
   TBV_CUDA(cudaGetLastError());
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   return TBV_OK;
@@ -270,7 +272,7 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   FilterState& F = ctx->filt;
   if (od->par.compensate) {
     k_odom_motion<<<(n_seq + 127) / 128, 128, 0, st>>>(od->state.p, n_seq, od->mot.p);
-    ctx->launches++;
+    launched(ctx, "k_odom_motion");
     if ((rc = compensate_clouds_dev(ctx, F.filtered, od->mot.p, od->par.radar_ccw))) return rc;
     if ((rc = compensate_clouds_dev(ctx, F.peaks, od->mot.p, od->par.radar_ccw))) return rc;
   }
@@ -278,13 +280,13 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
                             od->cell_cap, od->cur)))
     return rc;
   k_odom_problems<<<(n_seq + 127) / 128, 128, 0, st>>>(od->state.p, n_seq, od->dpar, od->problems.p, od->fixed_set.p, od->fixed_pose.p);
-  ctx->launches++;
+  launched(ctx, "k_odom_problems");
   if ((rc = register_launch(ctx, REG_MODE_REGISTER, 0, od->views.p, od->problems.p, od->fixed_set.p, od->fixed_pose.p, n_seq, od->K, od->cell_cap,
                             od->cell_cap, od->rpar, od->results.p, nullptr, false)))
     return rc;
   k_odom_update<<<n_seq, 256, 0, st>>>(od->state.p, od->dpar, od->results.p, F.filtered.count.p, od->cur.f64.p, od->cur.count.p, od->cell_cap,
-                                       od->kf.f64.p, od->kf.count.p, cells_err_dev(ctx), od->outs_dev.p);
-  ctx->launches++;
+                                       od->kf.f64.p, od->kf.count.p, cells_err_dev(ctx), od->cur.n_samples.p, od->outs_dev.p);
+  launched(ctx, "k_odom_update");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
 }
@@ -326,7 +328,7 @@ int tbv_odom_reset(tbv_odom* od) {
   od->n_submitted = od->n_collected = 0;
   TBV_CUDA(cudaMemsetAsync(od->kf.count.p, 0, (size_t)od->n_seq * od->K * sizeof(int), ctx->stream));
   k_odom_reset<<<(od->n_seq + 127) / 128, 128, 0, ctx->stream>>>(od->state.p, od->n_seq);
-  ctx->launches++;
+  launched(ctx, "k_odom_reset");
   TBV_CUDA(cudaGetLastError());
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   return TBV_OK;

@@ -761,7 +761,7 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   k_register<<<n_problems, RG_THREADS, smem, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                             slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
                                                             want_residuals ? S.residuals.p : nullptr);
-  ctx->launches++;
+  launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
 }

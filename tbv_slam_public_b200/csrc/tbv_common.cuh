@@ -90,18 +90,31 @@ struct FilterState {  // device-resident result of the last k-strongest call
   DevCloud filtered, peaks;
 };
 
+struct Prof {  // optional per-launch device timing: one event after every kernel launch (tbv_profile_begin/_end)
+  bool on = false;
+  int n = 0;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+};
+
 }  // namespace tbv
 
 struct tbv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  tbv::Prof prof;
   tbv::FilterState filt;
   void* cells_scratch = nullptr;  // tbv::CellsScratch (k_cells.cu)
   void* reg_scratch = nullptr;    // tbv::RegScratch (k_register.cu)
 };
 
 namespace tbv {
+void prof_mark(tbv_ctx* ctx, const char* name);  // k_misc.cu
+inline void launched(tbv_ctx* ctx, const char* name) {  // bookkeeping after every kernel launch of this library
+  ctx->launches++;
+  if (ctx->prof.on) prof_mark(ctx, name);
+}
 // implemented in k_filter.cu
 int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
                           const tbv_filter_params* params, int want_peaks);

@@ -112,3 +112,23 @@ def test_compensate(ctx, oracle, stream8):
         dy = np.abs(oy.view(np.int32).astype(np.int64) - gy.view(np.int32).astype(np.int64))
         assert dx.max() <= 1 and dy.max() <= 1, "compensation differs by more than 1 float ulp"
         assert (dx > 0).mean() < 1e-3 and (dy > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("w,g,pfa,zmin", [(40, 10, 0.01, 20.0), (100, 10, 1e-3, 20.0), (20, 0, 0.1, 0.0), (500, 2, 1e-4, 60.0)])
+def test_cacfar(ctx, oracle, stream8, w, g, pfa, zmin):
+    """K1b: CA-CFAR detections (azimuth, range, intensity) and x,y bit-exact vs the oracle, in the reference's order."""
+    for img in (stream8.scans[1], synth.stress_image("uniform", n_az=16, n_range=1000, seed=8)):
+        ref = oracle.cacfar(img, window_size=w, false_alarm_rate=pfa, nb_guard_cells=g, static_threshold=zmin)
+        out = ctx.AzimuthCACFAR(img, window_size=w, false_alarm_rate=pfa, nb_guard_cells=g, static_threshold=zmin)
+        _assert_same(ref, out.scan(0), "cfar")
+
+
+def test_cacfar_batch_and_row_ends(ctx, oracle):
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 60, size=(3, 8, 300), dtype=np.uint8)
+    img[:, :, :4] = 200     # bins whose trailing window is empty (0/0 -> rejected)
+    img[:, :, -5:] = 220    # bins whose leading window is clipped / empty
+    out = ctx.AzimuthCACFAR(img, window_size=10, nb_guard_cells=3, min_distance=0.0, static_threshold=20.0)
+    for b in range(3):
+        ref = oracle.cacfar(img[b], window_size=10, nb_guard_cells=3, min_distance=0.0, static_threshold=20.0)
+        _assert_same(ref, out.scan(b), f"cfar[{b}]")

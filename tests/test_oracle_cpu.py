@@ -1,0 +1,445 @@
+"""CPU tests (no GPU): the oracle against independent restatements and analytic identities, plus the C-ABI surface.
+
+The reference ships no golden vectors for this path ("parity unpinned"), so the oracle is pinned by
+(i) a second, independent numpy restatement of the integer parts, (ii) analytic identities (finite-difference Jacobians,
+known-transform recovery, eigen-decomposition vs LAPACK, scipy least-squares on the same problem), (iii) named regression
+tests for the reference quirks the oracle deliberately keeps.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+
+from tbv_slam_public_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# independent numpy restatement of radar_filters.cpp:198-337
+# ---------------------------------------------------------------------------------------------------------------
+def np_kstrongest(img, z_min=60, k=40, min_distance=2.5, range_res=0.0438):
+    n_az, n_r = img.shape
+    rr = float(np.float32(range_res))
+    mrb = int(math.ceil(float(np.float32(min_distance)) / rr))
+    flat = img.reshape(-1).astype(np.int64)
+    total = flat.size
+    out, peaks = [], []
+    for b in range(n_az):
+        row = img[b].astype(np.int64)
+        idx = np.nonzero(row >= z_min)[0]
+        key = row[idx] * 65536 + idx
+        sel = np.sort(key)[-k:] if len(key) else key
+        kept_r = (sel % 65536).astype(int)
+        kept_i = (sel // 65536).astype(int)
+        theta = (float(b + 1) / n_az) * 2.0 * math.pi
+        c, s = math.cos(theta), math.sin(theta)
+        # scores exist only around kept bins inside the guard band
+        have = set()
+        for r in kept_r:
+            if 3 <= r < n_r - 3:
+                have.update(range(r - 3, r + 4))
+
+        def score(r):
+            if r not in have:
+                return 0
+            tot = 0
+            for q in range(r - 3, r + 4):
+                f = b * n_r + q
+                tot += int(flat[f]) if 0 <= f < total else 0
+            return tot & 0xFFFF
+        for I, r in zip(kept_i, kept_r):
+            x = np.float32((rr / 2.0 + rr * r) * c)
+            y = np.float32((rr / 2.0 + rr * r) * s)
+            if r > mrb:
+                out.append((b, r, I, x, y))
+            ok = all(not (score(r - i) > score(r) or score(r) < score(r + i)) for i in (1, 2, 3))
+            if ok and r > mrb:
+                peaks.append((b, r, I, x, y))
+    return out, peaks
+
+
+def _as_tuples(res):
+    az, rg, I, x, y = res
+    return [(int(a), int(r), int(i), np.float32(xx), np.float32(yy)) for a, r, i, xx, yy in zip(az, rg, I, x, y)]
+
+
+@pytest.mark.parametrize("kind", ["radar", "uniform", "equal", "ramp", "sparse"])
+def test_kstrongest_oracle_vs_numpy(oracle, kind):
+    if kind == "radar":
+        img = synth.make_stream(1).scans[0][:64]
+    else:
+        img = synth.stress_image(kind, n_az=24, n_range=512, seed=4)
+    for k, z in [(12, 70), (40, 60), (5, 0)]:
+        ref = oracle.kstrongest(img, z_min=float(z), k=k, min_distance=0.3)
+        f, p = np_kstrongest(img, z_min=z, k=k, min_distance=0.3)
+        assert _as_tuples(ref["filtered"]) == f
+        assert _as_tuples(ref["peaks"]) == p
+
+
+def test_min_range_bin_float_widening_quirk(oracle):
+    """MulRan: 2.5 / (double)(float)0.0595238 = 42.0000078 -> ceil = 43, not 42."""
+    img = np.zeros((4, 128), np.uint8)
+    img[:, 42] = 200
+    img[:, 43] = 201
+    img[:, 44] = 202
+    az, rg, I, x, y = oracle.kstrongest(img, z_min=60.0, k=12, min_distance=2.5, range_res=0.0595238)["filtered"]
+    assert set(rg.tolist()) == {44}
+    az, rg, I, x, y = oracle.kstrongest(img, z_min=60.0, k=12, min_distance=2.5, range_res=0.0438)["filtered"]
+    assert 58 == math.ceil(2.5 / float(np.float32(0.0438))) and len(rg) == 0
+
+
+def test_cacfar_vs_numpy(oracle):
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 90, size=(6, 400), dtype=np.uint8)
+    img[:, 150:153] = 220
+    img[2, 395:] = 250
+    w, g, pfa, rr, zmin, mind, maxd = 20, 4, 0.01, 0.0438, 20.0, 0.5, 400.0
+    az, rg, I, x, y = oracle.cacfar(img, window_size=w, false_alarm_rate=pfa, nb_guard_cells=g, range_res=rr, static_threshold=zmin,
+                                    min_distance=mind, max_distance=maxd)
+    N = 2 * w
+    scale = N * (pfa ** (-1.0 / N) - 1.0)
+    want = []
+    for b in range(6):
+        row = img[b].astype(np.float64)
+        for r in range(400):
+            rng_m = rr * r
+            if not (rng_m > mind and rng_m < maxd and row[r] > zmin):
+                continue
+            t = row[max(0, r - g - w):max(0, r - g)] ** 2
+            f = row[r + g:min(400, r + g + w)] ** 2
+            if len(t) == 0 or len(f) == 0:
+                continue
+            if row[r] ** 2 > scale * (t.mean() + f.mean()) / 2.0:
+                want.append((b, r))
+    assert list(zip(az.tolist(), rg.tolist())) == want and len(want) > 5
+
+
+def test_compensate_identity_and_pure_translation(oracle):
+    x = np.float32([10, -10, 0.5, -3]); y = np.float32([0.1, 5, -20, -0.2])
+    ox, oy = oracle.compensate(x, y, (0, 0, 0))
+    assert np.array_equal(ox, x) and np.array_equal(oy, y)
+    ox, oy = oracle.compensate(x, y, (1.0, 0.0, 0.0))
+    a = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    d = np.where(a > 1e-5, a, 2 * np.pi + a) / (2 * np.pi) - 0.5
+    assert np.allclose(ox, x + d, atol=1e-6) and np.allclose(oy, y, atol=1e-6)
+    cx, cy = oracle.compensate(x, y, (1.0, 0.0, 0.0), ccw=True)
+    assert np.allclose(cx, x - d, atol=1e-6)
+
+
+def test_eig2_vs_lapack(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a = rng.normal(size=(2, 2)) * 10 ** rng.uniform(-3, 3)
+        m = a @ a.T
+        ev, evec = oracle.eig2(m[0, 0], m[1, 0], m[1, 1])
+        w, v = np.linalg.eigh(m)
+        assert np.abs(ev - w).max() <= 1e-13 * abs(w[1])   # backward-stable: absolute error ~ eps * lambda_max
+        if w[1] / max(w[0], 1e-300) < 1e8:
+            for j in range(2):
+                assert abs(abs(evec[:, j] @ v[:, j]) - 1) < 1e-6
+    ev, evec = oracle.eig2(2.0, 0.0, 1.0)   # already diagonal: sorted ascending, columns swapped
+    assert np.array_equal(ev, [1.0, 2.0]) and np.array_equal(evec, [[0.0, 1.0], [1.0, 0.0]])
+
+
+@pytest.fixture(scope="module")
+def two_sets(oracle):
+    st = synth.make_stream(3)
+    sets = []
+    for i in range(3):
+        az, rg, I, x, y = oracle.kstrongest(st.scans[i])["filtered"]
+        c, ns = oracle.build_cells(x, y, I.astype(np.float32), radius=3.0, weight_intensity=True)
+        sets.append(c)
+    return st, sets
+
+
+def test_cells_statistics_vs_numpy(oracle):
+    st = synth.make_stream(1)
+    az, rg, I, x, y = oracle.kstrongest(st.scans[0])["filtered"]
+    I = I.astype(np.float32)
+    cells, ns = oracle.build_cells(x, y, I, radius=3.0, weight_intensity=True)
+    assert 100 < len(cells) < 1000 and ns >= len(cells)
+    # voxel-grid samples: independent numpy restatement of the centroid list
+    inv = np.float32(1.0) / np.float32(3.0)
+    ix = np.floor(x * inv) - np.floor(x.min() * inv)
+    iy = np.floor(y * inv) - np.floor(y.min() * inv)
+    div_x = int(np.floor(x.max() * inv) - np.floor(x.min() * inv)) + 1
+    vid = (ix + iy * div_x).astype(np.int64)
+    assert len(np.unique(vid)) == ns
+    cx, cy, ci = oracle.voxel_centroids(x, y, I, leaf=3.0)
+    order = np.argsort(vid, kind="stable")
+    u, start = np.unique(vid[order], return_index=True)
+    j = len(u) // 2
+    members = order[start[j]:start[j + 1]]
+    assert abs(cx[j] - x[members].astype(np.float64).mean()) < 1e-4
+    # every kept cell: neighbours within r of SOME sample, weighted mean / covariance reproduce
+    r2 = np.float32(9.0)
+    checked = 0
+    for sx, sy in zip(cx, cy):
+        d = (np.float32(sx) - x) ** 2 + (np.float32(sy) - y) ** 2
+        nb = np.nonzero(d < r2)[0]
+        if len(nb) < 6:
+            continue
+        w = np.maximum(I[nb].astype(np.float64) - 60.0, 0.0)
+        if w.sum() <= 0:
+            continue
+        wn = w / w.sum()
+        mu = np.array([(wn * x[nb]).sum(), (wn * y[nb]).sum()])
+        # (samples whose neighbour sets differ only by zero-weight points share a mean: match on the count too)
+        hit = np.nonzero((np.abs(cells[:, 0] - mu[0]) < 1e-9) & (np.abs(cells[:, 1] - mu[1]) < 1e-9) & (cells[:, 15] == len(nb)))[0]
+        if len(hit) == 0:
+            continue  # invalid cell (dropped)
+        c = cells[hit[0]]
+        dx = np.stack([x[nb] - mu[0], y[nb] - mu[1]], 1)
+        cov = (dx * wn[:, None]).T @ dx
+        assert np.allclose(c[2:6].reshape(2, 2), cov, rtol=1e-9, atol=1e-12)
+        assert c[15] == len(nb) and abs(c[13] - w.sum()) < 1e-9
+        lam, vec = np.linalg.eigh(cov)
+        assert np.allclose([c[11], c[12]], lam, rtol=1e-9)
+        n = c[7:9]
+        assert abs(abs(n @ vec[:, 0]) - 1) < 1e-9 and n @ (-mu) >= 0       # normal = smallest eigenvector, facing the sensor
+        assert abs(c[6] - math.log(1 + abs(lam[1] / lam[0]) / 2)) < 1e-9   # planarity
+        assert lam[1] / lam[0] <= 1e4 and lam[0] * lam[1] > 1e-5           # validity gate
+        checked += 1
+    assert checked > 100
+
+
+def test_closest_idx_bucket_equals_brute(oracle, two_sets):
+    _, sets = two_sets
+    rng = np.random.default_rng(1)
+    c = sets[0]
+    for _ in range(300):
+        i = rng.integers(len(c))
+        px, py = c[i, 0] + rng.normal(0, 1.5), c[i, 1] + rng.normal(0, 1.5)
+        for d in (2.0, 4.0):
+            assert oracle.closest_idx(c, px, py, d) == oracle.closest_idx(c, px, py, d, brute=True)
+    assert oracle.closest_idx(c, 1e4, 1e4, 4.0) == -1
+
+
+@pytest.mark.parametrize("loss", [1, 2, 3, 4, 5])
+def test_loss_derivatives(oracle, loss):
+    for s in (1e-4, 0.005, 0.0099, 0.0101, 0.5, 3.0):
+        rho = oracle.loss(loss, 0.1, 1.7, s)
+        h = s * 1e-6
+        d1 = (oracle.loss(loss, 0.1, 1.7, s + h)[0] - oracle.loss(loss, 0.1, 1.7, s - h)[0]) / (2 * h)
+        assert abs(d1 - rho[1]) <= 1e-5 * max(abs(rho[1]), 1e-3)
+    assert np.allclose(oracle.loss(0, 0.1, 2.5, 0.3), [0.75, 2.5, 0.0])   # ScaledLoss over a null loss
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+def test_pair_gradient_is_derivative_of_cost(oracle, two_sets, cost):
+    """g = J^T r must be the gradient of the robustified cost w.r.t. (x, y, theta) with associations frozen; the frozen
+    association makes the cost smooth, so compare against central differences of `cost` from the same call."""
+    _, sets = two_sets
+    # Cauchy: smooth everywhere.  Sim_N weights: pose-independent (the direction-similarity weight is frozen at association
+    # time in the reference, so re-associating at the probe points would leak d(weight)/d(theta) into the difference).
+    P = oracle.default_reg_params(cost=cost, loss=2, weight_opt=1, regularization=0.1)
+    T = np.array([2.45, 0.03, 0.002])
+    base = oracle.pair_normal_eq(sets[0], (0, 0, 0), sets[1], T, P, itr=1)
+    assert base["n_res"] > 100
+    for a in range(3):
+        h = 1e-6
+        Tp, Tm = T.copy(), T.copy()
+        Tp[a] += h; Tm[a] -= h
+        cp = oracle.pair_normal_eq(sets[0], (0, 0, 0), sets[1], Tp, P, itr=1)
+        cm = oracle.pair_normal_eq(sets[0], (0, 0, 0), sets[1], Tm, P, itr=1)
+        if not (np.array_equal(cp["assoc"], base["assoc"]) and np.array_equal(cm["assoc"], base["assoc"])):
+            pytest.skip("association changed under the probe")
+        fd = (cp["cost"] - cm["cost"]) / (2 * h)
+        assert abs(fd - base["g"][a]) <= 2e-5 * max(1.0, abs(base["g"][a]))
+    assert np.allclose(base["H"], base["H"].T) and np.all(np.linalg.eigvalsh(base["H"]) > 0)
+
+
+def _transform_cells(c, T):
+    """cells of the same surface seen from a frame displaced by T (x, y, theta): u' = R^T (u - t), n' = R^T n."""
+    ct, s = math.cos(T[2]), math.sin(T[2])
+    R = np.array([[ct, -s], [s, ct]])
+    o = c.copy()
+    o[:, 0:2] = (c[:, 0:2] - np.array(T[:2])) @ R
+    o[:, 7:9] = c[:, 7:9] @ R
+    cov = c[:, 2:6].reshape(-1, 2, 2)
+    o[:, 2:6] = (R.T @ cov @ R).reshape(-1, 4)
+    return o
+
+
+@pytest.mark.parametrize("cost", [0, 1, 2])
+def test_register_recovers_known_transform(oracle, two_sets, cost):
+    """Noise-free pair: the moving scan is the fixed scan expressed in a displaced frame; registration must return the
+    displacement (GN on noise-free synthetic pairs recovering the known SE(2))."""
+    _, sets = two_sets
+    Ttrue = (0.8, -0.5, 0.03)
+    moving = _transform_cells(sets[0], Ttrue)
+    P = oracle.default_reg_params(cost=cost, loss=1, weight_opt=4, regularization=0.1)
+    T, s = oracle.register([sets[0], moving], [(0, 0, 0), (0.5, -0.2, 0.0)], P)
+    assert s.success == 1
+    assert np.abs(T[1, :2] - Ttrue[:2]).max() < 1e-7 and abs(T[1, 2] - Ttrue[2]) < 1e-8
+    assert s.score < 1e-12
+
+
+def test_lm_matches_scipy_on_frozen_associations(oracle, two_sets):
+    """One ceres::Solve restated vs scipy.optimize.least_squares (trf) on the same residuals: same minimum."""
+    from scipy.optimize import least_squares
+    _, sets = two_sets
+    P = oracle.default_reg_params(cost=1, loss=0, weight_opt=0, max_itr_association=1, max_itr_solver=50)
+    T0 = np.array([2.3, 0.1, 0.01])
+    T, s = oracle.register([sets[0], sets[1]], [(0, 0, 0), T0], P)
+    base = oracle.pair_normal_eq(sets[0], (0, 0, 0), sets[1], T0, P, itr=1)
+    assoc = base["assoc"]
+    j = np.nonzero(assoc >= 0)[0]
+    src, tgt = sets[1][j], sets[0][assoc[j]]
+
+    def res(x):
+        c, sn = math.cos(x[2]), math.sin(x[2])
+        mx = c * src[:, 0] - sn * src[:, 1] + x[0]
+        my = sn * src[:, 0] + c * src[:, 1] + x[1]
+        return (mx - tgt[:, 0]) * tgt[:, 7] + (my - tgt[:, 1]) * tgt[:, 8]
+    sol = least_squares(res, T0, method="trf", xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    assert s.num_residuals == len(j)
+    assert abs(0.5 * (sol.fun ** 2).sum() - s.final_cost) <= 1e-6 * s.final_cost   # function_tolerance 1e-6
+    assert np.abs(T[1] - sol.x).max() < 1e-4
+
+
+def test_register_stopping_rules_and_failure(oracle, two_sets):
+    _, sets = two_sets
+    T, s = oracle.register([sets[0], sets[1]], [(0, 0, 0), (2.5, 0, 0)])
+    assert s.success == 1 and 4 <= s.itrs <= 9      # min_itr_ = 3: never stops before the 4th association round
+    T, s = oracle.register([sets[0], sets[1]], [(0, 0, 0), (900.0, 0, 0)])
+    assert s.success == 0 and s.itrs == 1           # <= 1 residual: BuildOptimizationProblem fails, pose untouched
+    assert np.allclose(T[1], [900.0, 0, 0])
+
+
+def test_odometry_tracks_ground_truth(oracle):
+    st = synth.make_stream(10)
+    od = oracle.Odometry()
+    gt0 = st.gt[0]
+    for i in range(10):
+        o = od.step(st.scans[i])
+        rel = synth.se2_mul(synth.se2_inv(gt0), st.gt[i])
+        assert abs(o.pose[0] - rel[0]) < 0.6 and abs(o.pose[1] - rel[1]) < 0.6 and abs(o.pose[2] - rel[2]) < 0.02
+    assert o.n_keyframes == 4 and o.is_keyframe == 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Scan Context and pose graph
+# ---------------------------------------------------------------------------------------------------------------
+def test_scan_context_descriptor_and_quirk(oracle):
+    rng = np.random.default_rng(3)
+    n = 500
+    r = rng.uniform(1, 95, n); a = rng.uniform(0, 2 * np.pi, n)
+    x = (r * np.cos(a)).astype(np.float32); y = (r * np.sin(a)).astype(np.float32)
+    I = rng.integers(60, 200, n).astype(np.float32)
+    P = oracle.default_sc_params()
+    desc, rk, sk = oracle.sc_make(x, y, I, P)
+    d = desc.reshape(120, 40).T     # column-major 40 x 120
+    want = np.full((40, 120), -1000.0)
+    rr = np.sqrt(x * x + y * y)
+    ang = np.degrees(np.arctan2(y.astype(np.float64), x.astype(np.float64))) % 360.0
+    for i in range(n):
+        if rr[i] > 80:
+            continue
+        ri = max(min(40, int(math.ceil(float(rr[i]) / 80.0 * 40))), 1) - 1
+        si = max(min(120, int(math.ceil(ang[i] / 360.0 * 120))), 1) - 1
+        want[ri, si] = I[i] if want[ri, si] == -1000 else want[ri, si] + I[i]
+    want /= 1000.0
+    # sector index uses a float atan path: allow a handful of bin-edge disagreements with the double restatement
+    assert (np.abs(d - want) > 1e-9).sum() <= 4
+    assert np.isclose(d.min(), -1.0)   # quirk: empty bins hold -1000/1000 = -1.0, not no_point (RadarScancontext.cpp:113-125)
+    assert np.allclose(rk, d.mean(1), atol=1e-6) and np.allclose(sk, d.mean(0))
+
+
+def test_scan_context_shift_recovery(oracle):
+    rng = np.random.default_rng(4)
+    a = rng.uniform(0, 3, size=(120, 40))
+    a[rng.random((120, 40)) < 0.6] = -1.0
+    for sh in (0, 1, 17, 119):
+        b = np.roll(a, -sh, axis=0)     # b shifted right by sh equals a
+        dist, shift = oracle.sc_distance(a.reshape(-1), b.reshape(-1))
+        assert shift == sh and dist < 1e-12
+    c = rng.uniform(0, 3, size=(120, 40))
+    dist, _ = oracle.sc_distance(a.reshape(-1), c.reshape(-1))
+    assert 0.05 < dist < 1.0
+
+
+def test_pgo_jacobian_finite_difference(oracle):
+    rng = np.random.default_rng(5)
+
+    def rnd_pose():
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        return np.concatenate([rng.normal(size=3), q])
+
+    def plus(p, d):   # EigenQuaternionParameterization: q <- dq * q, dq = exp(d) ; position additive
+        out = p.copy()
+        out[:3] += d[:3]
+        n = np.linalg.norm(d[3:])
+        dq = np.concatenate([np.sin(n) * d[3:] / n, [np.cos(n)]]) if n > 0 else np.array([0, 0, 0, 1.0])
+        x1, y1, z1, w1 = dq; x2, y2, z2, w2 = p[3:]
+        out[3:] = [w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                   w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]
+        return out
+    for ctype in (0, 1):
+        a, b, m = rnd_pose(), rnd_pose(), rnd_pose()
+        r, Ja, Jb = oracle.pgo_residual(a, b, m, ctype)
+        for k in range(6):
+            d = np.zeros(6); d[k] = 1e-6
+            ra = (oracle.pgo_residual(plus(a, d), b, m, ctype)[0] - oracle.pgo_residual(plus(a, -d), b, m, ctype)[0]) / 2e-6
+            rb = (oracle.pgo_residual(a, plus(b, d), m, ctype)[0] - oracle.pgo_residual(a, plus(b, -d), m, ctype)[0]) / 2e-6
+            assert np.allclose(Ja[:, k], ra, rtol=1e-5, atol=1e-6 * np.abs(Ja).max())
+            assert np.allclose(Jb[:, k], rb, rtol=1e-5, atol=1e-6 * np.abs(Jb).max())
+
+
+def test_pgo_consistent_graph_has_zero_cost(oracle):
+    n = 12
+    nodes = np.zeros((n, 7)); nodes[:, 6] = 1
+    for i in range(n):
+        th = 0.1 * i
+        nodes[i, :3] = [i * 1.0, 0.2 * i * i, 0]
+        nodes[i, 3:] = [0, 0, math.sin(th / 2), math.cos(th / 2)]
+    ids, meas = [], []
+    for i in range(n - 1):
+        for (a, b, t) in [(i, i + 1, 0)] + ([(0, i + 1, 1)] if i % 4 == 3 else []):
+            qa, qb = nodes[a, 3:], nodes[b, 3:]
+            tha, thb = 2 * math.atan2(qa[2], qa[3]), 2 * math.atan2(qb[2], qb[3])
+            d = nodes[b, :3] - nodes[a, :3]
+            c, s = math.cos(-tha), math.sin(-tha)
+            p = [c * d[0] - s * d[1], s * d[0] + c * d[1], 0]
+            dth = thb - tha
+            ids.append((a, b, t)); meas.append(p + [0, 0, math.sin(dth / 2), math.cos(dth / 2)])
+    cost, Hd, Ho, g, res = oracle.pgo_assemble(nodes, ids, meas)
+    assert cost < 1e-20 and np.abs(g).max() < 1e-9
+    assert np.all(Hd[0] == 0)                        # first node fixed: its block stays empty
+    for i in range(1, n):
+        assert np.all(np.linalg.eigvalsh(Hd[i]) > 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the C-ABI surface (no compute without a GPU)
+# ---------------------------------------------------------------------------------------------------------------
+def test_cabi_exports_every_declared_symbol():
+    from tbv_slam_public_b200 import build as b
+    lib = b.build()
+    L = ctypes.CDLL(lib)
+    assert len(b.EXPORTS) >= 30
+    for sym in b.EXPORTS:
+        assert hasattr(L, sym), f"{sym} declared in include/tbv_b200.h but not exported"
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tbv_slam_public_b200 import api
+    with pytest.raises(api.TbvError) as e:
+        api.Context(0)
+    assert e.value.code == api.TBV_ERR_NO_GPU and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    import re
+    pkg = os.path.join(ROOT, "tbv_slam_public_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle", src, flags=re.M), f
