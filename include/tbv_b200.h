@@ -226,6 +226,53 @@ int tbv_odom_collect(tbv_odom* od, tbv_odom_out* out);
 int tbv_odom_cells(tbv_odom* od, int seq, int keyframe /* -1 = current scan */, tbv_cell* cells, int capacity, int* n_cells,
                    double pose[3]);
 
+/* ---- K6/K7: radar Scan Context ---------------------------------------------------------------------------------------
+ * RSCManager::Parameters + SCManager constants (place_recognition_radar/include/place_recognition_radar/RadarScancontext.h:38-85,
+ * Scancontext.h:100-118); TBV-8 offline values: 40 rings x 120 sectors, 80 m, sum / 1000, 10 from the ring-key search. */
+typedef struct tbv_sc_params {
+  int num_ring, num_sector;
+  double max_radius;
+  double search_ratio;              /* 0.1 */
+  int num_candidates_from_tree;     /* 10 */
+  int n_candidates;
+  double odom_sigma_error;          /* 0.05 */
+  int odometry_coupled_closure, augment_sc;
+  double no_point;
+  int desc_function;                /* 0 = "sum", 1 = "max" */
+  double desc_divider;
+  double distance_exclude_recent;   /* 10 m */
+} tbv_sc_params;
+
+/* RSCManager::MakeRadarCloudContext (RadarScancontext.cpp:59-131) for the cloud translated by each of n_offsets lateral
+ * offsets (the augmentations of makeAndSaveScancontextAndKeysRadarCloud, :162-179; offset (0,0) = the cloud itself), plus
+ * makeRingkeyFromScancontext / makeSectorkeyFromScancontext (Scancontext.cpp:239-268).
+ * desc: [n_offsets][num_sector][num_ring] (column-major rings x sectors, Eigen's layout); ringkey: [n_offsets][num_ring] float;
+ * sectorkey (optional): [n_offsets][num_sector]. */
+int tbv_sc_make(tbv_ctx* ctx, const float* x, const float* y, const float* intensity, int n, const tbv_sc_params* params, int n_offsets,
+                const double* offsets_xy, double* desc, float* ringkey, double* sectorkey);
+/* SCManager::distanceBtnScanContext (Scancontext.cpp:157-189) for n_pairs (query, candidate) descriptor pairs. */
+int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const double* desc_c, int n_c, int n_pairs, const int* q_idx,
+                          const int* c_idx, const tbv_sc_params* params, double* dist, int* shift);
+/* RSCManager::ExcludeAndUpdateLikelihood + OdometryNNSearch (RadarScancontext.cpp:183-221, 259-284) for n_q queries; query q
+ * belongs to keyframe q_current[q] and sees database entries [0, q_current[q] - 1 - n_exclude).  db_keys: [n_db][num_ring],
+ * odom_xyt: [n_db][3].  Outputs: cand_idx / cand_odom_sim [n_q][num_candidates_from_tree] (-1 / 0 padded), n_exclude [n_q]. */
+int tbv_sc_search(tbv_ctx* ctx, const float* db_keys, const double* odom_xyt, int n_db, int n_q, const float* q_keys, const int* q_current,
+                  const tbv_sc_params* params, int* cand_idx, double* cand_odom_sim, int* n_exclude);
+
+/* ---- K8: pose-graph normal equations ------------------------------------------------------------------------------------
+ * CeresLeastSquares::BuildOptimizationProblem / AddConstraintType + PoseGraph3dErrorTerm (tbv_slam/src/tbv_slam/ceresoptimizer.cpp:
+ * 28-108, tbv_slam/include/tbv_slam/ceresoptimizer.h:51-95) followed by one evaluation: robustified residuals, tangent-space
+ * Jacobians (EigenQuaternionParameterization), and the block normal equations.  nodes: 7 doubles (p xyz, q xyzw); constraint c:
+ * ids[3c..] = (id_begin, id_end, type: 0 odometry / 1 loop), meas[7c..] = t_be (p, q), info (optional) [36c..] row-major.
+ * Outputs: H_diag [n_nodes][36], H_off [n_con][36] (block (begin,end) = Ja^T Jb), g [n_nodes][6], residuals (optional) [n_con][6]. */
+typedef struct tbv_pgo_params {
+  double odom_vxx, odom_vyy, odom_vtt, loop_scaling;   /* 0.01, 0.01, 0.001, 500000 (ceresoptimizer.cpp:18-27) */
+  int replace_cov_by_identity;
+  double loop_cauchy;                                  /* CauchyLoss(0.1) on loop constraints */
+} tbv_pgo_params;
+int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, int n_con, const int* ids, const double* meas, const double* info,
+                     const tbv_pgo_params* params, int fixed_node, double* cost, double* H_diag, double* H_off, double* g, double* residuals);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
 void* tbv_host_alloc(size_t bytes);
 void tbv_host_free(void* p);

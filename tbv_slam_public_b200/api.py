@@ -414,3 +414,147 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+# ---- Scan Context / pose graph ------------------------------------------------------------------------------------------
+class SCParams(C.Structure):
+    _fields_ = [("num_ring", C.c_int), ("num_sector", C.c_int), ("max_radius", C.c_double), ("search_ratio", C.c_double),
+                ("num_candidates_from_tree", C.c_int), ("n_candidates", C.c_int), ("odom_sigma_error", C.c_double),
+                ("odometry_coupled_closure", C.c_int), ("augment_sc", C.c_int), ("no_point", C.c_double),
+                ("desc_function", C.c_int), ("desc_divider", C.c_double), ("distance_exclude_recent", C.c_double)]
+
+
+class PGOParams(C.Structure):
+    _fields_ = [("odom_vxx", C.c_double), ("odom_vyy", C.c_double), ("odom_vtt", C.c_double), ("loop_scaling", C.c_double),
+                ("replace_cov_by_identity", C.c_int), ("loop_cauchy", C.c_double)]
+
+
+def default_sc_params(**kw) -> SCParams:
+    """TBV-8 offline settings (tbv_slam/src/tbv_slam_offline.cpp:81-101): 40 x 120, 80 m, sum / 1000, 3 candidates, augmentations."""
+    p = SCParams(40, 120, 80.0, 0.1, 10, 3, 0.05, 1, 1, 0.0, 0, 1000.0, 10.0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_pgo_params(**kw) -> PGOParams:
+    p = PGOParams(0.01, 0.01, 0.001, 500000.0, 1, 0.1)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+AUGMENTS = ((0.0, 0.0), (0.0, -2.0), (0.0, 2.0), (0.0, -4.0), (0.0, 4.0))   # RadarScancontext.cpp:162-166 (+ identity)
+
+
+def _sc_bind():
+    L = lib()
+    if getattr(L, "_sc_bound", False):
+        return L
+    L.tbv_sc_make.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SCParams), C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p]
+    L.tbv_sc_distance_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.POINTER(SCParams), C.c_void_p, C.c_void_p]
+    L.tbv_sc_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(SCParams), C.c_void_p,
+                                C.c_void_p, C.c_void_p]
+    L.tbv_pgo_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PGOParams), C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L._sc_bound = True
+    return L
+
+
+def sc_make(ctx: Context, x, y, intensity, params: SCParams | None = None, offsets=((0.0, 0.0),)):
+    """RSCManager::MakeRadarCloudContext for each lateral offset. Returns (desc [n_off, S*R], ringkey [n_off, R] f32, sectorkey [n_off, S])."""
+    params = params or default_sc_params()
+    x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32); intensity = np.ascontiguousarray(intensity, np.float32)
+    off = np.ascontiguousarray(offsets, np.float64).reshape(-1, 2)
+    R, S = params.num_ring, params.num_sector
+    desc = np.zeros((len(off), R * S)); rk = np.zeros((len(off), R), np.float32); sk = np.zeros((len(off), S))
+    _check(_sc_bind().tbv_sc_make(ctx.h, _ptr(x), _ptr(y), _ptr(intensity), len(x), C.byref(params), len(off), _ptr(off), _ptr(desc), _ptr(rk), _ptr(sk)))
+    return desc, rk, sk
+
+
+def sc_distance_batch(ctx: Context, desc_q, desc_c, q_idx, c_idx, params: SCParams | None = None):
+    params = params or default_sc_params()
+    dq = np.ascontiguousarray(desc_q, np.float64).reshape(-1, params.num_ring * params.num_sector)
+    dc = np.ascontiguousarray(desc_c, np.float64).reshape(-1, params.num_ring * params.num_sector)
+    qi = np.ascontiguousarray(q_idx, np.int32); ci = np.ascontiguousarray(c_idx, np.int32)
+    dist = np.zeros(len(qi)); shift = np.zeros(len(qi), np.int32)
+    _check(_sc_bind().tbv_sc_distance_batch(ctx.h, _ptr(dq), len(dq), _ptr(dc), len(dc), len(qi), _ptr(qi), _ptr(ci), C.byref(params), _ptr(dist),
+                                            _ptr(shift)))
+    return dist, shift
+
+
+def sc_search(ctx: Context, db_keys, odom_xyt, q_keys, q_current, params: SCParams | None = None):
+    """Returns (cand_idx [n_q, k] (-1 padded), cand_odom_sim [n_q, k], n_exclude [n_q])."""
+    params = params or default_sc_params()
+    dk = np.ascontiguousarray(db_keys, np.float32).reshape(-1, params.num_ring)
+    od = np.ascontiguousarray(odom_xyt, np.float64).reshape(-1, 3)
+    qk = np.ascontiguousarray(q_keys, np.float32).reshape(-1, params.num_ring)
+    qc = np.ascontiguousarray(q_current, np.int32)
+    k = params.num_candidates_from_tree
+    ci = np.zeros((len(qc), k), np.int32); cs = np.zeros((len(qc), k)); ne = np.zeros(len(qc), np.int32)
+    _check(_sc_bind().tbv_sc_search(ctx.h, _ptr(dk), _ptr(od), len(dk), len(qc), _ptr(qk), _ptr(qc), C.byref(params), _ptr(ci), _ptr(cs), _ptr(ne)))
+    return ci, cs, ne
+
+
+def pgo_assemble(ctx: Context, nodes, ids, meas, params: PGOParams | None = None, info=None, fixed_node=0):
+    """CeresLeastSquares problem build + one evaluation. Returns (cost, H_diag [n,6,6], H_off [m,6,6], g [n,6], residuals [m,6])."""
+    params = params or default_pgo_params()
+    nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, 7)
+    ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+    meas = np.ascontiguousarray(meas, np.float64).reshape(-1, 7)
+    n, m = len(nodes), len(ids)
+    Hd, Ho, g, res = np.zeros((n, 36)), np.zeros((max(m, 1), 36)), np.zeros((n, 6)), np.zeros((max(m, 1), 6))
+    inf = np.ascontiguousarray(info, np.float64) if info is not None else None
+    cost = C.c_double(0)
+    _check(_sc_bind().tbv_pgo_assemble(ctx.h, n, _ptr(nodes), m, _ptr(ids), _ptr(meas), _ptr(inf), C.byref(params), fixed_node, C.byref(cost),
+                                       _ptr(Hd), _ptr(Ho), _ptr(g), _ptr(res)))
+    return cost.value, Hd.reshape(n, 6, 6), Ho[:m].reshape(m, 6, 6), g, res[:m]
+
+
+class RSCManager:
+    """Host mirror of RSCManager (RadarScancontext.h:31-131): the database lives here, every computation runs on the GPU.
+
+    makeAndSaveScancontextAndKeysRadarCloud -> sc_make (identity + 4 lateral augmentations in one launch);
+    detectLoopClosureID -> sc_search (ring-key NN with the odometry likelihood) + sc_distance_batch over the <= 50 pairs,
+    then the reference's own candidate bookkeeping (RadarScancontext.cpp:286-345: sort by distance, keep N_CANDIDATES).
+    """
+
+    def __init__(self, ctx: Context, params: SCParams | None = None):
+        self.ctx, self.par = ctx, params or default_sc_params()
+        self.polarcontexts, self.ringkeys, self.odom = [], [], []
+        self.queries = None
+
+    def makeAndSaveScancontextAndKeysRadarCloud(self, x, y, intensity, Todom):
+        offs = AUGMENTS if self.par.augment_sc else AUGMENTS[:1]
+        desc, rk, _ = sc_make(self.ctx, x, y, intensity, self.par, offs)
+        self.polarcontexts.append(desc[0].copy()); self.ringkeys.append(rk[0].copy()); self.odom.append(np.asarray(Todom, np.float64))
+        self.queries = (desc, rk, offs)
+
+    def detectLoopClosureID(self):
+        """-> list of dict(min_dist, min_dist_sc, min_dist_odom, yaw_diff_rad, nn_idx, argmin_shift, aug_idx, aug_xy)."""
+        desc, rk, offs = self.queries
+        cur = len(self.ringkeys) - 1
+        nq = len(offs)
+        ci, cs, ne = sc_search(self.ctx, np.stack(self.ringkeys), np.stack(self.odom), rk, np.full(nq, cur, np.int32), self.par)
+        if len(self.ringkeys) < ne[0] + 1:
+            return []
+        pairs = [(q, int(ci[q, t]), float(cs[q, t])) for q in range(nq) for t in range(ci.shape[1]) if ci[q, t] >= 0]
+        if not pairs:
+            return []
+        uniq = sorted({c for _, c, _ in pairs})
+        pos = {c: i for i, c in enumerate(uniq)}
+        dist, shift = sc_distance_batch(self.ctx, desc, np.stack([self.polarcontexts[c] for c in uniq]), [q for q, _, _ in pairs],
+                                        [pos[c] for _, c, _ in pairs], self.par)
+        similar = []
+        unit = 360.0 / float(self.par.num_sector)
+        for (q, c, sim), d_sc, sh in zip(pairs, dist, shift):
+            d_odom = sim if self.par.odometry_coupled_closure else 0.0
+            deg = np.float32(int(sh) * unit)
+            similar.append(dict(min_dist=d_sc + d_odom if self.par.odometry_coupled_closure else d_sc, min_dist_sc=float(d_sc), min_dist_odom=d_odom,
+                                yaw_diff_rad=float(np.float32(float(deg) * np.pi / 180.0)), nn_idx=c, argmin_shift=int(sh), aug_idx=q, aug_xy=offs[q]))
+            similar.sort(key=lambda s: s["min_dist"])   # stable, like the oracle's restatement of the running std::sort
+            if len(similar) > self.par.n_candidates:
+                similar.pop()
+        return similar

@@ -1,0 +1,289 @@
+// k_pgo.cu — K8: pose-graph residuals, tangent-space Jacobians and block normal equations.
+//
+// Replaces CeresLeastSquares::{BuildOptimizationProblem, AddConstraintType} (tbv_slam/src/tbv_slam/ceresoptimizer.cpp:28-108),
+// PoseGraph3dErrorTerm::operator() (tbv_slam/include/tbv_slam/ceresoptimizer.h:56-82) with its AutoDiff Jacobian,
+// EigenQuaternionParameterization's plus-Jacobian, CauchyLoss(0.1) on loop constraints and the Ceres corrector — i.e. what
+// the first evaluation of ceres::Solve computes before the sparse Cholesky (which stays on the host).
+//
+//   pgo_blocks    one thread per constraint: sqrt-information L (Cholesky of the 6x6 information), residual r = L e,
+//                 Ja, Jb (6x6 each, tangent space), robustification; writes Ja^T Ja, Jb^T Jb, Ja^T Jb, Ja^T r, Jb^T r, cost.
+//   pgo_gather    one warp per node: sums the diagonal blocks / gradient of its incident constraints in the reference's
+//                 order (all odometry constraints in index order, then all loop constraints — AddConstraintType order),
+//                 through a CSR built on the host from the id list (index bookkeeping only).  Deterministic, no atomics.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <numeric>
+
+#include "tbv_common.cuh"
+
+namespace tbv {
+
+__device__ __forceinline__ void quat_rotate(const double q[4], const double v[3], double o[3]) {  // Eigen Quaternion::_transformVector
+  const double ux = q[1] * v[2] - q[2] * v[1], uy = q[2] * v[0] - q[0] * v[2], uz = q[0] * v[1] - q[1] * v[0];
+  const double uvx = ux + ux, uvy = uy + uy, uvz = uz + uz;
+  o[0] = v[0] + q[3] * uvx + (q[1] * uvz - q[2] * uvy);
+  o[1] = v[1] + q[3] * uvy + (q[2] * uvx - q[0] * uvz);
+  o[2] = v[2] + q[3] * uvz + (q[0] * uvy - q[1] * uvx);
+}
+__device__ __forceinline__ void quat_mul(const double p[4], const double q[4], double o[4]) {  // Hamilton product, (x,y,z,w)
+  o[0] = p[3] * q[0] + p[0] * q[3] + p[1] * q[2] - p[2] * q[1];
+  o[1] = p[3] * q[1] - p[0] * q[2] + p[1] * q[3] + p[2] * q[0];
+  o[2] = p[3] * q[2] + p[0] * q[1] - p[1] * q[0] + p[2] * q[3];
+  o[3] = p[3] * q[3] - p[0] * q[0] - p[1] * q[1] - p[2] * q[2];
+}
+
+constexpr int PGB = 36 * 3 + 12 + 1;  // per-constraint record: AtA, BtB, (unused), Atr, Btr, cost
+
+__global__ void __launch_bounds__(64)
+pgo_blocks(int n_con, const double* __restrict__ nodes, const int* __restrict__ ids, const double* __restrict__ meas, const double* __restrict__ info,
+           tbv_pgo_params P, int fixed_node, double* __restrict__ rec, double* __restrict__ H_off, double* __restrict__ residuals, int* __restrict__ err) {
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= n_con) return;
+  const int ia = ids[3 * ci], ib = ids[3 * ci + 1], type = ids[3 * ci + 2];
+  const double* A = nodes + 7 * (size_t)ia;
+  const double* B = nodes + 7 * (size_t)ib;
+  const double* M = meas + 7 * (size_t)ci;
+  // ---- sqrt information (ceresoptimizer.cpp:83-100)
+  double L[36];
+  {
+    double I[36];
+    const double lsf = (type == 1) ? 1.0 / P.loop_scaling : 1.0;
+    if (P.replace_cov_by_identity) {
+      const double diag[6] = {1.0 / P.odom_vxx, 1.0 / P.odom_vyy, 1, 1, 1, 1.0 / P.odom_vtt};
+      for (int i = 0; i < 36; i++) I[i] = 0;
+      for (int i = 0; i < 6; i++) I[i * 6 + i] = 1.0 * diag[i] * lsf;
+    } else {
+      for (int i = 0; i < 36; i++) I[i] = info[36 * (size_t)ci + i] * lsf;
+    }
+    for (int i = 0; i < 36; i++) L[i] = 0;
+    bool ok = true;
+    for (int j = 0; j < 6 && ok; j++) {
+      double d = I[j * 6 + j];
+      for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k];
+      if (!(d > 0)) { ok = false; break; }
+      L[j * 6 + j] = sqrt(d);
+      for (int i = j + 1; i < 6; i++) {
+        double v = I[i * 6 + j];
+        for (int k = 0; k < j; k++) v -= L[i * 6 + k] * L[j * 6 + k];
+        L[i * 6 + j] = v / L[j * 6 + j];
+      }
+    }
+    if (!ok) *err = 1;
+  }
+  // ---- residual
+  const double qa_inv[4] = {-A[3], -A[4], -A[5], A[6]};
+  const double d[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+  double p_ab[3], q_ab[4], dq[4];
+  quat_rotate(qa_inv, d, p_ab);
+  quat_mul(qa_inv, B + 3, q_ab);
+  const double q_ab_conj[4] = {-q_ab[0], -q_ab[1], -q_ab[2], q_ab[3]};
+  quat_mul(M + 3, q_ab_conj, dq);
+  const double e[6] = {p_ab[0] - M[0], p_ab[1] - M[1], p_ab[2] - M[2], 2.0 * dq[0], 2.0 * dq[1], 2.0 * dq[2]};
+  double r[6];
+  for (int i = 0; i < 6; i++) {
+    double s = 0;
+    for (int k = 0; k < 6; k++) s += L[i * 6 + k] * e[k];
+    r[i] = s;
+  }
+  // ---- ambient derivatives of e, then tangent space
+  const double u[3] = {qa_inv[0], qa_inv[1], qa_inv[2]}, w = qa_inv[3];
+  double Rm[3][3], dP_du[3][3], dP_dw[3];
+  {
+    const double ux[3][3] = {{0, -u[2], u[1]}, {u[2], 0, -u[0]}, {-u[1], u[0], 0}};
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double uu = 0;
+        for (int k = 0; k < 3; k++) uu += ux[i][k] * ux[k][j];
+        Rm[i][j] = (i == j ? 1.0 : 0.0) + 2.0 * w * ux[i][j] + 2.0 * uu;
+      }
+    dP_dw[0] = 2.0 * (u[1] * d[2] - u[2] * d[1]);
+    dP_dw[1] = 2.0 * (u[2] * d[0] - u[0] * d[2]);
+    dP_dw[2] = 2.0 * (u[0] * d[1] - u[1] * d[0]);
+    const double dx[3][3] = {{0, -d[2], d[1]}, {d[2], 0, -d[0]}, {-d[1], d[0], 0}};
+    const double ud = u[0] * d[0] + u[1] * d[1] + u[2] * d[2];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) dP_du[i][j] = -2.0 * w * dx[i][j] + 2.0 * ((i == j ? ud : 0.0) + u[i] * d[j] - 2.0 * d[i] * u[j]);
+  }
+  const double cb[4] = {-B[3], -B[4], -B[5], B[6]};
+  double Mq[4];
+  quat_mul(M + 3, cb, Mq);
+  const double LM[3][4] = {{Mq[3], -Mq[2], Mq[1], Mq[0]}, {Mq[2], Mq[3], -Mq[0], Mq[1]}, {-Mq[1], Mq[0], Mq[3], Mq[2]}};
+  const double* m = M + 3;
+  const double Lm[4][4] = {{m[3], -m[2], m[1], m[0]}, {m[2], m[3], -m[0], m[1]}, {-m[1], m[0], m[3], m[2]}, {-m[0], -m[1], -m[2], m[3]}};
+  const double* a = A + 3;
+  const double Ra[4][4] = {{a[3], a[2], -a[1], a[0]}, {-a[2], a[3], a[0], a[1]}, {a[1], -a[0], a[3], a[2]}, {-a[0], -a[1], -a[2], a[3]}};
+  double dD_db[3][4];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 4; j++) {
+      double s = 0;
+      for (int k = 0; k < 4; k++) s += Lm[i][k] * Ra[k][j];
+      dD_db[i][j] = s * (j < 3 ? -1.0 : 1.0);
+    }
+  double Eqa[6][4], Eqb[6][4];
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 4; j++) { Eqa[i][j] = 0; Eqb[i][j] = 0; }
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) Eqa[i][j] = -dP_du[i][j];
+    Eqa[i][3] = dP_dw[i];
+    for (int j = 0; j < 4; j++) { Eqa[3 + i][j] = 2.0 * LM[i][j]; Eqb[3 + i][j] = 2.0 * dD_db[i][j]; }
+  }
+  const double* bq = B + 3;
+  const double Pa[4][3] = {{a[3], a[2], -a[1]}, {-a[2], a[3], a[0]}, {a[1], -a[0], a[3]}, {-a[0], -a[1], -a[2]}};
+  const double Pb[4][3] = {{bq[3], bq[2], -bq[1]}, {-bq[2], bq[3], bq[0]}, {bq[1], -bq[0], bq[3]}, {-bq[0], -bq[1], -bq[2]}};
+  double Ea[6][6], Eb[6][6];
+  for (int i = 0; i < 6; i++) {
+    for (int j = 0; j < 3; j++) {
+      Ea[i][j] = i < 3 ? -Rm[i][j] : 0.0;
+      Eb[i][j] = i < 3 ? Rm[i][j] : 0.0;
+      double sa = 0, sb = 0;
+      for (int k = 0; k < 4; k++) { sa += Eqa[i][k] * Pa[k][j]; sb += Eqb[i][k] * Pb[k][j]; }
+      Ea[i][3 + j] = sa; Eb[i][3 + j] = sb;
+    }
+  }
+  double Ja[36], Jb[36];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) {
+      double sa = 0, sb = 0;
+      for (int k = 0; k < 6; k++) { sa += L[i * 6 + k] * Ea[k][j]; sb += L[i * 6 + k] * Eb[k][j]; }
+      Ja[i * 6 + j] = sa; Jb[i * 6 + j] = sb;
+    }
+  // ---- loss + corrector (CauchyLoss on loop constraints: rho'' < 0 -> sqrt(rho') scaling)
+  double sq = 0;
+  for (int i = 0; i < 6; i++) sq += r[i] * r[i];
+  double cost;
+  if (type == 1) {
+    const double b = P.loop_cauchy * P.loop_cauchy, cc = 1.0 / b;
+    const double sum = 1.0 + sq * cc, inv = 1.0 / sum;
+    const double rho0 = b * log(sum), rho1 = fmax(DBL_MIN, inv);
+    cost = 0.5 * rho0;
+    const double s1 = sqrt(rho1);
+    for (int i = 0; i < 36; i++) { Ja[i] *= s1; Jb[i] *= s1; }
+    for (int i = 0; i < 6; i++) r[i] *= s1;
+  } else {
+    cost = 0.5 * sq;
+  }
+  if (residuals) for (int i = 0; i < 6; i++) residuals[6 * (size_t)ci + i] = r[i];
+  const bool fa = (ia == fixed_node), fb = (ib == fixed_node);
+  double* o = rec + (size_t)ci * PGB;
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) {
+      double aa = 0, bb = 0, ab = 0;
+      for (int k = 0; k < 6; k++) { aa += Ja[k * 6 + i] * Ja[k * 6 + j]; bb += Jb[k * 6 + i] * Jb[k * 6 + j]; ab += Ja[k * 6 + i] * Jb[k * 6 + j]; }
+      o[i * 6 + j] = fa ? 0.0 : aa;
+      o[36 + i * 6 + j] = fb ? 0.0 : bb;
+      H_off[36 * (size_t)ci + i * 6 + j] = (fa || fb) ? 0.0 : ab;
+    }
+  for (int i = 0; i < 6; i++) {
+    double ga = 0, gb = 0;
+    for (int k = 0; k < 6; k++) { ga += Ja[k * 6 + i] * r[k]; gb += Jb[k * 6 + i] * r[k]; }
+    o[108 + i] = fa ? 0.0 : ga;
+    o[114 + i] = fb ? 0.0 : gb;
+  }
+  o[120] = cost;
+}
+
+// one warp per node; inc[] lists (constraint << 1 | side) in reference order, side 0 = begin (Ja), 1 = end (Jb)
+__global__ void __launch_bounds__(128)
+pgo_gather(int n_nodes, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ rec, double* __restrict__ H_diag,
+           double* __restrict__ g) {
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (node >= n_nodes) return;
+  double h0 = 0, h1 = 0, gg = 0;  // lane handles H entries lane and lane+32 (< 36) and g entry lane (< 6)
+  for (int t = row[node]; t < row[node + 1]; t++) {
+    const int v = inc[t];
+    const double* o = rec + (size_t)(v >> 1) * PGB;
+    const int side = v & 1;
+    h0 += o[side * 36 + lane];
+    if (lane < 4) h1 += o[side * 36 + 32 + lane];
+    if (lane < 6) gg += o[108 + side * 6 + lane];
+  }
+  H_diag[36 * (size_t)node + lane] = h0;
+  if (lane < 4) H_diag[36 * (size_t)node + 32 + lane] = h1;
+  if (lane < 6) g[6 * (size_t)node + lane] = gg;
+}
+
+// cost = sum over constraints in reference order (odometry first): single CTA, fixed-shape tree
+__global__ void __launch_bounds__(256)
+pgo_cost(int n_con, const int* __restrict__ order, const double* __restrict__ rec, double* __restrict__ cost) {
+  __shared__ double s[256];
+  double a = 0;
+  for (int i = threadIdx.x; i < n_con; i += 256) a += rec[(size_t)order[i] * PGB + 120];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *cost = s[0];
+}
+
+}  // namespace tbv
+
+using namespace tbv;
+
+extern "C" int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, int n_con, const int* ids, const double* meas, const double* info,
+                                const tbv_pgo_params* params, int fixed_node, double* cost, double* H_diag, double* H_off, double* g,
+                                double* residuals) {
+  TBV_REQUIRE(ctx && nodes && ids && meas && params && H_diag && H_off && g && n_nodes >= 1 && n_con >= 0, "bad arguments");
+  TBV_REQUIRE(params->replace_cov_by_identity || info, "information matrices required when replace_cov_by_identity is 0");
+  for (int c = 0; c < n_con; c++)
+    TBV_REQUIRE(ids[3 * c] >= 0 && ids[3 * c] < n_nodes && ids[3 * c + 1] >= 0 && ids[3 * c + 1] < n_nodes, "constraint references a missing node");
+  // reference order: AddConstraintType(odometry) then AddConstraintType(loop) (ceresoptimizer.cpp:34-35)
+  std::vector<int> order(n_con);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (ids[3 * a + 2] == 1) < (ids[3 * b + 2] == 1); });
+  std::vector<int> row(n_nodes + 1, 0), inc(2 * (size_t)n_con);
+  for (int c = 0; c < n_con; c++) { row[ids[3 * c] + 1]++; row[ids[3 * c + 1] + 1]++; }
+  for (int i = 0; i < n_nodes; i++) row[i + 1] += row[i];
+  {
+    std::vector<int> fill(row.begin(), row.end() - 1);
+    for (int c : order) { inc[fill[ids[3 * c]]++] = (c << 1); inc[fill[ids[3 * c + 1]]++] = (c << 1) | 1; }
+  }
+  DevBuf<double> dn, dm, di, drec, dho, dhd, dg, dres, dcost;
+  DevBuf<int> dids, drow, dinc, dord, derr;
+  auto cleanup = [&]() {
+    dn.release(); dm.release(); di.release(); drec.release(); dho.release(); dhd.release(); dg.release(); dres.release(); dcost.release();
+    dids.release(); drow.release(); dinc.release(); dord.release(); derr.release();
+  };
+  const size_t nc1 = n_con ? n_con : 1;
+  int rc;
+  if ((rc = dn.reserve(7 * (size_t)n_nodes)) || (rc = dm.reserve(7 * nc1)) || (rc = di.reserve(info ? 36 * nc1 : 1)) || (rc = drec.reserve(PGB * nc1)) ||
+      (rc = dho.reserve(36 * nc1)) || (rc = dhd.reserve(36 * (size_t)n_nodes)) || (rc = dg.reserve(6 * (size_t)n_nodes)) || (rc = dres.reserve(6 * nc1)) ||
+      (rc = dcost.reserve(1)) || (rc = dids.reserve(3 * nc1)) || (rc = drow.reserve(n_nodes + 1)) || (rc = dinc.reserve(2 * nc1)) ||
+      (rc = dord.reserve(nc1)) || (rc = derr.reserve(1))) { cleanup(); return rc; }
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaMemcpyAsync(dn.p, nodes, 7 * (size_t)n_nodes * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dm.p, meas, 7 * (size_t)n_con * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con && info) e = cudaMemcpyAsync(di.p, info, 36 * (size_t)n_con * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dids.p, ids, 3 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(drow.p, row.data(), (n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dinc.p, inc.data(), 2 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dord.p, order.data(), (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(derr.p, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    if (n_con) {
+      pgo_blocks<<<(n_con + 63) / 64, 64, 0, st>>>(n_con, dn.p, dids.p, dm.p, info ? di.p : nullptr, *params, fixed_node, drec.p, dho.p,
+                                                   residuals ? dres.p : nullptr, derr.p);
+      launched(ctx, "pgo_blocks");
+    }
+    pgo_gather<<<(n_nodes * 32 + 127) / 128, 128, 0, st>>>(n_nodes, drow.p, dinc.p, drec.p, dhd.p, dg.p);
+    launched(ctx, "pgo_gather");
+    pgo_cost<<<1, 256, 0, st>>>(n_con, dord.p, drec.p, dcost.p);
+    launched(ctx, "pgo_cost");
+    e = cudaGetLastError();
+  }
+  int herr = 0;
+  double hcost = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(H_diag, dhd.p, 36 * (size_t)n_nodes * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(g, dg.p, 6 * (size_t)n_nodes * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(H_off, dho.p, 36 * (size_t)n_con * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && n_con && residuals) e = cudaMemcpyAsync(residuals, dres.p, 6 * (size_t)n_con * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hcost, dcost.p, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) { set_error("tbv_pgo_assemble: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  if (herr) { set_error("tbv_pgo_assemble: an information matrix is not positive definite"); return TBV_ERR_INVALID; }
+  if (cost) *cost = hcost;
+  return TBV_OK;
+}
