@@ -22,9 +22,7 @@
 
 namespace tbv {
 
-constexpr int NB_CAP = 1024;      // neighbours sorted in shared memory per sample
-constexpr int C5_WARPS = 4;
-constexpr int C5_CHUNK = 64;
+constexpr int C5_WARPS = 8;
 
 struct GridInfo {
   int min_bx, min_by, div_x, div_y, n_vox, ok;
@@ -285,15 +283,15 @@ __device__ void self_adjoint_eig2(double m00, double m10, double m11, double eva
   evec[0][0] = Q00; evec[0][1] = Q01; evec[1][0] = Q10; evec[1][1] = Q11;
 }
 
+// One warp per sample point.  The neighbour SET is exact (float distance test of the FLANN radius search, strict <); the
+// statistics follow cell::cell's formulas (normalised weights, mean, covariance about the mean; pointnormal.cpp:13-33) with
+// per-lane partial sums in window-scan order and a fixed xor-tree across lanes: deterministic, and within a few ulp of the
+// reference's neighbour-order sums (cells are tolerance-parity, the neighbour counts are exact).
 __global__ void __launch_bounds__(C5_WARPS * 32)
 c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, int cap_pts, int vox_cap,
          const float* __restrict__ x, const float* __restrict__ y, const uint8_t* __restrict__ inten_u8, const float* __restrict__ inten_f32,
          const int* __restrict__ vox_start, const int* __restrict__ sorted, const float* __restrict__ cx, const float* __restrict__ cy,
-         float radius, int weight_intensity, double origin_x, double origin_y,
-         double* __restrict__ cand, uint8_t* __restrict__ cand_valid, int* __restrict__ err) {
-  __shared__ unsigned long long s_keys[C5_WARPS][NB_CAP];
-  __shared__ double s_t[C5_WARPS][4][C5_CHUNK];
-  __shared__ double s_u[C5_WARPS][2];
+         float radius, int weight_intensity, double* __restrict__ cand) {
   const int scan = blockIdx.y;
   const GridInfo g = grid[scan];
   if (!g.ok) return;
@@ -306,11 +304,10 @@ c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, i
   const float* pif = inten_f32 ? inten_f32 + (size_t)scan * cap_pts : nullptr;
   const int* vs = vox_start + (size_t)scan * (vox_cap + 1);
   const int* so = sorted + (size_t)scan * cap_pts;
-  unsigned long long* keys = s_keys[warp];
   const float r2 = (float)((double)radius * (double)radius);  // pcl::KdTreeFLANN::radiusSearch: static_cast<float>(radius*radius)
   const float eps = 1e-3f;
   double* cnd = cand + (size_t)scan * CELL_FIELDS * max_samples;
-  uint8_t* cv = cand_valid + (size_t)scan * max_samples;
+  const size_t st = max_samples;
 
   for (int s = blockIdx.x * C5_WARPS + warp; s < ns; s += gridDim.x * C5_WARPS) {
     const float qx = cx[(size_t)scan * max_samples + s], qy = cy[(size_t)scan * max_samples + s];
@@ -320,152 +317,120 @@ c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, i
     int iy0 = (int)(floorf((qy - radius - eps) * g.inv_leaf) - (float)g.min_by);
     int iy1 = (int)(floorf((qy + radius + eps) * g.inv_leaf) - (float)g.min_by);
     ix0 = max(ix0, 0); iy0 = max(iy0, 0); ix1 = min(ix1, g.div_x - 1); iy1 = min(iy1, g.div_y - 1);
-    int N = 0;
-    bool overflow = false;
+    // pass 1: neighbour count and weight sum (integer-valued weights: exact in any order)
+    int cnt = 0;
+    double wsum = 0.0;
     for (int iy = iy0; iy <= iy1; iy++) {
       const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
-      for (int base = a; base < b; base += 32) {
-        const int j = base + lane;
-        bool in = false;
-        unsigned long long key = 0;
-        if (j < b) {
-          const int i = so[j];
-          const float dx = qx - px[i], dy = qy - py[i];
-          float d = dx * dx;        // FLANN L2_Simple: result += diff*diff per dimension (z contributes +0)
-          d = d + dy * dy;
-          in = d < r2;
-          key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+      for (int j = a + lane; j < b; j += 32) {
+        const int i = so[j];
+        const float dx = qx - px[i], dy = qy - py[i];
+        float d = dx * dx;        // FLANN L2_Simple: result += diff*diff per dimension (z contributes +0)
+        d = d + dy * dy;
+        if (d < r2) {
+          cnt++;
+          const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
+          wsum += weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0;
         }
-        const unsigned bal = __ballot_sync(FULL, in);
-        if (in) {
-          const int pos = N + __popc(bal & ((1u << lane) - 1u));
-          if (pos < NB_CAP) keys[pos] = key;
-        }
-        N += __popc(bal);
       }
     }
-    if (N > NB_CAP) { overflow = true; }
-    bool valid = false;
-    if (N >= 6 && !overflow) {  // pointnormal.cpp:291
-      // ---- bitonic sort of the keys (ascending (d2, index): FLANN's DistanceIndex order) ---------------------
-      int P = 32;
-      while (P < N) P <<= 1;
-      for (int e = N + lane; e < P; e += 32) keys[e] = ~0ull;
-      __syncwarp();
-      for (int kk = 2; kk <= P; kk <<= 1) {
-        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-          for (int t = lane; t < (P >> 1); t += 32) {
-            const int lo = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));  // index with bit jj cleared
-            const int hi = lo | jj;
-            const unsigned long long a = keys[lo], b = keys[hi];
-            const bool up = ((lo & kk) == 0);
-            if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-          }
-          __syncwarp();
-        }
-      }
-      // ---- weights, mean, covariance in neighbour order (pointnormal.cpp:13-33) --------------------------------
-      double wsum = 0.0;
-      for (int e = lane; e < N; e += 32) {
-        const int i = (int)(keys[e] & 0xffffffffu);
-        const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
-        wsum += weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0;
-      }
-      for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(FULL, wsum, d);  // integer-valued terms: exact in any order
-      double u0 = 0.0, u1 = 0.0;
-      for (int base = 0; base < N; base += C5_CHUNK) {
-        const int m = min(C5_CHUNK, N - base);
-        for (int e = lane; e < m; e += 32) {
-          const int i = (int)(keys[base + e] & 0xffffffffu);
+    for (int d = 16; d > 0; d >>= 1) { cnt += __shfl_xor_sync(FULL, cnt, d); wsum += __shfl_xor_sync(FULL, wsum, d); }
+    if (cnt < 6) {  // pointnormal.cpp:291
+      if (lane == 0) cnd[CF_NS * st + s] = 0.0;
+      continue;
+    }
+    // pass 2: mean
+    double u0 = 0.0, u1 = 0.0;
+    for (int iy = iy0; iy <= iy1; iy++) {
+      const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
+      for (int j = a + lane; j < b; j += 32) {
+        const int i = so[j];
+        const float fx = px[i], fy = py[i];
+        const float dx = qx - fx, dy = qy - fy;
+        float d = dx * dx;
+        d = d + dy * dy;
+        if (d < r2) {
           const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
           const double w = (weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0) / wsum;
-          s_t[warp][0][e] = w * (double)px[i];
-          s_t[warp][1][e] = w * (double)py[i];
+          u0 += w * (double)fx;
+          u1 += w * (double)fy;
         }
-        __syncwarp();
-        if (lane < 2) {
-          double acc = lane == 0 ? u0 : u1;
-          const double* t = s_t[warp][lane];
-          for (int e = 0; e < m; e++) acc += t[e];
-          if (lane == 0) u0 = acc; else u1 = acc;
-        }
-        __syncwarp();
       }
-      if (lane == 0) s_u[warp][0] = u0;
-      if (lane == 1) s_u[warp][1] = u1;
-      __syncwarp();
-      u0 = s_u[warp][0]; u1 = s_u[warp][1];
-      double cacc = 0.0;  // lanes 0..3 hold c00, c01, c10, c11
-      for (int base = 0; base < N; base += C5_CHUNK) {
-        const int m = min(C5_CHUNK, N - base);
-        for (int e = lane; e < m; e += 32) {
-          const int i = (int)(keys[base + e] & 0xffffffffu);
+    }
+    for (int d = 16; d > 0; d >>= 1) { u0 += __shfl_xor_sync(FULL, u0, d); u1 += __shfl_xor_sync(FULL, u1, d); }
+    // pass 3: covariance about the mean
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    for (int iy = iy0; iy <= iy1; iy++) {
+      const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
+      for (int j = a + lane; j < b; j += 32) {
+        const int i = so[j];
+        const float fx = px[i], fy = py[i];
+        const float dx = qx - fx, dy = qy - fy;
+        float d = dx * dx;
+        d = d + dy * dy;
+        if (d < r2) {
           const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
           const double w = (weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0) / wsum;
-          const double d0 = (double)px[i] - u0, d1 = (double)py[i] - u1;
+          const double d0 = (double)fx - u0, d1 = (double)fy - u1;
           const double xw0 = w * d0, xw1 = w * d1;
-          s_t[warp][0][e] = d0 * xw0;
-          s_t[warp][1][e] = d0 * xw1;
-          s_t[warp][2][e] = d1 * xw0;
-          s_t[warp][3][e] = d1 * xw1;
+          c00 += d0 * xw0; c01 += d0 * xw1; c10 += d1 * xw0; c11 += d1 * xw1;
         }
-        __syncwarp();
-        if (lane < 4) {
-          const double* t = s_t[warp][lane];
-          for (int e = 0; e < m; e++) cacc += t[e];
-        }
-        __syncwarp();
       }
-      const double c00 = __shfl_sync(FULL, cacc, 0), c01 = __shfl_sync(FULL, cacc, 1), c10 = __shfl_sync(FULL, cacc, 2),
-                   c11 = __shfl_sync(FULL, cacc, 3);
-      if (lane == 0) {
-        // ---- cell::ComputeNormal (pointnormal.cpp:37-63) ----------------------------------------------------------
-        double eval[2], evec[2][2];
-        self_adjoint_eig2(c00, c10, c11, eval, evec);
-        double n0 = evec[0][0], n1 = evec[1][0];
-        const double lambda_min = eval[0], lambda_max = eval[1];
-        const double condition_number = fabs(lambda_max / lambda_min);
-        const double determinant = lambda_max * lambda_min;
-        valid = (condition_number <= 10000) && (determinant > 0.00001) && lambda_min > 0 && lambda_max > 0;
-        const double scale = log(1.0 + condition_number / 2);
-        const double pox = origin_x - u0, poy = origin_y - u1;
-        if (n0 * pox + n1 * poy < 0) { n0 = -n0; n1 = -n1; }
-        const size_t st = max_samples;
-        cnd[CF_U0 * st + s] = u0; cnd[CF_U1 * st + s] = u1;
-        cnd[CF_C00 * st + s] = c00; cnd[CF_C01 * st + s] = c01; cnd[CF_C10 * st + s] = c10; cnd[CF_C11 * st + s] = c11;
-        cnd[CF_SCALE * st + s] = scale;
-        cnd[CF_N0 * st + s] = n0; cnd[CF_N1 * st + s] = n1;
-        cnd[CF_O0 * st + s] = evec[0][1]; cnd[CF_O1 * st + s] = evec[1][1];
-        cnd[CF_LMIN * st + s] = lambda_min; cnd[CF_LMAX * st + s] = lambda_max;
-        cnd[CF_SUMI * st + s] = wsum; cnd[CF_AVGI * st + s] = wsum / (double)N;
-        cnd[CF_NS * st + s] = (double)N;
-      }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      c00 += __shfl_xor_sync(FULL, c00, d); c01 += __shfl_xor_sync(FULL, c01, d);
+      c10 += __shfl_xor_sync(FULL, c10, d); c11 += __shfl_xor_sync(FULL, c11, d);
     }
     if (lane == 0) {
-      cv[s] = valid ? 1 : 0;
-      if (overflow) err[scan] = TBV_ERR_CAPACITY;
+      cnd[CF_U0 * st + s] = u0; cnd[CF_U1 * st + s] = u1;
+      cnd[CF_C00 * st + s] = c00; cnd[CF_C01 * st + s] = c01; cnd[CF_C10 * st + s] = c10; cnd[CF_C11 * st + s] = c11;
+      cnd[CF_SUMI * st + s] = wsum;
+      cnd[CF_NS * st + s] = (double)cnt;
     }
-    __syncwarp();
   }
 }
 
 // ---- C6 -------------------------------------------------------------------------------------------------------
+// One thread per sample: cell::ComputeNormal (pointnormal.cpp:37-63) — 2x2 eigen-solve, validity, planarity, normal
+// orientation — then the ordered compaction of the valid cells (the reference's push_back order = sample order).
 __global__ void __launch_bounds__(256)
 c6_compact(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, const double* __restrict__ cand,
-           const uint8_t* __restrict__ cand_valid, double* __restrict__ out, int out_cap, int* __restrict__ out_count, int* __restrict__ err) {
+           double origin_x, double origin_y, double* __restrict__ out, int out_cap, int* __restrict__ out_count, int* __restrict__ err) {
   __shared__ int s_w[8];
   __shared__ int s_running;
   const int scan = blockIdx.x;
   const int ns = grid[scan].ok ? n_samples[scan] : 0;
   const double* cnd = cand + (size_t)scan * CELL_FIELDS * max_samples;
-  const uint8_t* cv = cand_valid + (size_t)scan * max_samples;
+  const size_t st = max_samples;
   double* o = out + (size_t)scan * CELL_FIELDS * out_cap;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) s_running = 0;
   __syncthreads();
   for (int base = 0; base < ns; base += 256) {
     const int s = base + threadIdx.x;
-    const bool v = s < ns && cv[s];
+    bool v = false;
+    double rec[CELL_FIELDS];
+    if (s < ns) {
+      const double N = cnd[CF_NS * st + s];
+      if (N >= 6.0) {
+        const double u0 = cnd[CF_U0 * st + s], u1 = cnd[CF_U1 * st + s];
+        const double c00 = cnd[CF_C00 * st + s], c01 = cnd[CF_C01 * st + s], c10 = cnd[CF_C10 * st + s], c11 = cnd[CF_C11 * st + s];
+        const double wsum = cnd[CF_SUMI * st + s];
+        double eval[2], evec[2][2];
+        self_adjoint_eig2(c00, c10, c11, eval, evec);
+        double n0 = evec[0][0], n1 = evec[1][0];
+        const double lambda_min = eval[0], lambda_max = eval[1];
+        const double condition_number = fabs(lambda_max / lambda_min);
+        const double determinant = lambda_max * lambda_min;
+        v = (condition_number <= 10000) && (determinant > 0.00001) && lambda_min > 0 && lambda_max > 0;
+        const double pox = origin_x - u0, poy = origin_y - u1;
+        if (n0 * pox + n1 * poy < 0) { n0 = -n0; n1 = -n1; }
+        rec[CF_U0] = u0; rec[CF_U1] = u1; rec[CF_C00] = c00; rec[CF_C01] = c01; rec[CF_C10] = c10; rec[CF_C11] = c11;
+        rec[CF_SCALE] = log(1.0 + condition_number / 2);
+        rec[CF_N0] = n0; rec[CF_N1] = n1; rec[CF_O0] = evec[0][1]; rec[CF_O1] = evec[1][1];
+        rec[CF_LMIN] = lambda_min; rec[CF_LMAX] = lambda_max; rec[CF_SUMI] = wsum; rec[CF_AVGI] = wsum / N; rec[CF_NS] = N;
+      }
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, v);
     if (lane == 0) s_w[warp] = __popc(bal);
     __syncthreads();
@@ -474,7 +439,8 @@ c6_compact(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples,
     if (v) {
       const int q = off + __popc(bal & ((1u << lane) - 1u));
       if (q < out_cap)
-        for (int f = 0; f < CELL_FIELDS; f++) o[(size_t)f * out_cap + q] = cnd[(size_t)f * max_samples + s];
+#pragma unroll
+        for (int f = 0; f < CELL_FIELDS; f++) o[(size_t)f * out_cap + q] = rec[f];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -550,17 +516,17 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
     launched(ctx, "c3_scatter");
   }
   {
-    const int gx = (max_samples + 3) / 4 < 512 ? (max_samples + 3) / 4 : 512;
+    const int gx = (max_samples + 3) / 4 < 96 ? (max_samples + 3) / 4 : 96;
     c4_centroids<<<dim3(gx, batch), 128, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, S.sample_vox.p, S.vox_start.p,
                                                   S.sorted_raw.p, S.sorted.p, S.cx.p, S.cy.p);
     launched(ctx, "c4_centroids");
-    const int g5 = (max_samples + C5_WARPS - 1) / C5_WARPS < 512 ? (max_samples + C5_WARPS - 1) / C5_WARPS : 512;
+    const int g5 = (max_samples + C5_WARPS - 1) / C5_WARPS < 48 ? (max_samples + C5_WARPS - 1) / C5_WARPS : 48;
     c5_cells<<<dim3(g5, batch), C5_WARPS * 32, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, inten_u8, inten_f32,
-                                                        S.vox_start.p, S.sorted.p, S.cx.p, S.cy.p, par.radius, par.weight_intensity,
-                                                        par.origin[0], par.origin[1], S.cand.p, S.cand_valid.p, S.err.p);
+                                                        S.vox_start.p, S.sorted.p, S.cx.p, S.cy.p, par.radius, par.weight_intensity, S.cand.p);
     launched(ctx, "c5_cells");
   }
-  c6_compact<<<batch, 256, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, S.cand.p, S.cand_valid.p, out.f64.p, cell_cap, out.count.p, S.err.p);
+  c6_compact<<<batch, 256, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, S.cand.p, par.origin[0], par.origin[1], out.f64.p, cell_cap, out.count.p,
+                                    S.err.p);
   launched(ctx, "c6_compact");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;

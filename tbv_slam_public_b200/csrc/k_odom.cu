@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256)
 k_odom_update(SeqState* __restrict__ st, OdomDevParams P, const RegResult* __restrict__ results, const int* __restrict__ n_points,
               const double* __restrict__ cur_cells, const int* __restrict__ cur_count, int cell_cap, double* __restrict__ kf_cells,
               int* __restrict__ kf_count, const int* __restrict__ cells_err, const int* __restrict__ cur_samples,
-              tbv_odom_out* __restrict__ outs) {
+              tbv_odom_out* __restrict__ outs, int* __restrict__ fused_set) {
   __shared__ int s_fuse_slot;
   const int s = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -179,6 +179,7 @@ k_odom_update(SeqState* __restrict__ st, OdomDevParams P, const RegResult* __res
     o.n_samples = cur_samples[s];
     outs[s] = o;
     s_fuse_slot = fuse_slot;
+    fused_set[s] = fuse_slot >= 0 ? s * (P.K + 1) + fuse_slot : -1;  // the set whose search grid must be rebuilt
   }
   __syncthreads();
   const int slot = s_fuse_slot;
@@ -205,7 +206,8 @@ struct tbv_odom {
   DevBuf<SeqState> state;
   DevBuf<double> mot, fixed_pose;
   DevBuf<RegProblem> problems;
-  DevBuf<int> fixed_set;
+  DevBuf<int> fixed_set, fused_set;
+  GridStore kf_grids;
   DevBuf<RegResult> results;
   DevBuf<SetView> views;
   DevBuf<tbv_odom_out> outs_dev;
@@ -224,7 +226,7 @@ static void odom_free(tbv_odom* od) {
   cudaStreamSynchronize(od->ctx->stream);
   if (od->copy_stream) cudaStreamSynchronize(od->copy_stream);
   od->state.release(); od->mot.release(); od->fixed_pose.release(); od->problems.release(); od->fixed_set.release();
-  od->results.release(); od->views.release(); od->outs_dev.release(); od->cur.release(); od->kf.release();
+  od->results.release(); od->views.release(); od->fused_set.release(); od->kf_grids.release(); od->outs_dev.release(); od->cur.release(); od->kf.release();
   for (int i = 0; i < 2; i++) {
     od->polar[i].release();
     if (od->uploaded[i]) cudaEventDestroy(od->uploaded[i]);
@@ -243,16 +245,18 @@ static int odom_init(tbv_odom* od) {
   if ((rc = od->state.reserve(n_seq)) || (rc = od->mot.reserve((size_t)n_seq * 3)) || (rc = od->fixed_pose.reserve((size_t)n_seq * K * 3)) ||
       (rc = od->problems.reserve(n_seq)) || (rc = od->fixed_set.reserve((size_t)n_seq * K)) || (rc = od->results.reserve(n_seq)) ||
       (rc = od->views.reserve((size_t)n_seq * (K + 1))) || (rc = od->outs_dev.reserve(n_seq)) || (rc = od->cur.reserve(n_seq, od->cell_cap)) ||
-      (rc = od->kf.reserve(n_seq * K, od->cell_cap)))
+      (rc = od->kf.reserve(n_seq * K, od->cell_cap)) || (rc = od->fused_set.reserve(n_seq)) || (rc = od->kf_grids.reserve(n_seq * K, od->cell_cap)))
     return rc;
   TBV_CUDA(cudaMemsetAsync(od->kf.count.p, 0, (size_t)n_seq * K * sizeof(int), ctx->stream));
+  TBV_CUDA(cudaMemsetAsync(od->kf_grids.hdr.p, 0, (size_t)n_seq * K * sizeof(CellGrid), ctx->stream));
   TBV_CUDA(cudaMemsetAsync(od->cur.count.p, 0, (size_t)n_seq * sizeof(int), ctx->stream));
   TBV_CUDA(cudaMemsetAsync(od->fixed_set.p, 0, (size_t)n_seq * K * sizeof(int), ctx->stream));
   TBV_CUDA(cudaMemsetAsync(od->fixed_pose.p, 0, (size_t)n_seq * K * 3 * sizeof(double), ctx->stream));
   std::vector<SetView> hv((size_t)n_seq * (K + 1));
   for (int s = 0; s < n_seq; s++) {
-    for (int i = 0; i < K; i++) hv[(size_t)s * (K + 1) + i] = SetView{od->kf.set_ptr(s * K + i), od->cell_cap, od->kf.count.p + s * K + i, 0};
-    hv[(size_t)s * (K + 1) + K] = SetView{od->cur.set_ptr(s), od->cell_cap, od->cur.count.p + s, 0};
+    for (int i = 0; i < K; i++)
+      hv[(size_t)s * (K + 1) + i] = od->kf_grids.view(s * K + i, od->kf.set_ptr(s * K + i), od->cell_cap, od->kf.count.p + s * K + i, 0);
+    hv[(size_t)s * (K + 1) + K] = SetView{od->cur.set_ptr(s), od->cell_cap, od->cur.count.p + s, 0, nullptr, nullptr, nullptr, nullptr};
   }
   TBV_CUDA(cudaMemcpyAsync(od->views.p, hv.data(), hv.size() * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
   k_odom_reset<<<(n_seq + 127) / 128, 128, 0, ctx->stream>>>(od->state.p, n_seq);
@@ -285,10 +289,11 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
                             od->cell_cap, od->rpar, od->results.p, nullptr, false)))
     return rc;
   k_odom_update<<<n_seq, 256, 0, st>>>(od->state.p, od->dpar, od->results.p, F.filtered.count.p, od->cur.f64.p, od->cur.count.p, od->cell_cap,
-                                       od->kf.f64.p, od->kf.count.p, cells_err_dev(ctx), od->cur.n_samples.p, od->outs_dev.p);
+                                       od->kf.f64.p, od->kf.count.p, cells_err_dev(ctx), od->cur.n_samples.p, od->outs_dev.p, od->fused_set.p);
   launched(ctx, "k_odom_update");
   TBV_CUDA(cudaGetLastError());
-  return TBV_OK;
+  // new keyframes get their search grid now (used by the registrations of the following frames)
+  return cellgrid_build_launch(ctx, od->views.p, od->fused_set.p, n_seq, n_seq * (od->K + 1));
 }
 
 extern "C" {

@@ -386,23 +386,155 @@ __device__ void lm_candidate(LMState& S, const double* acc) {
   }
 }
 
+// ---- uniform grid over a fixed scan's cell means (the reference's kd-tree over pcl::PointXY, pointnormal.cpp:151-162) -----
+// Buckets of side 4 m >= every search radius used (2*radius_ = 4 on the first association round, radius_ = 2 afterwards): an
+// accepted neighbour (d2 < R2) lies in the 3x3 block around the query's bucket and nothing outside the block can be closer
+// than an accepted one, so searching the block returns the reference's global 1-NN + distance test.
+constexpr float GRID_CELL = 4.0f;
+
+__device__ __forceinline__ int set_count(const SetView& s) { return s.n_ptr ? min(*s.n_ptr, s.cap) : min(s.n_val, s.cap); }
+
+__device__ __forceinline__ int grid_coord(float v, float mn, int n) {  // bucket of a stored point: clamped
+  const float f = floorf((v - mn) / GRID_CELL);
+  if (!(f >= 0.f)) return 0;
+  return f >= (float)n ? n - 1 : (int)f;
+}
+
+__global__ void __launch_bounds__(256)
+k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which, int n_sets) {
+  extern __shared__ int s_cnt[];  // [GRID_CAP]
+  __shared__ float s_red[4][8];
+  __shared__ int s_part[256];
+  __shared__ CellGrid s_g;
+  const int bi = blockIdx.x;
+  const int si = which ? which[bi] : bi;
+  if (si < 0 || si >= n_sets) return;
+  const SetView t = sets[si];
+  if (!t.grid) return;
+  const int n = set_count(t);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* U0 = t.f + (size_t)CF_U0 * t.cap;
+  const double* U1 = t.f + (size_t)CF_U1 * t.cap;
+  float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+  for (int i = tid; i < n; i += 256) {
+    const float a = (float)U0[i], b = (float)U1[i];
+    mnx = fminf(mnx, a); mxx = fmaxf(mxx, a); mny = fminf(mny, b); mxy = fmaxf(mxy, b);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+  }
+  if (lane == 0) { s_red[0][warp] = mnx; s_red[1][warp] = mny; s_red[2][warp] = mxx; s_red[3][warp] = mxy; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; w++) {
+      mnx = fminf(mnx, s_red[0][w]); mny = fminf(mny, s_red[1][w]); mxx = fmaxf(mxx, s_red[2][w]); mxy = fmaxf(mxy, s_red[3][w]);
+    }
+    CellGrid g;
+    g.minx = mnx; g.miny = mny; g.nx = 1; g.ny = 1; g.ok = 0;
+    if (n > 0 && n <= 65535) {
+      const float fx = floorf((mxx - mnx) / GRID_CELL), fy = floorf((mxy - mny) / GRID_CELL);
+      if (fx >= 0.f && fy >= 0.f && fx < 16384.f && fy < 16384.f) {
+        g.nx = (int)fx + 1; g.ny = (int)fy + 1;
+        g.ok = ((long long)g.nx * g.ny <= GRID_CAP) ? 1 : 0;
+      }
+    }
+    s_g = g;
+    *t.grid = g;
+  }
+  __syncthreads();
+  const CellGrid g = s_g;
+  if (!g.ok) return;
+  const int nb = g.nx * g.ny;
+  for (int b = tid; b < nb; b += 256) s_cnt[b] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256)
+    atomicAdd(&s_cnt[grid_coord((float)U1[i], g.miny, g.ny) * g.nx + grid_coord((float)U0[i], g.minx, g.nx)], 1);
+  __syncthreads();
+  const int chunk = (nb + 255) / 256;
+  const int b0 = min(nb, tid * chunk), b1 = min(nb, b0 + chunk);
+  int sum = 0;
+  for (int b = b0; b < b1; b++) sum += s_cnt[b];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < 256; k++) { const int v = s_part[k]; s_part[k] = run; run += v; }
+  }
+  __syncthreads();
+  int off = s_part[tid];
+  for (int b = b0; b < b1; b++) {
+    const int c = s_cnt[b];
+    t.gstart[b] = (uint16_t)off;
+    s_cnt[b] = off;
+    off += c;
+  }
+  if (tid == 0) t.gstart[nb] = (uint16_t)n;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const float a = (float)U0[i], b = (float)U1[i];
+    const int pos = atomicAdd(&s_cnt[grid_coord(b, g.miny, g.ny) * g.nx + grid_coord(a, g.minx, g.nx)], 1);
+    t.gmean[pos] = make_float2(a, b);
+    t.gidx[pos] = (uint16_t)i;
+  }
+}
+
+// MapPointNormal::GetClosestIdx (pointnormal.cpp:238-254): float 1-NN over the cell means, accepted iff d2 < R*R.
+__device__ __forceinline__ int nn_search(const SetView& t, int n_tgt, float qx, float qy, double R) {
+  float bestd = FLT_MAX;
+  int best = -1;
+  const CellGrid* gp = t.grid;
+  if (gp && gp->ok) {
+    const CellGrid g = *gp;
+    const float fx = floorf((qx - g.minx) / GRID_CELL), fy = floorf((qy - g.miny) / GRID_CELL);
+    const int cbx = !(fx >= -2.f) ? -2 : (fx > (float)(g.nx + 1) ? g.nx + 1 : (int)fx);
+    const int cby = !(fy >= -2.f) ? -2 : (fy > (float)(g.ny + 1) ? g.ny + 1 : (int)fy);
+    const int bx0 = max(cbx - 1, 0), bx1 = min(cbx + 1, g.nx - 1);
+    if (bx0 <= bx1) {
+      for (int by = max(cby - 1, 0); by <= min(cby + 1, g.ny - 1); by++) {
+        const int s0 = t.gstart[by * g.nx + bx0], s1 = t.gstart[by * g.nx + bx1 + 1];
+        for (int s = s0; s < s1; s++) {
+          const float2 m = t.gmean[s];
+          const int i = t.gidx[s];
+          const float dx = qx - m.x, dy = qy - m.y;
+          float dd = dx * dx;   // FLANN L2_Simple, no contraction (-fmad=false)
+          dd = dd + dy * dy;
+          if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
+        }
+      }
+    }
+  } else {  // no grid (huge extent / more than 65535 cells): exhaustive scan, first minimum wins
+    const double* U0 = t.f + (size_t)CF_U0 * t.cap;
+    const double* U1 = t.f + (size_t)CF_U1 * t.cap;
+    for (int i = 0; i < n_tgt; i++) {
+      const float dx = qx - (float)U0[i], dy = qy - (float)U1[i];
+      float dd = dx * dx;
+      dd = dd + dy * dy;
+      if (dd < bestd) { bestd = dd; best = i; }
+    }
+  }
+  return (best >= 0 && (double)bestd < R * R) ? best : -1;
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
+constexpr int RG_MAX_FIXED = 16;
+
 struct RegShared {
   double acc[NACC];
   double warp_acc[RG_WARPS][NACC];
   double ex[3], cs[2];
   int flag, n_blocks, warp_cnt[RG_WARPS], running;
+  Aff Tst[RG_MAX_FIXED], Ttar[RG_MAX_FIXED];
+  SetView tgt[RG_MAX_FIXED];
+  int n_tgt[RG_MAX_FIXED];
+  LMState lm;
 };
 
-__device__ __forceinline__ int set_count(const SetView& s) { return s.n_ptr ? min(*s.n_ptr, s.cap) : min(s.n_val, s.cap); }
-
-__global__ void __launch_bounds__(RG_THREADS)
+__global__ void __launch_bounds__(RG_THREADS, 2)
 k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
            const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
            double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
            double* __restrict__ residuals_all) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  float2* s_tgt = reinterpret_cast<float2*>(s_raw);  // [tgt_cap] cell means of the fixed scan being searched
   __shared__ RegShared sh;
   const int p = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -421,133 +553,116 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   }
   const SetView src = sets[prob.src_set];
   const int n_src = set_count(src);
+  const int n_fixed = min(prob.n_fixed, RG_MAX_FIXED);
   const size_t bstride = (size_t)max_fixed * slot_cap;
   int* assoc = assoc_all + (size_t)p * bstride;
   double* blocks = blocks_all + (size_t)p * BLK_FIELDS * bstride;
   const int nres_per_block = (P.cost == TBV_P2L) ? 1 : 2;
+  if (tid < n_fixed) {
+    sh.tgt[tid] = sets[fixed_set[prob.fixed_first + tid]];
+    sh.n_tgt[tid] = set_count(sh.tgt[tid]);
+  }
+  __syncthreads();
 
-  // ---- association at pose x with search radius R: fills assoc + compacted blocks, returns the block count in sh.n_blocks
+  // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan): one thread per (fixed, source)
+  // slot; accepted correspondences are compacted in slot order = the order the reference adds its residual blocks in.
   auto associate = [&](const double x[3], double R) {
-    const Aff Tsrc = vec_to_aff(x[0], x[1], x[2]);
-    if (tid == 0) sh.running = 0;
-    for (int fi = 0; fi < prob.n_fixed; fi++) {
-      const SetView tgt = sets[fixed_set[prob.fixed_first + fi]];
-      const int n_tgt = set_count(tgt);
-      const double* fp = fixed_pose + (size_t)(prob.fixed_first + fi) * 3;
+    if (tid < n_fixed) {
+      const double* fp = fixed_pose + (size_t)(prob.fixed_first + tid) * 3;
       const Aff Ttar = vec_to_aff(fp[0], fp[1], fp[2]);
-      const Aff Tst = aff_mul(aff_inv(Ttar), Tsrc);
-      __syncthreads();  // previous users of s_tgt are done
-      for (int i = tid; i < n_tgt; i += RG_THREADS)
-        s_tgt[i] = make_float2((float)tgt.f[(size_t)CF_U0 * tgt.cap + i], (float)tgt.f[(size_t)CF_U1 * tgt.cap + i]);
-      __syncthreads();
-      // 1-NN: one warp per source cell
-      for (int j = warp; j < n_src; j += RG_WARPS) {
+      sh.Ttar[tid] = Ttar;
+      sh.Tst[tid] = aff_mul(aff_inv(Ttar), vec_to_aff(x[0], x[1], x[2]));
+    }
+    if (tid == 0) sh.running = 0;
+    __syncthreads();
+    const int n_slots = n_fixed * n_src;
+    for (int base = 0; base < n_slots; base += RG_THREADS) {
+      const int slot = base + tid;
+      bool ok = false;
+      int ti = -1, fi = 0, j = 0;
+      double w = 0.0;
+      if (slot < n_slots) {
+        fi = slot / n_src;
+        j = slot - fi * n_src;
+        const Aff Tst = sh.Tst[fi];
+        const SetView& tgt = sh.tgt[fi];
         const double ux = src.f[(size_t)CF_U0 * src.cap + j], uy = src.f[(size_t)CF_U1 * src.cap + j];
         const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
         const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
-        const float qx = (float)qxd, qy = (float)qyd;
-        float bestd = FLT_MAX;
-        int best = 0x7fffffff;
-        for (int i = lane; i < n_tgt; i += 32) {
-          const float2 m = s_tgt[i];
-          const float dx = qx - m.x, dy = qy - m.y;
-          float dd = dx * dx;       // FLANN L2_Simple, no contraction (-fmad=false)
-          dd = dd + dy * dy;
-          if (dd < bestd) { bestd = dd; best = i; }
+        ti = nn_search(tgt, sh.n_tgt[fi], (float)qxd, (float)qyd, R);
+        if (ti >= 0) {
+          const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
+          const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
+          const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
+          const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
+          const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
+          if (sim > P.angle_outlier) {
+            ok = true;
+            const double N1 = src.f[(size_t)CF_NS * src.cap + j], N2 = tgt.f[(size_t)CF_NS * tgt.cap + ti];
+            const double p1 = src.f[(size_t)CF_SCALE * src.cap + j], p2 = tgt.f[(size_t)CF_SCALE * tgt.cap + ti];
+            const double simN = 2 * fmin(N1, N2) / (N1 + N2);
+            const double simP = 2 * fmin(p1, p2) / (p1 + p2);
+            switch (P.weight_opt) {   // registration.cpp:67-75
+              case TBV_W_UNIFORM: w = 1.0; break;
+              case TBV_W_SIM_N: w = simN; break;
+              case TBV_W_SIM_DIRECTION: w = sim; break;
+              case TBV_W_SIM_SCALE: w = simP; break;
+              case TBV_W_COMBINED: w = simN + sim + simP; break;
+              default: w = 1.0;
+            }
+          } else {
+            ti = -1;
+          }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          const float od = __shfl_xor_sync(FULL, bestd, d);
-          const int oi = __shfl_xor_sync(FULL, best, d);
-          if (od < bestd || (od == bestd && oi < best)) { bestd = od; best = oi; }
+        assoc[(size_t)fi * slot_cap + j] = ti;
+      }
+      const unsigned bal = __ballot_sync(FULL, ok);
+      if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
+      __syncthreads();
+      if (ok) {
+        int q = sh.running + __popc(bal & ((1u << lane) - 1u));
+        for (int wv = 0; wv < warp; wv++) q += sh.warp_cnt[wv];
+        const Aff Ttar = sh.Ttar[fi];
+        const SetView& tgt = sh.tgt[fi];
+        const double tu0 = tgt.f[(size_t)CF_U0 * tgt.cap + ti], tu1 = tgt.f[(size_t)CF_U1 * tgt.cap + ti];
+        blocks[0 * bstride + q] = src.f[(size_t)CF_U0 * src.cap + j];
+        blocks[1 * bstride + q] = src.f[(size_t)CF_U1 * src.cap + j];
+        blocks[2 * bstride + q] = (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx;
+        blocks[3 * bstride + q] = (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty;
+        if (P.cost == TBV_P2L) {
+          const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
+          blocks[4 * bstride + q] = Ttar.r00 * tn0 + Ttar.r01 * tn1;
+          blocks[5 * bstride + q] = Ttar.r10 * tn0 + Ttar.r11 * tn1;
+        } else if (P.cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
+          const double c00 = tgt.f[(size_t)CF_C00 * tgt.cap + ti], c01 = tgt.f[(size_t)CF_C01 * tgt.cap + ti];
+          const double c10 = tgt.f[(size_t)CF_C10 * tgt.cap + ti], c11 = tgt.f[(size_t)CF_C11 * tgt.cap + ti];
+          const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
+          const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
+          const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
+          const double M00 = RC00 * R00 + RC01 * R01, M01 = RC00 * R10 + RC01 * R11;
+          const double M10 = RC10 * R00 + RC11 * R01, M11 = RC10 * R10 + RC11 * R11;
+          const double t00 = (P.regularization + M00) * P.cov_scale, t01 = (0.0 + M01) * P.cov_scale;
+          const double t10 = (0.0 + M10) * P.cov_scale, t11 = (P.regularization + M11) * P.cov_scale;
+          const double det = t00 * t11 - t10 * t01;
+          const double invdet = 1.0 / det;
+          const double i00 = t11 * invdet, i10 = -t10 * invdet, i11 = t00 * invdet;
+          const double l00 = sqrt(i00);
+          const double l10 = i10 / l00;
+          const double l11 = sqrt(i11 - l10 * l10);
+          blocks[4 * bstride + q] = l00;
+          blocks[5 * bstride + q] = l10;
+          blocks[6 * bstride + q] = l11;
         }
-        if (lane == 0) {
-          int a = -1;
-          if (best != 0x7fffffff && (double)bestd < R * R) a = best;  // pointnormal.cpp:250
-          assoc[(size_t)fi * slot_cap + j] = a;
-        }
+        blocks[7 * bstride + q] = w;
       }
       __syncthreads();
-      // gate + weights + block data, ordered compaction
-      for (int base = 0; base < n_src; base += RG_THREADS) {
-        const int j = base + tid;
-        bool ok = false;
-        int ti = -1;
-        double w = 0.0;
-        if (j < n_src) {
-          ti = assoc[(size_t)fi * slot_cap + j];
-          if (ti >= 0) {
-            const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
-            const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
-            const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
-            const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
-            const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
-            if (sim > P.angle_outlier) {
-              ok = true;
-              const double N1 = src.f[(size_t)CF_NS * src.cap + j], N2 = tgt.f[(size_t)CF_NS * tgt.cap + ti];
-              const double p1 = src.f[(size_t)CF_SCALE * src.cap + j], p2 = tgt.f[(size_t)CF_SCALE * tgt.cap + ti];
-              const double simN = 2 * fmin(N1, N2) / (N1 + N2);
-              const double simP = 2 * fmin(p1, p2) / (p1 + p2);
-              switch (P.weight_opt) {   // registration.cpp:67-75
-                case TBV_W_UNIFORM: w = 1.0; break;
-                case TBV_W_SIM_N: w = simN; break;
-                case TBV_W_SIM_DIRECTION: w = sim; break;
-                case TBV_W_SIM_SCALE: w = simP; break;
-                case TBV_W_COMBINED: w = simN + sim + simP; break;
-                default: w = 1.0;
-              }
-            } else {
-              assoc[(size_t)fi * slot_cap + j] = -1;
-            }
-          }
-        }
-        const unsigned bal = __ballot_sync(FULL, ok);
-        if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        if (ok) {
-          int q = sh.running + __popc(bal & ((1u << lane) - 1u));
-          for (int wv = 0; wv < warp; wv++) q += sh.warp_cnt[wv];
-          const double tu0 = tgt.f[(size_t)CF_U0 * tgt.cap + ti], tu1 = tgt.f[(size_t)CF_U1 * tgt.cap + ti];
-          blocks[0 * bstride + q] = src.f[(size_t)CF_U0 * src.cap + j];
-          blocks[1 * bstride + q] = src.f[(size_t)CF_U1 * src.cap + j];
-          blocks[2 * bstride + q] = (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx;
-          blocks[3 * bstride + q] = (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty;
-          if (P.cost == TBV_P2L) {
-            const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
-            blocks[4 * bstride + q] = Ttar.r00 * tn0 + Ttar.r01 * tn1;
-            blocks[5 * bstride + q] = Ttar.r10 * tn0 + Ttar.r11 * tn1;
-          } else if (P.cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
-            const double c00 = tgt.f[(size_t)CF_C00 * tgt.cap + ti], c01 = tgt.f[(size_t)CF_C01 * tgt.cap + ti];
-            const double c10 = tgt.f[(size_t)CF_C10 * tgt.cap + ti], c11 = tgt.f[(size_t)CF_C11 * tgt.cap + ti];
-            const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
-            const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
-            const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
-            const double M00 = RC00 * R00 + RC01 * R01, M01 = RC00 * R10 + RC01 * R11;
-            const double M10 = RC10 * R00 + RC11 * R01, M11 = RC10 * R10 + RC11 * R11;
-            const double t00 = (P.regularization + M00) * P.cov_scale, t01 = (0.0 + M01) * P.cov_scale;
-            const double t10 = (0.0 + M10) * P.cov_scale, t11 = (P.regularization + M11) * P.cov_scale;
-            const double det = t00 * t11 - t10 * t01;
-            const double invdet = 1.0 / det;
-            const double i00 = t11 * invdet, i10 = -t10 * invdet, i11 = t00 * invdet;
-            const double l00 = sqrt(i00);
-            const double l10 = i10 / l00;
-            const double l11 = sqrt(i11 - l10 * l10);
-            blocks[4 * bstride + q] = l00;
-            blocks[5 * bstride + q] = l10;
-            blocks[6 * bstride + q] = l11;
-          }
-          blocks[7 * bstride + q] = w;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          int t = 0;
-          for (int wv = 0; wv < RG_WARPS; wv++) t += sh.warp_cnt[wv];
-          sh.running += t;
-        }
-        __syncthreads();
+      if (tid == 0) {
+        int t = 0;
+        for (int wv = 0; wv < RG_WARPS; wv++) t += sh.warp_cnt[wv];
+        sh.running += t;
       }
+      __syncthreads();
     }
-    __syncthreads();
     if (tid == 0) sh.n_blocks = sh.running;
     __syncthreads();
   };
@@ -616,8 +731,9 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     return;
   }
 
-  // ---- Register (n_scan_normal.cpp:82-185) — control state lives in thread 0, decisions are broadcast through sh.flag
-  LMState S;
+  // ---- Register (n_scan_normal.cpp:82-185) — the LM state lives in shared memory and is advanced by thread 0; decisions
+  // are broadcast through sh.flag
+  LMState& S = sh.lm;
   double par[3] = {prob.src_pose[0], prob.src_pose[1], prob.src_pose[2]};  // parameters.back()
   double prev_par[3] = {par[0], par[1], par[2]};
   double tsrc[3] = {par[0], par[1], par[2]};  // Tsrc.back(): only rewritten after a usable solve (:118-121, :166-170)
@@ -653,20 +769,12 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       }
       __syncthreads();
     }
-    // broadcast the outcome of this solve: parameters + the scalars the outer loop reads
-    if (tid == 0) {
-      sh.ex[0] = S.params[0]; sh.ex[1] = S.params[1]; sh.ex[2] = S.params[2];
-      sh.acc[0] = fmin(S.initial_cost, S.min_pushed_cost);  // SetSummaryFinalCost
-      sh.acc[1] = S.last_rel_dec;
-      sh.warp_cnt[0] = S.n_pushed;
-      sh.warp_cnt[1] = S.termination;
-    }
-    __syncthreads();
-    par[0] = sh.ex[0]; par[1] = sh.ex[1]; par[2] = sh.ex[2];
-    final_cost = sh.acc[0];
-    last_rel_dec = sh.acc[1];
-    last_n_iterations = sh.warp_cnt[0];
-    termination = sh.warp_cnt[1];
+    // the outcome of this solve: parameters + the scalars the outer loop reads (S is shared: every thread reads it)
+    par[0] = S.params[0]; par[1] = S.params[1]; par[2] = S.params[2];
+    final_cost = fmin(S.initial_cost, S.min_pushed_cost);  // SetSummaryFinalCost
+    last_rel_dec = S.last_rel_dec;
+    last_n_iterations = S.n_pushed;
+    termination = S.termination;
     __syncthreads();
     total_lm += last_n_iterations - 1;
     success = termination != 2;  // IsSolutionUsable
@@ -751,14 +859,9 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   int rc = reg_scratch_reserve(ctx, n_problems, max_fixed, slot_cap, want_residuals);
   if (rc) return rc;
   RegScratch& S = *reg_scratch(ctx);
-  const size_t smem = (size_t)tgt_cap * sizeof(float2);
-  TBV_REQUIRE(smem <= 160 * 1024, "fixed scan too large for the shared-memory search (more than 20480 cells)");
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) {
-    TBV_CUDA(cudaFuncSetAttribute(k_register, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
-  k_register<<<n_problems, RG_THREADS, smem, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
+  TBV_REQUIRE(max_fixed <= RG_MAX_FIXED, "too many fixed scans per problem (at most 16)");
+  (void)tgt_cap;
+  k_register<<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                             slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
                                                             want_residuals ? S.residuals.p : nullptr);
   launched(ctx, "k_register");
@@ -766,37 +869,64 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   return TBV_OK;
 }
 
+int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets) {
+  if (n_launch <= 0) return TBV_OK;
+  static bool attr = false;
+  if (!attr) {
+    TBV_CUDA(cudaFuncSetAttribute(k_cellgrid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, GRID_CAP * (int)sizeof(int)));
+    attr = true;
+  }
+  k_cellgrid_build<<<n_launch, 256, GRID_CAP * sizeof(int), ctx->stream>>>(sets_dev, which_dev, n_sets);
+  launched(ctx, "k_cellgrid_build");
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
+}
+
+int GridStore::reserve(int n_sets_, int cell_cap_) {
+  n_sets = n_sets_;
+  cell_cap = cell_cap_;
+  int rc;
+  if ((rc = hdr.reserve(n_sets_)) || (rc = start.reserve((size_t)n_sets_ * (GRID_CAP + 1))) || (rc = mean.reserve((size_t)n_sets_ * cell_cap_)) ||
+      (rc = idx.reserve((size_t)n_sets_ * cell_cap_)))
+    return rc;
+  return TBV_OK;
+}
+
 // --------------------------------------------------------------------------------------------------------------
 // C-ABI entry points with host-resident cell records
 // --------------------------------------------------------------------------------------------------------------
 namespace {
-struct HostProblemSet {  // uploads n_sets cell sets and describes them as SetViews
+struct HostProblemSet {  // uploads n_sets cell sets, describes them as SetViews and builds their search grids
   tbv_ctx* ctx;
   std::vector<DevBuf<double>> bufs;
   DevBuf<SetView> views;
+  GridStore grids;
   int max_n = 1;
   ~HostProblemSet() {
     for (auto& b : bufs) b.release();
     views.release();
+    grids.release();
   }
   int upload(int n_sets, const tbv_cell* const* sets, const int* n_cells) {
     bufs.resize(n_sets);
     std::vector<SetView> hv(n_sets);
     for (int i = 0; i < n_sets; i++) {
-      const int n = n_cells[i];
-      TBV_REQUIRE(n >= 0 && (n == 0 || sets[i]), "bad cell set");
-      const int cap = n > 0 ? n : 1;
-      int rc = bufs[i].reserve((size_t)CELL_FIELDS * cap);
-      if (rc) return rc;
-      if ((rc = cells_upload(ctx, sets[i], n, bufs[i].p, cap))) return rc;
-      hv[i] = SetView{bufs[i].p, cap, nullptr, n};
-      if (n > max_n) max_n = n;
+      TBV_REQUIRE(n_cells[i] >= 0 && (n_cells[i] == 0 || sets[i]), "bad cell set");
+      if (n_cells[i] > max_n) max_n = n_cells[i];
     }
-    int rc = views.reserve(n_sets);
+    int rc = grids.reserve(n_sets, max_n);
     if (rc) return rc;
+    for (int i = 0; i < n_sets; i++) {
+      const int n = n_cells[i];
+      const int cap = n > 0 ? n : 1;
+      if ((rc = bufs[i].reserve((size_t)CELL_FIELDS * cap))) return rc;
+      if ((rc = cells_upload(ctx, sets[i], n, bufs[i].p, cap))) return rc;
+      hv[i] = grids.view(i, bufs[i].p, cap, nullptr, n);
+    }
+    if ((rc = views.reserve(n_sets))) return rc;
     TBV_CUDA(cudaMemcpyAsync(views.p, hv.data(), n_sets * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
     TBV_CUDA(cudaStreamSynchronize(ctx->stream));  // hv goes out of scope
-    return TBV_OK;
+    return cellgrid_build_launch(ctx, views.p, nullptr, n_sets, n_sets);
   }
 };
 

@@ -4,12 +4,39 @@
 
 namespace tbv {
 
+constexpr int GRID_CAP = 16384;  // buckets of the 4 m search grid over a fixed scan's cell means (128 x 128 = 512 m span)
+
+struct CellGrid {       // header of one search grid; ok == 0: no grid (extent / size outside the limits) -> exhaustive search
+  float minx, miny;
+  int nx, ny, ok;
+};
+
 struct SetView {        // one cell set (MapPointNormal) on the device, field-major
   const double* f;      // f[field*cap + i]
   int cap;
   const int* n_ptr;     // number of cells lives on the device (pipeline) ...
   int n_val;            // ... or is known on the host (API calls); used when n_ptr == nullptr
+  // search grid over the cell means (optional; built by cellgrid_build_launch): bucket b holds entries [gstart[b], gstart[b+1])
+  CellGrid* grid;
+  uint16_t* gstart;     // [GRID_CAP + 1]
+  float2* gmean;        // [cap] cell means narrowed to float (pcl::PointXY), in bucket order
+  uint16_t* gidx;       // [cap] cell index of each entry
 };
+
+struct GridStore {      // storage for the grids of n_sets cell sets
+  int n_sets = 0, cell_cap = 0;
+  DevBuf<CellGrid> hdr;
+  DevBuf<uint16_t> start, idx;
+  DevBuf<float2> mean;
+  int reserve(int n_sets_, int cell_cap_);
+  void release() { hdr.release(); start.release(); idx.release(); mean.release(); }
+  SetView view(int i, const double* f, int cap, const int* n_ptr, int n_val) const {
+    return SetView{f, cap, n_ptr, n_val, hdr.p + i, start.p + (size_t)i * (GRID_CAP + 1), mean.p + (size_t)i * cell_cap, idx.p + (size_t)i * cell_cap};
+  }
+};
+
+// (re)builds the grids of sets which_dev[0..n_launch) (which_dev == nullptr: sets 0..n_launch-1; entries < 0 are skipped)
+int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets);
 
 struct RegProblem {     // one n_scan_normal_reg::Register call: fixed scans + one moving scan
   int n_fixed;

@@ -1,8 +1,9 @@
 """K3 parity: CUDA oriented surface points ("cells", MapPointNormal) vs the oracle, through the C-ABI.
 
-Bar: identical cell count and order, identical neighbour counts (the voxel-grid samples and the float radius search
-are integer / index work: bit-exact), means / covariances / eigen-decomposition bit-exact (same operation order, no FMA),
-planarity (a log) within 4 ulp (device log is not glibc's).
+Bar: identical cell count and order, identical neighbour counts and weight sums (the voxel-grid samples and the float radius
+search are integer / index work: bit-exact).  Means / covariances are sums of ~100 fp64 terms: the kernel adds them in a
+fixed lane tree, the reference in neighbour order -> tolerance 1e-12 relative (SURVEY §7 "hard parts": cells are
+tolerance-parity given identical neighbour sets); eigenvalues / normals / planarity inherit that through a 2x2 eigen-solve.
 """
 import numpy as np
 import pytest
@@ -19,11 +20,22 @@ def _cloud(oracle, img, **kw):
 
 def _compare(ref, got):
     assert got.shape == ref.shape, f"{ref.shape[0]} oracle cells vs {got.shape[0]} gpu"
-    assert np.array_equal(ref[:, NS], got[:, NS]), "neighbour counts differ"
-    exact = [U0, U1, C00, C01, C10, C11, N0, N1, O0, O1, LMIN, LMAX, SUMI, AVGI]
-    for f in exact:
-        assert np.array_equal(ref[:, f], got[:, f]), f"field {f} differs: max abs {np.abs(ref[:, f] - got[:, f]).max()}"
-    assert np.allclose(ref[:, SCALE], got[:, SCALE], rtol=1e-15 * 4, atol=0), "planarity differs by more than 4 ulp"
+    for f in (NS, SUMI, AVGI):
+        assert np.array_equal(ref[:, f], got[:, f]), f"field {f} (integer-valued) differs"
+    if len(ref) == 0:
+        return
+    scale = np.abs(ref[:, [U0, U1]]).max()
+    assert np.abs(ref[:, [U0, U1]] - got[:, [U0, U1]]).max() <= 1e-13 * max(scale, 1.0), "means differ"
+    cov_scale = np.abs(ref[:, C00:C11 + 1]).max(axis=1, keepdims=True)
+    assert (np.abs(ref[:, C00:C11 + 1] - got[:, C00:C11 + 1]) <= 1e-11 * cov_scale).all(), "covariances differ"
+    for f in (LMIN, LMAX):
+        assert np.allclose(ref[:, f], got[:, f], rtol=1e-9, atol=0), f"eigenvalue {f} differs"
+    # eigenvectors: conditioning ~ 1 / (relative eigenvalue gap)
+    gap = (ref[:, LMAX] - ref[:, LMIN]) / ref[:, LMAX]
+    tol = 1e-11 / np.maximum(gap, 1e-6)
+    assert (np.abs(ref[:, N0] - got[:, N0]) <= tol).all() and (np.abs(ref[:, N1] - got[:, N1]) <= tol).all(), "normals differ"
+    assert (np.abs(np.abs(ref[:, O0] * got[:, O0] + ref[:, O1] * got[:, O1]) - 1) <= tol).all(), "orth normals differ"
+    assert np.allclose(ref[:, SCALE], got[:, SCALE], rtol=1e-9, atol=1e-12), "planarity differs"
 
 
 @pytest.mark.parametrize("k,z,radius,wint", [(40, 60.0, 3.0, True), (12, 70.0, 3.5, False), (12, 60.0, 3.0, True)])

@@ -92,7 +92,7 @@ def test_rsc_manager_detects_like_the_oracle(ctx, oracle):
         OP, P = oracle.default_sc_params(n_candidates=n_cand), api.default_sc_params(n_candidates=n_cand)
         ref, gpu = oracle.RSC(OP), api.RSCManager(ctx, P)
         pose = np.zeros(3)
-        n_with = 0
+        n_with = n_override = 0
         for k, i in enumerate(order):
             x, y, I = _peaks(oracle, st.scans[i])
             pose = pose + np.array([2.5 * math.cos(0.05 * k), 2.5 * math.sin(0.05 * k), 0.05])   # a growing spiral: old places are far in odometry
