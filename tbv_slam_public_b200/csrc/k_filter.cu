@@ -51,38 +51,62 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Issue the copy of one row into buf such that buf[a0 + r] = row[r], a0 = (row address) & 15.
-__device__ __forceinline__ int stage_row(uint8_t* buf, const uint8_t* rp, int n_range, int lane) {
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of one row into shared memory, completion on an mbarrier --------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Stage row `rp` so that buf[a0 + r] = row[r], a0 = (row address) & 15.  Fast path: ONE bulk copy of the 16-byte-aligned
+// superset [rp - a0, ceil16(rp + n_range)) issued by lane 0 — legal whenever the superset stays inside the caller's buffer
+// [lo, hi) (every row but possibly the first / last of the whole batch).  Returns true if the copy is in flight on `bar`;
+// false means the caller must copy synchronously (stage_row_sync) when it consumes the row.
+__device__ __forceinline__ bool stage_row_tma(uint8_t* buf, const uint8_t* rp, int n_range, const uint8_t* lo, const uint8_t* hi, uint64_t* bar, int lane) {
   const int a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
-  if ((a0 & 7) == 0) {
-    // head: up to 8 bytes so that the body is 16-byte aligned in both spaces
-    int r0 = 0;
-    if (a0 == 8) {
-      if (lane == 0 && n_range >= 8) cp_async8(buf + 8, rp);
-      r0 = 8;
-    }
-    const int nvec = (n_range - r0) >> 4;  // full 16-byte chunks
-    for (int t = lane; t < nvec; t += 32) cp_async16(buf + a0 + r0 + 16 * t, rp + r0 + 16 * t);
-    const int done = r0 + (nvec << 4);
-    const int rem = n_range - done;  // < 16 (or the whole row when n_range < 8)
-    if (lane == 0) {
-      int o = done;
-      if (rem >= 8 && n_range >= 8) { cp_async8(buf + a0 + o, rp + o); o += 8; }
-      for (; o < n_range; o++) buf[a0 + o] = __ldg(rp + o);
-      if (a0 == 8 && n_range < 8) for (int q = 0; q < n_range; q++) buf[a0 + q] = __ldg(rp + q);
-    }
-  } else {
-    for (int o = lane; o < n_range; o += 32) buf[a0 + o] = __ldg(rp + o);  // unaligned stride: plain byte copies
+  const uint8_t* src = rp - a0;
+  const uint32_t bytes = (uint32_t)((a0 + n_range + 15) & ~15);
+  if (src < lo || src + bytes > hi) return false;
+  if (lane == 0) {
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(buf, src, bytes, bar);
   }
-  return a0;
+  return true;
+}
+__device__ __forceinline__ void stage_row_sync(uint8_t* buf, const uint8_t* rp, int n_range, int lane) {
+  const int a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
+  for (int o = lane; o < n_range; o += 32) buf[a0 + o] = __ldg(rp + o);
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n_range, size_t row_stride, int z_min, int k,
-              int want_peaks, int rowbuf, uint32_t* __restrict__ row_keys, uint16_t* __restrict__ row_cnt) {
-  extern __shared__ __align__(16) uint8_t s_dyn[];  // [K1_WARPS][2][rowbuf] staged rows
+              int want_peaks, int rowbuf, const uint8_t* buf_lo, const uint8_t* buf_hi, uint32_t* __restrict__ row_keys,
+              uint16_t* __restrict__ row_cnt) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];  // [K1_WARPS][2][rowbuf] staged rows
   __shared__ __align__(16) uint32_t s_list[K1_WARPS][K1_CAP];  // candidates (unordered)
   __shared__ __align__(16) uint32_t s_sel[K1_WARPS][K1_CAP];   // selected, ascending
+  __shared__ __align__(8) uint64_t s_bar[K1_WARPS][2];
   __shared__ int s_n[K1_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
@@ -94,30 +118,37 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
   uint8_t* mybuf = s_dyn + (size_t)warp * 2 * rowbuf;
   uint32_t* list = s_list[warp];
   uint32_t* sel = s_sel[warp];
+  uint64_t* bars = s_bar[warp];
   const int row_step = gridDim.x * K1_WARPS;
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncwarp();
 
+  auto row_ptr = [&](int row) -> const uint8_t* {
+    const int scan = row / n_az, az = row - scan * n_az;
+    return polar + (size_t)scan * scan_stride + (size_t)az * row_stride;
+  };
   int row = blockIdx.x * K1_WARPS + warp;
   int cur = 0;
-  int a0 = 0;
-  if (row < total_rows) {
-    const int scan = row / n_az, az = row - scan * n_az;
-    a0 = stage_row(mybuf, polar + (size_t)scan * scan_stride + (size_t)az * row_stride, n_range, lane);
-  }
-  cp_async_commit();
+  uint32_t phase = 0;    // bit b: parity to wait for on bars[b]
+  bool in_flight = false;
+  if (row < total_rows) in_flight = stage_row_tma(mybuf, row_ptr(row), n_range, buf_lo, buf_hi, &bars[0], lane);
   for (; row < total_rows; row += row_step) {
     const int scan = row / n_az, az = row - scan * n_az;
     const uint8_t* scan_base = polar + (size_t)scan * scan_stride;
+    const uint8_t* rp = scan_base + (size_t)az * row_stride;
+    const int a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
     uint8_t* buf = mybuf + (size_t)cur * rowbuf;
-    // prefetch the next row of this warp into the other buffer
+    // prefetch the next row of this warp into the other buffer (its previous contents were consumed last iteration)
     const int nrow = row + row_step;
-    int a0_next = 0;
-    if (nrow < total_rows) {
-      const int ns = nrow / n_az, na = nrow - ns * n_az;
-      a0_next = stage_row(mybuf + (size_t)(cur ^ 1) * rowbuf, polar + (size_t)ns * scan_stride + (size_t)na * row_stride, n_range, lane);
+    bool next_in_flight = false;
+    if (nrow < total_rows) next_in_flight = stage_row_tma(mybuf + (size_t)(cur ^ 1) * rowbuf, row_ptr(nrow), n_range, buf_lo, buf_hi, &bars[cur ^ 1], lane);
+    if (in_flight) {
+      mbar_wait(&bars[cur], (phase >> cur) & 1u);
+      phase ^= 1u << cur;
+    } else {
+      stage_row_sync(buf, rp, n_range, lane);
     }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncwarp();
 
     // word validity: byte offset wo in buf holds row index wo - a0; valid iff 0 <= wo + b - a0 < n_range
     const int lo_b = a0, hi_b = a0 + n_range;  // valid buffer byte range [lo_b, hi_b)
@@ -129,7 +160,11 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
     };
     const int nvec = (hi_b + 15) >> 4;  // 16-byte vectors covering [0, hi_b)
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf);
-    auto emit = [&](uint32_t m, uint32_t w, int wo) {  // scatter the flagged bytes of one word
+    auto masks = [&](const uint4 v, int wo, uint32_t ac, bool h, uint32_t m[4]) {
+      m[0] = ge_mask(v.x, ac, h); m[1] = ge_mask(v.y, ac, h); m[2] = ge_mask(v.z, ac, h); m[3] = ge_mask(v.w, ac, h);
+      if (wo < lo_b || wo + 16 > hi_b) { m[0] &= valid_mask(wo); m[1] &= valid_mask(wo + 4); m[2] &= valid_mask(wo + 8); m[3] &= valid_mask(wo + 12); }
+    };
+    auto emit = [&](uint32_t m, uint32_t w, int wo) {  // dense path only: scatter the flagged bytes of one word
       int pos = atomicAdd(&s_n[warp], __popc(m));
       while (m) {
         const int b = (__ffs(m) - 1) >> 3;
@@ -138,26 +173,51 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
         pos++;
       }
     };
-    if (lane == 0) s_n[warp] = 0;
-    __syncwarp();
-    // ---- pass 1: count candidates (I >= z_min) and scatter them optimistically ----------------------------
+    // ---- pass 1: count the candidates (I >= z_min); remember which of this lane's vectors hold any -----------------
     int cnt = 0;
-    for (int t = lane; t < nvec; t += 32) {
-      const uint4 v = vbuf[t];
-      const int wo = t << 4;
-      uint32_t m0 = ge_mask(v.x, addc, hi), m1 = ge_mask(v.y, addc, hi), m2 = ge_mask(v.z, addc, hi), m3 = ge_mask(v.w, addc, hi);
-      if (wo < lo_b || wo + 16 > hi_b) { m0 &= valid_mask(wo); m1 &= valid_mask(wo + 4); m2 &= valid_mask(wo + 8); m3 &= valid_mask(wo + 12); }
-      if (m0 | m1 | m2 | m3) {
-        cnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        if (m0) emit(m0, v.x, wo);
-        if (m1) emit(m1, v.y, wo + 4);
-        if (m2) emit(m2, v.z, wo + 8);
-        if (m3) emit(m3, v.w, wo + 12);
+    uint32_t flagged = 0;
+    {
+      int it = 0;
+      for (int t = lane; t < nvec; t += 32, it++) {
+        uint32_t m[4];
+        masks(vbuf[t], t << 4, addc, hi, m);
+        if (m[0] | m[1] | m[2] | m[3]) {
+          cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+          flagged |= 1u << it;
+        }
       }
     }
     const int total = __reduce_add_sync(FULL, cnt);
-    __syncwarp();
-    if (total > K1_CAP) {
+    int n;
+    if (total <= K1_CAP) {
+      // ---- sparse row (the normal case): exclusive prefix of the per-lane counts, then every lane writes its own -----
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      int pos = incl - cnt;
+      while (flagged) {
+        const int it = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        const int t = lane + (it << 5), wo = t << 4;
+        const uint4 v = vbuf[t];
+        uint32_t m[4];
+        masks(v, wo, addc, hi, m);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint32_t mm = m[q];
+          while (mm) {
+            const int b = (__ffs(mm) - 1) >> 3;
+            mm &= mm - 1;
+            list[pos++] = (((w[q] >> (8 * b)) & 0xffu) << 16) | (uint32_t)(wo + 4 * q + b - a0);
+          }
+        }
+      }
+      n = total;
+    } else {
       // ---- dense row: exact threshold + tie handling ----------------------------------------------------
       if (lane == 0) s_n[warp] = 0;
       __syncwarp();
@@ -166,11 +226,9 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
         const uint32_t ac = (h ? (256u - t) : (128u - t)) * 0x01010101u;
         int c = 0;
         for (int q = lane; q < nvec; q += 32) {
-          const uint4 v = vbuf[q];
-          const int wo = q << 4;
-          uint32_t m0 = ge_mask(v.x, ac, h), m1 = ge_mask(v.y, ac, h), m2 = ge_mask(v.z, ac, h), m3 = ge_mask(v.w, ac, h);
-          if (wo < lo_b || wo + 16 > hi_b) { m0 &= valid_mask(wo); m1 &= valid_mask(wo + 4); m2 &= valid_mask(wo + 8); m3 &= valid_mask(wo + 12); }
-          c += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+          uint32_t m[4];
+          masks(vbuf[q], q << 4, ac, h, m);
+          c += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
         }
         return __reduce_add_sync(FULL, c);
       };
@@ -189,12 +247,12 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
         for (int q = lane; q < nvec; q += 32) {
           const uint4 v = vbuf[q];
           const int wo = q << 4;
-          uint32_t m0 = ge_mask(v.x, ac, h), m1 = ge_mask(v.y, ac, h), m2 = ge_mask(v.z, ac, h), m3 = ge_mask(v.w, ac, h);
-          if (wo < lo_b || wo + 16 > hi_b) { m0 &= valid_mask(wo); m1 &= valid_mask(wo + 4); m2 &= valid_mask(wo + 8); m3 &= valid_mask(wo + 12); }
-          if (m0) emit(m0, v.x, wo);
-          if (m1) emit(m1, v.y, wo + 4);
-          if (m2) emit(m2, v.z, wo + 8);
-          if (m3) emit(m3, v.w, wo + 12);
+          uint32_t m[4];
+          masks(v, wo, ac, h, m);
+          if (m[0]) emit(m[0], v.x, wo);
+          if (m[1]) emit(m[1], v.y, wo + 4);
+          if (m[2]) emit(m[2], v.z, wo + 8);
+          if (m[3]) emit(m[3], v.w, wo + 12);
         }
       }
       // (2) ties at T, scanning ranges from the far end; 32 vectors (512 bytes) per step
@@ -232,9 +290,9 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
         }
         carry += __shfl_sync(FULL, suf, 0);
       }
+      __syncwarp();
+      n = min(s_n[warp], K1_CAP);  // == k
     }
-    __syncwarp();
-    const int n = min(s_n[warp], K1_CAP);  // candidates in the list (== k on the dense path)
     const int n_sel = n < k ? n : k;
     // pad to a multiple of 4 with zeros (never greater than a key)
     if (lane < 4 && n + lane < K1_CAP) list[n + lane] = 0;
@@ -257,21 +315,26 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
         const uint32_t key = sel[e];
         const int r = (int)(key & 0xffffu);
         const bool in_band = (r >= 3) && (r < n_range - 3);
-        int s[7] = {0, 0, 0, 0, 0, 0, 0};
-        const long long gbase = (long long)az * (long long)row_stride;
+        int B[13];
+        if (r >= 6 && r + 6 < n_range) {
 #pragma unroll
-        for (int t = 0; t < 13; t++) {
-          const int q = r - 6 + t;
-          int B;
-          if (q >= 0 && q < n_range) B = buf[a0 + q];
-          else {
-            const long long fi = gbase + q;  // flat index into the scan buffer, as cv::Mat::at(bearing, r_nn) addresses it
-            B = (fi >= 0 && fi < (long long)scan_bytes) ? (int)__ldg(scan_base + fi) : 0;
+          for (int t = 0; t < 13; t++) B[t] = buf[a0 + r - 6 + t];
+        } else {
+          const long long gbase = (long long)az * (long long)row_stride;
+#pragma unroll
+          for (int t = 0; t < 13; t++) {
+            const int q = r - 6 + t;
+            if (q >= 0 && q < n_range) B[t] = buf[a0 + q];
+            else {
+              const long long fi = gbase + q;  // flat index into the scan buffer, as cv::Mat::at(bearing, r_nn) addresses it
+              B[t] = (fi >= 0 && fi < (long long)scan_bytes) ? (int)__ldg(scan_base + fi) : 0;
+            }
           }
-#pragma unroll
-          for (int i = 0; i < 7; i++)
-            if (t >= i && t <= i + 6) s[i] += B;
         }
+        int s[7];  // s[i] = score at r - 3 + i = sum of the 7 bytes centred there (sliding window)
+        s[0] = B[0] + B[1] + B[2] + B[3] + B[4] + B[5] + B[6];
+#pragma unroll
+        for (int i = 1; i < 7; i++) s[i] = s[i - 1] - B[i - 1] + B[i + 6];
         if (!in_band) {
           // a score exists only where some selected in-band bin lies within 3 of the position
 #pragma unroll
@@ -300,11 +363,10 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
     uint32_t* out = row_keys + (size_t)row * k;
     for (int e = lane; e < n_sel; e += 32) out[e] = sel[e];
     if (lane == 0) row_cnt[row] = (uint16_t)n_sel;
-    __syncwarp();
+    __syncwarp();  // every lane is done with buf / list / sel before the next iteration reuses them
     cur ^= 1;
-    a0 = a0_next;
+    in_flight = next_in_flight;
   }
-  cp_async_wait<0>();
 }
 
 // K2: rows -> ordered clouds.  One CTA per scan.
@@ -457,18 +519,21 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int blocks_needed = (total_rows + K1_WARPS - 1) / K1_WARPS;
-  const int ctas_per_sm = (int)((200 * 1024) / ((size_t)K1_WARPS * 2 * (((n_range + 31) / 16) * 16) + 9 * 1024));
-  const int max_grid = dev_sms * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
-  const int grid = blocks_needed < max_grid ? blocks_needed : max_grid;  // persistent: resident CTAs only, rows strided over warps
-  const int rowbuf = ((n_range + 16 + 15) / 16) * 16;  // row + alignment slack, multiple of 16
+  const int rowbuf = ((n_range + 16 + 15 + 127) / 128) * 128;  // row + alignment slack, multiple of 128
   const size_t k1_smem = (size_t)K1_WARPS * 2 * rowbuf;
+  // resident CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA, ~8.3 KB static (lists, barriers)
+  int ctas_per_sm = (int)((228 * 1024) / (k1_smem + 8500 + 1024));
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  const int max_grid = dev_sms * ctas_per_sm;
+  const int grid = blocks_needed < max_grid ? blocks_needed : max_grid;  // persistent: resident CTAs only, rows strided over warps
   static bool attr_set = false;
   if (!attr_set) {
-    TBV_CUDA(cudaFuncSetAttribute(k1_kstrongest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TBV_CUDA(cudaFuncSetAttribute(k1_kstrongest, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr_set = true;
   }
+  const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
   k1_kstrongest<<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
-                                                             F.row_keys.p, F.row_cnt.p);
+                                                             polar_dev, buf_hi, F.row_keys.p, F.row_cnt.p);
   launched(ctx, "k1_kstrongest");
   TBV_CUDA(cudaGetLastError());
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
