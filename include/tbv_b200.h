@@ -273,6 +273,51 @@ typedef struct tbv_pgo_params {
 int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, int n_con, const int* ids, const double* meas, const double* info,
                      const tbv_pgo_params* params, int fixed_node, double* cost, double* H_diag, double* H_off, double* g, double* residuals);
 
+/* ---- loop-closure keyframe database + sharded candidate registration ---------------------------------------------------
+ * The loop-closure thread registers every Scan-Context candidate (from, to) with loopclosure::RegisterLoopCandidate ->
+ * loopclosure::Register (tbv_slam/src/tbv_slam/loopclosure.cpp:320-364, 35-97) against cells kept in the pose graph's
+ * RadarScan nodes (cloud_normal_, cfear_radarodometry/include/cfear_radarodometry/types.h).  tbv_loopdb keeps those cell
+ * sets (and their 4 m search grids) resident in HBM, so a batch of candidates is ONE kernel launch with no cell upload;
+ * candidates are independent, so a batch shards over GPUs by candidate with every rank holding the whole database
+ * (SURVEY 8e); accepted constraints come back as fixed-size records ready for an all-gather.
+ *
+ * tbv_constraint mirrors Constraint3d (cfear_radarodometry/include/cfear_radarodometry/types.h:155-172) for a planar
+ * pose: t_be = Talign = Trevised^-1 * Tto as (x, y, theta); cov = reg_cov of the moving scan (diag(0.1^2, 0.1^2, 0.01^2),
+ * n_scan_normal.cpp:171-175) with its translation block rotated into the revised frame (loopclosure.cpp:93):
+ * (xx, xy, yy, tt); the reference stores information = cov^-1.  128 bytes. */
+typedef struct tbv_constraint {
+  int32_t id_begin, id_end;   /* from, to (keyframe ids in the database) */
+  int32_t type;               /* ConstraintType: 0 odometry, 1 loop_appearance (types.h:153) */
+  int32_t candidate;          /* index of the candidate in the caller's (global) list: all-gather order key */
+  double t_be[3];
+  double cov[4];
+  double score;               /* n_scan_normal_reg::getScore() = final_cost / num_residuals */
+  double t_revised[3];        /* Trevised (world pose of `from` after registration) */
+  int32_t itrs, num_residuals;
+  double quality[2];          /* caller-defined (sc_sim, odom_bounds), copied from the candidate list */
+} tbv_constraint;
+
+typedef struct tbv_loopdb tbv_loopdb;
+tbv_loopdb* tbv_loopdb_create(tbv_ctx* ctx, int max_keyframes, int cell_capacity);
+void tbv_loopdb_destroy(tbv_loopdb* db);
+/* appends n_sets cell sets (keyframes); ids are assigned consecutively from the current size, which is returned in
+ * *first_id.  One H2D per set + one grid-build launch for the whole batch. */
+int tbv_loopdb_add(tbv_loopdb* db, int n_sets, const tbv_cell* const* sets, const int* n_cells, int* first_id);
+int tbv_loopdb_size(tbv_loopdb* db);
+/* Registers n_cand candidates in one launch.  from/to: keyframe ids; T_from/T_to: [n_cand][3] initial world poses
+ * (Tfrom = pose of `from`, Tto = Tfrom * guess, loopclosure.cpp:337-338); candidate_index (optional): global index
+ * stored in the record (default: the local index); quality (optional): [n_cand][2] copied through.
+ * Accepted = Register returned true (and score <= max_score when max_score > 0).  Accepted constraints are written in
+ * candidate order to out[0..*n_out) (host), at most out_capacity; summaries (optional) [n_cand] receives every result. */
+int tbv_loopdb_register(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
+                        const int* candidate_index, const double* quality, const tbv_reg_params* params, double max_score,
+                        tbv_constraint* out, int out_capacity, int* n_out, tbv_reg_summary* summaries);
+/* Same, results left on the device for a collective: out_dev [out_capacity] records, n_out_dev one int.  Enqueued on the
+ * context's stream; no host synchronisation. */
+int tbv_loopdb_register_dev(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
+                            const int* candidate_index, const double* quality, const tbv_reg_params* params, double max_score,
+                            tbv_constraint* out_dev, int out_capacity, int* n_out_dev);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
 void* tbv_host_alloc(size_t bytes);
 void tbv_host_free(void* p);

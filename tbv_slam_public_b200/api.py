@@ -143,6 +143,14 @@ _OPTIONAL = [
     ("tbv_odom_collect", [C.c_void_p, C.c_void_p], None),
     ("tbv_odom_cells", [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
     ("tbv_filter_cacfar", [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(CfarParams), C.POINTER(Points)], None),
+    ("tbv_loopdb_create", [C.c_void_p, C.c_int, C.c_int], C.c_void_p),
+    ("tbv_loopdb_destroy", [C.c_void_p], None),
+    ("tbv_loopdb_size", [C.c_void_p], None),
+    ("tbv_loopdb_add", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], None),
+    ("tbv_loopdb_register", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.POINTER(RegParams), C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
+    ("tbv_loopdb_register_dev", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(RegParams), C.c_double, C.c_void_p, C.c_int, C.c_void_p], None),
 ]
 
 
@@ -333,6 +341,79 @@ class Context:
         _check(lib().tbv_register_batch(self.h, len(arrs), ptrs, _ptr(ns), n, _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), C.byref(params),
                                         _ptr(Tr), _ptr(Ta), C.cast(summ, C.c_void_p)))
         return Tr, Ta, summ
+
+
+# tbv_constraint (include/tbv_b200.h): Constraint3d for a planar pose, 128 bytes — the record all-gathered between GPUs
+CONSTRAINT_DTYPE = np.dtype([("id_begin", np.int32), ("id_end", np.int32), ("type", np.int32), ("candidate", np.int32),
+                             ("t_be", np.float64, 3), ("cov", np.float64, 4), ("score", np.float64), ("t_revised", np.float64, 3),
+                             ("itrs", np.int32), ("num_residuals", np.int32), ("quality", np.float64, 2)])
+assert CONSTRAINT_DTYPE.itemsize == 128
+
+
+def loop_reg_params(**kw) -> RegParams:
+    """loopclosure::Register: n_scan_normal_reg(P2L) with ctor defaults (Huber 0.1, uniform weights) + SetParameters(4, 10)."""
+    return default_reg_params(max_itr_association=4, max_itr_solver=10, **kw)
+
+
+class LoopDB:
+    """Keyframe cell sets resident on the GPU + batched loopclosure::RegisterLoopCandidate (tbv_loopdb_*)."""
+
+    def __init__(self, ctx: Context, max_keyframes: int, cell_capacity: int = 1024):
+        self.ctx, self.cell_capacity = ctx, cell_capacity
+        self.h = lib().tbv_loopdb_create(ctx.h, max_keyframes, cell_capacity)
+        if not self.h:
+            raise TbvError(TBV_ERR_CUDA, lib().tbv_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tbv_loopdb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return lib().tbv_loopdb_size(self.h)
+
+    def add(self, sets) -> int:
+        """Appends keyframes (each an [n,16] array of tbv_cell records); returns the id of the first one."""
+        arrs, ptrs, ns = Context._scan_ptrs(sets)
+        first = C.c_int(0)
+        _check(lib().tbv_loopdb_add(self.h, len(arrs), ptrs, _ptr(ns), C.byref(first)))
+        return first.value
+
+    @staticmethod
+    def _cand_args(id_from, id_to, T_from, T_to, candidate_index, quality):
+        fs = np.ascontiguousarray(id_from, np.int32); ts = np.ascontiguousarray(id_to, np.int32)
+        Tf = np.ascontiguousarray(T_from, np.float64).reshape(-1, 3); Tt = np.ascontiguousarray(T_to, np.float64).reshape(-1, 3)
+        ci = None if candidate_index is None else np.ascontiguousarray(candidate_index, np.int32)
+        q = None if quality is None else np.ascontiguousarray(quality, np.float64).reshape(-1, 2)
+        return fs, ts, Tf, Tt, ci, q
+
+    def register_candidates(self, id_from, id_to, T_from, T_to, candidate_index=None, quality=None, params: RegParams | None = None,
+                            max_score=0.0, want_summaries=False):
+        """Returns the accepted constraints (CONSTRAINT_DTYPE array, candidate order) [and every candidate's RegSummary]."""
+        params = params or loop_reg_params()
+        fs, ts, Tf, Tt, ci, q = self._cand_args(id_from, id_to, T_from, T_to, candidate_index, quality)
+        n = len(fs)
+        out = np.zeros(max(n, 1), CONSTRAINT_DTYPE)
+        n_out = C.c_int(0)
+        summ = (RegSummary * max(n, 1))() if want_summaries else None
+        _check(lib().tbv_loopdb_register(self.h, n, _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), _ptr(ci), _ptr(q), C.byref(params),
+                                         float(max_score), _ptr(out), n, C.byref(n_out), C.cast(summ, C.c_void_p) if summ else None))
+        out = out[:n_out.value].copy()
+        return (out, summ) if want_summaries else out
+
+    def register_candidates_dev(self, id_from, id_to, T_from, T_to, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int,
+                                candidate_index=None, quality=None, params: RegParams | None = None, max_score=0.0):
+        """Same, leaving the records on the device (for a collective); enqueued on the context's stream."""
+        params = params or loop_reg_params()
+        fs, ts, Tf, Tt, ci, q = self._cand_args(id_from, id_to, T_from, T_to, candidate_index, quality)
+        _check(lib().tbv_loopdb_register_dev(self.h, len(fs), _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), _ptr(ci), _ptr(q), C.byref(params),
+                                             float(max_score), C.c_void_p(out_dev_ptr), out_capacity, C.c_void_p(n_out_dev_ptr)))
 
 
 class OdometryKeyframeFuser:
