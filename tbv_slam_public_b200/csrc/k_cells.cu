@@ -34,11 +34,12 @@ struct CellsScratch {
   DevBuf<GridInfo> grid;
   DevBuf<int> vox_idx, vox_start, vox_fill, sample_vox, sorted_raw, sorted, err;
   DevBuf<float> cx, cy;
+  DevBuf<float> sx, sy, si;     // [batch][cap_pts] voxel-sorted copy of the cloud (C4 -> C5)
   DevBuf<double> cand;          // [batch][CELL_FIELDS][max_samples]
   DevBuf<uint8_t> cand_valid;   // [batch][max_samples]
   void release() {
     grid.release(); vox_idx.release(); vox_start.release(); vox_fill.release(); sample_vox.release(); sorted_raw.release();
-    sorted.release(); err.release(); cx.release(); cy.release(); cand.release(); cand_valid.release();
+    sorted.release(); err.release(); cx.release(); cy.release(); cand.release(); cand_valid.release(); sx.release(); sy.release(); si.release();
   }
 };
 
@@ -178,45 +179,54 @@ __global__ void c3_scatter(const GridInfo* __restrict__ grid, const int* __restr
 }
 
 // ---- C4 -------------------------------------------------------------------------------------------------------
-// One warp per sample: order the voxel's points by cloud index ([DEV-1]: PCL's std::sort leaves the intra-voxel order
-// to libstdc++'s introsort; ascending index is used here and in the oracle's default mode), then accumulate the
-// centroid in float exactly like pcl::CentroidPoint (sum, then divide by (float)n).
+// Eight lanes per sample: order the voxel's points by cloud index ([DEV-1]: PCL's std::sort leaves the intra-voxel order
+// to libstdc++'s introsort; ascending index is used here and in the oracle's default mode), write them out in that order
+// as a voxel-sorted struct-of-arrays copy of the cloud (x, y, intensity as float) — what C5 streams, coalesced — then
+// accumulate the centroid in float exactly like pcl::CentroidPoint (sum in order, then divide by (float)n).
+constexpr int C4_LANES = 8;
 __global__ void __launch_bounds__(128)
 c4_centroids(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, int cap_pts, int vox_cap,
-             const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ sample_vox,
-             const int* __restrict__ vox_start, const int* __restrict__ sorted_raw, int* __restrict__ sorted,
-             float* __restrict__ cx, float* __restrict__ cy) {
+             const float* __restrict__ x, const float* __restrict__ y, const uint8_t* __restrict__ inten_u8, const float* __restrict__ inten_f32,
+             const int* __restrict__ sample_vox, const int* __restrict__ vox_start, const int* __restrict__ sorted_raw,
+             float* __restrict__ sx_out, float* __restrict__ sy_out, float* __restrict__ si_out, float* __restrict__ cx, float* __restrict__ cy) {
   const int scan = blockIdx.y;
   if (!grid[scan].ok) return;
   const int ns = n_samples[scan];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sub = lane & (C4_LANES - 1);
+  const unsigned gmask = ((1u << C4_LANES) - 1u) << (lane & ~(C4_LANES - 1));
+  const int group = threadIdx.x / C4_LANES, groups_per_cta = 128 / C4_LANES;
   const float* px = x + (size_t)scan * cap_pts;
   const float* py = y + (size_t)scan * cap_pts;
+  const uint8_t* pi8 = inten_u8 ? inten_u8 + (size_t)scan * cap_pts : nullptr;
+  const float* pif = inten_f32 ? inten_f32 + (size_t)scan * cap_pts : nullptr;
   const int* vs = vox_start + (size_t)scan * (vox_cap + 1);
   const int* sr = sorted_raw + (size_t)scan * cap_pts;
-  int* so = sorted + (size_t)scan * cap_pts;
-  for (int s = blockIdx.x * 4 + warp; s < ns; s += gridDim.x * 4) {
+  float* ox = sx_out + (size_t)scan * cap_pts;
+  float* oy = sy_out + (size_t)scan * cap_pts;
+  float* oi = si_out + (size_t)scan * cap_pts;
+  for (int s = blockIdx.x * groups_per_cta + group; s < ns; s += gridDim.x * groups_per_cta) {
     const int v = sample_vox[(size_t)scan * max_samples + s];
     const int s0 = vs[v], n = vs[v + 1] - s0;
-    for (int e = lane; e < n; e += 32) {
+    for (int e = sub; e < n; e += C4_LANES) {
       const int my = sr[s0 + e];
       int rank = 0;
       for (int j = 0; j < n; j++) rank += (sr[s0 + j] < my);
-      so[s0 + rank] = my;
+      ox[s0 + rank] = px[my];
+      oy[s0 + rank] = py[my];
+      oi[s0 + rank] = pi8 ? (float)pi8[my] : pif[my];
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncwarp(gmask);
+    if (sub == 0) {
       float sx = 0.f, sy = 0.f;
       for (int j = 0; j < n; j++) {
-        const int i = so[s0 + j];
-        sx += px[i];
-        sy += py[i];
+        sx += ox[s0 + j];
+        sy += oy[s0 + j];
       }
       const float fn = (float)n;
       cx[(size_t)scan * max_samples + s] = sx / fn;
       cy[(size_t)scan * max_samples + s] = sy / fn;
     }
-    __syncwarp();
+    __syncwarp(gmask);
   }
 }
 
@@ -283,33 +293,35 @@ __device__ void self_adjoint_eig2(double m00, double m10, double m11, double eva
   evec[0][0] = Q00; evec[0][1] = Q01; evec[1][0] = Q10; evec[1][1] = Q11;
 }
 
-// One warp per sample point.  The neighbour SET is exact (float distance test of the FLANN radius search, strict <); the
-// statistics follow cell::cell's formulas (normalised weights, mean, covariance about the mean; pointnormal.cpp:13-33) with
-// per-lane partial sums in window-scan order and a fixed xor-tree across lanes: deterministic, and within a few ulp of the
-// reference's neighbour-order sums (cells are tolerance-parity, the neighbour counts are exact).
+// Sixteen lanes per sample point (a window row holds ~13 points: a full warp would idle).  The neighbour SET is exact (float
+// distance test of the FLANN radius search, strict <); the statistics follow cell::cell's formulas (normalised weights, mean,
+// covariance about the mean; pointnormal.cpp:13-33) with per-lane partial sums in window-scan order and a fixed xor-tree
+// across the 16 lanes: deterministic, and within a few ulp of the reference's neighbour-order sums (cells are
+// tolerance-parity, the neighbour counts are exact).  Points are streamed from the voxel-sorted copy written by C4:
+// consecutive lanes read consecutive floats.
+constexpr int C5_LANES = 16;
 __global__ void __launch_bounds__(C5_WARPS * 32)
 c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, int cap_pts, int vox_cap,
-         const float* __restrict__ x, const float* __restrict__ y, const uint8_t* __restrict__ inten_u8, const float* __restrict__ inten_f32,
-         const int* __restrict__ vox_start, const int* __restrict__ sorted, const float* __restrict__ cx, const float* __restrict__ cy,
+         const float* __restrict__ sx_in, const float* __restrict__ sy_in, const float* __restrict__ si_in,
+         const int* __restrict__ vox_start, const float* __restrict__ cx, const float* __restrict__ cy,
          float radius, int weight_intensity, double* __restrict__ cand) {
   const int scan = blockIdx.y;
   const GridInfo g = grid[scan];
   if (!g.ok) return;
   const int ns = n_samples[scan];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned FULL = 0xffffffffu;
-  const float* px = x + (size_t)scan * cap_pts;
-  const float* py = y + (size_t)scan * cap_pts;
-  const uint8_t* pi8 = inten_u8 ? inten_u8 + (size_t)scan * cap_pts : nullptr;
-  const float* pif = inten_f32 ? inten_f32 + (size_t)scan * cap_pts : nullptr;
+  const int lane = threadIdx.x & 31, sub = lane & (C5_LANES - 1);
+  const unsigned gmask = 0xffffu << (lane & ~(C5_LANES - 1));
+  const int group = threadIdx.x / C5_LANES, groups_per_cta = C5_WARPS * 32 / C5_LANES;
+  const float* px = sx_in + (size_t)scan * cap_pts;
+  const float* py = sy_in + (size_t)scan * cap_pts;
+  const float* pi = si_in + (size_t)scan * cap_pts;
   const int* vs = vox_start + (size_t)scan * (vox_cap + 1);
-  const int* so = sorted + (size_t)scan * cap_pts;
   const float r2 = (float)((double)radius * (double)radius);  // pcl::KdTreeFLANN::radiusSearch: static_cast<float>(radius*radius)
   const float eps = 1e-3f;
   double* cnd = cand + (size_t)scan * CELL_FIELDS * max_samples;
   const size_t st = max_samples;
 
-  for (int s = blockIdx.x * C5_WARPS + warp; s < ns; s += gridDim.x * C5_WARPS) {
+  for (int s = blockIdx.x * groups_per_cta + group; s < ns; s += gridDim.x * groups_per_cta) {
     const float qx = cx[(size_t)scan * max_samples + s], qy = cy[(size_t)scan * max_samples + s];
     // voxel window that certainly contains every point with d2 < r2
     int ix0 = (int)(floorf((qx - radius - eps) * g.inv_leaf) - (float)g.min_bx);
@@ -322,66 +334,60 @@ c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, i
     double wsum = 0.0;
     for (int iy = iy0; iy <= iy1; iy++) {
       const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
-      for (int j = a + lane; j < b; j += 32) {
-        const int i = so[j];
-        const float dx = qx - px[i], dy = qy - py[i];
+      for (int j = a + sub; j < b; j += C5_LANES) {
+        const float dx = qx - px[j], dy = qy - py[j];
         float d = dx * dx;        // FLANN L2_Simple: result += diff*diff per dimension (z contributes +0)
         d = d + dy * dy;
         if (d < r2) {
           cnt++;
-          const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
-          wsum += weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0;
+          wsum += weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0;
         }
       }
     }
-    for (int d = 16; d > 0; d >>= 1) { cnt += __shfl_xor_sync(FULL, cnt, d); wsum += __shfl_xor_sync(FULL, wsum, d); }
+    for (int d = C5_LANES / 2; d > 0; d >>= 1) { cnt += __shfl_xor_sync(gmask, cnt, d); wsum += __shfl_xor_sync(gmask, wsum, d); }
     if (cnt < 6) {  // pointnormal.cpp:291
-      if (lane == 0) cnd[CF_NS * st + s] = 0.0;
+      if (sub == 0) cnd[CF_NS * st + s] = 0.0;
       continue;
     }
     // pass 2: mean
     double u0 = 0.0, u1 = 0.0;
     for (int iy = iy0; iy <= iy1; iy++) {
       const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
-      for (int j = a + lane; j < b; j += 32) {
-        const int i = so[j];
-        const float fx = px[i], fy = py[i];
+      for (int j = a + sub; j < b; j += C5_LANES) {
+        const float fx = px[j], fy = py[j];
         const float dx = qx - fx, dy = qy - fy;
         float d = dx * dx;
         d = d + dy * dy;
         if (d < r2) {
-          const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
-          const double w = (weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0) / wsum;
+          const double w = (weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0) / wsum;
           u0 += w * (double)fx;
           u1 += w * (double)fy;
         }
       }
     }
-    for (int d = 16; d > 0; d >>= 1) { u0 += __shfl_xor_sync(FULL, u0, d); u1 += __shfl_xor_sync(FULL, u1, d); }
+    for (int d = C5_LANES / 2; d > 0; d >>= 1) { u0 += __shfl_xor_sync(gmask, u0, d); u1 += __shfl_xor_sync(gmask, u1, d); }
     // pass 3: covariance about the mean
     double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
     for (int iy = iy0; iy <= iy1; iy++) {
       const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
-      for (int j = a + lane; j < b; j += 32) {
-        const int i = so[j];
-        const float fx = px[i], fy = py[i];
+      for (int j = a + sub; j < b; j += C5_LANES) {
+        const float fx = px[j], fy = py[j];
         const float dx = qx - fx, dy = qy - fy;
         float d = dx * dx;
         d = d + dy * dy;
         if (d < r2) {
-          const double inten = pi8 ? (double)(float)pi8[i] : (double)pif[i];
-          const double w = (weight_intensity ? fmax(inten - 60.0, 0.0) : 1.0) / wsum;
+          const double w = (weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0) / wsum;
           const double d0 = (double)fx - u0, d1 = (double)fy - u1;
           const double xw0 = w * d0, xw1 = w * d1;
           c00 += d0 * xw0; c01 += d0 * xw1; c10 += d1 * xw0; c11 += d1 * xw1;
         }
       }
     }
-    for (int d = 16; d > 0; d >>= 1) {
-      c00 += __shfl_xor_sync(FULL, c00, d); c01 += __shfl_xor_sync(FULL, c01, d);
-      c10 += __shfl_xor_sync(FULL, c10, d); c11 += __shfl_xor_sync(FULL, c11, d);
+    for (int d = C5_LANES / 2; d > 0; d >>= 1) {
+      c00 += __shfl_xor_sync(gmask, c00, d); c01 += __shfl_xor_sync(gmask, c01, d);
+      c10 += __shfl_xor_sync(gmask, c10, d); c11 += __shfl_xor_sync(gmask, c11, d);
     }
-    if (lane == 0) {
+    if (sub == 0) {
       cnd[CF_U0 * st + s] = u0; cnd[CF_U1 * st + s] = u1;
       cnd[CF_C00 * st + s] = c00; cnd[CF_C01 * st + s] = c01; cnd[CF_C10 * st + s] = c10; cnd[CF_C11 * st + s] = c11;
       cnd[CF_SUMI * st + s] = wsum;
@@ -497,7 +503,8 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
   if ((rc = S.grid.reserve(batch)) || (rc = S.err.reserve(batch)) || (rc = S.vox_idx.reserve((size_t)batch * cap_pts)) ||
       (rc = S.vox_start.reserve((size_t)batch * (vox_cap + 1))) || (rc = S.vox_fill.reserve((size_t)batch * vox_cap)) ||
       (rc = S.sample_vox.reserve((size_t)batch * max_samples)) || (rc = S.sorted_raw.reserve((size_t)batch * cap_pts)) ||
-      (rc = S.sorted.reserve((size_t)batch * cap_pts)) || (rc = S.cx.reserve((size_t)batch * max_samples)) ||
+      (rc = S.sx.reserve((size_t)batch * cap_pts)) || (rc = S.sy.reserve((size_t)batch * cap_pts)) ||
+      (rc = S.si.reserve((size_t)batch * cap_pts)) || (rc = S.cx.reserve((size_t)batch * max_samples)) ||
       (rc = S.cy.reserve((size_t)batch * max_samples)) || (rc = S.cand.reserve((size_t)batch * CELL_FIELDS * max_samples)) ||
       (rc = S.cand_valid.reserve((size_t)batch * max_samples)))
     return rc;
@@ -516,13 +523,13 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
     launched(ctx, "c3_scatter");
   }
   {
-    const int gx = (max_samples + 3) / 4 < 96 ? (max_samples + 3) / 4 : 96;
-    c4_centroids<<<dim3(gx, batch), 128, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, S.sample_vox.p, S.vox_start.p,
-                                                  S.sorted_raw.p, S.sorted.p, S.cx.p, S.cy.p);
+    const int g4 = 128 / C4_LANES, gx = (max_samples + g4 - 1) / g4 < 48 ? (max_samples + g4 - 1) / g4 : 48;
+    c4_centroids<<<dim3(gx, batch), 128, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, inten_u8, inten_f32, S.sample_vox.p,
+                                                  S.vox_start.p, S.sorted_raw.p, S.sx.p, S.sy.p, S.si.p, S.cx.p, S.cy.p);
     launched(ctx, "c4_centroids");
-    const int g5 = (max_samples + C5_WARPS - 1) / C5_WARPS < 48 ? (max_samples + C5_WARPS - 1) / C5_WARPS : 48;
-    c5_cells<<<dim3(g5, batch), C5_WARPS * 32, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, x, y, inten_u8, inten_f32,
-                                                        S.vox_start.p, S.sorted.p, S.cx.p, S.cy.p, par.radius, par.weight_intensity, S.cand.p);
+    const int gp = C5_WARPS * 32 / C5_LANES, g5 = (max_samples + gp - 1) / gp < 48 ? (max_samples + gp - 1) / gp : 48;
+    c5_cells<<<dim3(g5, batch), C5_WARPS * 32, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, cap_pts, vox_cap, S.sx.p, S.sy.p, S.si.p,
+                                                        S.vox_start.p, S.cx.p, S.cy.p, par.radius, par.weight_intensity, S.cand.p);
     launched(ctx, "c5_cells");
   }
   c6_compact<<<batch, 256, 0, st>>>(S.grid.p, out.n_samples.p, max_samples, S.cand.p, par.origin[0], par.origin[1], out.f64.p, cell_cap, out.count.p,

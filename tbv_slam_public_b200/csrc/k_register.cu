@@ -25,6 +25,7 @@
 // fp64 throughout (fp32 only where the reference uses float: the NN search), built with -fmad=false.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "tbv_reg.cuh"
 
@@ -249,7 +250,7 @@ __device__ bool chol_solve3(const double H[3][3], const double b[3], double y[3]
 }
 
 // after the evaluation at the initial point (acc = cost, g, H)
-__device__ void lm_begin(LMState& S, const double x0[3], const double* acc) {
+__device__ __noinline__ void lm_begin(LMState& S, const double x0[3], const double* acc) {
   for (int c = 0; c < 3; c++) { S.x[c] = x0[c]; S.params[c] = x0[c]; }
   S.x_norm = sqrt(S.x[0] * S.x[0] + S.x[1] * S.x[1] + S.x[2] * S.x[2]);
   S.radius = 1e4; S.decrease_factor = 2.0; S.reuse_diagonal = false;
@@ -274,7 +275,7 @@ __device__ void lm_begin(LMState& S, const double x0[3], const double* acc) {
 
 // FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep (+ HandleInvalidStep loop).
 // Returns true when S.cand must be evaluated; false when the solve is over.
-__device__ bool lm_advance(LMState& S, int max_iterations) {
+__device__ __noinline__ bool lm_advance(LMState& S, int max_iterations) {
   if (S.terminated) return false;
   for (;;) {
     // ---- Finalize
@@ -338,7 +339,7 @@ __device__ bool lm_advance(LMState& S, int max_iterations) {
 }
 
 // after the evaluation at S.cand (acc = cost, g, H there)
-__device__ void lm_candidate(LMState& S, const double* acc) {
+__device__ __noinline__ void lm_candidate(LMState& S, const double* acc) {
   double candidate_cost = acc[0];
   if (!isfinite(candidate_cost)) candidate_cost = DBL_MAX;
   {
@@ -519,22 +520,121 @@ __device__ __forceinline__ int nn_search(const SetView& t, int n_tgt, float qx, 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 constexpr int RG_MAX_FIXED = 16;
 
+// State of n_scan_normal_reg::Register's association loop (n_scan_normal.cpp:96-160), advanced by one thread.
+struct OuterState {
+  double par[3], prev_par[3], tsrc[3];   // parameters.back(), its previous value, Tsrc.back()
+  double prev_score, final_cost, last_rel_dec;
+  int total_lm, itr, pose_updated, success, num_residuals, last_n_iterations, termination;
+  int go;                                // 1: run another association round
+};
+
+// After one ceres::Solve (state S): the bookkeeping of n_scan_normal.cpp:112-158 and the loop header's itr++ / condition.
+__device__ __noinline__ void outer_advance(OuterState& O, const LMState& S, int num_residuals, int max_itr_association) {
+  O.num_residuals = num_residuals;
+  O.par[0] = S.params[0]; O.par[1] = S.params[1]; O.par[2] = S.params[2];
+  O.final_cost = fmin(S.initial_cost, S.min_pushed_cost);  // SetSummaryFinalCost
+  O.last_rel_dec = S.last_rel_dec;
+  O.last_n_iterations = S.n_pushed;
+  O.termination = S.termination;
+  O.total_lm += O.last_n_iterations - 1;
+  O.success = O.termination != 2;  // IsSolutionUsable
+  if (O.success) { O.pose_updated = 1; O.tsrc[0] = O.par[0]; O.tsrc[1] = O.par[1]; O.tsrc[2] = O.par[2]; }
+  const double current_score = O.final_cost;
+  const double rel_improvement = (O.prev_score - current_score) / O.prev_score;
+  O.go = 0;
+  if (O.itr > 3) {  // min_itr_ = 3
+    if (O.prev_score < current_score) {
+      O.par[0] = O.prev_par[0]; O.par[1] = O.prev_par[1]; O.par[2] = O.prev_par[2];
+      return;
+    } else if (rel_improvement < 0.00001) {
+      return;
+    } else if (O.last_rel_dec < 0.00001 || O.last_n_iterations == 1) {
+      return;
+    }
+  }
+  O.prev_score = current_score;
+  O.prev_par[0] = O.par[0]; O.prev_par[1] = O.par[1]; O.prev_par[2] = O.par[2];
+  O.itr++;
+  O.go = (O.itr <= max_itr_association && O.success) ? 1 : 0;
+}
+
 struct RegShared {
   double acc[NACC];
   double warp_acc[RG_WARPS][NACC];
   double ex[3], cs[2];
-  int flag, n_blocks, warp_cnt[RG_WARPS], running;
+  int flag, n_blocks, warp_cnt[RG_WARPS];
   Aff Tst[RG_MAX_FIXED], Ttar[RG_MAX_FIXED];
   SetView tgt[RG_MAX_FIXED];
   int n_tgt[RG_MAX_FIXED];
   LMState lm;
+  OuterState outer;
 };
 
-__global__ void __launch_bounds__(RG_THREADS, 2)
+// Fast evaluation of one residual block for the losses whose second derivative is never positive (Huber, none): Ceres'
+// Corrector then always takes its first branch (alpha = 0), so rho'' itself — one fp64 division per block in the generic
+// code — is not needed, and an inlier block's sqrt(rho') is sqrt(w), precomputed at association time (field 8).  Every
+// remaining operation is the generic path's, in the same order: results are bit-identical to eval_block.
+template <int COST, bool HUBER>
+__device__ __forceinline__ void eval_block_simple(const double* __restrict__ blk, size_t stride, double limit, double x0, double x1, double cy,
+                                                  double sy, double* __restrict__ a) {
+  const double sx = blk[0], sy_ = blk[stride], tx = blk[2 * stride], ty = blk[3 * stride];
+  const double a4 = blk[4 * stride], a5 = blk[5 * stride], w = blk[7 * stride], sw = blk[8 * stride];
+  const double mx = (cy * sx + (-sy) * sy_) + x0;
+  const double my = (sy * sx + cy * sy_) + x1;
+  const double dmx = (-sy) * sx + (-cy) * sy_;
+  const double dmy = cy * sx + (-sy) * sy_;
+  constexpr int n = (COST == TBV_P2L) ? 1 : 2;
+  double f[2], J[6];
+  if (COST == TBV_P2L) {
+    const double v0 = mx - tx, v1 = my - ty;
+    f[0] = v0 * a4 + v1 * a5;
+    J[0] = a4; J[1] = a5; J[2] = dmx * a4 + dmy * a5;
+  } else if (COST == TBV_P2P) {
+    f[0] = tx - mx; f[1] = ty - my;
+    J[0] = -1.0; J[1] = 0.0; J[2] = -dmx; J[3] = 0.0; J[4] = -1.0; J[5] = -dmy;
+  } else {
+    const double a6 = blk[6 * stride];
+    const double e0 = mx - tx, e1 = my - ty;
+    f[0] = a4 * e0 + 0.0 * e1;
+    f[1] = a5 * e0 + a6 * e1;
+    J[0] = a4; J[1] = 0.0; J[2] = a4 * dmx + 0.0 * dmy;
+    J[3] = a5; J[4] = a6; J[5] = a5 * dmx + a6 * dmy;
+  }
+  double sq = 0.0;
+#pragma unroll
+  for (int r = 0; r < n; r++) sq += f[r] * f[r];
+  double rho0, sqrt_rho1;
+  const double b = limit * limit;
+  if (HUBER && sq > b) {
+    const double r = sqrt(sq);
+    rho0 = (2.0 * limit * r - b) * w;
+    sqrt_rho1 = sqrt(fmax(DBL_MIN, limit / r) * w);
+  } else {
+    rho0 = HUBER ? sq * w : w * sq;
+    sqrt_rho1 = sw;
+  }
+  a[0] += 0.5 * rho0;
+#pragma unroll
+  for (int r = 0; r < n; r++) {
+    const double j0 = J[r * 3 + 0] * sqrt_rho1, j1 = J[r * 3 + 1] * sqrt_rho1, j2 = J[r * 3 + 2] * sqrt_rho1, fr = f[r] * sqrt_rho1;
+    a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
+    a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
+  }
+}
+
+template <int COST, bool HUBER>
+__device__ __forceinline__ void eval_loop_simple(const double* __restrict__ blocks, size_t bstride, int nblk, double limit, double x0, double x1,
+                                                 double cy, double sy, int tid, double* __restrict__ a) {
+  for (int q = tid; q < nblk; q += RG_THREADS) eval_block_simple<COST, HUBER>(blocks + q, bstride, limit, x0, x1, cy, sy, a);
+}
+
+// MIN_CTAS: resident CTAs per SM the register budget is set for (3 -> 80 registers, 4 -> 64)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(RG_THREADS, MIN_CTAS)
 k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
            const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
            double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
-           double* __restrict__ residuals_all) {
+           double* __restrict__ residuals_all, double* __restrict__ wgt_all) {
   __shared__ RegShared sh;
   const int p = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -556,6 +656,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   const int n_fixed = min(prob.n_fixed, RG_MAX_FIXED);
   const size_t bstride = (size_t)max_fixed * slot_cap;
   int* assoc = assoc_all + (size_t)p * bstride;
+  double* wgt = wgt_all + (size_t)p * bstride;
   double* blocks = blocks_all + (size_t)p * BLK_FIELDS * bstride;
   const int nres_per_block = (P.cost == TBV_P2L) ? 1 : 2;
   if (tid < n_fixed) {
@@ -564,8 +665,10 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   }
   __syncthreads();
 
-  // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan): one thread per (fixed, source)
-  // slot; accepted correspondences are compacted in slot order = the order the reference adds its residual blocks in.
+  // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan).  Slot = (fixed scan, source
+  // cell), fixed-major: the order the reference adds its residual blocks in.  Every warp owns a contiguous slot range:
+  // pass 1 searches and counts, one barrier publishes the per-warp counts, pass 2 writes the accepted correspondences of
+  // the warp's range at their final, ordered positions.  Two barriers per association round, whatever the slot count.
   auto associate = [&](const double x[3], double R) {
     if (tid < n_fixed) {
       const double* fp = fixed_pose + (size_t)(prob.fixed_first + tid) * 3;
@@ -573,23 +676,23 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       sh.Ttar[tid] = Ttar;
       sh.Tst[tid] = aff_mul(aff_inv(Ttar), vec_to_aff(x[0], x[1], x[2]));
     }
-    if (tid == 0) sh.running = 0;
     __syncthreads();
     const int n_slots = n_fixed * n_src;
-    for (int base = 0; base < n_slots; base += RG_THREADS) {
-      const int slot = base + tid;
+    const int chunk = (((n_slots + RG_WARPS - 1) / RG_WARPS) + 31) & ~31;
+    const int s_begin = min(n_slots, warp * chunk), s_end = min(n_slots, s_begin + chunk);
+    int my_cnt = 0;
+    for (int base = s_begin; base < s_end; base += 32) {
+      const int slot = base + lane;
       bool ok = false;
-      int ti = -1, fi = 0, j = 0;
-      double w = 0.0;
-      if (slot < n_slots) {
-        fi = slot / n_src;
-        j = slot - fi * n_src;
+      if (slot < s_end) {
+        const int fi = slot / n_src;
+        const int j = slot - fi * n_src;
         const Aff Tst = sh.Tst[fi];
         const SetView& tgt = sh.tgt[fi];
         const double ux = src.f[(size_t)CF_U0 * src.cap + j], uy = src.f[(size_t)CF_U1 * src.cap + j];
         const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
         const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
-        ti = nn_search(tgt, sh.n_tgt[fi], (float)qxd, (float)qyd, R);
+        int ti = nn_search(tgt, sh.n_tgt[fi], (float)qxd, (float)qyd, R);
         if (ti >= 0) {
           const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
           const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
@@ -598,30 +701,50 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
           const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
           if (sim > P.angle_outlier) {
             ok = true;
-            const double N1 = src.f[(size_t)CF_NS * src.cap + j], N2 = tgt.f[(size_t)CF_NS * tgt.cap + ti];
-            const double p1 = src.f[(size_t)CF_SCALE * src.cap + j], p2 = tgt.f[(size_t)CF_SCALE * tgt.cap + ti];
-            const double simN = 2 * fmin(N1, N2) / (N1 + N2);
-            const double simP = 2 * fmin(p1, p2) / (p1 + p2);
-            switch (P.weight_opt) {   // registration.cpp:67-75
-              case TBV_W_UNIFORM: w = 1.0; break;
-              case TBV_W_SIM_N: w = simN; break;
-              case TBV_W_SIM_DIRECTION: w = sim; break;
-              case TBV_W_SIM_SCALE: w = simP; break;
-              case TBV_W_COMBINED: w = simN + sim + simP; break;
-              default: w = 1.0;
+            double w = 1.0;
+            if (P.weight_opt != TBV_W_UNIFORM) {
+              const double N1 = src.f[(size_t)CF_NS * src.cap + j], N2 = tgt.f[(size_t)CF_NS * tgt.cap + ti];
+              const double p1 = src.f[(size_t)CF_SCALE * src.cap + j], p2 = tgt.f[(size_t)CF_SCALE * tgt.cap + ti];
+              const double simN = 2 * fmin(N1, N2) / (N1 + N2);
+              const double simP = 2 * fmin(p1, p2) / (p1 + p2);
+              switch (P.weight_opt) {   // registration.cpp:67-75
+                case TBV_W_SIM_N: w = simN; break;
+                case TBV_W_SIM_DIRECTION: w = sim; break;
+                case TBV_W_SIM_SCALE: w = simP; break;
+                case TBV_W_COMBINED: w = simN + sim + simP; break;
+                default: w = 1.0;
+              }
             }
+            wgt[slot] = w;
           } else {
             ti = -1;
           }
         }
         assoc[(size_t)fi * slot_cap + j] = ti;
       }
+      my_cnt += __popc(__ballot_sync(FULL, ok));
+    }
+    if (lane == 0) sh.warp_cnt[warp] = my_cnt;
+    __syncthreads();
+    int q0 = 0, total = 0;
+#pragma unroll
+    for (int wv = 0; wv < RG_WARPS; wv++) {
+      const int c = sh.warp_cnt[wv];
+      if (wv < warp) q0 += c;
+      total += c;
+    }
+    for (int base = s_begin; base < s_end; base += 32) {
+      const int slot = base + lane;
+      int ti = -1, fi = 0, j = 0;
+      if (slot < s_end) {
+        fi = slot / n_src;
+        j = slot - fi * n_src;
+        ti = assoc[(size_t)fi * slot_cap + j];   // written by this very thread in pass 1
+      }
+      const bool ok = ti >= 0;
       const unsigned bal = __ballot_sync(FULL, ok);
-      if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
-      __syncthreads();
       if (ok) {
-        int q = sh.running + __popc(bal & ((1u << lane) - 1u));
-        for (int wv = 0; wv < warp; wv++) q += sh.warp_cnt[wv];
+        const int q = q0 + __popc(bal & ((1u << lane) - 1u));
         const Aff Ttar = sh.Ttar[fi];
         const SetView& tgt = sh.tgt[fi];
         const double tu0 = tgt.f[(size_t)CF_U0 * tgt.cap + ti], tu1 = tgt.f[(size_t)CF_U1 * tgt.cap + ti];
@@ -653,38 +776,48 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
           blocks[5 * bstride + q] = l10;
           blocks[6 * bstride + q] = l11;
         }
+        const double w = wgt[slot];
         blocks[7 * bstride + q] = w;
+        blocks[8 * bstride + q] = sqrt(w);
       }
-      __syncthreads();
-      if (tid == 0) {
-        int t = 0;
-        for (int wv = 0; wv < RG_WARPS; wv++) t += sh.warp_cnt[wv];
-        sh.running += t;
-      }
-      __syncthreads();
+      q0 += __popc(bal);
     }
-    if (tid == 0) sh.n_blocks = sh.running;
+    if (tid == 0) sh.n_blocks = total;
     __syncthreads();
   };
 
-  // ---- evaluation at sh.ex (cos/sin in sh.cs): result in sh.acc
+  // ---- evaluation at sh.ex (cos/sin in sh.cs): per-warp partial sums in sh.warp_acc (fixed shapes: deterministic).
+  // The caller combines them after the barrier at the end.
+  const bool simple_loss = (P.loss == TBV_LOSS_HUBER || P.loss == TBV_LOSS_NONE) && mode == REG_MODE_REGISTER;
   auto evaluate = [&](int nblk, bool write_residuals) {
     double a[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; i++) a[i] = 0.0;
     const double x0 = sh.ex[0], x1 = sh.ex[1], cy = sh.cs[0], sy = sh.cs[1];
-    for (int q = tid; q < nblk; q += RG_THREADS) {
-      double f[2], J[6];
-      int n;
-      a[0] += eval_block(P.cost, P.loss, P.loss_limit, blocks + q, bstride, x0, x1, cy, sy, f, J, n, true);
-      for (int r = 0; r < n; r++) {
-        const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
-        a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
-        a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
+    if (simple_loss) {
+      if (P.loss == TBV_LOSS_HUBER) {
+        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, true>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, true>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else eval_loop_simple<TBV_P2D, true>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
+      } else {
+        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, false>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, false>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else eval_loop_simple<TBV_P2D, false>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
       }
-      if (write_residuals && residuals_all) {
-        double* ro = residuals_all + (size_t)p * 2 * bstride;
-        for (int r = 0; r < n; r++) ro[(size_t)q * n + r] = f[r];
+    } else {
+      for (int q = tid; q < nblk; q += RG_THREADS) {
+        double f[2], J[6];
+        int n;
+        a[0] += eval_block(P.cost, P.loss, P.loss_limit, blocks + q, bstride, x0, x1, cy, sy, f, J, n, true);
+        for (int r = 0; r < n; r++) {
+          const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
+          a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
+          a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
+        }
+        if (write_residuals && residuals_all) {
+          double* ro = residuals_all + (size_t)p * 2 * bstride;
+          for (int r = 0; r < n; r++) ro[(size_t)q * n + r] = f[r];
+        }
       }
     }
 #pragma unroll
@@ -695,16 +828,25 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       if (lane == 0) sh.warp_acc[warp][i] = v;
     }
     __syncthreads();
-    if (tid < NACC) {
-      double v = 0.0;
-      for (int wv = 0; wv < RG_WARPS; wv++) v += sh.warp_acc[wv][tid];
-      sh.acc[tid] = v;
-    }
-    __syncthreads();
   };
-  auto set_eval_point = [&](const double x[3]) {  // thread 0
-    sh.ex[0] = x[0]; sh.ex[1] = x[1]; sh.ex[2] = x[2];
-    sh.cs[0] = cos(x[2]); sh.cs[1] = sin(x[2]);
+  // warp 0, after evaluate(): cross-warp sums in warp order -> sh.acc (visible to the warp after __syncwarp)
+  auto combine = [&]() {
+    if (lane < NACC) {
+      double v = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < RG_WARPS; wv++) v += sh.warp_acc[wv][lane];
+      sh.acc[lane] = v;
+    }
+    __syncwarp();
+  };
+  // warp 0: publish the next evaluation point chosen by lane 0 (x in sh.ex); cos and sin are computed by two different lanes
+  auto publish_eval_point = [&](bool go) {
+    const int g = __shfl_sync(FULL, go ? 1 : 0, 0);
+    if (g) {
+      const double th = sh.ex[2];
+      if (lane == 1) sh.cs[0] = cos(th);
+      if (lane == 2) sh.cs[1] = sin(th);
+    }
   };
 
   // =========================================================================================================
@@ -712,106 +854,99 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     const double R = (eval_itr == 1) ? 2 * P.radius : P.radius;
     associate(prob.src_pose, R);
     const int nblk = sh.n_blocks;
-    if (tid == 0) set_eval_point(prob.src_pose);
+    if (tid == 0) {
+      sh.ex[0] = prob.src_pose[0]; sh.ex[1] = prob.src_pose[1]; sh.ex[2] = prob.src_pose[2];
+      sh.cs[0] = cos(prob.src_pose[2]); sh.cs[1] = sin(prob.src_pose[2]);
+    }
     __syncthreads();
     evaluate(nblk, true);
-    if (tid == 0) {
-      RegResult r;
-      memset(&r, 0, sizeof(r));
-      r.pose[0] = prob.src_pose[0]; r.pose[1] = prob.src_pose[1]; r.pose[2] = prob.src_pose[2];
-      r.num_residuals = nblk * nres_per_block;
-      r.success = r.num_residuals > 1;
-      r.final_cost = sh.acc[0];
-      r.score = sh.acc[0] / (double)max(r.num_residuals, 1);
-      *out = r;
-      n_blocks_all[p] = nblk;
-      if (eval_out)
-        for (int i = 0; i < NACC; i++) eval_out[(size_t)p * NACC + i] = sh.acc[i];
+    if (warp == 0) {
+      combine();
+      if (lane == 0) {
+        RegResult r;
+        memset(&r, 0, sizeof(r));
+        r.pose[0] = prob.src_pose[0]; r.pose[1] = prob.src_pose[1]; r.pose[2] = prob.src_pose[2];
+        r.num_residuals = nblk * nres_per_block;
+        r.success = r.num_residuals > 1;
+        r.final_cost = sh.acc[0];
+        r.score = sh.acc[0] / (double)max(r.num_residuals, 1);
+        *out = r;
+        n_blocks_all[p] = nblk;
+        if (eval_out)
+          for (int i = 0; i < NACC; i++) eval_out[(size_t)p * NACC + i] = sh.acc[i];
+      }
     }
     return;
   }
 
-  // ---- Register (n_scan_normal.cpp:82-185) — the LM state lives in shared memory and is advanced by thread 0; decisions
-  // are broadcast through sh.flag
+  // ---- Register (n_scan_normal.cpp:82-185) — the LM state AND the outer loop's state live in shared memory and are
+  // advanced by lane 0 of warp 0, which also owns the cross-warp reduction: two barriers per LM iteration (partial sums
+  // ready / decision published); the other threads only keep what the hot loops need in registers.
   LMState& S = sh.lm;
-  double par[3] = {prob.src_pose[0], prob.src_pose[1], prob.src_pose[2]};  // parameters.back()
-  double prev_par[3] = {par[0], par[1], par[2]};
-  double tsrc[3] = {par[0], par[1], par[2]};  // Tsrc.back(): only rewritten after a usable solve (:118-121, :166-170)
-  double prev_score = DBL_MAX;
-  int total_lm = 0, itr = 1, pose_updated = 0;
-  bool success = true;
-  int num_residuals = 0, last_n_iterations = 0, termination = 1;
-  double final_cost = 0.0, last_rel_dec = 0.0;
-  for (itr = 1; itr <= P.max_itr_association && success; itr++) {
-    const double R = (itr == 1) ? 2 * P.radius : P.radius;
-    associate(par, R);  // every thread keeps an identical copy of par (broadcast below)
-    const int nblk = sh.n_blocks;
-    num_residuals = nblk * nres_per_block;
-    if (num_residuals <= 1) { success = false; break; }  // BuildOptimizationProblem fails (:371-374)
-    // ---- ceres::Solve
-    if (tid == 0) set_eval_point(par);
-    __syncthreads();
-    evaluate(nblk, false);
-    if (tid == 0) {
-      lm_begin(S, par, sh.acc);
-      const bool go = lm_advance(S, P.max_itr_solver);
-      if (go) set_eval_point(S.cand);
-      sh.flag = go ? 1 : 0;
-    }
-    __syncthreads();
-    while (sh.flag) {
-      evaluate(nblk, false);
-      if (tid == 0) {
-        lm_candidate(S, sh.acc);
-        const bool go = lm_advance(S, P.max_itr_solver);
-        if (go) set_eval_point(S.cand);
-        sh.flag = go ? 1 : 0;
-      }
-      __syncthreads();
-    }
-    // the outcome of this solve: parameters + the scalars the outer loop reads (S is shared: every thread reads it)
-    par[0] = S.params[0]; par[1] = S.params[1]; par[2] = S.params[2];
-    final_cost = fmin(S.initial_cost, S.min_pushed_cost);  // SetSummaryFinalCost
-    last_rel_dec = S.last_rel_dec;
-    last_n_iterations = S.n_pushed;
-    termination = S.termination;
-    __syncthreads();
-    total_lm += last_n_iterations - 1;
-    success = termination != 2;  // IsSolutionUsable
-    if (success) { pose_updated = 1; tsrc[0] = par[0]; tsrc[1] = par[1]; tsrc[2] = par[2]; }
-    const double current_score = final_cost;
-    const double rel_improvement = (prev_score - current_score) / prev_score;
-    if (itr > 3) {  // min_itr_ = 3
-      if (prev_score < current_score) {
-        par[0] = prev_par[0]; par[1] = prev_par[1]; par[2] = prev_par[2];
-        break;
-      } else if (rel_improvement < 0.00001) {
-        break;
-      } else if (last_rel_dec < 0.00001 || last_n_iterations == 1) {
-        break;
-      }
-    }
-    prev_score = current_score;
-    prev_par[0] = par[0]; prev_par[1] = par[1]; prev_par[2] = par[2];
-  }
-  if (success && pose_updated) { tsrc[0] = par[0]; tsrc[1] = par[1]; tsrc[2] = par[2]; }
+  OuterState& O = sh.outer;
   if (tid == 0) {
+    for (int c = 0; c < 3; c++) { O.par[c] = prob.src_pose[c]; O.prev_par[c] = prob.src_pose[c]; O.tsrc[c] = prob.src_pose[c]; }
+    O.prev_score = DBL_MAX;
+    O.total_lm = 0; O.itr = 1; O.pose_updated = 0; O.success = 1;
+    O.num_residuals = 0; O.last_n_iterations = 0; O.termination = 1;
+    O.final_cost = 0.0; O.last_rel_dec = 0.0;
+    O.go = (1 <= P.max_itr_association) ? 1 : 0;
+  }
+  __syncthreads();
+  while (O.go) {
+    const double R = (O.itr == 1) ? 2 * P.radius : P.radius;
+    if (warp == 0) {   // evaluation point of the first evaluation = parameters.back()
+      if (lane == 0) { sh.ex[0] = O.par[0]; sh.ex[1] = O.par[1]; sh.ex[2] = O.par[2]; }
+      __syncwarp();
+      publish_eval_point(true);
+    }
+    associate(O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
+    const int nblk = sh.n_blocks;
+    if (nblk * nres_per_block <= 1) {  // BuildOptimizationProblem fails (:371-374): Register returns false, itr_ not advanced
+      if (tid == 0) { O.num_residuals = nblk * nres_per_block; O.success = 0; }
+      break;
+    }
+    // ---- ceres::Solve
+    bool first = true;
+    for (;;) {
+      evaluate(nblk, false);
+      if (warp == 0) {
+        combine();
+        bool go = false;
+        if (lane == 0) {
+          if (first) lm_begin(S, O.par, sh.acc); else lm_candidate(S, sh.acc);
+          go = lm_advance(S, P.max_itr_solver);
+          if (go) { sh.ex[0] = S.cand[0]; sh.ex[1] = S.cand[1]; sh.ex[2] = S.cand[2]; }
+          else outer_advance(O, S, nblk * nres_per_block, P.max_itr_association);
+          sh.flag = go ? 1 : 0;
+        }
+        __syncwarp();
+        publish_eval_point(go);
+      }
+      first = false;
+      __syncthreads();
+      if (!sh.flag) break;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (O.success && O.pose_updated) { O.tsrc[0] = O.par[0]; O.tsrc[1] = O.par[1]; O.tsrc[2] = O.par[2]; }
     RegResult r;
     memset(&r, 0, sizeof(r));
-    r.pose[0] = tsrc[0]; r.pose[1] = tsrc[1]; r.pose[2] = tsrc[2];
-    r.pose_updated = pose_updated;
-    r.success = success ? 1 : 0;
-    r.itrs = itr;
-    r.lm_iterations = total_lm;
-    r.num_residuals = num_residuals;
-    r.last_n_iterations = last_n_iterations;
-    r.termination = termination;
-    r.final_cost = final_cost;
-    r.last_relative_decrease = last_rel_dec;
-    r.score = success ? final_cost / (double)num_residuals : 0.0;
+    r.pose[0] = O.tsrc[0]; r.pose[1] = O.tsrc[1]; r.pose[2] = O.tsrc[2];
+    r.pose_updated = O.pose_updated;
+    r.success = O.success ? 1 : 0;
+    r.itrs = O.itr;
+    r.lm_iterations = O.total_lm;
+    r.num_residuals = O.num_residuals;
+    r.last_n_iterations = O.last_n_iterations;
+    r.termination = O.termination;
+    r.final_cost = O.final_cost;
+    r.last_relative_decrease = O.last_rel_dec;
+    r.score = O.success ? O.final_cost / (double)O.num_residuals : 0.0;
     // Talign = Trevised^-1 * Tto (loopclosure.cpp:73), Trevised = vectorToAffine(parameters)
     const double* fp = fixed_pose + (size_t)prob.fixed_first * 3;
-    const Aff Tal = aff_mul(aff_inv(vec_to_aff(tsrc[0], tsrc[1], tsrc[2])), vec_to_aff(fp[0], fp[1], fp[2]));
+    const Aff Tal = aff_mul(aff_inv(vec_to_aff(O.tsrc[0], O.tsrc[1], O.tsrc[2])), vec_to_aff(fp[0], fp[1], fp[2]));
     r.align[0] = Tal.tx; r.align[1] = Tal.ty; r.align[2] = atan2(Tal.r10, Tal.r11);
     *out = r;
     if (n_blocks_all) n_blocks_all[p] = sh.n_blocks;
@@ -846,7 +981,8 @@ int reg_scratch_reserve(tbv_ctx* ctx, int n_problems, int max_fixed, int slot_ca
   RegScratch& S = *reg_scratch(ctx);
   const size_t slots = (size_t)n_problems * max_fixed * slot_cap;
   int rc;
-  if ((rc = S.assoc.reserve(slots)) || (rc = S.blocks.reserve(slots * BLK_FIELDS)) || (rc = S.n_blocks.reserve(n_problems))) return rc;
+  if ((rc = S.assoc.reserve(slots)) || (rc = S.wgt.reserve(slots)) || (rc = S.blocks.reserve(slots * BLK_FIELDS)) || (rc = S.n_blocks.reserve(n_problems)))
+    return rc;
   if (want_residuals && (rc = S.residuals.reserve(slots * 2))) return rc;
   return TBV_OK;
 }
@@ -861,9 +997,19 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   RegScratch& S = *reg_scratch(ctx);
   TBV_REQUIRE(max_fixed <= RG_MAX_FIXED, "too many fixed scans per problem (at most 16)");
   (void)tgt_cap;
-  k_register<<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
-                                                            slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                            want_residuals ? S.residuals.p : nullptr);
+  static int min_ctas = 0;
+  if (!min_ctas) {
+    const char* e = getenv("TBV_REG_CTAS");
+    min_ctas = (e && atoi(e) == 3) ? 3 : 4;
+  }
+  if (min_ctas == 3)
+    k_register<3><<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
+                                                               slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
+                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p);
+  else
+    k_register<4><<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
+                                                               slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
+                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;

@@ -67,14 +67,15 @@ RegParamsDev to_dev(const tbv_reg_params& p);
 
 enum { REG_MODE_REGISTER = 0, REG_MODE_EVAL = 1 };
 
-constexpr int BLK_FIELDS = 8;  // per residual block: src(2) tar(2) [nrm(2) | L00 L10 L11] weight
+constexpr int BLK_FIELDS = 9;  // per residual block: src(2) tar(2) [nrm(2) | L00 L10 L11] weight sqrt(weight)
 
 struct RegScratch {            // association / residual-block scratch, [n_problems][...]
   DevBuf<int> assoc;           // [n_problems][max_fixed][slot_cap] target index per (fixed, src) or -1
+  DevBuf<double> wgt;          // [n_problems][max_fixed*slot_cap] loss weight of an accepted slot (between the two association passes)
   DevBuf<double> blocks;       // [n_problems][BLK_FIELDS][max_fixed*slot_cap] compacted residual blocks, field-major
   DevBuf<int> n_blocks;        // [n_problems]
   DevBuf<double> residuals;    // [n_problems][2*max_fixed*slot_cap] (eval mode, optional)
-  void release() { assoc.release(); blocks.release(); n_blocks.release(); residuals.release(); }
+  void release() { assoc.release(); wgt.release(); blocks.release(); n_blocks.release(); residuals.release(); }
 };
 
 // Launches one CTA per problem.  All pointers are device pointers.  slot_cap >= number of cells of any moving scan,
