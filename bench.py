@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=512, help="independent sequences per GPU advanced in lock-step")
+    ap.add_argument("--seqs", type=int, default=592, help="independent sequences per GPU advanced in lock-step (592 = 148 SMs x 4)")
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences in the cpu_baseline sample (0: sized for ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -252,17 +252,29 @@ def run_ours(args):
     except Exception:
         pass
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
-    dominant = max(kern, key=kern.get)
     kernels = {}
     for name, ms in sorted(kern.items(), key=lambda kv: -kv[1]):
         b = algorithmic_bytes(name, S, stats)
         kernels[name] = {"ms_per_step": round(ms, 4), "share": round(ms / sum(kern.values()), 4),
                          "algorithmic_GBps": round(b / ms / 1e6, 1) if b else None}
+    # The roofline object describes the kernel that dominates the step's HBM traffic: K1 streams every scan byte (96 % of the
+    # step's algorithmic bytes).  The longest kernels (k_register, c5_cells) move ~100x fewer bytes and are bound by fp64
+    # issue / dependent-load latency, not by HBM or the tensor pipe: their lines are in `kernels`, the whole step's in `step`.
+    dominant = "k1_kstrongest"
+    longest = max(kern, key=kern.get)
     b_dom = algorithmic_bytes(dominant, S, stats)
-    achieved = b_dom / kern[dominant] / 1e6 if b_dom else 0.0
+    achieved = b_dom / kern[dominant] / 1e6
+    step_bytes_alg = sum(algorithmic_bytes(k, S, stats) or 0.0 for k in kern)
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak_hbm, "unit": "GB/s",
-                "frac": round(achieved / peak_hbm, 5), "traffic": None,
+                "frac": round(achieved / peak_hbm, 5),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one k1_kstrongest launch over 512 scans (profiles/, ncu --set full):
+                # 776.73 MB + 15.06 MB -> 1.5465 MB per scan (algorithmic 1.572 MB incl. outputs that stay in L2)
+                "traffic": round(1.5465e6 * S, 0), "traffic_source": "profiles/r1c_full_k1_kstrongest.txt, scaled from 512 scans per launch",
+                "algorithmic_bytes_per_launch": b_dom, "launch_ms": round(kern[dominant], 4),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "share_of_step": kernels[dominant]["share"], "longest_kernel": longest, "longest_kernel_share": kernels[longest]["share"],
+                "step": {"algorithmic_bytes": step_bytes_alg, "achieved": round(step_bytes_alg / (ms_total / K) / 1e6, 2),
+                         "frac": round(step_bytes_alg / (ms_total / K) / 1e6 / peak_hbm, 5)},
                 "note": "launch duration from CUDA events recorded after every launch on the library's stream (tbv_profile_begin/_end)"}
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -312,6 +324,9 @@ def run_reference(args):
 
 
 if __name__ == "__main__":
+    # the bench prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -300,6 +300,8 @@ __device__ void self_adjoint_eig2(double m00, double m10, double m11, double eva
 // tolerance-parity, the neighbour counts are exact).  Points are streamed from the voxel-sorted copy written by C4:
 // consecutive lanes read consecutive floats.
 constexpr int C5_LANES = 16;
+constexpr int C5_MAXP = 4;      // window points cached per lane on the fast path (16 x 4 = 64 points)
+constexpr int C5_MAXROWS = 4;   // window rows on the fast path
 __global__ void __launch_bounds__(C5_WARPS * 32)
 c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, int max_samples, int cap_pts, int vox_cap,
          const float* __restrict__ sx_in, const float* __restrict__ sy_in, const float* __restrict__ si_in,
@@ -329,57 +331,112 @@ c5_cells(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples, i
     int iy0 = (int)(floorf((qy - radius - eps) * g.inv_leaf) - (float)g.min_by);
     int iy1 = (int)(floorf((qy + radius + eps) * g.inv_leaf) - (float)g.min_by);
     ix0 = max(ix0, 0); iy0 = max(iy0, 0); ix1 = min(ix1, g.div_x - 1); iy1 = min(iy1, g.div_y - 1);
-    // pass 1: neighbour count and weight sum (integer-valued weights: exact in any order)
+    const int nrow = iy1 - iy0 + 1;
+    // row runs of the window in the voxel-sorted order; all their bounds are fetched before any point is touched
+    int ra[C5_MAXROWS], rl[C5_MAXROWS];
+#pragma unroll
+    for (int r = 0; r < C5_MAXROWS; r++) {
+      ra[r] = 0; rl[r] = 0;
+      if (r < nrow) {
+        ra[r] = vs[(iy0 + r) * g.div_x + ix0];
+        rl[r] = vs[(iy0 + r) * g.div_x + ix1 + 1] - ra[r];
+      }
+    }
+    const int p1 = rl[0], p2 = p1 + rl[1], p3 = p2 + rl[2], total = p3 + rl[3];
     int cnt = 0;
-    double wsum = 0.0;
-    for (int iy = iy0; iy <= iy1; iy++) {
-      const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
-      for (int j = a + sub; j < b; j += C5_LANES) {
-        const float dx = qx - px[j], dy = qy - py[j];
-        float d = dx * dx;        // FLANN L2_Simple: result += diff*diff per dimension (z contributes +0)
-        d = d + dy * dy;
-        if (d < r2) {
-          cnt++;
-          wsum += weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0;
+    double wsum = 0.0, u0 = 0.0, u1 = 0.0, c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    if (nrow <= C5_MAXROWS && total <= C5_LANES * C5_MAXP) {
+      // ---- fast path: the whole window (<= 64 points) is read ONCE into registers, lane `sub` holds points sub, sub+16, ...
+      // of the concatenated rows; the three passes then run out of registers
+      float fx[C5_MAXP], fy[C5_MAXP];
+      double wv[C5_MAXP];
+      bool in[C5_MAXP];
+#pragma unroll
+      for (int k = 0; k < C5_MAXP; k++) {
+        const int t = sub + k * C5_LANES;
+        in[k] = false; fx[k] = 0.f; fy[k] = 0.f; wv[k] = 0.0;
+        if (t < total) {
+          const int j = t < p1 ? ra[0] + t : (t < p2 ? ra[1] + (t - p1) : (t < p3 ? ra[2] + (t - p2) : ra[3] + (t - p3)));
+          fx[k] = px[j]; fy[k] = py[j];
+          const float dx = qx - fx[k], dy = qy - fy[k];
+          float d = dx * dx;        // FLANN L2_Simple: result += diff*diff per dimension (z contributes +0)
+          d = d + dy * dy;
+          if (d < r2) {
+            in[k] = true;
+            wv[k] = weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0;
+          }
         }
       }
-    }
-    for (int d = C5_LANES / 2; d > 0; d >>= 1) { cnt += __shfl_xor_sync(gmask, cnt, d); wsum += __shfl_xor_sync(gmask, wsum, d); }
-    if (cnt < 6) {  // pointnormal.cpp:291
-      if (sub == 0) cnd[CF_NS * st + s] = 0.0;
-      continue;
-    }
-    // pass 2: mean
-    double u0 = 0.0, u1 = 0.0;
-    for (int iy = iy0; iy <= iy1; iy++) {
-      const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
-      for (int j = a + sub; j < b; j += C5_LANES) {
-        const float fx = px[j], fy = py[j];
-        const float dx = qx - fx, dy = qy - fy;
-        float d = dx * dx;
-        d = d + dy * dy;
-        if (d < r2) {
-          const double w = (weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0) / wsum;
-          u0 += w * (double)fx;
-          u1 += w * (double)fy;
-        }
+#pragma unroll
+      for (int k = 0; k < C5_MAXP; k++)
+        if (in[k]) { cnt++; wsum += wv[k]; }
+      for (int d = C5_LANES / 2; d > 0; d >>= 1) { cnt += __shfl_xor_sync(gmask, cnt, d); wsum += __shfl_xor_sync(gmask, wsum, d); }
+      if (cnt < 6) {  // pointnormal.cpp:291
+        if (sub == 0) cnd[CF_NS * st + s] = 0.0;
+        continue;
       }
-    }
-    for (int d = C5_LANES / 2; d > 0; d >>= 1) { u0 += __shfl_xor_sync(gmask, u0, d); u1 += __shfl_xor_sync(gmask, u1, d); }
-    // pass 3: covariance about the mean
-    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-    for (int iy = iy0; iy <= iy1; iy++) {
-      const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
-      for (int j = a + sub; j < b; j += C5_LANES) {
-        const float fx = px[j], fy = py[j];
-        const float dx = qx - fx, dy = qy - fy;
-        float d = dx * dx;
-        d = d + dy * dy;
-        if (d < r2) {
-          const double w = (weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0) / wsum;
-          const double d0 = (double)fx - u0, d1 = (double)fy - u1;
-          const double xw0 = w * d0, xw1 = w * d1;
+#pragma unroll
+      for (int k = 0; k < C5_MAXP; k++)
+        if (in[k]) {
+          wv[k] = wv[k] / wsum;
+          u0 += wv[k] * (double)fx[k];
+          u1 += wv[k] * (double)fy[k];
+        }
+      for (int d = C5_LANES / 2; d > 0; d >>= 1) { u0 += __shfl_xor_sync(gmask, u0, d); u1 += __shfl_xor_sync(gmask, u1, d); }
+#pragma unroll
+      for (int k = 0; k < C5_MAXP; k++)
+        if (in[k]) {
+          const double d0 = (double)fx[k] - u0, d1 = (double)fy[k] - u1;
+          const double xw0 = wv[k] * d0, xw1 = wv[k] * d1;
           c00 += d0 * xw0; c01 += d0 * xw1; c10 += d1 * xw0; c11 += d1 * xw1;
+        }
+    } else {
+      // ---- general path (large or tall windows): three streaming passes over the window rows
+      for (int iy = iy0; iy <= iy1; iy++) {
+        const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
+        for (int j = a + sub; j < b; j += C5_LANES) {
+          const float dx = qx - px[j], dy = qy - py[j];
+          float d = dx * dx;
+          d = d + dy * dy;
+          if (d < r2) {
+            cnt++;
+            wsum += weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0;
+          }
+        }
+      }
+      for (int d = C5_LANES / 2; d > 0; d >>= 1) { cnt += __shfl_xor_sync(gmask, cnt, d); wsum += __shfl_xor_sync(gmask, wsum, d); }
+      if (cnt < 6) {
+        if (sub == 0) cnd[CF_NS * st + s] = 0.0;
+        continue;
+      }
+      for (int iy = iy0; iy <= iy1; iy++) {
+        const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
+        for (int j = a + sub; j < b; j += C5_LANES) {
+          const float fx = px[j], fy = py[j];
+          const float dx = qx - fx, dy = qy - fy;
+          float d = dx * dx;
+          d = d + dy * dy;
+          if (d < r2) {
+            const double w = (weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0) / wsum;
+            u0 += w * (double)fx;
+            u1 += w * (double)fy;
+          }
+        }
+      }
+      for (int d = C5_LANES / 2; d > 0; d >>= 1) { u0 += __shfl_xor_sync(gmask, u0, d); u1 += __shfl_xor_sync(gmask, u1, d); }
+      for (int iy = iy0; iy <= iy1; iy++) {
+        const int a = vs[iy * g.div_x + ix0], b = vs[iy * g.div_x + ix1 + 1];
+        for (int j = a + sub; j < b; j += C5_LANES) {
+          const float fx = px[j], fy = py[j];
+          const float dx = qx - fx, dy = qy - fy;
+          float d = dx * dx;
+          d = d + dy * dy;
+          if (d < r2) {
+            const double w = (weight_intensity ? fmax((double)pi[j] - 60.0, 0.0) : 1.0) / wsum;
+            const double d0 = (double)fx - u0, d1 = (double)fy - u1;
+            const double xw0 = w * d0, xw1 = w * d1;
+            c00 += d0 * xw0; c01 += d0 * xw1; c10 += d1 * xw0; c11 += d1 * xw1;
+          }
         }
       }
     }

@@ -101,8 +101,8 @@ __device__ __forceinline__ void stage_row_sync(uint8_t* buf, const uint8_t* rp, 
 
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n_range, size_t row_stride, int z_min, int k,
-              int want_peaks, int rowbuf, const uint8_t* buf_lo, const uint8_t* buf_hi, uint32_t* __restrict__ row_keys,
-              uint16_t* __restrict__ row_cnt) {
+              int want_peaks, int rowbuf, const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, uint32_t* __restrict__ row_keys,
+              uint32_t* __restrict__ row_cnt) {
   extern __shared__ __align__(128) uint8_t s_dyn[];  // [K1_WARPS][2][rowbuf] staged rows
   __shared__ __align__(16) uint32_t s_list[K1_WARPS][K1_CAP];  // candidates (unordered)
   __shared__ __align__(16) uint32_t s_sel[K1_WARPS][K1_CAP];   // selected, ascending
@@ -112,6 +112,7 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
   const unsigned FULL = 0xffffffffu;
   const bool hi = z_min > 128;
   const uint32_t z = (uint32_t)z_min;
+  const bool zero_thr = z == 0;   // every byte is a candidate: padding bytes must be masked explicitly
   const uint32_t addc = (hi ? (256u - z) : (128u - z)) * 0x01010101u;
   const size_t scan_bytes = (size_t)(n_az - 1) * row_stride + (size_t)n_range;  // addressable bytes of one scan
   const size_t scan_stride = (size_t)n_az * row_stride;
@@ -124,30 +125,40 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   __syncwarp();
 
-  auto row_ptr = [&](int row) -> const uint8_t* {
-    const int scan = row / n_az, az = row - scan * n_az;
-    return polar + (size_t)scan * scan_stride + (size_t)az * row_stride;
-  };
+  auto row_ptr = [&](int scan, int az) -> const uint8_t* { return polar + (size_t)scan * scan_stride + (size_t)az * row_stride; };
   int row = blockIdx.x * K1_WARPS + warp;
+  // (scan, az) of the warp's current row, advanced without divisions: row += row_step
+  int scan = row / n_az, az = row - scan * n_az;
+  const int step_scan = row_step / n_az, step_az = row_step - step_scan * n_az;
   int cur = 0;
   uint32_t phase = 0;    // bit b: parity to wait for on bars[b]
   bool in_flight = false;
-  if (row < total_rows) in_flight = stage_row_tma(mybuf, row_ptr(row), n_range, buf_lo, buf_hi, &bars[0], lane);
+  if (row < total_rows) in_flight = stage_row_tma(mybuf, row_ptr(scan, az), n_range, buf_lo, buf_hi, &bars[0], lane);
   for (; row < total_rows; row += row_step) {
-    const int scan = row / n_az, az = row - scan * n_az;
     const uint8_t* scan_base = polar + (size_t)scan * scan_stride;
     const uint8_t* rp = scan_base + (size_t)az * row_stride;
     const int a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
     uint8_t* buf = mybuf + (size_t)cur * rowbuf;
     // prefetch the next row of this warp into the other buffer (its previous contents were consumed last iteration)
     const int nrow = row + row_step;
+    int scan_n = scan + step_scan, az_n = az + step_az;
+    if (az_n >= n_az) { az_n -= n_az; scan_n++; }
     bool next_in_flight = false;
-    if (nrow < total_rows) next_in_flight = stage_row_tma(mybuf + (size_t)(cur ^ 1) * rowbuf, row_ptr(nrow), n_range, buf_lo, buf_hi, &bars[cur ^ 1], lane);
+    if (nrow < total_rows) next_in_flight = stage_row_tma(mybuf + (size_t)(cur ^ 1) * rowbuf, row_ptr(scan_n, az_n), n_range, buf_lo, buf_hi, &bars[cur ^ 1], lane);
     if (in_flight) {
       mbar_wait(&bars[cur], (phase >> cur) & 1u);
       phase ^= 1u << cur;
     } else {
       stage_row_sync(buf, rp, n_range, lane);
+    }
+    // The staged superset starts up to 15 bytes before the row and ends up to 15 bytes after it: clear those bytes so that
+    // no threshold >= 1 ever matches them and the scan needs no per-vector validity test (z_min == 0 keeps the masks).
+    if (!zero_thr) {
+      const int head = a0, tail = (((a0 + n_range + 15) >> 4) << 4) - (a0 + n_range);
+      if (lane < head) buf[lane] = 0;
+      if (lane < tail) buf[a0 + n_range + lane] = 0;
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before the next bulk copy into this buffer
+      __syncwarp();
     }
 
     // word validity: byte offset wo in buf holds row index wo - a0; valid iff 0 <= wo + b - a0 < n_range
@@ -162,7 +173,14 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf);
     auto masks = [&](const uint4 v, int wo, uint32_t ac, bool h, uint32_t m[4]) {
       m[0] = ge_mask(v.x, ac, h); m[1] = ge_mask(v.y, ac, h); m[2] = ge_mask(v.z, ac, h); m[3] = ge_mask(v.w, ac, h);
-      if (wo < lo_b || wo + 16 > hi_b) { m[0] &= valid_mask(wo); m[1] &= valid_mask(wo + 4); m[2] &= valid_mask(wo + 8); m[3] &= valid_mask(wo + 12); }
+      if (zero_thr && (wo < lo_b || wo + 16 > hi_b)) { m[0] &= valid_mask(wo); m[1] &= valid_mask(wo + 4); m[2] &= valid_mask(wo + 8); m[3] &= valid_mask(wo + 12); }
+    };
+    // Conservative test "some byte of the 16 may be >= z_min" (never misses one; false positives only next to a byte >= 188):
+    // z <= 128: byte + (128 - z) sets bit 7, or overflows the byte only when the byte itself has bit 7 set; z > 128: bit 7.
+    auto any_ge = [&](const uint4 v) -> bool {
+      if (hi) return ((v.x | v.y | v.z | v.w) & 0x80808080u) != 0;
+      const uint32_t a = (v.x + addc) | v.x, b = (v.y + addc) | v.y, c = (v.z + addc) | v.z, d = (v.w + addc) | v.w;
+      return ((a | b | c | d) & 0x80808080u) != 0;
     };
     auto emit = [&](uint32_t m, uint32_t w, int wo) {  // dense path only: scatter the flagged bytes of one word
       int pos = atomicAdd(&s_n[warp], __popc(m));
@@ -173,50 +191,61 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
         pos++;
       }
     };
-    // ---- pass 1: count the candidates (I >= z_min); remember which of this lane's vectors hold any -----------------
-    int cnt = 0;
-    uint32_t flagged = 0;
-    {
-      int it = 0;
-      for (int t = lane; t < nvec; t += 32, it++) {
-        uint32_t m[4];
-        masks(vbuf[t], t << 4, addc, hi, m);
-        if (m[0] | m[1] | m[2] | m[3]) {
-          cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-          flagged |= 1u << it;
-        }
-      }
+    // ---- pass 1: branch-free scan.  The conservative test flags ~1 vector in 9 on radar data; the flagged vector ids are
+    // compacted (ballot order) into a per-warp queue so that pass 2 works on them with all 32 lanes busy instead of every
+    // lane dragging the whole warp through its own rare hits.  The queue lives in `sel` (free until the ranking step).
+    uint16_t* queue = reinterpret_cast<uint16_t*>(sel);  // K1_CAP + 1 entries are enough: more flagged vectors than that => dense row
+    int nq = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 2
+    for (int base = 0; base < nvec; base += 32) {
+      const int t = base + lane;
+      bool f = false;
+      if (t < nvec) f = any_ge(vbuf[t]);
+      const unsigned ball = __ballot_sync(FULL, f);
+      const int q = nq + __popc(ball & lt);
+      if (f && q <= K1_CAP) queue[q] = (uint16_t)t;
+      nq += __popc(ball);
     }
-    const int total = __reduce_add_sync(FULL, cnt);
-    int n;
-    if (total <= K1_CAP) {
-      // ---- sparse row (the normal case): exclusive prefix of the per-lane counts, then every lane writes its own -----
-      int incl = cnt;
+    __syncwarp();
+    // ---- pass 2 (sparse row, the normal case): exact masks of the queued vectors, one vector per lane per round; positions from
+    // a warp scan of the per-vector counts.  The list order is arbitrary (the ranking step orders it) but deterministic.
+    int n = 0;
+    bool dense = nq > K1_CAP;
+    for (int qb = 0; qb < nq && !dense; qb += 32) {
+      int c = 0, wo = 0;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      uint32_t m[4] = {0, 0, 0, 0};
+      if (qb + lane < nq) {
+        const int t = queue[qb + lane];
+        wo = t << 4;
+        v = vbuf[t];
+        masks(v, wo, addc, hi, m);
+        c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+      }
+      int incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t;
+        const int t2 = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t2;
       }
-      int pos = incl - cnt;
-      while (flagged) {
-        const int it = __ffs(flagged) - 1;
-        flagged &= flagged - 1;
-        const int t = lane + (it << 5), wo = t << 4;
-        const uint4 v = vbuf[t];
-        uint32_t m[4];
-        masks(v, wo, addc, hi, m);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      const int round_total = __shfl_sync(FULL, incl, 31);
+      if (n + round_total > K1_CAP) { dense = true; break; }
+      int pos = n + incl - c;
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          uint32_t mm = m[q];
-          while (mm) {
-            const int b = (__ffs(mm) - 1) >> 3;
-            mm &= mm - 1;
-            list[pos++] = (((w[q] >> (8 * b)) & 0xffu) << 16) | (uint32_t)(wo + 4 * q + b - a0);
-          }
+      for (int q = 0; q < 4; q++) {
+        uint32_t mm = m[q];
+        while (mm) {
+          const int b = (__ffs(mm) - 1) >> 3;
+          mm &= mm - 1;
+          list[pos++] = (((w[q] >> (8 * b)) & 0xffu) << 16) | (uint32_t)(wo + 4 * q + b - a0);
         }
       }
-      n = total;
+      n += round_total;
+    }
+    if (!dense) {
+      __syncwarp();
     } else {
       // ---- dense row: exact threshold + tie handling ----------------------------------------------------
       if (lane == 0) s_n[warp] = 0;
@@ -361,49 +390,64 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
     }
     // ---- write the row ------------------------------------------------------------------------------------------
     uint32_t* out = row_keys + (size_t)row * k;
-    for (int e = lane; e < n_sel; e += 32) out[e] = sel[e];
-    if (lane == 0) row_cnt[row] = (uint16_t)n_sel;
+    int nf = 0, np = 0;  // entries K2 will emit: range beyond min_range_bin (radar_filters.cpp:321), and the peaks among them
+    for (int e = lane; e < ((n_sel + 31) & ~31); e += 32) {
+      const uint32_t key = e < n_sel ? sel[e] : 0u;
+      if (e < n_sel) out[e] = key;
+      const bool ok = e < n_sel && (int)(key & 0xffffu) > min_range_bin;
+      nf += __popc(__ballot_sync(FULL, ok));
+      np += __popc(__ballot_sync(FULL, ok && (key >> 31)));
+    }
+    if (lane == 0) row_cnt[row] = (uint32_t)n_sel | ((uint32_t)nf << 8) | ((uint32_t)np << 16);
     __syncwarp();  // every lane is done with buf / list / sel before the next iteration reuses them
     cur ^= 1;
     in_flight = next_in_flight;
+    scan = scan_n; az = az_n;
   }
 }
 
-// K2: rows -> ordered clouds.  One CTA per scan.
+// Compensate one point (utils.cpp:96-113, utils.h:28-32): (x, y) are the stored float coordinates; m = previous frame-to-frame
+// motion (x, y, yaw).  Same operations, in the same order, as the reference's double arithmetic.
+__device__ __forceinline__ void compensate_point(float& x, float& y, double m0, double m1, double m2, int ccw) {
+  const double two_pi = __dmul_rn(2.0, 3.14159265358979323846);
+  const double px = (double)x, py = (double)y;
+  const double a = atan2(py, px);
+  double d = __ddiv_rn((a > 0.00001 ? a : __dadd_rn(two_pi, a)), two_pi);
+  d = ccw ? -(__dsub_rn(d, 0.5)) : __dsub_rn(d, 0.5);
+  const double ang = __dmul_rn(d, m2);
+  const double s1 = sin(ang), c1 = cos(ang);
+  const double tx = __dmul_rn(d, m0), ty = __dmul_rn(d, m1);
+  x = (float)__dadd_rn(__dadd_rn(__dmul_rn(c1, px), __dmul_rn(-s1, py)), tx);
+  y = (float)__dadd_rn(__dadd_rn(__dmul_rn(s1, px), __dmul_rn(c1, py)), ty);
+}
+
+// K2: rows -> ordered clouds.  K2_SPLIT CTAs per scan: each scans the scan's per-row counts (written by K1: selected, emitted,
+// emitted peaks — one packed word per row) into output offsets and emits its own slice of rows.  mot != nullptr: the points
+// are motion-compensated as they are emitted (odometrykeyframefuser.cpp:146-150 applies Compensate to both clouds right after
+// the filter; a peak is the same point in both clouds, so it is compensated once).
+constexpr int K2_SPLIT = 4;
 __global__ void __launch_bounds__(256)
-k2_make_clouds(const uint32_t* __restrict__ row_keys, const uint16_t* __restrict__ row_cnt, int n_az, int k, int min_range_bin,
+k2_make_clouds(const uint32_t* __restrict__ row_keys, const uint32_t* __restrict__ row_cnt, int n_az, int k, int min_range_bin,
                double range_res, const double2* __restrict__ cs_table, int cap,
                float* __restrict__ fx, float* __restrict__ fy, uint8_t* __restrict__ fi, uint16_t* __restrict__ faz, uint16_t* __restrict__ frg,
                int* __restrict__ fcount, int want_peaks,
                float* __restrict__ px, float* __restrict__ py, uint8_t* __restrict__ pi, uint16_t* __restrict__ paz, uint16_t* __restrict__ prg,
-               int* __restrict__ pcount) {
+               int* __restrict__ pcount, const double* __restrict__ mot, int ccw) {
   extern __shared__ int s_off[];  // [2][n_az + 1]
   int* off_f = s_off;
   int* off_p = s_off + (n_az + 1);
-  const int scan = blockIdx.x;
+  const int scan = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const unsigned FULL = 0xffffffffu;
   const uint32_t* keys = row_keys + (size_t)scan * n_az * k;
-  const uint16_t* cnts = row_cnt + (size_t)scan * n_az;
-  // phase 1: per-row emitted counts
-  for (int row = warp; row < n_az; row += nwarps) {
-    const int c = cnts[row];
-    int nf = 0, np = 0;
-    for (int e = lane; e < ((c + 31) & ~31); e += 32) {
-      const uint32_t key = e < c ? keys[(size_t)row * k + e] : 0u;
-      const bool ok = e < c && (int)(key & 0xffffu) > min_range_bin;
-      nf += __popc(__ballot_sync(FULL, ok));
-      np += __popc(__ballot_sync(FULL, ok && (key >> 31)));
-    }
-    if (lane == 0) { off_f[row] = nf; off_p[row] = np; }
-  }
-  __syncthreads();
-  // phase 2: exclusive scan (warp 0 for filtered, warp 1 for peaks)
+  const uint32_t* cnts = row_cnt + (size_t)scan * n_az;
+  // phase 1: exclusive scans of the per-row emitted counts (warp 0: filtered, warp 1: peaks)
   if (warp < 2) {
     int* o = warp == 0 ? off_f : off_p;
+    const int shift = warp == 0 ? 8 : 16;
     int running = 0;
     for (int base = 0; base < n_az; base += 32) {
-      const int v = (base + lane < n_az) ? o[base + lane] : 0;
+      const int v = (base + lane < n_az) ? (int)((cnts[base + lane] >> shift) & 0xffu) : 0;
       int inc = v;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -413,17 +457,20 @@ k2_make_clouds(const uint32_t* __restrict__ row_keys, const uint16_t* __restrict
       if (base + lane < n_az) o[base + lane] = running + inc - v;
       running += __shfl_sync(FULL, inc, 31);
     }
-    if (lane == 0) {
-      o[n_az] = running;
+    if (lane == 0 && blockIdx.x == 0) {
       if (warp == 0) fcount[scan] = running; else if (want_peaks) pcount[scan] = running;
     }
   }
   __syncthreads();
-  // phase 3: emit points
+  // phase 2: emit the points of this CTA's rows
   const double range_res_half = range_res / 2.0;
   const size_t cbase = (size_t)scan * cap;
-  for (int row = warp; row < n_az; row += nwarps) {
-    const int c = cnts[row];
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  if (mot) { m0 = mot[scan * 3 + 0]; m1 = mot[scan * 3 + 1]; m2 = mot[scan * 3 + 2]; }
+  const int rows_per = (n_az + gridDim.x - 1) / gridDim.x;
+  const int row_end = min(n_az, (int)(blockIdx.x + 1) * rows_per);
+  for (int row = blockIdx.x * rows_per + warp; row < row_end; row += nwarps) {
+    const int c = (int)(cnts[row] & 0xffu);
     const double2 cs = cs_table[row];
     int of = off_f[row], op = off_p[row];
     for (int e = lane; e < ((c + 31) & ~31); e += 32) {
@@ -435,8 +482,9 @@ k2_make_clouds(const uint32_t* __restrict__ row_keys, const uint16_t* __restrict
       const unsigned lt = (1u << lane) - 1u;
       if (ok) {
         const double rho = __dadd_rn(range_res_half, __dmul_rn(range_res, (double)r));  // radar_filters.cpp:329-330
-        const float x = (float)__dmul_rn(rho, cs.x);
-        const float y = (float)__dmul_rn(rho, cs.y);
+        float x = (float)__dmul_rn(rho, cs.x);
+        float y = (float)__dmul_rn(rho, cs.y);
+        if (mot) compensate_point(x, y, m0, m1, m2, ccw);
         const uint8_t inten = (uint8_t)((key >> 16) & 0xffu);
         const int q = of + __popc(bf & lt);
         if (q < cap) {
@@ -461,18 +509,12 @@ __global__ void k_compensate(float* __restrict__ x, float* __restrict__ y, const
   const int scan = blockIdx.y;
   const int n = count ? min(count[scan], cap) : cap;
   const double m0 = mot[scan * 3 + 0], m1 = mot[scan * 3 + 1], m2 = mot[scan * 3 + 2];
-  const double two_pi = __dmul_rn(2.0, 3.14159265358979323846);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const size_t q = (size_t)scan * cap + i;
-    const double px = (double)x[q], py = (double)y[q];
-    const double a = atan2(py, px);
-    double d = __ddiv_rn((a > 0.00001 ? a : __dadd_rn(two_pi, a)), two_pi);
-    d = ccw ? -(__dsub_rn(d, 0.5)) : __dsub_rn(d, 0.5);
-    const double ang = __dmul_rn(d, m2);
-    const double s1 = sin(ang), c1 = cos(ang);
-    const double tx = __dmul_rn(d, m0), ty = __dmul_rn(d, m1);
-    x[q] = (float)__dadd_rn(__dadd_rn(__dmul_rn(c1, px), __dmul_rn(-s1, py)), tx);
-    y[q] = (float)__dadd_rn(__dadd_rn(__dmul_rn(s1, px), __dmul_rn(c1, py)), ty);
+    float fx = x[q], fy = y[q];
+    compensate_point(fx, fy, m0, m1, m2, ccw);
+    x[q] = fx;
+    y[q] = fy;
   }
 }
 
@@ -497,7 +539,7 @@ int ensure_cs_table(tbv_ctx* ctx, int n_az) {
 }
 
 int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
-                          const tbv_filter_params* p, int want_peaks) {
+                          const tbv_filter_params* p, int want_peaks, const double* mot_dev, int ccw) {
   TBV_REQUIRE(ctx && polar_dev && p, "null pointer");
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
   TBV_REQUIRE(n_range <= 8192, "n_range > 8192 is not supported");
@@ -532,17 +574,17 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
     attr_set = true;
   }
   const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
-  k1_kstrongest<<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
-                                                             polar_dev, buf_hi, F.row_keys.p, F.row_cnt.p);
-  launched(ctx, "k1_kstrongest");
-  TBV_CUDA(cudaGetLastError());
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
   const int min_range_bin = (int)std::ceil((double)p->min_distance / rr);   // radar_filters.cpp:315
+  k1_kstrongest<<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
+                                                             polar_dev, buf_hi, min_range_bin, F.row_keys.p, F.row_cnt.p);
+  launched(ctx, "k1_kstrongest");
+  TBV_CUDA(cudaGetLastError());
   const size_t smem = 2 * (size_t)(n_az + 1) * sizeof(int);
-  k2_make_clouds<<<batch, 256, smem, ctx->stream>>>(F.row_keys.p, F.row_cnt.p, n_az, k, min_range_bin, rr, F.cs_table.p, n_az * k,
-                                                    F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, F.filtered.az.p, F.filtered.rg.p,
-                                                    F.filtered.count.p, want_peaks, F.peaks.x.p, F.peaks.y.p, F.peaks.inten.p, F.peaks.az.p,
-                                                    F.peaks.rg.p, F.peaks.count.p);
+  k2_make_clouds<<<dim3(K2_SPLIT, batch), 256, smem, ctx->stream>>>(F.row_keys.p, F.row_cnt.p, n_az, k, min_range_bin, rr, F.cs_table.p, n_az * k,
+                                                                    F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, F.filtered.az.p,
+                                                                    F.filtered.rg.p, F.filtered.count.p, want_peaks, F.peaks.x.p, F.peaks.y.p,
+                                                                    F.peaks.inten.p, F.peaks.az.p, F.peaks.rg.p, F.peaks.count.p, mot_dev, ccw);
   launched(ctx, "k2_make_clouds");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;

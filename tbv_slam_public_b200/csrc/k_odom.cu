@@ -256,7 +256,7 @@ static int odom_init(tbv_odom* od) {
   for (int s = 0; s < n_seq; s++) {
     for (int i = 0; i < K; i++)
       hv[(size_t)s * (K + 1) + i] = od->kf_grids.view(s * K + i, od->kf.set_ptr(s * K + i), od->cell_cap, od->kf.count.p + s * K + i, 0);
-    hv[(size_t)s * (K + 1) + K] = SetView{od->cur.set_ptr(s), od->cell_cap, od->cur.count.p + s, 0, nullptr, nullptr, nullptr, nullptr};
+    hv[(size_t)s * (K + 1) + K] = SetView{od->cur.set_ptr(s), od->cell_cap, od->cur.count.p + s, 0, nullptr, nullptr, nullptr};
   }
   TBV_CUDA(cudaMemcpyAsync(od->views.p, hv.data(), hv.size() * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
   k_odom_reset<<<(n_seq + 127) / 128, 128, 0, ctx->stream>>>(od->state.p, n_seq);
@@ -271,15 +271,16 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   tbv_ctx* ctx = od->ctx;
   const int n_seq = od->n_seq;
   cudaStream_t st = ctx->stream;
-  int rc = filter_kstrongest_dev(ctx, polar_dev, od->n_az, od->n_range, (size_t)od->n_range, n_seq, &od->par.filter, 1);
-  if (rc) return rc;
-  FilterState& F = ctx->filt;
+  // previous frame-to-frame motion first: K2 compensates the points as it emits them (odometrykeyframefuser.cpp:146-150)
+  int rc;
   if (od->par.compensate) {
     k_odom_motion<<<(n_seq + 127) / 128, 128, 0, st>>>(od->state.p, n_seq, od->mot.p);
     launched(ctx, "k_odom_motion");
-    if ((rc = compensate_clouds_dev(ctx, F.filtered, od->mot.p, od->par.radar_ccw))) return rc;
-    if ((rc = compensate_clouds_dev(ctx, F.peaks, od->mot.p, od->par.radar_ccw))) return rc;
   }
+  if ((rc = filter_kstrongest_dev(ctx, polar_dev, od->n_az, od->n_range, (size_t)od->n_range, n_seq, &od->par.filter, 1,
+                                  od->par.compensate ? od->mot.p : nullptr, od->par.radar_ccw)))
+    return rc;
+  FilterState& F = ctx->filt;
   if ((rc = cells_build_dev(ctx, F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, nullptr, F.filtered.count.p, F.filtered.cap, n_seq, od->cpar,
                             od->cell_cap, od->cur)))
     return rc;

@@ -366,7 +366,8 @@ __device__ __noinline__ void lm_candidate(LMState& S, const double* acc) {
     S.it_cost = S.x_cost;
     lm_gradient_norms(S);
     S.it_successful = true;
-    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * S.it_rel_dec - 1.0, 3.0));
+    const double q3 = 2.0 * S.it_rel_dec - 1.0;
+    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - q3 * q3 * q3);  // pow(2 rho - 1, 3)
     S.radius = fmin(1e16, S.radius);
     S.decrease_factor = 2.0;
     S.reuse_diagonal = false;
@@ -475,32 +476,49 @@ k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which
   for (int i = tid; i < n; i += 256) {
     const float a = (float)U0[i], b = (float)U1[i];
     const int pos = atomicAdd(&s_cnt[grid_coord(b, g.miny, g.ny) * g.nx + grid_coord(a, g.minx, g.nx)], 1);
-    t.gmean[pos] = make_float2(a, b);
-    t.gidx[pos] = (uint16_t)i;
+    t.gent[pos] = make_float4(a, b, __int_as_float(i), 0.f);
   }
 }
 
 // MapPointNormal::GetClosestIdx (pointnormal.cpp:238-254): float 1-NN over the cell means, accepted iff d2 < R*R.
-__device__ __forceinline__ int nn_search(const SetView& t, int n_tgt, float qx, float qy, double R) {
+// g = the set's grid header (staged in shared memory by the caller).  The bounds of the (at most three) bucket rows are
+// fetched together before any entry is read; an entry is one 16-byte record (mean x, y, cell index).
+__device__ __forceinline__ int nn_search(const SetView& t, const CellGrid& g, int n_tgt, float qx, float qy, double R) {
   float bestd = FLT_MAX;
   int best = -1;
-  const CellGrid* gp = t.grid;
-  if (gp && gp->ok) {
-    const CellGrid g = *gp;
+  if (t.grid && g.ok) {
     const float fx = floorf((qx - g.minx) / GRID_CELL), fy = floorf((qy - g.miny) / GRID_CELL);
     const int cbx = !(fx >= -2.f) ? -2 : (fx > (float)(g.nx + 1) ? g.nx + 1 : (int)fx);
     const int cby = !(fy >= -2.f) ? -2 : (fy > (float)(g.ny + 1) ? g.ny + 1 : (int)fy);
     const int bx0 = max(cbx - 1, 0), bx1 = min(cbx + 1, g.nx - 1);
-    if (bx0 <= bx1) {
-      for (int by = max(cby - 1, 0); by <= min(cby + 1, g.ny - 1); by++) {
-        const int s0 = t.gstart[by * g.nx + bx0], s1 = t.gstart[by * g.nx + bx1 + 1];
-        for (int s = s0; s < s1; s++) {
-          const float2 m = t.gmean[s];
-          const int i = t.gidx[s];
-          const float dx = qx - m.x, dy = qy - m.y;
-          float dd = dx * dx;   // FLANN L2_Simple, no contraction (-fmad=false)
-          dd = dd + dy * dy;
-          if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
+    const int by0 = max(cby - 1, 0), by1 = min(cby + 1, g.ny - 1);
+    if (bx0 <= bx1 && by0 <= by1) {
+      int s0[3], s1[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int by = by0 + r;
+        s0[r] = 0; s1[r] = 0;
+        if (by <= by1) { s0[r] = t.gstart[by * g.nx + bx0]; s1[r] = t.gstart[by * g.nx + bx1 + 1]; }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        for (int s = s0[r]; s < s1[r]; s += 2) {
+          const float4 e0 = t.gent[s];
+          const float4 e1 = t.gent[s + 1 < s1[r] ? s + 1 : s];   // odd tail: the same entry again (a tie with itself changes nothing)
+          {
+            const int i = __float_as_int(e0.z);
+            const float dx = qx - e0.x, dy = qy - e0.y;
+            float dd = dx * dx;   // FLANN L2_Simple, no contraction (-fmad=false)
+            dd = dd + dy * dy;
+            if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
+          }
+          {
+            const int i = __float_as_int(e1.z);
+            const float dx = qx - e1.x, dy = qy - e1.y;
+            float dd = dx * dx;
+            dd = dd + dy * dy;
+            if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
+          }
         }
       }
     }
@@ -565,6 +583,7 @@ struct RegShared {
   int flag, n_blocks, warp_cnt[RG_WARPS];
   Aff Tst[RG_MAX_FIXED], Ttar[RG_MAX_FIXED];
   SetView tgt[RG_MAX_FIXED];
+  CellGrid grid[RG_MAX_FIXED];   // search-grid headers of the fixed sets
   int n_tgt[RG_MAX_FIXED];
   LMState lm;
   OuterState outer;
@@ -662,6 +681,10 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   if (tid < n_fixed) {
     sh.tgt[tid] = sets[fixed_set[prob.fixed_first + tid]];
     sh.n_tgt[tid] = set_count(sh.tgt[tid]);
+    CellGrid g;
+    g.minx = g.miny = 0.f; g.nx = g.ny = 1; g.ok = 0;
+    if (sh.tgt[tid].grid) g = *sh.tgt[tid].grid;
+    sh.grid[tid] = g;
   }
   __syncthreads();
 
@@ -692,7 +715,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
         const double ux = src.f[(size_t)CF_U0 * src.cap + j], uy = src.f[(size_t)CF_U1 * src.cap + j];
         const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
         const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
-        int ti = nn_search(tgt, sh.n_tgt[fi], (float)qxd, (float)qyd, R);
+        int ti = nn_search(tgt, sh.grid[fi], sh.n_tgt[fi], (float)qxd, (float)qyd, R);
         if (ti >= 0) {
           const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
           const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
@@ -1032,8 +1055,7 @@ int GridStore::reserve(int n_sets_, int cell_cap_) {
   n_sets = n_sets_;
   cell_cap = cell_cap_;
   int rc;
-  if ((rc = hdr.reserve(n_sets_)) || (rc = start.reserve((size_t)n_sets_ * (GRID_CAP + 1))) || (rc = mean.reserve((size_t)n_sets_ * cell_cap_)) ||
-      (rc = idx.reserve((size_t)n_sets_ * cell_cap_)))
+  if ((rc = hdr.reserve(n_sets_)) || (rc = start.reserve((size_t)n_sets_ * (GRID_CAP + 1))) || (rc = ent.reserve((size_t)n_sets_ * cell_cap_)))
     return rc;
   return TBV_OK;
 }

@@ -84,7 +84,7 @@ struct FilterState {  // device-resident result of the last k-strongest call
   int batch = 0, n_az = 0, n_range = 0, k = 0;
   DevBuf<uint8_t> polar;       // staging for host-input calls
   DevBuf<uint32_t> row_keys;   // [batch][n_az][k]  bit31 = peak, bits 16..23 intensity, bits 0..15 range
-  DevBuf<uint16_t> row_cnt;    // [batch][n_az]
+  DevBuf<uint32_t> row_cnt;    // [batch][n_az]  bits 0..7 selected, 8..15 emitted (range > min_range_bin), 16..23 emitted peaks
   DevBuf<double2> cs_table;    // [n_az] (cos theta, sin theta) computed on the host with glibc
   int cs_n_az = 0;
   DevCloud filtered, peaks;
@@ -116,8 +116,9 @@ inline void launched(tbv_ctx* ctx, const char* name) {  // bookkeeping after eve
   if (ctx->prof.on) prof_mark(ctx, name);
 }
 // implemented in k_filter.cu
+// mot_dev != nullptr ([batch][3] previous frame-to-frame motion): both clouds are motion-compensated as they are emitted
 int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
-                          const tbv_filter_params* params, int want_peaks);
+                          const tbv_filter_params* params, int want_peaks, const double* mot_dev = nullptr, int ccw = 0);
 int compensate_clouds_dev(tbv_ctx* ctx, DevCloud& cloud, const double* mot_dev /*[batch][3]*/, int ccw);
 void cells_release(tbv_ctx* ctx);
 void reg_release(tbv_ctx* ctx);

@@ -19,19 +19,18 @@ struct SetView {        // one cell set (MapPointNormal) on the device, field-ma
   // search grid over the cell means (optional; built by cellgrid_build_launch): bucket b holds entries [gstart[b], gstart[b+1])
   CellGrid* grid;
   uint16_t* gstart;     // [GRID_CAP + 1]
-  float2* gmean;        // [cap] cell means narrowed to float (pcl::PointXY), in bucket order
-  uint16_t* gidx;       // [cap] cell index of each entry
+  float4* gent;         // [cap] entries in bucket order: (mean x, mean y) narrowed to float (pcl::PointXY), cell index as int bits
 };
 
 struct GridStore {      // storage for the grids of n_sets cell sets
   int n_sets = 0, cell_cap = 0;
   DevBuf<CellGrid> hdr;
-  DevBuf<uint16_t> start, idx;
-  DevBuf<float2> mean;
+  DevBuf<uint16_t> start;
+  DevBuf<float4> ent;
   int reserve(int n_sets_, int cell_cap_);
-  void release() { hdr.release(); start.release(); idx.release(); mean.release(); }
+  void release() { hdr.release(); start.release(); ent.release(); }
   SetView view(int i, const double* f, int cap, const int* n_ptr, int n_val) const {
-    return SetView{f, cap, n_ptr, n_val, hdr.p + i, start.p + (size_t)i * (GRID_CAP + 1), mean.p + (size_t)i * cell_cap, idx.p + (size_t)i * cell_cap};
+    return SetView{f, cap, n_ptr, n_val, hdr.p + i, start.p + (size_t)i * (GRID_CAP + 1), ent.p + (size_t)i * cell_cap};
   }
 };
 
