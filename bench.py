@@ -311,6 +311,22 @@ def run_reference(args):
     first = first_offsets(n_seq)
     sec, _ = oracle_py.odom_run_timed(oracle_py.default_odom_params(), pool, first, W, T, threads)
     value = n_seq * K / sec
+    # Filtering stage alone, one thread: the reference's OWN radar_filters.cpp (oracle/_ref, built from /root/reference where that
+    # exists) next to the oracle port of the same stage — shows which way the port's omitted overheads bias the baseline.
+    filtering = None
+    try:
+        from oracle import ref_py
+        if ref_py.available():
+            n_f = min(48, len(pool))
+            t0 = time.perf_counter(); ref_py.kstrongest_many(pool[:n_f], 60.0, K_STRONGEST, 2.5, 0.0438); t_ref = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for i in range(n_f):
+                oracle_py.kstrongest(pool[i], z_min=60.0, k=K_STRONGEST)
+            t_port = time.perf_counter() - t0
+            filtering = {"reference_ms_per_scan": round(t_ref / n_f * 1e3, 3), "port_ms_per_scan": round(t_port / n_f * 1e3, 3), "scans": n_f,
+                         "threads": 1, "note": "reference = unmodified radar_filters.cpp (constructor + both clouds) from oracle/_ref"}
+    except Exception as e:  # the timing of one stage must never take the arm down
+        filtering = {"error": str(e)[:200]}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": round(sec / K * 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -321,6 +337,7 @@ def run_reference(args):
                          "sample": f"{n_seq} independent sequences x {K} timed frames (after {W} warm-up frames) over {threads} host threads; "
                                    "a step = one frame of every sequence"},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "filtering_stage": filtering,
     }))
 
 
