@@ -69,6 +69,29 @@ def test_odometry_p2p_and_slow_motion_keyframes(ctx, oracle):
     _run_pair(ctx, oracle, [list(st.scans)], dict(reg=rp), dict(cost_type=oracle.P2P))
 
 
+def test_dense_short_range_clutter_uses_the_global_point_arrays(ctx, oracle):
+    """16 000 points per scan (every azimuth keeps k = 40) inside 39 m: more points than the fused cells kernel holds in shared
+    memory (8 192), so its point arrays live in global scratch — same results as the oracle, cell for cell."""
+    rng = np.random.default_rng(5)
+    img = np.full((400, 3768), 20, np.uint8)
+    hit = rng.random((400, 840)) < 0.3
+    img[:, 60:900][hit] = rng.integers(100, 256, size=int(hit.sum()), dtype=np.uint8)
+    scans = [img, img, img]
+    fuser = api.OdometryKeyframeFuser(ctx, 1, 400, 3768, api.default_odom_params())
+    ref = oracle.Odometry(oracle.default_odom_params())
+    for f in range(3):
+        g = fuser.pointcloudCallback(scans[f][None])[0]
+        r = ref.step(scans[f])
+        assert g.status == 0 and g.n_points > 8192
+        assert (g.n_points, g.n_cells, g.is_keyframe, g.n_keyframes) == (r.n_points, r.n_cells, r.is_keyframe, r.n_keyframes), f"frame {f}"
+        assert abs(g.pose[0] - r.pose[0]) < POS_TOL and abs(g.pose[1] - r.pose[1]) < POS_TOL and _ang(g.pose[2] - r.pose[2]) < ANG_TOL
+    cells, _ = fuser.cells(0, 0)
+    ref_cells = ref.keyframe_cells(0)
+    assert len(cells) == len(ref_cells) > 100
+    assert np.allclose(cells[:, :2], ref_cells[:, :2], rtol=0, atol=1e-9)
+    fuser.close()
+
+
 def test_pipelined_submit_collect_matches_sync(ctx):
     st = synth.make_stream(6)
     n_seq = 3
