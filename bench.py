@@ -110,7 +110,9 @@ def algorithmic_bytes(kernel: str, n_seq: int, st: dict) -> float | None:
         # row keys in + two clouds (x,y f32, I u8, az,rg u16 = 13 B/pt; peaks ~ a third of the points) out
         "k2_make_clouds": N_AZ * K_STRONGEST * 4 + N_AZ * 2 + 13 * npts * 1.33,
         "k_compensate": 2 * 8 * npts,
-        # points (x,y f32 + I u8) in, one 16-double candidate record per voxel sample out
+        # fused cells kernel: points (x,y f32 + I u8) in, one 16-double record per valid cell out (all tables in shared memory)
+        "cells_fused": 9 * npts + 128 * ncell,
+        # legacy multi-kernel cells path (fine voxel grids only)
         "c5_cells": 9 * npts + 128 * nsmp,
         "c4_centroids": 12 * npts + 8 * nsmp,
         # (moving + keyframes) cells x 6 doubles used (u, n, N, planarity) in, one result record out
@@ -258,8 +260,8 @@ def run_ours(args):
         kernels[name] = {"ms_per_step": round(ms, 4), "share": round(ms / sum(kern.values()), 4),
                          "algorithmic_GBps": round(b / ms / 1e6, 1) if b else None}
     # The roofline object describes the kernel that dominates the step's HBM traffic: K1 streams every scan byte (96 % of the
-    # step's algorithmic bytes).  The longest kernels (k_register, c5_cells) move ~100x fewer bytes and are bound by fp64
-    # issue / dependent-load latency, not by HBM or the tensor pipe: their lines are in `kernels`, the whole step's in `step`.
+    # step's algorithmic bytes).  The longest kernels (k_register, cells_fused) move ~100x fewer bytes and are bound by fp64
+    # issue / dependent-load latency / barriers, not by HBM or the tensor pipe: their lines are in `kernels`, the whole step's in `step`.
     dominant = "k1_kstrongest"
     longest = max(kern, key=kern.get)
     b_dom = algorithmic_bytes(dominant, S, stats)

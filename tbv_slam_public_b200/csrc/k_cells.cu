@@ -996,7 +996,7 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
     if (want_dbg) {
       if ((rc = S.dbg.reserve((size_t)batch * 8))) return rc;
     }
-    static const int l5 = getenv("TBV_CELLS_L5") ? atoi(getenv("TBV_CELLS_L5")) : 4;
+    static const int l5 = getenv("TBV_CELLS_L5") ? atoi(getenv("TBV_CELLS_L5")) : 2;
     auto launch = [&](auto kern) -> int {
       if (!S.fused_attr_set) {
         TBV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFU_SMEM));
@@ -1011,7 +1011,8 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
     else if (l5 == 2) rc = launch(cells_fused<2>);
     else if (l5 == 8) rc = launch(cells_fused<8>);
     else if (l5 == 16) rc = launch(cells_fused<16>);
-    else rc = launch(cells_fused<4>);
+    else if (l5 == 4) rc = launch(cells_fused<4>);
+    else rc = launch(cells_fused<2>);
     if (rc) return rc;
     launched(ctx, "cells_fused");
     TBV_CUDA(cudaGetLastError());

@@ -490,8 +490,19 @@ __device__ __forceinline__ int nn_search(const SetView& t, const CellGrid& g, in
     const float fx = floorf((qx - g.minx) / GRID_CELL), fy = floorf((qy - g.miny) / GRID_CELL);
     const int cbx = !(fx >= -2.f) ? -2 : (fx > (float)(g.nx + 1) ? g.nx + 1 : (int)fx);
     const int cby = !(fy >= -2.f) ? -2 : (fy > (float)(g.ny + 1) ? g.ny + 1 : (int)fy);
-    const int bx0 = max(cbx - 1, 0), bx1 = min(cbx + 1, g.nx - 1);
-    const int by0 = max(cby - 1, 0), by1 = min(cby + 1, g.ny - 1);
+    // Buckets that can hold a point closer than R: the 3 x 3 block around the query's bucket (R <= GRID_CELL), cut down to the
+    // buckets the square [q - R, q + R] (plus a float-rounding margin) touches — one or two per axis once R = radius_ = 2 m.
+    // A neighbour outside that square is farther than R and would be rejected by the final test anyway, so the result is the
+    // same as the exhaustive 1-NN + radius test of the reference.
+    const float Rm = (float)R + 1e-3f;
+    const float lx = floorf((qx - Rm - g.minx) / GRID_CELL), hx = floorf((qx + Rm - g.minx) / GRID_CELL);
+    const float ly = floorf((qy - Rm - g.miny) / GRID_CELL), hy = floorf((qy + Rm - g.miny) / GRID_CELL);
+    int bx0 = max(cbx - 1, 0), bx1 = min(cbx + 1, g.nx - 1);
+    int by0 = max(cby - 1, 0), by1 = min(cby + 1, g.ny - 1);
+    if (lx > (float)bx0) bx0 = (int)fminf(lx, (float)g.nx);
+    if (hx < (float)bx1) bx1 = (int)fmaxf(hx, -1.f);
+    if (ly > (float)by0) by0 = (int)fminf(ly, (float)g.ny);
+    if (hy < (float)by1) by1 = (int)fmaxf(hy, -1.f);
     if (bx0 <= bx1 && by0 <= by1) {
       int s0[3], s1[3];
 #pragma unroll

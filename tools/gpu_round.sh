@@ -12,9 +12,9 @@ timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2
 cat gpurun_out/bench_reference.json | head -c 400
 # launch list: skip warm-up launches (3 warm-up steps x ~14 launches), 2 timed steps
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-for k in k_register c5_cells k1_kstrongest c4_centroids; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 2 -f -o gpurun_out/full_$k \
-     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$k.log 2>&1; echo "ncu full $k rc=$?"
+   python bench.py --steps 2 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+for k in k_register cells_fused k1_kstrongest k2_make_clouds; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 2 -f -o gpurun_out/full_$k \
+     python bench.py --steps 2 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_full_$k.log 2>&1; echo "ncu full $k rc=$?"
 done
 ls -la gpurun_out
