@@ -197,6 +197,17 @@ int tbv_register(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const 
 int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T,
                  const tbv_reg_params* params, int itr, double* score, double* cost, int* n_res, double* residuals,
                  int res_capacity);
+/* OdometryKeyframeFuser::approximateCovarianceBySampling (cfear_radarodometry/src/cfear_radarodometry/odometrykeyframefuser.cpp:261-380;
+ * the same block in tbv_slam/src/tbv_slam/loopclosure.cpp:127-200).  Sampling half: the n_per_axis^3 GetCost evaluations around the last
+ * scan's pose T[n_scans-1] (grid linspace(-xy_range/2, xy_range/2) x same x linspace(-yaw_range/2, yaw_range/2); theta-major, then x,
+ * then y) run as independent problems in ONE launch.  samples: [n_per_axis^3][4] = dx, dy, dyaw, cost (problem_->Evaluate's total cost).
+ * itr: the registration object's itr_ at the time of the call (after Register: > 1 -> search radius radius_). */
+int tbv_cost_samples(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T,
+                     const tbv_reg_params* params, int itr, double xy_range, double yaw_range, int n_per_axis, double* samples);
+/* Fitting half (host arithmetic): least-squares quadric through the samples, Hessian, convexity test, covariance
+ * 2 H^-1 * score_scale * cov_scaler in the reference's 6x6 layout (x, y, ., ., ., yaw; row-major).  score_scale = GetCovarianceScaler()
+ * = final_cost / (num_residuals - 3) of the preceding Register (n_scan_normal.cpp:433-439).  *convex = 0: the sampling is not used. */
+int tbv_cov_from_cost_samples(const double* samples, int n_samples, double score_scale, double cov_scaler, double cov6x6[36], int* convex);
 /* Batched independent two-scan registrations — loopclosure::Register (tbv_slam/src/tbv_slam/loopclosure.cpp:35-97):
  * pair p registers `from` (moving, pose T_from[p]) against `to` (fixed, pose T_to[p]) with P2L / Huber 0.1 / uniform
  * weights / SetParameters(4,10) unless params says otherwise.  Cell sets are given once (n_sets), pairs index them.

@@ -186,6 +186,50 @@ int orc_get_cost(int n_scans, const double* const* recs, const int* n_cells, con
   for (size_t i = 0; i < res.size() && (int)i < cap; i++) residuals[i] = res[i];
   return (int)res.size();
 }
+// OdometryKeyframeFuser::approximateCovarianceBySampling (odometrykeyframefuser.cpp:261-380), the sampling half: n^3 GetCost
+// evaluations around T.back() on the grid linspace(-xy/2, xy/2, n)^2 x linspace(-yaw/2, yaw/2, n), theta-major then x then y (:293-296).
+// samples: [n^3][4] = (dx, dy, dyaw, cost); a failed GetCost keeps the previous sample's cost (sample_cost is not reset, :283,304).
+// Returns the number of samples.
+static std::vector<double> orc_linspace(double start, double end, int num) {  // odometrykeyframefuser.cpp:498-524
+  std::vector<double> v;
+  if (num == 0) return v;
+  if (num == 1) { v.push_back(start); return v; }
+  const double delta = (end - start) / ((double)num - 1);
+  for (int i = 0; i < num - 1; ++i) v.push_back(start + delta * i);
+  v.push_back(end);
+  return v;
+}
+int orc_cost_samples(int n_scans, const double* const* recs, const int* n_cells, const double* T, const orc_reg_params* p, int itr,
+                     double xy_range, double yaw_range, int n_per_axis, double* samples) {
+  std::vector<MapNormalPtr> scans;
+  std::vector<Affine2> Tv;
+  for (int i = 0; i < n_scans; i++) {
+    scans.push_back(MapFromRecs(recs[i], n_cells[i], 0.f));
+    Tv.push_back(vectorToAffine(T[3 * i], T[3 * i + 1], T[3 * i + 2]));
+  }
+  n_scan_normal_reg reg = MakeReg(p);
+  const Affine2 Tbest = Tv.back();
+  const std::vector<double> xy = orc_linspace(-xy_range * 0.5, xy_range * 0.5, n_per_axis);
+  const std::vector<double> th = orc_linspace(-yaw_range * 0.5, yaw_range * 0.5, n_per_axis);
+  double sample_cost = 0;
+  std::vector<double> res;
+  int k = 0;
+  for (int it = 0; it < n_per_axis; it++)
+    for (int ix = 0; ix < n_per_axis; ix++)
+      for (int iy = 0; iy < n_per_axis; iy++) {
+        Affine2 S;  // translation = (dx, dy) + T_best.translation ; linear = AngleAxis(dtheta, z) * T_best.linear
+        const double c = std::cos(th[it]), sn = std::sin(th[it]);
+        S.r00 = c * Tbest.r00 + (-sn) * Tbest.r10; S.r01 = c * Tbest.r01 + (-sn) * Tbest.r11;
+        S.r10 = sn * Tbest.r00 + c * Tbest.r10;    S.r11 = sn * Tbest.r01 + c * Tbest.r11;
+        S.tx = xy[ix] + Tbest.tx; S.ty = xy[iy] + Tbest.ty;
+        Tv.back() = S;
+        reg.itr_ = (size_t)itr;
+        reg.GetCost(scans, Tv, sample_cost, res);
+        samples[4 * k + 0] = xy[ix]; samples[4 * k + 1] = xy[iy]; samples[4 * k + 2] = th[it]; samples[4 * k + 3] = sample_cost;
+        k++;
+      }
+  return k;
+}
 // One (target, source) pair: associate at the given poses with search radius chosen by `itr` (1 -> 2*radius_),
 // then evaluate cost, gradient g = J^T r and H = J^T J (robustified, unscaled) at x = T_src.  assoc (optional,
 // length n_src): target index per source cell or -1.

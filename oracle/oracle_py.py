@@ -250,6 +250,19 @@ def get_cost(scans, T, params: RegParams | None = None, itr=0):
     return n, score.value, cost.value, res[:max(n, 0)]
 
 
+def cost_samples(scans, T, params: RegParams | None = None, itr=2, xy_range=0.4, yaw_range=0.0043625, n_per_axis=3):
+    """approximateCovarianceBySampling's sampling half: [n^3, 4] = (dx, dy, dyaw, cost)."""
+    params = params or default_reg_params()
+    arrs, ptrs, ns = _scan_ptrs(scans)
+    Tio = np.ascontiguousarray(T, np.float64).reshape(len(scans), 3)
+    out = np.zeros((n_per_axis ** 3, 4))
+    lib().orc_cost_samples.restype = C.c_int
+    n = lib().orc_cost_samples(len(scans), ptrs, _p(ns, C.c_int), _p(Tio, C.c_double), C.byref(params), itr, C.c_double(xy_range),
+                               C.c_double(yaw_range), n_per_axis, _p(out, C.c_double))
+    assert n == len(out)
+    return out
+
+
 def pair_normal_eq(tgt, T_tgt, src, T_src, params: RegParams | None = None, itr=1):
     params = params or default_reg_params()
     tgt = np.ascontiguousarray(tgt, np.float64); src = np.ascontiguousarray(src, np.float64)

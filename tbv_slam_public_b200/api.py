@@ -329,6 +329,21 @@ class Context:
                                   C.byref(n), _ptr(res), cap))
         return n.value, score.value, cost.value, res[:max(n.value, 0)]
 
+    def approximateCovarianceBySampling(self, scans, T, score_scale, params: RegParams | None = None, itr=2, xy_range=0.4,
+                                        yaw_range=0.0043625, samples_per_axis=3, covariance_scaler=4.0):
+        """OdometryKeyframeFuser::approximateCovarianceBySampling: returns (ok, cov6x6, samples[n^3, 4])."""
+        params = params or default_reg_params()
+        arrs, ptrs, ns = self._scan_ptrs(scans)
+        Tio = np.ascontiguousarray(T, np.float64).reshape(len(scans), 3)
+        samples = np.zeros((samples_per_axis ** 3, 4))
+        _check(lib().tbv_cost_samples(self.h, len(scans), ptrs, _ptr(ns), _ptr(Tio), C.byref(params), itr, C.c_double(xy_range),
+                                      C.c_double(yaw_range), samples_per_axis, _ptr(samples)))
+        cov = np.zeros((6, 6))
+        ok = C.c_int(0)
+        _check(lib().tbv_cov_from_cost_samples(_ptr(samples), len(samples), C.c_double(score_scale), C.c_double(covariance_scaler), _ptr(cov),
+                                               C.byref(ok)))
+        return bool(ok.value), cov, samples
+
     def RegisterBatch(self, sets, from_set, to_set, T_from, T_to, params: RegParams | None = None):
         """loopclosure::Register for many candidates at once. Returns (T_revised [n,3], T_align [n,3], summaries)."""
         params = params or default_reg_params(max_itr_association=4, max_itr_solver=10)

@@ -426,6 +426,7 @@ __device__ __forceinline__ void compensate_point(float& x, float& y, double m0, 
 // are motion-compensated as they are emitted (odometrykeyframefuser.cpp:146-150 applies Compensate to both clouds right after
 // the filter; a peak is the same point in both clouds, so it is compensated once).
 constexpr int K2_SPLIT = 4;
+constexpr int K2_STAGE = 4096;  // staged points per chunk of rows (k <= 128 <= K2_STAGE)
 __global__ void __launch_bounds__(256)
 k2_make_clouds(const uint32_t* __restrict__ row_keys, const uint32_t* __restrict__ row_cnt, int n_az, int k, int min_range_bin,
                double range_res, const double2* __restrict__ cs_table, int cap,
@@ -462,44 +463,64 @@ k2_make_clouds(const uint32_t* __restrict__ row_keys, const uint32_t* __restrict
     }
   }
   __syncthreads();
-  // phase 2: emit the points of this CTA's rows
+  // phase 2: the points of this CTA's rows.  A row keeps only ~12 of its k entries on radar data, so computing the points warp-per-row
+  // would leave most lanes idle through the fp64 atan2 / sincos of the compensation.  Instead the rows are first compacted (cheap,
+  // warp per row) into a staging list in shared memory, in output order; then one thread per staged point does the arithmetic and
+  // the stores are coalesced.  Rows are taken in chunks whose k * rows fit the staging list.
+  uint32_t* st_key = reinterpret_cast<uint32_t*>(s_off + 2 * (n_az + 1));   // [K2_STAGE] packed key
+  int* st_pq = reinterpret_cast<int*>(st_key + K2_STAGE);                   // [K2_STAGE] position in the peaks cloud, or -1
+  uint16_t* st_row = reinterpret_cast<uint16_t*>(st_pq + K2_STAGE);         // [K2_STAGE] azimuth
   const double range_res_half = range_res / 2.0;
   const size_t cbase = (size_t)scan * cap;
   double m0 = 0.0, m1 = 0.0, m2 = 0.0;
   if (mot) { m0 = mot[scan * 3 + 0]; m1 = mot[scan * 3 + 1]; m2 = mot[scan * 3 + 2]; }
   const int rows_per = (n_az + gridDim.x - 1) / gridDim.x;
-  const int row_end = min(n_az, (int)(blockIdx.x + 1) * rows_per);
-  for (int row = blockIdx.x * rows_per + warp; row < row_end; row += nwarps) {
-    const int c = (int)(cnts[row] & 0xffu);
-    const double2 cs = cs_table[row];
-    int of = off_f[row], op = off_p[row];
-    for (int e = lane; e < ((c + 31) & ~31); e += 32) {
-      const uint32_t key = e < c ? keys[(size_t)row * k + e] : 0u;
-      const int r = (int)(key & 0xffffu);
-      const bool ok = e < c && r > min_range_bin;
-      const bool pk = ok && (key >> 31);
-      const unsigned bf = __ballot_sync(FULL, ok), bp = __ballot_sync(FULL, pk);
-      const unsigned lt = (1u << lane) - 1u;
-      if (ok) {
-        const double rho = __dadd_rn(range_res_half, __dmul_rn(range_res, (double)r));  // radar_filters.cpp:329-330
-        float x = (float)__dmul_rn(rho, cs.x);
-        float y = (float)__dmul_rn(rho, cs.y);
-        if (mot) compensate_point(x, y, m0, m1, m2, ccw);
-        const uint8_t inten = (uint8_t)((key >> 16) & 0xffu);
-        const int q = of + __popc(bf & lt);
-        if (q < cap) {
-          fx[cbase + q] = x; fy[cbase + q] = y; fi[cbase + q] = inten; faz[cbase + q] = (uint16_t)row; frg[cbase + q] = (uint16_t)r;
+  const int row_begin = min(n_az, (int)blockIdx.x * rows_per), row_end = min(n_az, row_begin + rows_per);
+  const int chunk_rows = max(1, K2_STAGE / max(k, 1));
+  for (int r0 = row_begin; r0 < row_end; r0 += chunk_rows) {
+    const int r1 = min(row_end, r0 + chunk_rows);
+    const int base_f = off_f[r0];
+    for (int row = r0 + warp; row < r1; row += nwarps) {
+      const int c = (int)(cnts[row] & 0xffu);
+      int of = off_f[row] - base_f, op = off_p[row];
+      for (int e = lane; e < ((c + 31) & ~31); e += 32) {
+        const uint32_t key = e < c ? keys[(size_t)row * k + e] : 0u;
+        const bool ok = e < c && (int)(key & 0xffffu) > min_range_bin;
+        const bool pk = ok && (key >> 31);
+        const unsigned bf = __ballot_sync(FULL, ok), bp = __ballot_sync(FULL, pk);
+        const unsigned lt = (1u << lane) - 1u;
+        if (ok) {
+          const int q = of + __popc(bf & lt);
+          st_key[q] = key;
+          st_row[q] = (uint16_t)row;
+          st_pq[q] = (pk && want_peaks) ? op + __popc(bp & lt) : -1;
         }
-        if (pk && want_peaks) {
-          const int qp = op + __popc(bp & lt);
-          if (qp < cap) {
-            px[cbase + qp] = x; py[cbase + qp] = y; pi[cbase + qp] = inten; paz[cbase + qp] = (uint16_t)row; prg[cbase + qp] = (uint16_t)r;
-          }
-        }
+        of += __popc(bf);
+        op += __popc(bp);
       }
-      of += __popc(bf);
-      op += __popc(bp);
     }
+    __syncthreads();
+    const int n_local = off_f[r1 - 1] + (int)((cnts[r1 - 1] >> 8) & 0xffu) - base_f;
+    for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
+      const uint32_t key = st_key[i];
+      const int row = st_row[i];
+      const int r = (int)(key & 0xffffu);
+      const double2 cs = cs_table[row];
+      const double rho = __dadd_rn(range_res_half, __dmul_rn(range_res, (double)r));  // radar_filters.cpp:329-330
+      float x = (float)__dmul_rn(rho, cs.x);
+      float y = (float)__dmul_rn(rho, cs.y);
+      if (mot) compensate_point(x, y, m0, m1, m2, ccw);
+      const uint8_t inten = (uint8_t)((key >> 16) & 0xffu);
+      const int q = base_f + i;
+      if (q < cap) {
+        fx[cbase + q] = x; fy[cbase + q] = y; fi[cbase + q] = inten; faz[cbase + q] = (uint16_t)row; frg[cbase + q] = (uint16_t)r;
+      }
+      const int qp = st_pq[i];
+      if (qp >= 0 && qp < cap) {
+        px[cbase + qp] = x; py[cbase + qp] = y; pi[cbase + qp] = inten; paz[cbase + qp] = (uint16_t)row; prg[cbase + qp] = (uint16_t)r;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -580,7 +601,12 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
                                                              polar_dev, buf_hi, min_range_bin, F.row_keys.p, F.row_cnt.p);
   launched(ctx, "k1_kstrongest");
   TBV_CUDA(cudaGetLastError());
-  const size_t smem = 2 * (size_t)(n_az + 1) * sizeof(int);
+  const size_t smem = 2 * (size_t)(n_az + 1) * sizeof(int) + (size_t)K2_STAGE * (sizeof(uint32_t) + sizeof(int) + sizeof(uint16_t));
+  static size_t k2_smem_set = 48 * 1024;
+  if (smem > k2_smem_set) {
+    TBV_CUDA(cudaFuncSetAttribute(k2_make_clouds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k2_smem_set = smem;
+  }
   k2_make_clouds<<<dim3(K2_SPLIT, batch), 256, smem, ctx->stream>>>(F.row_keys.p, F.row_cnt.p, n_az, k, min_range_bin, rr, F.cs_table.p, n_az * k,
                                                                     F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, F.filtered.az.p,
                                                                     F.filtered.rg.p, F.filtered.count.p, want_peaks, F.peaks.x.p, F.peaks.y.p,

@@ -664,8 +664,10 @@ __global__ void __launch_bounds__(RG_THREADS, MIN_CTAS)
 k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
            const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
            double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
-           double* __restrict__ residuals_all, double* __restrict__ wgt_all) {
+           double* __restrict__ residuals_all, double* __restrict__ wgt_all, unsigned long long* __restrict__ dbg) {
   __shared__ RegShared sh;
+  long long t_assoc = 0, t_eval = 0, t_lm = 0, t_mark = 0;
+  const long long t_start = dbg ? clock64() : 0;
   const int p = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned FULL = 0xffffffffu;
@@ -698,6 +700,29 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     sh.grid[tid] = g;
   }
   __syncthreads();
+  // Pull the problem's read-only working set into L2 with full-line prefetches (all lines in flight at once): the cell fields
+  // the association reads (mean, normal, N, planarity) of the moving set and of every fixed set, and the fixed sets' grid
+  // entries.  The association itself touches them through short dependent chains (query -> bucket rows -> entries -> target
+  // fields) and would otherwise pay a DRAM round trip at every link the first time.
+  {
+    const int pf_fields[6] = {CF_U0, CF_U1, CF_N0, CF_N1, CF_NS, CF_SCALE};
+    for (int f = -1; f < n_fixed; f++) {
+      const double* base = (f < 0) ? src.f : sh.tgt[f].f;
+      const size_t cap = (f < 0) ? (size_t)src.cap : (size_t)sh.tgt[f].cap;
+      const int cnt = (f < 0) ? n_src : sh.n_tgt[f];
+      const int lines = (cnt * 8 + 127) / 128;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const char* ptr = reinterpret_cast<const char*>(base + (size_t)pf_fields[k] * cap);
+        for (int l = tid; l < lines; l += RG_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (size_t)l * 128));
+      }
+      if (f >= 0 && sh.tgt[f].gent) {
+        const char* ptr = reinterpret_cast<const char*>(sh.tgt[f].gent);
+        const int elines = (cnt * 16 + 127) / 128;
+        for (int l = tid; l < elines; l += RG_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (size_t)l * 128));
+      }
+    }
+  }
 
   // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan).  Slot = (fixed scan, source
   // cell), fixed-major: the order the reference adds its residual blocks in.  Every warp owns a contiguous slot range:
@@ -723,22 +748,25 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
         const int j = slot - fi * n_src;
         const Aff Tst = sh.Tst[fi];
         const SetView& tgt = sh.tgt[fi];
+        // every source-side value is fetched before the search, every target-side value right after it: two round trips
+        // instead of one per dependent use
         const double ux = src.f[(size_t)CF_U0 * src.cap + j], uy = src.f[(size_t)CF_U1 * src.cap + j];
+        const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
         const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
         const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
         int ti = nn_search(tgt, sh.grid[fi], sh.n_tgt[fi], (float)qxd, (float)qyd, R);
         if (ti >= 0) {
-          const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
+          const bool weighted = P.weight_opt != TBV_W_UNIFORM;
+          const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
+          const double N2 = weighted ? tgt.f[(size_t)CF_NS * tgt.cap + ti] : 0.0, p2 = weighted ? tgt.f[(size_t)CF_SCALE * tgt.cap + ti] : 0.0;
+          const double N1 = weighted ? src.f[(size_t)CF_NS * src.cap + j] : 0.0, p1 = weighted ? src.f[(size_t)CF_SCALE * src.cap + j] : 0.0;
           const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
           const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
-          const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
           const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
           if (sim > P.angle_outlier) {
             ok = true;
             double w = 1.0;
-            if (P.weight_opt != TBV_W_UNIFORM) {
-              const double N1 = src.f[(size_t)CF_NS * src.cap + j], N2 = tgt.f[(size_t)CF_NS * tgt.cap + ti];
-              const double p1 = src.f[(size_t)CF_SCALE * src.cap + j], p2 = tgt.f[(size_t)CF_SCALE * tgt.cap + ti];
+            if (weighted) {
               const double simN = 2 * fmin(N1, N2) / (N1 + N2);
               const double simP = 2 * fmin(p1, p2) / (p1 + p2);
               switch (P.weight_opt) {   // registration.cpp:67-75
@@ -934,7 +962,9 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       __syncwarp();
       publish_eval_point(true);
     }
+    if (dbg) t_mark = clock64();
     associate(O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
+    if (dbg) { const long long t = clock64(); t_assoc += t - t_mark; t_mark = t; }
     const int nblk = sh.n_blocks;
     if (nblk * nres_per_block <= 1) {  // BuildOptimizationProblem fails (:371-374): Register returns false, itr_ not advanced
       if (tid == 0) { O.num_residuals = nblk * nres_per_block; O.success = 0; }
@@ -944,6 +974,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     bool first = true;
     for (;;) {
       evaluate(nblk, false);
+      if (dbg) { const long long t = clock64(); t_eval += t - t_mark; t_mark = t; }
       if (warp == 0) {
         combine();
         bool go = false;
@@ -959,6 +990,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       }
       first = false;
       __syncthreads();
+      if (dbg) { const long long t = clock64(); t_lm += t - t_mark; t_mark = t; }
       if (!sh.flag) break;
     }
   }
@@ -984,6 +1016,10 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     r.align[0] = Tal.tx; r.align[1] = Tal.ty; r.align[2] = atan2(Tal.r10, Tal.r11);
     *out = r;
     if (n_blocks_all) n_blocks_all[p] = sh.n_blocks;
+    if (dbg) {
+      atomicAdd(&dbg[0], (unsigned long long)t_assoc); atomicAdd(&dbg[1], (unsigned long long)t_eval); atomicAdd(&dbg[2], (unsigned long long)t_lm);
+      atomicAdd(&dbg[3], (unsigned long long)(clock64() - t_start)); atomicAdd(&dbg[4], 1ull);
+    }
   }
 }
 
@@ -1036,16 +1072,27 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
     const char* e = getenv("TBV_REG_CTAS");
     min_ctas = (e && atoi(e) == 3) ? 3 : 4;
   }
+  static unsigned long long* dbg = nullptr;
+  static const bool want_dbg = getenv("TBV_REG_DBG") != nullptr;
+  if (want_dbg && !dbg) TBV_CUDA(cudaMalloc((void**)&dbg, 8 * sizeof(unsigned long long)));
+  if (want_dbg) TBV_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(unsigned long long), ctx->stream));
   if (min_ctas == 3)
     k_register<3><<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p);
+                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg);
   else
     k_register<4><<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p);
+                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
+  if (want_dbg) {  // debug only: mean cycles per problem spent in association / evaluation / LM + barrier
+    unsigned long long h[8];
+    TBV_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h[4]) fprintf(stderr, "k_register cycles/problem: associate %.0f  evaluate %.0f  lm+barrier %.0f  total %.0f\n", (double)h[0] / h[4], (double)h[1] / h[4],
+                      (double)h[2] / h[4], (double)h[3] / h[4]);
+  }
   return TBV_OK;
 }
 
@@ -1238,6 +1285,166 @@ int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const 
   if (score) *score = r.score;
   if (residuals)
     for (int i = 0; i < (int)res.size() && i < res_capacity; i++) residuals[i] = res[i];
+  return TBV_OK;
+}
+
+// OdometryKeyframeFuser::approximateCovarianceBySampling, sampling half (odometrykeyframefuser.cpp:261-313): the n^3 GetCost
+// evaluations around T.back() are n^3 independent problems over the same cell sets -> ONE launch of k_register in evaluation mode.
+int tbv_cost_samples(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T, const tbv_reg_params* params,
+                     int itr, double xy_range, double yaw_range, int n_per_axis, double* samples) {
+  TBV_REQUIRE(ctx && scans && n_cells && T && params && samples && n_scans >= 2 && n_per_axis >= 1 && n_per_axis <= 16, "bad arguments");
+  auto linspace = [](double start, double end, int num) {  // odometrykeyframefuser.cpp:498-524
+    std::vector<double> v;
+    if (num == 1) { v.push_back(start); return v; }
+    const double delta = (end - start) / ((double)num - 1);
+    for (int i = 0; i < num - 1; ++i) v.push_back(start + delta * i);
+    v.push_back(end);
+    return v;
+  };
+  const std::vector<double> xy = linspace(-xy_range * 0.5, xy_range * 0.5, n_per_axis);
+  const std::vector<double> th = linspace(-yaw_range * 0.5, yaw_range * 0.5, n_per_axis);
+  const int n_fixed = n_scans - 1, n_samples = n_per_axis * n_per_axis * n_per_axis;
+  HostProblemSet hs;
+  hs.ctx = ctx;
+  int rc = hs.upload(n_scans, scans, n_cells);
+  if (rc) return rc;
+  const double* Tb = T + 3 * (n_scans - 1);
+  const double cb = std::cos(Tb[2]), sb = std::sin(Tb[2]);  // T_best_guess.linear() (vectorToAffine3d, registration.cpp:129-135)
+  std::vector<RegProblem> hp(n_samples);
+  int q = 0;
+  for (int it = 0; it < n_per_axis; it++)
+    for (int ix = 0; ix < n_per_axis; ix++)
+      for (int iy = 0; iy < n_per_axis; iy++, q++) {
+        // sample_T.linear() = AngleAxis(dtheta, z) * T_best.linear(); GetCost reads the yaw back as atan2(R10, R11) (utils.cpp:115-122)
+        const double c = std::cos(th[it]), sn = std::sin(th[it]);
+        const double r10 = sn * cb + c * sb, r11 = sn * (-sb) + c * cb;
+        RegProblem& pr = hp[q];
+        pr.n_fixed = n_fixed; pr.fixed_first = 0; pr.src_set = n_scans - 1; pr.active = 1;
+        pr.src_pose[0] = xy[ix] + Tb[0]; pr.src_pose[1] = xy[iy] + Tb[1]; pr.src_pose[2] = std::atan2(r10, r11);
+        samples[4 * q + 0] = xy[ix]; samples[4 * q + 1] = xy[iy]; samples[4 * q + 2] = th[it]; samples[4 * q + 3] = 0.0;
+      }
+  std::vector<int> hfs(n_fixed);
+  std::vector<double> hfp((size_t)n_fixed * 3);
+  for (int i = 0; i < n_fixed; i++) {
+    hfs[i] = i;
+    for (int c = 0; c < 3; c++) hfp[3 * i + c] = T[3 * i + c];
+  }
+  DevBuf<RegProblem> dp; DevBuf<int> dfs; DevBuf<double> dfp, dev_eval; DevBuf<RegResult> dr;
+  auto cleanup = [&]() { dp.release(); dfs.release(); dfp.release(); dev_eval.release(); dr.release(); };
+  if ((rc = to_device(ctx, dp, hp)) || (rc = to_device(ctx, dfs, hfs)) || (rc = to_device(ctx, dfp, hfp)) || (rc = dr.reserve(n_samples)) ||
+      (rc = dev_eval.reserve((size_t)n_samples * NACC))) { cleanup(); return rc; }
+  const int slot_cap = n_cells[n_scans - 1] > 0 ? n_cells[n_scans - 1] : 1;
+  rc = register_launch(ctx, REG_MODE_EVAL, itr, hs.views.p, dp.p, dfs.p, dfp.p, n_samples, n_fixed, slot_cap, hs.max_n, to_dev(*params), dr.p,
+                       dev_eval.p, false);
+  if (rc) { cleanup(); return rc; }
+  std::vector<RegResult> hr(n_samples);
+  std::vector<double> ev((size_t)n_samples * NACC);
+  cudaError_t e = cudaMemcpyAsync(hr.data(), dr.p, n_samples * sizeof(RegResult), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ev.data(), dev_eval.p, ev.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e != cudaSuccess) { set_error("tbv_cost_samples: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  double sample_cost = 0.0;  // a failed GetCost (<= 1 residual) leaves the previous sample's cost in place (:283,304)
+  for (int i = 0; i < n_samples; i++) {
+    if (hr[i].num_residuals > 1) sample_cost = ev[(size_t)i * NACC];
+    samples[4 * i + 3] = sample_cost;
+  }
+  return TBV_OK;
+}
+
+// approximateCovarianceBySampling, fitting half (odometrykeyframefuser.cpp:315-378): least-squares quadric
+// f = a x^2 + b y^2 + c z^2 + d xy + e yz + f zx + g x + h y + i z + j through the samples (Householder QR here, Eigen bdcSvd there:
+// the same minimiser for a full-rank design), Hessian, convexity test on its eigenvalues, covariance = 2 H^-1 * score_scale * scaler
+// embedded in the reference's 6x6 layout (x, y, -, -, -, yaw).  *convex = 0 (and rc TBV_OK) when the fit is not convex or singular.
+int tbv_cov_from_cost_samples(const double* samples, int n_samples, double score_scale, double cov_scaler, double cov6x6[36], int* convex) {
+  TBV_REQUIRE(samples && cov6x6 && convex && n_samples >= 10, "bad arguments");
+  *convex = 0;
+  const int m = n_samples, nc = 10;
+  std::vector<double> A((size_t)m * nc), b(m);
+  for (int i = 0; i < m; i++) {
+    const double x = samples[4 * i], y = samples[4 * i + 1], z = samples[4 * i + 2];
+    double* r = &A[(size_t)i * nc];
+    r[0] = x * x; r[1] = y * y; r[2] = z * z; r[3] = x * y; r[4] = y * z; r[5] = z * x; r[6] = x; r[7] = y; r[8] = z; r[9] = 1.0;
+    b[i] = samples[4 * i + 3];
+  }
+  // columns differ by many orders of magnitude (yaw steps are ~1e-3 rad): scale them to unit norm before the factorisation
+  double cs[10];
+  for (int c = 0; c < nc; c++) {
+    double s2 = 0;
+    for (int i = 0; i < m; i++) s2 += A[(size_t)i * nc + c] * A[(size_t)i * nc + c];
+    cs[c] = s2 > 0 ? std::sqrt(s2) : 1.0;
+    for (int i = 0; i < m; i++) A[(size_t)i * nc + c] /= cs[c];
+  }
+  for (int c = 0; c < nc; c++) {  // Householder QR, applied to b on the fly
+    double norm = 0;
+    for (int i = c; i < m; i++) norm += A[(size_t)i * nc + c] * A[(size_t)i * nc + c];
+    norm = std::sqrt(norm);
+    if (norm < 1e-300) return TBV_OK;  // rank deficient sampling pattern
+    const double alpha = A[(size_t)c * nc + c] > 0 ? -norm : norm;
+    std::vector<double> v(m, 0.0);
+    for (int i = c; i < m; i++) v[i] = A[(size_t)i * nc + c];
+    v[c] -= alpha;
+    double vv = 0;
+    for (int i = c; i < m; i++) vv += v[i] * v[i];
+    if (vv < 1e-300) continue;
+    for (int k = c; k < nc; k++) {
+      double d = 0;
+      for (int i = c; i < m; i++) d += v[i] * A[(size_t)i * nc + k];
+      d = 2.0 * d / vv;
+      for (int i = c; i < m; i++) A[(size_t)i * nc + k] -= d * v[i];
+    }
+    double d = 0;
+    for (int i = c; i < m; i++) d += v[i] * b[i];
+    d = 2.0 * d / vv;
+    for (int i = c; i < m; i++) b[i] -= d * v[i];
+  }
+  double coef[10];
+  for (int c = nc - 1; c >= 0; c--) {
+    double s = b[c];
+    for (int k = c + 1; k < nc; k++) s -= A[(size_t)c * nc + k] * coef[k];
+    const double d = A[(size_t)c * nc + c];
+    if (std::fabs(d) < 1e-14) return TBV_OK;
+    coef[c] = s / d;
+  }
+  for (int c = 0; c < nc; c++) coef[c] /= cs[c];
+  double H[3][3] = {{2 * coef[0], coef[3], coef[5]}, {coef[3], 2 * coef[1], coef[4]}, {coef[5], coef[4], 2 * coef[2]}};
+  // eigenvalues of the symmetric 3x3 by cyclic Jacobi (SelfAdjointEigenSolver in the reference; only the signs are used).  The yaw
+  // axis is rescaled first so that the rotations see comparable entries; congruence scaling preserves the signs (Sylvester).
+  double Sx[3];
+  for (int i = 0; i < 3; i++) Sx[i] = std::fabs(H[i][i]) > 0 ? 1.0 / std::sqrt(std::fabs(H[i][i])) : 1.0;
+  double M[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) M[i][j] = H[i][j] * Sx[i] * Sx[j];
+  for (int sweep = 0; sweep < 50; sweep++) {
+    const double off = std::fabs(M[0][1]) + std::fabs(M[0][2]) + std::fabs(M[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++)
+      for (int qq = p + 1; qq < 3; qq++) {
+        if (M[p][qq] == 0.0) continue;
+        const double theta = (M[qq][qq] - M[p][p]) / (2.0 * M[p][qq]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; k++) { const double a = M[k][p], bq = M[k][qq]; M[k][p] = c * a - sn * bq; M[k][qq] = sn * a + c * bq; }
+        for (int k = 0; k < 3; k++) { const double a = M[p][k], bq = M[qq][k]; M[p][k] = c * a - sn * bq; M[qq][k] = sn * a + c * bq; }
+      }
+  }
+  if (!(M[0][0] > 0.0 && M[1][1] > 0.0 && M[2][2] > 0.0)) return TBV_OK;  // not convex (:352-356)
+  const double det = H[0][0] * (H[1][1] * H[2][2] - H[1][2] * H[2][1]) - H[0][1] * (H[1][0] * H[2][2] - H[1][2] * H[2][0]) +
+                     H[0][2] * (H[1][0] * H[2][1] - H[1][1] * H[2][0]);
+  if (det == 0.0 || !std::isfinite(det)) return TBV_OK;
+  double Hi[3][3];
+  Hi[0][0] = (H[1][1] * H[2][2] - H[1][2] * H[2][1]) / det; Hi[0][1] = (H[0][2] * H[2][1] - H[0][1] * H[2][2]) / det;
+  Hi[0][2] = (H[0][1] * H[1][2] - H[0][2] * H[1][1]) / det; Hi[1][0] = (H[1][2] * H[2][0] - H[1][0] * H[2][2]) / det;
+  Hi[1][1] = (H[0][0] * H[2][2] - H[0][2] * H[2][0]) / det; Hi[1][2] = (H[0][2] * H[1][0] - H[0][0] * H[1][2]) / det;
+  Hi[2][0] = (H[1][0] * H[2][1] - H[1][1] * H[2][0]) / det; Hi[2][1] = (H[0][1] * H[2][0] - H[0][0] * H[2][1]) / det;
+  Hi[2][2] = (H[0][0] * H[1][1] - H[0][1] * H[1][0]) / det;
+  double C3[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C3[i][j] = 2.0 * Hi[i][j] * score_scale * cov_scaler;
+  for (int i = 0; i < 36; i++) cov6x6[i] = (i % 7 == 0) ? 1.0 : 0.0;  // Identity, then the blocks of :368-375
+  cov6x6[0] = C3[0][0]; cov6x6[1] = C3[0][1]; cov6x6[6] = C3[1][0]; cov6x6[7] = C3[1][1];
+  cov6x6[35] = C3[2][2]; cov6x6[5] = C3[0][2]; cov6x6[11] = C3[1][2]; cov6x6[30] = C3[2][0]; cov6x6[31] = C3[2][1];
+  *convex = 1;
   return TBV_OK;
 }
 

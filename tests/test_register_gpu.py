@@ -112,3 +112,65 @@ def test_register_batch_loop_candidates(ctx, oracle, stream8, cellsets):
             assert np.abs(Ta_ref[:2] - Ta[p, :2]).max() < POS_TOL and _ang(Ta_ref[2], Ta[p, 2]) < ANG_TOL
             assert abs(score - summ[p].score) <= 1e-9 * abs(score)
     assert n_ok >= 20
+
+
+def _np_cov_from_samples(samples, score_scale, scaler):
+    """odometrykeyframefuser.cpp:315-378 restated with numpy (lstsq = minimum-norm least squares, like bdcSvd().solve())."""
+    x, y, z, c = samples.T
+    A = np.stack([x * x, y * y, z * z, x * y, y * z, z * x, x, y, z, np.ones_like(x)], axis=1)
+    # the columns span 12 orders of magnitude: condition the solve like the library does (column scaling leaves the minimiser unchanged)
+    s = np.linalg.norm(A, axis=0)
+    q = np.linalg.lstsq(A / s, c, rcond=None)[0] / s
+    H = np.array([[2 * q[0], q[3], q[5]], [q[3], 2 * q[1], q[4]], [q[5], q[4], 2 * q[2]]])
+    if not (np.linalg.eigvalsh(H) > 0).all():
+        return False, None
+    C3 = 2.0 * np.linalg.inv(H) * score_scale * scaler
+    cov = np.eye(6)
+    cov[:2, :2] = C3[:2, :2]
+    cov[5, 5] = C3[2, 2]
+    cov[0, 5], cov[1, 5], cov[5, 0], cov[5, 1] = C3[0, 2], C3[1, 2], C3[2, 0], C3[2, 1]
+    return True, cov
+
+
+@pytest.mark.parametrize("n_axis,cost", [(3, api.P2L), (5, api.P2L), (3, api.P2P)])
+def test_covariance_by_cost_sampling(ctx, oracle, cellsets, n_axis, cost):
+    """approximateCovarianceBySampling (odometrykeyframefuser.cpp:261-380): the n^3 GetCost samples come from ONE launch and must
+    equal the oracle's n^3 sequential GetCost calls; the fitted covariance must equal a numpy restatement of the fit."""
+    scans = [cellsets[0], cellsets[1], cellsets[2], cellsets[3]]
+    T = np.array([(0, 0, 0), (2.5, 0, 0), (5.0, 0.0, 0.0), (7.4, 0.03, 0.002)], float)
+    kw = dict(cost=cost, loss=api.HUBER, loss_limit=0.1, weight_opt=api.W_COMBINED)
+    # register first, as processFrame does; the sampling runs around the registered pose with the object's itr_ (> 1)
+    Treg, summary = ctx.Register(scans, T.copy(), api.default_reg_params(**kw))
+    ref = oracle.cost_samples(scans, Treg, oracle.default_reg_params(**kw), itr=2, n_per_axis=n_axis)
+    score_scale = summary.final_cost / (summary.num_residuals - 3)
+    ok, cov, got = ctx.approximateCovarianceBySampling(scans, Treg, score_scale, api.default_reg_params(**kw), itr=2, samples_per_axis=n_axis)
+    assert got.shape == ref.shape == (n_axis ** 3, 4)
+    assert np.array_equal(got[:, :3], ref[:, :3])                       # the sampling grid, in the reference's order
+    assert np.abs(got[:, 3] - ref[:, 3]).max() <= 1e-11 * np.abs(ref[:, 3]).max()
+    assert ref[:, 3].min() > 0 and np.ptp(ref[:, 3]) > 0
+    ok_np, cov_np = _np_cov_from_samples(ref, score_scale, 4.0)
+    assert ok == ok_np
+    if ok:
+        assert np.allclose(cov, cov_np, rtol=1e-6, atol=0)
+        assert np.allclose(cov, cov.T) and (np.linalg.eigvalsh(cov[np.ix_([0, 1, 5], [0, 1, 5])]) > 0).all()
+
+
+def test_cov_from_cost_samples_recovers_a_known_quadric(ctx):
+    """Samples of f = 1/2 d^T H d + g^T d + c on the 3x3x3 grid give back 2 H^-1 * scale exactly; a saddle is reported not convex."""
+    import ctypes as C
+    H = np.array([[40.0, 3.0, 200.0], [3.0, 25.0, -150.0], [200.0, -150.0, 9.0e5]])
+    g = np.array([0.3, -0.2, 5.0])
+    xy = np.linspace(-0.2, 0.2, 3)
+    th = np.linspace(-0.00218125, 0.00218125, 3)
+    S = np.array([(x, y, t, 0.0) for t in th for x in xy for y in xy])
+    d = S[:, :3]
+    S[:, 3] = 0.5 * np.einsum("ni,ij,nj->n", d, H, d) + d @ g + 7.0
+    cov = np.zeros((6, 6)); ok = C.c_int(0)
+    L = api.lib()
+    assert L.tbv_cov_from_cost_samples(S.ctypes.data_as(C.c_void_p), len(S), C.c_double(0.5), C.c_double(4.0), cov.ctypes.data_as(C.c_void_p), C.byref(ok)) == 0
+    assert ok.value == 1
+    want = 2.0 * np.linalg.inv(H) * 0.5 * 4.0
+    assert np.allclose(cov[np.ix_([0, 1, 5], [0, 1, 5])], want, rtol=1e-7)
+    S[:, 3] = 0.5 * np.einsum("ni,ij,nj->n", d, np.diag([40.0, -25.0, 9e5]), d)
+    assert L.tbv_cov_from_cost_samples(S.ctypes.data_as(C.c_void_p), len(S), C.c_double(0.5), C.c_double(4.0), cov.ctypes.data_as(C.c_void_p), C.byref(ok)) == 0
+    assert ok.value == 0
