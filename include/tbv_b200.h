@@ -270,6 +270,28 @@ int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const dou
 int tbv_sc_search(tbv_ctx* ctx, const float* db_keys, const double* odom_xyt, int n_db, int n_q, const float* q_keys, const int* q_current,
                   const tbv_sc_params* params, int* cand_idx, double* cand_odom_sim, int* n_exclude);
 
+/* ---- CorAl alignment quality (next-row f-1): CorAlRadarQuality ------------------------------------------------------------
+ * coral_alignment_quality/src/alignment_checker/AlignmentQuality.cpp:8-229 as called by ScanLearningInterface::getCorAlQualityMeasure
+ * (coral_alignment_quality/src/alignment_checker/alignmentinterface.cpp:437-454: peaks clouds, radius 1.0, entropy setting `any`,
+ * weight_res_intensity false).  Batched over pairs, one CTA per pair: clouds are given once (local frames) and indexed by the pairs;
+ * pair p compares cloud src_cloud[p] at pose T_src[p] * T_offset[p] with cloud ref_cloud[p] at pose T_ref[p] (poses: x, y, theta;
+ * T_offset may be NULL = identity).  results[p] = quality_ {joint, sep, overlap} + counts; valid = (overlap >= 0.1).
+ * per_point (optional): sum over pairs of merged_size rows of 3 doubles = sep, joint, valid of every point (src points first), the
+ * reference's sep_res_ / joint_res_ / sep_valid before the weighting loop.  Clouds are limited to 4096 points (TBV_ERR_CAPACITY). */
+typedef struct tbv_coral_params {
+  double radius;             /* AlignmentQuality::parameters::radius (TBV: 1.0) */
+  int weight_res_intensity;  /* weights = point intensity instead of 1 */
+  int overlap_req;           /* AlignmentQuality.h:244 overlap_req_ = 1 */
+} tbv_coral_params;
+typedef struct tbv_coral_result {
+  double joint, sep, overlap;
+  int count_valid, merged_size, valid;
+} tbv_coral_result;
+int tbv_coral_quality_batch(tbv_ctx* ctx, int n_clouds, const float* const* x, const float* const* y, const float* const* intensity,
+                            const int* n_points, int n_pairs, const int* src_cloud, const int* ref_cloud, const double* T_src,
+                            const double* T_offset, const double* T_ref, const tbv_coral_params* params, tbv_coral_result* results,
+                            double* per_point);
+
 /* ---- K8: pose-graph normal equations ------------------------------------------------------------------------------------
  * CeresLeastSquares::BuildOptimizationProblem / AddConstraintType + PoseGraph3dErrorTerm (tbv_slam/src/tbv_slam/ceresoptimizer.cpp:
  * 28-108, tbv_slam/include/tbv_slam/ceresoptimizer.h:51-95) followed by one evaluation: robustified residuals, tangent-space

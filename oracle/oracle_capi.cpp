@@ -10,6 +10,7 @@
 #include <thread>
 
 #include "tbv_oracle_loop.hpp"
+#include "tbv_oracle_coral.hpp"
 #include "tbv_oracle_reg.hpp"
 
 using namespace tbv_oracle;

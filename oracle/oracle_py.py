@@ -23,7 +23,7 @@ VOXEL_ORDER_STABLE, VOXEL_ORDER_STD_SORT = 0, 1
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "tbv_oracle.hpp", "tbv_oracle_reg.hpp", "tbv_oracle_loop.hpp",
-                                             "oracle_capi_loop.inc")]
+                                             "oracle_capi_loop.inc", "tbv_oracle_coral.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
     return so
@@ -400,6 +400,23 @@ class RSC:
 
 
 # ---- pose graph ----------------------------------------------------------------------------------------------
+def coral_quality(src, ref, Tsrc, Tref, Toffset=(0.0, 0.0, 0.0), radius=1.0, weight_res_intensity=False, per_point=False):
+    """CorAlRadarQuality (AlignmentQuality.cpp:99-229): src / ref = (x, y, intensity) float32 peaks clouds in their own frames.
+    Returns dict(joint, sep, overlap, count_valid, merged_size, valid[, per_point [n, 3] = sep, joint, valid])."""
+    sx, sy, si = (np.ascontiguousarray(a, np.float32) for a in src)
+    rx, ry, ri = (np.ascontiguousarray(a, np.float32) for a in ref)
+    out = np.zeros(6)
+    pp = np.zeros((len(sx) + len(rx), 3)) if per_point else None
+    a3 = lambda t: np.ascontiguousarray(t, np.float64)
+    lib().orc_coral_quality(_p(sx, C.c_float), _p(sy, C.c_float), _p(si, C.c_float), len(sx), _p(rx, C.c_float), _p(ry, C.c_float),
+                            _p(ri, C.c_float), len(rx), _p(a3(Tsrc), C.c_double), _p(a3(Toffset), C.c_double), _p(a3(Tref), C.c_double),
+                            C.c_double(radius), int(weight_res_intensity), _p(out, C.c_double), _p(pp, C.c_double))
+    r = dict(joint=out[0], sep=out[1], overlap=out[2], count_valid=int(out[3]), merged_size=int(out[4]), valid=bool(out[5]))
+    if per_point:
+        r["per_point"] = pp
+    return r
+
+
 def pgo_assemble(nodes, ids, meas, params: PGOParams | None = None, info=None, fixed_node=0):
     params = params or default_pgo_params()
     nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, 7)

@@ -654,3 +654,34 @@ class RSCManager:
             if len(similar) > self.par.n_candidates:
                 similar.pop()
         return similar
+
+
+class CoralParams(C.Structure):
+    _fields_ = [("radius", C.c_double), ("weight_res_intensity", C.c_int), ("overlap_req", C.c_int)]
+
+
+class CoralResult(C.Structure):
+    _fields_ = [("joint", C.c_double), ("sep", C.c_double), ("overlap", C.c_double), ("count_valid", C.c_int), ("merged_size", C.c_int),
+                ("valid", C.c_int)]
+
+
+def CorAlRadarQuality(ctx: Context, clouds, src_cloud, ref_cloud, T_src, T_ref, T_offset=None, radius=1.0, weight_res_intensity=False,
+                      per_point=False):
+    """CorAlRadarQuality for a batch of pairs (AlignmentQuality.cpp:99-229 via alignmentinterface.cpp:437-454).
+    clouds: list of (x, y, intensity) float32 arrays in the scans' own frames; pair p = (src_cloud[p] at T_src[p] * T_offset[p],
+    ref_cloud[p] at T_ref[p]).  Returns a list of CoralResult (and the per-point [sum merged_size, 3] array if asked)."""
+    arrs = [[np.ascontiguousarray(a, np.float32) for a in c] for c in clouds]
+    n_pts = np.array([len(c[0]) for c in arrs], np.int32)
+    ptr = lambda k: (C.c_void_p * len(arrs))(*[c[k].ctypes.data_as(C.c_void_p).value for c in arrs])
+    sc = np.ascontiguousarray(src_cloud, np.int32)
+    rc_ = np.ascontiguousarray(ref_cloud, np.int32)
+    n = len(sc)
+    Ts = np.ascontiguousarray(T_src, np.float64).reshape(n, 3)
+    Tr = np.ascontiguousarray(T_ref, np.float64).reshape(n, 3)
+    To = np.ascontiguousarray(T_offset, np.float64).reshape(n, 3) if T_offset is not None else None
+    res = (CoralResult * n)()
+    par = CoralParams(radius, int(weight_res_intensity), 1)
+    pp = np.zeros((int(sum(n_pts[s] + n_pts[r] for s, r in zip(sc, rc_))), 3)) if per_point else None
+    _check(lib().tbv_coral_quality_batch(ctx.h, len(arrs), ptr(0), ptr(1), ptr(2), _ptr(n_pts), n, _ptr(sc), _ptr(rc_), _ptr(Ts), _ptr(To), _ptr(Tr),
+                                         C.byref(par), res, _ptr(pp)))
+    return (list(res), pp) if per_point else list(res)

@@ -416,6 +416,67 @@ def test_pgo_consistent_graph_has_zero_cost(oracle):
 # ---------------------------------------------------------------------------------------------------------------
 # the C-ABI surface (no compute without a GPU)
 # ---------------------------------------------------------------------------------------------------------------
+def test_coral_quality_vs_numpy(oracle):
+    """CorAlRadarQuality restatement (AlignmentQuality.cpp:8-229) vs an independent numpy one: brute-force float radius test,
+    np.cov (ddof = 1) of the own / merged neighbourhoods, 1/2 log(2 pi e det + 1e-8), means over the valid points."""
+    st = synth.make_stream(2)
+    cl = []
+    for i in range(2):
+        az, rg, I, x, y = oracle.kstrongest(st.scans[i], z_min=70.0, k=12)["filtered"]
+        cl.append((x[::2], y[::2], I[::2].astype(np.float32)))
+    Toff = (0.3, -0.2, 0.01)
+    ref = oracle.coral_quality(cl[1], cl[0], st.gt[1], st.gt[0], Toffset=Toff, per_point=True)
+
+    def aff(v):
+        c, s = math.cos(v[2]), math.sin(v[2])
+        return np.array([[c, -s, v[0]], [s, c, v[1]], [0, 0, 1]])
+
+    def move(c, T):
+        xy = np.stack([c[0].astype(np.float64), c[1].astype(np.float64), np.ones(len(c[0]))])
+        out = T @ xy
+        return out[0].astype(np.float32), out[1].astype(np.float32)
+    sx, sy = move(cl[1], aff(st.gt[1]) @ aff(Toff))
+    rx, ry = move(cl[0], aff(st.gt[0]))
+    P = [np.stack([sx, sy], 1), np.stack([rx, ry], 1)]
+    r2 = np.float32(1.0)
+    sep, joint, valid = [], [], []
+    for c in (0, 1):
+        for q in P[c]:
+            nb = []
+            for d in (0, 1):
+                dd = (q[0] - P[d][:, 0]) ** 2 + (q[1] - P[d][:, 1]) ** 2    # float32 arithmetic
+                nb.append(P[d][dd < r2].astype(np.float64))
+            own, oth = nb[c], nb[1 - c]
+            ok = len(oth) >= 1 and len(own) > 2
+            if ok:
+                ds = np.linalg.det(np.cov(own.T, ddof=1))
+                dj = np.linalg.det(np.cov(np.concatenate([nb[0], nb[1]]).T, ddof=1))
+                se, je = 0.5 * np.log(2 * np.pi * np.e * ds + 1e-8), 0.5 * np.log(2 * np.pi * np.e * dj + 1e-8)
+                ok = np.isfinite(se) and np.isfinite(je)
+            sep.append(se if ok else 100.0); joint.append(je if ok else 100.0); valid.append(ok)
+    valid = np.array(valid)
+    assert np.array_equal(valid, ref["per_point"][:, 2] == 1) and valid.sum() > 200
+    assert np.abs(np.array(sep) - ref["per_point"][:, 0]).max() < 1e-6 and np.abs(np.array(joint) - ref["per_point"][:, 1]).max() < 1e-6
+    assert abs(np.mean(np.array(joint)[valid]) - ref["joint"]) < 1e-8 and abs(np.mean(np.array(sep)[valid]) - ref["sep"]) < 1e-8
+    assert ref["overlap"] == valid.sum() / len(valid) and ref["valid"] == (ref["overlap"] >= 0.1)
+    # identical clouds at identical poses: every joint neighbourhood is the own one twice -> same mean, (2n-2)/(2n-1) of the covariance
+    same = oracle.coral_quality(cl[0], cl[0], (0, 0, 0), (0, 0, 0))
+    assert same["joint"] < same["sep"]
+
+
+def test_cost_samples_grid_and_centre(oracle, two_sets):
+    """approximateCovarianceBySampling's sampling half: theta-major / x / y order, linspace end points exact, centre sample = GetCost."""
+    _, sets = two_sets
+    T = np.array([(0, 0, 0), (2.5, 0.0, 0.0), (5.0, 0.02, 0.001)])
+    S = oracle.cost_samples(sets, T, itr=2, xy_range=0.4, yaw_range=0.0043625, n_per_axis=3)
+    assert S.shape == (27, 4)
+    assert np.array_equal(S[:, 2], np.repeat([-0.00218125, 0.0, 0.00218125], 9))
+    assert np.array_equal(S[:9, 0], np.repeat([-0.2, 0.0, 0.2], 3)) and np.array_equal(S[:3, 1], [-0.2, 0.0, 0.2])
+    n, score, cost, res = oracle.get_cost(sets, T, itr=2)
+    assert abs(S[13, 3] - cost) <= 1e-12 * cost            # the (0, 0, 0) sample; the yaw goes through atan2(sin, cos)
+    assert S[:, 3].min() > 0 and np.ptp(S[:, 3]) > 0
+
+
 def test_cabi_exports_every_declared_symbol():
     from tbv_slam_public_b200 import build as b
     lib = b.build()
