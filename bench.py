@@ -142,15 +142,33 @@ def run_ours(args):
     fuser = api.OdometryKeyframeFuser(ctx, S, N_AZ, N_RANGE, par)
     stream = torch.cuda.ExternalStream(ctx.stream)
 
-    # host side: every step's scans in pinned memory (what a sensor-facing producer would hand over)
+    # host side: the scans of the steps the e2e leg replays, in pinned memory (what a sensor-facing producer would hand over).
+    # All ranks of the node pin memory at once: keep the node total under 40 % of what is available (T_pin steps per rank, the
+    # e2e leg then times T_pin - W steps; on the single-GPU box that is every step).
     step_bytes = S * SCAN_BYTES
-    pinned = api.PinnedBuffer(T * step_bytes)
-    host = pinned.array.reshape(T, S, N_AZ, N_RANGE)
-    for t in range(T):
-        np.take(pool, first + t, axis=0, out=host[t])
-    # device side: the same bytes resident in HBM (each step reads S x 1.5 MB, far larger than the 126 MB L2)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    T_pin = int(max(W + 3, min(T, 0.4 * avail / local_world // step_bytes)))
+    T_pin = min(T_pin, T)
+    if world > 1:  # the same number of e2e steps on every rank
+        tp = torch.tensor([T_pin], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tp, op=dist.ReduceOp.MIN)
+        T_pin = int(tp[0])
+    pinned = api.PinnedBuffer(T_pin * step_bytes)
+    host = pinned.array.reshape(T_pin, S, N_AZ, N_RANGE)
+    # device side: every step's scans resident in HBM (each step reads S x 1.5 MB, far larger than the 126 MB L2)
     dev = torch.empty((T, step_bytes), dtype=torch.uint8, device="cuda")
-    dev.copy_(torch.from_numpy(pinned.array.reshape(T, step_bytes)), non_blocking=False)
+    for t in range(T):   # stage through the pinned ring
+        slot = t % T_pin
+        np.take(pool, first + t, axis=0, out=host[slot])
+        dev[t].copy_(torch.from_numpy(pinned.array.reshape(T_pin, step_bytes)[slot]), non_blocking=False)
+    for t in range(T_pin):  # the pinned buffer ends up holding steps 0 .. T_pin-1
+        if T_pin < T:
+            np.take(pool, first + t, axis=0, out=host[t])
     torch.cuda.synchronize()
 
     def barrier():
@@ -207,8 +225,9 @@ def run_ours(args):
         fuser.pointcloudCallback(host[t])
     ctx.synchronize(); torch.cuda.synchronize()
     barrier()
+    K_e2e = T_pin - W
     t0 = time.perf_counter()
-    for t in range(W, T):
+    for t in range(W, T_pin):
         fuser.submit(pinned.ptr + t * step_bytes)
         if t > W:
             fuser.collect()
@@ -218,7 +237,14 @@ def run_ours(args):
     barrier()
     e2e_s = t1 - t0
     final_e2e = api.poses(outs_e2e).copy()
-    if not np.array_equal(final_dev, final_e2e):
+    if T_pin == T:
+        same = np.array_equal(final_dev, final_e2e)
+    else:  # fewer e2e steps than device-resident ones: replay those steps from HBM and compare
+        fuser.reset()
+        for t in range(T_pin):
+            fuser.step_dev(dev[t].data_ptr())
+        same = np.array_equal(api.poses(fuser.fetch()), final_e2e)
+    if not same:
         raise RuntimeError("device-resident and host-buffer runs disagree")
 
     # ---------------- max over ranks ---------------------------------------------------------------------------
@@ -228,7 +254,7 @@ def run_ours(args):
         ms_total, e2e_s = float(tt[0]), float(tt[1])
     total_scans = S * K * world
     value = total_scans / (ms_total * 1e-3)
-    e2e_value = total_scans / e2e_s
+    e2e_value = S * K_e2e * world / e2e_s
 
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
@@ -288,7 +314,7 @@ def run_ours(args):
                    "weights": "combined", "sharding": f"sequences over {world} GPU(s), no collective",
                    "l2": "each step reads sequences_per_gpu x 1.5 MB of scans (>> 126 MB L2); no flush needed"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": S * 80,
-                "ms_per_step": round(e2e_s / K * 1e3, 4), "api": "tbv_odom_submit/tbv_odom_collect (pinned host scans, double-buffered)"},
+                "ms_per_step": round(e2e_s / K_e2e * 1e3, 4), "steps": K_e2e, "api": "tbv_odom_submit/tbv_odom_collect (pinned host scans, double-buffered)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline, "parity_check": parity, "workload_stats": {k: round(v, 3) if isinstance(v, float) else v for k, v in stats.items()},
     }

@@ -99,6 +99,7 @@ __device__ __forceinline__ void stage_row_sync(uint8_t* buf, const uint8_t* rp, 
   __syncwarp();
 }
 
+template <bool HI>   // HI: z_min > 128 (selects the form of the byte compare at compile time: the scan loop carries no branch on it)
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n_range, size_t row_stride, int z_min, int k,
               int want_peaks, int rowbuf, const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, uint32_t* __restrict__ row_keys,
@@ -110,7 +111,7 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
   __shared__ int s_n[K1_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
-  const bool hi = z_min > 128;
+  constexpr bool hi = HI;
   const uint32_t z = (uint32_t)z_min;
   const bool zero_thr = z == 0;   // every byte is a candidate: padding bytes must be masked explicitly
   const uint32_t addc = (hi ? (256u - z) : (128u - z)) * 0x01010101u;
@@ -122,6 +123,10 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
   uint64_t* bars = s_bar[warp];
   const int row_step = gridDim.x * K1_WARPS;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  // Both row buffers start out zero: the scan loop below always runs over whole groups of 32 vectors (rowbuf is a multiple of 512
+  // bytes), and the bytes past a row's staged superset are never written by a bulk copy, so they stay below every threshold >= 1.
+  for (int o = lane * 16; o < 2 * rowbuf; o += 32 * 16) *reinterpret_cast<uint4*>(mybuf + o) = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   __syncwarp();
 
@@ -156,7 +161,9 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
     if (!zero_thr) {
       const int head = a0, tail = (((a0 + n_range + 15) >> 4) << 4) - (a0 + n_range);
       if (lane < head) buf[lane] = 0;
-      if (lane < tail) buf[a0 + n_range + lane] = 0;
+      // the superset ends up to 15 bytes after the row; a previous row of this buffer with another alignment may have ended one
+      // vector later: clear through the end of that vector as well
+      if (lane < tail + 16 && a0 + n_range + lane < rowbuf) buf[a0 + n_range + lane] = 0;
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before the next bulk copy into this buffer
       __syncwarp();
     }
@@ -198,10 +205,10 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
     int nq = 0;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 2
-    for (int base = 0; base < nvec; base += 32) {
+    const int nvec32 = zero_thr ? nvec : ((nvec + 31) & ~31);  // whole groups of 32 vectors: the padding is zero (z_min = 0 keeps the exact count)
+    for (int base = 0; base < nvec32; base += 32) {
       const int t = base + lane;
-      bool f = false;
-      if (t < nvec) f = any_ge(vbuf[t]);
+      const bool f = (zero_thr && t >= nvec) ? false : any_ge(vbuf[t]);
       const unsigned ball = __ballot_sync(FULL, f);
       const int q = nq + __popc(ball & lt);
       if (f && q <= K1_CAP) queue[q] = (uint16_t)t;
@@ -582,7 +589,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int blocks_needed = (total_rows + K1_WARPS - 1) / K1_WARPS;
-  const int rowbuf = ((n_range + 16 + 15 + 127) / 128) * 128;  // row + alignment slack, multiple of 128
+  const int rowbuf = ((n_range + 16 + 15 + 511) / 512) * 512;  // row + alignment slack, whole groups of 32 16-byte vectors
   const size_t k1_smem = (size_t)K1_WARPS * 2 * rowbuf;
   // resident CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA, ~8.3 KB static (lists, barriers)
   int ctas_per_sm = (int)((228 * 1024) / (k1_smem + 8500 + 1024));
@@ -591,14 +598,19 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   const int grid = blocks_needed < max_grid ? blocks_needed : max_grid;  // persistent: resident CTAs only, rows strided over warps
   static bool attr_set = false;
   if (!attr_set) {
-    TBV_CUDA(cudaFuncSetAttribute(k1_kstrongest, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    TBV_CUDA(cudaFuncSetAttribute(k1_kstrongest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    TBV_CUDA(cudaFuncSetAttribute(k1_kstrongest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr_set = true;
   }
   const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
   const int min_range_bin = (int)std::ceil((double)p->min_distance / rr);   // radar_filters.cpp:315
-  k1_kstrongest<<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
-                                                             polar_dev, buf_hi, min_range_bin, F.row_keys.p, F.row_cnt.p);
+  if (z_min > 128)
+    k1_kstrongest<true><<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
+                                                                     polar_dev, buf_hi, min_range_bin, F.row_keys.p, F.row_cnt.p);
+  else
+    k1_kstrongest<false><<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
+                                                                      polar_dev, buf_hi, min_range_bin, F.row_keys.p, F.row_cnt.p);
   launched(ctx, "k1_kstrongest");
   TBV_CUDA(cudaGetLastError());
   const size_t smem = 2 * (size_t)(n_az + 1) * sizeof(int) + (size_t)K2_STAGE * (sizeof(uint32_t) + sizeof(int) + sizeof(uint16_t));
