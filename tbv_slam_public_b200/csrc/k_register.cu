@@ -546,6 +546,30 @@ __device__ __forceinline__ int nn_search(const SetView& t, const CellGrid& g, in
   return (best >= 0 && (double)bestd < R * R) ? best : -1;
 }
 
+// The same search over a copy of the set's grid entries in SHARED memory.  The entries are in bucket order (row-major), so the bucket
+// rows the square [q - R, q + R] touches form ONE contiguous run [row[by0], row[by1 + 1]) — row[r] = first entry of bucket row r.
+// Every entry of the run is tested (a row holds ~5 cells; no per-bucket table is needed): a superset of the buckets nn_search
+// visits, the same accepted neighbour (the closest entry overall, ties to the smaller cell index, kept iff d2 < R*R).
+__device__ __forceinline__ int nn_search_staged(const float4* __restrict__ ent, const uint16_t* __restrict__ row, const CellGrid& g, float qx, float qy,
+                                                double R) {
+  const float Rm = (float)R + 1e-3f;
+  const float ly = floorf((qy - Rm - g.miny) / GRID_CELL), hy = floorf((qy + Rm - g.miny) / GRID_CELL);
+  if (!(hy >= 0.f) || !(ly <= (float)(g.ny - 1))) return -1;  // the square lies outside the grid rows (or q is NaN)
+  const int by0 = ly > 0.f ? (int)ly : 0, by1 = hy < (float)(g.ny - 1) ? (int)hy : g.ny - 1;
+  float bestd = FLT_MAX;
+  int best = -1;
+  const int j1 = row[by1 + 1];
+  for (int j = row[by0]; j < j1; j++) {
+    const float4 e = ent[j];
+    const int i = __float_as_int(e.z);
+    const float dx = qx - e.x, dy = qy - e.y;
+    float dd = dx * dx;   // FLANN L2_Simple, no contraction (-fmad=false)
+    dd = dd + dy * dy;
+    if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
+  }
+  return (best >= 0 && (double)bestd < R * R) ? best : -1;
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 constexpr int RG_MAX_FIXED = 16;
 
@@ -596,6 +620,7 @@ struct RegShared {
   SetView tgt[RG_MAX_FIXED];
   CellGrid grid[RG_MAX_FIXED];   // search-grid headers of the fixed sets
   int n_tgt[RG_MAX_FIXED];
+  int staged, ent_off[RG_MAX_FIXED], row_off[RG_MAX_FIXED];   // byte offsets into the dynamic shared memory (staged working set)
   LMState lm;
   OuterState outer;
 };
@@ -664,8 +689,9 @@ __global__ void __launch_bounds__(RG_THREADS, MIN_CTAS)
 k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
            const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
            double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
-           double* __restrict__ residuals_all, double* __restrict__ wgt_all, unsigned long long* __restrict__ dbg) {
+           double* __restrict__ residuals_all, double* __restrict__ wgt_all, unsigned long long* __restrict__ dbg, int stage_bytes) {
   __shared__ RegShared sh;
+  extern __shared__ __align__(16) uint8_t rg_stage[];
   long long t_assoc = 0, t_eval = 0, t_lm = 0, t_mark = 0;
   const long long t_start = dbg ? clock64() : 0;
   const int p = blockIdx.x;
@@ -724,6 +750,35 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     }
   }
 
+  // Stage what the nearest-neighbour search reads into shared memory when it fits (it does for the odometry and loop workloads:
+  // ~37 KB for 450-cell sets and four keyframes): the moving set's means and, per fixed set, its grid entries + one start offset
+  // per bucket row.  The search then runs out of shared memory and the association pays ONE global round trip per slot (the
+  // matched target's normal / N / planarity) instead of one per link of query -> bucket rows -> entries -> target fields.
+  if (tid == 0) {
+    int need = n_src * 16, ok = 1;
+    for (int f = 0; f < n_fixed; f++) {
+      if (!(sh.tgt[f].grid && sh.grid[f].ok)) { ok = 0; break; }
+      sh.ent_off[f] = need; need += sh.n_tgt[f] * 16;
+      sh.row_off[f] = need; need += ((sh.grid[f].ny + 2) * 2 + 15) & ~15;
+    }
+    sh.staged = (ok && need <= stage_bytes) ? 1 : 0;
+  }
+  __syncthreads();
+  const bool staged = sh.staged != 0;
+  const double2* s_u = reinterpret_cast<const double2*>(rg_stage);
+  if (staged) {
+    double2* su = reinterpret_cast<double2*>(rg_stage);
+    for (int j = tid; j < n_src; j += RG_THREADS) su[j] = make_double2(src.f[(size_t)CF_U0 * src.cap + j], src.f[(size_t)CF_U1 * src.cap + j]);
+    for (int f = 0; f < n_fixed; f++) {
+      float4* e = reinterpret_cast<float4*>(rg_stage + sh.ent_off[f]);
+      uint16_t* r = reinterpret_cast<uint16_t*>(rg_stage + sh.row_off[f]);
+      const int nt = sh.n_tgt[f], ny = sh.grid[f].ny, nx = sh.grid[f].nx;
+      for (int j = tid; j < nt; j += RG_THREADS) e[j] = sh.tgt[f].gent[j];
+      for (int k = tid; k <= ny; k += RG_THREADS) r[k] = k < ny ? sh.tgt[f].gstart[k * nx] : (uint16_t)nt;
+    }
+  }
+  __syncthreads();
+
   // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan).  Slot = (fixed scan, source
   // cell), fixed-major: the order the reference adds its residual blocks in.  Every warp owns a contiguous slot range:
   // pass 1 searches and counts, one barrier publishes the per-warp counts, pass 2 writes the accepted correspondences of
@@ -750,12 +805,16 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
         const SetView& tgt = sh.tgt[fi];
         // every source-side value is fetched before the search, every target-side value right after it: two round trips
         // instead of one per dependent use
-        const double ux = src.f[(size_t)CF_U0 * src.cap + j], uy = src.f[(size_t)CF_U1 * src.cap + j];
-        const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
+        double ux, uy;
+        if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
+        else { ux = src.f[(size_t)CF_U0 * src.cap + j]; uy = src.f[(size_t)CF_U1 * src.cap + j]; }
         const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
         const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
-        int ti = nn_search(tgt, sh.grid[fi], sh.n_tgt[fi], (float)qxd, (float)qyd, R);
+        int ti = staged ? nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]),
+                                           reinterpret_cast<const uint16_t*>(rg_stage + sh.row_off[fi]), sh.grid[fi], (float)qxd, (float)qyd, R)
+                        : nn_search(tgt, sh.grid[fi], sh.n_tgt[fi], (float)qxd, (float)qyd, R);
         if (ti >= 0) {
+          const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
           const bool weighted = P.weight_opt != TBV_W_UNIFORM;
           const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
           const double N2 = weighted ? tgt.f[(size_t)CF_NS * tgt.cap + ti] : 0.0, p2 = weighted ? tgt.f[(size_t)CF_SCALE * tgt.cap + ti] : 0.0;
@@ -1076,14 +1135,23 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   static const bool want_dbg = getenv("TBV_REG_DBG") != nullptr;
   if (want_dbg && !dbg) TBV_CUDA(cudaMalloc((void**)&dbg, 8 * sizeof(unsigned long long)));
   if (want_dbg) TBV_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  // dynamic shared memory for the staged working set: 4 CTAs x (48 KB + 4.2 KB static + 1 KB reserved) fit one SM's 228 KB
+  constexpr int RG_STAGE = 48 * 1024;
+  static bool stage_attr = false;
+  if (!stage_attr) {
+    TBV_CUDA(cudaFuncSetAttribute(k_register<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_STAGE));
+    TBV_CUDA(cudaFuncSetAttribute(k_register<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_STAGE));
+    stage_attr = true;
+  }
+  static const int stage_bytes = getenv("TBV_REG_NOSTAGE") ? 0 : RG_STAGE;
   if (min_ctas == 3)
-    k_register<3><<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
+    k_register<3><<<n_problems, RG_THREADS, stage_bytes, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg);
+                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg, stage_bytes);
   else
-    k_register<4><<<n_problems, RG_THREADS, 0, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
+    k_register<4><<<n_problems, RG_THREADS, stage_bytes, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg);
+                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg, stage_bytes);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
   if (want_dbg) {  // debug only: mean cycles per problem spent in association / evaluation / LM + barrier
