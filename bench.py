@@ -318,7 +318,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline, "parity_check": parity, "workload_stats": {k: round(v, 3) if isinstance(v, float) else v for k, v in stats.items()},
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -355,7 +355,7 @@ def run_reference(args):
                          "threads": 1, "note": "reference = unmodified radar_filters.cpp (constructor + both clouds) from oracle/_ref"}
     except Exception as e:  # the timing of one stage must never take the arm down
         filtering = {"error": str(e)[:200]}
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": round(sec / K * 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 scan bytes -> f32 points -> f64 cells / normal equations / LM", "data": "synthetic",
@@ -369,10 +369,25 @@ def run_reference(args):
     }))
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """The bench prints exactly ONE line on stdout.  Libraries write there too (NCCL's version banner, for one), so the process's
+    fd 1 is pointed at stderr for the whole run and the result line goes to the saved original stdout."""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line + "\n"); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 if __name__ == "__main__":
-    # the bench prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
