@@ -48,14 +48,21 @@ def parse_args():
     return ap.parse_args()
 
 
+N_PLACES = 8  # distinct stretches of the figure-8 the sequences start from
+
+
 def make_pool(n_frames: int, rank: int):
+    """[N_PLACES * n_frames] scans: N_PLACES stretches of the synthetic world, n_frames consecutive frames each.  Every rank renders
+    the same stretches; what differs per rank is which sequence drives which stretch (first_offsets), so every GPU gets the same mix
+    of scene densities — weak scaling measures the machine, not the luck of one rank's neighbourhood."""
     from tbv_slam_public_b200 import synth
-    # every rank drives the same world from a different place on the figure-8 (different bytes per rank)
-    return synth.make_stream(n_frames, s0=137.0 * rank).scans
+    return np.concatenate([synth.make_stream(n_frames, s0=137.0 * p).scans for p in range(N_PLACES)])
 
 
-def first_offsets(n_seq: int):
-    return ((np.arange(n_seq) * 5) % POOL_EXTRA).astype(np.int32)
+def first_offsets(n_seq: int, n_frames: int, rank: int = 0):
+    """Index of every sequence's first scan in the pool: stretch (j + rank) mod N_PLACES, starting frame (5 j) mod POOL_EXTRA."""
+    j = np.arange(n_seq)
+    return (((j + rank) % N_PLACES) * n_frames + (j * 5) % POOL_EXTRA).astype(np.int32)
 
 
 class ClockSampler:
@@ -135,7 +142,7 @@ def run_ours(args):
     W, K, S = args.warmup, args.steps, args.seqs
     T = W + K
     pool = make_pool(T + POOL_EXTRA, rank)
-    first = first_offsets(S)
+    first = first_offsets(S, T + POOL_EXTRA, rank)
 
     ctx = api.Context(local)
     par = api.default_odom_params()
@@ -311,7 +318,7 @@ def run_ours(args):
         "dtype": "u8 scan bytes -> f32 points -> f64 cells / normal equations / LM", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sequences_per_gpu": S, "scans_per_step": S * world, "n_az": N_AZ, "n_range": N_RANGE,
                    "k_strongest": K_STRONGEST, "z_min": 60, "cell_radius_m": 3.0, "keyframes": 4, "cost": "P2L", "loss": "Huber(0.1)",
-                   "weights": "combined", "sharding": f"sequences over {world} GPU(s), no collective",
+                   "weights": "combined", "sharding": f"sequences over {world} GPU(s), no collective", "places": N_PLACES,
                    "l2": "each step reads sequences_per_gpu x 1.5 MB of scans (>> 126 MB L2); no flush needed"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": S * 80,
                 "ms_per_step": round(e2e_s / K_e2e * 1e3, 4), "steps": K_e2e, "api": "tbv_odom_submit/tbv_odom_collect (pinned host scans, double-buffered)"},
@@ -336,7 +343,7 @@ def run_reference(args):
     n_seq = threads * max(1, int(round(20.0 / (0.0035 * T))))  # ~20 s of work per thread
     n_seq = min(n_seq, threads * 64)
     pool = make_pool(T + POOL_EXTRA, 0)
-    first = first_offsets(n_seq)
+    first = first_offsets(n_seq, T + POOL_EXTRA, 0)
     sec, _ = oracle_py.odom_run_timed(oracle_py.default_odom_params(), pool, first, W, T, threads)
     value = n_seq * K / sec
     # Filtering stage alone, one thread: the reference's OWN radar_filters.cpp (oracle/_ref, built from /root/reference where that
