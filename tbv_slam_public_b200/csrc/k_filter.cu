@@ -205,10 +205,13 @@ k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n
     int nq = 0;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 2
-    const int nvec32 = zero_thr ? nvec : ((nvec + 31) & ~31);  // whole groups of 32 vectors: the padding is zero (z_min = 0 keeps the exact count)
+    // whole groups of 32 vectors: the padding is zero, so the loop body has no guard.  z_min = 0 makes every byte a candidate (more
+    // than the list holds in any real row): that case goes straight to the dense path, which masks the padding explicitly.
+    const int nvec32 = zero_thr ? 0 : ((nvec + 31) & ~31);
+    if (zero_thr) nq = K1_CAP + 1;
     for (int base = 0; base < nvec32; base += 32) {
       const int t = base + lane;
-      const bool f = (zero_thr && t >= nvec) ? false : any_ge(vbuf[t]);
+      const bool f = any_ge(vbuf[t]);
       const unsigned ball = __ballot_sync(FULL, f);
       const int q = nq + __popc(ball & lt);
       if (f && q <= K1_CAP) queue[q] = (uint16_t)t;

@@ -55,6 +55,17 @@ def test_shapes_and_alignment(ctx, oracle, shape):
     _check_scan(ctx, oracle, img, z_min=5.0, k_strongest=12, min_distance=0.1)
 
 
+@pytest.mark.parametrize("shape", [(3, 5), (4, 17), (6, 64), (5, 130), (2, 600)])
+@pytest.mark.parametrize("k", [1, 12, 128])
+def test_zero_threshold_rows_shorter_and_longer_than_the_list(ctx, oracle, shape, k):
+    """z_min = 0: every bin is a candidate; such rows always take the exact dense path, whatever their length."""
+    rng = np.random.default_rng(shape[1] + k)
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    img[:, ::3] = 0                      # many ties at the threshold itself
+    _check_scan(ctx, oracle, img, z_min=0.0, k_strongest=k, min_distance=0.0)
+    _check_scan(ctx, oracle, np.zeros(shape, np.uint8), z_min=0.0, k_strongest=k, min_distance=0.0)
+
+
 def test_edge_bins_and_row_crossing(ctx, oracle):
     """Kept bins within 6 of either row end: NMS reads across the row edge (flat cv::Mat indexing)."""
     img = np.full((6, 128), 20, np.uint8)
