@@ -1107,6 +1107,7 @@ extern "C" int tbv_build_cells(tbv_ctx* ctx, const float* x, const float* y, con
                                double downsample_factor, int weight_intensity, const double origin[2], tbv_cell* cells, int cell_capacity,
                                int* n_cells, int* n_samples) {
   TBV_REQUIRE(ctx && x && y && intensity && origin && cells && n_cells, "null pointer");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n >= 0 && cell_capacity > 0, "bad sizes");
   *n_cells = 0;
   if (n_samples) *n_samples = 0;

@@ -132,6 +132,7 @@ using namespace tbv;
 extern "C" int tbv_filter_cacfar(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_range, size_t row_stride, int batch,
                                  const tbv_cfar_params* p, tbv_points* out) {
   TBV_REQUIRE(ctx && polar && p && out, "null pointer");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
   TBV_REQUIRE(n_range <= 8192 && n_az <= 4096, "image too large (n_range <= 8192, n_az <= 4096)");
   TBV_REQUIRE(p->window_size >= 1 && p->nb_guard_cells >= 0 && out->capacity > 0, "bad CFAR parameters");

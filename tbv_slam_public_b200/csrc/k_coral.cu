@@ -251,6 +251,7 @@ extern "C" int tbv_coral_quality_batch(tbv_ctx* ctx, int n_clouds, const float* 
                                        double* per_point) {
   TBV_REQUIRE(ctx && x && y && intensity && n_points && src_cloud && ref_cloud && T_src && T_ref && params && results && n_clouds >= 1 && n_pairs >= 0,
               "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(params->radius > 0, "radius must be positive");
   if (n_pairs == 0) return TBV_OK;
   cudaSetDevice(ctx->device);

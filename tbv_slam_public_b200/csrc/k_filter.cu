@@ -683,6 +683,7 @@ int tbv_filter_fetch(tbv_ctx* ctx, tbv_points* out_filtered, tbv_points* out_pea
 int tbv_filter_kstrongest(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_range, size_t row_stride, int batch,
                           const tbv_filter_params* params, tbv_points* out_filtered, tbv_points* out_peaks) {
   TBV_REQUIRE(ctx && polar && params && out_filtered, "null pointer");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
   const size_t bytes = (size_t)batch * n_az * row_stride;
   int rc = ctx->filt.polar.reserve(bytes);
@@ -695,6 +696,7 @@ int tbv_filter_kstrongest(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_ra
 
 int tbv_compensate(tbv_ctx* ctx, float* x, float* y, int n, const double mot_xyt[3], int ccw) {
   TBV_REQUIRE(ctx && x && y && mot_xyt && n >= 0, "null pointer");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n == 0) return TBV_OK;
   DevBuf<float> dx, dy;
   DevBuf<double> dm;

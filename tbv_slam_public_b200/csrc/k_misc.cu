@@ -4,6 +4,7 @@
 #include "tbv_common.cuh"
 
 namespace tbv {
+thread_local cudaStream_t g_alloc_stream = nullptr;
 static thread_local std::string g_err;
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -73,6 +74,13 @@ tbv_ctx* tbv_create(int device) {
     delete ctx;
     return nullptr;
   }
+  {  // keep freed blocks in the default pool: the host-pointer entry points allocate their temporaries from it on every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   return ctx;
 }
 
@@ -140,6 +148,7 @@ void tbv_host_free(void* p) {
 
 int tbv_rotate90ccw(tbv_ctx* ctx, const uint8_t* src, int rows, int cols, uint8_t* dst) {
   TBV_REQUIRE(ctx && src && dst && rows > 0 && cols > 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   const size_t n = (size_t)rows * cols;
   DevBuf<uint8_t> a, b;
   int rc;

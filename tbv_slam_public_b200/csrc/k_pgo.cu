@@ -225,6 +225,7 @@ extern "C" int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, 
                                 const tbv_pgo_params* params, int fixed_node, double* cost, double* H_diag, double* H_off, double* g,
                                 double* residuals) {
   TBV_REQUIRE(ctx && nodes && ids && meas && params && H_diag && H_off && g && n_nodes >= 1 && n_con >= 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(params->replace_cov_by_identity || info, "information matrices required when replace_cov_by_identity is 0");
   for (int c = 0; c < n_con; c++)
     TBV_REQUIRE(ids[3 * c] >= 0 && ids[3 * c] < n_nodes && ids[3 * c + 1] >= 0 && ids[3 * c + 1] < n_nodes, "constraint references a missing node");

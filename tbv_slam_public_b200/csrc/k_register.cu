@@ -1300,6 +1300,7 @@ int tbv_pair_normal_eq(tbv_ctx* ctx, const tbv_cell* tgt, int n_tgt, const doubl
                        const double T_src[3], const tbv_reg_params* params, int itr, double* cost, int* n_res, double H[9], double g[3],
                        int32_t* assoc) {
   TBV_REQUIRE(ctx && T_tgt && T_src && params && n_tgt >= 0 && n_src >= 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   const tbv_cell* scans[2] = {tgt, src};
   const int n_cells[2] = {n_tgt, n_src};
   const double T[6] = {T_tgt[0], T_tgt[1], T_tgt[2], T_src[0], T_src[1], T_src[2]};
@@ -1323,6 +1324,7 @@ int tbv_pair_normal_eq(tbv_ctx* ctx, const tbv_cell* tgt, int n_tgt, const doubl
 int tbv_register(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, double* T, const tbv_reg_params* params,
                  tbv_reg_summary* summary) {
   TBV_REQUIRE(ctx && scans && n_cells && T && params && n_scans >= 2, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   RegResult r;
   int rc = run_single(ctx, REG_MODE_REGISTER, 0, n_scans, scans, n_cells, T, params, &r, nullptr, nullptr, nullptr, nullptr);
   if (rc) return rc;
@@ -1343,6 +1345,7 @@ int tbv_register(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const 
 int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T, const tbv_reg_params* params,
                  int itr, double* score, double* cost, int* n_res, double* residuals, int res_capacity) {
   TBV_REQUIRE(ctx && scans && n_cells && T && params && n_scans >= 2, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   RegResult r;
   double ev[NACC];
   std::vector<double> res;
@@ -1361,6 +1364,7 @@ int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const 
 int tbv_cost_samples(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T, const tbv_reg_params* params,
                      int itr, double xy_range, double yaw_range, int n_per_axis, double* samples) {
   TBV_REQUIRE(ctx && scans && n_cells && T && params && samples && n_scans >= 2 && n_per_axis >= 1 && n_per_axis <= 16, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   auto linspace = [](double start, double end, int num) {  // odometrykeyframefuser.cpp:498-524
     std::vector<double> v;
     if (num == 1) { v.push_back(start); return v; }
@@ -1520,6 +1524,7 @@ int tbv_register_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, co
                        const int* to_set, const double* T_from, const double* T_to, const tbv_reg_params* params, double* T_revised,
                        double* T_align, tbv_reg_summary* summaries) {
   TBV_REQUIRE(ctx && sets && n_cells && from_set && to_set && T_from && T_to && params && n_sets >= 1 && n_pairs >= 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n_pairs == 0) return TBV_OK;
   HostProblemSet hs;
   hs.ctx = ctx;

@@ -109,40 +109,74 @@ __device__ __forceinline__ void aff2_rel_translation(const Aff2& A, const Aff2& 
   ty = (i10 * B.tx + i11 * B.ty) + ity;
 }
 
-// one thread per query: ExcludeAndUpdateLikelihood (:183-221) as of keyframe cur = q_current[q]
-__global__ void sc_similarity(const double* __restrict__ odom, int n_q, const int* __restrict__ q_current, double sigma, double exclude_dist,
-                              int sim_stride, double* __restrict__ sim, int* __restrict__ n_exclude) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// one CTA per query: ExcludeAndUpdateLikelihood (:183-221) as of keyframe cur = q_current[q].  The travelled distance is a running
+// sum from the query backwards — the reference adds the steps one by one, and so does this kernel (thread 0, out of shared memory,
+// eight loads ahead of eight dependent adds), so every trav_i is bit-identical; the step lengths before it and the likelihoods
+// after it (sqrt, division, exp per keyframe) are computed by all threads.
+constexpr int SCS_CHUNK = 2048;
+__global__ void __launch_bounds__(256)
+sc_similarity(const double* __restrict__ odom, int n_q, const int* __restrict__ q_current, double sigma, double exclude_dist,
+              int sim_stride, double* __restrict__ sim, int* __restrict__ n_exclude) {
+  __shared__ double s_t[SCS_CHUNK];
+  __shared__ double s_carry;
+  const int q = blockIdx.x;
   if (q >= n_q) return;
   const int cur = q_current[q];
-  int ne;
-  if (cur + 1 <= 2) ne = 2;
-  else {
-    double distance = 0.0;
-    ne = 0;
-    Aff2 Tprev = aff2_from(odom + 3 * (size_t)cur);
-    for (int i = cur; i >= 0 && distance < exclude_dist; i--) {
-      const Aff2 Ti = aff2_from(odom + 3 * (size_t)i);
-      double tx, ty;
-      aff2_rel_translation(Tprev, Ti, tx, ty);
-      distance = distance + sqrt(tx * tx + ty * ty);
-      Tprev = Ti;
-      ne++;
+  if (threadIdx.x == 0) {
+    int ne;
+    if (cur + 1 <= 2) ne = 2;
+    else {
+      double distance = 0.0;
+      ne = 0;
+      Aff2 Tprev = aff2_from(odom + 3 * (size_t)cur);
+      for (int i = cur; i >= 0 && distance < exclude_dist; i--) {
+        const Aff2 Ti = aff2_from(odom + 3 * (size_t)i);
+        double tx, ty;
+        aff2_rel_translation(Tprev, Ti, tx, ty);
+        distance = distance + sqrt(tx * tx + ty * ty);
+        Tprev = Ti;
+        ne++;
+      }
     }
+    n_exclude[q] = ne;
+    s_carry = 0.0;
   }
-  n_exclude[q] = ne;
+  __syncthreads();
   const double cx = odom[3 * (size_t)cur], cy = odom[3 * (size_t)cur + 1];
-  double tpx = cx, tpy = cy, trav = 0.0;
   double* sq = sim + (size_t)q * sim_stride;
-  for (int i = cur - 1; i >= 0; i--) {
-    const double tix = odom[3 * (size_t)i], tiy = odom[3 * (size_t)i + 1];
-    trav += sqrt((tpx - tix) * (tpx - tix) + (tpy - tiy) * (tpy - tiy));
-    tpx = tix; tpy = tiy;
-    const double est = sqrt((cx - tix) * (cx - tix) + (cy - tiy) * (cy - tiy));
-    const double error = fmax(est - 5.0, 0.0);
-    const double rel = error / trav;
-    const double prob = exp(-rel * rel / (2 * sigma * sigma));
-    sq[i] = 1.0 - prob;
+  // keyframes i = cur-1 ... 0 in chunks; slot j of a chunk is keyframe i = hi - j (descending, the order of the running sum)
+  for (int hi = cur - 1; hi >= 0; hi -= SCS_CHUNK) {
+    const int m = min(SCS_CHUNK, hi + 1);
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+      const int i = hi - j;
+      const double tpx = odom[3 * (size_t)(i + 1)], tpy = odom[3 * (size_t)(i + 1) + 1];
+      const double tix = odom[3 * (size_t)i], tiy = odom[3 * (size_t)i + 1];
+      s_t[j] = sqrt((tpx - tix) * (tpx - tix) + (tpy - tiy) * (tpy - tiy));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double trav = s_carry;
+      int j = 0;
+      for (; j + 8 <= m; j += 8) {
+        const double d0 = s_t[j], d1 = s_t[j + 1], d2 = s_t[j + 2], d3 = s_t[j + 3], d4 = s_t[j + 4], d5 = s_t[j + 5], d6 = s_t[j + 6], d7 = s_t[j + 7];
+        trav += d0; s_t[j] = trav; trav += d1; s_t[j + 1] = trav; trav += d2; s_t[j + 2] = trav; trav += d3; s_t[j + 3] = trav;
+        trav += d4; s_t[j + 4] = trav; trav += d5; s_t[j + 5] = trav; trav += d6; s_t[j + 6] = trav; trav += d7; s_t[j + 7] = trav;
+      }
+      for (; j < m; j++) { trav += s_t[j]; s_t[j] = trav; }
+      s_carry = trav;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+      const int i = hi - j;
+      const double tix = odom[3 * (size_t)i], tiy = odom[3 * (size_t)i + 1];
+      const double trav = s_t[j];
+      const double est = sqrt((cx - tix) * (cx - tix) + (cy - tiy) * (cy - tiy));
+      const double error = fmax(est - 5.0, 0.0);
+      const double rel = error / trav;
+      const double prob = exp(-rel * rel / (2 * sigma * sigma));
+      sq[i] = 1.0 - prob;
+    }
+    __syncthreads();
   }
 }
 
@@ -327,6 +361,7 @@ extern "C" {
 int tbv_sc_make(tbv_ctx* ctx, const float* x, const float* y, const float* intensity, int n, const tbv_sc_params* p, int n_offsets,
                 const double* offsets_xy, double* desc, float* ringkey, double* sectorkey) {
   TBV_REQUIRE(ctx && p && desc && offsets_xy && n >= 0 && n_offsets >= 1, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n == 0 || (x && y && intensity), "null cloud");
   const int R = p->num_ring, S = p->num_sector;
   TBV_REQUIRE(R >= 1 && S >= 1 && (size_t)R * S <= 16384 && p->desc_divider != 0.0, "bad descriptor shape");
@@ -354,6 +389,7 @@ int tbv_sc_make(tbv_ctx* ctx, const float* x, const float* y, const float* inten
 int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const double* desc_c, int n_c, int n_pairs, const int* q_idx,
                           const int* c_idx, const tbv_sc_params* p, double* dist, int* shift) {
   TBV_REQUIRE(ctx && desc_q && desc_c && q_idx && c_idx && p && dist && shift && n_q >= 1 && n_c >= 1 && n_pairs >= 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n_pairs == 0) return TBV_OK;
   const int R = p->num_ring, S = p->num_sector;
   const int radius = (int)std::round(0.5 * p->search_ratio * S);  // Scancontext.cpp:168
@@ -380,6 +416,7 @@ int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const dou
 int tbv_sc_search(tbv_ctx* ctx, const float* db_keys, const double* odom_xyt, int n_db, int n_q, const float* q_keys, const int* q_current,
                   const tbv_sc_params* p, int* cand_idx, double* cand_odom_sim, int* n_exclude) {
   TBV_REQUIRE(ctx && db_keys && odom_xyt && q_keys && q_current && p && cand_idx && n_db >= 1 && n_q >= 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n_q == 0) return TBV_OK;
   const int R = p->num_ring, want = p->num_candidates_from_tree;
   TBV_REQUIRE(R >= 1 && R <= 128 && want >= 1, "bad search parameters");
@@ -392,7 +429,7 @@ int tbv_sc_search(tbv_ctx* ctx, const float* db_keys, const double* odom_xyt, in
       (rc = dcur.up(ctx, q_current, n_q)) || (rc = dsim.up(ctx, nullptr, (size_t)n_q * n_db)) || (rc = dscr.up(ctx, nullptr, (size_t)n_q * n_db)) ||
       (rc = dne.up(ctx, nullptr, n_q)) || (rc = dci.up(ctx, nullptr, (size_t)n_q * want)) || (rc = dcs.up(ctx, nullptr, (size_t)n_q * want)))
     return rc;
-  sc_similarity<<<(n_q + 63) / 64, 64, 0, ctx->stream>>>(dod.b.p, n_q, dcur.b.p, p->odom_sigma_error, p->distance_exclude_recent, n_db, dsim.b.p, dne.b.p);
+  sc_similarity<<<n_q, 256, 0, ctx->stream>>>(dod.b.p, n_q, dcur.b.p, p->odom_sigma_error, p->distance_exclude_recent, n_db, dsim.b.p, dne.b.p);
   launched(ctx, "sc_similarity");
   sc_search<<<n_q, 256, 0, ctx->stream>>>(dk.b.p, R, n_q, dqk.b.p, dcur.b.p, dne.b.p, dsim.b.p, n_db, p->odometry_coupled_closure, want, dscr.b.p, dci.b.p,
                                           dcs.b.p);

@@ -33,28 +33,49 @@ void set_error(const char* fmt, ...);
     }                                            \
   } while (0)
 
+// Stream-ordered allocation for the host-pointer entry points: while an AllocScope is alive on this thread, DevBuf takes its memory
+// from the device's default memory pool with cudaMallocAsync on the scope's stream and gives it back with cudaFreeAsync — a few
+// microseconds once the pool is warm (tbv_create sets the pool's release threshold so that it keeps its memory), instead of the
+// cudaMalloc / cudaFree pair (100+ us each, and cudaFree synchronises the device) these calls used to pay per temporary buffer.
+// Long-lived state allocated outside a scope keeps plain cudaMalloc.
+extern thread_local cudaStream_t g_alloc_stream;
+struct AllocScope {
+  cudaStream_t prev;
+  explicit AllocScope(cudaStream_t s) : prev(g_alloc_stream) { g_alloc_stream = s; }
+  ~AllocScope() { g_alloc_stream = prev; }
+};
+
 // growable device buffer
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t pool_stream = nullptr;  // non-null: p came from cudaMallocAsync on this stream
   int reserve(size_t count) {
     if (count <= n) return TBV_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    release();
+    cudaError_t e;
+    if (g_alloc_stream) {
+      e = cudaMallocAsync((void**)&p, count * sizeof(T), g_alloc_stream);
+      if (e == cudaSuccess) pool_stream = g_alloc_stream;
+    } else {
+      e = cudaMalloc((void**)&p, count * sizeof(T));
+    }
     if (e != cudaSuccess) {
-      set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      p = nullptr;
+      set_error("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
       return TBV_ERR_CUDA;
     }
     n = count;
     return TBV_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (pool_stream) cudaFreeAsync(p, pool_stream); else cudaFree(p);
+    }
     p = nullptr;
     n = 0;
+    pool_stream = nullptr;
   }
 };
 
