@@ -615,7 +615,7 @@ struct RegShared {
   double acc[NACC];
   double warp_acc[RG_WARPS][NACC];
   double ex[3], cs[2];
-  int flag, n_blocks, warp_cnt[RG_WARPS];
+  int flag, n_blocks, warp_cnt[RG_WARPS], warp_pre[RG_WARPS + 1];   // blocks per warp segment and their exclusive prefix
   Aff Tst[RG_MAX_FIXED], Ttar[RG_MAX_FIXED];
   SetView tgt[RG_MAX_FIXED];
   CellGrid grid[RG_MAX_FIXED];   // search-grid headers of the fixed sets
@@ -677,10 +677,10 @@ __device__ __forceinline__ void eval_block_simple(const double* __restrict__ blk
   }
 }
 
-template <int COST, bool HUBER>
-__device__ __forceinline__ void eval_loop_simple(const double* __restrict__ blocks, size_t bstride, int nblk, double limit, double x0, double x1,
-                                                 double cy, double sy, int tid, double* __restrict__ a) {
-  for (int q = tid; q < nblk; q += RG_THREADS) eval_block_simple<COST, HUBER>(blocks + q, bstride, limit, x0, x1, cy, sy, a);
+template <int COST, bool HUBER, typename At>
+__device__ __forceinline__ void eval_loop_simple(const double* __restrict__ blocks, size_t bstride, int nblk, At at, double limit, double x0,
+                                                 double x1, double cy, double sy, int tid, double* __restrict__ a) {
+  for (int q = tid; q < nblk; q += RG_THREADS) eval_block_simple<COST, HUBER>(blocks + at(q), bstride, limit, x0, x1, cy, sy, a);
 }
 
 // MIN_CTAS: resident CTAs per SM the register budget is set for (3 -> 80 registers, 4 -> 64)
@@ -714,7 +714,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   const int n_fixed = min(prob.n_fixed, RG_MAX_FIXED);
   const size_t bstride = (size_t)max_fixed * slot_cap;
   int* assoc = assoc_all + (size_t)p * bstride;
-  double* wgt = wgt_all + (size_t)p * bstride;
+  (void)wgt_all;  // weights now go straight into the residual blocks
   double* blocks = blocks_all + (size_t)p * BLK_FIELDS * bstride;
   const int nres_per_block = (P.cost == TBV_P2L) ? 1 : 2;
   if (tid < n_fixed) {
@@ -779,6 +779,12 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   }
   __syncthreads();
 
+  // every warp owns a contiguous range of (fixed scan, source cell) slots — fixed-major, the order the reference adds its residual
+  // blocks in — and the matching segment of the block arrays
+  const int n_slots = n_fixed * n_src;
+  const int chunk = (((n_slots + RG_WARPS - 1) / RG_WARPS) + 31) & ~31;
+  const int s_begin = min(n_slots, warp * chunk), s_end = min(n_slots, s_begin + chunk);
+
   // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan).  Slot = (fixed scan, source
   // cell), fixed-major: the order the reference adds its residual blocks in.  Every warp owns a contiguous slot range:
   // pass 1 searches and counts, one barrier publishes the per-warp counts, pass 2 writes the accepted correspondences of
@@ -791,32 +797,30 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       sh.Tst[tid] = aff_mul(aff_inv(Ttar), vec_to_aff(x[0], x[1], x[2]));
     }
     __syncthreads();
-    const int n_slots = n_fixed * n_src;
-    const int chunk = (((n_slots + RG_WARPS - 1) / RG_WARPS) + 31) & ~31;
-    const int s_begin = min(n_slots, warp * chunk), s_end = min(n_slots, s_begin + chunk);
     int my_cnt = 0;
     for (int base = s_begin; base < s_end; base += 32) {
       const int slot = base + lane;
       bool ok = false;
+      int ti = -1, fi = 0, j = 0;
+      double w = 1.0, tn0 = 0.0, tn1 = 0.0;
       if (slot < s_end) {
-        const int fi = slot / n_src;
-        const int j = slot - fi * n_src;
+        fi = slot / n_src;
+        j = slot - fi * n_src;
         const Aff Tst = sh.Tst[fi];
         const SetView& tgt = sh.tgt[fi];
-        // every source-side value is fetched before the search, every target-side value right after it: two round trips
-        // instead of one per dependent use
         double ux, uy;
         if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
         else { ux = src.f[(size_t)CF_U0 * src.cap + j]; uy = src.f[(size_t)CF_U1 * src.cap + j]; }
         const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
         const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
-        int ti = staged ? nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]),
-                                           reinterpret_cast<const uint16_t*>(rg_stage + sh.row_off[fi]), sh.grid[fi], (float)qxd, (float)qyd, R)
-                        : nn_search(tgt, sh.grid[fi], sh.n_tgt[fi], (float)qxd, (float)qyd, R);
+        ti = staged ? nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]),
+                                       reinterpret_cast<const uint16_t*>(rg_stage + sh.row_off[fi]), sh.grid[fi], (float)qxd, (float)qyd, R)
+                    : nn_search(tgt, sh.grid[fi], sh.n_tgt[fi], (float)qxd, (float)qyd, R);
         if (ti >= 0) {
-          const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
+          // every value the decision and the weight need, in one round trip
           const bool weighted = P.weight_opt != TBV_W_UNIFORM;
-          const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
+          const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
+          tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti]; tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
           const double N2 = weighted ? tgt.f[(size_t)CF_NS * tgt.cap + ti] : 0.0, p2 = weighted ? tgt.f[(size_t)CF_SCALE * tgt.cap + ti] : 0.0;
           const double N1 = weighted ? src.f[(size_t)CF_NS * src.cap + j] : 0.0, p1 = weighted ? src.f[(size_t)CF_SCALE * src.cap + j] : 0.0;
           const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
@@ -824,7 +828,6 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
           const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
           if (sim > P.angle_outlier) {
             ok = true;
-            double w = 1.0;
             if (weighted) {
               const double simN = 2 * fmin(N1, N2) / (N1 + N2);
               const double simP = 2 * fmin(p1, p2) / (p1 + p2);
@@ -836,45 +839,29 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
                 default: w = 1.0;
               }
             }
-            wgt[slot] = w;
           } else {
             ti = -1;
           }
         }
         assoc[(size_t)fi * slot_cap + j] = ti;
       }
-      my_cnt += __popc(__ballot_sync(FULL, ok));
-    }
-    if (lane == 0) sh.warp_cnt[warp] = my_cnt;
-    __syncthreads();
-    int q0 = 0, total = 0;
-#pragma unroll
-    for (int wv = 0; wv < RG_WARPS; wv++) {
-      const int c = sh.warp_cnt[wv];
-      if (wv < warp) q0 += c;
-      total += c;
-    }
-    for (int base = s_begin; base < s_end; base += 32) {
-      const int slot = base + lane;
-      int ti = -1, fi = 0, j = 0;
-      if (slot < s_end) {
-        fi = slot / n_src;
-        j = slot - fi * n_src;
-        ti = assoc[(size_t)fi * slot_cap + j];   // written by this very thread in pass 1
-      }
-      const bool ok = ti >= 0;
+      // the accepted correspondences of this warp, in slot order, go to the warp's own segment of the block arrays (it starts at
+      // the warp's first slot): the warp that writes a block is the warp that evaluates it, so no second pass and no barrier
+      // stand between the search and the first evaluation
       const unsigned bal = __ballot_sync(FULL, ok);
       if (ok) {
-        const int q = q0 + __popc(bal & ((1u << lane) - 1u));
+        const int q = s_begin + my_cnt + __popc(bal & ((1u << lane) - 1u));
         const Aff Ttar = sh.Ttar[fi];
         const SetView& tgt = sh.tgt[fi];
         const double tu0 = tgt.f[(size_t)CF_U0 * tgt.cap + ti], tu1 = tgt.f[(size_t)CF_U1 * tgt.cap + ti];
-        blocks[0 * bstride + q] = src.f[(size_t)CF_U0 * src.cap + j];
-        blocks[1 * bstride + q] = src.f[(size_t)CF_U1 * src.cap + j];
+        double ux, uy;
+        if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
+        else { ux = src.f[(size_t)CF_U0 * src.cap + j]; uy = src.f[(size_t)CF_U1 * src.cap + j]; }
+        blocks[0 * bstride + q] = ux;
+        blocks[1 * bstride + q] = uy;
         blocks[2 * bstride + q] = (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx;
         blocks[3 * bstride + q] = (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty;
         if (P.cost == TBV_P2L) {
-          const double tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti], tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
           blocks[4 * bstride + q] = Ttar.r00 * tn0 + Ttar.r01 * tn1;
           blocks[5 * bstride + q] = Ttar.r10 * tn0 + Ttar.r11 * tn1;
         } else if (P.cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
@@ -897,14 +884,28 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
           blocks[5 * bstride + q] = l10;
           blocks[6 * bstride + q] = l11;
         }
-        const double w = wgt[slot];
         blocks[7 * bstride + q] = w;
         blocks[8 * bstride + q] = sqrt(w);
       }
-      q0 += __popc(bal);
+      my_cnt += __popc(bal);
     }
-    if (tid == 0) sh.n_blocks = total;
+    if (lane == 0) sh.warp_cnt[warp] = my_cnt;
     __syncthreads();
+    if (tid == 0) {
+      int total = 0;
+      for (int wv = 0; wv < RG_WARPS; wv++) { sh.warp_pre[wv] = total; total += sh.warp_cnt[wv]; }
+      sh.warp_pre[RG_WARPS] = total;
+      sh.n_blocks = total;
+    }
+    __syncthreads();
+  };
+  // block q of the reference's order (fixed-major, compacted) -> its place in the segmented block arrays.  The evaluation strides all
+  // 256 threads over q: the segments are not equally full (a recent keyframe matches far more cells than an old one), the threads are.
+  auto block_at = [&](int q) -> int {
+    int wv = 0;
+#pragma unroll
+    for (int k = 1; k < RG_WARPS; k++) wv += (q >= sh.warp_pre[k]);
+    return wv * chunk + (q - sh.warp_pre[wv]);
   };
 
   // ---- evaluation at sh.ex (cos/sin in sh.cs): per-warp partial sums in sh.warp_acc (fixed shapes: deterministic).
@@ -917,19 +918,19 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     const double x0 = sh.ex[0], x1 = sh.ex[1], cy = sh.cs[0], sy = sh.cs[1];
     if (simple_loss) {
       if (P.loss == TBV_LOSS_HUBER) {
-        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, true>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, true>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else eval_loop_simple<TBV_P2D, true>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
+        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, true>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, true>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else eval_loop_simple<TBV_P2D, true>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
       } else {
-        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, false>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, false>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else eval_loop_simple<TBV_P2D, false>(blocks, bstride, nblk, P.loss_limit, x0, x1, cy, sy, tid, a);
+        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, false>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, false>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
+        else eval_loop_simple<TBV_P2D, false>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
       }
     } else {
       for (int q = tid; q < nblk; q += RG_THREADS) {
         double f[2], J[6];
         int n;
-        a[0] += eval_block(P.cost, P.loss, P.loss_limit, blocks + q, bstride, x0, x1, cy, sy, f, J, n, true);
+        a[0] += eval_block(P.cost, P.loss, P.loss_limit, blocks + block_at(q), bstride, x0, x1, cy, sy, f, J, n, true);
         for (int r = 0; r < n; r++) {
           const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
           a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
