@@ -187,8 +187,13 @@ k_odom_update(SeqState* __restrict__ st, OdomDevParams P, const RegResult* __res
   const int n = min(cur_count[s], cell_cap);
   const double* src = cur_cells + (size_t)s * CELL_FIELDS * cell_cap;
   double* dst = kf_cells + ((size_t)s * P.K + slot) * CELL_FIELDS * cell_cap;
-  for (int f = 0; f < CELL_FIELDS; f++)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[(size_t)f * cell_cap + i] = src[(size_t)f * cell_cap + i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // all 16 fields of a cell in flight at once
+    double v[CELL_FIELDS];
+#pragma unroll
+    for (int f = 0; f < CELL_FIELDS; f++) v[f] = src[(size_t)f * cell_cap + i];
+#pragma unroll
+    for (int f = 0; f < CELL_FIELDS; f++) dst[(size_t)f * cell_cap + i] = v[f];
+  }
   if (threadIdx.x == 0) kf_count[s * P.K + slot] = n;
 }
 
@@ -294,7 +299,7 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   launched(ctx, "k_odom_update");
   TBV_CUDA(cudaGetLastError());
   // new keyframes get their search grid now (used by the registrations of the following frames)
-  return cellgrid_build_launch(ctx, od->views.p, od->fused_set.p, n_seq, n_seq * (od->K + 1));
+  return cellgrid_build_launch(ctx, od->views.p, od->fused_set.p, n_seq, n_seq * (od->K + 1), od->cpar.max_extent);
 }
 
 extern "C" {

@@ -403,8 +403,8 @@ __device__ __forceinline__ int grid_coord(float v, float mn, int n) {  // bucket
 }
 
 __global__ void __launch_bounds__(256)
-k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which, int n_sets) {
-  extern __shared__ int s_cnt[];  // [GRID_CAP]
+k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which, int n_sets, int bucket_cap) {
+  extern __shared__ int s_cnt[];  // [bucket_cap] <= GRID_CAP: the caller's bound on the buckets of one grid (larger grids: no grid)
   __shared__ float s_red[4][8];
   __shared__ int s_part[256];
   __shared__ CellGrid s_g;
@@ -438,7 +438,7 @@ k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which
       const float fx = floorf((mxx - mnx) / GRID_CELL), fy = floorf((mxy - mny) / GRID_CELL);
       if (fx >= 0.f && fy >= 0.f && fx < 16384.f && fy < 16384.f) {
         g.nx = (int)fx + 1; g.ny = (int)fy + 1;
-        g.ok = ((long long)g.nx * g.ny <= GRID_CAP) ? 1 : 0;
+        g.ok = ((long long)g.nx * g.ny <= bucket_cap) ? 1 : 0;
       }
     }
     s_g = g;
@@ -457,11 +457,15 @@ k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which
   const int b0 = min(nb, tid * chunk), b1 = min(nb, b0 + chunk);
   int sum = 0;
   for (int b = b0; b < b1; b++) sum += s_cnt[b];
-  s_part[tid] = sum;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int k = 0; k < 256; k++) { const int v = s_part[k]; s_part[k] = run; run += v; }
+  {  // exclusive scan of the 256 per-thread sums: warp shuffles + one pass over the 8 warp totals
+    int inc = sum;
+    for (int d = 1; d < 32; d <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t2; }
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();
+    int wbase = 0;
+    for (int k = 0; k < warp; k++) wbase += s_part[k];
+    __syncthreads();
+    s_part[tid] = wbase + inc - sum;
   }
   __syncthreads();
   int off = s_part[tid];
@@ -1165,14 +1169,21 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   return TBV_OK;
 }
 
-int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets) {
+int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets, double max_extent) {
   if (n_launch <= 0) return TBV_OK;
   static bool attr = false;
   if (!attr) {
     TBV_CUDA(cudaFuncSetAttribute(k_cellgrid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, GRID_CAP * (int)sizeof(int)));
     attr = true;
   }
-  k_cellgrid_build<<<n_launch, 256, GRID_CAP * sizeof(int), ctx->stream>>>(sets_dev, which_dev, n_sets);
+  // shared-memory counters for as many buckets as a grid over cells within max_extent of the sensor can have (<= GRID_CAP): for the
+  // odometry's 181 m that is 33 KB instead of 64 KB, so all 592 CTAs are resident at once instead of running as 1.33 waves
+  int bucket_cap = GRID_CAP;
+  if (max_extent > 0) {
+    const long long side = (long long)(2.0 * max_extent / GRID_CELL) + 2;
+    if (side * side < GRID_CAP) bucket_cap = (int)(side * side);
+  }
+  k_cellgrid_build<<<n_launch, 256, (size_t)bucket_cap * sizeof(int), ctx->stream>>>(sets_dev, which_dev, n_sets, bucket_cap);
   launched(ctx, "k_cellgrid_build");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;

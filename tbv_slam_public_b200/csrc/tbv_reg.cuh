@@ -35,7 +35,8 @@ struct GridStore {      // storage for the grids of n_sets cell sets
 };
 
 // (re)builds the grids of sets which_dev[0..n_launch) (which_dev == nullptr: sets 0..n_launch-1; entries < 0 are skipped)
-int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets);
+// max_extent > 0: bound on |x|, |y| of the cell means (sizes the kernel's shared-memory counters; a larger set simply gets no grid)
+int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets, double max_extent = 0.0);
 
 struct RegProblem {     // one n_scan_normal_reg::Register call: fixed scans + one moving scan
   int n_fixed;
