@@ -303,9 +303,9 @@ def run_ours(args):
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak_hbm, "unit": "GB/s",
                 "frac": round(achieved / peak_hbm, 5),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k1_kstrongest launch over 592 scans (ncu --set full,
-                # profiles/r1g_full_k1_kstrongest.txt): 898.1 MB + 17.8 MB -> 1.5471 MB per scan; the algorithmic figure (1.572 MB)
+                # profiles/r1h_full_k1_kstrongest.txt): 898.1 MB + 17.6 MB -> 1.5467 MB per scan; the algorithmic figure (1.572 MB)
                 # is slightly larger because part of the 64.8 kB of row keys per scan is still in L2 when K2 consumes it
-                "traffic": round(1.5471e6 * S, 0), "traffic_source": "profiles/r1g_full_k1_kstrongest.txt (592 scans per launch), scaled by sequences_per_gpu / 592",
+                "traffic": round(1.5467e6 * S, 0), "traffic_source": "profiles/r1h_full_k1_kstrongest.txt (592 scans per launch), scaled by sequences_per_gpu / 592",
                 "algorithmic_bytes_per_launch": b_dom, "launch_ms": round(kern[dominant], 4),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "share_of_step": kernels[dominant]["share"], "longest_kernel": longest, "longest_kernel_share": kernels[longest]["share"],
