@@ -69,6 +69,26 @@ def test_odometry_p2p_and_slow_motion_keyframes(ctx, oracle):
     _run_pair(ctx, oracle, [list(st.scans)], dict(reg=rp), dict(cost_type=oracle.P2P))
 
 
+def test_odometry_mulran_shape_rotate_on_receipt_ccw(ctx, oracle):
+    """BASELINE config 5 shape: MulRan scans arrive range-major (3360 x 400) and are rotated 90 degrees CCW on receipt
+    (radar_driver.cpp:80-84), 400 x 3360 bins of 0.0595238 m, counter-clockwise sweep (compensation sign flips), CFEAR-1 (MulRan) preset:
+    z_min 70, k 12, r 3.5, P2L, one keyframe, uniform cell weights."""
+    st = synth.make_stream(8, dataset=synth.MULRAN)
+    scans = []
+    for img in st.scans:
+        wire = np.ascontiguousarray(np.rot90(img, -1))          # what the driver receives: range-major
+        assert wire.shape == (3360, 400)
+        rot = ctx.rotate90ccw(wire)
+        assert np.array_equal(rot, img) and np.array_equal(oracle.rotate90ccw(wire), img)
+        scans.append(rot)
+    gp = api.default_odom_params(submap_scan_size=1, weight_intensity=0, res=3.5, radar_ccw=1)
+    gp.filter.k_strongest = 12
+    gp.filter.z_min = 70.0
+    gp.filter.range_res = 0.0595238
+    _run_pair(ctx, oracle, [scans], dict(submap_scan_size=1, weight_intensity=0, res=3.5, radar_ccw=1, filter=gp.filter),
+              dict(submap_scan_size=1, weight_intensity=0, res=3.5, radar_ccw=1, k_strongest=12, z_min=70.0, range_res=0.0595238))
+
+
 def test_dense_short_range_clutter_uses_the_global_point_arrays(ctx, oracle):
     """16 000 points per scan (every azimuth keeps k = 40) inside 39 m: more points than the fused cells kernel holds in shared
     memory (8 192), so its point arrays live in global scratch — same results as the oracle, cell for cell."""
