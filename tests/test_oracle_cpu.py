@@ -504,3 +504,31 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle", src, flags=re.M), f
+
+
+def test_oracle_regression_fixture(oracle):
+    """tests/golden/oracle_regression.json freezes the oracle's own outputs downstream of the filter (NOT reference outputs — see the
+    generator's header): integers exact, floating point within 1e-9 relative (libm / compiler differences between boxes)."""
+    import importlib.util
+    import json
+    here = os.path.join(ROOT, "tests", "golden")
+    spec = importlib.util.spec_from_file_location("make_oracle_regression", os.path.join(here, "make_oracle_regression.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = json.loads(json.dumps(mod.compute()))
+    want = json.load(open(os.path.join(here, "oracle_regression.json")))
+
+    def cmp(a, b, path):
+        if isinstance(b, dict):
+            assert isinstance(a, dict) and sorted(a) == sorted(b), path
+            for k in b:
+                cmp(a[k], b[k], path + "/" + k)
+        elif isinstance(b, list):
+            assert isinstance(a, list) and len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                cmp(x, y, f"{path}[{i}]")
+        elif isinstance(b, float):
+            assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (path, a, b)
+        else:
+            assert a == b, (path, a, b)
+    cmp(got, want, "")
