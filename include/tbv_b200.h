@@ -270,6 +270,14 @@ int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const dou
 int tbv_sc_search(tbv_ctx* ctx, const float* db_keys, const double* odom_xyt, int n_db, int n_q, const float* q_keys, const int* q_current,
                   const tbv_sc_params* params, int* cand_idx, double* cand_odom_sim, int* n_exclude);
 
+/* CFEARQuality (coral_alignment_quality/src/alignment_checker/AlignmentQuality.cpp:330-352, called from
+ * ScanLearningInterface::getCFEARQualityMeasure, alignmentinterface.cpp:457-475): GetCost of {ref (fixed), src} at the given poses with the
+ * caller's params (reference: P2L, Huber 0.3, uniform weights; itr_ = 0) for a batch of pairs in one launch.
+ * quality: [n_pairs][3] = score, number of residuals, (|src| + |ref|) / 2  ({0, 0, 0} when GetCost fails). */
+int tbv_cfear_quality_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, const int* n_cells, int n_pairs, const int* src_set,
+                            const int* ref_set, const double* T_src, const double* T_offset, const double* T_ref,
+                            const tbv_reg_params* params, double* quality);
+
 /* ---- CorAl alignment quality (next-row f-1): CorAlRadarQuality ------------------------------------------------------------
  * coral_alignment_quality/src/alignment_checker/AlignmentQuality.cpp:8-229 as called by ScanLearningInterface::getCorAlQualityMeasure
  * (coral_alignment_quality/src/alignment_checker/alignmentinterface.cpp:437-454: peaks clouds, radius 1.0, entropy setting `any`,

@@ -344,6 +344,19 @@ class Context:
                                                C.byref(ok)))
         return bool(ok.value), cov, samples
 
+    def CFEARQualityBatch(self, sets, src_set, ref_set, T_src, T_ref, T_offset=None, params: RegParams | None = None):
+        """CFEARQuality for many candidate pairs at once: [n, 3] = score, residual count, mean set size."""
+        params = params or default_reg_params(cost=P2L, loss=HUBER, loss_limit=0.3, weight_opt=W_UNIFORM)
+        arrs, ptrs, ns = self._scan_ptrs(sets)
+        ss = np.ascontiguousarray(src_set, np.int32); rs = np.ascontiguousarray(ref_set, np.int32)
+        n = len(ss)
+        Ts = np.ascontiguousarray(T_src, np.float64).reshape(n, 3); Tr = np.ascontiguousarray(T_ref, np.float64).reshape(n, 3)
+        To = np.ascontiguousarray(T_offset, np.float64).reshape(n, 3) if T_offset is not None else None
+        q = np.zeros((n, 3))
+        _check(lib().tbv_cfear_quality_batch(self.h, len(sets), ptrs, _ptr(ns), n, _ptr(ss), _ptr(rs), _ptr(Ts), _ptr(To), _ptr(Tr), C.byref(params),
+                                             _ptr(q)))
+        return q
+
     def RegisterBatch(self, sets, from_set, to_set, T_from, T_to, params: RegParams | None = None):
         """loopclosure::Register for many candidates at once. Returns (T_revised [n,3], T_align [n,3], summaries)."""
         params = params or default_reg_params(max_itr_association=4, max_itr_solver=10)

@@ -1580,4 +1580,61 @@ int tbv_register_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, co
   return TBV_OK;
 }
 
+// CFEARQuality (coral_alignment_quality/src/alignment_checker/AlignmentQuality.cpp:330-352) for a batch of candidate pairs: one
+// GetCost per pair — scans {ref (fixed, pose T_ref), src (pose T_src * T_offset)}, the registration object's itr_ = 0 (search radius
+// radius_), caller's params (the reference: P2L, Huber 0.3, uniform weights) — all pairs in ONE launch of k_register in evaluation mode.
+// quality[p] = {score (problem_->Evaluate's cost), number of residuals, (|src| + |ref|) / 2}; a failed GetCost (<= 1 residual) gives
+// {0, 0, 0} like the reference's else branch.
+int tbv_cfear_quality_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, const int* n_cells, int n_pairs, const int* src_set,
+                            const int* ref_set, const double* T_src, const double* T_offset, const double* T_ref, const tbv_reg_params* params,
+                            double* quality) {
+  TBV_REQUIRE(ctx && sets && n_cells && src_set && ref_set && T_src && T_ref && params && quality && n_sets >= 1 && n_pairs >= 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);
+  if (n_pairs == 0) return TBV_OK;
+  HostProblemSet hs;
+  hs.ctx = ctx;
+  int rc = hs.upload(n_sets, sets, n_cells);
+  if (rc) return rc;
+  std::vector<RegProblem> hp(n_pairs);
+  std::vector<int> hfs(n_pairs);
+  std::vector<double> hfp((size_t)n_pairs * 3);
+  for (int p = 0; p < n_pairs; p++) {
+    TBV_REQUIRE(src_set[p] >= 0 && src_set[p] < n_sets && ref_set[p] >= 0 && ref_set[p] < n_sets, "pair indexes a missing set");
+    hp[p].n_fixed = 1; hp[p].fixed_first = p; hp[p].src_set = src_set[p]; hp[p].active = 1;
+    hfs[p] = ref_set[p];
+    // src->GetAffine() * Toffset, read back as (x, y, yaw) by Affine3dToVectorXYeZ (utils.cpp:115-122)
+    const double* a = T_src + 3 * p;
+    double x = a[0], y = a[1], th = a[2];
+    if (T_offset) {
+      const double* o = T_offset + 3 * p;
+      const double ca = std::cos(a[2]), sa = std::sin(a[2]), co = std::cos(o[2]), so = std::sin(o[2]);
+      x = (ca * o[0] + (-sa) * o[1]) + a[0];
+      y = (sa * o[0] + ca * o[1]) + a[1];
+      th = std::atan2(sa * co + ca * so, sa * (-so) + ca * co);
+    }
+    hp[p].src_pose[0] = x; hp[p].src_pose[1] = y; hp[p].src_pose[2] = th;
+    for (int c = 0; c < 3; c++) hfp[3 * p + c] = T_ref[3 * p + c];
+  }
+  DevBuf<RegProblem> dp; DevBuf<int> dfs; DevBuf<double> dfp, dev_eval; DevBuf<RegResult> dr;
+  auto cleanup = [&]() { dp.release(); dfs.release(); dfp.release(); dev_eval.release(); dr.release(); };
+  if ((rc = to_device(ctx, dp, hp)) || (rc = to_device(ctx, dfs, hfs)) || (rc = to_device(ctx, dfp, hfp)) || (rc = dr.reserve(n_pairs)) ||
+      (rc = dev_eval.reserve((size_t)n_pairs * NACC))) { cleanup(); return rc; }
+  rc = register_launch(ctx, REG_MODE_EVAL, 0, hs.views.p, dp.p, dfs.p, dfp.p, n_pairs, 1, hs.max_n, hs.max_n, to_dev(*params), dr.p, dev_eval.p, false);
+  if (rc) { cleanup(); return rc; }
+  std::vector<RegResult> hr(n_pairs);
+  std::vector<double> ev((size_t)n_pairs * NACC);
+  cudaError_t e = cudaMemcpyAsync(hr.data(), dr.p, n_pairs * sizeof(RegResult), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ev.data(), dev_eval.p, ev.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e != cudaSuccess) { set_error("tbv_cfear_quality_batch: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  for (int p = 0; p < n_pairs; p++) {
+    const bool ok = hr[p].num_residuals > 1;
+    quality[3 * p + 0] = ok ? ev[(size_t)p * NACC] : 0.0;
+    quality[3 * p + 1] = ok ? (double)hr[p].num_residuals : 0.0;
+    quality[3 * p + 2] = ok ? (n_cells[src_set[p]] + n_cells[ref_set[p]]) / 2.0 : 0.0;
+  }
+  return TBV_OK;
+}
+
 }  // extern "C"

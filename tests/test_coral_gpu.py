@@ -90,3 +90,26 @@ def test_coral_capacity_is_reported(ctx):
     big = (np.zeros(5000, np.float32), np.zeros(5000, np.float32), np.zeros(5000, np.float32))
     with pytest.raises(api.TbvError):
         api.CorAlRadarQuality(ctx, [big], [0], [0], np.zeros((1, 3)), np.zeros((1, 3)))
+
+
+def test_verify_candidates_composes_both_batched_kernels(ctx, oracle, stream8, clouds):
+    """verification.verify_candidates: CorAl + CFEAR features of all candidates from two launches -> alignment score -> probability."""
+    from tbv_slam_public_b200 import verification as V
+    cells = []
+    for i in range(4):
+        az, rg, I, x, y = oracle.kstrongest(stream8.scans[i])["filtered"]
+        cells.append(oracle.build_cells(x, y, I.astype(np.float32), radius=3.0, weight_intensity=True)[0])
+    gt = stream8.gt
+    src, ref = [1, 2, 3], [0, 0, 1]
+    Ts, Tr = np.array([gt[s] for s in src]), np.array([gt[r] for r in ref])
+    clf = V.LogisticRegression(-8.42595, [-15.2287, 7.47573, -0.0680198, -1.74182, 0.0945444, 0.022217])
+    p, X, quality = V.verify_candidates(ctx, clouds["peaks"][:4], cells, src, ref, Ts, Tr, sc_sim=[0.1, 0.2, 0.1], odom_bounds=[0.0, 0.0, 0.3],
+                                        alignment_classifier=clf)
+    assert X.shape == (3, 6) and p.shape == (3,) and np.all((p > 0) & (p < 1))
+    for k in range(3):
+        c = oracle.coral_quality(clouds["peaks"][src[k]], clouds["peaks"][ref[k]], Ts[k], Tr[k])
+        n, score, cost, res = oracle.get_cost([cells[ref[k]], cells[src[k]]], [Tr[k], Ts[k]],
+                                              oracle.default_reg_params(cost=oracle.P2L, loss=oracle.HUBER, loss_limit=0.3, weight_opt=oracle.W_UNIFORM), itr=0)
+        want = np.array([c["joint"], c["sep"], c["overlap"], cost, n, (len(cells[src[k]]) + len(cells[ref[k]])) / 2.0])
+        assert np.allclose(X[k], want, rtol=1e-9, atol=1e-8)
+        assert abs(quality[k] - (want @ clf.coef_ + clf.intercept_)) < 1e-6

@@ -174,3 +174,28 @@ def test_cov_from_cost_samples_recovers_a_known_quadric(ctx):
     S[:, 3] = 0.5 * np.einsum("ni,ij,nj->n", d, np.diag([40.0, -25.0, 9e5]), d)
     assert L.tbv_cov_from_cost_samples(S.ctypes.data_as(C.c_void_p), len(S), C.c_double(0.5), C.c_double(4.0), cov.ctypes.data_as(C.c_void_p), C.byref(ok)) == 0
     assert ok.value == 0
+
+
+def test_cfear_quality_batch(ctx, oracle, cellsets):
+    """CFEARQuality (AlignmentQuality.cpp:330-352) for a batch of pairs in one launch == one oracle GetCost per pair (P2L, Huber 0.3,
+    uniform weights, itr_ = 0): score within 1e-12 relative, residual counts exact; a pair too far apart to match gives {0, 0, 0}."""
+    pairs = [(1, 0), (2, 1), (3, 2), (5, 0), (4, 4)]
+    T = {0: (0, 0, 0), 1: (2.5, 0, 0), 2: (5.0, 0.02, 0.001), 3: (7.5, 0.0, 0.0), 4: (10.0, 0, 0), 5: (900.0, 0, 0)}
+    Ts = np.array([T[s] for s, _ in pairs], float); Tr = np.array([T[r] for _, r in pairs], float)
+    To = np.zeros((len(pairs), 3)); To[1] = (0.4, -0.3, 0.02)
+    q = ctx.CFEARQualityBatch(cellsets, [p[0] for p in pairs], [p[1] for p in pairs], Ts, Tr, To)
+    kw = dict(cost=api.P2L, loss=api.HUBER, loss_limit=0.3, weight_opt=api.W_UNIFORM)
+    for k, (s, r) in enumerate(pairs):
+        c, sn = np.cos(Ts[k, 2]), np.sin(Ts[k, 2])
+        A = np.array([[c, -sn, Ts[k, 0]], [sn, c, Ts[k, 1]], [0, 0, 1]])
+        co, so = np.cos(To[k, 2]), np.sin(To[k, 2])
+        B = np.array([[co, -so, To[k, 0]], [so, co, To[k, 1]], [0, 0, 1]])
+        M = A @ B
+        pose = (M[0, 2], M[1, 2], np.arctan2(M[1, 0], M[1, 1]))
+        n, score, cost, res = oracle.get_cost([cellsets[r], cellsets[s]], [Tr[k], pose], oracle.default_reg_params(**kw), itr=0)
+        if n <= 1:
+            assert np.array_equal(q[k], [0, 0, 0])
+        else:
+            assert q[k, 1] == n and q[k, 2] == (len(cellsets[s]) + len(cellsets[r])) / 2.0
+            assert abs(q[k, 0] - cost) <= 1e-12 * abs(cost)
+    assert q[0, 1] > 100 and np.array_equal(q[3], [0, 0, 0])
