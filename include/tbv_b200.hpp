@@ -1,0 +1,188 @@
+// tbv_b200.hpp — C++14 host mirror of the reference's class surface for the hot path, over the C-ABI of tbv_b200.h.
+//
+// The reference calls its hot path through C++ classes.  This header gives the same names, argument meaning and error
+// behaviour on top of libtbv_b200.so, with std containers where the reference uses PCL / Eigen types (neither exists in this image):
+//   StructuredKStrongest   cfear_radarodometry/include/cfear_radarodometry/radar_filters.h:86-110
+//   AzimuthCACFAR          cfear_radarodometry/include/cfear_radarodometry/cfar.h:28-42
+//   MapPointNormal         cfear_radarodometry/include/cfear_radarodometry/pointnormal.h:108-200
+//   n_scan_normal_reg      cfear_radarodometry/include/cfear_radarodometry/n_scan_normal.h:33-75 (Registration, registration.h:76)
+//   OdometryKeyframeFuser  cfear_radarodometry/include/cfear_radarodometry/odometrykeyframefuser.h:90-213 (batched over sequences)
+// A maintainer of the reference replaces the bodies of those classes with these calls; tests/cpp/test_host_mirror.cpp
+// exercises the header against the CPU oracle the way the reference's own tests would.  Header-only; link with -ltbv_b200.
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tbv_b200.h"
+
+namespace tbv_b200 {
+
+struct PointXYZI { float x = 0, y = 0, z = 0, intensity = 0; };   // pcl::PointXYZI
+typedef std::vector<PointXYZI> PointCloud;                        // pcl::PointCloud<pcl::PointXYZI>
+struct Pose2 { double x = 0, y = 0, yaw = 0; };                   // an Eigen::Affine3d of the planar problem, as Affine3dToVectorXYeZ reads it
+typedef std::array<double, 36> Matrix6d;                          // row-major
+
+enum costmetric { P2P = TBV_P2P, P2L = TBV_P2L, P2D = TBV_P2D };                                                  // registration.h:55
+enum losstype { None = TBV_LOSS_NONE, Huber = TBV_LOSS_HUBER, Cauchy = TBV_LOSS_CAUCHY, SoftLOne = TBV_LOSS_SOFTLONE,
+                Combined = TBV_LOSS_COMBINED, Tukey = TBV_LOSS_TUKEY };                                            // registration.h:60
+enum weightoption { Uniform = TBV_W_UNIFORM, Sim_N = TBV_W_SIM_N, Sim_direciton = TBV_W_SIM_DIRECTION, Sim_scale = TBV_W_SIM_SCALE,
+                    Combined_weights = TBV_W_COMBINED };                                                           // registration.h:50
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+inline void check(int rc) { if (rc != TBV_OK) throw Error(rc, tbv_last_error()); }
+
+class Context {   // one GPU context = one stream; distinct contexts may be used from distinct threads (odometry thread + loop thread)
+ public:
+  explicit Context(int device = 0) : h_(tbv_create(device)) { if (!h_) throw Error(TBV_ERR_NO_GPU, tbv_last_error()); }
+  ~Context() { tbv_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  tbv_ctx* get() const { return h_; }
+ private:
+  tbv_ctx* h_;
+};
+
+// radarDriver::Process's k-strongest branch (radar_driver.cpp:57-61): the constructor filters, getPeaksFilteredPointCloud appends the
+// requested cloud.  image: CV_8UC1, rows = azimuths, `step` bytes between rows (cv::Mat::step).
+class StructuredKStrongest {
+ public:
+  StructuredKStrongest(Context& ctx, const uint8_t* image, int rows, int cols, size_t step, int z_min, int k_strongest, double min_distance,
+                       double range_res) {
+    const int cap = rows * k_strongest;
+    for (auto* c : {&f_, &p_}) { c->x.resize(cap); c->y.resize(cap); c->i.resize(cap); }
+    tbv_points f{cap, &f_.n, nullptr, nullptr, f_.i.data(), f_.x.data(), f_.y.data()};
+    tbv_points p{cap, &p_.n, nullptr, nullptr, p_.i.data(), p_.x.data(), p_.y.data()};
+    tbv_filter_params par{(float)z_min, k_strongest, (float)min_distance, (float)range_res};
+    check(tbv_filter_kstrongest(ctx.get(), image, rows, cols, step, 1, &par, &f, &p));
+  }
+  void getPeaksFilteredPointCloud(PointCloud& output_pointcloud, bool peaks = false) const {
+    const Soa& c = peaks ? p_ : f_;
+    for (int k = 0; k < c.n; k++) { PointXYZI q; q.x = c.x[k]; q.y = c.y[k]; q.z = 0; q.intensity = c.i[k]; output_pointcloud.push_back(q); }
+  }
+ private:
+  struct Soa { std::vector<float> x, y; std::vector<uint8_t> i; int n = 0; };
+  Soa f_, p_;
+};
+
+class AzimuthCACFAR {
+ public:
+  AzimuthCACFAR(Context& ctx, int window_size = 40, double false_alarm_rate = 0.01, int nb_guard_cells = 5, double range_resolution = 0.0438,
+                double static_threshold = 60.0, double min_distance = 2.5, double max_distance = 200.0)
+      : ctx_(ctx), par_{window_size, false_alarm_rate, nb_guard_cells, range_resolution, static_threshold, min_distance, max_distance} {}
+  void getFilteredPointCloud(const uint8_t* image, int rows, int cols, size_t step, PointCloud& output_pointcloud) const {
+    const int cap = rows * cols;
+    std::vector<float> x(cap), y(cap);
+    std::vector<uint8_t> I(cap);
+    int n = 0;
+    tbv_points o{cap, &n, nullptr, nullptr, I.data(), x.data(), y.data()};
+    check(tbv_filter_cacfar(ctx_.get(), image, rows, cols, step, 1, &par_, &o));
+    for (int k = 0; k < n; k++) { PointXYZI q; q.x = x[k]; q.y = y[k]; q.intensity = I[k]; output_pointcloud.push_back(q); }
+  }
+ private:
+  Context& ctx_;
+  tbv_cfar_params par_;
+};
+
+// MapPointNormal(cloud, radius, origin, weight_intensity, raw) (pointnormal.h:118): the oriented surface points of a filtered cloud.
+class MapPointNormal {
+ public:
+  static double& downsample_factor() { static double v = 1.0; return v; }   // pointnormal.cpp:5: a static of the reference class as well
+  MapPointNormal(Context& ctx, const PointCloud& cld, float radius, const std::array<double, 2>& origin = {0.0, 0.0}, bool weight_intensity = false) {
+    if (cld.empty()) return;         // the reference exits on an empty cloud (pointnormal.cpp:72-75); here: no cells
+    std::vector<float> x(cld.size()), y(cld.size()), I(cld.size());
+    for (size_t k = 0; k < cld.size(); k++) { x[k] = cld[k].x; y[k] = cld[k].y; I[k] = cld[k].intensity; }
+    cells.resize(cld.size());
+    int n = 0;
+    check(tbv_build_cells(ctx.get(), x.data(), y.data(), I.data(), (int)cld.size(), radius, downsample_factor(), weight_intensity ? 1 : 0, origin.data(),
+                          cells.data(), (int)cells.size(), &n, nullptr));
+    cells.resize(n);
+  }
+  size_t GetSize() const { return cells.size(); }
+  const tbv_cell& GetCell(size_t i) const { return cells[i]; }
+  std::vector<tbv_cell> cells;
+};
+typedef std::shared_ptr<MapPointNormal> MapNormalPtr;
+
+// n_scan_normal_reg (n_scan_normal.h:33-75): scans.back() is the moving scan in its own frame, the others are fixed; Tsrc in/out.
+class n_scan_normal_reg {
+ public:
+  explicit n_scan_normal_reg(Context& ctx, costmetric cost = P2L, losstype loss = Huber, double loss_limit = 0.1, weightoption opt = Uniform)
+      : ctx_(ctx), par_{cost, loss, opt, loss_limit, 1.0, 0.0, 8, 20} {}
+  void SetParameters(unsigned max_itr_association, unsigned max_itr_solver) { par_.max_itr_association = (int)max_itr_association; par_.max_itr_solver = (int)max_itr_solver; }
+  void SetD2dPar(double cov_scale, double regularization) { par_.cov_scale = cov_scale; par_.regularization = regularization; }
+  bool Register(std::vector<MapNormalPtr>& scans, std::vector<Pose2>& Tsrc, std::vector<Matrix6d>* reg_cov = nullptr) {
+    std::vector<const tbv_cell*> ptr; std::vector<int> n; std::vector<double> T;
+    pack(scans, Tsrc, ptr, n, T);
+    check(tbv_register(ctx_.get(), (int)scans.size(), ptr.data(), n.data(), T.data(), &par_, &summary_));
+    for (size_t k = 0; k < Tsrc.size(); k++) Tsrc[k] = Pose2{T[3 * k], T[3 * k + 1], T[3 * k + 2]};
+    itr_ = (size_t)summary_.itrs;
+    score_ = summary_.score;
+    if (reg_cov) {   // n_scan_normal.cpp:171-175: the same fixed covariance for every scan
+      Matrix6d c; c.fill(0.0); c[0] = 0.1 * 0.1; c[7] = 0.1 * 0.1; c[35] = 0.01 * 0.01;
+      reg_cov->assign(scans.size(), c);
+    }
+    return summary_.success != 0;
+  }
+  bool GetCost(std::vector<MapNormalPtr>& scans, std::vector<Pose2>& Tsrc, double& score, std::vector<double>& residuals) {
+    std::vector<const tbv_cell*> ptr; std::vector<int> n; std::vector<double> T;
+    pack(scans, Tsrc, ptr, n, T);
+    const int cap = 2 * n.back() * (int)(scans.size() - 1) + 8;
+    residuals.assign(cap, 0.0);
+    double sc = 0, cost = 0; int nres = 0;
+    check(tbv_get_cost(ctx_.get(), (int)scans.size(), ptr.data(), n.data(), T.data(), &par_, (int)itr_, &sc, &cost, &nres, residuals.data(), cap));
+    residuals.resize(nres > 0 ? nres : 0);
+    if (nres <= 1) return false;    // "too few residuals" (n_scan_normal.cpp:203-206)
+    score = cost;                   // problem_->Evaluate's total cost (:208)
+    score_ = sc;                    // score_ = score / max(residuals, 1) (:209)
+    return true;
+  }
+  double getScore() const { return score_; }
+  bool GetCovarianceScaler(double& cov_scale) const {   // n_scan_normal.cpp:433-439: one free 3-parameter block
+    if (summary_.num_residuals - 3 == 0) return false;
+    cov_scale = summary_.final_cost / (summary_.num_residuals - 3);
+    return true;
+  }
+  tbv_reg_summary summary_{};
+  size_t itr_ = 0;
+ private:
+  static void pack(const std::vector<MapNormalPtr>& scans, const std::vector<Pose2>& Tsrc, std::vector<const tbv_cell*>& ptr, std::vector<int>& n,
+                   std::vector<double>& T) {
+    if (scans.size() != Tsrc.size() || scans.size() < 2) throw Error(TBV_ERR_INVALID, "Register: need >= 2 scans and as many poses");
+    for (size_t k = 0; k < scans.size(); k++) {
+      ptr.push_back(scans[k]->cells.data()); n.push_back((int)scans[k]->cells.size());
+      T.push_back(Tsrc[k].x); T.push_back(Tsrc[k].y); T.push_back(Tsrc[k].yaw);
+    }
+  }
+  Context& ctx_;
+  tbv_reg_params par_;
+  double score_ = 0;
+};
+
+// radarDriver::Process + OdometryKeyframeFuser::processFrame (odometrykeyframefuser.cpp:143-259) for n_seq independent sequences in
+// lock-step: one call = one frame of every sequence (scans back to back in one host buffer); all state stays on the device.
+class OdometryKeyframeFuser {
+ public:
+  OdometryKeyframeFuser(Context& ctx, int n_seq, int n_az, int n_range, const tbv_odom_params& par)
+      : n_seq_(n_seq), h_(tbv_odom_create(ctx.get(), n_seq, n_az, n_range, &par)) { if (!h_) throw Error(TBV_ERR_INVALID, tbv_last_error()); }
+  ~OdometryKeyframeFuser() { tbv_odom_destroy(h_); }
+  OdometryKeyframeFuser(const OdometryKeyframeFuser&) = delete;
+  OdometryKeyframeFuser& operator=(const OdometryKeyframeFuser&) = delete;
+  std::vector<tbv_odom_out> pointcloudCallback(const uint8_t* polar_scans) {
+    std::vector<tbv_odom_out> out(n_seq_);
+    check(tbv_odom_step(h_, polar_scans, out.data()));
+    return out;
+  }
+ private:
+  int n_seq_;
+  tbv_odom* h_;
+};
+
+}  // namespace tbv_b200

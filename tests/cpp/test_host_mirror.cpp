@@ -1,0 +1,133 @@
+// tests/cpp/test_host_mirror.cpp — the C++ host mirror (include/tbv_b200.hpp over libtbv_b200.so) against the CPU oracle, written the
+// way a test of the reference's own classes would read: build the filter, the surface points, register, ask for the cost, run the fuser.
+// TEST INFRASTRUCTURE: includes oracle/ headers as the checker.  Usage: test_host_mirror <scans.bin> <n_scans> <n_az> <n_range>
+// (scans.bin: n_scans x n_az x n_range u8, written by tests/test_cpp_host_gpu.py).  Exit code 0 and a final "PASS" line on success.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "tbv_b200.hpp"
+#include "tbv_oracle.hpp"
+#include "tbv_oracle_reg.hpp"
+
+namespace gpu = tbv_b200;
+namespace cpu = tbv_oracle;
+
+static int g_checks = 0;
+#define EXPECT(cond, ...)                                                        \
+  do {                                                                           \
+    g_checks++;                                                                  \
+    if (!(cond)) { std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); std::exit(1); } \
+  } while (0)
+
+static double ang(double d) { return std::fabs(std::atan2(std::sin(d), std::cos(d))); }
+
+int main(int argc, char** argv) {
+  if (argc < 5) { std::printf("usage: %s scans.bin n_scans n_az n_range\n", argv[0]); return 2; }
+  const int n_scans = std::atoi(argv[2]), n_az = std::atoi(argv[3]), n_range = std::atoi(argv[4]);
+  const size_t scan_bytes = (size_t)n_az * n_range;
+  std::vector<uint8_t> scans(scan_bytes * n_scans);
+  { std::ifstream f(argv[1], std::ios::binary); f.read((char*)scans.data(), (std::streamsize)scans.size()); EXPECT(f.gcount() == (std::streamsize)scans.size(), "short read"); }
+
+  gpu::Context ctx(0);
+  const int z_min = 60, k = 40;
+  const double min_distance = 2.5, range_res = 0.0438;
+  const float radius = 3.0f;
+
+  // ---- radarDriver::Process: both clouds, bit for bit -----------------------------------------------------------------------------
+  std::vector<gpu::MapNormalPtr> g_maps;
+  std::vector<cpu::MapNormalPtr> c_maps;
+  for (int s = 0; s < n_scans; s++) {
+    const uint8_t* img = scans.data() + s * scan_bytes;
+    gpu::StructuredKStrongest filt(ctx, img, n_az, n_range, (size_t)n_range, z_min, k, min_distance, range_res);
+    gpu::PointCloud cloud, peaks;
+    filt.getPeaksFilteredPointCloud(cloud, false);
+    filt.getPeaksFilteredPointCloud(peaks, true);
+    cpu::KStrongestOutput ref;
+    cpu::StructuredKStrongest(img, n_az, n_range, (size_t)n_range, (float)z_min, k, (float)min_distance, (float)range_res, ref, true);
+    EXPECT(cloud.size() == ref.cloud.size() && peaks.size() == ref.cloud_peaks.size(), "scan %d: %zu/%zu points vs %zu/%zu", s, cloud.size(), peaks.size(),
+           ref.cloud.size(), ref.cloud_peaks.size());
+    for (size_t i = 0; i < cloud.size(); i++)
+      EXPECT(std::memcmp(&cloud[i].x, &ref.cloud[i].x, 4) == 0 && std::memcmp(&cloud[i].y, &ref.cloud[i].y, 4) == 0 && cloud[i].intensity == ref.cloud[i].intensity,
+             "scan %d point %zu differs", s, i);
+    for (size_t i = 0; i < peaks.size(); i++)
+      EXPECT(std::memcmp(&peaks[i].x, &ref.cloud_peaks[i].x, 4) == 0 && std::memcmp(&peaks[i].y, &ref.cloud_peaks[i].y, 4) == 0, "scan %d peak %zu differs", s, i);
+
+    // ---- MapPointNormal: same cells in the same order; statistics within the tolerance of DESIGN.md ------------------------------
+    gpu::MapNormalPtr gm(new gpu::MapPointNormal(ctx, cloud, radius, {0.0, 0.0}, true));
+    const double origin[2] = {0, 0};
+    cpu::MapNormalPtr cm(new cpu::MapPointNormal(ref.cloud, radius, origin, true));
+    EXPECT(gm->GetSize() == cm->GetSize() && gm->GetSize() > 50, "scan %d: %zu cells vs %zu", s, gm->GetSize(), cm->GetSize());
+    for (size_t i = 0; i < gm->GetSize(); i++) {
+      const tbv_cell& a = gm->GetCell(i);
+      const cpu::Cell& b = cm->GetCell(i);
+      EXPECT(std::fabs(a.u[0] - b.u[0]) < 1e-10 && std::fabs(a.u[1] - b.u[1]) < 1e-10 && a.n_samples == (double)b.Nsamples, "scan %d cell %zu differs", s, i);
+      EXPECT(std::fabs(a.snormal[0] - b.snormal[0]) < 1e-7 && std::fabs(a.snormal[1] - b.snormal[1]) < 1e-7, "scan %d cell %zu normal differs", s, i);
+    }
+    g_maps.push_back(gm);
+    c_maps.push_back(cm);
+  }
+
+  // ---- n_scan_normal_reg::Register / GetCost: scan s against scans s-1 (and s-2) -----------------------------------------------------
+  for (int s = 1; s < n_scans; s++) {
+    std::vector<gpu::MapNormalPtr> gs;
+    std::vector<cpu::MapNormalPtr> cs;
+    std::vector<gpu::Pose2> gT;
+    std::vector<cpu::Affine2> cT;
+    for (int t = std::max(0, s - 2); t <= s; t++) {
+      gs.push_back(g_maps[t]); cs.push_back(c_maps[t]);
+      const double x = 1.77 * t, y = 1.77 * t, yaw = 0.785 - 0.0001 * t;       // rough poses along the synthetic trajectory; the last is the guess
+      gT.push_back(gpu::Pose2{x, y, yaw}); cT.push_back(cpu::vectorToAffine(x, y, yaw));
+    }
+    gpu::n_scan_normal_reg greg(ctx, gpu::P2L, gpu::Huber, 0.1, gpu::Combined_weights);
+    cpu::n_scan_normal_reg creg(cpu::P2L, cpu::Huber, 0.1, cpu::Combined_weights);
+    std::vector<gpu::Matrix6d> cov;
+    const bool gok = greg.Register(gs, gT, &cov);
+    const bool cok = creg.Register(cs, cT);
+    double cp[3];
+    cpu::AffineToVector(cT.back(), cp);
+    EXPECT(gok == cok && gok, "Register scan %d: success %d vs %d", s, (int)gok, (int)cok);
+    EXPECT(greg.itr_ == creg.itr_, "Register scan %d: %zu association rounds vs %zu", s, greg.itr_, creg.itr_);
+    EXPECT(std::fabs(gT.back().x - cp[0]) < 1e-5 && std::fabs(gT.back().y - cp[1]) < 1e-5 && ang(gT.back().yaw - cp[2]) < 1e-6, "Register scan %d: pose (%.9f %.9f %.9f) vs (%.9f %.9f %.9f)",
+           s, gT.back().x, gT.back().y, gT.back().yaw, cp[0], cp[1], cp[2]);
+    EXPECT(std::fabs(greg.getScore() - creg.getScore()) <= 1e-9 * std::fabs(creg.getScore()), "Register scan %d: score", s);
+    EXPECT(cov.size() == gs.size() && cov[0][0] == 0.1 * 0.1 && cov[0][35] == 0.01 * 0.01, "reg_cov");
+    double gscore = 0, cscore = 0;
+    std::vector<double> gres, cres;
+    EXPECT(greg.GetCost(gs, gT, gscore, gres) && creg.GetCost(cs, cT, cscore, cres), "GetCost scan %d failed", s);
+    EXPECT(gres.size() == cres.size() && std::fabs(gscore - cscore) <= 1e-9 * std::fabs(cscore), "GetCost scan %d: %zu residuals cost %.12g vs %zu, %.12g", s, gres.size(), gscore,
+           cres.size(), cscore);
+    double gsc = 0;
+    EXPECT(greg.GetCovarianceScaler(gsc) && gsc > 0, "GetCovarianceScaler");
+  }
+
+  // ---- OdometryKeyframeFuser: the whole frame loop -----------------------------------------------------------------------------------
+  {
+    tbv_odom_params op;
+    std::memset(&op, 0, sizeof(op));
+    op.filter = tbv_filter_params{(float)z_min, k, (float)min_distance, (float)range_res};
+    op.reg = tbv_reg_params{TBV_P2L, TBV_LOSS_HUBER, TBV_W_COMBINED, 0.1, 1.0, 1.0, 0, 0};
+    op.submap_scan_size = 4; op.weight_intensity = 1; op.use_guess = 1; op.compensate = 1; op.radar_ccw = 0; op.use_keyframe = 1;
+    op.res = 3.0; op.min_keyframe_dist = 1.5; op.min_keyframe_rot_deg = 5.0; op.downsample_factor = 1.0;
+    gpu::OdometryKeyframeFuser gf(ctx, 1, n_az, n_range, op);
+    cpu::FuserParameters fp;
+    fp.cost_type = cpu::P2L; fp.weight_opt = cpu::Combined_weights; fp.submap_scan_size = 4; fp.weight_intensity = true; fp.res = 3.0;
+    fp.loss_type = cpu::Huber; fp.loss_limit = 0.1; fp.covar_scale = 1.0; fp.regularization = 1.0;
+    cpu::OdometryKeyframeFuser cf(fp);
+    for (int s = 0; s < n_scans; s++) {
+      const uint8_t* img = scans.data() + s * scan_bytes;
+      const std::vector<tbv_odom_out> o = gf.pointcloudCallback(img);
+      cpu::KStrongestOutput ref;
+      cpu::StructuredKStrongest(img, n_az, n_range, (size_t)n_range, (float)z_min, k, (float)min_distance, (float)range_res, ref, true);
+      const cpu::Affine2 Tc = cf.processFrame(ref.cloud, &ref.cloud_peaks);
+      double cp[3];
+      cpu::AffineToVector(Tc, cp);
+      EXPECT(o[0].status == TBV_OK, "frame %d status %d", s, o[0].status);
+      EXPECT(std::fabs(o[0].pose[0] - cp[0]) < 1e-5 && std::fabs(o[0].pose[1] - cp[1]) < 1e-5 && ang(o[0].pose[2] - cp[2]) < 1e-6, "fuser frame %d pose (%.9f %.9f %.9f) vs (%.9f %.9f %.9f)", s,
+             o[0].pose[0], o[0].pose[1], o[0].pose[2], cp[0], cp[1], cp[2]);
+    }
+  }
+  std::printf("PASS %d checks (%d scans %dx%d)\n", g_checks, n_scans, n_az, n_range);
+  return 0;
+}
