@@ -112,6 +112,25 @@ def test_dense_short_range_clutter_uses_the_global_point_arrays(ctx, oracle):
     fuser.close()
 
 
+def test_empty_and_nearly_empty_scans_do_not_break_the_pipeline(ctx):
+    """A blank scan (no bin >= z_min) has no points, no cells and nothing to register: the reference exits on an empty cloud
+    (pointnormal.cpp:72-75); the library reports zero counts, keeps the previous pose and carries on with the next frame."""
+    st = synth.make_stream(3)
+    blank = np.zeros((400, 3768), np.uint8)
+    sparse = blank.copy()
+    sparse[10, 500] = 200; sparse[200, 900] = 210          # two points: fewer than any cell needs
+    fuser = api.OdometryKeyframeFuser(ctx, 2, 400, 3768, api.default_odom_params())
+    seq = [np.stack([st.scans[0], st.scans[0]]), np.stack([blank, sparse]), np.stack([st.scans[1], st.scans[1]]), np.stack([st.scans[2], st.scans[2]])]
+    outs = []
+    for b in seq:   # the returned records live in a buffer the next call reuses: copy what is checked
+        outs.append([(o.status, o.n_points, o.n_cells, tuple(o.pose)) for o in fuser.pointcloudCallback(b)])
+    assert all(o[0] == 0 for f in outs for o in f)
+    assert outs[1][0][1:3] == (0, 0) and outs[1][1][1:3] == (2, 0)
+    for s in range(2):
+        assert outs[2][s][2] > 100 and outs[3][s][2] > 100 and np.all(np.isfinite(outs[3][s][3]))
+    fuser.close()
+
+
 def test_pipelined_submit_collect_matches_sync(ctx):
     st = synth.make_stream(6)
     n_seq = 3
