@@ -10,6 +10,7 @@
 // A maintainer of the reference replaces the bodies of those classes with these calls; tests/cpp/test_host_mirror.cpp
 // exercises the header against the CPU oracle the way the reference's own tests would.  Header-only; link with -ltbv_b200.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -184,5 +185,102 @@ class OdometryKeyframeFuser {
   int n_seq_;
   tbv_odom* h_;
 };
+
+// RSCManager (place_recognition_radar/include/place_recognition_radar/RadarScancontext.h:31-131): the keyframe database (descriptors,
+// ring keys, odometry poses) lives on the host, as in the reference; every computation runs on the GPU — the descriptor + keys of the
+// keyframe and its four lateral augmentations in one launch, the ring-key search with the odometry likelihood, and all descriptor
+// distances of the <= 50 (query, candidate) pairs in one launch.  The candidate bookkeeping is the reference's (RadarScancontext.cpp:
+// 286-345: running sort by distance, keep N_CANDIDATES).
+struct candidate {        // RadarScancontext.h: struct candidate
+  double min_dist = 0, min_dist_sc = 0, min_dist_odom = 0;
+  float yaw_diff_rad = 0;
+  int nn_idx = -1, argmin_shift = 0;
+  int aug_idx = 0;        // which query: 0 = the keyframe itself, 1..4 = the lateral offsets of Taug
+  double aug_xy[2] = {0, 0};
+};
+inline tbv_sc_params default_sc_params() {   // TBV-8 offline settings (tbv_slam/src/tbv_slam_offline.cpp:81-101)
+  return tbv_sc_params{40, 120, 80.0, 0.1, 10, 3, 0.05, 1, 1, 0.0, 0, 1000.0, 10.0};
+}
+class RSCManager {
+ public:
+  explicit RSCManager(Context& ctx, const tbv_sc_params& par = default_sc_params()) : ctx_(ctx), par_(par) {}
+  void makeAndSaveScancontextAndKeysRadarCloud(const PointCloud& cloud, const Pose2& Todom) {
+    static const double aug[5][2] = {{0, 0}, {0, -2}, {0, 2}, {0, -4}, {0, 4}};   // RadarScancontext.cpp:162-166 (+ the cloud itself)
+    const int nq = par_.augment_sc ? 5 : 1, R = par_.num_ring, S = par_.num_sector;
+    std::vector<float> x(cloud.size()), y(cloud.size()), I(cloud.size());
+    for (size_t k = 0; k < cloud.size(); k++) { x[k] = cloud[k].x; y[k] = cloud[k].y; I[k] = cloud[k].intensity; }
+    q_desc_.assign((size_t)nq * R * S, 0.0); q_keys_.assign((size_t)nq * R, 0.f); q_off_.assign(&aug[0][0], &aug[0][0] + 2 * nq);
+    check(tbv_sc_make(ctx_.get(), x.data(), y.data(), I.data(), (int)cloud.size(), &par_, nq, q_off_.data(), q_desc_.data(), q_keys_.data(), nullptr));
+    polarcontexts_.insert(polarcontexts_.end(), q_desc_.begin(), q_desc_.begin() + (size_t)R * S);
+    ringkeys_.insert(ringkeys_.end(), q_keys_.begin(), q_keys_.begin() + R);
+    odom_.push_back(Todom.x); odom_.push_back(Todom.y); odom_.push_back(Todom.yaw);
+  }
+  std::vector<candidate> detectLoopClosureID() {
+    std::vector<candidate> similar;
+    const int R = par_.num_ring, S = par_.num_sector, n_db = (int)(ringkeys_.size() / R), nq = (int)(q_keys_.size() / R), want = par_.num_candidates_from_tree;
+    if (n_db == 0) return similar;
+    std::vector<int> cur(nq, n_db - 1), ci((size_t)nq * want), ne(nq);
+    std::vector<double> cs((size_t)nq * want);
+    check(tbv_sc_search(ctx_.get(), ringkeys_.data(), odom_.data(), n_db, nq, q_keys_.data(), cur.data(), &par_, ci.data(), cs.data(), ne.data()));
+    if (n_db < ne[0] + 1) return similar;
+    std::vector<int> pq, pc, uniq;        // (query, candidate) pairs; the candidates' descriptors are gathered once
+    std::vector<double> psim;
+    for (int q = 0; q < nq; q++)
+      for (int t = 0; t < want; t++)
+        if (ci[(size_t)q * want + t] >= 0) { pq.push_back(q); pc.push_back(ci[(size_t)q * want + t]); psim.push_back(cs[(size_t)q * want + t]); }
+    if (pq.empty()) return similar;
+    uniq = pc;
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    std::vector<double> cdesc((size_t)uniq.size() * R * S);
+    for (size_t u = 0; u < uniq.size(); u++) std::copy(polarcontexts_.begin() + (size_t)uniq[u] * R * S, polarcontexts_.begin() + (size_t)(uniq[u] + 1) * R * S, cdesc.begin() + u * R * S);
+    std::vector<int> cpos(pc.size()), shift(pc.size());
+    for (size_t k = 0; k < pc.size(); k++) cpos[k] = (int)(std::lower_bound(uniq.begin(), uniq.end(), pc[k]) - uniq.begin());
+    std::vector<double> dist(pc.size());
+    check(tbv_sc_distance_batch(ctx_.get(), q_desc_.data(), nq, cdesc.data(), (int)uniq.size(), (int)pc.size(), pq.data(), cpos.data(), &par_, dist.data(), shift.data()));
+    const double unit = 360.0 / (double)S;
+    for (size_t k = 0; k < pc.size(); k++) {
+      candidate c;
+      c.min_dist_sc = dist[k];
+      c.min_dist_odom = par_.odometry_coupled_closure ? psim[k] : 0.0;
+      c.min_dist = par_.odometry_coupled_closure ? dist[k] + c.min_dist_odom : dist[k];
+      const float deg = (float)(shift[k] * unit);
+      c.yaw_diff_rad = (float)((double)deg * M_PI / 180.0);
+      c.nn_idx = pc[k]; c.argmin_shift = shift[k]; c.aug_idx = pq[k];
+      c.aug_xy[0] = q_off_[2 * pq[k]]; c.aug_xy[1] = q_off_[2 * pq[k] + 1];
+      similar.push_back(c);
+      std::stable_sort(similar.begin(), similar.end(), [](const candidate& a, const candidate& b) { return a.min_dist < b.min_dist; });
+      if ((int)similar.size() > par_.n_candidates) similar.pop_back();
+    }
+    return similar;
+  }
+  size_t size() const { return odom_.size() / 3; }
+ private:
+  Context& ctx_;
+  tbv_sc_params par_;
+  std::vector<double> polarcontexts_, odom_, q_desc_, q_off_;
+  std::vector<float> ringkeys_, q_keys_;
+};
+
+// CorAlRadarQuality / CFEARQuality for a batch of candidate pairs (coral_alignment_quality/.../AlignmentQuality.cpp:99-229, 330-352):
+// clouds / cell sets are given once and indexed by the pairs; pair p compares src at T_src[p] (* T_offset[p]) with ref at T_ref[p].
+inline std::vector<tbv_coral_result> CorAlRadarQuality(Context& ctx, const std::vector<PointCloud>& clouds, const std::vector<int>& src, const std::vector<int>& ref,
+                                                       const std::vector<Pose2>& T_src, const std::vector<Pose2>& T_ref, double radius = 1.0,
+                                                       bool weight_res_intensity = false) {
+  std::vector<std::vector<float>> x(clouds.size()), y(clouds.size()), I(clouds.size());
+  std::vector<const float*> px, py, pi;
+  std::vector<int> n;
+  for (size_t c = 0; c < clouds.size(); c++) {
+    for (const PointXYZI& q : clouds[c]) { x[c].push_back(q.x); y[c].push_back(q.y); I[c].push_back(q.intensity); }
+    px.push_back(x[c].data()); py.push_back(y[c].data()); pi.push_back(I[c].data()); n.push_back((int)clouds[c].size());
+  }
+  std::vector<double> ts, tr;
+  for (size_t k = 0; k < src.size(); k++) { ts.insert(ts.end(), {T_src[k].x, T_src[k].y, T_src[k].yaw}); tr.insert(tr.end(), {T_ref[k].x, T_ref[k].y, T_ref[k].yaw}); }
+  tbv_coral_params par{radius, weight_res_intensity ? 1 : 0, 1};
+  std::vector<tbv_coral_result> out(src.size());
+  check(tbv_coral_quality_batch(ctx.get(), (int)clouds.size(), px.data(), py.data(), pi.data(), n.data(), (int)src.size(), src.data(), ref.data(), ts.data(), nullptr, tr.data(),
+                                &par, out.data(), nullptr));
+  return out;
+}
 
 }  // namespace tbv_b200

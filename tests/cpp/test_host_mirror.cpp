@@ -10,6 +10,8 @@
 #include "tbv_b200.hpp"
 #include "tbv_oracle.hpp"
 #include "tbv_oracle_reg.hpp"
+#include "tbv_oracle_loop.hpp"
+#include "tbv_oracle_coral.hpp"
 
 namespace gpu = tbv_b200;
 namespace cpu = tbv_oracle;
@@ -126,6 +128,49 @@ int main(int argc, char** argv) {
       EXPECT(o[0].status == TBV_OK, "frame %d status %d", s, o[0].status);
       EXPECT(std::fabs(o[0].pose[0] - cp[0]) < 1e-5 && std::fabs(o[0].pose[1] - cp[1]) < 1e-5 && ang(o[0].pose[2] - cp[2]) < 1e-6, "fuser frame %d pose (%.9f %.9f %.9f) vs (%.9f %.9f %.9f)", s,
              o[0].pose[0], o[0].pose[1], o[0].pose[2], cp[0], cp[1], cp[2]);
+    }
+  }
+  // ---- RSCManager: descriptors + keys per keyframe, loop candidates; CorAl quality of consecutive keyframes ---------------------------
+  {
+    tbv_sc_params sp = gpu::default_sc_params();
+    gpu::RSCManager gsc(ctx, sp);
+    cpu::SCParams cp;
+    cp.N_CANDIDATES = sp.n_candidates; cp.desc_divider = sp.desc_divider; cp.no_point = sp.no_point;
+    cpu::RSCManager csc(cp);
+    std::vector<gpu::PointCloud> gpeaks;
+    std::vector<cpu::Cloud> cpeaks;
+    for (int rep = 0; rep < 12; rep++) {          // the same 4 places visited three times, 30 m of odometry apart: revisits become candidates
+      const int s = rep % n_scans;
+      const uint8_t* img = scans.data() + s * scan_bytes;
+      gpu::StructuredKStrongest filt(ctx, img, n_az, n_range, (size_t)n_range, z_min, k, min_distance, range_res);
+      gpu::PointCloud peaks;
+      filt.getPeaksFilteredPointCloud(peaks, true);
+      cpu::KStrongestOutput ref;
+      cpu::StructuredKStrongest(img, n_az, n_range, (size_t)n_range, (float)z_min, k, (float)min_distance, (float)range_res, ref, true);
+      const double ox = 30.0 * rep, oy = 0.5 * rep, oyaw = 0.01 * rep;
+      gsc.makeAndSaveScancontextAndKeysRadarCloud(peaks, gpu::Pose2{ox, oy, oyaw});
+      csc.makeAndSaveScancontextAndKeysRadarCloud(ref.cloud_peaks, cpu::vectorToAffine(ox, oy, oyaw));
+      const std::vector<gpu::candidate> gc = gsc.detectLoopClosureID();
+      const std::vector<cpu::SCCandidate> cc = csc.detectLoopClosureID();
+      EXPECT(gc.size() == cc.size(), "keyframe %d: %zu candidates vs %zu", rep, gc.size(), cc.size());
+      for (size_t i = 0; i < gc.size(); i++)
+        EXPECT(gc[i].nn_idx == cc[i].nn_idx && gc[i].argmin_shift == cc[i].argmin_shift && gc[i].aug_idx == cc[i].aug_idx &&
+                   std::fabs(gc[i].min_dist - cc[i].min_dist) < 1e-9 && gc[i].yaw_diff_rad == cc[i].yaw_diff_rad,
+               "keyframe %d candidate %zu: (%d, %d, %d, %.12g) vs (%d, %d, %d, %.12g)", rep, i, gc[i].nn_idx, gc[i].argmin_shift, gc[i].aug_idx, gc[i].min_dist,
+               cc[i].nn_idx, cc[i].argmin_shift, cc[i].aug_idx, cc[i].min_dist);
+      if (rep >= 8) EXPECT(!gc.empty(), "keyframe %d: a revisit produced no candidate", rep);
+      if (rep < n_scans) { gpeaks.push_back(peaks); cpeaks.push_back(ref.cloud_peaks); }
+    }
+    std::vector<int> src, refi;
+    std::vector<gpu::Pose2> Ts, Tr;
+    for (int s = 1; s < n_scans; s++) { src.push_back(s); refi.push_back(s - 1); Ts.push_back(gpu::Pose2{1.77 * s, 1.77 * s, 0.785}); Tr.push_back(gpu::Pose2{1.77 * (s - 1), 1.77 * (s - 1), 0.785}); }
+    const std::vector<tbv_coral_result> q = gpu::CorAlRadarQuality(ctx, gpeaks, src, refi, Ts, Tr);
+    for (size_t p = 0; p < src.size(); p++) {
+      const cpu::CoralResult r = cpu::CorAlRadarQuality(cpeaks[src[p]], cpeaks[refi[p]], cpu::vectorToAffine(Ts[p].x, Ts[p].y, Ts[p].yaw),
+                                                        cpu::vectorToAffine(Tr[p].x, Tr[p].y, Tr[p].yaw), cpu::CoralParams());
+      EXPECT(q[p].count_valid == r.count_valid && q[p].merged_size == r.merged_size && q[p].valid == r.valid, "CorAl pair %zu counts", p);
+      EXPECT(std::fabs(q[p].joint - r.joint) < 1e-8 && std::fabs(q[p].sep - r.sep) < 1e-8 && q[p].overlap == r.overlap, "CorAl pair %zu: %.12g %.12g vs %.12g %.12g", p, q[p].joint,
+             q[p].sep, r.joint, r.sep);
     }
   }
   std::printf("PASS %d checks (%d scans %dx%d)\n", g_checks, n_scans, n_az, n_range);
