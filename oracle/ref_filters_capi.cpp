@@ -11,6 +11,7 @@
 
 #include "cfear_radarodometry/cfar.h"
 #include "cfear_radarodometry/radar_filters.h"
+#include "cfear_radarodometry/statistics.h"
 
 namespace {
 cv_bridge::CvImagePtr wrap(const uint8_t* img, int n_az, int n_range, long row_stride) {
@@ -77,6 +78,22 @@ long tbv_ref_kstrongest_many(const uint8_t* imgs, int n_scans, int n_az, int n_r
     total += (long)c0->size() + (long)c1->size();
   }
   return total;
+}
+
+// CFEAR_Radarodometry::statistics (statistics.cpp:10-51), the reference's timing table: Document every (name, value), return
+// GetStatistics().  names: n zero-terminated strings back to back.  Returns the length written (without the terminator).
+int tbv_ref_statistics(const char* names, const double* values, int n, char* out, int cap) {
+  CFEAR_Radarodometry::statistics st;
+  const char* p = names;
+  for (int i = 0; i < n; i++) {
+    st.Document(std::string(p), values[i]);
+    p += std::strlen(p) + 1;
+  }
+  const std::string s = st.GetStatistics();
+  const int len = (int)s.size() < cap - 1 ? (int)s.size() : cap - 1;
+  std::memcpy(out, s.data(), len);
+  out[len] = 0;
+  return len;
 }
 
 }  // extern "C"

@@ -78,3 +78,13 @@ def kstrongest_many(imgs: np.ndarray, z_min=60.0, k=40, min_distance=2.5, range_
     imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
     n, n_az, n_range = imgs.shape
     return int(lib().tbv_ref_kstrongest_many(_p(imgs, C.c_uint8), n, n_az, n_range, C.c_float(z_min), int(k), C.c_float(min_distance), C.c_float(range_res)))
+
+
+def statistics(pairs) -> str:
+    """CFEAR_Radarodometry::statistics: Document every (name, value) of `pairs`, return GetStatistics() (statistics.cpp:40-51)."""
+    names = b"".join(n.encode() + b"\0" for n, _ in pairs)
+    vals = np.ascontiguousarray([v for _, v in pairs], np.float64)
+    out = C.create_string_buffer(1 << 16)
+    lib().tbv_ref_statistics.restype = C.c_int
+    lib().tbv_ref_statistics(names, _p(vals, C.c_double), len(pairs), out, len(out))
+    return out.value.decode()
