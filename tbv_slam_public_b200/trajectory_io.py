@@ -8,6 +8,8 @@ evaluation reads.
   metric : KittiEvalOdom.calc_sequence_errors / compute_overall_err (kitti_odometry.py:197-262): mean translational (fraction) and
            rotational (rad/m) drift over sub-sequences of 100 ... 800 m, the number the reference's papers quote.
 
+  graph  : `graph.txt` (posegraph.cpp:177-187): the same 12 numbers + the node's time stamp, one empty line between nodes.
+
 Host-side Python, no GPU: this is a file format, not a kernel.  `simple_graph.sgh` (a Boost binary archive) is out of scope.
 """
 from __future__ import annotations
@@ -37,6 +39,31 @@ def write_kitti(path: str, poses) -> None:
         for p in poses:
             m = np.asarray(p, float)
             f.write(mat_to_string(m if m.shape == (4, 4) else pose_matrix(m)) + "\n")
+
+
+def write_graph_txt(path: str, poses, stamps_ns) -> None:
+    """PoseGraph::SaveGraphString + RadarScan::ToString (tbv_slam/src/tbv_slam/posegraph.cpp:177-187,
+    cfear_radarodometry/src/cfear_radarodometry/types.cpp:93-102): the 12 pose numbers, the node's stamp (std::to_string of the integer),
+    and — ToString ends its line, SaveGraphString adds another — an empty line after every node."""
+    with open(path, "w") as f:
+        for p, t in zip(poses, stamps_ns):
+            m = np.asarray(p, float)
+            f.write(mat_to_string(m if m.shape == (4, 4) else pose_matrix(m)) + " " + str(int(t)) + "\n\n")
+
+
+def read_graph_txt(path: str):
+    """-> (list of 4x4 poses, list of stamps) from a graph.txt."""
+    poses, stamps = [], []
+    with open(path) as f:
+        for line in f:
+            v = line.strip().split(" ")
+            if len(v) != 13:
+                continue
+            P = np.eye(4)
+            P[:3, :4] = np.asarray([float(t) for t in v[:12]]).reshape(3, 4)
+            poses.append(P)
+            stamps.append(int(v[12]))
+    return poses, stamps
 
 
 def read_kitti(path: str) -> dict:

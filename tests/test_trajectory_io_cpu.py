@@ -73,3 +73,14 @@ def test_against_the_references_own_reader_and_metric(tmp_path):
     assert n == len(err) and n > 100
     assert abs(t - ave_t) < 1e-12 and abs(r - ave_r) < 1e-12
     assert 0.005 < t < 0.05
+
+
+def test_graph_txt_roundtrip(tmp_path):
+    traj = synth.figure8(20)
+    stamps = [1547131046353776000 + 250000000 * i for i in range(20)]
+    p = str(tmp_path / "graph.txt")
+    tio.write_graph_txt(p, traj, stamps)
+    raw = open(p).read().split("\n")
+    assert raw[1] == "" and raw[0].endswith(" 1547131046353776000") and len(raw[0].split(" ")) == 13
+    poses, st = tio.read_graph_txt(p)
+    assert st == stamps and all(np.abs(P - tio.pose_matrix(x)).max() < 5.1e-7 for P, x in zip(poses, traj))
