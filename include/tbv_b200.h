@@ -314,6 +314,18 @@ typedef struct tbv_pgo_params {
 int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, int n_con, const int* ids, const double* meas, const double* info,
                      const tbv_pgo_params* params, int fixed_node, double* cost, double* H_diag, double* H_off, double* g, double* residuals);
 
+/* ---- K8b: one trust-region step of the pose graph on the device (next-row f-2) -------------------------------------------
+ * The linear solve inside ceres::Solve as CeresLeastSquares::SolveOptimizationProblem configures it (tbv_slam/src/tbv_slam/
+ * ceresoptimizer.cpp:50-62: LEVENBERG_MARQUARDT + SPARSE_NORMAL_CHOLESKY, Ceres 2.1.0 is a system dependency, not vendored):
+ * (H + D) delta = -g with D = clamp(diag(H), 1e-6, 1e32) / radius (min_lm_diagonal / max_lm_diagonal), H, g exactly the
+ * tbv_pgo_assemble outputs (H_diag, H_off, g; the fixed node's rows and columns are held at zero).  Solved by conjugate
+ * gradients with the 6x6 block-Jacobi preconditioner in ONE persistent CTA (deterministic reductions) instead of a sparse
+ * Cholesky: delta agrees with the direct solve to rel_tol * |g| in the residual.  delta: [n_nodes][6] tangent step
+ * (p xyz | rotation), applied as p += dp, q = exp(dr) * q (EigenQuaternionParameterization::Plus).
+ * iters / rel_residual (optional): CG iterations used and |b - A delta| / |b| reached.  Stops at max_iters or rel_tol. */
+int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const int* ids, const double* H_diag, const double* H_off, const double* g,
+                       int fixed_node, double radius, int max_iters, double rel_tol, double* delta, int* iters, double* rel_residual);
+
 /* ---- loop-closure keyframe database + sharded candidate registration ---------------------------------------------------
  * The loop-closure thread registers every Scan-Context candidate (from, to) with loopclosure::RegisterLoopCandidate ->
  * loopclosure::Register (tbv_slam/src/tbv_slam/loopclosure.cpp:320-364, 35-97) against cells kept in the pose graph's

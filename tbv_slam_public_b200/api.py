@@ -568,6 +568,8 @@ def _sc_bind():
                                 C.c_void_p, C.c_void_p]
     L.tbv_pgo_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PGOParams), C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tbv_pgo_solve_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                     C.c_double, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L._sc_bound = True
     return L
 
@@ -620,6 +622,120 @@ def pgo_assemble(ctx: Context, nodes, ids, meas, params: PGOParams | None = None
     _check(_sc_bind().tbv_pgo_assemble(ctx.h, n, _ptr(nodes), m, _ptr(ids), _ptr(meas), _ptr(inf), C.byref(params), fixed_node, C.byref(cost),
                                        _ptr(Hd), _ptr(Ho), _ptr(g), _ptr(res)))
     return cost.value, Hd.reshape(n, 6, 6), Ho[:m].reshape(m, 6, 6), g, res[:m]
+
+
+def pgo_solve_step(ctx: Context, ids, H_diag, H_off, g, fixed_node=0, radius=1e4, max_iters=20000, rel_tol=1e-12):
+    """(H + D) delta = -g, D = clamp(diag H, 1e-6, 1e32) / radius: the linear solve of one Ceres LM iteration (ceresoptimizer.cpp:50-62),
+    block-Jacobi PCG on the device. Returns (delta [n, 6], cg_iterations, relative_residual)."""
+    ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+    Hd = np.ascontiguousarray(H_diag, np.float64).reshape(-1, 36)
+    m = len(ids)
+    Ho = np.ascontiguousarray(H_off, np.float64).reshape(-1, 36)[:m]
+    if m == 0:
+        Ho = np.zeros((1, 36))
+    g = np.ascontiguousarray(g, np.float64).reshape(-1, 6)
+    n = len(Hd)
+    if len(g) != n or len(Ho) < m:
+        raise ValueError("H_diag, H_off, g do not describe one graph")
+    delta = np.zeros((n, 6)); it = C.c_int(0); rel = C.c_double(0)
+    _check(_sc_bind().tbv_pgo_solve_step(ctx.h, n, m, _ptr(ids), _ptr(Hd), _ptr(Ho), _ptr(g), fixed_node, float(radius), int(max_iters), float(rel_tol),
+                                         _ptr(delta), C.byref(it), C.byref(rel)))
+    return delta, it.value, rel.value
+
+
+def pgo_plus(nodes, delta):
+    """x (+) delta of the graph's parameter blocks: p += dp; q = exp(dr) * q (ceres::EigenQuaternionParameterization::Plus, q = x y z w)."""
+    nodes = np.array(nodes, np.float64).reshape(-1, 7)
+    delta = np.asarray(delta, np.float64).reshape(-1, 6)
+    out = nodes.copy()
+    out[:, :3] += delta[:, :3]
+    nrm = np.linalg.norm(delta[:, 3:], axis=1)
+    k = np.where(nrm > 0, np.sin(nrm) / np.where(nrm > 0, nrm, 1.0), 1.0)
+    dv, dw = delta[:, 3:] * k[:, None], np.cos(nrm)
+    v, w = nodes[:, 3:6], nodes[:, 6]
+    out[:, 6] = dw * w - np.einsum("ij,ij->i", dv, v)
+    out[:, 3:6] = dw[:, None] * v + w[:, None] * dv + np.cross(dv, v)
+    return out
+
+
+def _pgo_hessian_times(ids, Hd, Ho, x):
+    """H x for the block layout of pgo_assemble (host side: the model-cost term of the step-quality ratio)."""
+    y = np.einsum("nij,nj->ni", Hd, x)
+    if len(ids):
+        a, b = ids[:, 0], ids[:, 1]
+        np.add.at(y, a, np.einsum("cij,cj->ci", Ho, x[b]))
+        np.add.at(y, b, np.einsum("cji,cj->ci", Ho, x[a]))
+    return y
+
+
+class PGOSummary:
+    def __init__(self):
+        self.initial_cost = self.final_cost = 0.0
+        self.iterations, self.successful_steps, self.cg_iterations = 0, 0, 0
+        self.termination = ""
+
+    def __repr__(self):
+        return (f"PGOSummary(initial_cost={self.initial_cost:.6e}, final_cost={self.final_cost:.6e}, iterations={self.iterations}, "
+                f"successful_steps={self.successful_steps}, cg_iterations={self.cg_iterations}, termination={self.termination!r})")
+
+
+def pgo_optimize(ctx: Context, nodes, ids, meas, params: PGOParams | None = None, info=None, fixed_node=0, max_num_iterations=200,
+                 function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8, initial_radius=1e4, cg_rel_tol=1e-10,
+                 cg_max_iters=20000):
+    """CeresLeastSquares::Solve (ceresoptimizer.cpp:13-62): Levenberg-Marquardt over the pose graph, max_num_iterations = 200, every other
+    option the Ceres 2.1.0 default (trust_region_minimizer.cc: initial radius 1e4, accept rho > 1e-3, radius /= max(1/3, 1 - (2 rho - 1)^3) on
+    success, radius /= 2, 4, 8 ... on consecutive failures; stop on |dcost| <= function_tolerance * cost, max |g| <= gradient_tolerance,
+    |step| <= parameter_tolerance * (|x| + parameter_tolerance)).  Evaluation (tbv_pgo_assemble) and the linear solve (tbv_pgo_solve_step)
+    run on the device; this loop is the trust-region bookkeeping only.  Ceres' Jacobi column scaling is not applied, so iterates differ from
+    Ceres' while the fixed point is the same: parity is stated on the optimum, not on the trajectory.  Returns (nodes [n, 7], PGOSummary)."""
+    params = params or default_pgo_params()
+    x = np.array(nodes, np.float64).reshape(-1, 7)
+    ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+    S = PGOSummary()
+    cost, Hd, Ho, g, _ = pgo_assemble(ctx, x, ids, meas, params, info, fixed_node)
+    S.initial_cost = S.final_cost = cost
+    radius, decrease = float(initial_radius), 2.0
+    S.termination = "max_num_iterations"
+    if np.abs(g).max(initial=0.0) <= gradient_tolerance:
+        S.termination = "gradient_tolerance"
+        return x, S
+    for _it in range(max_num_iterations):
+        S.iterations += 1
+        delta, cg_it, _rel = pgo_solve_step(ctx, ids, Hd, Ho, g, fixed_node, radius, cg_max_iters, cg_rel_tol)
+        S.cg_iterations += cg_it
+        model_change = -float(np.sum(delta * (g + 0.5 * _pgo_hessian_times(ids, Hd, Ho, delta))))
+        step_norm, x_norm = float(np.linalg.norm(delta)), float(np.linalg.norm(x))
+        if not np.all(np.isfinite(delta)) or model_change <= 0.0:
+            radius /= decrease; decrease *= 2.0
+            if radius < 1e-32:
+                S.termination = "min_trust_region_radius"
+                break
+            continue
+        if step_norm <= parameter_tolerance * (x_norm + parameter_tolerance):
+            S.termination = "parameter_tolerance"
+            break
+        x_new = pgo_plus(x, delta)
+        cost_new, Hd_n, Ho_n, g_n, _ = pgo_assemble(ctx, x_new, ids, meas, params, info, fixed_node)
+        rho = (cost - cost_new) / model_change
+        if rho > 1e-3:
+            S.successful_steps += 1
+            dcost = cost - cost_new
+            x, cost, Hd, Ho, g = x_new, cost_new, Hd_n, Ho_n, g_n
+            S.final_cost = cost
+            radius = min(radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3), 1e16)
+            decrease = 2.0
+            if np.abs(g).max(initial=0.0) <= gradient_tolerance:
+                S.termination = "gradient_tolerance"
+                break
+            if abs(dcost) <= function_tolerance * cost:
+                S.termination = "function_tolerance"
+                break
+        else:
+            radius /= decrease; decrease *= 2.0
+            if radius < 1e-32:
+                S.termination = "min_trust_region_radius"
+                break
+    return x, S
 
 
 class RSCManager:

@@ -217,6 +217,156 @@ pgo_cost(int n_con, const int* __restrict__ order, const double* __restrict__ re
   if (threadIdx.x == 0) *cost = s[0];
 }
 
+// ---- one Levenberg-Marquardt step of the pose graph on the device (first part) ------------------------------------------
+// Solves (H + D) delta = -g for the block-sparse normal equations tbv_pgo_assemble produces (H_diag: 6x6 per node, H_off: block
+// (begin, end) per constraint, symmetric), D = clamp(diag(H), 1e-6, 1e32) / radius — the system Ceres' LEVENBERG_MARQUARDT strategy
+// hands to SPARSE_NORMAL_CHOLESKY (ceresoptimizer.cpp:50-62) — by conjugate gradients with the 6x6 block-Jacobi preconditioner.
+// ONE persistent CTA: the graph is small (4.5 k nodes, 27 k unknowns, 1.4 MB of blocks: L2-resident), an iteration is a block-sparse
+// product plus two dot products, and keeping it in one CTA makes every reduction a fixed-shape tree (deterministic) with no grid sync.
+constexpr int PCG_THREADS = 1024;
+
+__device__ __forceinline__ double pcg_block_sum(double v, double* s_w) {  // fixed tree: lanes, then the 32 warp totals in order
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();            // s_w may still be read from the previous reduction
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < PCG_THREADS / 32; w++) t += s_w[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+pgo_pcg(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
+        const double* __restrict__ Ho, const double* __restrict__ g, double radius, int max_iters, double rel_tol, double* __restrict__ x,
+        double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q, double* __restrict__ Minv, double* __restrict__ Dg,
+        int* __restrict__ out_iters, double* __restrict__ out_rel) {
+  __shared__ double s_w[PCG_THREADS / 32];
+  const int tid = threadIdx.x;
+  // ---- damped diagonal blocks and their inverses (Cholesky of the SPD 6x6, then L^-T L^-1) ------------------------------------------
+  for (int i = tid; i < n; i += PCG_THREADS) {
+    double A[6][6], L[6][6], Li[6][6];
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b < 6; b++) A[a][b] = Hd[36 * (size_t)i + a * 6 + b];
+    bool ok = i != fixed_node;
+    for (int a = 0; a < 6; a++) {
+      const double d = fmin(fmax(A[a][a], 1e-6), 1e32) / radius;
+      Dg[6 * (size_t)i + a] = d;
+      A[a][a] += d;
+    }
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b < 6; b++) { L[a][b] = 0.0; Li[a][b] = 0.0; }
+    for (int j = 0; j < 6 && ok; j++) {
+      double d = A[j][j];
+      for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+      if (!(d > 0.0)) { ok = false; break; }
+      L[j][j] = sqrt(d);
+      for (int a = j + 1; a < 6; a++) {
+        double v = A[a][j];
+        for (int k = 0; k < j; k++) v -= L[a][k] * L[j][k];
+        L[a][j] = v / L[j][j];
+      }
+    }
+    if (ok) {
+      for (int c = 0; c < 6; c++) {            // Li = L^-1 by forward substitution on the identity
+        for (int a = 0; a < 6; a++) {
+          double v = (a == c) ? 1.0 : 0.0;
+          for (int k = 0; k < a; k++) v -= L[a][k] * Li[k][c];
+          Li[a][c] = v / L[a][a];
+        }
+      }
+    }
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b < 6; b++) {
+        double v = 0.0;
+        if (ok) for (int k = 0; k < 6; k++) v += Li[k][a] * Li[k][b];   // (L L^T)^-1 = L^-T L^-1
+        Minv[36 * (size_t)i + a * 6 + b] = v;
+      }
+  }
+  __syncthreads();
+  auto apply_Minv = [&](const double* v, double* o) {
+    for (int i = tid; i < n; i += PCG_THREADS) {
+      double t[6];
+      for (int a = 0; a < 6; a++) t[a] = v[6 * (size_t)i + a];
+      for (int a = 0; a < 6; a++) {
+        double acc = 0.0;
+        for (int b = 0; b < 6; b++) acc += Minv[36 * (size_t)i + a * 6 + b] * t[b];
+        o[6 * (size_t)i + a] = acc;
+      }
+    }
+  };
+  // q = (H + D) v: the node's own block, then its constraints in the order of `inc` (side 0: this node begins the constraint -> H_off v_end;
+  // side 1: it ends it -> H_off^T v_begin)
+  auto apply_A = [&](const double* v, double* o) {
+    for (int i = tid; i < n; i += PCG_THREADS) {
+      double acc[6] = {0, 0, 0, 0, 0, 0};
+      if (i != fixed_node) {
+        double t[6];
+        for (int a = 0; a < 6; a++) t[a] = v[6 * (size_t)i + a];
+        for (int a = 0; a < 6; a++) {
+          double s0 = Dg[6 * (size_t)i + a] * t[a];
+          for (int b = 0; b < 6; b++) s0 += Hd[36 * (size_t)i + a * 6 + b] * t[b];
+          acc[a] = s0;
+        }
+        for (int e = row[i]; e < row[i + 1]; e++) {
+          const int c = inc[e] >> 1, side = inc[e] & 1;
+          const int other = side ? ids[3 * c] : ids[3 * c + 1];
+          const double* B = Ho + 36 * (size_t)c;
+          double u[6];
+          for (int a = 0; a < 6; a++) u[a] = v[6 * (size_t)other + a];
+          if (side == 0) { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[a * 6 + b] * u[b]; }
+          else           { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[b * 6 + a] * u[b]; }
+        }
+      }
+      for (int a = 0; a < 6; a++) o[6 * (size_t)i + a] = acc[a];
+    }
+  };
+  auto dot = [&](const double* u, const double* v) {
+    double acc = 0.0;
+    for (int i = tid; i < n; i += PCG_THREADS)
+      for (int a = 0; a < 6; a++) acc += u[6 * (size_t)i + a] * v[6 * (size_t)i + a];
+    return pcg_block_sum(acc, s_w);
+  };
+  // ---- x = 0, r = b = -g (the fixed node's rows are zero), z = M^-1 r, p = z ---------------------------------------------------------
+  for (int i = tid; i < n; i += PCG_THREADS)
+    for (int a = 0; a < 6; a++) {
+      x[6 * (size_t)i + a] = 0.0;
+      r[6 * (size_t)i + a] = (i == fixed_node) ? 0.0 : -g[6 * (size_t)i + a];
+    }
+  __syncthreads();
+  apply_Minv(r, z);
+  for (int i = tid; i < n; i += PCG_THREADS)
+    for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a];   // own elements only: no barrier needed before
+  __syncthreads();
+  double rz = dot(r, z);
+  const double bnorm = sqrt(dot(r, r));
+  double rel = bnorm > 0.0 ? 1.0 : 0.0;
+  int it = 0;
+  while (it < max_iters && rel > rel_tol) {
+    apply_A(p, q);
+    __syncthreads();
+    const double pq = dot(p, q);
+    if (!(pq > 0.0)) break;                      // lost positive definiteness (never with D > 0): stop with what we have
+    const double alpha = rz / pq;
+    for (int i = tid; i < n; i += PCG_THREADS)
+      for (int a = 0; a < 6; a++) {
+        x[6 * (size_t)i + a] += alpha * p[6 * (size_t)i + a];
+        r[6 * (size_t)i + a] -= alpha * q[6 * (size_t)i + a];
+      }
+    apply_Minv(r, z);                            // own elements of r: written by this thread just above
+    __syncthreads();
+    const double rz_new = dot(r, z);
+    rel = sqrt(dot(r, r)) / bnorm;
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    for (int i = tid; i < n; i += PCG_THREADS)
+      for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a] + beta * p[6 * (size_t)i + a];
+    __syncthreads();
+    it++;
+  }
+  if (tid == 0) { *out_iters = it; *out_rel = rel; }
+}
+
 }  // namespace tbv
 
 using namespace tbv;
@@ -286,5 +436,59 @@ extern "C" int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, 
   if (e != cudaSuccess) { set_error("tbv_pgo_assemble: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
   if (herr) { set_error("tbv_pgo_assemble: an information matrix is not positive definite"); return TBV_ERR_INVALID; }
   if (cost) *cost = hcost;
+  return TBV_OK;
+}
+
+
+extern "C" int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const int* ids, const double* H_diag, const double* H_off, const double* g,
+                                  int fixed_node, double radius, int max_iters, double rel_tol, double* delta, int* iters, double* rel_residual) {
+  TBV_REQUIRE(ctx && ids && H_diag && H_off && g && delta && n_nodes >= 1 && n_con >= 0 && radius > 0 && max_iters >= 0, "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
+  for (int c = 0; c < n_con; c++)
+    TBV_REQUIRE(ids[3 * c] >= 0 && ids[3 * c] < n_nodes && ids[3 * c + 1] >= 0 && ids[3 * c + 1] < n_nodes, "constraint references a missing node");
+  std::vector<int> row(n_nodes + 1, 0), inc(2 * (size_t)n_con + 1);
+  for (int c = 0; c < n_con; c++) { row[ids[3 * c] + 1]++; row[ids[3 * c + 1] + 1]++; }
+  for (int i = 0; i < n_nodes; i++) row[i + 1] += row[i];
+  {
+    std::vector<int> fill(row.begin(), row.end() - 1);
+    for (int c = 0; c < n_con; c++) { inc[fill[ids[3 * c]]++] = (c << 1); inc[fill[ids[3 * c + 1]]++] = (c << 1) | 1; }
+  }
+  const size_t N6 = 6 * (size_t)n_nodes, nc1 = n_con ? n_con : 1;
+  DevBuf<double> dhd, dho, dg, dx, dr, dz, dp, dq, dmi, ddg, drel;
+  DevBuf<int> dids, drow, dinc, dit;
+  auto cleanup = [&]() {
+    dhd.release(); dho.release(); dg.release(); dx.release(); dr.release(); dz.release(); dp.release(); dq.release(); dmi.release(); ddg.release();
+    drel.release(); dids.release(); drow.release(); dinc.release(); dit.release();
+  };
+  int rc;
+  if ((rc = dhd.reserve(36 * (size_t)n_nodes)) || (rc = dho.reserve(36 * nc1)) || (rc = dg.reserve(N6)) || (rc = dx.reserve(N6)) || (rc = dr.reserve(N6)) ||
+      (rc = dz.reserve(N6)) || (rc = dp.reserve(N6)) || (rc = dq.reserve(N6)) || (rc = dmi.reserve(36 * (size_t)n_nodes)) || (rc = ddg.reserve(N6)) ||
+      (rc = drel.reserve(1)) || (rc = dids.reserve(3 * nc1)) || (rc = drow.reserve(n_nodes + 1)) || (rc = dinc.reserve(inc.size())) || (rc = dit.reserve(1))) {
+    cleanup();
+    return rc;
+  }
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaMemcpyAsync(dhd.p, H_diag, 36 * (size_t)n_nodes * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dho.p, H_off, 36 * (size_t)n_con * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dg.p, g, N6 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dids.p, ids, 3 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(drow.p, row.data(), (n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dinc.p, inc.data(), 2 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    pgo_pcg<<<1, PCG_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p, dz.p, dp.p,
+                                        dq.p, dmi.p, ddg.p, dit.p, drel.p);
+    launched(ctx, "pgo_pcg");
+    e = cudaGetLastError();
+  }
+  int h_it = 0;
+  double h_rel = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(delta, dx.p, N6 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_it, dit.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_rel, drel.p, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) { set_error("tbv_pgo_solve_step: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  if (iters) *iters = h_it;
+  if (rel_residual) *rel_residual = h_rel;
   return TBV_OK;
 }

@@ -88,6 +88,18 @@ def main():
     w, k = timed(ctx, lambda: api.pgo_assemble(ctx, nodes, ids, meas), reps=3)
     c = cpu(lambda: o.pgo_assemble(nodes, ids, meas), reps=2)
     out["pgo_assemble (%d nodes, %d constraints)" % (len(nodes), len(ids))] = {"call_ms": w, "kernel_ms": sum(k.values()), "oracle_ms": c}
+    # K8b: one LM step solve on the same graph (block-Jacobi PCG in one CTA) and the whole LM run
+    _, Hd, Ho, g, _ = api.pgo_assemble(ctx, nodes, ids, meas)
+    info = {}
+    def step():
+        info["r"] = api.pgo_solve_step(ctx, ids, Hd, Ho, g, radius=1e4, rel_tol=1e-10)
+    w, k = timed(ctx, step, reps=3)
+    out["pgo_solve_step (%d nodes, rel_tol 1e-10, %d CG iterations)" % (len(nodes), info["r"][1])] = {"call_ms": w, "kernel_ms": sum(k.values())}
+    import time as _t
+    t0 = _t.perf_counter()
+    _, S = api.pgo_optimize(ctx, nodes, ids, meas)
+    out["pgo_optimize (%d nodes, Ceres default tolerances, %d LM iterations, %d CG iterations, %s)" % (
+        len(nodes), S.iterations, S.cg_iterations, S.termination)] = {"call_ms": 1e3 * (_t.perf_counter() - t0), "cost_ratio": S.final_cost / S.initial_cost}
     # K1b: CA-CFAR on one Oxford scan
     w, k = timed(ctx, lambda: ctx.AzimuthCACFAR(st.scans[0], window_size=40, nb_guard_cells=10, capacity=65536))
     c = cpu(lambda: o.cacfar(st.scans[0], 40, 0.01, 10), reps=2)
