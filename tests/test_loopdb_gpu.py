@@ -1,6 +1,6 @@
 """Loop-closure keyframe database (tbv_loopdb_*): batched RegisterLoopCandidate vs the oracle's loopclosure::Register, the
 constraint records, and the sharded front end (world size 1 here; world size 2 is covered on CPU with gloo in
-test_parallel_cpu.py and on 2 GPUs with NCCL by tools/loop_bench.py).
+test_parallel_cpu.py and on 2 GPUs with NCCL by tests/tools/loop_bench.py).
 
 Bar: accept/reject decisions and iteration counts identical; Talign / Trevised within 1e-5 m / 1e-6 rad (north_star).
 """

@@ -1,7 +1,7 @@
 """CorAl quality over a batch of candidate pairs: kernel time (run under ncu for the exact figure) and the oracle's per-pair time."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tbv_slam_public_b200 import api, synth
 from oracle import oracle_py as o
 

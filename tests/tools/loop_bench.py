@@ -1,8 +1,8 @@
 """BASELINE configs[2] / [4]: batched loop-closure candidate registration (256 scan pairs per iteration by default), on 1 GPU
 or sharded over N GPUs with the accepted constraints all-gathered over NCCL (tbv_slam_public_b200/parallel.py).
 
-  python tools/loop_bench.py [--pairs 256] [--iters 20] [--keyframes 64]
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/loop_bench.py --pairs 1024
+  python tests/tools/loop_bench.py [--pairs 256] [--iters 20] [--keyframes 64]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/tools/loop_bench.py --pairs 1024
 
 Keyframes: consecutive frames of the synthetic Oxford-shape stream, filtered (k=40, z_min=60) and turned into cells on the
 GPU.  Candidates: (from, to) with |from - to| <= 3 (overlapping views, like a revisit), `to` placed at its true pose and
@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tbv_slam_public_b200 import api, parallel, synth  # noqa: E402
 
 
