@@ -283,4 +283,159 @@ inline std::vector<tbv_coral_result> CorAlRadarQuality(Context& ctx, const std::
   return out;
 }
 
+// ---- CeresLeastSquares (tbv_slam/include/tbv_slam/ceresoptimizer.h:25-49, tbv_slam/src/tbv_slam/ceresoptimizer.cpp:13-62) ----------------------------
+// Solve() = BuildOptimizationProblem + ceres::Solve(LEVENBERG_MARQUARDT, SPARSE_NORMAL_CHOLESKY, max_num_iterations 200), in place on the node
+// poses.  Evaluation (tbv_pgo_assemble) and the damped linear solve (tbv_pgo_solve_step) run on the device; this class is the trust-region
+// bookkeeping of Ceres 2.1.0's TrustRegionMinimizer with its default options (initial radius 1e4, accept rho > 1e-3, radius update by
+// max(1/3, 1 - (2 rho - 1)^3), halving / quartering / ... on consecutive rejections, function / gradient / parameter tolerances 1e-6 / 1e-10 / 1e-8).
+// Ceres' Jacobi column scaling is not applied: same fixed point, different iterates.  The backend is a template parameter so that the loop can
+// be exercised without a GPU (tests/cpp/test_pgo_host.cpp plugs the oracle in); the product type is CeresLeastSquares = ...<DevicePoseGraph>.
+struct Pose3d {                                   // types.h:46-81, q stored (x, y, z, w) like Eigen::Quaterniond::coeffs()
+  double p[3] = {0, 0, 0};
+  double q[4] = {0, 0, 0, 1};
+};
+struct Constraint3d {                             // types.h:155-190 (members the optimiser reads)
+  unsigned long id_begin = 0, id_end = 0;         // ROW of the node in the vector handed to the optimiser
+  Pose3d t_be;
+  Matrix6d information{};                         // used when replace_cov_by_identity == 0
+  int type = 0;                                   // 0 odometry, 1 loop_appearance; others are not optimised (ceresoptimizer.cpp:34-35)
+};
+inline tbv_pgo_params default_pgo_params() { return tbv_pgo_params{0.01, 0.01, 0.001, 500000.0, 1, 0.1}; }   // ceresoptimizer.cpp:18-27
+
+struct DevicePoseGraph {                          // the two device calls
+  Context* ctx;
+  explicit DevicePoseGraph(Context& c) : ctx(&c) {}
+  void assemble(int n, const double* nodes, int m, const int* ids, const double* meas, const double* info, const tbv_pgo_params& par, int fixed,
+                double* cost, double* Hd, double* Ho, double* g) const {
+    check(tbv_pgo_assemble(ctx->get(), n, nodes, m, ids, meas, info, &par, fixed, cost, Hd, Ho, g, nullptr));
+  }
+  void solve(int n, int m, const int* ids, const double* Hd, const double* Ho, const double* g, int fixed, double radius, int max_iters, double rel_tol,
+             double* delta, int* iters) const {
+    check(tbv_pgo_solve_step(ctx->get(), n, m, ids, Hd, Ho, g, fixed, radius, max_iters, rel_tol, delta, iters, nullptr));
+  }
+};
+
+template <class Backend>
+class CeresLeastSquaresT {
+ public:
+  struct Options {                                // ceres::Solver::Options defaults except max_num_iterations (ceresoptimizer.cpp:53)
+    int max_num_iterations = 200;
+    double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+    double initial_trust_region_radius = 1e4, max_trust_region_radius = 1e16, min_trust_region_radius = 1e-32, min_relative_decrease = 1e-3;
+    int cg_max_iterations = 20000;
+    double cg_relative_tolerance = 1e-10;
+  };
+  struct Summary {
+    double initial_cost = 0, final_cost = 0;
+    int iterations = 0, num_successful_steps = 0, cg_iterations = 0;
+    std::string termination = "max_num_iterations";   // NO_CONVERGENCE in Ceres' words; the others are CONVERGENCE
+    bool IsSolutionUsable() const { return termination != "min_trust_region_radius"; }
+  };
+
+  CeresLeastSquaresT(Backend backend, std::vector<Pose3d>& nodes, const std::vector<Constraint3d>& constraints,
+                     const tbv_pgo_params& par = default_pgo_params(), int fixed_node = 0)
+      : be_(backend), nodes_(nodes), par_(par), fixed_(fixed_node) {
+    for (const Constraint3d& c : constraints) {
+      if (c.type != 0 && c.type != 1) continue;
+      if (c.id_begin >= nodes.size() || c.id_end >= nodes.size()) throw Error(TBV_ERR_INVALID, "constraint references a missing node");
+      ids_.insert(ids_.end(), {(int)c.id_begin, (int)c.id_end, c.type});
+      meas_.insert(meas_.end(), c.t_be.p, c.t_be.p + 3);
+      meas_.insert(meas_.end(), c.t_be.q, c.t_be.q + 4);
+      info_.insert(info_.end(), c.information.begin(), c.information.end());
+    }
+  }
+  Options options;
+  Summary summary_;
+
+  // x (+) delta: p += dp, q = exp(dr) * q  (ceres::EigenQuaternionParameterization::Plus)
+  static void Plus(const double* x, const double* d, double* out) {
+    for (int k = 0; k < 3; k++) out[k] = x[k] + d[k];
+    const double n = std::sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+    const double s = n > 0.0 ? std::sin(n) / n : 1.0, dw = std::cos(n);
+    const double dx = s * d[3], dy = s * d[4], dz = s * d[5];
+    const double qx = x[3], qy = x[4], qz = x[5], qw = x[6];
+    out[3] = dw * qx + qw * dx + (dy * qz - dz * qy);
+    out[4] = dw * qy + qw * dy + (dz * qx - dx * qz);
+    out[5] = dw * qz + qw * dz + (dx * qy - dy * qx);
+    out[6] = dw * qw - (dx * qx + dy * qy + dz * qz);
+  }
+
+  void Solve() {
+    const int n = (int)nodes_.size(), m = (int)(ids_.size() / 3);
+    Summary S;
+    std::vector<double> x(7 * (size_t)n), xc(7 * (size_t)n), Hd(36 * (size_t)n), Ho(36 * (size_t)std::max(m, 1)), g(6 * (size_t)n), Hdc(Hd.size()),
+        Hoc(Ho.size()), gc(g.size()), delta(6 * (size_t)n), Hx(6 * (size_t)n);
+    for (int i = 0; i < n; i++) { std::copy(nodes_[i].p, nodes_[i].p + 3, &x[7 * i]); std::copy(nodes_[i].q, nodes_[i].q + 4, &x[7 * i + 3]); }
+    const double* info = par_.replace_cov_by_identity ? nullptr : info_.data();
+    double cost = 0;
+    be_.assemble(n, x.data(), m, ids_.data(), meas_.data(), info, par_, fixed_, &cost, Hd.data(), Ho.data(), g.data());
+    S.initial_cost = S.final_cost = cost;
+    auto max_abs = [](const std::vector<double>& v) { double a = 0; for (double e : v) a = std::max(a, std::fabs(e)); return a; };
+    auto norm = [](const std::vector<double>& v) { double a = 0; for (double e : v) a += e * e; return std::sqrt(a); };
+    double radius = options.initial_trust_region_radius, decrease = 2.0;
+    if (max_abs(g) <= options.gradient_tolerance) S.termination = "gradient_tolerance";
+    else
+      for (int it = 0; it < options.max_num_iterations; it++) {
+        S.iterations++;
+        int cg = 0;
+        be_.solve(n, m, ids_.data(), Hd.data(), Ho.data(), g.data(), fixed_, radius, options.cg_max_iterations, options.cg_relative_tolerance, delta.data(), &cg);
+        S.cg_iterations += cg;
+        // model_cost_change = -delta^T (g + H delta / 2), H in the block layout of tbv_pgo_assemble
+        for (int i = 0; i < n; i++)
+          for (int a = 0; a < 6; a++) {
+            double acc = 0;
+            for (int b = 0; b < 6; b++) acc += Hd[36 * (size_t)i + 6 * a + b] * delta[6 * (size_t)i + b];
+            Hx[6 * (size_t)i + a] = acc;
+          }
+        for (int c = 0; c < m; c++) {
+          const int ia = ids_[3 * c], ib = ids_[3 * c + 1];
+          const double* B = &Ho[36 * (size_t)c];
+          for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++) {
+              Hx[6 * (size_t)ia + a] += B[6 * a + b] * delta[6 * (size_t)ib + b];
+              Hx[6 * (size_t)ib + a] += B[6 * b + a] * delta[6 * (size_t)ia + b];
+            }
+        }
+        double model_change = 0;
+        bool finite = true;
+        for (size_t k = 0; k < delta.size(); k++) { model_change -= delta[k] * (g[k] + 0.5 * Hx[k]); finite = finite && std::isfinite(delta[k]); }
+        auto reject = [&]() { radius /= decrease; decrease *= 2.0; return radius < options.min_trust_region_radius; };
+        if (!finite || !(model_change > 0.0)) {
+          if (reject()) { S.termination = "min_trust_region_radius"; break; }
+          continue;
+        }
+        if (norm(delta) <= options.parameter_tolerance * (norm(x) + options.parameter_tolerance)) { S.termination = "parameter_tolerance"; break; }
+        for (int i = 0; i < n; i++) Plus(&x[7 * (size_t)i], &delta[6 * (size_t)i], &xc[7 * (size_t)i]);
+        double cost_c = 0;
+        be_.assemble(n, xc.data(), m, ids_.data(), meas_.data(), info, par_, fixed_, &cost_c, Hdc.data(), Hoc.data(), gc.data());
+        const double rho = (cost - cost_c) / model_change;
+        if (rho > options.min_relative_decrease) {
+          const double dcost = cost - cost_c;
+          S.num_successful_steps++;
+          x.swap(xc); Hd.swap(Hdc); Ho.swap(Hoc); g.swap(gc);
+          cost = S.final_cost = cost_c;
+          const double t = 2.0 * rho - 1.0;
+          radius = std::min(radius / std::max(1.0 / 3.0, 1.0 - t * t * t), options.max_trust_region_radius);
+          decrease = 2.0;
+          if (max_abs(g) <= options.gradient_tolerance) { S.termination = "gradient_tolerance"; break; }
+          if (std::fabs(dcost) <= options.function_tolerance * cost) { S.termination = "function_tolerance"; break; }
+        } else if (reject()) {
+          S.termination = "min_trust_region_radius";
+          break;
+        }
+      }
+    for (int i = 0; i < n; i++) { std::copy(&x[7 * i], &x[7 * i] + 3, nodes_[i].p); std::copy(&x[7 * i + 3], &x[7 * i] + 7, nodes_[i].q); }
+    summary_ = S;
+  }
+
+ private:
+  Backend be_;
+  std::vector<Pose3d>& nodes_;
+  tbv_pgo_params par_;
+  int fixed_;
+  std::vector<int> ids_;
+  std::vector<double> meas_, info_;
+};
+typedef CeresLeastSquaresT<DevicePoseGraph> CeresLeastSquares;
+
 }  // namespace tbv_b200

@@ -25,7 +25,9 @@ def build_cpp_test() -> str:
 def test_cpp_header_compiles_as_cxx14(tmp_path):
     """The mirror is header-only C++14 (the reference's dialect, cfear_radarodometry/CMakeLists.txt:4): syntax check without linking."""
     tu = tmp_path / "tu.cpp"
-    tu.write_text('#include "tbv_b200.hpp"\nint main() { return sizeof(tbv_b200::n_scan_normal_reg) > 0 ? 0 : 1; }\n')
+    tu.write_text('#include "tbv_b200.hpp"\n'
+                  'template class tbv_b200::CeresLeastSquaresT<tbv_b200::DevicePoseGraph>;   // every member of the device-backed optimiser\n'
+                  'int main() { return sizeof(tbv_b200::n_scan_normal_reg) > 0 ? 0 : 1; }\n')
     subprocess.check_call(["g++", "-std=c++14", "-Wall", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(tu)])
 
 
