@@ -84,3 +84,43 @@ def test_graph_txt_roundtrip(tmp_path):
     assert raw[1] == "" and raw[0].endswith(" 1547131046353776000") and len(raw[0].split(" ")) == 13
     poses, st = tio.read_graph_txt(p)
     assert st == stamps and all(np.abs(P - tio.pose_matrix(x)).max() < 5.1e-7 for P, x in zip(poses, traj))
+
+
+@pytest.mark.parametrize("alignment", [None, "6dof", "7dof"])
+def test_evaluate_matches_the_references_numbers(tmp_path, alignment):
+    """trajectory_io.evaluate against tests/golden/eval_ref.json — numbers the reference's own kitti_odometry.py produced for the same two
+    pose files (tests/golden/make_eval_golden.py; the files are rewritten here from the same seed). Tolerance 1e-9 relative: the two
+    implementations differ only in summation order."""
+    import json
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    try:
+        import make_eval_golden as M
+    finally:
+        sys.path.pop(0)
+    gt, est = M.trajectories()
+    pg, pe = str(tmp_path / "gt.txt"), str(tmp_path / "est.txt")
+    tio.write_kitti(pg, gt)
+    tio.write_kitti(pe, est)
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "eval_ref.json")))[alignment or "none"]
+    got = tio.evaluate(tio.read_kitti(pg), tio.read_kitti(pe), alignment)
+    assert got["n_segments"] == want["n_segments"]
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-9 * max(abs(v), 1e-3), (k, got[k], v)
+    if os.path.isdir(REF_PY):                                   # and live, where the reference is present
+        live = M.reference_numbers(pg, pe, alignment)
+        for k, v in live.items():
+            assert abs(got[k] - v) <= 1e-9 * max(abs(v), 1e-3), (k, got[k], v)
+
+
+def test_umeyama_recovers_a_known_similarity():
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(3, 40))
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    y = 1.3 * R @ x + np.array([[2.0], [-1.0], [0.5]])
+    r, t, c = tio.umeyama_alignment(x, y, True)
+    assert np.allclose(r, R, atol=1e-12) and np.allclose(t, [2.0, -1.0, 0.5], atol=1e-12) and abs(c - 1.3) < 1e-12
+    r, t, c = tio.umeyama_alignment(x, R @ x, False)
+    assert c == 1.0 and np.allclose(r, R, atol=1e-12) and np.allclose(t, 0, atol=1e-12)
+    with pytest.raises(ValueError):
+        tio.umeyama_alignment(x, y[:, :5])
