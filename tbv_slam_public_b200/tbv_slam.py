@@ -132,8 +132,10 @@ class ScanContextClosure:
     verification.LogisticRegression.LoadCoefficients); `verification_classifier`: optional, else the preset coefficients."""
 
     def __init__(self, graph: G.SimpleGraph, device, alignment_classifier: V.LogisticRegression, params: LoopClosureParams | None = None,
-                 verification_classifier: V.LogisticRegression | None = None, odometry_coupled_closure: bool = True):
+                 verification_classifier: V.LogisticRegression | None = None, odometry_coupled_closure: bool = True,
+                 model_training_file_save: str = ""):
         self.graph, self.dev, self.par = graph, device, params or LoopClosureParams()
+        self.model_training_file_save = model_training_file_save          # par_.model_training_file_save: collect (features, is-loop) samples
         self.alignment_classifier, self.verification_classifier = alignment_classifier, verification_classifier
         self.odometry_coupled_closure = odometry_coupled_closure
         self.itr_current = 0                              # row of the next keyframe to process
@@ -184,6 +186,10 @@ class ScanContextClosure:
                 break
             self._process_keyframe(self.itr_current)
             self.itr_current += 1
+        if self.itr_current == n and self.model_training_file_save and self.verification_classifier is not None \
+                and self.verification_classifier.DataValid():
+            self.verification_classifier.fit()                        # SaveVerificationTrainingData (:253-259)
+            self.verification_classifier.SaveData(self.model_training_file_save)
         return self.itr_current != n
 
     def _process_keyframe(self, row: int):
@@ -257,6 +263,12 @@ class ScanContextClosure:
             con = G.Constraint3d(scan.idx_, scan_to.idx_, G.pose3d_from_xyt(t), G._information(cov6), G.LOOP_APPEARANCE, quality, "")
             rec = CandidateRecord(scan.idx_, scan_to.idx_, guess_nr, np.array(t), dict(quality), float(prob), bool(ok))
             self.statistics.append(rec)
+            if self.model_training_file_save:                         # AddVerificationTrainingData (:240-251)
+                is_loop, pos_ok = candidate_loop_status(update_statistics(self.graph, rec))
+                if pos_ok:
+                    if self.verification_classifier is None:
+                        self.verification_classifier = V.LogisticRegression()
+                    self.verification_classifier.AddDataPoint([[quality[f] for f in self.par.model_features]], [float(is_loop)])
             evaluated.append((prob, con, rec))
         # ApplyConstratins (:261-275)
         for i in V.apply_constraints([e[0] for e in evaluated], self.par.model_threshold, self.par.all_candidates):

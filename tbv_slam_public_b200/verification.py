@@ -22,6 +22,7 @@ class LogisticRegression:
     def __init__(self, intercept: float | None = None, coef=None):
         self.intercept_ = intercept
         self.coef_ = None if coef is None else np.asarray(coef, float)
+        self.X_, self.y_, self.py_clf_ = None, None, None
 
     def IsFit(self) -> bool:
         return self.coef_ is not None
@@ -42,8 +43,78 @@ class LogisticRegression:
         with open(path, "w") as f:
             f.write(",".join(["%g" % self.intercept_] + ["%g" % c for c in self.coef_]) + "\n")
 
+    # ---- training side (PythonClassifierInterface, alignmentinterface.cpp:46-222): sklearn does the fit, as in the reference ----------
+    def AddDataPoint(self, X_i, y_i):
+        X_i = np.atleast_2d(np.asarray(X_i, float))
+        y_i = np.asarray(y_i, float).reshape(-1)
+        if X_i.shape[0] != len(y_i) and X_i.shape[1] == len(y_i):       # a column of samples, as Eigen's (n, 1) matrices in the reference's tests
+            X_i = X_i.T
+        self.X_ = X_i if getattr(self, "X_", None) is None or len(self.X_) == 0 else np.vstack([self.X_, X_i])
+        self.y_ = y_i if getattr(self, "y_", None) is None or len(self.y_) == 0 else np.concatenate([self.y_, y_i])
+
+    def DataValid(self) -> bool:
+        X, y = getattr(self, "X_", None), getattr(self, "y_", None)
+        if X is None or y is None or len(X) != len(y) or len(y) < 1:
+            return False
+        return bool(np.all(np.isfinite(X)) and np.all(np.isfinite(y)))
+
+    def fit(self):
+        """LogisticRegression::fit (alignmentinterface.cpp:196-222): sklearn LogisticRegression(class_weight="balanced", max_iter=1000)."""
+        if not self.DataValid():
+            raise ValueError("training data invalid (the reference exits here)")
+        from sklearn.linear_model import LogisticRegression as SkLR
+        self.py_clf_ = SkLR(class_weight="balanced", max_iter=1000).fit(self.X_, self.y_)
+        self.coef_ = np.asarray(self.py_clf_.coef_, float)[0].copy()
+        self.intercept_ = float(np.asarray(self.py_clf_.intercept_, float).reshape(-1)[0])
+        return self
+
+    def predict(self, X) -> np.ndarray:
+        if not self.IsFit():
+            return np.zeros(len(np.atleast_2d(X)))
+        return (self.predict_linear(X) > 0).astype(float)
+
+    def Accuracy(self, y_true=None, y_pred=None) -> float:
+        """balanced_accuracy_score; without arguments: on the training data (alignmentinterface.h Accuracy())."""
+        if y_true is None:
+            y_true, y_pred = self.y_, self.predict(self.X_)
+        y_true, y_pred = np.asarray(y_true, float), np.asarray(y_pred, float)
+        if len(y_true) != len(y_pred) or len(y_true) == 0:
+            return -1.0
+        recalls = [float(np.mean(y_pred[y_true == c] == c)) for c in np.unique(y_true)]
+        return float(np.mean(recalls))
+
+    def ConfusionMatrix(self, y_true=None, y_pred=None) -> np.ndarray:
+        if y_true is None:
+            y_true, y_pred = self.y_, self.predict(self.X_)
+        y_true, y_pred = np.asarray(y_true, float), np.asarray(y_pred, float)
+        if len(y_true) != len(y_pred) or len(y_true) == 0:
+            return np.zeros((2, 2))
+        m = np.zeros((2, 2))
+        for t, p_ in zip(y_true, y_pred):
+            m[int(t), int(p_)] += 1
+        return m
+
+    def SaveData(self, path: str):
+        """One line per sample: y,x0,x1,... (alignmentinterface.cpp:160-180)."""
+        with open(path, "w") as f:
+            for y, x in zip(self.y_, self.X_):
+                f.write(",".join(["%g" % y] + ["%g" % v for v in x]) + "\n")
+
+    def LoadData(self, path: str):
+        ys, xs = [], []
+        with open(path) as f:
+            for line in f:
+                v = [t for t in line.strip().split(",") if t != ""]
+                if v:
+                    ys.append(float(v[0])); xs.append([float(t) for t in v[1:]])
+        if ys:
+            self.X_, self.y_ = np.asarray(xs, float), np.asarray(ys, float)
+        return self
+
     def predict_linear(self, X) -> np.ndarray:
-        X = np.atleast_2d(np.asarray(X, float))
+        X = np.asarray(X, float)
+        if X.ndim == 1:                                    # one sample, or (single-feature model) a vector of samples
+            X = X.reshape(-1, 1) if len(self.coef_) == 1 else X.reshape(1, -1)
         return X @ self.coef_ + self.intercept_
 
     def predict_proba(self, X) -> np.ndarray:

@@ -275,3 +275,19 @@ def test_all_candidates_and_disabled_verification(drive):
     off = TS.TBVSLAM(_copy(g), OracleLoopDevice(), _classifier(), TS.LoopClosureParams(verification_disabled=True))
     off.ProcessFrame(False, True)
     assert not off.loop.loop_constraints and all(r.probability == 0.0 for r in off.loop.statistics)
+
+
+def test_verification_training_data_is_collected_and_fitted(drive, tmp_path):
+    """par_.model_training_file_save: every candidate whose outcome is unambiguous (not a loop, or a loop registered close to ground truth)
+    becomes a sample (features, is-loop); at the end the verification model is fitted and the samples are saved (loopclosure.cpp:240-259)."""
+    g, gt, est = drive
+    p = str(tmp_path / "training_data.txt")
+    loop = TS.ScanContextClosure(_copy(g), OracleLoopDevice(), _classifier(), TS.LoopClosureParams(), model_training_file_save=p)
+    assert loop.SearchAndAddConstraint() is False
+    clf = loop.verification_classifier
+    n_cand = sum(1 for r in loop.statistics if r.guess_nr >= 0)
+    assert clf is not None and clf.IsFit() and 0 < len(clf.y_) <= n_cand and clf.X_.shape[1] == 3
+    assert set(np.unique(clf.y_)) == {0.0, 1.0}                        # first-lap candidates are not loops, second-lap ones are
+    rows = open(p).read().splitlines()
+    assert len(rows) == len(clf.y_) and all(len(r.split(",")) == 4 for r in rows)
+    assert clf.Accuracy() > 0.9

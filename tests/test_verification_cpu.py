@@ -58,3 +58,63 @@ def test_verify_by_odometry():
     rel = (200.0 - 5.0) / 200.0
     assert abs(s - (1 - math.exp(-rel * rel / (2 * 0.05 ** 2)))) < 1e-12
     assert V.VerifyByOdometry(line, verify_via_odometry=False) == 1.0
+
+
+# ---- the reference's own unit tests for the classifier bridge (coral_alignment_quality/test/python_classifier_interface_tests.cpp), restated:
+# same fixture (X = 1..6, y = 0 0 0 1 1 1), same assertions.  The decision-tree and ROC-plot cases are not restated: the reference's fit()
+# has the decision tree commented out (alignmentinterface.cpp:212-215) and the plot needs matplotlib, which this image lacks.
+@pytest.fixture()
+def python_classifier():
+    clf = V.LogisticRegression()
+    clf.AddDataPoint(np.array([1, 2, 3, 4, 5, 6.0]).reshape(6, 1), np.array([0, 0, 0, 1, 1, 1.0]))
+    return clf
+
+
+def test_logisticRegressionPredictTest(python_classifier):
+    python_classifier.fit()
+    y_pred = python_classifier.predict(np.array([3.0, 4.0]))
+    assert y_pred[0] == 0 and y_pred[1] == 1
+
+
+def test_logisticRegressionPredictProbaTest(python_classifier):
+    assert np.array_equal(python_classifier.predict_proba(np.array([[3.0], [4.0]])), [0, 0])     # not fitted yet: zeros (:23-28)
+    python_classifier.fit()
+    y_prob = python_classifier.predict_proba(np.array([3.0, 4.0]))
+    assert y_prob[0] < 0.5 < y_prob[1]
+    sk = python_classifier.py_clf_.predict_proba(np.array([[3.0], [4.0]]))[:, 1]                   # numpy.delete(result, 0, 1) in the reference
+    assert np.allclose(y_prob, sk, rtol=1e-12)
+
+
+def test_accuracyTest(python_classifier):
+    python_classifier.AddDataPoint(np.array([[2.0], [5.0]]), np.array([1.0, 0.0]))
+    python_classifier.fit()
+    assert 0.5 < python_classifier.Accuracy() < 1
+    from sklearn.metrics import balanced_accuracy_score, confusion_matrix
+    y, p = python_classifier.y_, python_classifier.predict(python_classifier.X_)
+    assert python_classifier.Accuracy() == pytest.approx(balanced_accuracy_score(y, p))
+    assert np.array_equal(python_classifier.ConfusionMatrix(), confusion_matrix(y, p))
+    assert python_classifier.Accuracy([1, 0], [1]) == -1 and python_classifier.Accuracy([], []) == -1
+
+
+def test_saveAndLoadDataTest(python_classifier, tmp_path):
+    p = str(tmp_path / "training_data.txt")
+    python_classifier.SaveData(p)
+    assert open(p).read().splitlines()[:2] == ["0,1", "0,2"]
+    loaded = V.LogisticRegression().LoadData(p)
+    python_classifier.fit(); loaded.fit()
+    assert loaded.predict_proba(np.array([3.0]))[0] == pytest.approx(python_classifier.predict_proba(np.array([3.0]))[0], rel=1e-6)   # EXPECT_FLOAT_EQ
+    # coefficients written by one instance drive another without sklearn (LoadCoefficients is what the SLAM run uses)
+    c = str(tmp_path / "coef.txt")
+    python_classifier.SaveCoefficients(c)
+    other = V.LogisticRegression().LoadCoefficients(c)
+    # the file holds 6 significant digits, like the reference's `file << coef_(i)` (alignmentinterface.cpp:256-270)
+    assert other.predict_proba(np.array([3.0]))[0] == pytest.approx(python_classifier.predict_proba(np.array([3.0]))[0], rel=1e-4)
+
+
+def test_invalid_training_data_is_refused():
+    clf = V.LogisticRegression()
+    assert not clf.DataValid()
+    with pytest.raises(ValueError):
+        clf.fit()
+    clf.AddDataPoint(np.array([[1.0], [np.nan]]), np.array([0.0, 1.0]))
+    assert not clf.DataValid()
