@@ -101,16 +101,93 @@ class GpuLoopDevice:
         return res
 
     # getCorAlQualityMeasure / getCFEARQualityMeasure for all candidates of a keyframe (alignmentinterface.cpp:437-475)
-    def coral(self, clouds, src, ref, T_src, T_ref):
-        r = self.api.CorAlRadarQuality(self.ctx, clouds, src, ref, T_src, T_ref)
+    def coral(self, clouds, src, ref, T_src, T_ref, T_offset=None):
+        r = self.api.CorAlRadarQuality(self.ctx, clouds, src, ref, T_src, T_ref, T_offset)
         return np.array([[q.joint, q.sep, q.overlap] for q in r], np.float64).reshape(-1, 3)
 
-    def cfear(self, cellsets, src, ref, T_src, T_ref):
-        return self.ctx.CFEARQualityBatch(cellsets, src, ref, T_src, T_ref)
+    def cfear(self, cellsets, src, ref, T_src, T_ref, T_offset=None):
+        return self.ctx.CFEARQualityBatch(cellsets, src, ref, T_src, T_ref, T_offset)
 
     # CeresLeastSquares(...).Solve() (ceresoptimizer.cpp:13-62)
     def optimize(self, nodes, ids, meas, info, pgo_params, **kw):
         return self.api.pgo_optimize(self.ctx, nodes, ids, meas, pgo_params, info=info, **kw)
+
+
+class ScanLearningInterface:
+    """Training of the alignment classifier from odometry (coral_alignment_quality/src/alignment_checker/alignmentinterface.cpp:288-347,
+    479-495; driven by cfear_radarodometry's odometry_training_node): every keyframe is compared with the previous one under 13 pose
+    perturbations of the PREVIOUS scan — aligned, and +-0.5 / 1 / 2 m in x or y with 0.5 / 2 / 15 degrees — and the CorAl + CFEAR features
+    of each become one sample (label 1 only for the unperturbed pair).  The 13 pairs of a keyframe are ONE CorAl launch and ONE CFEAR
+    launch (T_offset carries the perturbations)."""
+    range_error_, min_dist_btw_scans_ = 0.5, 0.5
+    small_th_err, medium_th_err, large_th_err = 0.5 * math.pi / 180.0, 2 * math.pi / 180.0, 15 * math.pi / 180.0
+
+    def __init__(self, device, combined: bool = True, small_errors=True, medium_errors=True, large_errors=True):
+        self.dev, self.combined_ = device, combined
+        self.cfear_class, self.coral_class, self.combined_class = V.LogisticRegression(), V.LogisticRegression(), V.LogisticRegression()
+        self.prev_, self.frame_ = None, 0
+        r = self.range_error_
+        self.vek_perturbation_ = [(0.0, 0.0, 0.0)]                                   # CreatePerturbations (:479-495)
+        for on, k, th in ((small_errors, 1, self.small_th_err), (medium_errors, 2, self.medium_th_err), (large_errors, 4, self.large_th_err)):
+            if on:
+                self.vek_perturbation_ += [(k * r, 0.0, th), (0.0, k * r, th), (-k * r, 0.0, th), (0.0, -k * r, th)]
+
+    def features(self, current, prev, perturbations):
+        """[n, 3] CorAl and [n, 3] CFEAR features of (ref = current, src = prev * perturbation); a scan is (pose xyt, peaks [n,4], cells [m,16])."""
+        n = len(perturbations)
+        cloud = lambda s: (s[1][:, 0], s[1][:, 1], s[1][:, 3])
+        T_src, T_ref = np.tile(np.asarray(prev[0], np.float64), (n, 1)), np.tile(np.asarray(current[0], np.float64), (n, 1))
+        off = np.asarray(perturbations, np.float64).reshape(n, 3)
+        x_coral = self.dev.coral([cloud(current), cloud(prev)], [1] * n, [0] * n, T_src, T_ref, off)
+        x_cfear = self.dev.cfear([current[2], prev[2]], [1] * n, [0] * n, T_src, T_ref, off)
+        return np.asarray(x_coral, np.float64).reshape(n, 3), np.asarray(x_cfear, np.float64).reshape(n, 3)
+
+    def AddTrainingData(self, pose_xyt, cloud_peaks, cells) -> int:
+        current = (np.asarray(pose_xyt, np.float64), np.asarray(cloud_peaks, np.float32).reshape(-1, 4), np.asarray(cells, np.float64).reshape(-1, 16))
+        first = self.frame_ == 0
+        self.frame_ += 1
+        if first:
+            self.prev_ = current
+            return 0
+        if math.hypot(*(current[0][:2] - self.prev_[0][:2])) < self.min_dist_btw_scans_:
+            return 0
+        xc, xf = self.features(current, self.prev_, self.vek_perturbation_)
+        y = np.array([1.0 if sum(abs(e) for e in v) < 0.0001 else 0.0 for v in self.vek_perturbation_])
+        if self.combined_:
+            self.combined_class.AddDataPoint(np.concatenate([xc, xf], axis=1), y)
+        else:
+            self.coral_class.AddDataPoint(xc, y)
+            self.cfear_class.AddDataPoint(xf, y)
+        self.prev_ = current
+        return len(y)
+
+    def FitModels(self):
+        if self.combined_:
+            self.combined_class.fit()
+        else:
+            self.coral_class.fit()
+            self.cfear_class.fit()
+
+    def PredAlignment(self, current, prev) -> dict:
+        """quality map of one pair (:349-368): combined -> {alignment_quality: predict_linear}, else {Coral, CFEAR: predict_proba}."""
+        xc, xf = self.features(current, prev, [(0.0, 0.0, 0.0)])
+        if self.combined_:
+            return {COMBINED_COST: float(self.combined_class.predict_linear(np.concatenate([xc, xf], axis=1))[0])}
+        return {"Coral": float(self.coral_class.predict_proba(xc)[0]), "CFEAR": float(self.cfear_class.predict_proba(xf)[0])}
+
+    def SaveCoefficients(self, directory: str):
+        if self.combined_:
+            self.combined_class.SaveCoefficients(directory + "/trained_alignment_classifier.txt")
+        else:
+            self.coral_class.SaveCoefficients(directory + "/trained_alignment_classifier_CorAl.txt")
+            self.cfear_class.SaveCoefficients(directory + "/trained_alignment_classifier_CFEAR.txt")
+
+    def LoadCoefficients(self, directory: str):
+        if self.combined_:
+            self.combined_class.LoadCoefficients(directory + "/trained_alignment_classifier.txt")
+        else:
+            self.coral_class.LoadCoefficients(directory + "/trained_alignment_classifier_CorAl.txt")
+            self.cfear_class.LoadCoefficients(directory + "/trained_alignment_classifier_CFEAR.txt")
 
 
 @dataclass
@@ -239,9 +316,11 @@ class ScanContextClosure:
         slot = {r: i + 1 for i, r in enumerate(uniq)}
         clouds = [cloud(scan)] + [cloud(self.graph.graph[r][0]) for r in uniq]
         cellsets = [scan.cloud_normal_] + [self.graph.graph[r][0].cloud_normal_ for r in uniq]
-        src, ref = [0] * k, [slot[r] for r in ids_to]
-        x_coral = self.dev.coral(clouds, src, ref, T_from, T_to_reg)
-        x_cfear = self.dev.cfear(cellsets, src, ref, T_from, T_to_reg)
+        # PredAlignment(current = from, prev = to) -> CreateQualityType(ref = current, src = prev) (alignmentinterface.cpp:349-353, 437-475;
+        # AlignmentQuality.h:263): the candidate (`to`, at Tfrom * t_be) is the MOVING / src scan, the query keyframe the reference one
+        src, ref = [slot[r] for r in ids_to], [0] * k
+        x_coral = self.dev.coral(clouds, src, ref, T_to_reg, T_from)
+        x_cfear = self.dev.cfear(cellsets, src, ref, T_to_reg, T_from)
         X = np.concatenate([np.asarray(x_coral, np.float64).reshape(k, 3), np.asarray(x_cfear, np.float64).reshape(k, 3)], axis=1)
         alignment_quality = self.alignment_classifier.predict_linear(X)          # quality[COMBINED_COST] = predict_linear (PredAlignment :355-360)
         evaluated = []

@@ -39,16 +39,19 @@ class OracleLoopDevice:
             out.append((ok, Ta, np.array([0.01, 0.0, 0.01, 1e-4]), score) if ok else (False, np.zeros(3), np.array([1.0, 0, 1.0, 1.0]), score))
         return out
 
-    def coral(self, clouds, src, ref, T_src, T_ref):
+    def coral(self, clouds, src, ref, T_src, T_ref, T_offset=None):
         self.calls["coral"] += 1
-        q = [self.O.coral_quality(clouds[s], clouds[r], Ts, Tr) for s, r, Ts, Tr in zip(src, ref, T_src, T_ref)]
+        off = np.zeros((len(src), 3)) if T_offset is None else T_offset
+        q = [self.O.coral_quality(clouds[s], clouds[r], Ts, Tr, To) for s, r, Ts, Tr, To in zip(src, ref, T_src, T_ref, off)]
         return np.array([[d["joint"], d["sep"], d["overlap"]] for d in q])
 
-    def cfear(self, cellsets, src, ref, T_src, T_ref):
+    def cfear(self, cellsets, src, ref, T_src, T_ref, T_offset=None):
         self.calls["cfear"] += 1
         P = self.O.default_reg_params(cost=api.P2L, loss=api.HUBER, loss_limit=0.3, weight_opt=api.W_UNIFORM)
+        off = np.zeros((len(src), 3)) if T_offset is None else T_offset
         out = []
-        for s, r, Ts, Tr in zip(src, ref, T_src, T_ref):
+        for s, r, Ts, Tr, To in zip(src, ref, T_src, T_ref, off):
+            Ts = TS._xyt(TS._mat3(Ts) @ TS._mat3(To))                 # src.GetAffine() * Toffset (AlignmentQuality.cpp:337)
             n, score, cost, res = self.O.get_cost([cellsets[r], cellsets[s]], [Tr, Ts], P, itr=0)
             out.append([cost, n, (len(cellsets[s]) + len(cellsets[r])) / 2.0] if n > 1 else [0.0, 0.0, 0.0])
         return np.array(out)
@@ -291,3 +294,36 @@ def test_verification_training_data_is_collected_and_fitted(drive, tmp_path):
     rows = open(p).read().splitlines()
     assert len(rows) == len(clf.y_) and all(len(r.split(",")) == 4 for r in rows)
     assert clf.Accuracy() > 0.9
+
+
+def test_alignment_classifier_is_trained_from_odometry_and_closes_the_loop(drive, tmp_path):
+    """ScanLearningInterface::AddTrainingData over the first lap (13 perturbations per keyframe pair, one CorAl + one CFEAR batch each),
+    FitModels, SaveCoefficients / LoadCoefficients, then the trained model — not a hand-made one — drives the loop closure."""
+    g, gt, est = drive
+    dev = OracleLoopDevice()
+    sli = TS.ScanLearningInterface(dev)
+    assert len(sli.vek_perturbation_) == 13 and sli.vek_perturbation_[0] == (0.0, 0.0, 0.0)
+    assert sli.vek_perturbation_[1] == (0.5, 0.0, 0.5 * math.pi / 180) and sli.vek_perturbation_[12] == (0.0, -2.0, 15 * math.pi / 180)
+    n = 0
+    for r in range(N_LAP):
+        s = g.graph[r][0]
+        n += sli.AddTrainingData(G.pose3d_to_xyt(s.T), s.cloud_peaks_, s.cloud_normal_)
+    assert n == 13 * (N_LAP - 1) and dev.calls["coral"] == dev.calls["cfear"] == N_LAP - 1
+    assert sli.AddTrainingData(G.pose3d_to_xyt(g.graph[N_LAP - 1][0].T), g.graph[N_LAP - 1][0].cloud_peaks_, g.graph[N_LAP - 1][0].cloud_normal_) == 0
+    X, y = sli.combined_class.X_, sli.combined_class.y_
+    assert X.shape == (n, 6) and y.sum() == N_LAP - 1
+    sli.FitModels()
+    assert sli.combined_class.Accuracy() > 0.9
+    a, b = g.graph[3][0], g.graph[2][0]
+    scan = lambda s: (G.pose3d_to_xyt(s.T), s.cloud_peaks_, s.cloud_normal_)
+    good = sli.PredAlignment(scan(a), scan(b))[TS.COMBINED_COST]
+    moved = (G.pose3d_to_xyt(b.T) + [1.5, -1.0, 0.1], b.cloud_peaks_, b.cloud_normal_)
+    assert good > 0 > sli.PredAlignment(scan(a), moved)[TS.COMBINED_COST]
+    sli.SaveCoefficients(str(tmp_path))
+    loaded = TS.ScanLearningInterface(dev)
+    loaded.LoadCoefficients(str(tmp_path))
+    assert np.allclose(loaded.combined_class.coef_, sli.combined_class.coef_, rtol=1e-5)
+    slam = TS.TBVSLAM(_copy(g), OracleLoopDevice(), loaded.combined_class, TS.LoopClosureParams(), api.default_pgo_params(loop_scaling=1.0))
+    slam.ProcessFrame(False, True)
+    applied = [r for r in slam.loop.statistics if r.applied]
+    assert len(applied) >= 6 and all(abs((r.id_from - r.id_to) - N_LAP) <= 2 for r in applied)
