@@ -17,6 +17,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "tbv_b200.h"
@@ -437,5 +438,169 @@ class CeresLeastSquaresT {
   std::vector<double> meas_, info_;
 };
 typedef CeresLeastSquaresT<DevicePoseGraph> CeresLeastSquares;
+
+// ---- simple graph hand-off (cfear_radarodometry/include/cfear_radarodometry/types.h:93-192, types.cpp:103-130) in the Boost-free .tbvg layout ---------
+// Same content as the reference's simple_graph (vector<pair<RadarScan, vector<Constraint3d>>>), member for member; the byte layout is specified in
+// tbv_slam_public_b200/graph_io.py (little endian, no padding) and is what SaveSimpleGraph / LoadSimpleGraph below write and read.
+struct GraphConstraint {                          // Constraint3d with every serialised member
+  unsigned long id_begin = 0, id_end = 0;
+  Pose3d t_be;
+  Matrix6d information{};
+  int type = 0;                                   // ConstraintType: 0 odometry, 1 loop_appearance, 2 mini_loop, 3 candidate
+  std::vector<std::pair<std::string, double>> quality;   // std::map order (sorted by key) on disk
+  std::string info;
+};
+struct RadarScan {                                // serialised members of RadarScan + MapPointNormal
+  Pose3d T, Tgt;
+  bool has_Tgt_ = false;
+  unsigned int idx_ = 0;
+  unsigned long stamp_ = 0;
+  std::array<double, 16> motion_{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};   // 4x4 row-major
+  PointCloud cloud_peaks_, cloud_nopeaks_;
+  std::vector<tbv_cell> cloud_normal_;
+  std::vector<std::array<float, 2>> downsampled_;
+  float radius_ = 3.0f;
+  bool weight_intensity_ = true;
+};
+typedef std::vector<std::pair<RadarScan, std::vector<GraphConstraint>>> simple_graph;
+
+namespace detail {
+struct Writer {
+  std::string out;
+  void raw(const void* p, size_t n) { out.append(static_cast<const char*>(p), n); }
+  template <class T> void put(T v) { raw(&v, sizeof(T)); }          // host is little endian (x86-64 / aarch64), as the layout requires
+};
+struct Reader {
+  const std::string& in;
+  size_t o = 0;
+  explicit Reader(const std::string& s) : in(s) {}
+  void raw(void* p, size_t n) {
+    if (o + n > in.size()) throw Error(TBV_ERR_INVALID, "truncated .tbvg file");
+    std::copy(in.data() + o, in.data() + o + n, static_cast<char*>(p));
+    o += n;
+  }
+  template <class T> T get() { T v; raw(&v, sizeof(T)); return v; }
+  template <class N> size_t count(size_t element_bytes) {           // an element count that the rest of the file can actually hold
+    const size_t n = (size_t)get<N>();
+    if (element_bytes && n > (in.size() - o) / element_bytes) throw Error(TBV_ERR_INVALID, "truncated .tbvg file");
+    return n;
+  }
+};
+inline void put_pose(Writer& w, const Pose3d& P) { w.raw(P.p, 24); w.raw(P.q, 32); }
+inline void get_pose(Reader& r, Pose3d& P) { r.raw(P.p, 24); r.raw(P.q, 32); }
+inline void put_cloud(Writer& w, const PointCloud& c) {
+  w.put<uint32_t>((uint32_t)c.size());
+  for (const PointXYZI& p : c) { w.put(p.x); w.put(p.y); w.put(p.z); w.put(p.intensity); }
+}
+inline void get_cloud(Reader& r, PointCloud& c) {
+  c.resize(r.count<uint32_t>(16));
+  for (PointXYZI& p : c) { p.x = r.get<float>(); p.y = r.get<float>(); p.z = r.get<float>(); p.intensity = r.get<float>(); }
+}
+}  // namespace detail
+
+inline std::string SerializeSimpleGraph(const simple_graph& graph) {
+  static_assert(sizeof(tbv_cell) == 128, "tbv_cell is 16 doubles");
+  detail::Writer w;
+  w.raw("TBVG", 4);
+  w.put<uint32_t>(1);
+  w.put<uint32_t>((uint32_t)graph.size());
+  for (const auto& nc : graph) {
+    const RadarScan& s = nc.first;
+    detail::put_pose(w, s.T);
+    detail::put_pose(w, s.Tgt);
+    w.put<uint8_t>(s.has_Tgt_ ? 1 : 0);
+    w.put<uint32_t>(s.idx_);
+    w.put<uint64_t>((uint64_t)s.stamp_);
+    w.raw(s.motion_.data(), 128);
+    detail::put_cloud(w, s.cloud_peaks_);
+    detail::put_cloud(w, s.cloud_nopeaks_);
+    w.put<uint32_t>((uint32_t)s.cloud_normal_.size());
+    if (!s.cloud_normal_.empty()) w.raw(s.cloud_normal_.data(), s.cloud_normal_.size() * sizeof(tbv_cell));
+    w.put<uint32_t>((uint32_t)s.downsampled_.size());
+    for (const auto& d : s.downsampled_) { w.put(d[0]); w.put(d[1]); }
+    w.put<float>(s.radius_);
+    w.put<uint8_t>(s.weight_intensity_ ? 1 : 0);
+    w.put<uint32_t>((uint32_t)nc.second.size());
+    for (const GraphConstraint& c : nc.second) {
+      w.put<uint64_t>((uint64_t)c.id_begin);
+      w.put<uint64_t>((uint64_t)c.id_end);
+      detail::put_pose(w, c.t_be);
+      w.raw(c.information.data(), 288);
+      w.put<uint32_t>((uint32_t)c.type);
+      std::vector<std::pair<std::string, double>> q = c.quality;
+      std::sort(q.begin(), q.end(), [](const std::pair<std::string, double>& a, const std::pair<std::string, double>& b) { return a.first < b.first; });
+      w.put<uint32_t>((uint32_t)q.size());
+      for (const auto& kv : q) { w.put<uint16_t>((uint16_t)kv.first.size()); w.raw(kv.first.data(), kv.first.size()); w.put<double>(kv.second); }
+      w.put<uint32_t>((uint32_t)c.info.size());
+      w.raw(c.info.data(), c.info.size());
+    }
+  }
+  return w.out;
+}
+
+inline simple_graph ParseSimpleGraph(const std::string& bytes) {
+  detail::Reader r(bytes);
+  char magic[4];
+  r.raw(magic, 4);
+  if (std::string(magic, 4) != "TBVG") throw Error(TBV_ERR_INVALID, "not a .tbvg file");
+  if (r.get<uint32_t>() != 1) throw Error(TBV_ERR_INVALID, "unsupported .tbvg version");
+  simple_graph graph(r.count<uint32_t>(1));
+  for (auto& nc : graph) {
+    RadarScan& s = nc.first;
+    detail::get_pose(r, s.T);
+    detail::get_pose(r, s.Tgt);
+    s.has_Tgt_ = r.get<uint8_t>() != 0;
+    s.idx_ = r.get<uint32_t>();
+    s.stamp_ = (unsigned long)r.get<uint64_t>();
+    r.raw(s.motion_.data(), 128);
+    detail::get_cloud(r, s.cloud_peaks_);
+    detail::get_cloud(r, s.cloud_nopeaks_);
+    s.cloud_normal_.resize(r.count<uint32_t>(sizeof(tbv_cell)));
+    if (!s.cloud_normal_.empty()) r.raw(s.cloud_normal_.data(), s.cloud_normal_.size() * sizeof(tbv_cell));
+    s.downsampled_.resize(r.count<uint32_t>(8));
+    for (auto& d : s.downsampled_) { d[0] = r.get<float>(); d[1] = r.get<float>(); }
+    s.radius_ = r.get<float>();
+    s.weight_intensity_ = r.get<uint8_t>() != 0;
+    nc.second.resize(r.count<uint32_t>(1));
+    for (GraphConstraint& c : nc.second) {
+      c.id_begin = (unsigned long)r.get<uint64_t>();
+      c.id_end = (unsigned long)r.get<uint64_t>();
+      detail::get_pose(r, c.t_be);
+      r.raw(c.information.data(), 288);
+      c.type = (int)r.get<uint32_t>();
+      c.quality.resize(r.count<uint32_t>(10));
+      for (auto& kv : c.quality) {
+        kv.first.resize(r.count<uint16_t>(1));
+        if (!kv.first.empty()) r.raw(&kv.first[0], kv.first.size());
+        kv.second = r.get<double>();
+      }
+      c.info.resize(r.count<uint32_t>(1));
+      if (!c.info.empty()) r.raw(&c.info[0], c.info.size());
+    }
+  }
+  if (r.o != bytes.size()) throw Error(TBV_ERR_INVALID, "trailing bytes in .tbvg file");
+  return graph;
+}
+
+// The constraints the optimiser takes, with ids mapped to rows (CeresLeastSquares reads nodes by id; here: by position in the graph)
+inline void GraphToOptimizerInput(const simple_graph& graph, std::vector<Pose3d>& nodes, std::vector<Constraint3d>& constraints) {
+  nodes.clear();
+  constraints.clear();
+  std::vector<std::pair<unsigned int, size_t>> rows;
+  for (size_t i = 0; i < graph.size(); i++) { nodes.push_back(graph[i].first.T); rows.emplace_back(graph[i].first.idx_, i); }
+  std::sort(rows.begin(), rows.end());
+  auto row_of = [&](unsigned long id) -> unsigned long {
+    auto it = std::lower_bound(rows.begin(), rows.end(), std::make_pair((unsigned int)id, (size_t)0));
+    if (it == rows.end() || it->first != id) throw Error(TBV_ERR_INVALID, "constraint references a missing node");
+    return (unsigned long)it->second;
+  };
+  for (const auto& nc : graph)
+    for (const GraphConstraint& c : nc.second) {
+      if (c.type != 0 && c.type != 1) continue;
+      Constraint3d o;
+      o.id_begin = row_of(c.id_begin); o.id_end = row_of(c.id_end); o.t_be = c.t_be; o.information = c.information; o.type = c.type;
+      constraints.push_back(o);
+    }
+}
 
 }  // namespace tbv_b200
