@@ -7,6 +7,7 @@ a missing library or a missing GPU raises.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -735,6 +736,117 @@ def pgo_optimize(ctx: Context, nodes, ids, meas, params: PGOParams | None = None
             if radius < 1e-32:
                 S.termination = "min_trust_region_radius"
                 break
+    return x, S
+
+
+def pgo_solve_damped(ctx: Context, ids, H_diag, H_off, g, damping, fixed_node=0, max_iters=20000, rel_tol=1e-12):
+    """(H + diag(damping)) delta = -g with a caller-given damping vector [n, 6] (> 0), on the device.
+
+    tbv_pgo_solve_step derives its damping from the diagonal it is handed (clamp(diag, 1e-6, 1e32) / radius); called with radius = 1 on a
+    copy of H_diag whose diagonal e satisfies e + clamp(e, 1e-6, 1e32) = diag(H) + damping, it solves exactly the system asked for here
+    (off-diagonal entries of the blocks untouched).  An explicit damping argument in the C-ABI is the cleaner form and is planned with the
+    next kernel revision; this wrapper needs no kernel change."""
+    Hd = np.array(H_diag, np.float64).reshape(-1, 6, 6)
+    damping = np.asarray(damping, np.float64).reshape(-1, 6)
+    n = len(Hd)
+    if damping.shape != (n, 6) or not np.all(damping > 0):
+        raise ValueError("damping: [n, 6], positive")
+    idx = np.arange(6)
+    total = Hd[:, idx, idx] + damping
+    e = np.where(total / 2.0 >= 1e-6, total / 2.0, total - 1e-6)
+    e = np.where(e > 1e32, total - 1e32, e)
+    Hd[:, idx, idx] = e
+    return pgo_solve_step(ctx, ids, Hd, H_off, g, fixed_node, 1.0, max_iters, rel_tol)
+
+
+def pgo_optimize_ceres(ctx: Context, nodes, ids, meas, params: PGOParams | None = None, info=None, fixed_node=0, max_num_iterations=200,
+                       function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8, initial_radius=1e4, cg_rel_tol=1e-10,
+                       cg_max_iters=20000):
+    """ceres::Solve as CeresLeastSquares::SolveOptimizationProblem configures it (ceresoptimizer.cpp:50-62), restated step by step the way
+    oracle/tbv_oracle_reg.hpp restates it for the 3-parameter registration problem (TrustRegionMinimizer + LevenbergMarquardtStrategy of
+    Ceres 2.1.0, monotonic steps):
+      * Jacobi scaling s = 1 / (1 + sqrt(diag H)) fixed at iteration 0; LM diagonal clamp(diag(S H S), 1e-6, 1e32), recomputed after a
+        successful step and reused after a rejected one; step from (S H S + diag / radius) y = -S g, delta = S y — on the device as
+        (H + diag / (radius s^2)) delta = -g (pgo_solve_damped);
+      * an invalid step (model change <= 0) shrinks the radius, five in a row fail the solve;
+      * parameter and function tolerance are tested on the CANDIDATE before it is accepted (a converged run does not take its last step);
+      * accepted when (cost - candidate) / model change > 1e-3; radius /= max(1/3, 1 - (2 rho - 1)^3), capped at 1e16; rejected: radius
+        /= 2, 4, 8 ...; gradient tolerance on max |x - Plus(x, -g)| after every successful step; radius < 1e-32 ends the run.
+    Ceres itself is not in the container, so the restatement is unpinned; pgo_optimize stays the default driver until this
+    one has run on the GPU.  Returns (nodes [n, 7], PGOSummary)."""
+    params = params or default_pgo_params()
+    x = np.array(nodes, np.float64).reshape(-1, 7)
+    ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+    n = len(x)
+    S = PGOSummary()
+    free = np.ones((n, 1)); free[fixed_node] = 0.0
+    idx = np.arange(6)
+
+    def evaluate(xx):
+        cost, Hd, Ho, g, _ = pgo_assemble(ctx, xx, ids, meas, params, info, fixed_node)
+        return cost, Hd, Ho, g
+
+    def gradient_max_norm(xx, g):
+        return float(np.abs(xx - pgo_plus(xx, -g * free)).max(initial=0.0))
+
+    x_cost, Hd, Ho, g = evaluate(x)
+    S.initial_cost = S.final_cost = x_cost
+    diag_h = Hd[:, idx, idx]
+    scale = 1.0 / (1.0 + np.sqrt(np.maximum(diag_h, 0.0)))          # jacobi scaling, iteration 0 only
+    gmax = gradient_max_norm(x, g)
+    radius, decrease, lm_diag, reuse, invalid = float(initial_radius), 2.0, None, False, 0
+    x_norm = float(np.linalg.norm(x))
+    step_ok = True
+    S.termination = "max_num_iterations"
+    iteration = 0
+    while True:
+        # FinalizeIterationAndCheckIfMinimizerCanContinue
+        if iteration >= max_num_iterations:
+            S.termination = "max_num_iterations"; break
+        if step_ok and gmax <= gradient_tolerance:
+            S.termination = "gradient_tolerance"; break
+        if radius < 1e-32:
+            S.termination = "min_trust_region_radius"; break
+        iteration += 1
+        S.iterations = iteration
+        # LevenbergMarquardtStrategy::ComputeStep
+        if not reuse:
+            lm_diag = np.clip(Hd[:, idx, idx] * scale * scale, 1e-6, 1e32)
+        damping = lm_diag / (radius * scale * scale)
+        damping[fixed_node] = 1.0                                    # the fixed block is not a variable; any positive value
+        delta, cg_it, _ = pgo_solve_damped(ctx, ids, Hd, Ho, g, damping, fixed_node, cg_max_iters, cg_rel_tol)
+        S.cg_iterations += cg_it
+        reuse = True
+        model_change = -float(np.sum(delta * (g + 0.5 * _pgo_hessian_times(ids, Hd, Ho, delta))))
+        if not (np.all(np.isfinite(delta)) and model_change > 0.0):  # HandleInvalidStep
+            invalid += 1
+            step_ok = False
+            if invalid >= 5:
+                S.termination = "failure: consecutive invalid steps"; break
+            radius /= decrease; decrease *= 2.0
+            continue
+        invalid = 0
+        candidate = pgo_plus(x, delta)
+        cand_cost, Hd_c, Ho_c, g_c = evaluate(candidate)
+        if not math.isfinite(cand_cost):
+            cand_cost = float(np.finfo(np.float64).max)
+        if float(np.linalg.norm(x - candidate)) <= parameter_tolerance * (x_norm + parameter_tolerance):
+            S.termination = "parameter_tolerance"; break
+        if abs(x_cost - cand_cost) <= function_tolerance * x_cost:
+            S.termination = "function_tolerance"; break
+        rho = (x_cost - cand_cost) / model_change if cand_cost < np.finfo(np.float64).max else -np.inf
+        if rho > 1e-3:                                               # HandleSuccessfulStep
+            x, x_cost, Hd, Ho, g = candidate, cand_cost, Hd_c, Ho_c, g_c
+            x_norm = float(np.linalg.norm(x))
+            gmax = gradient_max_norm(x, g)
+            step_ok = True
+            S.successful_steps += 1
+            S.final_cost = min(S.final_cost, x_cost)
+            radius = min(radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3), 1e16)
+            decrease, reuse = 2.0, False
+        else:
+            step_ok = False
+            radius /= decrease; decrease *= 2.0
     return x, S
 
 

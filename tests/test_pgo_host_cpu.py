@@ -136,3 +136,51 @@ def test_lm_loop_terminations(cpu_device):
     xt, St = api.pgo_optimize(None, nodes, ids, meas, function_tolerance=1e-15, gradient_tolerance=1e-9, parameter_tolerance=1e-15)
     g = cpu_device.pgo_assemble(xt, ids, meas)[3]
     assert np.abs(g).max() <= 1e-8 and St.final_cost <= S.final_cost
+
+
+def test_solve_damped_reproduces_an_arbitrary_damping_through_the_radius_interface(cpu_device):
+    """pgo_solve_damped hands tbv_pgo_solve_step (radius = 1) a diagonal e with e + clamp(e, 1e-6, 1e32) = diag(H) + damping: the system solved
+    is (H + diag(damping)) delta = -g for ANY positive damping, including totals below the clamp."""
+    rng = np.random.default_rng(3)
+    _, nodes, ids, meas = _graph(14, rng)
+    _, Hd, Ho, g, _ = cpu_device.pgo_assemble(nodes, ids, meas)
+    n = len(Hd)
+    H = np.zeros((6 * n, 6 * n))
+    for i in range(n):
+        H[6 * i:6 * i + 6, 6 * i:6 * i + 6] = Hd[i]
+    for c, (a, b, _t) in enumerate(ids):
+        H[6 * a:6 * a + 6, 6 * b:6 * b + 6] += Ho[c]
+        H[6 * b:6 * b + 6, 6 * a:6 * a + 6] += Ho[c].T
+    for damping in (rng.uniform(0.1, 50.0, size=(n, 6)), np.full((n, 6), 1e-9), rng.uniform(1e-3, 1.0, size=(n, 6)) * Hd[:, np.arange(6), np.arange(6)].clip(1e-3)):
+        delta, _, _ = api.pgo_solve_damped(None, ids, Hd, Ho, g, damping, fixed_node=0)
+        keep = np.arange(6, 6 * n)
+        A = (H + np.diag(damping.reshape(-1)))[np.ix_(keep, keep)]
+        want = np.linalg.solve(A, -g.reshape(-1)[keep])
+        assert np.all(delta[0] == 0) and np.allclose(delta.reshape(-1)[keep], want, rtol=1e-8, atol=1e-12 * np.abs(want).max())
+    Hz = Hd.copy(); Hz[5] = 0.0                                   # a block whose diagonal + damping is below twice the clamp
+    tiny = np.full((n, 6), 1e-7)
+    d2, _, _ = api.pgo_solve_damped(None, ids, Hz, Ho, g, tiny)
+    assert np.all(np.isfinite(d2))
+    with pytest.raises(ValueError):
+        api.pgo_solve_damped(None, ids, Hd, Ho, g, np.zeros((n, 6)))
+
+
+def test_ceres_restatement_converges_and_does_not_take_its_last_step(cpu_device):
+    rng = np.random.default_rng(7)
+    truth, nodes, ids, meas = _graph(40, rng, noise=0.0)
+    x, S = api.pgo_optimize_ceres(None, nodes, ids, meas, function_tolerance=1e-16, gradient_tolerance=1e-12, parameter_tolerance=1e-14)
+    assert S.final_cost <= 1e-14 * S.initial_cost and S.successful_steps >= 2 and np.abs(x[:, :3] - truth[:, :3]).max() <= 1e-6
+    assert np.array_equal(x[0], nodes[0])
+    rng = np.random.default_rng(8)
+    _, nodes, ids, meas = _graph(40, rng)
+    x, S = api.pgo_optimize_ceres(None, nodes, ids, meas)
+    assert S.termination in ("function_tolerance", "gradient_tolerance", "parameter_tolerance") and S.final_cost < S.initial_cost
+    # the returned point is the last ACCEPTED one: its cost is the summary's final cost (the candidate that triggered the stop is dropped)
+    assert cpu_device.pgo_assemble(x, ids, meas)[0] == pytest.approx(S.final_cost, rel=1e-12)
+    assert S.iterations >= S.successful_steps + (1 if S.termination != "gradient_tolerance" else 0)
+    xd, Sd = api.pgo_optimize(None, nodes, ids, meas)
+    assert S.final_cost == pytest.approx(Sd.final_cost, rel=1e-3)            # both drivers end in the same valley
+    _, S1 = api.pgo_optimize_ceres(None, nodes, ids, meas, max_num_iterations=1)
+    assert S1.iterations == 1 and S1.termination == "max_num_iterations"
+    _, S0 = api.pgo_optimize_ceres(None, x, ids, meas, gradient_tolerance=1e30)
+    assert S0.iterations == 0 and S0.termination == "gradient_tolerance"
