@@ -1,0 +1,104 @@
+"""offline_odometry.radarReader — the scan-stream -> trajectory + simple graph loop (offline_odometry.cpp:57-141) — without a GPU: the device
+argument is an oracle-backed stand-in with the interface of offline_odometry.GpuOdometryDevice (test infrastructure only).  The strongest
+check is self-consistency: the cells a keyframe node stores must be exactly the cells one gets by building surface points from the
+(compensated) filtered cloud the same node stores — which holds only if the reader pairs every frame with the motion the fuser used."""
+import math
+
+import numpy as np
+import pytest
+
+from tbv_slam_public_b200 import graph_io as G, offline_odometry as OO, synth, trajectory_io as TIO
+
+
+class OracleOdometryDevice:
+    def __init__(self, **kw):
+        from oracle import oracle_py as O
+        O.lib()
+        self.O, self.params = O, O.default_odom_params(**kw)
+        self.od = O.Odometry(self.params)
+
+    def step(self, scan):
+        o = self.od.step(scan)
+        return dict(pose=np.array([o.pose[0], o.pose[1], o.pose[2]]), is_keyframe=bool(o.is_keyframe), n_keyframes=int(o.n_keyframes),
+                    n_cells=int(o.n_cells), score=0.0, itrs=int(o.itrs))          # the oracle's record carries no score
+
+    def newest_keyframe_cells(self, n_keyframes):
+        return self.od.keyframe_cells(n_keyframes - 1)
+
+    def clouds(self, scan, motion_xyt):
+        f = self.params                                              # the oracle's parameter record is flat
+        r = self.O.kstrongest(scan, f.z_min, f.k_strongest, f.min_distance, f.range_res, peaks=True)
+        out = []
+        for key in ("filtered", "peaks"):
+            _, _, I, x, y = r[key]
+            if self.params.compensate and len(x):
+                x, y = self.O.compensate(x, y, motion_xyt, bool(self.params.radar_ccw))
+            out.append(np.c_[x, y, np.zeros(len(x), np.float32), I.astype(np.float32)].astype(np.float32).reshape(-1, 4))
+        return out[0], out[1]
+
+
+@pytest.fixture(scope="module")
+def run():
+    st = synth.make_stream(26, speed=4.0)                     # 1 m per frame: a keyframe every other frame (threshold 1.5 m)
+    dev = OracleOdometryDevice()
+    rd = OO.radarReader(dev)
+    outs = [rd.process(st.scans[i], stamp_ns=1_000_000_000 + 250_000_000 * i, gt=st.gt[i]) for i in range(len(st.scans))]
+    return st, dev, rd, outs
+
+
+def test_every_frame_is_evaluated_and_keyframes_become_nodes(run):
+    st, dev, rd, outs = run
+    n_kf = sum(o["is_keyframe"] for o in outs)
+    assert len(rd.est) == len(st.scans) == len(rd.stamps) == len(rd.gt)
+    assert outs[0]["is_keyframe"] and 8 <= n_kf < len(st.scans) and len(rd.graph) == n_kf
+    assert rd.keyframe_rows == [i for i, o in enumerate(outs) if o["is_keyframe"]]
+    first, cons0 = rd.graph.graph[0]
+    assert cons0 == [] and np.array_equal(first.T, [0, 0, 0, 0, 0, 0, 1]) and np.array_equal(first.motion_, np.eye(4))
+    for r in range(1, n_kf):
+        scan, cons = rd.graph.graph[r]
+        assert scan.idx_ == r and scan.stamp_ == rd.stamps[rd.keyframe_rows[r]] and len(cons) == 1
+        c = cons[0]
+        assert (c.id_begin, c.id_end, c.type) == (r, r - 1, G.ODOMETRY)
+        assert np.allclose(scan.GetPose() @ G.pose3d_to_matrix(c.t_be), rd.graph.graph[r - 1][0].GetPose(), atol=1e-12)
+        assert np.allclose(G.pose3d_to_xyt(scan.T), outs[rd.keyframe_rows[r]]["pose"], atol=1e-12)
+        d = np.linalg.norm(scan.T[:2] - rd.graph.graph[r - 1][0].T[:2])
+        assert d > 1.5 or abs(G.pose3d_to_xyt(c.t_be)[2]) > math.radians(5.0)            # the keyframe rule
+
+
+def test_stored_cells_are_the_cells_of_the_stored_cloud(run):
+    st, dev, rd, outs = run
+    for r, (scan, _) in enumerate(rd.graph.graph):
+        c = scan.cloud_nopeaks_
+        rebuilt, _ = dev.O.build_cells(c[:, 0], c[:, 1], c[:, 3], radius=3.0, weight_intensity=True)
+        assert len(rebuilt) == len(scan.cloud_normal_) > 100, r
+        assert np.array_equal(rebuilt, scan.cloud_normal_), r                           # same points, same motion -> same bits
+        assert 0 < len(scan.cloud_peaks_) <= len(c) and np.array_equal(scan.downsampled_, scan.cloud_normal_[:, :2].astype(np.float32))
+    # and they would NOT match with the wrong motion (the check has teeth): re-derive one node's cloud without compensation
+    k = rd.keyframe_rows[5]
+    raw, _ = OracleOdometryDevice(compensate=0).clouds(st.scans[k], np.zeros(3))
+    assert not np.array_equal(raw[:, :2], rd.graph.graph[5][0].cloud_nopeaks_[:, :2])
+
+
+def test_save_writes_what_the_back_end_and_the_evaluation_read(run, tmp_path):
+    st, dev, rd, outs = run
+    paths = rd.Save(str(tmp_path), "07")
+    assert set(paths) == {"est", "gt", "graph"} and paths["est"].endswith("est/07.txt")
+    est, gt = TIO.read_kitti(paths["est"]), TIO.read_kitti(paths["gt"])
+    assert len(est) == len(gt) == len(st.scans)
+    g = G.load_simple_graph(paths["graph"])
+    assert len(g) == len(rd.graph) and all(s.has_Tgt_ for s, _ in g.graph)
+    for r, (s, _) in enumerate(g.graph):
+        assert np.allclose(G.pose3d_to_xyt(s.Tgt)[:2], st.gt[rd.keyframe_rows[r]][:2], atol=1e-12)
+    # odometry quality on the synthetic world: the estimate follows the ground truth (both re-based on their first pose)
+    res = TIO.evaluate(gt, est, "6dof", step_size=1)
+    assert res["ate"] < 0.25 and res["rpe_trans"] < 0.1
+    nodes, ids, meas, info, _ = g.pgo_arrays()
+    assert len(ids) == len(g) - 1 and np.all(ids[:, 2] == 0)
+
+
+def test_run_assigns_sensor_clock_stamps():
+    st = synth.make_stream(4)
+    rd = OO.radarReader(OracleOdometryDevice()).run(st.scans)
+    assert rd.stamps == [250_000_000 * (i + 1) for i in range(4)] and len(rd.graph) == 4 and not rd.gt
+    paths_free = rd.graph.graph[3][0]
+    assert paths_free.stamp_ == 1_000_000_000 and not paths_free.has_Tgt_
