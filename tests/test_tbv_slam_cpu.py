@@ -165,12 +165,13 @@ def closed(drive):
     g = _copy(g)
     dev = OracleLoopDevice()
     slam = TS.TBVSLAM(g, dev, _classifier(), TS.LoopClosureParams(), api.default_pgo_params(loop_scaling=1.0))
+    assert slam.ProcessFrame(False, True) is False                    # the search itself; the tests below look at what it left behind
     return slam, dev, g, gt, est
 
 
 def test_search_finds_and_verifies_the_revisits(closed):
     slam, dev, g, gt, est = closed
-    more = slam.ProcessFrame(False, True)
+    more = slam.ProcessFrame(False, True)                            # nothing left: no keyframe is processed twice
     assert more is False and slam.loop.itr_current == N_KF
     assert dev.calls["context"] == N_KF and len(dev.cells) == N_KF
     recs = slam.loop.statistics
@@ -362,3 +363,34 @@ def test_full_offline_flow_from_scans(tmp_path):
     assert max(np.hypot(*r.t_be[:2]) for r in applied) < 0.5
     out = str(tmp_path / "loop.csv")
     assert TS.write_loop_csv(out, g, slam.loop.statistics) == len(slam.loop.statistics)
+
+
+REF_LOOP_EVAL = "/root/reference/place_recognition_radar/python"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_LOOP_EVAL), reason="/root/reference not present (GPU box)")
+def test_the_references_own_loop_evaluation_accepts_our_loop_csv(closed, tmp_path):
+    """place_recognition_radar/python/LoopClosureEval.py — the script tbv_slam_offline tells the user to run on loop/loop.csv
+    (tbv_slam_offline.cpp:263-265) — run UNMODIFIED on the file write_loop_csv produced (matplotlib, which this image lacks, is stubbed:
+    it only draws).  Its loop / correct-candidate counts must be the ones our own restatement of its rules gives."""
+    import os
+    import subprocess
+    import sys
+    slam, dev, g, gt, est = closed
+    p = str(tmp_path / "loop.csv")
+    TS.write_loop_csv(p, g, slam.loop.statistics, "dataset,sequence", "synthetic,circle")
+    code = ("import sys, runpy; from unittest import mock\n"
+            "for m in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.widgets', 'mpl_toolkits', 'mpl_toolkits.mplot3d'): sys.modules[m] = mock.MagicMock()\n"
+            f"sys.path.insert(0, {REF_LOOP_EVAL!r})\n"
+            f"sys.argv = ['LoopClosureEval.py', '--output_folder', {str(tmp_path)!r}, '--csv_file', {p!r}, '--p-threshold', '0.8', '--save_roc', 'False',"
+            " '--disable-output', '1']\n"
+            f"runpy.run_path({os.path.join(REF_LOOP_EVAL, 'LoopClosureEval.py')!r}, run_name='__main__')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    res = dict(line.split(",", 1) for line in open(tmp_path / "result.txt").read().splitlines() if "," in line)
+    rows = [TS.update_statistics(g, rec) for rec in slam.loop.statistics if rec.guess_nr == 0]
+    n_loops = sum(TS.candidate_loop_status(row)[0] for row in rows)
+    e = [row["Tgt_diff"] for row in rows]
+    n_close = sum(float(np.hypot(m[0, 3], m[1, 3])) < 4 and abs(math.atan2(m[1, 0], m[1, 1])) < math.radians(2.5) for m in e)
+    assert int(res["nr loops"]) == n_loops == N_KF - N_LAP + 2 and int(res["nr correct candidates"]) == n_close
+    assert float(res["Testing precision [%]"]) == 100.0 and float(res["Testing recall [%]"]) > 80.0
