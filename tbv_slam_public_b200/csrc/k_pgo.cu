@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cooperative_groups.h>
 #include <numeric>
 
 #include "tbv_common.cuh"
@@ -367,6 +368,165 @@ pgo_pcg(int n, int fixed_node, const int* __restrict__ ids, const int* __restric
   if (tid == 0) { *out_iters = it; *out_rel = rel; }
 }
 
+// ---- the same solve on a thread-block CLUSTER (opt-in: TBV_PGO_CLUSTER=1; not yet run on a GPU — see DESIGN.md §7b) -----------------------
+// pgo_pcg is bound by one SM's latency chain (35 us per CG iteration measured at 600 nodes).  Here the nodes are split into contiguous ranges over
+// the PCGC_CL CTAs of one cluster, ONE ROW (node, component) PER THREAD, so an iteration is: a block-sparse product whose rows read 6-element
+// slices (blocks and vectors stream from L2, 1/PCGC_CL of them per SM), three cluster barriers (380 cycles each on this part) and two reductions
+// whose per-CTA partials are exchanged through distributed shared memory and summed in rank order by every CTA — the same bits everywhere, so
+// all CTAs take the same branch and the result does not depend on scheduling.  All 6 rows of a node live in one CTA: z = M^-1 r needs only a
+// __syncthreads.
+constexpr int PCGC_CL = 8;          // portable cluster size
+constexpr int PCGC_THREADS = 1024;
+
+__device__ __forceinline__ void pcgc_block_sum2(double& a, double& b, double (*s_w)[2]) {   // fixed tree per CTA; both values at once
+  for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { s_w[warp][0] = a; s_w[warp][1] = b; }
+  __syncthreads();
+  double ta = 0.0, tb = 0.0;
+  for (int w = 0; w < PCGC_THREADS / 32; w++) { ta += s_w[w][0]; tb += s_w[w][1]; }
+  a = ta; b = tb;
+}
+
+__global__ void __cluster_dims__(PCGC_CL, 1, 1) __launch_bounds__(PCGC_THREADS, 1)
+pgo_pcg_cluster(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
+                const double* __restrict__ Ho, const double* __restrict__ g, double radius, int max_iters, double rel_tol, double* __restrict__ x,
+                double* __restrict__ r, double* __restrict__ z, double* p, double* __restrict__ q, double* __restrict__ Minv, double* __restrict__ Dg,
+                int* __restrict__ out_iters, double* __restrict__ out_rel) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double s_w[PCGC_THREADS / 32][2];
+  __shared__ double s_part[2][2];                    // [0]: (p.q, -)   [1]: (r.z, r.r) — this CTA's partials, read by the whole cluster
+  const int tid = threadIdx.x, rank = (int)cluster.block_rank();
+  const int npc = (n + PCGC_CL - 1) / PCGC_CL;        // nodes per CTA
+  const int n0 = min(rank * npc, n), n1 = min(n0 + npc, n);
+  const int rows0 = 6 * n0, nrows = 6 * (n1 - n0);
+
+  // cluster-wide sums of (a, b): per-CTA fixed tree, then every CTA adds the PCGC_CL partials in rank order (DSMEM reads)
+  auto cluster_sum2 = [&](double& a, double& b, int slot) {
+    pcgc_block_sum2(a, b, s_w);
+    if (tid == 0) { s_part[slot][0] = a; s_part[slot][1] = b; }
+    cluster.sync();
+    double ta = 0.0, tb = 0.0;
+    for (int k = 0; k < PCGC_CL; k++) {
+      const double* remote = cluster.map_shared_rank(&s_part[slot][0], k);
+      ta += remote[0]; tb += remote[1];
+    }
+    a = ta; b = tb;
+  };
+
+  // ---- setup, one thread per owned node: damped diagonal block, its inverse, r = -g, z = M^-1 r, p = z, x = 0 --------------------------------------
+  for (int i = n0 + tid; i < n1; i += PCGC_THREADS) {
+    double A[6][6], L[6][6], Li[6][6];
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b < 6; b++) { A[a][b] = Hd[36 * (size_t)i + a * 6 + b]; L[a][b] = 0.0; Li[a][b] = 0.0; }
+    bool ok = i != fixed_node;
+    for (int a = 0; a < 6; a++) {
+      const double d = fmin(fmax(A[a][a], 1e-6), 1e32) / radius;
+      Dg[6 * (size_t)i + a] = d;
+      A[a][a] += d;
+    }
+    for (int j = 0; j < 6 && ok; j++) {
+      double d = A[j][j];
+      for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+      if (!(d > 0.0)) { ok = false; break; }
+      L[j][j] = sqrt(d);
+      for (int a = j + 1; a < 6; a++) {
+        double v = A[a][j];
+        for (int k = 0; k < j; k++) v -= L[a][k] * L[j][k];
+        L[a][j] = v / L[j][j];
+      }
+    }
+    if (ok)
+      for (int c = 0; c < 6; c++)
+        for (int a = 0; a < 6; a++) {
+          double v = (a == c) ? 1.0 : 0.0;
+          for (int k = 0; k < a; k++) v -= L[a][k] * Li[k][c];
+          Li[a][c] = v / L[a][a];
+        }
+    double rr[6];
+    for (int a = 0; a < 6; a++) rr[a] = (i == fixed_node) ? 0.0 : -g[6 * (size_t)i + a];
+    for (int a = 0; a < 6; a++) {
+      double zz = 0.0;
+      for (int b = 0; b < 6; b++) {
+        double v = 0.0;
+        if (ok) for (int k = 0; k < 6; k++) v += Li[k][a] * Li[k][b];
+        Minv[36 * (size_t)i + a * 6 + b] = v;
+        zz += v * rr[b];
+      }
+      x[6 * (size_t)i + a] = 0.0;
+      r[6 * (size_t)i + a] = rr[a];
+      z[6 * (size_t)i + a] = zz;
+      p[6 * (size_t)i + a] = zz;
+    }
+  }
+  __syncthreads();
+  double rz = 0.0, bb = 0.0;
+  for (int lr = tid; lr < nrows; lr += PCGC_THREADS) { rz += r[rows0 + lr] * z[rows0 + lr]; bb += r[rows0 + lr] * r[rows0 + lr]; }
+  cluster_sum2(rz, bb, 1);                           // also publishes p to the cluster (barrier.cluster release / acquire)
+  const double bnorm = sqrt(bb);
+  double rel = bnorm > 0.0 ? 1.0 : 0.0;
+  int it = 0;
+  while (it < max_iters && rel > rel_tol) {
+    // q = (H + D) p, own rows; p.q
+    double pq = 0.0, unused = 0.0;
+    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
+      const int R = rows0 + lr, i = R / 6, a = R - 6 * i;
+      double acc = 0.0;
+      if (i != fixed_node) {
+        const double* Hr = Hd + 36 * (size_t)i + 6 * a;
+        const double* pi = p + 6 * (size_t)i;
+        acc = Dg[R] * pi[a];
+        for (int b = 0; b < 6; b++) acc += Hr[b] * pi[b];
+        for (int e = row[i]; e < row[i + 1]; e++) {
+          const int c = inc[e] >> 1, side = inc[e] & 1;
+          const int other = side ? ids[3 * c] : ids[3 * c + 1];
+          const double* B = Ho + 36 * (size_t)c;
+          const double* u = p + 6 * (size_t)other;
+          // the other node may belong to another CTA: read its slice of p from L2 (the cluster barrier orders the writes; no stale L1 line)
+          if (side == 0) { for (int b = 0; b < 6; b++) acc += B[6 * a + b] * __ldcg(u + b); }
+          else           { for (int b = 0; b < 6; b++) acc += B[6 * b + a] * __ldcg(u + b); }
+        }
+      }
+      q[R] = acc;
+      pq += p[R] * acc;
+    }
+    cluster_sum2(pq, unused, 0);
+    if (!(pq > 0.0)) break;                          // same value in every CTA: the whole cluster leaves together
+    const double alpha = rz / pq;
+    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
+      const int R = rows0 + lr;
+      x[R] += alpha * p[R];
+      r[R] -= alpha * q[R];
+    }
+    __syncthreads();                                 // z needs the node's six residual rows (same CTA)
+    double rz_new = 0.0, rr_new = 0.0;
+    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
+      const int R = rows0 + lr, i = R / 6, a = R - 6 * i;
+      const double* Mr = Minv + 36 * (size_t)i + 6 * a;
+      const double* ri = r + 6 * (size_t)i;
+      double acc = 0.0;
+      for (int b = 0; b < 6; b++) acc += Mr[b] * ri[b];
+      z[R] = acc;
+      rz_new += ri[a] * acc;
+      rr_new += ri[a] * ri[a];
+    }
+    cluster_sum2(rz_new, rr_new, 1);
+    rel = sqrt(rr_new) / bnorm;
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
+      const int R = rows0 + lr;
+      p[R] = z[R] + beta * p[R];
+    }
+    cluster.sync();                                  // the next product reads other CTAs' rows of p
+    it++;
+  }
+  cluster.sync();                                    // no CTA may exit while another still reads its partials through DSMEM
+  if (rank == 0 && tid == 0) { *out_iters = it; *out_rel = rel; }
+}
+
 }  // namespace tbv
 
 using namespace tbv;
@@ -475,9 +635,16 @@ extern "C" int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const in
   if (e == cudaSuccess) e = cudaMemcpyAsync(drow.p, row.data(), (n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dinc.p, inc.data(), 2 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
-    pgo_pcg<<<1, PCG_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p, dz.p, dp.p,
-                                        dq.p, dmi.p, ddg.p, dit.p, drel.p);
-    launched(ctx, "pgo_pcg");
+    static const bool use_cluster = getenv("TBV_PGO_CLUSTER") != nullptr;   // opt-in until the cluster kernel has been run and timed on a B200
+    if (use_cluster) {
+      pgo_pcg_cluster<<<PCGC_CL, PCGC_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p,
+                                                         dz.p, dp.p, dq.p, dmi.p, ddg.p, dit.p, drel.p);
+      launched(ctx, "pgo_pcg_cluster");
+    } else {
+      pgo_pcg<<<1, PCG_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p, dz.p, dp.p,
+                                          dq.p, dmi.p, ddg.p, dit.p, drel.p);
+      launched(ctx, "pgo_pcg");
+    }
     e = cudaGetLastError();
   }
   int h_it = 0;
