@@ -1,0 +1,46 @@
+"""Host-side pieces of bench.py that need no GPU: the MEASURED_PEAKS.json lookup, the per-rank workload layout, the algorithmic byte
+counts the roofline is computed from."""
+import importlib.util
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_hbm_peak_lookup_is_layout_tolerant():
+    b = _bench()
+    assert b.pick_hbm_peak({}) == (6650.0, None)                                           # the profiling recipe's fallback
+    assert b.pick_hbm_peak({"hbm_gbs": 6533.8, "bf16_tflops": 1800.0}) == (6533.8, "hbm_gbs")
+    assert b.pick_hbm_peak({"hbm": {"burst_gbs": 7100.0, "sustained_gbs": 6533.8}, "bf16": {"tflops": 1700}}) == (6533.8, "hbm.sustained_gbs")
+    assert b.pick_hbm_peak({"copy_bandwidth_tbs": 6.5338})[0] == 6533.8
+    assert b.pick_hbm_peak({"HBM_GBps_burst": 7000, "HBM_GBps_sustained": 6500, "dense_bf16_TFs": 1900}) == (6500.0, "HBM_GBps_sustained")
+    assert b.pick_hbm_peak({"l2_bandwidth_gbs": 9000.0, "bf16_tflops": 1800.0}) == (6650.0, None)   # nothing that is an HBM figure
+
+
+def test_k1_algorithmic_bytes_match_the_survey_figure():
+    """K1 per Oxford scan, k = 40, reads 400 x 3768 bytes; the bench counts the scan bytes plus what K1 itself writes."""
+    b = _bench()
+    S = 592
+    st = {"n_points": 4500.0, "n_samples": 1060.0, "n_cells": 464.0, "n_keyframes": 4}
+    per_scan = b.algorithmic_bytes("k1_kstrongest", S, st) / S
+    assert per_scan == 400 * 3768 + 400 * 40 * 4 + 400 * 2                                  # scan bytes in, row keys + counts out
+    assert 400 * 3768 <= per_scan <= 400 * 3768 + 208000                                    # within SURVEY's K1 figure (its output is the final cloud)
+    assert b.algorithmic_bytes("k_odom_update", S, st) is None                              # pose algebra: not HBM-shaped
+    assert b.algorithmic_bytes("cells_fused", S, st) == S * (9 * 4500.0 + 128 * 464.0)
+
+
+def test_first_offsets_give_every_rank_the_same_mix_of_places():
+    b = _bench()
+    n_seq, n_frames = 8 * b.N_PLACES, 25
+    a, c = b.first_offsets(n_seq, n_frames, 0), b.first_offsets(n_seq, n_frames, 3)
+    assert len(a) == len(c) == n_seq and not np.array_equal(a, c)
+    place = lambda v: sorted(((np.asarray(v) - (np.arange(n_seq) * 5) % b.POOL_EXTRA) // n_frames).tolist())
+    assert place(a) == place(c) == sorted(list(range(b.N_PLACES)) * 8)                      # every rank: the same mix of stretches
