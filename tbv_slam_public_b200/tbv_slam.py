@@ -67,11 +67,18 @@ def transform_cloud(cloud4: np.ndarray, xyt) -> np.ndarray:
 class GpuLoopDevice:
     """The device calls of the loop-closure thread, one method per reference call site."""
 
-    def __init__(self, ctx, max_keyframes: int, cell_capacity: int = 1024, sc_params=None):
+    def __init__(self, ctx, max_keyframes: int, cell_capacity: int = 1024, sc_params=None, sharded: bool = False, group=None):
+        """sharded: register candidates through parallel.ShardedLoopClosure — every rank of the torch.distributed group holds the whole
+        keyframe database and registers the candidates with id_from mod world == rank; the accepted constraints are all-gathered.
+        All ranks must then run the same search (same graph, same calls); useful with SearchAndAddConstraintBatched."""
         from . import api
         self.api, self.ctx = api, ctx
         self.rsc = api.RSCManager(ctx, sc_params)
         self.db = api.LoopDB(ctx, max_keyframes, cell_capacity)
+        self.sharded = None
+        if sharded:
+            from . import parallel
+            self.sharded = parallel.ShardedLoopClosure(self.db, group)
 
     def close(self):
         self.db.close()
@@ -89,15 +96,18 @@ class GpuLoopDevice:
 
     # loopclosure::Register for all candidates of a keyframe (:35-97): -> per candidate (ok, t_be xyt, cov (xx, xy, yy, tt), score)
     def register(self, id_from, id_to, T_from, T_to):
-        out, summ = self.db.register_candidates(id_from, id_to, T_from, T_to, want_summaries=True)
+        if self.sharded is not None:
+            out, summ = self.sharded.register_candidates(id_from, id_to, T_from, T_to), None
+        else:
+            out, summ = self.db.register_candidates(id_from, id_to, T_from, T_to, want_summaries=True)
         acc = {int(c["candidate"]): c for c in out}
         res = []
         for p in range(len(id_from)):
             if p in acc:
                 c = acc[p]
                 res.append((True, np.array(c["t_be"]), np.array(c["cov"]), float(c["score"])))
-            else:
-                res.append((False, np.zeros(3), np.array([1.0, 0.0, 1.0, 1.0]), float(summ[p].score)))
+            else:                                                     # Register returned false: Tdiff stays Identity, Cov Identity (:344-352)
+                res.append((False, np.zeros(3), np.array([1.0, 0.0, 1.0, 1.0]), float(summ[p].score) if summ is not None else 0.0))
         return res
 
     # getCorAlQualityMeasure / getCFEARQualityMeasure for all candidates of a keyframe (alignmentinterface.cpp:437-475)
@@ -263,70 +273,128 @@ class ScanContextClosure:
                 break
             self._process_keyframe(self.itr_current)
             self.itr_current += 1
-        if self.itr_current == n and self.model_training_file_save and self.verification_classifier is not None \
-                and self.verification_classifier.DataValid():
-            self.verification_classifier.fit()                        # SaveVerificationTrainingData (:253-259)
-            self.verification_classifier.SaveData(self.model_training_file_save)
+        if self.itr_current == n:
+            self._maybe_fit_verification_model()
         return self.itr_current != n
 
+    def _maybe_fit_verification_model(self):
+        if self.model_training_file_save and self.verification_classifier is not None and self.verification_classifier.DataValid() \
+                and not self.verification_classifier.IsFit():
+            self.verification_classifier.fit()                        # SaveVerificationTrainingData (:253-259)
+            self.verification_classifier.SaveData(self.model_training_file_save)
+
+    # ---- one keyframe = four stages; the batched search runs each stage once for ALL keyframes -----------------------------------------
     def _process_keyframe(self, row: int):
+        plan = self._plan_keyframe(row)
+        if plan is not None:
+            self._register_plans([plan])
+            self._verify_plans([plan])
+            self._finish_keyframe(plan)
+
+    def SearchAndAddConstraintBatched(self) -> bool:
+        """The whole remaining graph at once.  In the offline flow nothing a keyframe does depends on an earlier keyframe's loop result
+        (poses change only in ForceOptimize, after the search: tbv_slam_offline.cpp:279-282), so the per-keyframe loop can be cut into its
+        stages: the Scan-Context sweep (sequential: the database grows), then ONE registration call for every candidate of every keyframe
+        (the call parallel.ShardedLoopClosure shards over GPUs), ONE CorAl and ONE CFEAR call for all of them, then the host bookkeeping
+        per keyframe in order.  Same records in the same order, same constraints as SearchAndAddConstraint (tests/test_tbv_slam_cpu.py)."""
+        n = len(self.graph.graph)
+        plans = []
+        while self.itr_current < n:
+            plan = self._plan_keyframe(self.itr_current)
+            if plan is not None:
+                plans.append(plan)
+            self.itr_current += 1
+        self._register_plans(plans)
+        self._verify_plans(plans)
+        for plan in plans:
+            self._finish_keyframe(plan)
+        self._maybe_fit_verification_model()
+        return False
+
+    def _plan_keyframe(self, row: int):
+        """Stage A (:636-699): context, Scan-Context candidates, registration guesses.  Returns None when the keyframe needs nothing more."""
         scan = self.graph.graph[row][0]
         while self.n_resident <= row:                                 # cells of every keyframe up to this one are on the device
             self.dev.add_keyframe(self.graph.graph[self.n_resident][0].cloud_normal_)
             self.n_resident += 1
         if len(self.graph.graph) == 1:                                # itr_begin == itr_end (:640)
-            return
+            return None
         pose = G.pose3d_to_xyt(scan.T)
         self.dev.make_context(self.ScansToLocalMap(row), pose)        # CreateContext (:573-592): the node's own pose is the odometry pose
         candidates = self.dev.detect()
+        plan = dict(row=row, pose=pose, entries=[], batch=[])         # entries: per guess, a finished record or the index into batch
         if not candidates:
-            self.statistics.append(CandidateRecord(scan.idx_, scan.idx_, -1, np.zeros(3),
+            plan["entries"].append(CandidateRecord(scan.idx_, scan.idx_, -1, np.zeros(3),
                                                    {ODOM_BOUNDS: 1.0, SC_SIM: 1.0 + float(self.odometry_coupled_closure), COMBINED_COST: -20.0},
                                                    0.0, False))
-            return
-        rows = self._row_of()
-        batch = []                                                    # (guess_nr, candidate dict, row_to, T_to_guess)
+            return plan
         for guess_nr, cand in enumerate(candidates):
             id_to = int(cand["nn_idx"])                               # database index = order of makeAndSave calls = graph row
             scan_to = self.graph.graph[id_to][0]
             if self.odometry_coupled_closure and self.par.speedup and cand["min_dist_odom"] > 0.7:
-                self.statistics.append(CandidateRecord(scan.idx_, scan_to.idx_, guess_nr, np.zeros(3),
+                plan["entries"].append(CandidateRecord(scan.idx_, scan_to.idx_, guess_nr, np.zeros(3),
                                                        {ODOM_BOUNDS: cand["min_dist_odom"], SC_SIM: cand["min_dist"], COMBINED_COST: -20.0}, 0.0, False))
                 continue
             # Tsrcguess = Taug^-1 * Rz(yaw) (:691-696); Tto = Tfrom * guess (:337-338)
             ax, ay = (cand["aug_xy"] if self.par.transl_guess else (0.0, 0.0))
             guess = _mat3((-float(ax), -float(ay), 0.0)) @ _mat3((0.0, 0.0, float(cand["yaw_diff_rad"])))
-            batch.append((guess_nr, cand, id_to, _xyt(_mat3(pose) @ guess)))
-        if not batch:
+            plan["entries"].append(len(plan["batch"]))
+            plan["batch"].append((guess_nr, cand, id_to, _xyt(_mat3(pose) @ guess)))
+        return plan
+
+    def _register_plans(self, plans):
+        """Stage B: loopclosure::Register for every candidate of every plan in one device call (:704 -> :320-364 -> :35-97)."""
+        todo = [(pl, b) for pl in plans for b in pl["batch"]]
+        for pl in plans:
+            pl["reg"] = []
+        if not todo:
             return
-        k = len(batch)
-        T_from = np.tile(pose, (k, 1))
-        T_to = np.array([b[3] for b in batch]).reshape(k, 3)
-        ids_to = [b[2] for b in batch]
         if self.par.registration_disabled:                            # Tdiff = Tfrom^-1 * T(to) (:349)
-            reg = [(True, _xyt(np.linalg.inv(_mat3(pose)) @ _mat3(G.pose3d_to_xyt(self.graph.graph[r][0].T))), np.array([1.0, 0.0, 1.0, 1.0]), 0.0)
-                   for r in ids_to]
-        else:
-            reg = self.dev.register([row] * k, ids_to, T_from, T_to)
-        # VerifyLoopCandidate (:365-384): from at its graph pose, to at Tfrom * t_be
-        t_be = np.array([r[1] for r in reg]).reshape(k, 3)
-        T_to_reg = np.array([_xyt(_mat3(pose) @ _mat3(t)) for t in t_be]).reshape(k, 3)
+            for pl, b in todo:
+                Tto = _mat3(G.pose3d_to_xyt(self.graph.graph[b[2]][0].T))
+                pl["reg"].append((True, _xyt(np.linalg.inv(_mat3(pl["pose"])) @ Tto), np.array([1.0, 0.0, 1.0, 1.0]), 0.0))
+            return
+        reg = self.dev.register([pl["row"] for pl, _ in todo], [b[2] for _, b in todo], np.array([pl["pose"] for pl, _ in todo]).reshape(-1, 3),
+                                np.array([b[3] for _, b in todo]).reshape(-1, 3))
+        for (pl, _), r in zip(todo, reg):
+            pl["reg"].append(r)
+
+    def _verify_plans(self, plans):
+        """Stage C: VerifyByAlignment for every candidate of every plan — one CorAl call, one CFEAR call (:708 -> :365-384 -> :759-775).
+        PredAlignment(current = from, prev = to) -> CreateQualityType(ref = current, src = prev) (alignmentinterface.cpp:349-353, 437-475;
+        AlignmentQuality.h:263): the candidate (`to`, at Tfrom * t_be) is the MOVING / src scan, the query keyframe the reference one."""
+        todo = [(pl, j) for pl in plans for j in range(len(pl["batch"]))]
+        for pl in plans:
+            pl["X"] = np.zeros((len(pl["batch"]), 6))
+        if not todo:
+            return
+        used = sorted({pl["row"] for pl, _ in todo} | {pl["batch"][j][2] for pl, j in todo})
+        slot = {r: i for i, r in enumerate(used)}
         cloud = lambda s: (s.cloud_peaks_[:, 0], s.cloud_peaks_[:, 1], s.cloud_peaks_[:, 3])
-        uniq = sorted(set(ids_to))
-        slot = {r: i + 1 for i, r in enumerate(uniq)}
-        clouds = [cloud(scan)] + [cloud(self.graph.graph[r][0]) for r in uniq]
-        cellsets = [scan.cloud_normal_] + [self.graph.graph[r][0].cloud_normal_ for r in uniq]
-        # PredAlignment(current = from, prev = to) -> CreateQualityType(ref = current, src = prev) (alignmentinterface.cpp:349-353, 437-475;
-        # AlignmentQuality.h:263): the candidate (`to`, at Tfrom * t_be) is the MOVING / src scan, the query keyframe the reference one
-        src, ref = [slot[r] for r in ids_to], [0] * k
-        x_coral = self.dev.coral(clouds, src, ref, T_to_reg, T_from)
-        x_cfear = self.dev.cfear(cellsets, src, ref, T_to_reg, T_from)
-        X = np.concatenate([np.asarray(x_coral, np.float64).reshape(k, 3), np.asarray(x_cfear, np.float64).reshape(k, 3)], axis=1)
-        alignment_quality = self.alignment_classifier.predict_linear(X)          # quality[COMBINED_COST] = predict_linear (PredAlignment :355-360)
+        clouds = [cloud(self.graph.graph[r][0]) for r in used]
+        cellsets = [self.graph.graph[r][0].cloud_normal_ for r in used]
+        src = [slot[pl["batch"][j][2]] for pl, j in todo]
+        ref = [slot[pl["row"]] for pl, _ in todo]
+        T_from = np.array([pl["pose"] for pl, _ in todo]).reshape(-1, 3)
+        T_to_reg = np.array([_xyt(_mat3(pl["pose"]) @ _mat3(pl["reg"][j][1])) for pl, j in todo]).reshape(-1, 3)   # to at Tfrom * t_be
+        x_coral = np.asarray(self.dev.coral(clouds, src, ref, T_to_reg, T_from), np.float64).reshape(-1, 3)
+        x_cfear = np.asarray(self.dev.cfear(cellsets, src, ref, T_to_reg, T_from), np.float64).reshape(-1, 3)
+        for (pl, j), xc, xf in zip(todo, x_coral, x_cfear):
+            pl["X"][j] = np.concatenate([xc, xf])
+
+    def _finish_keyframe(self, plan):
+        """Stage D: quality -> probability -> statistics -> ApplyConstratins, in guess order (:700-724)."""
+        scan = self.graph.graph[plan["row"]][0]
+        k = len(plan["batch"])
+        alignment_quality = self.alignment_classifier.predict_linear(plan["X"]) if k else []   # quality[COMBINED_COST] (PredAlignment :355-360)
         evaluated = []
-        for j, (guess_nr, cand, id_to, _) in enumerate(batch):
+        for entry in plan["entries"]:
+            if isinstance(entry, CandidateRecord):                    # no candidate / skipped by `speedup`
+                self.statistics.append(entry)
+                continue
+            guess_nr, cand, id_to, _ = plan["batch"][entry]
             scan_to = self.graph.graph[id_to][0]
-            quality = {ODOM_BOUNDS: 0.0, SC_SIM: float(cand["min_dist"]), COMBINED_COST: float(alignment_quality[j])}   # CreateAppearanceConstraint
+            quality = {ODOM_BOUNDS: 0.0, SC_SIM: float(cand["min_dist"]), COMBINED_COST: float(alignment_quality[entry])}   # CreateAppearanceConstraint
             quality[ODOM_BOUNDS] = V.VerifyByOdometry(self._odometry_chain(scan_to.idx_, scan.idx_), self.par.odom_sigma_error,
                                                       self.par.verify_via_odometry)
             if self.par.verification_disabled:
@@ -334,7 +402,7 @@ class ScanContextClosure:
             else:
                 feats = [quality[f] for f in self.par.model_features]
                 prob = V.VerificationModel(feats[0], feats[1], feats[2], self.verification_classifier)
-            ok, t, cov4, _score = reg[j]
+            ok, t, cov4, _score = plan["reg"][entry]
             cov6 = np.eye(6)
             if ok and not self.par.registration_disabled:             # reg_cov of the moving scan, xy block rotated (:91-94); singular like the reference's
                 cov6 = np.diag([0.0, 0.0, 0.0, 0.0, 0.0, float(cov4[3])])
@@ -374,8 +442,8 @@ class TBVSLAM:
         self.loop = ScanContextClosure(graph, device, alignment_classifier, loop_params, verification_classifier, odometry_coupled_closure)
         self.last_optimization: OptimizeResult | None = None
 
-    def ProcessFrame(self, optimize: bool, loopclosure: bool) -> bool:
-        more = self.loop.SearchAndAddConstraint() if loopclosure else False
+    def ProcessFrame(self, optimize: bool, loopclosure: bool, batched: bool = False) -> bool:
+        more = (self.loop.SearchAndAddConstraintBatched() if batched else self.loop.SearchAndAddConstraint()) if loopclosure else False
         if optimize:
             self.ForceOptimize()
         return more
@@ -396,9 +464,9 @@ class TBVSLAM:
         self.last_optimization = res
         return res
 
-    def Run(self) -> OptimizeResult:
-        """SLAMEval::RunBasicEvaluation (tbv_slam_offline.cpp:269-285)."""
-        while self.ProcessFrame(False, True):
+    def Run(self, batched: bool = False) -> OptimizeResult:
+        """SLAMEval::RunBasicEvaluation (tbv_slam_offline.cpp:269-285); batched = the whole search as one call per stage."""
+        while self.ProcessFrame(False, True, batched):
             pass
         self.ProcessFrame(True, False)
         return self.last_optimization

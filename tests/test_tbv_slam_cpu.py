@@ -394,3 +394,36 @@ def test_the_references_own_loop_evaluation_accepts_our_loop_csv(closed, tmp_pat
     n_close = sum(float(np.hypot(m[0, 3], m[1, 3])) < 4 and abs(math.atan2(m[1, 0], m[1, 1])) < math.radians(2.5) for m in e)
     assert int(res["nr loops"]) == n_loops == N_KF - N_LAP + 2 and int(res["nr correct candidates"]) == n_close
     assert float(res["Testing precision [%]"]) == 100.0 and float(res["Testing recall [%]"]) > 80.0
+
+
+def test_batched_search_equals_the_per_keyframe_search(drive):
+    """SearchAndAddConstraintBatched (one registration / CorAl / CFEAR call for the whole graph) against SearchAndAddConstraint (one of each
+    per keyframe): identical records in identical order, identical constraints — also with `speedup` skipping candidates and with all
+    candidates applied — and 1 device call per stage instead of one per keyframe."""
+    g, gt, est = drive
+    for par in (TS.LoopClosureParams(), TS.LoopClosureParams(speedup=True, all_candidates=True, model_threshold=0.5)):
+        seq_dev, bat_dev = OracleLoopDevice(), OracleLoopDevice()
+        a = TS.ScanContextClosure(_copy(g), seq_dev, _classifier(), par)
+        b = TS.ScanContextClosure(_copy(g), bat_dev, _classifier(), par)
+        assert a.SearchAndAddConstraint() is False and b.SearchAndAddConstraintBatched() is False
+        assert len(a.statistics) == len(b.statistics) > N_KF
+        for ra, rb in zip(a.statistics, b.statistics):
+            assert (ra.id_from, ra.id_to, ra.guess_nr, ra.reg_ok, ra.applied, ra.probability) == (rb.id_from, rb.id_to, rb.guess_nr, rb.reg_ok, rb.applied, rb.probability)
+            assert np.array_equal(ra.t_be, rb.t_be) and ra.quality == rb.quality
+        assert a.loop_constraints.keys() == b.loop_constraints.keys() and len(a.loop_constraints) >= 6
+        for k in a.loop_constraints:
+            assert np.array_equal(a.loop_constraints[k].t_be, b.loop_constraints[k].t_be)
+        assert bat_dev.calls["register"] == bat_dev.calls["coral"] == bat_dev.calls["cfear"] == 1 < seq_dev.calls["register"]
+        assert bat_dev.calls["context"] == seq_dev.calls["context"] == N_KF
+    # records of one keyframe come in guess order, skipped ones included
+    last = {}
+    for r in b.statistics:
+        if r.id_from in last:
+            assert r.guess_nr > last[r.id_from]
+        last[r.id_from] = r.guess_nr
+    # and the driver takes the switch
+    slam = TS.TBVSLAM(_copy(g), OracleLoopDevice(), _classifier(), TS.LoopClosureParams(), api.default_pgo_params(loop_scaling=1.0))
+    res = slam.Run(batched=True)
+    seq = TS.TBVSLAM(_copy(g), OracleLoopDevice(), _classifier(), TS.LoopClosureParams(), api.default_pgo_params(loop_scaling=1.0))
+    ref = seq.Run()
+    assert res.n_loop_constraints == ref.n_loop_constraints >= 6 and np.array_equal(res.poses_after, ref.poses_after)

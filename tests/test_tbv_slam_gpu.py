@@ -43,3 +43,27 @@ def test_offline_slam_closes_the_loop_on_the_gpu(ctx, drive):
     assert res.n_loop_constraints == len(slam.loop.loop_constraints) and res.summary.final_cost < res.summary.initial_cost
     assert e_before > 1.0 and e_after < 0.5 * e_before
     dev.close()
+
+
+def test_batched_and_sharded_search_equal_the_per_keyframe_search_on_the_gpu(ctx, drive):
+    """One registration / CorAl / CFEAR launch for the whole graph (SearchAndAddConstraintBatched), directly and through the sharded front end
+    (parallel.ShardedLoopClosure, world size 1 here; 2 GPUs: tests/tools/loop_bench.py), against one launch per keyframe: every kernel works on
+    one candidate per CTA, so the records must be the same whatever the batch they arrived in."""
+    g, gt, est = drive
+    runs = []
+    for kw, batched in ((dict(), False), (dict(), True), (dict(sharded=True), True)):
+        dev = TS.GpuLoopDevice(ctx, max_keyframes=64, **kw)
+        loop = TS.ScanContextClosure(copy.deepcopy(g), dev, _classifier(), TS.LoopClosureParams())
+        n0 = ctx.launch_count()
+        assert (loop.SearchAndAddConstraintBatched() if batched else loop.SearchAndAddConstraint()) is False
+        runs.append((loop, ctx.launch_count() - n0))
+        dev.close()
+    ref, n_ref = runs[0]
+    assert len(ref.loop_constraints) >= 6
+    for loop, n_launch in runs[1:]:
+        assert n_launch < n_ref                                       # fewer, larger launches
+        assert len(loop.statistics) == len(ref.statistics)
+        for a, b in zip(ref.statistics, loop.statistics):
+            assert (a.id_from, a.id_to, a.guess_nr, a.reg_ok, a.applied) == (b.id_from, b.id_to, b.guess_nr, b.reg_ok, b.applied)
+            assert np.allclose(a.t_be, b.t_be, rtol=0, atol=1e-12) and abs(a.probability - b.probability) <= 1e-12
+        assert loop.loop_constraints.keys() == ref.loop_constraints.keys()
