@@ -44,7 +44,7 @@ def main():
         sli.FitModels()
         clf = sli.combined_class
     slam = TS.TBVSLAM(g, dev, clf, TS.LoopClosureParams(), api.default_pgo_params(loop_scaling=args.loop_scaling))
-    res = slam.Run()
+    res = slam.Run(batched=True)          # one registration / CorAl / CFEAR launch for the whole sequence
     os.makedirs(os.path.join(args.out, "loop"), exist_ok=True)
     os.makedirs(os.path.join(args.out, "est_slam"), exist_ok=True)
     n_rows = TS.write_loop_csv(os.path.join(args.out, "loop", "loop.csv"), g, slam.loop.statistics, "dataset,sequence", "synthetic,00")
