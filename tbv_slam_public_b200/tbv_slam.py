@@ -15,11 +15,13 @@ oracle in); the product default fails loudly when there is no GPU (api.Context r
 from __future__ import annotations
 
 import math
+import time
 from dataclasses import dataclass, field
 
 import numpy as np
 
 from . import graph_io as G
+from . import statistics as STAT
 from . import verification as V
 
 ODOM_BOUNDS, SC_SIM, COMBINED_COST = "odom-bounds", "sc-sim", "alignment_quality"      # tbv_slam/include/tbv_slam/utils.h:43-47
@@ -228,6 +230,7 @@ class ScanContextClosure:
         self.itr_current = 0                              # row of the next keyframe to process
         self.n_resident = 0                               # rows whose cells are in the device database
         self.statistics: list[CandidateRecord] = []
+        self.timing = STAT.statistics()                   # CFEAR_Radarodometry::timing under the reference's keys (loopclosure.cpp:647-731), host wall ms
         self.loop_constraints: dict[tuple[int, int], G.Constraint3d] = {}     # constraints_[loop_appearance], keyed (min, max)
 
     # ---- helpers ---------------------------------------------------------------------------------------------------------------------
@@ -320,8 +323,13 @@ class ScanContextClosure:
         if len(self.graph.graph) == 1:                                # itr_begin == itr_end (:640)
             return None
         pose = G.pose3d_to_xyt(scan.T)
+        t1 = time.perf_counter()
         self.dev.make_context(self.ScansToLocalMap(row), pose)        # CreateContext (:573-592): the node's own pose is the odometry pose
+        t2 = time.perf_counter()
         candidates = self.dev.detect()
+        t3 = time.perf_counter()
+        self.timing.Document("Descriptor", 1e3 * (t2 - t1))
+        self.timing.Document("Detect loop", 1e3 * (t3 - t2))
         plan = dict(row=row, pose=pose, entries=[], batch=[])         # entries: per guess, a finished record or the index into batch
         if not candidates:
             plan["entries"].append(CandidateRecord(scan.idx_, scan.idx_, -1, np.zeros(3),
@@ -354,8 +362,10 @@ class ScanContextClosure:
                 Tto = _mat3(G.pose3d_to_xyt(self.graph.graph[b[2]][0].T))
                 pl["reg"].append((True, _xyt(np.linalg.inv(_mat3(pl["pose"])) @ Tto), np.array([1.0, 0.0, 1.0, 1.0]), 0.0))
             return
+        t0 = time.perf_counter()
         reg = self.dev.register([pl["row"] for pl, _ in todo], [b[2] for _, b in todo], np.array([pl["pose"] for pl, _ in todo]).reshape(-1, 3),
                                 np.array([b[3] for _, b in todo]).reshape(-1, 3))
+        self.timing.Document("Register", 1e3 * (time.perf_counter() - t0))          # one sample per CALL: all its candidates together
         for (pl, _), r in zip(todo, reg):
             pl["reg"].append(r)
 
@@ -377,8 +387,10 @@ class ScanContextClosure:
         ref = [slot[pl["row"]] for pl, _ in todo]
         T_from = np.array([pl["pose"] for pl, _ in todo]).reshape(-1, 3)
         T_to_reg = np.array([_xyt(_mat3(pl["pose"]) @ _mat3(pl["reg"][j][1])) for pl, j in todo]).reshape(-1, 3)   # to at Tfrom * t_be
+        t0 = time.perf_counter()
         x_coral = np.asarray(self.dev.coral(clouds, src, ref, T_to_reg, T_from), np.float64).reshape(-1, 3)
         x_cfear = np.asarray(self.dev.cfear(cellsets, src, ref, T_to_reg, T_from), np.float64).reshape(-1, 3)
+        self.timing.Document("VerifyByAlignment", 1e3 * (time.perf_counter() - t0))
         for (pl, j), xc, xf in zip(todo, x_coral, x_cfear):
             pl["X"][j] = np.concatenate([xc, xf])
 
@@ -418,10 +430,12 @@ class ScanContextClosure:
                     self.verification_classifier.AddDataPoint([[quality[f] for f in self.par.model_features]], [float(is_loop)])
             evaluated.append((prob, con, rec))
         # ApplyConstratins (:261-275)
+        t0 = time.perf_counter()
         for i in V.apply_constraints([e[0] for e in evaluated], self.par.model_threshold, self.par.all_candidates):
             _, con, rec = evaluated[i]
             rec.applied = True
             self.loop_constraints[(min(con.id_begin, con.id_end), max(con.id_begin, con.id_end))] = con
+        self.timing.Document("Apply contraints", 1e3 * (time.perf_counter() - t0))  # sic
 
 
 @dataclass
@@ -458,7 +472,9 @@ class TBVSLAM:
         nodes, ids, meas, info, _ = self.graph.pgo_arrays()
         res = OptimizeResult(n_loop_constraints=int((ids[:, 2] == 1).sum()) if len(ids) else 0, poses_before=self.graph.poses_xyt())
         replace = True if self.pgo_params is None else bool(self.pgo_params.replace_cov_by_identity)
+        t0 = time.perf_counter()
         new_nodes, res.summary = self.dev.optimize(nodes, ids, meas, None if replace else info, self.pgo_params, **solver_options)
+        self.loop.timing.Document("Pose grapgh optimization", 1e3 * (time.perf_counter() - t0))   # sic (posegraph.cpp:126)
         self.graph.set_poses(new_nodes)
         res.poses_after = self.graph.poses_xyt()
         self.last_optimization = res

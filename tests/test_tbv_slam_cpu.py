@@ -200,6 +200,17 @@ def test_search_finds_and_verifies_the_revisits(closed):
         assert set(r.quality) == {TS.ODOM_BOUNDS, TS.SC_SIM, TS.COMBINED_COST} and 0.0 <= r.quality[TS.ODOM_BOUNDS] <= 1.0
 
 
+def test_stage_times_are_documented_under_the_references_keys(closed):
+    slam, dev, g, gt, est = closed
+    t = slam.loop.timing.t
+    assert len(t["Descriptor"]) == len(t["Detect loop"]) == N_KF                     # one sample per keyframe (loopclosure.cpp:647-652)
+    with_cand = len({r.id_from for r in slam.loop.statistics if r.guess_nr >= 0})
+    assert len(t["Register"]) == len(t["VerifyByAlignment"]) == with_cand
+    assert len(t["Apply contraints"]) == N_KF                                        # called for every keyframe, candidates or not (:723-726)
+    text = slam.loop.timing.GetStatistics()
+    assert "Descriptor avg, " in text and "Detect loop count, %d" % N_KF in text and all(v >= 0 for k in t for v in t[k])
+
+
 def test_loop_constraints_are_what_the_graph_will_hold(closed):
     slam, dev, g, gt, est = closed
     for (a, b), c in slam.loop.loop_constraints.items():
