@@ -118,3 +118,112 @@ class radarReader:
             self.graph.AddGroundTruth(self.stamps, self.gt)
         G.save_simple_graph(paths["graph"], self.graph)
         return paths
+
+
+# ---- the fuser with the reference's OWN interface: point clouds in ------------------------------------------------------------------------
+# OdometryKeyframeFuser::pointcloudCallback(cloud_filtered, cloud_filtered_peaks, Tcurr, t) (odometrykeyframefuser.cpp:395-411) takes CLOUDS,
+# whatever filter produced them (k-strongest, CA-CFAR: radar_driver.cpp:48-62, or a caller's own).  tbv_odom_step fuses the k-strongest
+# filter into the frame and is the fast path; this class is the general one: the same processFrame (:143-259) as host bookkeeping over
+# the primitive device calls tbv_compensate, tbv_build_cells and tbv_register — one launch each per frame.
+class GpuPrimitiveDevice:
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def compensate(self, x, y, mot, ccw):
+        return self.ctx.Compensate(x, y, mot, ccw)
+
+    def build_cells(self, x, y, intensity, radius, downsample_factor, weight_intensity):
+        cells, _ = self.ctx.MapPointNormal(x, y, intensity, radius, downsample_factor, weight_intensity)
+        return cells
+
+    def register(self, scans, T, reg_params):
+        Tio, s = self.ctx.Register(scans, T, reg_params)
+        return Tio, bool(s.success), int(s.itrs), float(s.score)
+
+
+class _Affine:
+    """Planar Eigen::Affine3d as the reference multiplies it (2x2 linear part + translation), operation order of Eigen's products."""
+    __slots__ = ("r00", "r01", "r10", "r11", "tx", "ty")
+
+    def __init__(self, r00=1.0, r01=0.0, r10=0.0, r11=1.0, tx=0.0, ty=0.0):
+        self.r00, self.r01, self.r10, self.r11, self.tx, self.ty = r00, r01, r10, r11, tx, ty
+
+    @staticmethod
+    def from_xyt(v):                                                   # vectorToAffine3d (registration.cpp:129-135)
+        c, s = math.cos(v[2]), math.sin(v[2])
+        return _Affine(c, -s, s, c, float(v[0]), float(v[1]))
+
+    def xyt(self):                                                     # Affine3dToVectorXYeZ: yaw from the rotation's second column pair
+        return np.array([self.tx, self.ty, math.atan2(self.r10, self.r11)])
+
+    def __matmul__(self, b):
+        return _Affine(self.r00 * b.r00 + self.r01 * b.r10, self.r00 * b.r01 + self.r01 * b.r11,
+                       self.r10 * b.r00 + self.r11 * b.r10, self.r10 * b.r01 + self.r11 * b.r11,
+                       (self.r00 * b.tx + self.r01 * b.ty) + self.tx, (self.r10 * b.tx + self.r11 * b.ty) + self.ty)
+
+    def inverse(self):                                                 # Eigen's general affine inverse: cofactors / determinant
+        inv = 1.0 / (self.r00 * self.r11 - self.r01 * self.r10)
+        a, b, c, d = self.r11 * inv, -self.r01 * inv, -self.r10 * inv, self.r00 * inv
+        return _Affine(a, b, c, d, -(a * self.tx + b * self.ty), -(c * self.tx + d * self.ty))
+
+
+class OdometryKeyframeFuser:
+    """processFrame (odometrykeyframefuser.cpp:143-259) over clouds.  params: api.OdomParams (its filter member is unused here)."""
+
+    def __init__(self, device, params):
+        self.dev, self.par = device, params
+        self.keyframes_ = []                                           # (pose _Affine, cells)
+        self.Tcurrent, self.T_prev, self.Tmot = _Affine(), _Affine(), _Affine()
+        self.updated, self.last_reg_ok, self.last_itrs, self.last_cells = False, True, 0, None
+
+    @staticmethod
+    def KeyFrameBasedFuse(diff: _Affine, use_keyframe, min_keyframe_dist, min_keyframe_rot_deg) -> bool:       # :62-73
+        if not use_keyframe:
+            return True
+        return math.sqrt(diff.tx * diff.tx + diff.ty * diff.ty) > min_keyframe_dist or \
+            abs(math.atan2(diff.r10, diff.r11)) > (min_keyframe_rot_deg * math.pi / 180.0)
+
+    @staticmethod
+    def AccelerationVelocitySanityCheck(prev: _Affine, cur: _Affine) -> bool:                                    # :76-94
+        dt, vel_limit, acc_limit = 0.25, 200.0, 200.0
+        vel = math.sqrt((cur.tx / dt) ** 2 + (cur.ty / dt) ** 2)
+        acc = math.sqrt(((cur.tx - prev.tx) / (dt * dt)) ** 2 + ((cur.ty - prev.ty) / (dt * dt)) ** 2)
+        return not (acc > acc_limit or vel > vel_limit)
+
+    def pointcloudCallback(self, x, y, intensity, peaks=None):
+        """-> (pose (x, y, yaw), compensated cloud (x, y), compensated peaks or None).  peaks: (x, y, intensity) of the peaks cloud."""
+        p = self.par
+        TprevMot = self.Tmot
+        x, y = np.asarray(x, np.float32), np.asarray(y, np.float32)
+        if p.compensate:
+            mot = TprevMot.xyt()
+            if len(x):
+                x, y = self.dev.compensate(x, y, mot, bool(p.radar_ccw))
+            if peaks is not None and len(peaks[0]):
+                px, py = self.dev.compensate(peaks[0], peaks[1], mot, bool(p.radar_ccw))
+                peaks = (px, py, peaks[2])
+        cells = self.dev.build_cells(x, y, intensity, float(p.res), float(p.downsample_factor), bool(p.weight_intensity))
+        self.last_cells = cells
+        Tguess = (self.T_prev @ TprevMot) if p.use_guess else self.T_prev
+        self.updated, self.last_reg_ok, self.last_itrs = False, True, 0
+        if not self.keyframes_:
+            self.keyframes_.append((_Affine(), cells))
+            self.updated = True
+            return self.Tcurrent.xyt(), (x, y), peaks
+        scans = [c for _, c in self.keyframes_] + [cells]
+        T = np.array([k.xyt() for k, _ in self.keyframes_] + [Tguess.xyt()])
+        Tio, ok, itrs, _score = self.dev.register(scans, T, p.reg)     # the reference ignores `ok` (shadowed variable, :184-193)
+        self.last_reg_ok, self.last_itrs = ok, itrs
+        self.Tcurrent = _Affine.from_xyt(Tio[-1])
+        Tmot_current = self.T_prev.inverse() @ self.Tcurrent
+        if not self.AccelerationVelocitySanityCheck(self.Tmot, Tmot_current):
+            self.Tcurrent = Tguess
+        self.Tmot = self.T_prev.inverse() @ self.Tcurrent
+        Tkeydiff = self.keyframes_[-1][0].inverse() @ self.Tcurrent
+        if self.KeyFrameBasedFuse(Tkeydiff, bool(p.use_keyframe), p.min_keyframe_dist, p.min_keyframe_rot_deg):
+            self.keyframes_.append((self.Tcurrent, cells))
+            if len(self.keyframes_) > p.submap_scan_size:
+                self.keyframes_.pop(0)
+            self.updated = True
+        self.T_prev = self.Tcurrent
+        return self.Tcurrent.xyt(), (x, y), peaks

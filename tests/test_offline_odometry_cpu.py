@@ -102,3 +102,77 @@ def test_run_assigns_sensor_clock_stamps():
     assert rd.stamps == [250_000_000 * (i + 1) for i in range(4)] and len(rd.graph) == 4 and not rd.gt
     paths_free = rd.graph.graph[3][0]
     assert paths_free.stamp_ == 1_000_000_000 and not paths_free.has_Tgt_
+
+
+# ---- the fuser with the reference's own (cloud) interface, over primitive device calls ----------------------------------------------------
+class OraclePrimitiveDevice:
+    def __init__(self):
+        from oracle import oracle_py as O
+        O.lib()
+        self.O = O
+
+    def compensate(self, x, y, mot, ccw):
+        return self.O.compensate(x, y, mot, ccw)
+
+    def build_cells(self, x, y, intensity, radius, downsample_factor, weight_intensity):
+        return self.O.build_cells(x, y, intensity, radius=radius, downsample_factor=downsample_factor, weight_intensity=weight_intensity)[0]
+
+    def register(self, scans, T, rp):
+        P = self.O.default_reg_params(cost=rp.cost, loss=rp.loss, weight_opt=rp.weight_opt, loss_limit=rp.loss_limit, cov_scale=rp.cov_scale,
+                                      regularization=rp.regularization, max_itr_association=rp.max_itr_association, max_itr_solver=rp.max_itr_solver)
+        Tio, s = self.O.register(scans, T, P)
+        return Tio, bool(s.success), int(s.itrs), float(s.score)
+
+
+def test_cloud_interface_fuser_equals_the_fused_frame():
+    """OdometryKeyframeFuser.pointcloudCallback(cloud) = compensate + build_cells + register + the reference's pose / keyframe bookkeeping on the
+    host must reproduce the fused frame (oracle.Odometry.step, the checker of tbv_odom_step) when it is fed the k-strongest cloud: poses to
+    1e-12 (one atan2 / sincos round trip apart), same keyframe decisions, same association-iteration counts, same window."""
+    from tbv_slam_public_b200 import api
+    dev = OraclePrimitiveDevice()
+    st = synth.make_stream(18, speed=4.0)
+    fuser = OO.OdometryKeyframeFuser(dev, api.default_odom_params())
+    ref = dev.O.Odometry()
+    n_kf = 0
+    for i in range(len(st.scans)):
+        _, _, I, x, y = dev.O.kstrongest(st.scans[i], 60.0, 40, 2.5, 0.0438, peaks=False)["filtered"]
+        pose, (cx, cy), _ = fuser.pointcloudCallback(x, y, I.astype(np.float32))
+        o = ref.step(st.scans[i])
+        assert np.abs(pose - np.array(o.pose[:])).max() < 1e-12, i
+        assert (fuser.updated, fuser.last_itrs, len(fuser.keyframes_), len(fuser.last_cells)) == (bool(o.is_keyframe), o.itrs, o.n_keyframes, o.n_cells), i
+        n_kf += fuser.updated
+    assert 6 <= n_kf < len(st.scans) and len(fuser.keyframes_) == 4
+    kp, _ = ref.keyframes()
+    for (k, cells), want in zip(fuser.keyframes_, kp):
+        assert np.abs(k.xyt() - want).max() < 1e-12
+
+
+def test_cloud_interface_fuser_runs_on_ca_cfar_clouds():
+    """The reason the cloud interface exists: odometry on CA-CFAR detections (radar_driver.cpp:52-56; the kstrong_vs_cfar presets, SURVEY
+    Appendix A) — different points, same fuser.  The estimate must follow the ground truth of the synthetic drive."""
+    from tbv_slam_public_b200 import api
+    dev = OraclePrimitiveDevice()
+    st = synth.make_stream(12)
+    par = api.default_odom_params(weight_intensity=0)
+    par.reg = api.default_reg_params(cost=api.P2P, weight_opt=api.W_UNIFORM, regularization=1.0)
+    fuser = OO.OdometryKeyframeFuser(dev, par)
+    est = []
+    for i in range(len(st.scans)):
+        _, _, I, x, y = dev.O.cacfar(st.scans[i], 40, 0.01, 10)
+        assert len(x) > 500
+        pose, _, _ = fuser.pointcloudCallback(x, y, I.astype(np.float32))
+        est.append(pose)
+    est = np.array(est)
+    rel_gt = np.array([synth.se2_mul(synth.se2_inv(st.gt[0]), p) for p in st.gt])
+    assert np.hypot(*(est[:, :2] - rel_gt[:, :2]).T).max() < 0.5 and np.abs(est[:, 2] - rel_gt[:, 2]).max() < 0.02
+    assert np.hypot(*est[-1, :2]) > 20.0                                                   # it did move: 11 steps of 2.5 m
+
+
+def test_affine_helper_matches_numpy():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        a, b = OO._Affine.from_xyt(rng.normal(size=3)), OO._Affine.from_xyt(rng.normal(size=3))
+        m = lambda t: np.array([[t.r00, t.r01, t.tx], [t.r10, t.r11, t.ty], [0, 0, 1.0]])
+        assert np.allclose(m(a @ b), m(a) @ m(b), atol=1e-15) and np.allclose(m(a.inverse()), np.linalg.inv(m(a)), atol=1e-14)
+        v = rng.normal(size=3); v[2] = math.remainder(v[2], 2 * math.pi)
+        assert np.allclose(OO._Affine.from_xyt(v).xyt(), v, atol=1e-15)
