@@ -527,6 +527,196 @@ pgo_pcg_cluster(int n, int fixed_node, const int* __restrict__ ids, const int* _
   if (rank == 0 && tid == 0) { *out_iters = it; *out_rel = rel; }
 }
 
+// ---- the same solve with the ODOMETRY CHAIN as preconditioner (opt-in: TBV_PGO_CHAIN=1; not yet run on a GPU — see DESIGN.md §7b) ----------------
+// M = block-tridiagonal part of (H + D): diagonal blocks + the blocks coupling nodes i and i + 1 (chain[i] = A[i+1][i], summed on the host from the
+// constraints between consecutive nodes), factorised once as M = L S L^T (block Thomas: S_0 = A_00, W_i = chain[i-1] S_{i-1}^-1,
+// S_i = A_ii - W_i chain[i-1]^T).  A pose graph is that chain plus a few weak loop blocks: CG needs ~5 iterations where block-Jacobi needs ~1100
+// (measured with the numpy prototype tests/tools/pgo_chain_prototype.py, which restates this kernel operation by operation and is its checker).
+// First version: factorisation and the two sweeps of every application run on ONE thread (dependent 6x6 recurrences; the blocks stream from L2);
+// the product and the block-diagonal solve use the whole CTA.  Next: 6 lanes per recurrence, then parallel cyclic reduction.
+__device__ void pcgc_inverse_spd6(const double* S, double* Sinv, bool* ok) {   // Cholesky S = L L^T, then S^-1 = L^-T L^-1
+  double L[6][6], Li[6][6];
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) { L[a][b] = 0.0; Li[a][b] = 0.0; }
+  *ok = true;
+  for (int j = 0; j < 6; j++) {
+    double d = S[6 * j + j];
+    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0)) { *ok = false; d = 1.0; }           // not positive definite: keep going with a unit pivot, the caller reports it
+    L[j][j] = sqrt(d);
+    for (int a = j + 1; a < 6; a++) {
+      double v = S[6 * a + j];
+      for (int k = 0; k < j; k++) v -= L[a][k] * L[j][k];
+      L[a][j] = v / L[j][j];
+    }
+  }
+  for (int c = 0; c < 6; c++)
+    for (int a = 0; a < 6; a++) {
+      double v = (a == c) ? 1.0 : 0.0;
+      for (int k = 0; k < a; k++) v -= L[a][k] * Li[k][c];
+      Li[a][c] = v / L[a][a];
+    }
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) {
+      double v = 0.0;
+      for (int k = 0; k < 6; k++) v += Li[k][a] * Li[k][b];
+      Sinv[6 * a + b] = v;
+    }
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+pgo_pcg_chain(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
+              const double* __restrict__ Ho, const double* __restrict__ chain, const double* __restrict__ g, double radius, int max_iters, double rel_tol,
+              double* __restrict__ x, double* r, double* z, double* __restrict__ p, double* __restrict__ q, double* Sinv, double* Wb, double* __restrict__ Dg,
+              double* y, int* __restrict__ out_iters, double* __restrict__ out_rel) {
+  __shared__ double s_w[PCG_THREADS / 32];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  for (int i = tid; i < n; i += PCG_THREADS)
+    for (int a = 0; a < 6; a++) Dg[6 * (size_t)i + a] = fmin(fmax(Hd[36 * (size_t)i + 7 * a], 1e-6), 1e32) / radius;
+  __syncthreads();
+  // ---- block Thomas factorisation of the chain (sequential in i) -----------------------------------------------------------------------------------
+  if (tid == 0) {
+    double Sp[36];                                        // S_{i-1}^-1
+    for (int i = 0; i < n; i++) {
+      double S[36];
+      for (int e = 0; e < 36; e++) S[e] = (i == fixed_node) ? ((e % 7 == 0) ? 1.0 : 0.0) : Hd[36 * (size_t)i + e];
+      if (i != fixed_node)
+        for (int a = 0; a < 6; a++) S[7 * a] += Dg[6 * (size_t)i + a];
+      if (i > 0) {
+        const double* C = chain + 36 * (size_t)(i - 1);   // A[i][i-1]; zero on both sides of the fixed node (host)
+        double W[36];
+        for (int a = 0; a < 6; a++)
+          for (int b = 0; b < 6; b++) {
+            double v = 0.0;
+            for (int k = 0; k < 6; k++) v += C[6 * a + k] * Sp[6 * k + b];
+            W[6 * a + b] = v;
+          }
+        for (int e = 0; e < 36; e++) Wb[36 * (size_t)(i - 1) + e] = W[e];
+        for (int a = 0; a < 6; a++)
+          for (int b = 0; b < 6; b++) {
+            double v = 0.0;
+            for (int k = 0; k < 6; k++) v += W[6 * a + k] * C[6 * b + k];
+            S[6 * a + b] -= v;
+          }
+      }
+      bool ok;
+      pcgc_inverse_spd6(S, Sp, &ok);
+      if (!ok) s_bad = 1;
+      for (int e = 0; e < 36; e++) Sinv[36 * (size_t)i + e] = Sp[e];
+    }
+  }
+  __syncthreads();
+  // z = M^-1 v: forward sweep (thread 0), block-diagonal solve (all threads), backward sweep (thread 0)
+  auto apply_chain = [&](const double* v, double* o) {
+    if (tid == 0) {
+      double prev[6], cur[6];
+      for (int a = 0; a < 6; a++) { prev[a] = v[a]; y[a] = prev[a]; }
+      for (int i = 1; i < n; i++) {
+        const double* W = Wb + 36 * (size_t)(i - 1);
+        for (int a = 0; a < 6; a++) {
+          double acc = v[6 * (size_t)i + a];
+          for (int b = 0; b < 6; b++) acc -= W[6 * a + b] * prev[b];
+          cur[a] = acc;
+        }
+        for (int a = 0; a < 6; a++) { prev[a] = cur[a]; y[6 * (size_t)i + a] = cur[a]; }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += PCG_THREADS)
+      for (int a = 0; a < 6; a++) {
+        double acc = 0.0;
+        for (int b = 0; b < 6; b++) acc += Sinv[36 * (size_t)i + 6 * a + b] * y[6 * (size_t)i + b];
+        o[6 * (size_t)i + a] = acc;
+      }
+    __syncthreads();
+    if (tid == 0) {
+      double nxt[6], cur[6];
+      for (int a = 0; a < 6; a++) nxt[a] = o[6 * (size_t)(n - 1) + a];
+      for (int i = n - 2; i >= 0; i--) {
+        const double* W = Wb + 36 * (size_t)i;            // W_{i+1}: o_i -= W_{i+1}^T o_{i+1}
+        for (int a = 0; a < 6; a++) {
+          double acc = o[6 * (size_t)i + a];
+          for (int b = 0; b < 6; b++) acc -= W[6 * b + a] * nxt[b];
+          cur[a] = acc;
+        }
+        for (int a = 0; a < 6; a++) { nxt[a] = cur[a]; o[6 * (size_t)i + a] = cur[a]; }
+      }
+      if (fixed_node >= 0 && fixed_node < n)
+        for (int a = 0; a < 6; a++) o[6 * (size_t)fixed_node + a] = 0.0;
+    }
+    __syncthreads();
+  };
+  auto apply_A = [&](const double* v, double* o) {        // as in pgo_pcg
+    for (int i = tid; i < n; i += PCG_THREADS) {
+      double acc[6] = {0, 0, 0, 0, 0, 0};
+      if (i != fixed_node) {
+        double t[6];
+        for (int a = 0; a < 6; a++) t[a] = v[6 * (size_t)i + a];
+        for (int a = 0; a < 6; a++) {
+          double s0 = Dg[6 * (size_t)i + a] * t[a];
+          for (int b = 0; b < 6; b++) s0 += Hd[36 * (size_t)i + a * 6 + b] * t[b];
+          acc[a] = s0;
+        }
+        for (int e = row[i]; e < row[i + 1]; e++) {
+          const int c = inc[e] >> 1, side = inc[e] & 1;
+          const int other = side ? ids[3 * c] : ids[3 * c + 1];
+          const double* B = Ho + 36 * (size_t)c;
+          double u[6];
+          for (int a = 0; a < 6; a++) u[a] = v[6 * (size_t)other + a];
+          if (side == 0) { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[a * 6 + b] * u[b]; }
+          else           { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[b * 6 + a] * u[b]; }
+        }
+      }
+      for (int a = 0; a < 6; a++) o[6 * (size_t)i + a] = acc[a];
+    }
+  };
+  auto dot = [&](const double* u, const double* v) {
+    double acc = 0.0;
+    for (int i = tid; i < n; i += PCG_THREADS)
+      for (int a = 0; a < 6; a++) acc += u[6 * (size_t)i + a] * v[6 * (size_t)i + a];
+    return pcg_block_sum(acc, s_w);
+  };
+  for (int i = tid; i < n; i += PCG_THREADS)
+    for (int a = 0; a < 6; a++) {
+      x[6 * (size_t)i + a] = 0.0;
+      r[6 * (size_t)i + a] = (i == fixed_node) ? 0.0 : -g[6 * (size_t)i + a];
+    }
+  __syncthreads();
+  apply_chain(r, z);
+  for (int i = tid; i < n; i += PCG_THREADS)
+    for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a];
+  __syncthreads();
+  double rz = dot(r, z);
+  const double bnorm = sqrt(dot(r, r));
+  double rel = bnorm > 0.0 ? 1.0 : 0.0;
+  int it = 0;
+  while (it < max_iters && rel > rel_tol) {
+    apply_A(p, q);
+    __syncthreads();
+    const double pq = dot(p, q);
+    if (!(pq > 0.0)) break;
+    const double alpha = rz / pq;
+    for (int i = tid; i < n; i += PCG_THREADS)
+      for (int a = 0; a < 6; a++) {
+        x[6 * (size_t)i + a] += alpha * p[6 * (size_t)i + a];
+        r[6 * (size_t)i + a] -= alpha * q[6 * (size_t)i + a];
+      }
+    __syncthreads();                                     // the sweeps read every row of r
+    apply_chain(r, z);
+    const double rz_new = dot(r, z);
+    rel = sqrt(dot(r, r)) / bnorm;
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    for (int i = tid; i < n; i += PCG_THREADS)
+      for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a] + beta * p[6 * (size_t)i + a];
+    __syncthreads();
+    it++;
+  }
+  if (tid == 0) { *out_iters = s_bad ? -it - 1 : it; *out_rel = rel; }   // negative: a chain pivot block was not positive definite
+}
+
 }  // namespace tbv
 
 using namespace tbv;
@@ -636,7 +826,36 @@ extern "C" int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const in
   if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dinc.p, inc.data(), 2 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
     static const bool use_cluster = getenv("TBV_PGO_CLUSTER") != nullptr;   // opt-in until the cluster kernel has been run and timed on a B200
-    if (use_cluster) {
+    static const bool use_chain = getenv("TBV_PGO_CHAIN") != nullptr;       // opt-in: odometry-chain preconditioner (same status)
+    if (use_chain) {
+      // chain[i] = A[i+1][i]: sum over the constraints between nodes i and i+1 of H_off (begin = i+1) or its transpose (begin = i)
+      std::vector<double> chain(36 * (size_t)std::max(n_nodes - 1, 1), 0.0);
+      for (int c = 0; c < n_con; c++) {
+        const int a = ids[3 * c], b = ids[3 * c + 1];
+        if (a - b != 1 && b - a != 1) continue;
+        const int lo = a < b ? a : b;
+        if (lo == fixed_node || lo + 1 == fixed_node) continue;            // no coupling across the fixed node
+        const double* B = H_off + 36 * (size_t)c;
+        double* C = chain.data() + 36 * (size_t)lo;
+        for (int u = 0; u < 6; u++)
+          for (int v = 0; v < 6; v++) C[6 * u + v] += (a > b) ? B[6 * u + v] : B[6 * v + u];
+      }
+      DevBuf<double> dch, dsi, dwb, dy;
+      int rc2;
+      if ((rc2 = dch.reserve(chain.size())) || (rc2 = dsi.reserve(36 * (size_t)n_nodes)) || (rc2 = dwb.reserve(chain.size())) || (rc2 = dy.reserve(N6))) {
+        dch.release(); dsi.release(); dwb.release(); dy.release(); cleanup();
+        return rc2;
+      }
+      e = cudaMemcpyAsync(dch.p, chain.data(), chain.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) {
+        pgo_pcg_chain<<<1, PCG_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dch.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p,
+                                                  dz.p, dp.p, dq.p, dsi.p, dwb.p, ddg.p, dy.p, dit.p, drel.p);
+        launched(ctx, "pgo_pcg_chain");
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);               // `chain` (host) and the extra buffers must outlive the kernel
+      }
+      dch.release(); dsi.release(); dwb.release(); dy.release();
+    } else if (use_cluster) {
       pgo_pcg_cluster<<<PCGC_CL, PCGC_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p,
                                                          dz.p, dp.p, dq.p, dmi.p, ddg.p, dit.p, drel.p);
       launched(ctx, "pgo_pcg_cluster");
@@ -645,7 +864,7 @@ extern "C" int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const in
                                           dq.p, dmi.p, ddg.p, dit.p, drel.p);
       launched(ctx, "pgo_pcg");
     }
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
   }
   int h_it = 0;
   double h_rel = 0;

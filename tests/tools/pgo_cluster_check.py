@@ -1,8 +1,9 @@
 """First GPU run of the thread-block-cluster PCG (k_pgo.cu: pgo_pcg_cluster, opt-in via TBV_PGO_CLUSTER=1) — correctness against scipy's sparse
 direct solve and timing against the one-CTA kernel.  Written when the round's GPU budget was spent; run it FIRST next round:
 
-    TBV_PGO_CLUSTER=1 python tests/tools/pgo_cluster_check.py      # cluster kernel
-    python tests/tools/pgo_cluster_check.py                        # one-CTA kernel, same checks, for the comparison
+    TBV_PGO_CLUSTER=1 python tests/tools/pgo_cluster_check.py      # cluster kernel (block-Jacobi PCG on 8 CTAs)
+    TBV_PGO_CHAIN=1 python tests/tools/pgo_cluster_check.py        # odometry-chain preconditioner (one CTA): expect ~5 CG iterations
+    python tests/tools/pgo_cluster_check.py                        # one-CTA block-Jacobi kernel, same checks, for the comparison
 
 Prints one JSON line; exits 1 on a parity failure.  If it passes and is faster, make the cluster kernel the default in tbv_pgo_solve_step,
 add its cases to tests/test_loop_gpu.py and update DESIGN.md §4 / §7b."""
@@ -21,9 +22,10 @@ from test_loop_gpu import _damped_system, _graph  # noqa: E402
 def main():
     import scipy.sparse.linalg as spl
     ctx = api.Context(0)
-    out = {"kernel": "pgo_pcg_cluster" if os.environ.get("TBV_PGO_CLUSTER") else "pgo_pcg", "cases": []}
+    out = {"kernel": "pgo_pcg_chain" if os.environ.get("TBV_PGO_CHAIN") else ("pgo_pcg_cluster" if os.environ.get("TBV_PGO_CLUSTER") else "pgo_pcg"),
+           "cases": []}
     ok = True
-    for n, radius, fixed in ((2, 1e4, 0), (7, 1e4, 3), (30, 1e4, 0), (600, 1e4, 0), (600, 1e2, 17), (4500, 1e4, 0), (4500, 1e2, 0)):
+    for n, radius, fixed in ((2, 1e4, 0), (7, 1e4, 3), (30, 1e4, 0), (600, 1e4, 0), (600, 1e2, 17), (600, 1e8, 17), (4500, 1e4, 0), (4500, 1e2, 0)):
         rng = np.random.default_rng(n)
         nodes, ids, meas = _graph(n, rng)
         _, Hd, Ho, g, _ = api.pgo_assemble(ctx, nodes, ids, meas, fixed_node=fixed)
