@@ -438,3 +438,21 @@ def test_batched_search_equals_the_per_keyframe_search(drive):
     seq = TS.TBVSLAM(_copy(g), OracleLoopDevice(), _classifier(), TS.LoopClosureParams(), api.default_pgo_params(loop_scaling=1.0))
     ref = seq.Run()
     assert res.n_loop_constraints == ref.n_loop_constraints >= 6 and np.array_equal(res.poses_after, ref.poses_after)
+
+
+def test_slam_regression_fixture():
+    """tests/golden/slam_regression.json freezes the driver's records on the seeded drive (oracle as device): candidates, decisions and applied
+    constraints exactly, numbers to 1e-8 (the fixture holds 9 decimals)."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_slam_regression", os.path.join(here, "make_slam_regression.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    got, want = m.compute(), json.load(open(os.path.join(here, "slam_regression.json")))
+    assert got["keyframes"] == want["keyframes"] and got["constraints"] == want["constraints"] and len(got["records"]) == len(want["records"])
+    for a, b in zip(got["records"], want["records"]):
+        assert a[:5] == b[:5]
+        assert abs(a[5] - b[5]) <= 1e-8 and np.allclose(a[6], b[6], rtol=0, atol=1e-8)
+        assert a[7].keys() == b[7].keys() and all(abs(a[7][k] - b[7][k]) <= 1e-8 * max(1.0, abs(b[7][k])) for k in a[7])
