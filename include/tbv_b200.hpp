@@ -263,7 +263,7 @@ class RSCManager {
   std::vector<float> ringkeys_, q_keys_;
 };
 
-// CorAlRadarQuality / CFEARQuality for a batch of candidate pairs (coral_alignment_quality/.../AlignmentQuality.cpp:99-229, 330-352):
+// CorAlRadarQuality / CFEARQuality for a batch of candidate pairs (coral_alignment_quality/src/alignment_checker/AlignmentQuality.cpp:99-229, 330-352):
 // clouds / cell sets are given once and indexed by the pairs; pair p compares src at T_src[p] (* T_offset[p]) with ref at T_ref[p].
 inline std::vector<tbv_coral_result> CorAlRadarQuality(Context& ctx, const std::vector<PointCloud>& clouds, const std::vector<int>& src, const std::vector<int>& ref,
                                                        const std::vector<Pose2>& T_src, const std::vector<Pose2>& T_ref, double radius = 1.0,
