@@ -211,3 +211,30 @@ def test_chain_preconditioned_solve_prototype(cpu_device):
     _, Hd, Ho, g, _ = cpu_device.pgo_assemble(nodes, ids[odo], meas[odo])
     _, iters, rel = P.solve(ids[odo], Hd, Ho, g, 0, 1e4, rel_tol=1e-10)
     assert iters <= 2 and rel <= 1e-10
+
+
+def test_parallel_cyclic_reduction_equals_the_sweeps(cpu_device):
+    """pgo_chain_prototype.pcr_*: the log2(n)-level, fully parallel form of the chain preconditioner gives the block-Thomas result (to the
+    conditioning of the chain: 1e-8 at Ceres' initial radius, 1e-5 at radius 1e8) — the checker of the next kernel revision's sweeps."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "tools"))
+    import pgo_chain_prototype as P
+    from test_loop_gpu import _graph as big_graph
+    for n, radius, fixed, tol in ((2, 1e4, 0, 1e-12), (3, 1e4, 1, 1e-12), (37, 1e4, 5, 1e-9), (600, 1e4, 0, 1e-8), (600, 1e8, 17, 1e-5), (1500, 1e4, 0, 1e-8)):
+        rng = np.random.default_rng(n)
+        nodes, ids, meas = big_graph(n, rng)
+        _, Hd, Ho, g, _ = cpu_device.pgo_assemble(nodes, ids, meas, fixed_node=fixed)
+        Ad, C = P.chain_blocks(ids, Hd, Ho, radius, fixed)
+        r = rng.normal(size=(n, 6))
+        want = P.apply(*P.factorise(Ad, C), r)
+        levels, Dinv = P.pcr_factorise(Ad, C)
+        assert len(levels) == int(np.ceil(np.log2(n)))
+        got = P.pcr_apply(levels, Dinv, r)
+        assert np.abs(got - want).max() <= tol * np.abs(want).max(), (n, radius)
+        # and it is M^-1: multiplying back by the block-tridiagonal matrix returns r
+        back = np.einsum("nij,nj->ni", Ad, got)
+        back[1:] += np.einsum("nij,nj->ni", C, got[:-1])
+        back[:-1] += np.einsum("nji,nj->ni", C, got[1:])
+        scale = max(np.abs(Ad).max(), np.abs(C).max() if len(C) else 0.0) * np.abs(got).max()      # |M| |z|: the size of the terms that cancel
+        assert np.abs(back - r).max() <= 1e-9 * scale + 1e3 * tol * np.abs(r).max()

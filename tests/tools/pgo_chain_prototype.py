@@ -94,3 +94,47 @@ def solve(ids, Hd, Ho, g, fixed=0, radius=1e4, max_iters=2000, rel_tol=1e-12):
         rz = rz_new
         it += 1
     return x, it, rel
+
+
+# ---- the same preconditioner by PARALLEL CYCLIC REDUCTION: the fully parallel form of the two sweeps (log2 n levels) ------------------------------
+# Row i of M z = r is  L_i z_{i-1} + D_i z_i + U_i z_{i+1} = r_i  with L_i = C_{i-1}, U_i = C_i^T.  One PCR level with stride s eliminates the
+# neighbours at distance s from every row at once:
+#     alpha_i = -L_i D_{i-s}^-1,  gamma_i = -U_i D_{i+s}^-1
+#     D_i <- D_i + alpha_i U_{i-s} + gamma_i L_{i+s};   L_i <- alpha_i L_{i-s};   U_i <- gamma_i U_{i+s};   r_i <- r_i + alpha_i r_{i-s} + gamma_i r_{i+s}
+# After ceil(log2 n) levels every row is decoupled: z_i = D_i^-1 r_i.  The matrix part does not depend on r: `pcr_factorise` keeps alpha, gamma of
+# every level and the final D^-1 (once per solve), `pcr_apply` replays the right-hand-side part (once per CG iteration; every level is one fully
+# parallel pass over the nodes).
+def pcr_factorise(Ad, C):
+    n = len(Ad)
+    D = np.array(Ad, np.float64)
+    L = np.zeros((n, 6, 6)); U = np.zeros((n, 6, 6))
+    if n > 1:
+        L[1:] = C
+        U[:-1] = np.transpose(C, (0, 2, 1))
+    levels = []
+    s = 1
+    while s < n:
+        Dinv = np.linalg.inv(D)
+        alpha, gamma = np.zeros((n, 6, 6)), np.zeros((n, 6, 6))
+        alpha[s:] = -np.einsum("nij,njk->nik", L[s:], Dinv[:-s])
+        gamma[:-s] = -np.einsum("nij,njk->nik", U[:-s], Dinv[s:])
+        Dn = D.copy()
+        Dn[s:] += np.einsum("nij,njk->nik", alpha[s:], U[:-s])
+        Dn[:-s] += np.einsum("nij,njk->nik", gamma[:-s], L[s:])
+        Ln, Un = np.zeros_like(L), np.zeros_like(U)
+        Ln[s:] = np.einsum("nij,njk->nik", alpha[s:], L[:-s])
+        Un[:-s] = np.einsum("nij,njk->nik", gamma[:-s], U[s:])
+        levels.append((s, alpha, gamma))
+        D, L, U = Dn, Ln, Un
+        s *= 2
+    return levels, np.linalg.inv(D)
+
+
+def pcr_apply(levels, Dinv, r):
+    r = np.array(r, np.float64).reshape(len(Dinv), 6).copy()
+    for s, alpha, gamma in levels:
+        rn = r.copy()
+        rn[s:] += np.einsum("nij,nj->ni", alpha[s:], r[:-s])
+        rn[:-s] += np.einsum("nij,nj->ni", gamma[:-s], r[s:])
+        r = rn
+    return np.einsum("nij,nj->ni", Dinv, r)
