@@ -439,6 +439,139 @@ class CeresLeastSquaresT {
 };
 typedef CeresLeastSquaresT<DevicePoseGraph> CeresLeastSquares;
 
+// ---- OdometryKeyframeFuser with the reference's OWN interface: point clouds in (odometrykeyframefuser.cpp:143-259, 395-411) -------------------------------
+// The batched OdometryKeyframeFuser above fuses the k-strongest filter into the frame (tbv_odom_step) and is the fast path.  This one takes the CLOUD,
+// whatever filter produced it (CA-CFAR: radar_driver.cpp:52-56, or a caller's own): processFrame as host bookkeeping — poses as planar affine
+// matrices multiplied in Eigen's operation order, keyframe rule, sliding window — over three device calls per frame: tbv_compensate, tbv_build_cells,
+// tbv_register.  The backend is a template parameter so the bookkeeping can be checked without a GPU (tests/cpp/test_points_fuser.cpp plugs the
+// oracle in); the product type is PointCloudOdometryFuser = ...<DeviceOdometryPrimitives>.
+struct Affine2d {                                  // planar Eigen::Affine3d: 2x2 linear part + translation
+  double r00 = 1, r01 = 0, r10 = 0, r11 = 1, tx = 0, ty = 0;
+  static Affine2d FromPose(const Pose2& p) {       // vectorToAffine3d (registration.cpp:129-135)
+    const double c = std::cos(p.yaw), s = std::sin(p.yaw);
+    Affine2d T; T.r00 = c; T.r01 = -s; T.r10 = s; T.r11 = c; T.tx = p.x; T.ty = p.y;
+    return T;
+  }
+  Pose2 ToPose() const { return Pose2{tx, ty, std::atan2(r10, r11)}; }   // Affine3dToVectorXYeZ
+  Affine2d operator*(const Affine2d& b) const {
+    Affine2d c;
+    c.r00 = r00 * b.r00 + r01 * b.r10; c.r01 = r00 * b.r01 + r01 * b.r11;
+    c.r10 = r10 * b.r00 + r11 * b.r10; c.r11 = r10 * b.r01 + r11 * b.r11;
+    c.tx = (r00 * b.tx + r01 * b.ty) + tx; c.ty = (r10 * b.tx + r11 * b.ty) + ty;
+    return c;
+  }
+  Affine2d inverse() const {                       // Eigen's general affine inverse: cofactors / determinant, t' = -L^-1 t
+    const double inv = 1.0 / (r00 * r11 - r01 * r10);
+    Affine2d i;
+    i.r00 = r11 * inv; i.r01 = -r01 * inv; i.r10 = -r10 * inv; i.r11 = r00 * inv;
+    i.tx = -(i.r00 * tx + i.r01 * ty); i.ty = -(i.r10 * tx + i.r11 * ty);
+    return i;
+  }
+};
+
+struct DeviceOdometryPrimitives {
+  Context* ctx;
+  explicit DeviceOdometryPrimitives(Context& c) : ctx(&c) {}
+  void compensate(std::vector<float>& x, std::vector<float>& y, const double mot[3], bool ccw) const {
+    if (!x.empty()) check(tbv_compensate(ctx->get(), x.data(), y.data(), (int)x.size(), mot, ccw ? 1 : 0));
+  }
+  std::vector<tbv_cell> build_cells(const std::vector<float>& x, const std::vector<float>& y, const std::vector<float>& intensity, float radius,
+                                    double downsample_factor, bool weight_intensity) const {
+    std::vector<tbv_cell> cells(std::max<size_t>(x.size(), 1));
+    const double origin[2] = {0.0, 0.0};
+    int n = 0;
+    if (!x.empty())
+      check(tbv_build_cells(ctx->get(), x.data(), y.data(), intensity.data(), (int)x.size(), radius, downsample_factor, weight_intensity ? 1 : 0, origin,
+                            cells.data(), (int)cells.size(), &n, nullptr));
+    cells.resize(n);
+    return cells;
+  }
+  void register_scans(const std::vector<const tbv_cell*>& scans, const std::vector<int>& n_cells, std::vector<double>& T, const tbv_reg_params& par,
+                      tbv_reg_summary& summary) const {
+    check(tbv_register(ctx->get(), (int)scans.size(), scans.data(), n_cells.data(), T.data(), &par, &summary));
+  }
+};
+
+template <class Backend>
+class PointCloudOdometryFuserT {
+ public:
+  PointCloudOdometryFuserT(Backend backend, const tbv_odom_params& par) : be_(backend), par_(par) {}   // par.filter is not used here
+  struct Keyframe { Affine2d pose; std::shared_ptr<std::vector<tbv_cell>> cells; };
+
+  static bool KeyFrameBasedFuse(const Affine2d& diff, bool use_keyframe, double min_keyframe_dist, double min_keyframe_rot_deg) {   // :62-73
+    if (!use_keyframe) return true;
+    const double yaw = std::atan2(diff.r10, diff.r11), tnorm = std::sqrt(diff.tx * diff.tx + diff.ty * diff.ty);
+    return tnorm > min_keyframe_dist || std::fabs(yaw) > (min_keyframe_rot_deg * M_PI / 180.0);
+  }
+  static bool AccelerationVelocitySanityCheck(const Affine2d& prev, const Affine2d& cur) {                                             // :76-94
+    const double dt = 0.25, vel_limit = 200, acc_limit = 200;
+    const double vx = cur.tx / dt, vy = cur.ty / dt, ax = (cur.tx - prev.tx) / (dt * dt), ay = (cur.ty - prev.ty) / (dt * dt);
+    return !(std::sqrt(ax * ax + ay * ay) > acc_limit || std::sqrt(vx * vx + vy * vy) > vel_limit);
+  }
+
+  // cloud (and the optional peaks cloud) are compensated in place, as the reference does; returns Tcurrent
+  Pose2 pointcloudCallback(PointCloud& cloud, PointCloud* cloud_peaks = nullptr) {
+    const Affine2d TprevMot = Tmot_;
+    if (par_.compensate) {
+      const Pose2 m = TprevMot.ToPose();
+      const double mot[3] = {m.x, m.y, m.yaw};
+      compensate_cloud(cloud, mot);
+      if (cloud_peaks) compensate_cloud(*cloud_peaks, mot);
+    }
+    std::vector<float> x(cloud.size()), y(cloud.size()), I(cloud.size());
+    for (size_t k = 0; k < cloud.size(); k++) { x[k] = cloud[k].x; y[k] = cloud[k].y; I[k] = cloud[k].intensity; }
+    auto cells = std::make_shared<std::vector<tbv_cell>>(be_.build_cells(x, y, I, (float)par_.res, par_.downsample_factor, par_.weight_intensity != 0));
+    last_cells_ = cells;
+    const Affine2d Tguess = par_.use_guess ? T_prev_ * TprevMot : T_prev_;
+    updated = false; last_reg_ok = true; last_itrs = 0;
+    if (keyframes_.empty()) {
+      keyframes_.push_back(Keyframe{Affine2d(), cells});
+      updated = true;
+      return Tcurrent_.ToPose();
+    }
+    std::vector<const tbv_cell*> scans; std::vector<int> n; std::vector<double> T;
+    for (const Keyframe& k : keyframes_) {
+      const Pose2 p = k.pose.ToPose();
+      scans.push_back(k.cells->data()); n.push_back((int)k.cells->size()); T.insert(T.end(), {p.x, p.y, p.yaw});
+    }
+    const Pose2 g = Tguess.ToPose();
+    scans.push_back(cells->data()); n.push_back((int)cells->size()); T.insert(T.end(), {g.x, g.y, g.yaw});
+    tbv_reg_summary s{};
+    be_.register_scans(scans, n, T, par_.reg, s);                     // the reference ignores the result (shadowed `success`, :184-193)
+    last_reg_ok = s.success != 0; last_itrs = s.itrs;
+    Tcurrent_ = Affine2d::FromPose(Pose2{T[T.size() - 3], T[T.size() - 2], T[T.size() - 1]});
+    const Affine2d Tmot_current = T_prev_.inverse() * Tcurrent_;
+    if (!AccelerationVelocitySanityCheck(Tmot_, Tmot_current)) Tcurrent_ = Tguess;
+    Tmot_ = T_prev_.inverse() * Tcurrent_;
+    const Affine2d Tkeydiff = keyframes_.back().pose.inverse() * Tcurrent_;
+    if (KeyFrameBasedFuse(Tkeydiff, par_.use_keyframe != 0, par_.min_keyframe_dist, par_.min_keyframe_rot_deg)) {
+      keyframes_.push_back(Keyframe{Tcurrent_, cells});
+      if (keyframes_.size() > (size_t)par_.submap_scan_size) keyframes_.erase(keyframes_.begin());
+      updated = true;
+    }
+    T_prev_ = Tcurrent_;
+    return Tcurrent_.ToPose();
+  }
+  const std::vector<Keyframe>& keyframes() const { return keyframes_; }
+  size_t last_n_cells() const { return last_cells_ ? last_cells_->size() : 0; }
+  bool updated = false, last_reg_ok = true;
+  int last_itrs = 0;
+
+ private:
+  void compensate_cloud(PointCloud& c, const double mot[3]) {
+    std::vector<float> x(c.size()), y(c.size());
+    for (size_t k = 0; k < c.size(); k++) { x[k] = c[k].x; y[k] = c[k].y; }
+    be_.compensate(x, y, mot, par_.radar_ccw != 0);
+    for (size_t k = 0; k < c.size(); k++) { c[k].x = x[k]; c[k].y = y[k]; }
+  }
+  Backend be_;
+  tbv_odom_params par_;
+  std::vector<Keyframe> keyframes_;
+  std::shared_ptr<std::vector<tbv_cell>> last_cells_;
+  Affine2d Tcurrent_, T_prev_, Tmot_;
+};
+typedef PointCloudOdometryFuserT<DeviceOdometryPrimitives> PointCloudOdometryFuser;
+
 // ---- simple graph hand-off (cfear_radarodometry/include/cfear_radarodometry/types.h:93-192, types.cpp:103-130) in the Boost-free .tbvg layout ---------
 // Same content as the reference's simple_graph (vector<pair<RadarScan, vector<Constraint3d>>>), member for member; the byte layout is specified in
 // tbv_slam_public_b200/graph_io.py (little endian, no padding) and is what SaveSimpleGraph / LoadSimpleGraph below write and read.

@@ -27,6 +27,7 @@ def test_cpp_header_compiles_as_cxx14(tmp_path):
     tu = tmp_path / "tu.cpp"
     tu.write_text('#include "tbv_b200.hpp"\n'
                   'template class tbv_b200::CeresLeastSquaresT<tbv_b200::DevicePoseGraph>;   // every member of the device-backed optimiser\n'
+                  'template class tbv_b200::PointCloudOdometryFuserT<tbv_b200::DeviceOdometryPrimitives>;   // and of the cloud-interface fuser\n'
                   'int main() { return sizeof(tbv_b200::n_scan_normal_reg) > 0 ? 0 : 1; }\n')
     subprocess.check_call(["g++", "-std=c++14", "-Wall", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(tu)])
 
