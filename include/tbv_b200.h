@@ -371,6 +371,39 @@ int tbv_loopdb_register_dev(tbv_loopdb* db, int n_cand, const int* from, const i
                             const int* candidate_index, const double* quality, const tbv_reg_params* params, double max_score,
                             tbv_constraint* out_dev, int out_capacity, int* n_out_dev);
 
+/* ---- multi-GPU: candidates sharded over ranks, accepted constraints all-gathered (SURVEY 8b "multi-GPU", 8e) --------------------------
+ * Replaces, for a candidate list split over GPUs, the serial order in which ScanContextClosure::SearchAndAddConstraint
+ * (tbv_slam/src/tbv_slam/loopclosure.cpp:658-724) hands accepted candidates to ApplyConstratins (:261-318) /
+ * PoseGraph::AddConstraintThSafe: every rank ends up with ALL accepted constraints in global candidate order.
+ * One process (or host thread) per GPU; each context carries one NCCL communicator.  Either the host owns the communicator
+ * (tbv_comm_init: a C++/ROS host that already uses NCCL passes its ncclComm_t) or the library creates one from an
+ * ncclUniqueId that the host distributes with whatever it has (MPI, a ROS parameter, torch.distributed's store):
+ * rank 0 calls tbv_comm_unique_id, every rank calls tbv_comm_init_rank.  NCCL is loaded at run time (libnccl.so.2);
+ * contexts without a communicator behave as world = 1 and never touch it. */
+#define TBV_COMM_ID_BYTES 128                                    /* sizeof(ncclUniqueId) */
+int tbv_comm_unique_id(void* unique_id /* TBV_COMM_ID_BYTES, out */);
+int tbv_comm_init_rank(tbv_ctx* ctx, const void* unique_id, int world, int rank);   /* collective; the context owns the communicator */
+int tbv_comm_init(tbv_ctx* ctx, void* nccl_comm /* ncclComm_t on the context's device; stays owned by the caller */);
+int tbv_comm_world(tbv_ctx* ctx, int* world, int* rank);
+int tbv_comm_destroy(tbv_ctx* ctx);
+/* All-gather of accepted constraints.  local_dev: [capacity] records on the device, the first *n_local_dev valid, ascending by
+ * `candidate` (what tbv_loopdb_register_dev writes); capacity: the same on every rank (>= the largest share).  ONE ncclAllGather
+ * of (capacity + 1) 128-byte records per rank on the context's stream — the count travels in the block — then a device merge into
+ * global candidate order.  all [all_capacity] (host) receives the *n_all merged records, identical on every rank. */
+int tbv_allgather_constraints(tbv_ctx* ctx, const tbv_constraint* local_dev, const int* n_local_dev, int capacity, tbv_constraint* all,
+                              int all_capacity, int* n_all);
+/* Same, results left on the device (valid until the next exchange on this context); no host synchronisation. */
+int tbv_allgather_constraints_dev(tbv_ctx* ctx, const tbv_constraint* local_dev, const int* n_local_dev, int capacity,
+                                  const tbv_constraint** all_dev, const int** n_all_dev);
+/* The sharded form of tbv_loopdb_register in one call: every rank passes the SAME global candidate list; rank r registers the
+ * candidates with from mod world == r in one launch, packs its accepted constraints (candidate = global index), and the
+ * exchange above returns all of them, in global candidate order, to every rank.  At world = 1 (no communicator) it equals
+ * tbv_loopdb_register.  timing_ms (optional, [4]): device time of {H2D of the share + registration + packing, all-gather + merge,
+ * D2H of the merged records, whole call} of this call in ms, from events on the context's stream. */
+int tbv_loopdb_register_sharded(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
+                                const double* quality, const tbv_reg_params* params, double max_score, tbv_constraint* all,
+                                int all_capacity, int* n_all, float* timing_ms);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
 void* tbv_host_alloc(size_t bytes);
 void tbv_host_free(void* p);

@@ -152,7 +152,18 @@ _OPTIONAL = [
                              C.POINTER(RegParams), C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
     ("tbv_loopdb_register_dev", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.POINTER(RegParams), C.c_double, C.c_void_p, C.c_int, C.c_void_p], None),
+    ("tbv_loopdb_register_sharded", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RegParams),
+                                     C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
+    ("tbv_comm_unique_id", [C.c_void_p], None),
+    ("tbv_comm_init_rank", [C.c_void_p, C.c_void_p, C.c_int, C.c_int], None),
+    ("tbv_comm_init", [C.c_void_p, C.c_void_p], None),
+    ("tbv_comm_world", [C.c_void_p, C.c_void_p, C.c_void_p], None),
+    ("tbv_comm_destroy", [C.c_void_p], None),
+    ("tbv_allgather_constraints", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p], None),
+    ("tbv_allgather_constraints_dev", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
 ]
+
+COMM_ID_BYTES = 128
 
 
 def _check(rc):
@@ -223,6 +234,36 @@ class Context:
         n = C.c_int(0)
         _check(lib().tbv_profile_end(self.h, capacity, names, ms, C.byref(n)))
         return [(names[i].decode(), float(ms[i])) for i in range(min(n.value, capacity))]
+
+    # ---- multi-GPU: one NCCL communicator per context (tbv_comm_*) ----------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId through the library (rank 0 calls it and hands the 128 bytes to every rank)."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().tbv_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_rank(self, unique_id: bytes, world: int, rank: int):
+        """Collective: every rank of the group calls it with the same id."""
+        assert len(unique_id) == COMM_ID_BYTES
+        _check(lib().tbv_comm_init_rank(self.h, unique_id, int(world), int(rank)))
+
+    def comm_world(self):
+        w, r = C.c_int(1), C.c_int(0)
+        _check(lib().tbv_comm_world(self.h, C.byref(w), C.byref(r)))
+        return w.value, r.value
+
+    def comm_destroy(self):
+        _check(lib().tbv_comm_destroy(self.h))
+
+    def allgather_constraints(self, local_dev_ptr: int, n_local_dev_ptr: int, capacity: int) -> np.ndarray:
+        """tbv_allgather_constraints: records of every rank, global candidate order (CONSTRAINT_DTYPE array, identical on every rank)."""
+        world, _ = self.comm_world()
+        out = np.zeros(max(world * capacity, 1), CONSTRAINT_DTYPE)
+        n = C.c_int(0)
+        _check(lib().tbv_allgather_constraints(self.h, C.c_void_p(local_dev_ptr), C.c_void_p(n_local_dev_ptr), int(capacity), _ptr(out), len(out),
+                                               C.byref(n)))
+        return out[:n.value].copy()
 
     # ---- radarDriver::Process (k-strongest branch) -----------------------------------------------------------
     def StructuredKStrongest(self, polar: np.ndarray, z_min=60.0, k_strongest=40, min_distance=2.5, range_res=0.0438,
@@ -435,6 +476,21 @@ class LoopDB:
                                          float(max_score), _ptr(out), n, C.byref(n_out), C.cast(summ, C.c_void_p) if summ else None))
         out = out[:n_out.value].copy()
         return (out, summ) if want_summaries else out
+
+    def register_sharded(self, id_from, id_to, T_from, T_to, quality=None, params: RegParams | None = None, max_score=0.0, want_timing=False):
+        """tbv_loopdb_register_sharded: every rank passes the SAME global candidate list; each registers the candidates with
+        id_from mod world == rank and all ranks receive every accepted constraint in global candidate order (one NCCL all-gather
+        inside the library).  Without a communicator on the context (world 1) it equals register_candidates."""
+        params = params or loop_reg_params()
+        fs, ts, Tf, Tt, _, q = self._cand_args(id_from, id_to, T_from, T_to, None, quality)
+        n = len(fs)
+        out = np.zeros(max(n, 1), CONSTRAINT_DTYPE)
+        n_out = C.c_int(0)
+        tm = (C.c_float * 4)() if want_timing else None
+        _check(lib().tbv_loopdb_register_sharded(self.h, n, _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), _ptr(q), C.byref(params), float(max_score),
+                                                 _ptr(out), n, C.byref(n_out), tm))
+        out = out[:n_out.value].copy()
+        return (out, [float(v) for v in tm]) if want_timing else out
 
     def register_candidates_dev(self, id_from, id_to, T_from, T_to, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int,
                                 candidate_index=None, quality=None, params: RegParams | None = None, max_score=0.0):

@@ -40,7 +40,6 @@ struct CellsScratch {
   DevBuf<uint8_t> cand_valid;   // [batch][max_samples]
   DevBuf<long long> dbg;
   DevBuf<uint16_t> vidx16, order16;  // fused path, scans larger than CFU_PCAP points only
-  bool fused_attr_set = false;
   void release() {
     vidx16.release(); order16.release();
     grid.release(); vox_idx.release(); vox_start.release(); vox_fill.release(); sample_vox.release(); sorted_raw.release();
@@ -978,8 +977,7 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
   const int vox_cap = (int)vox_cap_ll;
   const int max_samples = par.max_samples > 0 ? par.max_samples : cell_cap;
   cudaStream_t st = ctx->stream;
-  static const bool force_legacy = getenv("TBV_CELLS_LEGACY") != nullptr;
-  if (!force_legacy && vox_cap <= CFU_VMAX && max_samples <= CFU_SMAX && cap_pts <= 65535) {
+  if (vox_cap <= CFU_VMAX && max_samples <= CFU_SMAX && cap_pts <= 65535) {
     // ---- fused path: one launch, one CTA per scan --------------------------------------------------------------------------
     int rc;
     if ((rc = S.err.reserve(batch)) || (rc = out.reserve(batch, cell_cap)))
@@ -992,27 +990,19 @@ int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t*
           (rc = S.vidx16.reserve((size_t)batch * cap_pts)) || (rc = S.order16.reserve((size_t)batch * cap_pts)))
         return rc;
     }
-    static const bool want_dbg = getenv("TBV_CELLS_DBG") != nullptr;
+#ifdef TBV_DEV_TIMERS
+    const bool want_dbg = true;
+#else
+    const bool want_dbg = false;   // per-phase clocks: development builds only
+#endif
     if (want_dbg) {
       if ((rc = S.dbg.reserve((size_t)batch * 8))) return rc;
     }
-    static const int l5 = getenv("TBV_CELLS_L5") ? atoi(getenv("TBV_CELLS_L5")) : 2;
-    auto launch = [&](auto kern) -> int {
-      if (!S.fused_attr_set) {
-        TBV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFU_SMEM));
-        S.fused_attr_set = true;
-      }
-      kern<<<batch, CFU_THREADS, CFU_SMEM, st>>>(x, y, inten_u8, inten_f32, count_dev, cap_pts, leaf, par.radius, par.weight_intensity, vox_cap, max_samples,
-                                                 S.sx.p, S.sy.p, S.si.p, S.vidx16.p, S.order16.p, S.cand.p, cand_stride, par.origin[0], par.origin[1], out.f64.p, cell_cap,
-                                                 out.count.p, out.n_samples.p, S.err.p, S.dbg.p);
-      return TBV_OK;
-    };
-    if (l5 == 1) rc = launch(cells_fused<1>);
-    else if (l5 == 2) rc = launch(cells_fused<2>);
-    else if (l5 == 8) rc = launch(cells_fused<8>);
-    else if (l5 == 16) rc = launch(cells_fused<16>);
-    else if (l5 == 4) rc = launch(cells_fused<4>);
-    else rc = launch(cells_fused<2>);
+    // 2 lanes per sample in the neighbourhood phase (1 / 2 / 4 / 8 / 16 were measured on a B200; 2 is the fastest)
+    if ((rc = ensure_dyn_smem(ctx, cells_fused<2>, CFU_SMEM))) return rc;
+    cells_fused<2><<<batch, CFU_THREADS, CFU_SMEM, st>>>(x, y, inten_u8, inten_f32, count_dev, cap_pts, leaf, par.radius, par.weight_intensity, vox_cap, max_samples,
+                                                         S.sx.p, S.sy.p, S.si.p, S.vidx16.p, S.order16.p, S.cand.p, cand_stride, par.origin[0], par.origin[1], out.f64.p, cell_cap,
+                                                         out.count.p, out.n_samples.p, S.err.p, S.dbg.p);
     if (rc) return rc;
     launched(ctx, "cells_fused");
     TBV_CUDA(cudaGetLastError());
@@ -1106,6 +1096,7 @@ using namespace tbv;
 extern "C" int tbv_build_cells(tbv_ctx* ctx, const float* x, const float* y, const float* intensity, int n, float radius,
                                double downsample_factor, int weight_intensity, const double origin[2], tbv_cell* cells, int cell_capacity,
                                int* n_cells, int* n_samples) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && x && y && intensity && origin && cells && n_cells, "null pointer");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n >= 0 && cell_capacity > 0, "bad sizes");

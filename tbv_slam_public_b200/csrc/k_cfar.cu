@@ -131,6 +131,7 @@ using namespace tbv;
 
 extern "C" int tbv_filter_cacfar(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_range, size_t row_stride, int batch,
                                  const tbv_cfar_params* p, tbv_points* out) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && polar && p && out, "null pointer");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
@@ -152,13 +153,9 @@ extern "C" int tbv_filter_cacfar(tbv_ctx* ctx, const uint8_t* polar, int n_az, i
   const double N = (double)(p->window_size * 2);                                  // cfar.cpp:32
   const double scaling = N * (std::pow(p->false_alarm_rate, -1. / N) - 1.);       // cfar.cpp:12-16 (host libm)
   const size_t smem = (size_t)CF_WARPS * (n_range + 1) * sizeof(uint32_t);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(cfar_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  if ((rc = ensure_dyn_smem(ctx, cfar_rows, smem))) { cleanup(); return rc; }
   const int grid = (total_rows + CF_WARPS - 1) / CF_WARPS;
-  cfar_rows<<<grid < 148 * 8 ? grid : 148 * 8, CF_WARPS * 32, smem, ctx->stream>>>(F.polar.p, total_rows, n_az, n_range, row_stride, p->window_size,
+  cfar_rows<<<grid < ctx->sm_count * 8 ? grid : ctx->sm_count * 8, CF_WARPS * 32, smem, ctx->stream>>>(F.polar.p, total_rows, n_az, n_range, row_stride, p->window_size,
                                                                                   p->nb_guard_cells, p->range_resolution, p->static_threshold,
                                                                                   p->min_distance, p->max_distance, scaling, words, bitmap.p, row_cnt.p);
   launched(ctx, "cfar_rows");

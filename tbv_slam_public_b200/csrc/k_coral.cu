@@ -249,6 +249,7 @@ extern "C" int tbv_coral_quality_batch(tbv_ctx* ctx, int n_clouds, const float* 
                                        const int* n_points, int n_pairs, const int* src_cloud, const int* ref_cloud, const double* T_src,
                                        const double* T_offset, const double* T_ref, const tbv_coral_params* params, tbv_coral_result* results,
                                        double* per_point) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && x && y && intensity && n_points && src_cloud && ref_cloud && T_src && T_ref && params && results && n_clouds >= 1 && n_pairs >= 0,
               "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
@@ -302,8 +303,7 @@ extern "C" int tbv_coral_quality_batch(tbv_ctx* ctx, int n_clouds, const float* 
   if (e == cudaSuccess) e = cudaMemcpyAsync(dy.p, hy.data(), hy.size() * sizeof(float), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(di.p, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dp.p, hp.data(), hp.size() * sizeof(CoralPair), cudaMemcpyHostToDevice, st);
-  static bool attr = false;
-  if (e == cudaSuccess && !attr) { e = cudaFuncSetAttribute(k_coral, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_SMEM); attr = true; }
+  if (e == cudaSuccess && ensure_dyn_smem(ctx, k_coral, CQ_SMEM) != TBV_OK) { cleanup(); return TBV_ERR_CUDA; }
   if (e == cudaSuccess) {
     k_coral<<<n_pairs, CQ_THREADS, CQ_SMEM, st>>>(dx.p, dy.p, di.p, dp.p, (float)params->radius, params->weight_res_intensity,
                                                   params->overlap_req > 0 ? params->overlap_req : 1, dr.p, per_point ? dpp.p : nullptr);

@@ -589,8 +589,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   F.batch = batch; F.n_az = n_az; F.n_range = n_range; F.k = k;
 
   const int total_rows = batch * n_az;
-  int dev_sms = 148;
-  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int dev_sms = ctx->sm_count;
   const int blocks_needed = (total_rows + K1_WARPS - 1) / K1_WARPS;
   const int rowbuf = ((n_range + 16 + 15 + 511) / 512) * 512;  // row + alignment slack, whole groups of 32 16-byte vectors
   const size_t k1_smem = (size_t)K1_WARPS * 2 * rowbuf;
@@ -599,12 +598,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
   const int max_grid = dev_sms * ctas_per_sm;
   const int grid = blocks_needed < max_grid ? blocks_needed : max_grid;  // persistent: resident CTAs only, rows strided over warps
-  static bool attr_set = false;
-  if (!attr_set) {
-    TBV_CUDA(cudaFuncSetAttribute(k1_kstrongest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-    TBV_CUDA(cudaFuncSetAttribute(k1_kstrongest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-    attr_set = true;
-  }
+  if ((rc = ensure_dyn_smem(ctx, k1_kstrongest<false>, k1_smem)) || (rc = ensure_dyn_smem(ctx, k1_kstrongest<true>, k1_smem))) return rc;
   const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
   const int min_range_bin = (int)std::ceil((double)p->min_distance / rr);   // radar_filters.cpp:315
@@ -617,11 +611,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   launched(ctx, "k1_kstrongest");
   TBV_CUDA(cudaGetLastError());
   const size_t smem = 2 * (size_t)(n_az + 1) * sizeof(int) + (size_t)K2_STAGE * (sizeof(uint32_t) + sizeof(int) + sizeof(uint16_t));
-  static size_t k2_smem_set = 48 * 1024;
-  if (smem > k2_smem_set) {
-    TBV_CUDA(cudaFuncSetAttribute(k2_make_clouds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k2_smem_set = smem;
-  }
+  if ((rc = ensure_dyn_smem(ctx, k2_make_clouds, smem))) return rc;
   k2_make_clouds<<<dim3(K2_SPLIT, batch), 256, smem, ctx->stream>>>(F.row_keys.p, F.row_cnt.p, n_az, k, min_range_bin, rr, F.cs_table.p, n_az * k,
                                                                     F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, F.filtered.az.p,
                                                                     F.filtered.rg.p, F.filtered.count.p, want_peaks, F.peaks.x.p, F.peaks.y.p,
@@ -670,10 +660,12 @@ extern "C" {
 
 int tbv_filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
                               const tbv_filter_params* params, int want_peaks) {
+  TBV_ENTER(ctx);
   return filter_kstrongest_dev(ctx, polar_dev, n_az, n_range, row_stride, batch, params, want_peaks);
 }
 
 int tbv_filter_fetch(tbv_ctx* ctx, tbv_points* out_filtered, tbv_points* out_peaks) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && ctx->filt.batch > 0, "no filter result on the device");
   int rc = fetch_cloud(ctx, ctx->filt.filtered, ctx->filt.batch, out_filtered);
   if (rc) return rc;
@@ -682,6 +674,7 @@ int tbv_filter_fetch(tbv_ctx* ctx, tbv_points* out_filtered, tbv_points* out_pea
 
 int tbv_filter_kstrongest(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_range, size_t row_stride, int batch,
                           const tbv_filter_params* params, tbv_points* out_filtered, tbv_points* out_peaks) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && polar && params && out_filtered, "null pointer");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
@@ -695,6 +688,7 @@ int tbv_filter_kstrongest(tbv_ctx* ctx, const uint8_t* polar, int n_az, int n_ra
 }
 
 int tbv_compensate(tbv_ctx* ctx, float* x, float* y, int n, const double mot_xyt[3], int ccw) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && x && y && mot_xyt && n >= 0, "null pointer");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n == 0) return TBV_OK;

@@ -9,6 +9,7 @@
 // sharded over ranks.
 #include <cmath>
 
+#include "tbv_comm.cuh"
 #include "tbv_reg.cuh"
 
 namespace tbv {
@@ -93,7 +94,9 @@ struct tbv_loopdb {
   DevBuf<Candidate> cand;
   DevBuf<tbv_constraint> out;
   DevBuf<int> n_out;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // tbv_loopdb_register_sharded's optional phase timing
   void release() {
+    for (cudaEvent_t& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     store.release(); grids.release(); views.release(); problems.release(); fixed_set.release(); fixed_pose.release();
     results.release(); cand.release(); out.release(); n_out.release();
   }
@@ -148,6 +151,7 @@ int loopdb_enqueue(tbv_loopdb* db, int n_cand, const int* from, const int* to, c
 extern "C" {
 
 tbv_loopdb* tbv_loopdb_create(tbv_ctx* ctx, int max_keyframes, int cell_capacity) {
+  TBV_ENTER(ctx);
   if (!ctx || max_keyframes < 1 || cell_capacity < 1) { set_error("tbv_loopdb_create: bad arguments"); return nullptr; }
   tbv_loopdb* db = new tbv_loopdb();
   db->ctx = ctx; db->max_kf = max_keyframes; db->cell_cap = cell_capacity;
@@ -162,6 +166,7 @@ tbv_loopdb* tbv_loopdb_create(tbv_ctx* ctx, int max_keyframes, int cell_capacity
 }
 
 void tbv_loopdb_destroy(tbv_loopdb* db) {
+  TBV_ENTER(db ? db->ctx : nullptr);
   if (!db) return;
   cudaStreamSynchronize(db->ctx->stream);
   db->release();
@@ -171,6 +176,7 @@ void tbv_loopdb_destroy(tbv_loopdb* db) {
 int tbv_loopdb_size(tbv_loopdb* db) { return db ? db->n_kf : TBV_ERR_INVALID; }
 
 int tbv_loopdb_add(tbv_loopdb* db, int n_sets, const tbv_cell* const* sets, const int* n_cells, int* first_id) {
+  TBV_ENTER(db ? db->ctx : nullptr);
   TBV_REQUIRE(db && sets && n_cells && n_sets >= 0, "bad arguments");
   TBV_REQUIRE(db->n_kf + n_sets <= db->max_kf, "keyframe database is full");
   tbv_ctx* ctx = db->ctx;
@@ -196,6 +202,7 @@ int tbv_loopdb_add(tbv_loopdb* db, int n_sets, const tbv_cell* const* sets, cons
 int tbv_loopdb_register_dev(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
                             const int* candidate_index, const double* quality, const tbv_reg_params* params, double max_score,
                             tbv_constraint* out_dev, int out_capacity, int* n_out_dev) {
+  TBV_ENTER(db ? db->ctx : nullptr);
   TBV_REQUIRE(db && n_cand >= 0 && params && out_dev && n_out_dev && out_capacity >= 0, "bad arguments");
   if (n_cand == 0) {
     TBV_CUDA(cudaMemsetAsync(n_out_dev, 0, sizeof(int), db->ctx->stream));
@@ -208,6 +215,7 @@ int tbv_loopdb_register_dev(tbv_loopdb* db, int n_cand, const int* from, const i
 int tbv_loopdb_register(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
                         const int* candidate_index, const double* quality, const tbv_reg_params* params, double max_score,
                         tbv_constraint* out, int out_capacity, int* n_out, tbv_reg_summary* summaries) {
+  TBV_ENTER(db ? db->ctx : nullptr);
   TBV_REQUIRE(db && n_cand >= 0 && params && n_out && out_capacity >= 0 && (out || out_capacity == 0), "bad arguments");
   *n_out = 0;
   if (n_cand == 0) return TBV_OK;
@@ -234,6 +242,72 @@ int tbv_loopdb_register(tbv_loopdb* db, int n_cand, const int* from, const int* 
       s->last_relative_decrease = r.last_relative_decrease;
     }
   return TBV_OK;
+}
+
+int tbv_loopdb_register_sharded(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
+                                const double* quality, const tbv_reg_params* params, double max_score, tbv_constraint* all,
+                                int all_capacity, int* n_all, float* timing_ms) {
+  TBV_ENTER(db ? db->ctx : nullptr);
+  TBV_REQUIRE(db && n_cand >= 0 && params && n_all && all_capacity >= 0 && (all || all_capacity == 0), "bad arguments");
+  TBV_REQUIRE(n_cand == 0 || (from && to && T_from && T_to), "bad arguments");
+  tbv_ctx* ctx = db->ctx;
+  const int world = comm_world(ctx), rank = comm_rank(ctx);
+  *n_all = 0;
+  if (timing_ms) for (int i = 0; i < 4; i++) timing_ms[i] = 0.f;
+  if (n_cand == 0) return TBV_OK;
+  // this rank's share: from mod world == rank, ascending global index; capacity = the largest share over ranks, which
+  // every rank computes from the replicated list
+  std::vector<int> share(world, 0), mine;
+  for (int p = 0; p < n_cand; p++) {
+    TBV_REQUIRE(from[p] >= 0, "candidate indexes a keyframe that is not in the database");
+    const int r = from[p] % world;
+    share[r]++;
+    if (r == rank) mine.push_back(p);
+  }
+  int capacity = 1;
+  for (int r = 0; r < world; r++) capacity = std::max(capacity, share[r]);
+  const int n_mine = (int)mine.size();
+  std::vector<int> f(n_mine), t(n_mine);
+  std::vector<double> Tf((size_t)n_mine * 3), Tt((size_t)n_mine * 3), q;
+  if (quality) q.resize((size_t)n_mine * 2);
+  for (int i = 0; i < n_mine; i++) {
+    const int p = mine[i];
+    f[i] = from[p]; t[i] = to[p];
+    for (int c = 0; c < 3; c++) { Tf[3 * (size_t)i + c] = T_from[3 * (size_t)p + c]; Tt[3 * (size_t)i + c] = T_to[3 * (size_t)p + c]; }
+    if (quality) { q[2 * (size_t)i] = quality[2 * (size_t)p]; q[2 * (size_t)i + 1] = quality[2 * (size_t)p + 1]; }
+  }
+  int rc = comm_reserve(ctx, capacity);
+  if (rc) return rc;
+  if (timing_ms)
+    for (cudaEvent_t& e : db->ev)
+      if (!e) TBV_CUDA(cudaEventCreate(&e));
+  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[0], ctx->stream));
+  if (n_mine > 0) {
+    rc = loopdb_enqueue(db, n_mine, f.data(), t.data(), Tf.data(), Tt.data(), mine.data(), quality ? q.data() : nullptr, params, max_score,
+                        comm_send_records(ctx), capacity, comm_send_count(ctx));
+    if (rc) return rc;
+  } else {
+    TBV_CUDA(cudaMemsetAsync(comm_send_count(ctx), 0, sizeof(int), ctx->stream));
+  }
+  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[1], ctx->stream));
+  if ((rc = comm_allgather_merge(ctx, capacity))) return rc;
+  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[2], ctx->stream));
+  TBV_CUDA(cudaMemcpyAsync(n_all, comm_n_all(ctx), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  int n = *n_all;
+  if (n > all_capacity) { set_error("tbv_loopdb_register_sharded: %d constraints accepted, room for %d", n, all_capacity); n = all_capacity; rc = TBV_ERR_CAPACITY; }
+  if (n > 0) TBV_CUDA(cudaMemcpyAsync(all, comm_all(ctx), (size_t)n * sizeof(tbv_constraint), cudaMemcpyDeviceToHost, ctx->stream));
+  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[3], ctx->stream));
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (timing_ms) {
+    // {registration + packing, all-gather + merge, -, whole call}: the collective and the merge kernel are timed together here; their
+    // split is available through tbv_profile_begin/_end ("nccl_all_gather", "k_merge_constraints")
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[0], db->ev[0], db->ev[1]));
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[1], db->ev[1], db->ev[2]));
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[2], db->ev[2], db->ev[3]));
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[3], db->ev[0], db->ev[3]));
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -69,6 +69,8 @@ tbv_ctx* tbv_create(int device) {
   }
   tbv_ctx* ctx = new tbv_ctx();
   ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (ctx->sm_count <= 0) ctx->sm_count = 148;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
     delete ctx;
@@ -85,6 +87,7 @@ tbv_ctx* tbv_create(int device) {
 }
 
 void tbv_destroy(tbv_ctx* ctx) {
+  TBV_ENTER(ctx);
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -92,12 +95,14 @@ void tbv_destroy(tbv_ctx* ctx) {
   F.polar.release(); F.row_keys.release(); F.row_cnt.release(); F.cs_table.release(); F.filtered.release(); F.peaks.release();
   cells_release(ctx);
   reg_release(ctx);
+  comm_release(ctx);
   for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 int tbv_profile_begin(tbv_ctx* ctx) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx, "null context");
   ctx->prof.n = 0;
   ctx->prof.on = true;
@@ -106,6 +111,7 @@ int tbv_profile_begin(tbv_ctx* ctx) {
 }
 
 int tbv_profile_end(tbv_ctx* ctx, int capacity, const char** names, float* ms, int* n) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && n, "null pointer");
   Prof& P = ctx->prof;
   P.on = false;
@@ -127,6 +133,7 @@ int tbv_profile_end(tbv_ctx* ctx, int capacity, const char** names, float* ms, i
 void* tbv_stream(tbv_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int tbv_synchronize(tbv_ctx* ctx) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx, "null context");
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   return TBV_OK;
@@ -147,6 +154,7 @@ void tbv_host_free(void* p) {
 }
 
 int tbv_rotate90ccw(tbv_ctx* ctx, const uint8_t* src, int rows, int cols, uint8_t* dst) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && src && dst && rows > 0 && cols > 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   const size_t n = (size_t)rows * cols;

@@ -305,6 +305,7 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
 extern "C" {
 
 tbv_odom* tbv_odom_create(tbv_ctx* ctx, int n_seq, int n_az, int n_range, const tbv_odom_params* params) {
+  TBV_ENTER(ctx);
   if (!ctx || !params || n_seq <= 0 || n_az <= 0 || n_range <= 0) { set_error("tbv_odom_create: bad arguments"); return nullptr; }
   if (params->submap_scan_size < 1 || params->submap_scan_size > MAX_KF) { set_error("submap_scan_size must be in [1,%d]", MAX_KF); return nullptr; }
   if (!(params->res > 0) || !(params->downsample_factor > 0)) { set_error("res and downsample_factor must be positive"); return nullptr; }
@@ -331,6 +332,7 @@ tbv_odom* tbv_odom_create(tbv_ctx* ctx, int n_seq, int n_az, int n_range, const 
 void tbv_odom_destroy(tbv_odom* od) { odom_free(od); }
 
 int tbv_odom_reset(tbv_odom* od) {
+  TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od, "null handle");
   tbv_ctx* ctx = od->ctx;
   cudaSetDevice(ctx->device);
@@ -346,12 +348,14 @@ int tbv_odom_reset(tbv_odom* od) {
 }
 
 int tbv_odom_step_dev(tbv_odom* od, const uint8_t* polar_dev) {
+  TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od && polar_dev, "null pointer");
   cudaSetDevice(od->ctx->device);
   return odom_enqueue(od, polar_dev);
 }
 
 int tbv_odom_fetch(tbv_odom* od, tbv_odom_out* out) {
+  TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od && out, "null pointer");
   TBV_CUDA(cudaMemcpyAsync(out, od->outs_dev.p, (size_t)od->n_seq * sizeof(tbv_odom_out), cudaMemcpyDeviceToHost, od->ctx->stream));
   TBV_CUDA(cudaStreamSynchronize(od->ctx->stream));
@@ -374,6 +378,7 @@ static int odom_pipeline_init(tbv_odom* od) {
 }
 
 int tbv_odom_submit(tbv_odom* od, const uint8_t* polar_host) {
+  TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od && polar_host, "null pointer");
   TBV_REQUIRE(od->n_submitted - od->n_collected < 2, "two steps are already in flight: call tbv_odom_collect first");
   cudaSetDevice(od->ctx->device);
@@ -396,6 +401,7 @@ int tbv_odom_submit(tbv_odom* od, const uint8_t* polar_host) {
 }
 
 int tbv_odom_collect(tbv_odom* od, tbv_odom_out* out) {
+  TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od && out, "null pointer");
   TBV_REQUIRE(od->n_collected < od->n_submitted, "nothing in flight");
   const int b = od->n_collected & 1;
@@ -406,6 +412,7 @@ int tbv_odom_collect(tbv_odom* od, tbv_odom_out* out) {
 }
 
 int tbv_odom_step(tbv_odom* od, const uint8_t* polar_host, tbv_odom_out* out) {
+  TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od && polar_host && out, "null pointer");
   TBV_REQUIRE(od->n_submitted == od->n_collected, "steps are in flight: collect them before a synchronous step");
   int rc = tbv_odom_submit(od, polar_host);
@@ -414,6 +421,7 @@ int tbv_odom_step(tbv_odom* od, const uint8_t* polar_host, tbv_odom_out* out) {
 }
 
 int tbv_odom_cells(tbv_odom* od, int seq, int keyframe, tbv_cell* cells, int capacity, int* n_cells, double pose[3]) {
+  TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od && cells && n_cells && seq >= 0 && seq < od->n_seq && capacity > 0, "bad arguments");
   tbv_ctx* ctx = od->ctx;
   cudaSetDevice(ctx->device);

@@ -724,6 +724,7 @@ using namespace tbv;
 extern "C" int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, int n_con, const int* ids, const double* meas, const double* info,
                                 const tbv_pgo_params* params, int fixed_node, double* cost, double* H_diag, double* H_off, double* g,
                                 double* residuals) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && nodes && ids && meas && params && H_diag && H_off && g && n_nodes >= 1 && n_con >= 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(params->replace_cov_by_identity || info, "information matrices required when replace_cov_by_identity is 0");
@@ -792,6 +793,7 @@ extern "C" int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, 
 
 extern "C" int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const int* ids, const double* H_diag, const double* H_off, const double* g,
                                   int fixed_node, double radius, int max_iters, double rel_tol, double* delta, int* iters, double* rel_residual) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && ids && H_diag && H_off && g && delta && n_nodes >= 1 && n_con >= 0 && radius > 0 && max_iters >= 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   for (int c = 0; c < n_con; c++)

@@ -1131,50 +1131,37 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   RegScratch& S = *reg_scratch(ctx);
   TBV_REQUIRE(max_fixed <= RG_MAX_FIXED, "too many fixed scans per problem (at most 16)");
   (void)tgt_cap;
-  static int min_ctas = 0;
-  if (!min_ctas) {
-    const char* e = getenv("TBV_REG_CTAS");
-    min_ctas = (e && atoi(e) == 3) ? 3 : 4;
-  }
-  static unsigned long long* dbg = nullptr;
-  static const bool want_dbg = getenv("TBV_REG_DBG") != nullptr;
-  if (want_dbg && !dbg) TBV_CUDA(cudaMalloc((void**)&dbg, 8 * sizeof(unsigned long long)));
-  if (want_dbg) TBV_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(unsigned long long), ctx->stream));
   // dynamic shared memory for the staged working set: 4 CTAs x (48 KB + 4.2 KB static + 1 KB reserved) fit one SM's 228 KB
   constexpr int RG_STAGE = 48 * 1024;
-  static bool stage_attr = false;
-  if (!stage_attr) {
-    TBV_CUDA(cudaFuncSetAttribute(k_register<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_STAGE));
-    TBV_CUDA(cudaFuncSetAttribute(k_register<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_STAGE));
-    stage_attr = true;
-  }
-  static const int stage_bytes = getenv("TBV_REG_NOSTAGE") ? 0 : RG_STAGE;
-  if (min_ctas == 3)
-    k_register<3><<<n_problems, RG_THREADS, stage_bytes, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
+  unsigned long long* dbg = nullptr;  // per-phase cycle counters: development builds only (-DTBV_DEV_TIMERS)
+#ifdef TBV_DEV_TIMERS
+  if (!S.dbg.p) { if ((rc = S.dbg.reserve(8))) return rc; }
+  dbg = S.dbg.p;
+  TBV_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(unsigned long long), ctx->stream));
+#endif
+  if ((rc = ensure_dyn_smem(ctx, k_register<4>, RG_STAGE + 1))) return rc;   // + 1: opt in even at exactly 48 KB (the static part comes on top)
+  k_register<4><<<n_problems, RG_THREADS, RG_STAGE, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg, stage_bytes);
-  else
-    k_register<4><<<n_problems, RG_THREADS, stage_bytes, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
-                                                               slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg, stage_bytes);
+                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg, RG_STAGE);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
-  if (want_dbg) {  // debug only: mean cycles per problem spent in association / evaluation / LM + barrier
+#ifdef TBV_DEV_TIMERS
+  {  // mean cycles per problem spent in association / evaluation / LM + barrier
     unsigned long long h[8];
     TBV_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     TBV_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h[4]) fprintf(stderr, "k_register cycles/problem: associate %.0f  evaluate %.0f  lm+barrier %.0f  total %.0f\n", (double)h[0] / h[4], (double)h[1] / h[4],
                       (double)h[2] / h[4], (double)h[3] / h[4]);
   }
+#endif
   return TBV_OK;
 }
 
 int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets, double max_extent) {
   if (n_launch <= 0) return TBV_OK;
-  static bool attr = false;
-  if (!attr) {
-    TBV_CUDA(cudaFuncSetAttribute(k_cellgrid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, GRID_CAP * (int)sizeof(int)));
-    attr = true;
+  {
+    const int rc = ensure_dyn_smem(ctx, k_cellgrid_build, (size_t)GRID_CAP * sizeof(int));
+    if (rc) return rc;
   }
   // shared-memory counters for as many buckets as a grid over cells within max_extent of the sensor can have (<= GRID_CAP): for the
   // odometry's 181 m that is 33 KB instead of 64 KB, so all 592 CTAs are resident at once instead of running as 1.33 waves
@@ -1311,6 +1298,7 @@ extern "C" {
 int tbv_pair_normal_eq(tbv_ctx* ctx, const tbv_cell* tgt, int n_tgt, const double T_tgt[3], const tbv_cell* src, int n_src,
                        const double T_src[3], const tbv_reg_params* params, int itr, double* cost, int* n_res, double H[9], double g[3],
                        int32_t* assoc) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && T_tgt && T_src && params && n_tgt >= 0 && n_src >= 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   const tbv_cell* scans[2] = {tgt, src};
@@ -1335,6 +1323,7 @@ int tbv_pair_normal_eq(tbv_ctx* ctx, const tbv_cell* tgt, int n_tgt, const doubl
 
 int tbv_register(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, double* T, const tbv_reg_params* params,
                  tbv_reg_summary* summary) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && scans && n_cells && T && params && n_scans >= 2, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   RegResult r;
@@ -1356,6 +1345,7 @@ int tbv_register(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const 
 
 int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T, const tbv_reg_params* params,
                  int itr, double* score, double* cost, int* n_res, double* residuals, int res_capacity) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && scans && n_cells && T && params && n_scans >= 2, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   RegResult r;
@@ -1375,6 +1365,7 @@ int tbv_get_cost(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const 
 // evaluations around T.back() are n^3 independent problems over the same cell sets -> ONE launch of k_register in evaluation mode.
 int tbv_cost_samples(tbv_ctx* ctx, int n_scans, const tbv_cell* const* scans, const int* n_cells, const double* T, const tbv_reg_params* params,
                      int itr, double xy_range, double yaw_range, int n_per_axis, double* samples) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && scans && n_cells && T && params && samples && n_scans >= 2 && n_per_axis >= 1 && n_per_axis <= 16, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   auto linspace = [](double start, double end, int num) {  // odometrykeyframefuser.cpp:498-524
@@ -1535,6 +1526,7 @@ int tbv_cov_from_cost_samples(const double* samples, int n_samples, double score
 int tbv_register_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, const int* n_cells, int n_pairs, const int* from_set,
                        const int* to_set, const double* T_from, const double* T_to, const tbv_reg_params* params, double* T_revised,
                        double* T_align, tbv_reg_summary* summaries) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && sets && n_cells && from_set && to_set && T_from && T_to && params && n_sets >= 1 && n_pairs >= 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n_pairs == 0) return TBV_OK;
@@ -1588,6 +1580,7 @@ int tbv_register_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, co
 int tbv_cfear_quality_batch(tbv_ctx* ctx, int n_sets, const tbv_cell* const* sets, const int* n_cells, int n_pairs, const int* src_set,
                             const int* ref_set, const double* T_src, const double* T_offset, const double* T_ref, const tbv_reg_params* params,
                             double* quality) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && sets && n_cells && src_set && ref_set && T_src && T_ref && params && quality && n_sets >= 1 && n_pairs >= 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);
   if (n_pairs == 0) return TBV_OK;

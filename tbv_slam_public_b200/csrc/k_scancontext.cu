@@ -360,6 +360,7 @@ extern "C" {
 
 int tbv_sc_make(tbv_ctx* ctx, const float* x, const float* y, const float* intensity, int n, const tbv_sc_params* p, int n_offsets,
                 const double* offsets_xy, double* desc, float* ringkey, double* sectorkey) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && p && desc && offsets_xy && n >= 0 && n_offsets >= 1, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   TBV_REQUIRE(n == 0 || (x && y && intensity), "null cloud");
@@ -373,8 +374,7 @@ int tbv_sc_make(tbv_ctx* ctx, const float* x, const float* y, const float* inten
       (rc = dsk.up(ctx, nullptr, (size_t)n_offsets * S)))
     return rc;
   const size_t smem = (size_t)R * S * (sizeof(double) + 1) + 8;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) { TBV_CUDA(cudaFuncSetAttribute(sc_make, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  if ((rc = ensure_dyn_smem(ctx, sc_make, smem))) return rc;
   sc_make<<<n_offsets, 256, smem, ctx->stream>>>(dx.b.p, dy.b.p, di.b.p, n, R, S, p->max_radius, p->desc_function, p->desc_divider, p->no_point, doff.b.p,
                                                  ddesc.b.p, drk.b.p, dsk.b.p);
   launched(ctx, "sc_make");
@@ -388,6 +388,7 @@ int tbv_sc_make(tbv_ctx* ctx, const float* x, const float* y, const float* inten
 
 int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const double* desc_c, int n_c, int n_pairs, const int* q_idx,
                           const int* c_idx, const tbv_sc_params* p, double* dist, int* shift) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && desc_q && desc_c && q_idx && c_idx && p && dist && shift && n_q >= 1 && n_c >= 1 && n_pairs >= 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n_pairs == 0) return TBV_OK;
@@ -403,8 +404,7 @@ int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const dou
   if ((rc = dq.up(ctx, desc_q, (size_t)n_q * R * S)) || (rc = dc.up(ctx, desc_c, (size_t)n_c * R * S)) || (rc = dqi.up(ctx, q_idx, n_pairs)) ||
       (rc = dci.up(ctx, c_idx, n_pairs)) || (rc = dd.up(ctx, nullptr, n_pairs)) || (rc = dsh.up(ctx, nullptr, n_pairs)))
     return rc;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) { TBV_CUDA(cudaFuncSetAttribute(sc_distance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  if ((rc = ensure_dyn_smem(ctx, sc_distance, smem))) return rc;
   sc_distance<<<n_pairs, 128, smem, ctx->stream>>>(dq.b.p, dc.b.p, dqi.b.p, dci.b.p, R, S, radius, dd.b.p, dsh.b.p);
   launched(ctx, "sc_distance");
   TBV_CUDA(cudaGetLastError());
@@ -415,6 +415,7 @@ int tbv_sc_distance_batch(tbv_ctx* ctx, const double* desc_q, int n_q, const dou
 
 int tbv_sc_search(tbv_ctx* ctx, const float* db_keys, const double* odom_xyt, int n_db, int n_q, const float* q_keys, const int* q_current,
                   const tbv_sc_params* p, int* cand_idx, double* cand_odom_sim, int* n_exclude) {
+  TBV_ENTER(ctx);
   TBV_REQUIRE(ctx && db_keys && odom_xyt && q_keys && q_current && p && cand_idx && n_db >= 1 && n_q >= 0, "bad arguments");
   AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
   if (n_q == 0) return TBV_OK;

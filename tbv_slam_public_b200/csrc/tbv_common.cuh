@@ -111,6 +111,11 @@ struct FilterState {  // device-resident result of the last k-strongest call
   DevCloud filtered, peaks;
 };
 
+struct SmemOptIn {  // largest dynamic shared-memory size a kernel has been opted into on this context's device
+  const void* func;
+  size_t bytes;
+};
+
 struct Prof {  // optional per-launch device timing: one event after every kernel launch (tbv_profile_begin/_end)
   bool on = false;
   int n = 0;
@@ -124,13 +129,41 @@ struct tbv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  int sm_count = 148;             // multiprocessors of `device` (queried in tbv_create)
   tbv::Prof prof;
+  std::vector<tbv::SmemOptIn> smem_optin;  // per context (= per device): no process-global launch state
   tbv::FilterState filt;
   void* cells_scratch = nullptr;  // tbv::CellsScratch (k_cells.cu)
   void* reg_scratch = nullptr;    // tbv::RegScratch (k_register.cu)
+  void* comm = nullptr;           // tbv::CommState (k_comm.cu): NCCL communicator + exchange buffers, or null
 };
 
+// Every C-ABI entry point makes its context's device current first: contexts on different devices may live in one process
+// (one host thread per context, or one thread alternating between them).
+#define TBV_ENTER(c)                             \
+  do {                                           \
+    const tbv_ctx* _tbv_c = (c);                 \
+    if (_tbv_c) cudaSetDevice(_tbv_c->device);   \
+  } while (0)
+
 namespace tbv {
+// Opt kernel `func` into `bytes` of dynamic shared memory on this context's device (a per-device attribute; sizes <= 48 KB need
+// nothing).  The record is kept per context, so a second context on another device gets its own opt-in.
+template <typename F>
+inline int ensure_dyn_smem(tbv_ctx* ctx, F* func, size_t bytes) {
+  if (bytes <= 48 * 1024) return TBV_OK;
+  const void* f = reinterpret_cast<const void*>(func);
+  for (SmemOptIn& o : ctx->smem_optin)
+    if (o.func == f) {
+      if (o.bytes >= bytes) return TBV_OK;
+      TBV_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      o.bytes = bytes;
+      return TBV_OK;
+    }
+  TBV_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  ctx->smem_optin.push_back({f, bytes});
+  return TBV_OK;
+}
 void prof_mark(tbv_ctx* ctx, const char* name);  // k_misc.cu
 inline void launched(tbv_ctx* ctx, const char* name) {  // bookkeeping after every kernel launch of this library
   ctx->launches++;
@@ -143,4 +176,5 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
 int compensate_clouds_dev(tbv_ctx* ctx, DevCloud& cloud, const double* mot_dev /*[batch][3]*/, int ccw);
 void cells_release(tbv_ctx* ctx);
 void reg_release(tbv_ctx* ctx);
+void comm_release(tbv_ctx* ctx);
 }  // namespace tbv

@@ -75,7 +75,8 @@ struct RegScratch {            // association / residual-block scratch, [n_probl
   DevBuf<double> blocks;       // [n_problems][BLK_FIELDS][max_fixed*slot_cap] compacted residual blocks, field-major
   DevBuf<int> n_blocks;        // [n_problems]
   DevBuf<double> residuals;    // [n_problems][2*max_fixed*slot_cap] (eval mode, optional)
-  void release() { assoc.release(); wgt.release(); blocks.release(); n_blocks.release(); residuals.release(); }
+  DevBuf<unsigned long long> dbg;  // development builds only (-DTBV_DEV_TIMERS): per-phase cycle counters
+  void release() { assoc.release(); wgt.release(); blocks.release(); n_blocks.release(); residuals.release(); dbg.release(); }
 };
 
 // Launches one CTA per problem.  All pointers are device pointers.  slot_cap >= number of cells of any moving scan,

@@ -22,14 +22,19 @@ from . import graph_io as G
 from . import trajectory_io as TIO
 
 
+def _wrap(t: float) -> float:
+    """Yaw in (-pi, pi], as Affine3dToVectorXYeZ's atan2 yields it (utils.cpp:115-122) and as the device stores poses (k_odom.cu)."""
+    return math.atan2(math.sin(t), math.cos(t))
+
+
 def _mul(a, b):
     ca, sa = math.cos(a[2]), math.sin(a[2])
-    return np.array([a[0] + ca * b[0] - sa * b[1], a[1] + sa * b[0] + ca * b[1], a[2] + b[2]])
+    return np.array([a[0] + ca * b[0] - sa * b[1], a[1] + sa * b[0] + ca * b[1], _wrap(a[2] + b[2])])
 
 
 def _inv(a):
     ca, sa = math.cos(a[2]), math.sin(a[2])
-    return np.array([-(ca * a[0] + sa * a[1]), -(-sa * a[0] + ca * a[1]), -a[2]])
+    return np.array([-(ca * a[0] + sa * a[1]), -(-sa * a[0] + ca * a[1]), _wrap(-a[2])])
 
 
 class GpuOdometryDevice:

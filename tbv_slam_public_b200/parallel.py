@@ -8,8 +8,13 @@ What shards and how
     are independent given the keyframe database, so the candidate list shards by `id_from mod world` (`shard_candidates`),
     every rank keeps the whole database (cells ~33 kB / keyframe), registers its share in one launch (tbv_loopdb_register_dev)
     and the accepted constraints — fixed-size 128-byte tbv_constraint records, padded to the largest share — are exchanged
-    with ONE all-gather straight from device memory (`all_gather_constraints`).  Every rank ends up with the same list in
-    global candidate order, which is what PoseGraph::AddConstraintThSafe would have seen in the serial program.
+    with ONE all-gather straight from device memory.  Every rank ends up with the same list in global candidate order, which
+    is what PoseGraph::AddConstraintThSafe would have seen in the serial program.
+
+The exchange itself lives behind the C-ABI (tbv_comm_init_rank / tbv_loopdb_register_sharded / tbv_allgather_constraints:
+ncclAllGather on the context's stream + a device merge, csrc/k_comm.cu) so that a C++/ROS host can run it; on GPUs this module
+only hands the library an ncclUniqueId through torch.distributed's store (`init_comm`).  `all_gather_constraints` below is the
+same record exchange over a torch.distributed group and exists for the gloo / world-2 CPU tests of the host logic.
 """
 from __future__ import annotations
 
@@ -43,6 +48,18 @@ def shard_capacity(id_from, world: int) -> int:
     return int(np.bincount(id_from % world, minlength=world).max())
 
 
+def init_comm(ctx, group=None):
+    """Gives `ctx` an NCCL communicator spanning the torch.distributed group: rank 0 draws the ncclUniqueId (tbv_comm_unique_id), the
+    group's object broadcast carries its 128 bytes, every rank calls tbv_comm_init_rank.  No-op for a single process."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 1, 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init_rank(box[0], world, rank)
+    return world, rank
+
+
 def all_gather_constraints(local: torch.Tensor, count: torch.Tensor, group=None) -> np.ndarray:
     """local: [cap, 128] uint8 records of this rank (first count[0] valid; same cap on every rank), on the GPU (NCCL) or the
     CPU (gloo); count: int32[1] on the same device.  Returns all valid records of all ranks as a CONSTRAINT_DTYPE array sorted
@@ -57,6 +74,8 @@ def all_gather_constraints(local: torch.Tensor, count: torch.Tensor, group=None)
         dist.all_gather_into_tensor(counts, count.reshape(1).to(torch.int32), group=group)
         dist.all_gather_into_tensor(gathered.reshape(-1), local.reshape(-1).contiguous(), group=group)
     counts_h = counts.cpu().numpy()
+    if int(counts_h.max(initial=0)) > cap:
+        raise ValueError(f"a rank reports {int(counts_h.max())} records but the exchange buffers hold {cap}")
     recs_h = gathered.cpu().numpy()
     parts = [recs_h[r, :int(counts_h[r])].reshape(-1).view(CONSTRAINT_DTYPE) for r in range(world)]
     out = np.concatenate(parts) if parts else np.zeros(0, CONSTRAINT_DTYPE)
@@ -64,15 +83,28 @@ def all_gather_constraints(local: torch.Tensor, count: torch.Tensor, group=None)
 
 
 class ShardedLoopClosure:
-    """Candidate registration sharded over the ranks of a process group; the database is replicated."""
+    """Candidate registration sharded over the ranks of a process group; the database is replicated.
 
-    def __init__(self, db: LoopDB, group=None):
-        self.db, self.group = db, group
+    On GPUs (the product path) the whole exchange is ONE library call, tbv_loopdb_register_sharded, over the context's NCCL communicator
+    (created here from the torch.distributed group if the context has none).  `transport="torch"` keeps the records on the device and
+    gathers them with torch.distributed instead — the form the gloo CPU tests exercise."""
+
+    def __init__(self, db: LoopDB, group=None, transport: str = "nccl"):
+        self.db, self.group, self.transport = db, group, transport
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.stream = torch.cuda.ExternalStream(db.ctx.stream)
+        if transport == "nccl":
+            if self.world > 1 and db.ctx.comm_world()[0] != self.world:
+                init_comm(db.ctx, group)
+        else:
+            self.stream = torch.cuda.ExternalStream(db.ctx.stream)
+        self.last_timing = None
 
     def register_candidates(self, id_from, id_to, T_from, T_to, quality=None, params: RegParams | None = None, max_score=0.0) -> np.ndarray:
+        if self.transport == "nccl":
+            out, self.last_timing = self.db.register_sharded(id_from, id_to, T_from, T_to, quality=quality, params=params, max_score=max_score,
+                                                             want_timing=True)
+            return out
         id_from = np.asarray(id_from, np.int32); id_to = np.asarray(id_to, np.int32)
         T_from = np.asarray(T_from, np.float64).reshape(-1, 3); T_to = np.asarray(T_to, np.float64).reshape(-1, 3)
         mine = shard_candidates(id_from, self.world, self.rank)

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <fstream>
 
+#include <cuda_runtime_api.h>
+
 #include "tbv_b200.hpp"
 #include "tbv_oracle.hpp"
 #include "tbv_oracle_reg.hpp"
@@ -172,6 +174,56 @@ int main(int argc, char** argv) {
       EXPECT(std::fabs(q[p].joint - r.joint) < 1e-8 && std::fabs(q[p].sep - r.sep) < 1e-8 && q[p].overlap == r.overlap, "CorAl pair %zu: %.12g %.12g vs %.12g %.12g", p, q[p].joint,
              q[p].sep, r.joint, r.sep);
     }
+  }
+  // ---- multi-GPU exports from a C++ host: the candidate loop of ScanContextClosure::SearchAndAddConstraint (loopclosure.cpp:658-724), sharded ------
+  // One rank here (a one-rank NCCL communicator is a real communicator): tbv_comm_unique_id -> tbv_comm_init_rank -> tbv_loopdb_register_sharded must
+  // return exactly the records of the single-GPU tbv_loopdb_register, and tbv_allgather_constraints must return a device-resident share unchanged.
+  {
+    int cell_cap = 1;
+    std::vector<const tbv_cell*> sets;
+    std::vector<int> n_cells;
+    for (auto& m : g_maps) { sets.push_back(m->cells.data()); n_cells.push_back((int)m->cells.size()); cell_cap = std::max(cell_cap, (int)m->cells.size()); }
+    tbv_loopdb* db = tbv_loopdb_create(ctx.get(), n_scans, cell_cap);
+    EXPECT(db != nullptr, "tbv_loopdb_create: %s", tbv_last_error());
+    int first = -1;
+    EXPECT(tbv_loopdb_add(db, n_scans, sets.data(), n_cells.data(), &first) == TBV_OK && first == 0, "tbv_loopdb_add: %s", tbv_last_error());
+    std::vector<int> from, to;
+    std::vector<double> Tf, Tt;
+    for (int a = 0; a < n_scans; a++)
+      for (int b = 0; b < n_scans; b++) {
+        if (a == b) continue;
+        from.push_back(a); to.push_back(b);
+        Tf.insert(Tf.end(), {1.77 * a + 0.4, 1.77 * a - 0.3, 0.785 + 0.02});     // a perturbed guess for `from`
+        Tt.insert(Tt.end(), {1.77 * b, 1.77 * b, 0.785});
+      }
+    const int n_cand = (int)from.size();
+    // n_scan_normal_reg(P2L) with ctor defaults (Huber 0.1, uniform weights) + SetParameters(4, 10), loopclosure.cpp:56-57
+    tbv_reg_params lp{gpu::P2L, gpu::Huber, gpu::Uniform, 0.1, 1.0, 0.0, 4, 10};
+    std::vector<tbv_constraint> ref(n_cand), got(n_cand), low(n_cand);
+    int n_ref = 0, n_got = 0, n_low = 0, world = 0, rank = -1;
+    EXPECT(tbv_loopdb_register(db, n_cand, from.data(), to.data(), Tf.data(), Tt.data(), nullptr, nullptr, &lp, 0.0, ref.data(), n_cand, &n_ref, nullptr) == TBV_OK,
+           "tbv_loopdb_register: %s", tbv_last_error());
+    EXPECT(n_ref >= n_cand / 2, "only %d of %d candidates accepted", n_ref, n_cand);
+    unsigned char id[TBV_COMM_ID_BYTES];
+    EXPECT(tbv_comm_unique_id(id) == TBV_OK, "tbv_comm_unique_id: %s", tbv_last_error());
+    EXPECT(tbv_comm_init_rank(ctx.get(), id, 1, 0) == TBV_OK, "tbv_comm_init_rank: %s", tbv_last_error());
+    EXPECT(tbv_comm_world(ctx.get(), &world, &rank) == TBV_OK && world == 1 && rank == 0, "tbv_comm_world");
+    float ms[4] = {0, 0, 0, 0};
+    EXPECT(tbv_loopdb_register_sharded(db, n_cand, from.data(), to.data(), Tf.data(), Tt.data(), nullptr, &lp, 0.0, got.data(), n_cand, &n_got, ms) == TBV_OK,
+           "tbv_loopdb_register_sharded: %s", tbv_last_error());
+    EXPECT(n_got == n_ref && std::memcmp(got.data(), ref.data(), (size_t)n_ref * sizeof(tbv_constraint)) == 0, "sharded registration differs from the single-GPU call (%d vs %d)", n_got, n_ref);
+    EXPECT(ms[3] > 0.f && ms[0] > 0.f, "phase timing missing");
+    // the low-level export: records left on the device by tbv_loopdb_register_dev, then the exchange
+    tbv_constraint* d_rec = nullptr;
+    int* d_n = nullptr;
+    EXPECT(cudaMalloc((void**)&d_rec, (size_t)n_cand * sizeof(tbv_constraint)) == 0 && cudaMalloc((void**)&d_n, sizeof(int)) == 0, "cudaMalloc");
+    EXPECT(tbv_loopdb_register_dev(db, n_cand, from.data(), to.data(), Tf.data(), Tt.data(), nullptr, nullptr, &lp, 0.0, d_rec, n_cand, d_n) == TBV_OK,
+           "tbv_loopdb_register_dev: %s", tbv_last_error());
+    EXPECT(tbv_allgather_constraints(ctx.get(), d_rec, d_n, n_cand, low.data(), n_cand, &n_low) == TBV_OK, "tbv_allgather_constraints: %s", tbv_last_error());
+    EXPECT(n_low == n_ref && std::memcmp(low.data(), ref.data(), (size_t)n_ref * sizeof(tbv_constraint)) == 0, "tbv_allgather_constraints changed the records");
+    cudaFree(d_rec); cudaFree(d_n);
+    EXPECT(tbv_comm_destroy(ctx.get()) == TBV_OK, "tbv_comm_destroy");
+    tbv_loopdb_destroy(db);
   }
   std::printf("PASS %d checks (%d scans %dx%d)\n", g_checks, n_scans, n_az, n_range);
   return 0;

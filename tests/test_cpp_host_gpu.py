@@ -16,7 +16,8 @@ def build_cpp_test() -> str:
     if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
         os.makedirs(os.path.dirname(BIN), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
-                               "-o", BIN, src, "-L" + os.path.join(ROOT, "tbv_slam_public_b200"), "-ltbv_b200",
+                               "-I/usr/local/cuda/include", "-o", BIN, src, "-L" + os.path.join(ROOT, "tbv_slam_public_b200"), "-ltbv_b200",
+                               "-L/usr/local/cuda/lib64", "-lcudart",
                                # relative run path: the tree is built in one place and run in another (the GPU box's snapshot)
                                "-Wl,-rpath,$ORIGIN/../../../tbv_slam_public_b200"])
     return BIN

@@ -176,3 +176,34 @@ def test_affine_helper_matches_numpy():
         assert np.allclose(m(a @ b), m(a) @ m(b), atol=1e-15) and np.allclose(m(a.inverse()), np.linalg.inv(m(a)), atol=1e-14)
         v = rng.normal(size=3); v[2] = math.remainder(v[2], 2 * math.pi)
         assert np.allclose(OO._Affine.from_xyt(v).xyt(), v, atol=1e-15)
+
+
+def test_frame_motion_stays_small_when_the_heading_crosses_pi():
+    """device poses are atan2-normalised; composing them with raw yaw sums gave a motion yaw near -2 pi for the frame after the
+    heading crosses +-pi, and Compensate scales that yaw by the per-point time fraction.  The motion must be the small relative turn."""
+    class Stub:
+        def __init__(self, poses):
+            self.poses, self.k, self.motions = poses, 0, []
+
+        def step(self, scan):
+            p = self.poses[self.k]
+            self.k += 1
+            return dict(pose=np.array(p, float), is_keyframe=True, n_keyframes=self.k, n_cells=0, score=0.0, itrs=0)
+
+        def newest_keyframe_cells(self, n):
+            return np.zeros((0, 16))
+
+        def clouds(self, scan, motion_xyt):
+            self.motions.append(np.array(motion_xyt, float))
+            e = np.zeros((0, 4), np.float32)
+            return e, e
+
+    yaws = [3.10, 3.13, -3.13, -3.10, -3.07]                          # +0.03 rad per frame across the branch cut
+    dev = Stub([(0.5 * i, 0.0, y) for i, y in enumerate(yaws)])
+    rd = OO.radarReader(dev)
+    for i in range(len(yaws)):
+        rd.process(np.zeros((4, 8), np.uint8), stamp_ns=i + 1)
+    for m in dev.motions[2:]:
+        assert abs(m[2]) < 0.05, m                                     # was -6.25 for the frame after the crossing
+    assert abs(dev.motions[3][2] - (2 * math.pi - 6.26)) < 1e-9
+    assert abs(OO._mul((0, 0, 3.0), (0, 0, 1.0))[2] - (4.0 - 2 * math.pi)) < 1e-12 and abs(OO._inv((0, 0, -math.pi))[2] - math.pi) < 1e-12
