@@ -140,10 +140,8 @@ def algorithmic_bytes(kernel: str, n_seq: int, st: dict) -> float | None:
     """ALGORITHMIC bytes one launch of `kernel` must move for n_seq scans (DESIGN.md 'Kernels'); None if not HBM-shaped."""
     npts, nsmp, ncell, nkf = st["n_points"], st["n_samples"], st["n_cells"], st["n_keyframes"]
     per = {
-        # scan bytes in + per-row keys (u32 x k) and counts (u16) out
-        "k1_kstrongest": SCAN_BYTES + N_AZ * K_STRONGEST * 4 + N_AZ * 2,
-        # row keys in + two clouds (x,y f32, I u8, az,rg u16 = 13 B/pt; peaks ~ a third of the points) out
-        "k2_make_clouds": N_AZ * K_STRONGEST * 4 + N_AZ * 2 + 13 * npts * 1.33,
+        # fused filter kernel: scan bytes in, the two clouds out (x,y f32, I u8, az,rg u16 = 13 B/pt; peaks ~ a third of the points)
+        "k1_filter_fused": SCAN_BYTES + 13 * npts * 1.33,
         "k_compensate": 2 * 8 * npts,
         # fused cells kernel: points (x,y f32 + I u8) in, one 16-double record per valid cell out (all tables in shared memory)
         "cells_fused": 9 * npts + 128 * ncell,
@@ -323,7 +321,7 @@ def run_ours(args):
     # The roofline object describes the kernel that dominates the step's HBM traffic: K1 streams every scan byte (96 % of the
     # step's algorithmic bytes).  The longest kernels (k_register, cells_fused) move ~100x fewer bytes and are bound by fp64
     # issue / dependent-load latency / barriers, not by HBM or the tensor pipe: their lines are in `kernels`, the whole step's in `step`.
-    dominant = "k1_kstrongest"
+    dominant = "k1_filter_fused"
     longest = max(kern, key=kern.get)
     b_dom = algorithmic_bytes(dominant, S, stats)
     achieved = b_dom / kern[dominant] / 1e6

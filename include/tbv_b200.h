@@ -226,6 +226,10 @@ void tbv_odom_destroy(tbv_odom* od);
 int tbv_odom_reset(tbv_odom* od);
 /* host scans [n_seq][n_az][n_range] (pinned or pageable) -> out[n_seq]; includes H2D and D2H */
 int tbv_odom_step(tbv_odom* od, const uint8_t* polar_host, tbv_odom_out* out);
+/* range_major != 0: from now on every scan handed to tbv_odom_step / _step_dev / _submit is in the sensor's wire layout
+ * [n_range][n_az] (MulRan and every non-Oxford dataset: radar_driver.cpp:74-90) and is rotated 90 deg CCW on the device as the
+ * first launch of the step — cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on receipt.  Default 0: azimuth-major [n_az][n_range] (Oxford). */
+int tbv_odom_set_wire_layout(tbv_odom* od, int range_major);
 /* scans already on the device; results stay on the device until tbv_odom_fetch */
 int tbv_odom_step_dev(tbv_odom* od, const uint8_t* polar_dev);
 int tbv_odom_fetch(tbv_odom* od, tbv_odom_out* out);

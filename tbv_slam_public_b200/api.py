@@ -137,6 +137,7 @@ _OPTIONAL = [
     ("tbv_odom_create", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(OdomParams)], C.c_void_p),
     ("tbv_odom_destroy", [C.c_void_p], None),
     ("tbv_odom_reset", [C.c_void_p], None),
+    ("tbv_odom_set_wire_layout", [C.c_void_p, C.c_int], None),
     ("tbv_odom_step", [C.c_void_p, C.c_void_p, C.c_void_p], None),
     ("tbv_odom_step_dev", [C.c_void_p, C.c_void_p], None),
     ("tbv_odom_fetch", [C.c_void_p, C.c_void_p], None),
@@ -522,6 +523,10 @@ class OdometryKeyframeFuser:
             self.close()
         except Exception:
             pass
+
+    def set_wire_layout(self, range_major: bool):
+        """True: scans arrive [n_range][n_az] (MulRan wire layout) and are rotated 90 deg CCW on the device on receipt (radar_driver.cpp:80-84)."""
+        _check(lib().tbv_odom_set_wire_layout(self.h, int(bool(range_major))))
 
     def reset(self):
         _check(lib().tbv_odom_reset(self.h))

@@ -4,31 +4,17 @@
 // (cfear_radarodometry/src/cfear_radarodometry/radar_filters.cpp:198-337) and CFEAR_Radarodometry::Compensate
 // (cfear_radarodometry/src/cfear_radarodometry/utils.cpp:96-113).
 //
-// K1 design (sm_100a, HBM-bound byte scan):
-//   * one warp owns one azimuth row at a time; rows are streamed HBM -> shared memory with cp.async (16-byte
-//     transfers, 8-byte head/tail when the row start is only 8-byte aligned, as every odd Oxford row is) into a
-//     per-warp double buffer, so the next row is in flight while the current one is processed and no registers are
-//     tied up by staging (3 CTAs x 8 warps x 3.7 KB in flight per SM);
-//   * the reference keeps, per row, the k largest (intensity, range) pairs under std::pair ordering — i.e. the k
-//     largest 24-bit keys (intensity << 16 | range) — in ascending order.  Bytes >= z_min are found with a 3-instruction
-//     SWAR compare per 4 bytes on conflict-free 16-byte shared loads; the (usually few) candidates are scattered to a
-//     per-warp list and ranked all-pairs (rank = number of larger keys), which yields both the selection (rank < k)
-//     and the output position;
-//   * rows with more candidates than the list holds (dense / adversarial input) take an exact two-level path:
-//     8-step binary search of the intensity threshold over the staged row, then a suffix scan over the ties so that
-//     the largest ranges win, exactly as the reference's erase(begin()) does;
-//   * the 7+7-tap axial non-max suppression runs in the same kernel on the selected bins straight from the staged row
-//     (bytes across the row edge come from global memory, as the reference's flat cv::Mat indexing reads them) and is
-//     stored as bit 31 of the key.
-// Output per row: up to k keys ascending + count.  K2 turns rows into the two ordered clouds.
+// Design (sm_100a, HBM-bound byte scan): ONE kernel, k1_filter_fused, turns scans into the two ordered clouds — see the comment above the
+// kernel.  The reference keeps, per azimuth row, the k largest (intensity, range) pairs under std::pair ordering, i.e. the k largest 24-bit
+// keys (intensity << 16 | range), ascending; bins at range <= min_range_bin stay in that selection but are not emitted; a selected bin is a
+// "peak" when its 7-tap score is not exceeded within +-3 bins (bytes across the row edge come from the neighbouring row of the flat
+// cv::Mat, as the reference's indexing reads them).
 #include <cmath>
 
 #include "tbv_common.cuh"
 
 namespace tbv {
 
-constexpr int K1_WARPS = 8;
-constexpr int K1_CAP = 128;  // per-warp candidate list capacity (also the largest supported k)
 
 __device__ __forceinline__ uint32_t ge_mask(uint32_t w, uint32_t addc, bool hi) {
   // 0x80 in every byte whose value >= z.  z <= 128: ((low7 + 128 - z) | w) & 0x80 ; z > 128: (low7 + 256 - z) & w & 0x80
@@ -99,323 +85,6 @@ __device__ __forceinline__ void stage_row_sync(uint8_t* buf, const uint8_t* rp, 
   __syncwarp();
 }
 
-template <bool HI>   // HI: z_min > 128 (selects the form of the byte compare at compile time: the scan loop carries no branch on it)
-__global__ void __launch_bounds__(K1_WARPS * 32)
-k1_kstrongest(const uint8_t* __restrict__ polar, int total_rows, int n_az, int n_range, size_t row_stride, int z_min, int k,
-              int want_peaks, int rowbuf, const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, uint32_t* __restrict__ row_keys,
-              uint32_t* __restrict__ row_cnt) {
-  extern __shared__ __align__(128) uint8_t s_dyn[];  // [K1_WARPS][2][rowbuf] staged rows
-  __shared__ __align__(16) uint32_t s_list[K1_WARPS][K1_CAP];  // candidates (unordered)
-  __shared__ __align__(16) uint32_t s_sel[K1_WARPS][K1_CAP];   // selected, ascending
-  __shared__ __align__(8) uint64_t s_bar[K1_WARPS][2];
-  __shared__ int s_n[K1_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned FULL = 0xffffffffu;
-  constexpr bool hi = HI;
-  const uint32_t z = (uint32_t)z_min;
-  const bool zero_thr = z == 0;   // every byte is a candidate: padding bytes must be masked explicitly
-  const uint32_t addc = (hi ? (256u - z) : (128u - z)) * 0x01010101u;
-  const size_t scan_bytes = (size_t)(n_az - 1) * row_stride + (size_t)n_range;  // addressable bytes of one scan
-  const size_t scan_stride = (size_t)n_az * row_stride;
-  uint8_t* mybuf = s_dyn + (size_t)warp * 2 * rowbuf;
-  uint32_t* list = s_list[warp];
-  uint32_t* sel = s_sel[warp];
-  uint64_t* bars = s_bar[warp];
-  const int row_step = gridDim.x * K1_WARPS;
-  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-  // Both row buffers start out zero: the scan loop below always runs over whole groups of 32 vectors (rowbuf is a multiple of 512
-  // bytes), and the bytes past a row's staged superset are never written by a bulk copy, so they stay below every threshold >= 1.
-  for (int o = lane * 16; o < 2 * rowbuf; o += 32 * 16) *reinterpret_cast<uint4*>(mybuf + o) = make_uint4(0, 0, 0, 0);
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  __syncwarp();
-
-  auto row_ptr = [&](int scan, int az) -> const uint8_t* { return polar + (size_t)scan * scan_stride + (size_t)az * row_stride; };
-  int row = blockIdx.x * K1_WARPS + warp;
-  // (scan, az) of the warp's current row, advanced without divisions: row += row_step
-  int scan = row / n_az, az = row - scan * n_az;
-  const int step_scan = row_step / n_az, step_az = row_step - step_scan * n_az;
-  int cur = 0;
-  uint32_t phase = 0;    // bit b: parity to wait for on bars[b]
-  bool in_flight = false;
-  if (row < total_rows) in_flight = stage_row_tma(mybuf, row_ptr(scan, az), n_range, buf_lo, buf_hi, &bars[0], lane);
-  for (; row < total_rows; row += row_step) {
-    const uint8_t* scan_base = polar + (size_t)scan * scan_stride;
-    const uint8_t* rp = scan_base + (size_t)az * row_stride;
-    const int a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
-    uint8_t* buf = mybuf + (size_t)cur * rowbuf;
-    // prefetch the next row of this warp into the other buffer (its previous contents were consumed last iteration)
-    const int nrow = row + row_step;
-    int scan_n = scan + step_scan, az_n = az + step_az;
-    if (az_n >= n_az) { az_n -= n_az; scan_n++; }
-    bool next_in_flight = false;
-    if (nrow < total_rows) next_in_flight = stage_row_tma(mybuf + (size_t)(cur ^ 1) * rowbuf, row_ptr(scan_n, az_n), n_range, buf_lo, buf_hi, &bars[cur ^ 1], lane);
-    if (in_flight) {
-      mbar_wait(&bars[cur], (phase >> cur) & 1u);
-      phase ^= 1u << cur;
-    } else {
-      stage_row_sync(buf, rp, n_range, lane);
-    }
-    // The staged superset starts up to 15 bytes before the row and ends up to 15 bytes after it: clear those bytes so that
-    // no threshold >= 1 ever matches them and the scan needs no per-vector validity test (z_min == 0 keeps the masks).
-    if (!zero_thr) {
-      const int head = a0, tail = (((a0 + n_range + 15) >> 4) << 4) - (a0 + n_range);
-      if (lane < head) buf[lane] = 0;
-      // the superset ends up to 15 bytes after the row; a previous row of this buffer with another alignment may have ended one
-      // vector later: clear through the end of that vector as well
-      if (lane < tail + 16 && a0 + n_range + lane < rowbuf) buf[a0 + n_range + lane] = 0;
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before the next bulk copy into this buffer
-      __syncwarp();
-    }
-
-    // word validity: byte offset wo in buf holds row index wo - a0; valid iff 0 <= wo + b - a0 < n_range
-    const int lo_b = a0, hi_b = a0 + n_range;  // valid buffer byte range [lo_b, hi_b)
-    auto valid_mask = [&](int wo) -> uint32_t {
-      uint32_t m = 0x80808080u;
-      if (wo < lo_b) m &= (lo_b - wo >= 4) ? 0u : (0x80808080u << (8 * (lo_b - wo)));
-      if (wo + 4 > hi_b) m &= (hi_b - wo <= 0) ? 0u : (0x80808080u >> (8 * (wo + 4 - hi_b)));
-      return m;
-    };
-    const int nvec = (hi_b + 15) >> 4;  // 16-byte vectors covering [0, hi_b)
-    const uint4* vbuf = reinterpret_cast<const uint4*>(buf);
-    auto masks = [&](const uint4 v, int wo, uint32_t ac, bool h, uint32_t m[4]) {
-      m[0] = ge_mask(v.x, ac, h); m[1] = ge_mask(v.y, ac, h); m[2] = ge_mask(v.z, ac, h); m[3] = ge_mask(v.w, ac, h);
-      if (zero_thr && (wo < lo_b || wo + 16 > hi_b)) { m[0] &= valid_mask(wo); m[1] &= valid_mask(wo + 4); m[2] &= valid_mask(wo + 8); m[3] &= valid_mask(wo + 12); }
-    };
-    // Conservative test "some byte of the 16 may be >= z_min" (never misses one; false positives only next to a byte >= 188):
-    // z <= 128: byte + (128 - z) sets bit 7, or overflows the byte only when the byte itself has bit 7 set; z > 128: bit 7.
-    auto any_ge = [&](const uint4 v) -> bool {
-      if (hi) return ((v.x | v.y | v.z | v.w) & 0x80808080u) != 0;
-      const uint32_t a = (v.x + addc) | v.x, b = (v.y + addc) | v.y, c = (v.z + addc) | v.z, d = (v.w + addc) | v.w;
-      return ((a | b | c | d) & 0x80808080u) != 0;
-    };
-    auto emit = [&](uint32_t m, uint32_t w, int wo) {  // dense path only: scatter the flagged bytes of one word
-      int pos = atomicAdd(&s_n[warp], __popc(m));
-      while (m) {
-        const int b = (__ffs(m) - 1) >> 3;
-        m &= m - 1;
-        if (pos < K1_CAP) list[pos] = (((w >> (8 * b)) & 0xffu) << 16) | (uint32_t)(wo + b - a0);
-        pos++;
-      }
-    };
-    // ---- pass 1: branch-free scan.  The conservative test flags ~1 vector in 9 on radar data; the flagged vector ids are
-    // compacted (ballot order) into a per-warp queue so that pass 2 works on them with all 32 lanes busy instead of every
-    // lane dragging the whole warp through its own rare hits.  The queue lives in `sel` (free until the ranking step).
-    uint16_t* queue = reinterpret_cast<uint16_t*>(sel);  // K1_CAP + 1 entries are enough: more flagged vectors than that => dense row
-    int nq = 0;
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 2
-    // whole groups of 32 vectors: the padding is zero, so the loop body has no guard.  z_min = 0 makes every byte a candidate (more
-    // than the list holds in any real row): that case goes straight to the dense path, which masks the padding explicitly.
-    const int nvec32 = zero_thr ? 0 : ((nvec + 31) & ~31);
-    if (zero_thr) nq = K1_CAP + 1;
-    for (int base = 0; base < nvec32; base += 32) {
-      const int t = base + lane;
-      const bool f = any_ge(vbuf[t]);
-      const unsigned ball = __ballot_sync(FULL, f);
-      const int q = nq + __popc(ball & lt);
-      if (f && q <= K1_CAP) queue[q] = (uint16_t)t;
-      nq += __popc(ball);
-    }
-    __syncwarp();
-    // ---- pass 2 (sparse row, the normal case): exact masks of the queued vectors, one vector per lane per round; positions from
-    // a warp scan of the per-vector counts.  The list order is arbitrary (the ranking step orders it) but deterministic.
-    int n = 0;
-    bool dense = nq > K1_CAP;
-    for (int qb = 0; qb < nq && !dense; qb += 32) {
-      int c = 0, wo = 0;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      uint32_t m[4] = {0, 0, 0, 0};
-      if (qb + lane < nq) {
-        const int t = queue[qb + lane];
-        wo = t << 4;
-        v = vbuf[t];
-        masks(v, wo, addc, hi, m);
-        c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-      }
-      int incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t2 = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t2;
-      }
-      const int round_total = __shfl_sync(FULL, incl, 31);
-      if (n + round_total > K1_CAP) { dense = true; break; }
-      int pos = n + incl - c;
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint32_t mm = m[q];
-        while (mm) {
-          const int b = (__ffs(mm) - 1) >> 3;
-          mm &= mm - 1;
-          list[pos++] = (((w[q] >> (8 * b)) & 0xffu) << 16) | (uint32_t)(wo + 4 * q + b - a0);
-        }
-      }
-      n += round_total;
-    }
-    if (!dense) {
-      __syncwarp();
-    } else {
-      // ---- dense row: exact threshold + tie handling ----------------------------------------------------
-      if (lane == 0) s_n[warp] = 0;
-      __syncwarp();
-      auto count_ge = [&](uint32_t t) -> int {
-        const bool h = t > 128;
-        const uint32_t ac = (h ? (256u - t) : (128u - t)) * 0x01010101u;
-        int c = 0;
-        for (int q = lane; q < nvec; q += 32) {
-          uint32_t m[4];
-          masks(vbuf[q], q << 4, ac, h, m);
-          c += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-        }
-        return __reduce_add_sync(FULL, c);
-      };
-      uint32_t lo = z, hi_t = 256;  // count(>= lo) >= k, count(>= hi_t) < k
-      while (hi_t - lo > 1) {
-        const uint32_t mid = (lo + hi_t) >> 1;
-        if (count_ge(mid) >= k) lo = mid; else hi_t = mid;
-      }
-      const uint32_t T = lo;
-      const int n_gt = (T >= 255) ? 0 : count_ge(T + 1);
-      const int need = k - n_gt;  // >= 1 ties to take, largest ranges first
-      if (T < 255) {  // (1) everything strictly above the threshold
-        const uint32_t t1 = T + 1;
-        const bool h = t1 > 128;
-        const uint32_t ac = (h ? (256u - t1) : (128u - t1)) * 0x01010101u;
-        for (int q = lane; q < nvec; q += 32) {
-          const uint4 v = vbuf[q];
-          const int wo = q << 4;
-          uint32_t m[4];
-          masks(v, wo, ac, h, m);
-          if (m[0]) emit(m[0], v.x, wo);
-          if (m[1]) emit(m[1], v.y, wo + 4);
-          if (m[2]) emit(m[2], v.z, wo + 8);
-          if (m[3]) emit(m[3], v.w, wo + 12);
-        }
-      }
-      // (2) ties at T, scanning ranges from the far end; 32 vectors (512 bytes) per step
-      const uint32_t T4 = T * 0x01010101u;
-      int carry = 0;
-      for (int base = ((nvec - 1) >> 5) << 5; base >= 0 && carry < need; base -= 32) {
-        const int q = base + lane;
-        uint32_t m[4] = {0, 0, 0, 0};
-        if (q < nvec) {
-          const uint4 v = vbuf[q];
-          const int wo = q << 4;
-          m[0] = eq_mask(v.x, T4) & valid_mask(wo); m[1] = eq_mask(v.y, T4) & valid_mask(wo + 4);
-          m[2] = eq_mask(v.z, T4) & valid_mask(wo + 8); m[3] = eq_mask(v.w, T4) & valid_mask(wo + 12);
-        }
-        const int c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-        int suf = c;  // inclusive suffix sum over lanes (higher lane = larger range)
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v2 = __shfl_down_sync(FULL, suf, d);
-          if (lane + d < 32) suf += v2;
-        }
-        const int after = carry + suf - c;
-        int take = need - after;
-        if (take > c) take = c;
-        if (take > 0) {
-          int pos = atomicAdd(&s_n[warp], take);
-          const int wo = q << 4;
-          for (int b = 15; b >= 0 && take > 0; b--) {  // highest bytes first
-            if (m[b >> 2] & (0x80u << (8 * (b & 3)))) {
-              if (pos < K1_CAP) list[pos] = (T << 16) | (uint32_t)(wo + b - a0);
-              pos++;
-              take--;
-            }
-          }
-        }
-        carry += __shfl_sync(FULL, suf, 0);
-      }
-      __syncwarp();
-      n = min(s_n[warp], K1_CAP);  // == k
-    }
-    const int n_sel = n < k ? n : k;
-    // pad to a multiple of 4 with zeros (never greater than a key)
-    if (lane < 4 && n + lane < K1_CAP) list[n + lane] = 0;
-    __syncwarp();
-    // ---- all-pairs rank: rank = number of strictly larger keys; selected iff rank < k -----------------------
-    for (int e = lane; e < n; e += 32) {
-      const uint32_t key = list[e];
-      int rank = 0;
-      for (int q = 0; q < n; q += 4) {
-        const uint4 v = *reinterpret_cast<const uint4*>(list + q);
-        rank += (v.x > key) + (v.y > key) + (v.z > key) + (v.w > key);
-      }
-      if (rank < k) sel[n_sel - 1 - rank] = key;
-    }
-    __syncwarp();
-    // ---- axial non-max suppression on the selected bins ---------------------------------------------------
-    if (want_peaks) {
-      uint32_t peak_bits = 0;  // bit t: entry lane + 32*t is a peak
-      for (int e = lane; e < n_sel; e += 32) {
-        const uint32_t key = sel[e];
-        const int r = (int)(key & 0xffffu);
-        const bool in_band = (r >= 3) && (r < n_range - 3);
-        int B[13];
-        if (r >= 6 && r + 6 < n_range) {
-#pragma unroll
-          for (int t = 0; t < 13; t++) B[t] = buf[a0 + r - 6 + t];
-        } else {
-          const long long gbase = (long long)az * (long long)row_stride;
-#pragma unroll
-          for (int t = 0; t < 13; t++) {
-            const int q = r - 6 + t;
-            if (q >= 0 && q < n_range) B[t] = buf[a0 + q];
-            else {
-              const long long fi = gbase + q;  // flat index into the scan buffer, as cv::Mat::at(bearing, r_nn) addresses it
-              B[t] = (fi >= 0 && fi < (long long)scan_bytes) ? (int)__ldg(scan_base + fi) : 0;
-            }
-          }
-        }
-        int s[7];  // s[i] = score at r - 3 + i = sum of the 7 bytes centred there (sliding window)
-        s[0] = B[0] + B[1] + B[2] + B[3] + B[4] + B[5] + B[6];
-#pragma unroll
-        for (int i = 1; i < 7; i++) s[i] = s[i - 1] - B[i - 1] + B[i + 6];
-        if (!in_band) {
-          // a score exists only where some selected in-band bin lies within 3 of the position
-#pragma unroll
-          for (int i = 0; i < 7; i++) {
-            const int p = r - 3 + i;
-            bool computed = false;
-            for (int q = 0; q < n_sel; q++) {
-              const int r2 = (int)(sel[q] & 0xffffu);
-              if (r2 >= 3 && r2 < n_range - 3 && r2 - p <= 3 && p - r2 <= 3) { computed = true; break; }
-            }
-            if (!computed) s[i] = 0;
-          }
-        }
-        bool largest = true;
-#pragma unroll
-        for (int i = 1; i <= 3; i++)
-          if (s[3 - i] > s[3] || s[3] < s[3 + i]) largest = false;
-        if (largest) peak_bits |= 1u << (e >> 5);
-      }
-      __syncwarp();
-      for (int e = lane; e < n_sel; e += 32)
-        if (peak_bits & (1u << (e >> 5))) sel[e] |= 0x80000000u;
-      __syncwarp();
-    }
-    // ---- write the row ------------------------------------------------------------------------------------------
-    uint32_t* out = row_keys + (size_t)row * k;
-    int nf = 0, np = 0;  // entries K2 will emit: range beyond min_range_bin (radar_filters.cpp:321), and the peaks among them
-    for (int e = lane; e < ((n_sel + 31) & ~31); e += 32) {
-      const uint32_t key = e < n_sel ? sel[e] : 0u;
-      if (e < n_sel) out[e] = key;
-      const bool ok = e < n_sel && (int)(key & 0xffffu) > min_range_bin;
-      nf += __popc(__ballot_sync(FULL, ok));
-      np += __popc(__ballot_sync(FULL, ok && (key >> 31)));
-    }
-    if (lane == 0) row_cnt[row] = (uint32_t)n_sel | ((uint32_t)nf << 8) | ((uint32_t)np << 16);
-    __syncwarp();  // every lane is done with buf / list / sel before the next iteration reuses them
-    cur ^= 1;
-    in_flight = next_in_flight;
-    scan = scan_n; az = az_n;
-  }
-}
-
 // Compensate one point (utils.cpp:96-113, utils.h:28-32): (x, y) are the stored float coordinates; m = previous frame-to-frame
 // motion (x, y, yaw).  Same operations, in the same order, as the reference's double arithmetic.
 __device__ __forceinline__ void compensate_point(float& x, float& y, double m0, double m1, double m2, int ccw) {
@@ -431,106 +100,422 @@ __device__ __forceinline__ void compensate_point(float& x, float& y, double m0, 
   y = (float)__dadd_rn(__dadd_rn(__dmul_rn(s1, px), __dmul_rn(c1, py)), ty);
 }
 
-// K2: rows -> ordered clouds.  K2_SPLIT CTAs per scan: each scans the scan's per-row counts (written by K1: selected, emitted,
-// emitted peaks — one packed word per row) into output offsets and emits its own slice of rows.  mot != nullptr: the points
-// are motion-compensated as they are emitted (odometrykeyframefuser.cpp:146-150 applies Compensate to both clouds right after
-// the filter; a peak is the same point in both clouds, so it is compensated once).
-constexpr int K2_SPLIT = 4;
-constexpr int K2_STAGE = 4096;  // staged points per chunk of rows (k <= 128 <= K2_STAGE)
-__global__ void __launch_bounds__(256)
-k2_make_clouds(const uint32_t* __restrict__ row_keys, const uint32_t* __restrict__ row_cnt, int n_az, int k, int min_range_bin,
-               double range_res, const double2* __restrict__ cs_table, int cap,
-               float* __restrict__ fx, float* __restrict__ fy, uint8_t* __restrict__ fi, uint16_t* __restrict__ faz, uint16_t* __restrict__ frg,
-               int* __restrict__ fcount, int want_peaks,
-               float* __restrict__ px, float* __restrict__ py, uint8_t* __restrict__ pi, uint16_t* __restrict__ paz, uint16_t* __restrict__ prg,
-               int* __restrict__ pcount, const double* __restrict__ mot, int ccw) {
-  extern __shared__ int s_off[];  // [2][n_az + 1]
-  int* off_f = s_off;
-  int* off_p = s_off + (n_az + 1);
-  const int scan = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+// ---- the fused filter kernel ----------------------------------------------------------------------------------------------------------
+// One CTA (8 warps) per scan walks the scan's rows in chunks of 8 (one row per warp) and writes the two final clouds directly:
+//   P1 (warp per row)      the row arrives by ONE bulk copy (TMA, mbarrier) in the warp's row buffer; branch-free conservative scan of the
+//                          16-byte vectors (flags kept as a bit per lane and vector), flagged vector ids queued, exact byte masks of the queued
+//                          vectors, candidates (key << 2 | emitted << 1) appended to the row's list.  Rows with more candidates than the list
+//                          holds take the exact dense path (threshold bisection on the staged row + ties from the far end) and end with <= k.
+//   P2 (half-warp per row) all-pairs rank inside the row's list -> the k strongest in ascending (intensity, range) order; 7+7-tap axial
+//                          non-max suppression of the selected bins on the staged row; per-entry output offsets by ballot prefix.
+//   P3 (one thread per point, all 256 threads) the emitted entries of the 8 rows, staged in output order: fp64 polar -> Cartesian with the
+//                          host (glibc) cos/sin table, motion compensation, coalesced stores to both clouds at the scan's running offsets.
+// The next chunk's rows are requested as soon as P2 has read the current ones, so the copies fly under P3's fp64 work and under the other
+// resident CTAs (4 per SM).  Nothing but the scan bytes is read from HBM and nothing but the clouds is written: the per-row key arrays of
+// the two-kernel version (and their round trip through L2) are gone.
+constexpr int KF_WARPS = 8;                  // warps per CTA = rows per chunk
+constexpr int KF_THREADS = KF_WARPS * 32;
+constexpr int KF_CAP = 128;                  // per-row candidate list capacity = largest supported k
+
+// list entry: bits 2..25 = intensity << 16 | range (the reference's std::pair<uchar,int> order), bit 1 = emitted (range > min_range_bin),
+// bit 0 = peak (set in P2).  Distinct entries of a row have distinct keys, so comparing entries compares keys.
+__device__ __forceinline__ uint32_t kf_entry(uint32_t inten, int r, int min_range_bin) {
+  return (((inten << 16) | (uint32_t)r) << 2) | (r > min_range_bin ? 2u : 0u);
+}
+
+// HI: z_min > 128 (selects the form of the conservative byte compare at compile time: the scan loop carries no branch on it);
+// NG: number of 32-vector groups of a staged row, unrolled at compile time (8: Oxford, 7: MulRan); 0 = run-time loop over n_groups.
+template <bool HI, int NG>
+__global__ void __launch_bounds__(KF_THREADS, 4)
+k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t row_stride, int z_min, int k, int want_peaks, int rowbuf, int n_groups,
+                const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, double range_res, const double2* __restrict__ cs_table, int cap,
+                float* __restrict__ fx, float* __restrict__ fy, uint8_t* __restrict__ fi, uint16_t* __restrict__ faz, uint16_t* __restrict__ frg,
+                int* __restrict__ fcount,
+                float* __restrict__ px, float* __restrict__ py, uint8_t* __restrict__ pi, uint16_t* __restrict__ paz, uint16_t* __restrict__ prg,
+                int* __restrict__ pcount, const double* __restrict__ mot, int ccw) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];               // [KF_WARPS][rowbuf] staged rows
+  __shared__ __align__(16) uint32_t s_list[KF_WARPS][KF_CAP + 4];  // candidates of the row (unordered), zero-padded to a multiple of 4
+  __shared__ __align__(16) uint32_t s_sel[KF_WARPS][KF_CAP];       // P1: queue of flagged vectors (u16); P2: selected entries, ascending
+  __shared__ uint32_t s_idx[KF_WARPS][KF_CAP];                     // P2: per selected entry (index among emitted) | (index among peaks) << 16
+  __shared__ uint32_t s_stkey[KF_WARPS * KF_CAP];                  // P3 staging, output order: entry
+  __shared__ int16_t s_stpp[KF_WARPS * KF_CAP];                    //   position among the chunk's peaks, or -1
+  __shared__ uint8_t s_strow[KF_WARPS * KF_CAP];                   //   row within the chunk
+  __shared__ __align__(8) uint64_t s_bar[KF_WARPS];
+  __shared__ int s_n[KF_WARPS], s_cntf[KF_WARPS], s_cntp[KF_WARPS], s_dn[KF_WARPS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned FULL = 0xffffffffu;
-  const uint32_t* keys = row_keys + (size_t)scan * n_az * k;
-  const uint32_t* cnts = row_cnt + (size_t)scan * n_az;
-  // phase 1: exclusive scans of the per-row emitted counts (warp 0: filtered, warp 1: peaks)
-  if (warp < 2) {
-    int* o = warp == 0 ? off_f : off_p;
-    const int shift = warp == 0 ? 8 : 16;
-    int running = 0;
-    for (int base = 0; base < n_az; base += 32) {
-      const int v = (base + lane < n_az) ? (int)((cnts[base + lane] >> shift) & 0xffu) : 0;
-      int inc = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += t;
-      }
-      if (base + lane < n_az) o[base + lane] = running + inc - v;
-      running += __shfl_sync(FULL, inc, 31);
-    }
-    if (lane == 0 && blockIdx.x == 0) {
-      if (warp == 0) fcount[scan] = running; else if (want_peaks) pcount[scan] = running;
-    }
-  }
-  __syncthreads();
-  // phase 2: the points of this CTA's rows.  A row keeps only ~12 of its k entries on radar data, so computing the points warp-per-row
-  // would leave most lanes idle through the fp64 atan2 / sincos of the compensation.  Instead the rows are first compacted (cheap,
-  // warp per row) into a staging list in shared memory, in output order; then one thread per staged point does the arithmetic and
-  // the stores are coalesced.  Rows are taken in chunks whose k * rows fit the staging list.
-  uint32_t* st_key = reinterpret_cast<uint32_t*>(s_off + 2 * (n_az + 1));   // [K2_STAGE] packed key
-  int* st_pq = reinterpret_cast<int*>(st_key + K2_STAGE);                   // [K2_STAGE] position in the peaks cloud, or -1
-  uint16_t* st_row = reinterpret_cast<uint16_t*>(st_pq + K2_STAGE);         // [K2_STAGE] azimuth
-  const double range_res_half = range_res / 2.0;
-  const size_t cbase = (size_t)scan * cap;
+  const int scan = blockIdx.x;
+  const uint32_t z = (uint32_t)z_min;
+  const bool zero_thr = z == 0;   // every byte is a candidate: no sparse pass
+  const uint32_t addc = (HI ? (256u - z) : (128u - z)) * 0x01010101u;
+  const size_t scan_bytes = (size_t)(n_az - 1) * row_stride + (size_t)n_range;  // addressable bytes of one scan
+  const uint8_t* scan_base = polar + (size_t)scan * (size_t)n_az * row_stride;
+  uint8_t* buf = s_dyn + (size_t)warp * rowbuf;
+  const uint4* vbuf = reinterpret_cast<const uint4*>(buf);
+  uint32_t* list = s_list[warp];
+  uint64_t* bar = &s_bar[warp];
+  if (lane == 0) mbar_init(bar, 1);
+  // The row buffer starts out zero: the scan loop runs over whole groups of 32 vectors, and the vectors past a row's staged superset are
+  // never written by a bulk copy (the one right behind it is re-zeroed per row, see below).
+  for (int o = lane * 16; o < rowbuf; o += 32 * 16) *reinterpret_cast<uint4*>(buf + o) = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncwarp();
+  uint32_t parity = 0;
+  bool in_flight = false;
+  if (warp < n_az) in_flight = stage_row_tma(buf, scan_base + (size_t)warp * row_stride, n_range, buf_lo, buf_hi, bar, lane);
   double m0 = 0.0, m1 = 0.0, m2 = 0.0;
   if (mot) { m0 = mot[scan * 3 + 0]; m1 = mot[scan * 3 + 1]; m2 = mot[scan * 3 + 2]; }
-  const int rows_per = (n_az + gridDim.x - 1) / gridDim.x;
-  const int row_begin = min(n_az, (int)blockIdx.x * rows_per), row_end = min(n_az, row_begin + rows_per);
-  const int chunk_rows = max(1, K2_STAGE / max(k, 1));
-  for (int r0 = row_begin; r0 < row_end; r0 += chunk_rows) {
-    const int r1 = min(row_end, r0 + chunk_rows);
-    const int base_f = off_f[r0];
-    for (int row = r0 + warp; row < r1; row += nwarps) {
-      const int c = (int)(cnts[row] & 0xffu);
-      int of = off_f[row] - base_f, op = off_p[row];
-      for (int e = lane; e < ((c + 31) & ~31); e += 32) {
-        const uint32_t key = e < c ? keys[(size_t)row * k + e] : 0u;
-        const bool ok = e < c && (int)(key & 0xffffu) > min_range_bin;
-        const bool pk = ok && (key >> 31);
-        const unsigned bf = __ballot_sync(FULL, ok), bp = __ballot_sync(FULL, pk);
-        const unsigned lt = (1u << lane) - 1u;
-        if (ok) {
-          const int q = of + __popc(bf & lt);
-          st_key[q] = key;
-          st_row[q] = (uint16_t)row;
-          st_pq[q] = (pk && want_peaks) ? op + __popc(bp & lt) : -1;
+  const double range_res_half = range_res / 2.0;
+  const size_t cbase = (size_t)scan * cap;
+  int base_f = 0, base_p = 0;   // running output offsets of the scan (every thread keeps its own copy)
+
+  for (int row0 = 0; row0 < n_az; row0 += KF_WARPS) {
+    // =============================== P1: warp per row ===============================================================================
+    const int row = row0 + warp;
+    int n = 0;
+    int a0 = 0;
+    if (row < n_az) {
+      const uint8_t* rp = scan_base + (size_t)row * row_stride;
+      a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
+      if (in_flight) { mbar_wait(bar, parity); parity ^= 1u; }
+      else stage_row_sync(buf, rp, n_range, lane);
+      const int lo_b = a0, hi_b = a0 + n_range;  // valid buffer byte range [lo_b, hi_b)
+      const int nvec = (hi_b + 15) >> 4;         // 16-byte vectors covering [0, hi_b)
+      // a previous row with another alignment may have ended one vector later: that vector must not be seen by the guard-free scan
+      if (lane == 0 && (nvec << 4) < rowbuf) *reinterpret_cast<uint4*>(buf + (nvec << 4)) = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      auto valid_mask = [&](int wo) -> uint32_t {   // word at buffer offset wo: 0x80 per byte that belongs to the row
+        uint32_t m = 0x80808080u;
+        if (wo < lo_b) m &= (lo_b - wo >= 4) ? 0u : (0x80808080u << (8 * (lo_b - wo)));
+        if (wo + 4 > hi_b) m &= (hi_b - wo <= 0) ? 0u : (0x80808080u >> (8 * (wo + 4 - hi_b)));
+        return m;
+      };
+      // exact "byte >= t" masks of one vector; the staged superset starts / ends up to 15 bytes outside the row: masked at both ends
+      auto masks = [&](const uint4 v, int wo, uint32_t ac, bool h, uint32_t m[4]) {
+        m[0] = ge_mask(v.x, ac, h); m[1] = ge_mask(v.y, ac, h); m[2] = ge_mask(v.z, ac, h); m[3] = ge_mask(v.w, ac, h);
+        if (wo < lo_b || wo + 16 > hi_b) { m[0] &= valid_mask(wo); m[1] &= valid_mask(wo + 4); m[2] &= valid_mask(wo + 8); m[3] &= valid_mask(wo + 12); }
+      };
+      // Conservative test "some byte of the 16 may be >= z_min" (never misses one; false positives only next to a byte >= 188):
+      // z <= 128: byte + (128 - z) sets bit 7, or overflows the byte only when the byte itself has bit 7 set; z > 128: bit 7.
+      auto any_ge = [&](const uint4 v) -> bool {
+        if (HI) return ((v.x | v.y | v.z | v.w) & 0x80808080u) != 0;
+        const uint32_t a = (v.x + addc) | v.x, b = (v.y + addc) | v.y, c = (v.z + addc) | v.z, d = (v.w + addc) | v.w;
+        return ((a | b | c | d) & 0x80808080u) != 0;
+      };
+      // ---- scan: one flag bit per (lane, group); no ballots, no stores in the loop -----------------------------------------------------
+      bool dense = zero_thr;
+      uint16_t* queue = reinterpret_cast<uint16_t*>(s_sel[warp]);   // <= KF_CAP flagged vector ids
+      int nq = 0;
+      if (!dense) {
+        uint32_t bits = 0;
+        if (NG > 0) {
+#pragma unroll
+          for (int j = 0; j < NG; j++)
+            if (any_ge(vbuf[j * 32 + lane])) bits |= 1u << j;
+        } else {
+#pragma unroll 4
+          for (int j = 0; j < n_groups; j++) bits |= (any_ge(vbuf[j * 32 + lane]) ? 1u : 0u) << j;
         }
-        of += __popc(bf);
-        op += __popc(bp);
+        const int mine = __popc(bits);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t2 = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += t2;
+        }
+        nq = __shfl_sync(FULL, incl, 31);
+        if (nq > KF_CAP) dense = true;
+        else {
+          int q = incl - mine;
+          while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1;
+            queue[q++] = (uint16_t)(j * 32 + lane);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- exact masks of the queued vectors, one vector per lane per round; list positions from a warp scan of the per-vector counts ----
+      for (int qb = 0; qb < nq && !dense; qb += 32) {
+        int c = 0, wo = 0;
+        uint32_t m16 = 0;   // bit b: byte b of the vector is a candidate
+        if (qb + lane < nq) {
+          const int t = queue[qb + lane];
+          wo = t << 4;
+          uint32_t m[4];
+          masks(vbuf[t], wo, addc, HI, m);
+          // movemask of 4 bytes: bits 7, 15, 23, 31 -> bits 0..3 (multiply gathers them at bits 21..24; no carries, all partial products distinct)
+          m16 = (((m[0] >> 7) * 0x00204081u) >> 21 & 0xfu) | (((m[1] >> 7) * 0x00204081u) >> 17 & 0xf0u) |
+                (((m[2] >> 7) * 0x00204081u) >> 13 & 0xf00u) | (((m[3] >> 7) * 0x00204081u) >> 9 & 0xf000u);
+          c = __popc(m16);
+        }
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t2 = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += t2;
+        }
+        const int round_total = __shfl_sync(FULL, incl, 31);
+        if (n + round_total > KF_CAP) { dense = true; break; }
+        int pos = n + incl - c;
+        while (m16) {
+          const int b = __ffs(m16) - 1;
+          m16 &= m16 - 1;
+          list[pos++] = kf_entry(buf[wo + b], wo + b - a0, min_range_bin);
+        }
+        n += round_total;
+      }
+      if (dense) {
+        // ---- dense row: exact threshold T = k-th largest intensity (bisection over the staged row), everything above T, then the ties at
+        // T from the far end — the largest ranges win, exactly as the reference's erase(begin()) leaves them --------------------------------
+        if (lane == 0) s_dn[warp] = 0;
+        __syncwarp();
+        auto count_ge = [&](uint32_t t) -> int {   // bytes of the row >= t (t in 1..255; t == 0 never asked)
+          const bool h = t > 128;
+          const uint32_t ac = (h ? (256u - t) : (128u - t)) * 0x01010101u;
+          uint32_t c = 0;   // 128 x the count: dp4a sums the four flag bytes (0x80 each) of a word in one instruction
+          for (int q = lane; q < nvec; q += 32) {
+            uint32_t m[4];
+            masks(vbuf[q], q << 4, ac, h, m);
+            c = __dp4a(m[0], 0x01010101u, c); c = __dp4a(m[1], 0x01010101u, c);
+            c = __dp4a(m[2], 0x01010101u, c); c = __dp4a(m[3], 0x01010101u, c);
+          }
+          return (int)(__reduce_add_sync(FULL, c) >> 7);
+        };
+        // T = the k-th largest intensity among the candidates (or z_min when the row holds no more than k candidates: all are taken)
+        auto cnt = [&](uint32_t t) -> int { return t == 0 ? n_range : count_ge(t); };
+        uint32_t T = z;
+        int n_ge = cnt(z), n_gt = -1;
+        if (n_ge > k) {
+          uint32_t lo = z, hi_t = 256;   // count(>= lo) >= k, count(>= hi_t) < k
+          int c_hi = 0;
+          while (hi_t - lo > 1) {
+            const uint32_t mid = (lo + hi_t) >> 1;
+            const int c = count_ge(mid);
+            if (c >= k) { lo = mid; n_ge = c; } else { hi_t = mid; c_hi = c; }
+          }
+          T = lo;
+          n_gt = c_hi;                   // hi_t == T + 1 (0 entries above 255)
+        }
+        if (n_gt < 0) n_gt = (T >= 255) ? 0 : count_ge(T + 1);
+        const int want = n_ge < k ? n_ge : k;
+        const int need = want - n_gt;   // ties to take at T, largest ranges first (>= 0)
+        if (T < 255 && n_gt > 0) {      // (1) everything strictly above the threshold
+          const uint32_t t1 = T + 1;
+          const bool h = t1 > 128;
+          const uint32_t ac = (h ? (256u - t1) : (128u - t1)) * 0x01010101u;
+          for (int q = lane; q < nvec; q += 32) {
+            const int wo = q << 4;
+            uint32_t m[4];
+            masks(vbuf[q], wo, ac, h, m);
+            uint32_t m16 = (((m[0] >> 7) * 0x00204081u) >> 21 & 0xfu) | (((m[1] >> 7) * 0x00204081u) >> 17 & 0xf0u) |
+                           (((m[2] >> 7) * 0x00204081u) >> 13 & 0xf00u) | (((m[3] >> 7) * 0x00204081u) >> 9 & 0xf000u);
+            if (m16) {
+              int pos = atomicAdd(&s_dn[warp], __popc(m16));
+              while (m16) {
+                const int b = __ffs(m16) - 1;
+                m16 &= m16 - 1;
+                if (pos < KF_CAP) list[pos] = kf_entry(buf[wo + b], wo + b - a0, min_range_bin);
+                pos++;
+              }
+            }
+          }
+        }
+        // (2) ties at T, scanning ranges from the far end; 32 vectors (512 bytes) per step
+        const uint32_t T4 = T * 0x01010101u;
+        int carry = 0;
+        for (int base = ((nvec - 1) >> 5) << 5; base >= 0 && carry < need; base -= 32) {
+          const int q = base + lane;
+          uint32_t m16 = 0;
+          if (q < nvec) {
+            const uint4 v = vbuf[q];
+            const int wo = q << 4;
+            const uint32_t e0 = eq_mask(v.x, T4) & valid_mask(wo), e1 = eq_mask(v.y, T4) & valid_mask(wo + 4);
+            const uint32_t e2 = eq_mask(v.z, T4) & valid_mask(wo + 8), e3 = eq_mask(v.w, T4) & valid_mask(wo + 12);
+            m16 = (((e0 >> 7) * 0x00204081u) >> 21 & 0xfu) | (((e1 >> 7) * 0x00204081u) >> 17 & 0xf0u) |
+                  (((e2 >> 7) * 0x00204081u) >> 13 & 0xf00u) | (((e3 >> 7) * 0x00204081u) >> 9 & 0xf000u);
+          }
+          const int c = __popc(m16);
+          int suf = c;  // inclusive suffix sum over lanes (higher lane = larger range)
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v2 = __shfl_down_sync(FULL, suf, d);
+            if (lane + d < 32) suf += v2;
+          }
+          const int after = carry + suf - c;
+          int take = need - after;
+          if (take > c) take = c;
+          if (take > 0) {
+            int pos = atomicAdd(&s_dn[warp], take);
+            const int wo = q << 4;
+            while (take > 0) {  // highest bytes first
+              const int b = 31 - __clz(m16);
+              m16 &= ~(1u << b);
+              if (pos < KF_CAP) list[pos] = kf_entry(T, wo + b - a0, min_range_bin);
+              pos++;
+              take--;
+            }
+          }
+          carry += __shfl_sync(FULL, suf, 0);
+        }
+        __syncwarp();
+        n = min(s_dn[warp], KF_CAP);   // == want
+      }
+      __syncwarp();
+      if (lane < 4) list[n + lane] = 0;   // pad to a multiple of 4 with zeros (never greater than an entry)
+    }
+    if (lane == 0) s_n[warp] = n;
+    __syncthreads();   // ---- (1) lists complete ---------------------------------------------------------------------------------------
+
+    // =============================== P2: half-warp per row ==========================================================================
+    if (tid < KF_WARPS * 16) {
+      const int r8 = tid >> 4, hl = tid & 15;
+      const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
+      const int nr = s_n[r8];
+      const int n_sel = nr < k ? nr : k;
+      const uint32_t* lst = s_list[r8];
+      uint32_t* sel = s_sel[r8];
+      // all-pairs rank: rank = number of strictly larger entries; selected iff rank < k; position n_sel - 1 - rank (ascending order)
+      for (int e = hl; e < nr; e += 16) {
+        const uint32_t mine = lst[e];
+        int rank = 0;
+        for (int q = 0; q < nr; q += 4) {
+          const uint4 v = *reinterpret_cast<const uint4*>(lst + q);
+          rank += (v.x > mine) + (v.y > mine) + (v.z > mine) + (v.w > mine);
+        }
+        if (rank < k) sel[n_sel - 1 - rank] = mine;
+      }
+      __syncwarp(hmask);
+      // axial non-max suppression of the emitted selected bins (radar_filters.cpp:238-298) on the staged row of warp r8
+      if (want_peaks) {
+        const int rowp = row0 + r8;
+        const uint8_t* rb = s_dyn + (size_t)r8 * rowbuf;
+        const int ra0 = (int)(reinterpret_cast<uintptr_t>(scan_base + (size_t)rowp * row_stride) & 15u);
+        for (int e = hl; e < n_sel; e += 16) {
+          const uint32_t ent = sel[e];
+          if (!(ent & 2u)) continue;   // not emitted: its peak flag is never read
+          const int r = (int)((ent >> 2) & 0xffffu);
+          const bool in_band = (r >= 3) && (r < n_range - 3);
+          int B[13];
+          if (r >= 6 && r + 6 < n_range) {
+#pragma unroll
+            for (int t = 0; t < 13; t++) B[t] = rb[ra0 + r - 6 + t];
+          } else {
+            const long long gbase = (long long)rowp * (long long)row_stride;
+#pragma unroll
+            for (int t = 0; t < 13; t++) {
+              const int q = r - 6 + t;
+              if (q >= 0 && q < n_range) B[t] = rb[ra0 + q];
+              else {
+                const long long fidx = gbase + q;  // flat index into the scan buffer, as cv::Mat::at(bearing, r_nn) addresses it
+                B[t] = (fidx >= 0 && fidx < (long long)scan_bytes) ? (int)__ldg(scan_base + fidx) : 0;
+              }
+            }
+          }
+          int s[7];  // s[i] = score at r - 3 + i = sum of the 7 bytes centred there (sliding window)
+          s[0] = B[0] + B[1] + B[2] + B[3] + B[4] + B[5] + B[6];
+#pragma unroll
+          for (int i = 1; i < 7; i++) s[i] = s[i - 1] - B[i - 1] + B[i + 6];
+          if (!in_band) {
+            // a score exists only where some selected in-band bin lies within 3 of the position
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+              const int p = r - 3 + i;
+              bool computed = false;
+              for (int q = 0; q < n_sel; q++) {
+                const int r2 = (int)((sel[q] >> 2) & 0xffffu);
+                if (r2 >= 3 && r2 < n_range - 3 && r2 - p <= 3 && p - r2 <= 3) { computed = true; break; }
+              }
+              if (!computed) s[i] = 0;
+            }
+          }
+          bool largest = true;
+#pragma unroll
+          for (int i = 1; i <= 3; i++)
+            if (s[3 - i] > s[3] || s[3] < s[3 + i]) largest = false;
+          if (largest) sel[e] = ent | 1u;   // other lanes read only the range field of this entry
+        }
+      }
+      __syncwarp(hmask);
+      // output offsets inside the row: ballot prefix over the ascending entries (emitted, emitted peaks)
+      int run_f = 0, run_p = 0;
+      const unsigned lt = (1u << hl) - 1u;
+      for (int b0 = 0; b0 < n_sel; b0 += 16) {
+        const int e = b0 + hl;
+        const uint32_t ent = e < n_sel ? sel[e] : 0u;
+        const bool fe = (ent & 2u) != 0, fp = (ent & 3u) == 3u;
+        const unsigned bf = (__ballot_sync(hmask, fe) >> (16 * ((tid >> 4) & 1))) & 0xffffu;
+        const unsigned bp = (__ballot_sync(hmask, fp) >> (16 * ((tid >> 4) & 1))) & 0xffffu;
+        if (e < n_sel) s_idx[r8][e] = (uint32_t)(run_f + __popc(bf & lt)) | ((uint32_t)(run_p + __popc(bp & lt)) << 16);
+        run_f += __popc(bf);
+        run_p += __popc(bp);
+      }
+      if (hl == 0) { s_cntf[r8] = run_f; s_cntp[r8] = run_p; }
+    }
+    __syncthreads();   // ---- (2) rows consumed, per-row counts known ---------------------------------------------------------------------
+
+    // request the next chunk's rows: they fly under the staging and the fp64 work below
+    {
+      const int nrow = row0 + KF_WARPS + warp;
+      in_flight = false;
+      if (nrow < n_az) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads / writes of this buffer before the bulk copy into it
+        in_flight = stage_row_tma(buf, scan_base + (size_t)nrow * row_stride, n_range, buf_lo, buf_hi, bar, lane);
       }
     }
-    __syncthreads();
-    const int n_local = off_f[r1 - 1] + (int)((cnts[r1 - 1] >> 8) & 0xffu) - base_f;
-    for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
-      const uint32_t key = st_key[i];
-      const int row = st_row[i];
-      const int r = (int)(key & 0xffffu);
-      const double2 cs = cs_table[row];
+    int tot_f = 0, tot_p = 0;
+    if (tid < KF_WARPS * 16) {   // staging in output order (rows ascending, entries ascending inside a row)
+      const int r8 = tid >> 4, hl = tid & 15;
+      int off_f = 0, off_p = 0;
+#pragma unroll
+      for (int j = 0; j < KF_WARPS - 1; j++) { off_f += j < r8 ? s_cntf[j] : 0; off_p += j < r8 ? s_cntp[j] : 0; }
+      const int nr = s_n[r8];
+      const int n_sel = nr < k ? nr : k;
+      for (int e = hl; e < n_sel; e += 16) {
+        const uint32_t ent = s_sel[r8][e];
+        if (ent & 2u) {
+          const uint32_t ix = s_idx[r8][e];
+          const int q = off_f + (int)(ix & 0xffffu);
+          s_stkey[q] = ent;
+          s_strow[q] = (uint8_t)r8;
+          s_stpp[q] = (ent & 1u) ? (int16_t)(off_p + (int)(ix >> 16)) : (int16_t)-1;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KF_WARPS; j++) { tot_f += s_cntf[j]; tot_p += s_cntp[j]; }
+    __syncthreads();   // ---- (3) staging complete -----------------------------------------------------------------------------------------
+
+    // =============================== P3: one thread per emitted point =================================================================
+    for (int i = tid; i < tot_f; i += KF_THREADS) {
+      const uint32_t ent = s_stkey[i];
+      const int az = row0 + (int)s_strow[i];
+      const int r = (int)((ent >> 2) & 0xffffu);
+      const double2 cs = cs_table[az];
       const double rho = __dadd_rn(range_res_half, __dmul_rn(range_res, (double)r));  // radar_filters.cpp:329-330
       float x = (float)__dmul_rn(rho, cs.x);
       float y = (float)__dmul_rn(rho, cs.y);
       if (mot) compensate_point(x, y, m0, m1, m2, ccw);
-      const uint8_t inten = (uint8_t)((key >> 16) & 0xffu);
+      const uint8_t inten = (uint8_t)((ent >> 18) & 0xffu);
       const int q = base_f + i;
       if (q < cap) {
-        fx[cbase + q] = x; fy[cbase + q] = y; fi[cbase + q] = inten; faz[cbase + q] = (uint16_t)row; frg[cbase + q] = (uint16_t)r;
+        fx[cbase + q] = x; fy[cbase + q] = y; fi[cbase + q] = inten; faz[cbase + q] = (uint16_t)az; frg[cbase + q] = (uint16_t)r;
       }
-      const int qp = st_pq[i];
-      if (qp >= 0 && qp < cap) {
-        px[cbase + qp] = x; py[cbase + qp] = y; pi[cbase + qp] = inten; paz[cbase + qp] = (uint16_t)row; prg[cbase + qp] = (uint16_t)r;
+      const int pp = s_stpp[i];
+      if (pp >= 0 && base_p + pp < cap) {
+        const int qp = base_p + pp;
+        px[cbase + qp] = x; py[cbase + qp] = y; pi[cbase + qp] = inten; paz[cbase + qp] = (uint16_t)az; prg[cbase + qp] = (uint16_t)r;
       }
     }
-    __syncthreads();
+    base_f += tot_f;
+    base_p += tot_p;
+    // no barrier here: the next chunk's P1 touches only the row buffers / lists, and its barrier (1) orders P3's staging reads before the
+    // next staging writes
+  }
+  if (tid == 0) {
+    fcount[scan] = base_f < cap ? base_f : cap;
+    if (want_peaks) pcount[scan] = base_p < cap ? base_p : cap;
   }
 }
 
@@ -575,48 +560,38 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
   TBV_REQUIRE(n_range <= 8192, "n_range > 8192 is not supported");
   TBV_REQUIRE(n_az <= 4096, "n_az > 4096 is not supported");
-  TBV_REQUIRE(p->k_strongest >= 1 && p->k_strongest <= K1_CAP, "k_strongest must be in [1,128]");
+  TBV_REQUIRE(p->k_strongest >= 1 && p->k_strongest <= KF_CAP, "k_strongest must be in [1,128]");
   const int z_min = (int)p->z_min;  // float -> int as StructuredKStrongest's ctor does (radar_filters.h:86)
   TBV_REQUIRE(z_min >= 0 && z_min <= 255, "z_min must be in [0,255]");
   FilterState& F = ctx->filt;
   const int k = p->k_strongest;
   int rc;
-  if ((rc = F.row_keys.reserve((size_t)batch * n_az * k))) return rc;
-  if ((rc = F.row_cnt.reserve((size_t)batch * n_az))) return rc;
   if ((rc = F.filtered.reserve(batch, n_az * k))) return rc;
   if (want_peaks && (rc = F.peaks.reserve(batch, n_az * k))) return rc;
   if ((rc = ensure_cs_table(ctx, n_az))) return rc;
   F.batch = batch; F.n_az = n_az; F.n_range = n_range; F.k = k;
 
-  const int total_rows = batch * n_az;
-  const int dev_sms = ctx->sm_count;
-  const int blocks_needed = (total_rows + K1_WARPS - 1) / K1_WARPS;
-  const int rowbuf = ((n_range + 16 + 15 + 511) / 512) * 512;  // row + alignment slack, whole groups of 32 16-byte vectors
-  const size_t k1_smem = (size_t)K1_WARPS * 2 * rowbuf;
-  // resident CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA, ~8.3 KB static (lists, barriers)
-  int ctas_per_sm = (int)((228 * 1024) / (k1_smem + 8500 + 1024));
-  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
-  const int max_grid = dev_sms * ctas_per_sm;
-  const int grid = blocks_needed < max_grid ? blocks_needed : max_grid;  // persistent: resident CTAs only, rows strided over warps
-  if ((rc = ensure_dyn_smem(ctx, k1_kstrongest<false>, k1_smem)) || (rc = ensure_dyn_smem(ctx, k1_kstrongest<true>, k1_smem))) return rc;
+  // staged row: the 16-byte-aligned superset of a row (<= 15 bytes of slack at either end) + one spare vector, in whole groups of 32 vectors
+  const int nvec_max = (15 + n_range + 15) >> 4;
+  const int n_groups = (nvec_max + 1 + 31) / 32;
+  const int rowbuf = n_groups * 512;
+  const size_t k1_smem = (size_t)KF_WARPS * rowbuf;
   const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
   const int min_range_bin = (int)std::ceil((double)p->min_distance / rr);   // radar_filters.cpp:315
-  if (z_min > 128)
-    k1_kstrongest<true><<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
-                                                                     polar_dev, buf_hi, min_range_bin, F.row_keys.p, F.row_cnt.p);
-  else
-    k1_kstrongest<false><<<grid, K1_WARPS * 32, k1_smem, ctx->stream>>>(polar_dev, total_rows, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf,
-                                                                      polar_dev, buf_hi, min_range_bin, F.row_keys.p, F.row_cnt.p);
-  launched(ctx, "k1_kstrongest");
-  TBV_CUDA(cudaGetLastError());
-  const size_t smem = 2 * (size_t)(n_az + 1) * sizeof(int) + (size_t)K2_STAGE * (sizeof(uint32_t) + sizeof(int) + sizeof(uint16_t));
-  if ((rc = ensure_dyn_smem(ctx, k2_make_clouds, smem))) return rc;
-  k2_make_clouds<<<dim3(K2_SPLIT, batch), 256, smem, ctx->stream>>>(F.row_keys.p, F.row_cnt.p, n_az, k, min_range_bin, rr, F.cs_table.p, n_az * k,
-                                                                    F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, F.filtered.az.p,
-                                                                    F.filtered.rg.p, F.filtered.count.p, want_peaks, F.peaks.x.p, F.peaks.y.p,
-                                                                    F.peaks.inten.p, F.peaks.az.p, F.peaks.rg.p, F.peaks.count.p, mot_dev, ccw);
-  launched(ctx, "k2_make_clouds");
+  auto launch = [&](auto kern) -> int {
+    const int rc2 = ensure_dyn_smem(ctx, kern, k1_smem);
+    if (rc2) return rc2;
+    kern<<<batch, KF_THREADS, k1_smem, ctx->stream>>>(polar_dev, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf, n_groups, polar_dev, buf_hi,
+                                                     min_range_bin, rr, F.cs_table.p, n_az * k, F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p,
+                                                     F.filtered.az.p, F.filtered.rg.p, F.filtered.count.p, F.peaks.x.p, F.peaks.y.p, F.peaks.inten.p,
+                                                     F.peaks.az.p, F.peaks.rg.p, F.peaks.count.p, mot_dev, ccw);
+    return TBV_OK;
+  };
+  if (z_min > 128) rc = n_groups == 8 ? launch(k1_filter_fused<true, 8>) : n_groups == 7 ? launch(k1_filter_fused<true, 7>) : launch(k1_filter_fused<true, 0>);
+  else rc = n_groups == 8 ? launch(k1_filter_fused<false, 8>) : n_groups == 7 ? launch(k1_filter_fused<false, 7>) : launch(k1_filter_fused<false, 0>);
+  if (rc) return rc;
+  launched(ctx, "k1_filter_fused");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
 }

@@ -32,6 +32,8 @@ void prof_mark(tbv_ctx* ctx, const char* name) {
 // 32x32 shared-memory tile transpose so both the read and the write are coalesced.
 __global__ void k_rotate90ccw(const uint8_t* __restrict__ src, int H, int W, uint8_t* __restrict__ dst) {
   __shared__ uint8_t tile[32][33];
+  src += (size_t)blockIdx.z * H * W;   // blockIdx.z: image of a batch
+  dst += (size_t)blockIdx.z * H * W;
   const int j0 = blockIdx.y * 32, c0 = blockIdx.x * 32;  // src rows j, src cols c
   for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
     const int j = j0 + dy, c = c0 + threadIdx.x;
@@ -42,6 +44,16 @@ __global__ void k_rotate90ccw(const uint8_t* __restrict__ src, int H, int W, uin
     const int c = c0 + dy, j = j0 + threadIdx.x;  // dst row i = W-1-c, dst col j
     if (j < H && c < W) dst[(size_t)(W - 1 - c) * H + j] = tile[threadIdx.x][dy];
   }
+}
+int rotate90ccw_dev(tbv_ctx* ctx, const uint8_t* src_dev, int rows, int cols, int batch, uint8_t* dst_dev) {
+  for (int b0 = 0; b0 < batch; b0 += 65535) {   // gridDim.z limit
+    const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, nb), block(32, 8);
+    k_rotate90ccw<<<grid, block, 0, ctx->stream>>>(src_dev + (size_t)b0 * rows * cols, rows, cols, dst_dev + (size_t)b0 * rows * cols);
+    launched(ctx, "k_rotate90ccw");
+  }
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
 }
 }  // namespace tbv
 
@@ -92,7 +104,7 @@ void tbv_destroy(tbv_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   FilterState& F = ctx->filt;
-  F.polar.release(); F.row_keys.release(); F.row_cnt.release(); F.cs_table.release(); F.filtered.release(); F.peaks.release();
+  F.polar.release(); F.cs_table.release(); F.filtered.release(); F.peaks.release();
   cells_release(ctx);
   reg_release(ctx);
   comm_release(ctx);
@@ -163,10 +175,7 @@ int tbv_rotate90ccw(tbv_ctx* ctx, const uint8_t* src, int rows, int cols, uint8_
   if ((rc = a.reserve(n)) || (rc = b.reserve(n))) { a.release(); b.release(); return rc; }
   cudaError_t e = cudaMemcpyAsync(a.p, src, n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    k_rotate90ccw<<<grid, block, 0, ctx->stream>>>(a.p, rows, cols, b.p);
-    launched(ctx, "k_rotate90ccw");
-    e = cudaGetLastError();
+    e = rotate90ccw_dev(ctx, a.p, rows, cols, 1, b.p) == TBV_OK ? cudaSuccess : cudaErrorUnknown;
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(dst, b.p, n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -223,6 +223,8 @@ struct tbv_odom {
   cudaEvent_t uploaded[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
   tbv_odom_out* outs_host[2] = {nullptr, nullptr};  // pinned
   int n_submitted = 0, n_collected = 0;
+  int wire_range_major = 0;        // scans arrive [n_range][n_az] (MulRan wire layout) and are rotated on receipt (tbv_odom_set_wire_layout)
+  DevBuf<uint8_t> rotated;         // [n_seq][n_az][n_range] azimuth-major copies of the step's scans
 };
 
 static void odom_free(tbv_odom* od) {
@@ -231,6 +233,7 @@ static void odom_free(tbv_odom* od) {
   cudaStreamSynchronize(od->ctx->stream);
   if (od->copy_stream) cudaStreamSynchronize(od->copy_stream);
   od->state.release(); od->mot.release(); od->fixed_pose.release(); od->problems.release(); od->fixed_set.release();
+  od->rotated.release();
   od->results.release(); od->views.release(); od->fused_set.release(); od->kf_grids.release(); od->outs_dev.release(); od->cur.release(); od->kf.release();
   for (int i = 0; i < 2; i++) {
     od->polar[i].release();
@@ -278,6 +281,11 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   cudaStream_t st = ctx->stream;
   // previous frame-to-frame motion first: K2 compensates the points as it emits them (odometrykeyframefuser.cpp:146-150)
   int rc;
+  if (od->wire_range_major) {   // radar_driver.cpp:80-84: cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on receipt
+    if ((rc = od->rotated.reserve((size_t)n_seq * od->n_az * od->n_range))) return rc;
+    if ((rc = rotate90ccw_dev(ctx, polar_dev, od->n_range, od->n_az, n_seq, od->rotated.p))) return rc;
+    polar_dev = od->rotated.p;
+  }
   if (od->par.compensate) {
     k_odom_motion<<<(n_seq + 127) / 128, 128, 0, st>>>(od->state.p, n_seq, od->mot.p);
     launched(ctx, "k_odom_motion");
@@ -344,6 +352,12 @@ int tbv_odom_reset(tbv_odom* od) {
   launched(ctx, "k_odom_reset");
   TBV_CUDA(cudaGetLastError());
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TBV_OK;
+}
+
+int tbv_odom_set_wire_layout(tbv_odom* od, int range_major) {
+  TBV_REQUIRE(od, "null handle");
+  od->wire_range_major = range_major != 0;
   return TBV_OK;
 }
 

@@ -1139,7 +1139,7 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   dbg = S.dbg.p;
   TBV_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(unsigned long long), ctx->stream));
 #endif
-  if ((rc = ensure_dyn_smem(ctx, k_register<4>, RG_STAGE + 1))) return rc;   // + 1: opt in even at exactly 48 KB (the static part comes on top)
+  if ((rc = ensure_dyn_smem(ctx, k_register<4>, RG_STAGE))) return rc;
   k_register<4><<<n_problems, RG_THREADS, RG_STAGE, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
                                                                want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg, RG_STAGE);

@@ -104,8 +104,6 @@ struct DevCloud {
 struct FilterState {  // device-resident result of the last k-strongest call
   int batch = 0, n_az = 0, n_range = 0, k = 0;
   DevBuf<uint8_t> polar;       // staging for host-input calls
-  DevBuf<uint32_t> row_keys;   // [batch][n_az][k]  bit31 = peak, bits 16..23 intensity, bits 0..15 range
-  DevBuf<uint32_t> row_cnt;    // [batch][n_az]  bits 0..7 selected, 8..15 emitted (range > min_range_bin), 16..23 emitted peaks
   DevBuf<double2> cs_table;    // [n_az] (cos theta, sin theta) computed on the host with glibc
   int cs_n_az = 0;
   DevCloud filtered, peaks;
@@ -147,11 +145,11 @@ struct tbv_ctx {
   } while (0)
 
 namespace tbv {
-// Opt kernel `func` into `bytes` of dynamic shared memory on this context's device (a per-device attribute; sizes <= 48 KB need
-// nothing).  The record is kept per context, so a second context on another device gets its own opt-in.
+// Opt kernel `func` into `bytes` of dynamic shared memory on this context's device (a per-device attribute).  Always set on first use:
+// the 48 KB default covers static + dynamic together, so a kernel with static shared memory needs the opt-in below 48 KB of dynamic too.
+// The record is kept per context, so a second context on another device gets its own opt-in.
 template <typename F>
 inline int ensure_dyn_smem(tbv_ctx* ctx, F* func, size_t bytes) {
-  if (bytes <= 48 * 1024) return TBV_OK;
   const void* f = reinterpret_cast<const void*>(func);
   for (SmemOptIn& o : ctx->smem_optin)
     if (o.func == f) {
@@ -173,6 +171,8 @@ inline void launched(tbv_ctx* ctx, const char* name) {  // bookkeeping after eve
 // mot_dev != nullptr ([batch][3] previous frame-to-frame motion): both clouds are motion-compensated as they are emitted
 int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
                           const tbv_filter_params* params, int want_peaks, const double* mot_dev = nullptr, int ccw = 0);
+// batched cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on the device (k_misc.cu): src [batch][rows][cols] -> dst [batch][cols][rows]
+int rotate90ccw_dev(tbv_ctx* ctx, const uint8_t* src_dev, int rows, int cols, int batch, uint8_t* dst_dev);
 int compensate_clouds_dev(tbv_ctx* ctx, DevCloud& cloud, const double* mot_dev /*[batch][3]*/, int ccw);
 void cells_release(tbv_ctx* ctx);
 void reg_release(tbv_ctx* ctx);

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 # kernel -> the reference's timing key (radar_driver.cpp:87,111; odometrykeyframefuser.cpp:253-256; loopclosure.cpp:647-731; posegraph.cpp:126)
 STAGE_OF_KERNEL = {
-    "k1_kstrongest": "Filtering", "k2_make_clouds": "Filtering", "cfar_rows": "Filtering", "cfar_emit": "Filtering", "k_rotate90ccw": "Filtering",
+    "k1_filter_fused": "Filtering", "cfar_rows": "Filtering", "cfar_emit": "Filtering", "k_rotate90ccw": "Filtering",
     "k_compensate": "compensate",
     "cells_fused": "build_normals", "c1_grid": "build_normals", "c2_scan": "build_normals", "c3_scatter": "build_normals", "c4_centroids": "build_normals",
     "c5_cells": "build_normals", "c6_compact": "build_normals",
@@ -18,7 +18,7 @@ STAGE_OF_KERNEL = {
     "k_odom_motion": "publish_etc", "k_odom_update": "publish_etc", "k_cellgrid_build": "publish_etc",
     "sc_make": "Descriptor",
     "sc_similarity": "Detect loop", "sc_search": "Detect loop", "sc_distance": "Detect loop",
-    "k_pack_constraints": "Register",
+    "k_pack_constraints": "Register", "k_merge_constraints": "Register", "nccl_all_gather": "Register",
     "k_coral": "Verify loop candidate",
     "pgo_blocks": "Pose grapgh optimization", "pgo_gather": "Pose grapgh optimization", "pgo_cost": "Pose grapgh optimization", "pgo_pcg": "Pose grapgh optimization", "pgo_pcg_cluster": "Pose grapgh optimization", "pgo_pcg_chain": "Pose grapgh optimization",   # sic: the reference's spelling
 }

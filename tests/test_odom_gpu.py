@@ -87,6 +87,18 @@ def test_odometry_mulran_shape_rotate_on_receipt_ccw(ctx, oracle):
     gp.filter.range_res = 0.0595238
     _run_pair(ctx, oracle, [scans], dict(submap_scan_size=1, weight_intensity=0, res=3.5, radar_ccw=1, filter=gp.filter),
               dict(submap_scan_size=1, weight_intensity=0, res=3.5, radar_ccw=1, k_strongest=12, z_min=70.0, range_res=0.0595238))
+    # rotate-on-receipt inside the device step (tbv_odom_set_wire_layout): the wire-layout scans give, bit for bit, the poses of the
+    # pre-rotated ones — two sequences so that the batched rotate kernel sees more than one image
+    kw = dict(submap_scan_size=1, weight_intensity=0, res=3.5, radar_ccw=1, filter=gp.filter)
+    pre = api.OdometryKeyframeFuser(ctx, 2, 400, 3360, api.default_odom_params(**kw))
+    wired = api.OdometryKeyframeFuser(ctx, 2, 400, 3360, api.default_odom_params(**kw))
+    wired.set_wire_layout(True)
+    for f in range(len(scans) - 1):
+        a = pre.pointcloudCallback(np.stack([scans[f], scans[f + 1]]))
+        w = np.stack([np.ascontiguousarray(np.rot90(st.scans[f], -1)), np.ascontiguousarray(np.rot90(st.scans[f + 1], -1))])
+        b = wired.pointcloudCallback(w.reshape(2, 400, 3360))      # same bytes, wire layout [3360][400] per scan
+        assert np.array_equal(api.poses(a), api.poses(b)) and [o.n_points for o in a] == [o.n_points for o in b]
+    pre.close(); wired.close()
 
 
 def test_dense_short_range_clutter_uses_the_global_point_arrays(ctx, oracle):

@@ -39,7 +39,7 @@ def test_every_launched_kernel_has_a_stage():
 def test_document_profile_folds_kernels_into_stages():
     st = S.statistics()
     for step in range(2):
-        S.document_profile(st, [("k1_kstrongest", 0.25), ("k2_make_clouds", 0.09), ("cells_fused", 0.2), ("k_register", 0.44), ("k_odom_update", 0.02)])
+        S.document_profile(st, [("k1_filter_fused", 0.34), ("cells_fused", 0.2), ("k_register", 0.44), ("k_odom_update", 0.02)])
     S.document_profile(st, [("k_register", 0.4), ("k_pack_constraints", 0.01)], loop_registration=True)
     assert all(abs(v - 0.34) < 1e-12 for v in st.t["Filtering"]) and len(st.t["Filtering"]) == 2
     assert st.t["register"] == [0.44, 0.44] and abs(st.t["Register"][0] - 0.41) < 1e-12
