@@ -60,7 +60,7 @@ N_PLACES = 8  # distinct stretches of the figure-8 the sequences start from
 LOOP_PAIRS_PER_GPU = (1024, 256)   # loop_batch leg: candidates per GPU per iteration
 LOOP_KF_PER_PLACE = 12             # keyframes of the loop database: the first frames of every stretch (2.5 m apart: overlapping views)
 MU_N_RANGE, MU_RANGE_RES = 3360, 0.0595238
-MU_PLACES, MU_SEQS, MU_WARMUP, MU_STEPS, MU_LOOP_PAIRS = 2, 296, 3, 8, 1000
+MU_PLACES, MU_SEQS, MU_WARMUP, MU_STEPS, MU_LOOP_PAIRS = 2, 592, 3, 8, 1000
 SURVEY_K1_UNIT = 1_715_200         # K1 per OX scan, k = 40: 1 507 200 B read + 208 000 B written with every row full
 K1_TRAFFIC_FILE = "profiles/r2_full_k1_filter_fused.txt"   # ncu --set full summary the roofline's `traffic` is read from
 

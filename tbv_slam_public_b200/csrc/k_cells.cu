@@ -536,10 +536,10 @@ c6_compact(const GridInfo* __restrict__ grid, const int* __restrict__ n_samples,
 // then u = q + S / W and cov = SS / W - (S / W)(S / W)^T — algebraically cell::cell's normalised-weight mean / covariance
 // (pointnormal.cpp:13-33), within a few ulp of it (cells are tolerance-parity).
 constexpr int CFU_THREADS = 1024;
-constexpr int CFU_VMAX = 16384;  // voxels of the scratch grid
+constexpr int CFU_VMAX = 22528;  // voxels of the scratch grid at 3 m leaves, extent = 1.05 x range + 8 m: Oxford (165 m) 15.4 k, MulRan (200 m) 22.2 k
 constexpr int CFU_SMAX = 4096;   // samples per scan
 constexpr int CFU_PCAP = 8192;   // points per scan held in shared memory
-constexpr int CFU_CHUNK = (CFU_VMAX + 1 + CFU_THREADS - 1) / CFU_THREADS;  // entries of A per thread (17)
+constexpr int CFU_CHUNK = (CFU_VMAX + 1 + CFU_THREADS - 1) / CFU_THREADS;  // entries of A per thread (23)
 constexpr int CFU_OFF_A = 0;
 constexpr int CFU_OFF_SVOX = ((CFU_VMAX + 2) * 2 + 15) & ~15;
 constexpr int CFU_OFF_CX = CFU_OFF_SVOX + CFU_SMAX * 2;

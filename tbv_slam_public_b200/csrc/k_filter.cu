@@ -10,6 +10,7 @@
 // "peak" when its 7-tap score is not exceeded within +-3 bins (bytes across the row edge come from the neighbouring row of the flat
 // cv::Mat, as the reference's indexing reads them).
 #include <cmath>
+#include <type_traits>
 
 #include "tbv_common.cuh"
 
@@ -100,48 +101,196 @@ __device__ __forceinline__ void compensate_point(float& x, float& y, double m0, 
   y = (float)__dadd_rn(__dadd_rn(__dmul_rn(s1, px), __dmul_rn(c1, py)), ty);
 }
 
-// ---- the fused filter kernel ----------------------------------------------------------------------------------------------------------
-// One CTA (8 warps) per scan walks the scan's rows in chunks of 8 (one row per warp) and writes the two final clouds directly:
-//   P1 (warp per row)      the row arrives by ONE bulk copy (TMA, mbarrier) in the warp's row buffer; branch-free conservative scan of the
-//                          16-byte vectors (flags kept as a bit per lane and vector), flagged vector ids queued, exact byte masks of the queued
-//                          vectors, candidates (key << 2 | emitted << 1) appended to the row's list.  Rows with more candidates than the list
-//                          holds take the exact dense path (threshold bisection on the staged row + ties from the far end) and end with <= k.
-//   P2 (half-warp per row) all-pairs rank inside the row's list -> the k strongest in ascending (intensity, range) order; 7+7-tap axial
-//                          non-max suppression of the selected bins on the staged row; per-entry output offsets by ballot prefix.
-//   P3 (one thread per point, all 256 threads) the emitted entries of the 8 rows, staged in output order: fp64 polar -> Cartesian with the
-//                          host (glibc) cos/sin table, motion compensation, coalesced stores to both clouds at the scan's running offsets.
-// The next chunk's rows are requested as soon as P2 has read the current ones, so the copies fly under P3's fp64 work and under the other
-// resident CTAs (4 per SM).  Nothing but the scan bytes is read from HBM and nothing but the clouds is written: the per-row key arrays of
-// the two-kernel version (and their round trip through L2) are gone.
-constexpr int KF_WARPS = 8;                  // warps per CTA = rows per chunk
-constexpr int KF_THREADS = KF_WARPS * 32;
-constexpr int KF_CAP = 128;                  // per-row candidate list capacity = largest supported k
+// The same compensation for a point the filter itself just made: (x, y) = float(rho cos theta), float(rho sin theta) with (c, s) the
+// azimuth's table entry and th = atan2(s, c) from the host (glibc).  atan2(y, x) = th + atan2(c y - s x, c x + s y) exactly (rotation by
+// -th), and the second term is the float rounding of x and y seen as an angle: < 1e-7 rad, so atan(t) = t to 3e-22 rad.  The cross product
+// is formed with its rounding error removed (two-product by fma), which leaves the sum th + delta with the one rounding a libm atan2 has
+// as well — at a tenth of the instructions (no argument reduction, no polynomial, one division).
+__device__ __forceinline__ void compensate_polar_point(float& x, float& y, double c, double s, double th, double m0, double m1, double m2, int ccw) {
+  const double two_pi = __dmul_rn(2.0, 3.14159265358979323846);
+  const double px = (double)x, py = (double)y;
+  const double t = __dmul_rn(s, px);
+  const double terr = __fma_rn(s, px, -t);                            // s * px = t + terr exactly
+  const double cross = __dsub_rn(__fma_rn(c, py, -t), terr);          // c * py - s * px
+  const double dot = __fma_rn(c, px, __dmul_rn(s, py));
+  const double a = __dadd_rn(th, __ddiv_rn(cross, dot));
+  double d = __ddiv_rn((a > 0.00001 ? a : __dadd_rn(two_pi, a)), two_pi);
+  d = ccw ? -(__dsub_rn(d, 0.5)) : __dsub_rn(d, 0.5);
+  const double ang = __dmul_rn(d, m2);
+  double s1, c1;
+  sincos(ang, &s1, &c1);
+  const double tx = __dmul_rn(d, m0), ty = __dmul_rn(d, m1);
+  x = (float)__dadd_rn(__dadd_rn(__dmul_rn(c1, px), __dmul_rn(-s1, py)), tx);
+  y = (float)__dadd_rn(__dadd_rn(__dmul_rn(s1, px), __dmul_rn(c1, py)), ty);
+}
 
-// list entry: bits 2..25 = intensity << 16 | range (the reference's std::pair<uchar,int> order), bit 1 = emitted (range > min_range_bin),
-// bit 0 = peak (set in P2).  Distinct entries of a row have distinct keys, so comparing entries compares keys.
-__device__ __forceinline__ uint32_t kf_entry(uint32_t inten, int r, int min_range_bin) {
-  return (((inten << 16) | (uint32_t)r) << 2) | (r > min_range_bin ? 2u : 0u);
+// ---- the fused filter kernel ----------------------------------------------------------------------------------------------------------
+// One CTA (6 warps) per scan walks the scan's rows in chunks of 12 — TWO rows per warp — and writes the two final clouds directly:
+//   P1 (warp, its two rows)  each row arrives by ONE bulk copy (TMA, mbarrier) in one of the warp's two row buffers; branch-free
+//                            conservative scan of the 16-byte vectors (one flag bit per lane and vector, no ballots in the loop); the
+//                            flagged vector ids of BOTH rows go into one queue, so that the exact byte masks, the candidate extraction and
+//                            everything after it run once per row pair with twice the lanes busy (a radar row holds ~14 candidates).
+//                            Candidates carry their row in the bit above the intensity: entry = (row bit | intensity | range) << 2 | emitted
+//                            << 1 | peak, so one all-pairs rank over the pair's list orders both rows at once (rank inside the row = rank in
+//                            the pair minus, for the first row, the size of the second).  Rows with more candidates than a list holds take
+//                            the exact dense path (threshold bisection on the staged row + ties from the far end) and contribute <= k.
+//   P2 (warp)                rank -> the k strongest of each row, ascending (intensity, range); 7+7-tap axial non-max suppression of the
+//                            emitted bins on the staged rows.  Then the warp requests its next two rows: the copies fly under P3 and the
+//                            other warps.
+//   P3 (warp)                the pair's emitted entries, one lane per point: fp64 polar -> Cartesian with the host (glibc) cos/sin table,
+//                            motion compensation, stores to both clouds.  The clouds are in row order, so the pair's offset is the total of
+//                            all earlier rows: the running totals travel warp to warp (and chunk to chunk) through shared memory — a warp
+//                            publishes its totals as soon as it has counted, before computing a point, and its successor sleeps on an
+//                            mbarrier until then.
+// No CTA barrier inside the row loop: every phase is warp-local.  (Measured alternatives: two CTA barriers per chunk with a flattened
+// emission — same speed, more shared memory; per-warp scratch segments compacted at the end of the scan — the compaction is a serial
+// tail that all CTAs of the single wave reach together, 40 % slower.)  Nothing but the scan bytes is read from HBM and nothing but the
+// clouds is written: the per-row key arrays of the two-kernel version (and their round trip through L2) are gone.
+constexpr int KF_WARPS = 6;                  // warps per CTA; a chunk is 2 * KF_WARPS rows.  6: 48 KB of row buffers -> 4 CTAs per SM (592 scans = one wave on 148 SMs)
+constexpr int KF_THREADS = KF_WARPS * 32;
+constexpr int KF_MAX_K = 128;                // largest supported k (list capacity per row: 64 for k <= 64, else 128)
+
+struct KfCloud {   // one cloud of the batch, struct of arrays, `cap` entries per scan
+  float* x; float* y; uint8_t* i; uint16_t* az; uint16_t* rg;
+};
+__device__ __forceinline__ void kf_store(const KfCloud& c, size_t q, float x, float y, uint8_t inten, int az, int r) {
+  c.x[q] = x; c.y[q] = y; c.i[q] = inten; c.az[q] = (uint16_t)az; c.rg[q] = (uint16_t)r;
+}
+
+__device__ __forceinline__ uint32_t kf_entry(uint32_t inten, int r, int min_range_bin, uint32_t rowbit) {
+  return (((rowbit << 24) | (inten << 16) | (uint32_t)r) << 2) | (r > min_range_bin ? 2u : 0u);
+}
+// movemask of the four flag bytes (0x80 each) of a word: bits 7, 15, 23, 31 -> bits 0..3 (the multiply gathers them at bits 21..24; all
+// partial products are distinct bits, so there are no carries)
+__device__ __forceinline__ uint32_t kf_nibble(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xfu; }
+
+struct KfRow {          // one staged row, as the warp sees it
+  const uint8_t* buf;   // staged superset: buf[a0 + r] = row[r]
+  int a0, nvec;         // alignment offset of the row start; 16-byte vectors covering [0, a0 + n_range)
+};
+__device__ __forceinline__ uint32_t kf_valid_mask(int wo, int lo_b, int hi_b) {   // word at buffer offset wo: 0x80 per byte inside the row
+  uint32_t m = 0x80808080u;
+  if (wo < lo_b) m &= (lo_b - wo >= 4) ? 0u : (0x80808080u << (8 * (lo_b - wo)));
+  if (wo + 4 > hi_b) m &= (hi_b - wo <= 0) ? 0u : (0x80808080u >> (8 * (wo + 4 - hi_b)));
+  return m;
+}
+// exact "byte >= t" flags of one staged vector as a 16-bit mask; the staged superset starts / ends up to 15 bytes outside the row
+__device__ __forceinline__ uint32_t kf_ge16(const KfRow& R, int n_range, int t, uint32_t ac, bool h) {
+  const uint4 v = reinterpret_cast<const uint4*>(R.buf)[t];
+  const int wo = t << 4, lo_b = R.a0, hi_b = R.a0 + n_range;
+  uint32_t m0 = ge_mask(v.x, ac, h), m1 = ge_mask(v.y, ac, h), m2 = ge_mask(v.z, ac, h), m3 = ge_mask(v.w, ac, h);
+  if (wo < lo_b || wo + 16 > hi_b) { m0 &= kf_valid_mask(wo, lo_b, hi_b); m1 &= kf_valid_mask(wo + 4, lo_b, hi_b); m2 &= kf_valid_mask(wo + 8, lo_b, hi_b); m3 &= kf_valid_mask(wo + 12, lo_b, hi_b); }
+  return kf_nibble(m0) | (kf_nibble(m1) << 4) | (kf_nibble(m2) << 8) | (kf_nibble(m3) << 12);
+}
+
+// Dense row: exact threshold T = k-th largest intensity (bisection over the staged row), everything above T, then the ties at T from the
+// far end — the largest ranges win, exactly as the reference's erase(begin()) leaves them.  Appends min(k, #candidates) entries at
+// list[*counter ...] (counter: the warp's shared cursor) and returns how many.  Whole warp.
+__device__ __noinline__ int kf_dense_select(const KfRow R, int n_range, uint32_t z, int k, int min_range_bin, uint32_t rowbit, uint32_t* list,
+                                            int list_cap, int* counter, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const int lo_b = R.a0, hi_b = R.a0 + n_range;
+  const uint4* vbuf = reinterpret_cast<const uint4*>(R.buf);
+  auto count_ge = [&](uint32_t t) -> int {   // bytes of the row >= t, t in 1..255
+    const bool h = t > 128;
+    const uint32_t ac = (h ? (256u - t) : (128u - t)) * 0x01010101u;
+    int c = 0;
+    for (int q = lane; q < R.nvec; q += 32) c += __popc(kf_ge16(R, n_range, q, ac, h));
+    return __reduce_add_sync(FULL, c);
+  };
+  auto cnt = [&](uint32_t t) -> int { return t == 0 ? n_range : count_ge(t); };
+  // T = the k-th largest intensity among the candidates (or z_min when the row holds no more than k candidates: all are taken)
+  uint32_t T = z;
+  int n_ge = cnt(z), n_gt = -1;
+  if (n_ge > k) {
+    uint32_t lo = z, hi_t = 256;   // count(>= lo) >= k, count(>= hi_t) < k
+    int c_hi = 0;
+    while (hi_t - lo > 1) {
+      const uint32_t mid = (lo + hi_t) >> 1;
+      const int c = count_ge(mid);
+      if (c >= k) { lo = mid; n_ge = c; } else { hi_t = mid; c_hi = c; }
+    }
+    T = lo;
+    n_gt = c_hi;                   // hi_t == T + 1 (0 entries above 255)
+  }
+  if (n_gt < 0) n_gt = (T >= 255) ? 0 : count_ge(T + 1);
+  const int want = n_ge < k ? n_ge : k;
+  const int need = want - n_gt;    // ties to take at T, largest ranges first (>= 0)
+  const int start = *counter;
+  __syncwarp();
+  if (T < 255 && n_gt > 0) {       // (1) everything strictly above the threshold
+    const uint32_t t1 = T + 1;
+    const bool h = t1 > 128;
+    const uint32_t ac = (h ? (256u - t1) : (128u - t1)) * 0x01010101u;
+    for (int q = lane; q < R.nvec; q += 32) {
+      uint32_t m16 = kf_ge16(R, n_range, q, ac, h);
+      if (m16) {
+        const int wo = q << 4;
+        int pos = atomicAdd(counter, __popc(m16));
+        while (m16) {
+          const int b = __ffs(m16) - 1;
+          m16 &= m16 - 1;
+          if (pos < list_cap) list[pos] = kf_entry(R.buf[wo + b], wo + b - R.a0, min_range_bin, rowbit);
+          pos++;
+        }
+      }
+    }
+  }
+  // (2) ties at T, scanning ranges from the far end; 32 vectors (512 bytes) per step
+  const uint32_t T4 = T * 0x01010101u;
+  int carry = 0;
+  for (int base = ((R.nvec - 1) >> 5) << 5; base >= 0 && carry < need; base -= 32) {
+    const int q = base + lane;
+    uint32_t m16 = 0;
+    if (q < R.nvec) {
+      const uint4 v = vbuf[q];
+      const int wo = q << 4;
+      m16 = kf_nibble(eq_mask(v.x, T4) & kf_valid_mask(wo, lo_b, hi_b)) | (kf_nibble(eq_mask(v.y, T4) & kf_valid_mask(wo + 4, lo_b, hi_b)) << 4) |
+            (kf_nibble(eq_mask(v.z, T4) & kf_valid_mask(wo + 8, lo_b, hi_b)) << 8) | (kf_nibble(eq_mask(v.w, T4) & kf_valid_mask(wo + 12, lo_b, hi_b)) << 12);
+    }
+    const int c = __popc(m16);
+    int suf = c;  // inclusive suffix sum over lanes (higher lane = larger range)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v2 = __shfl_down_sync(FULL, suf, d);
+      if (lane + d < 32) suf += v2;
+    }
+    const int after = carry + suf - c;
+    int take = need - after;
+    if (take > c) take = c;
+    if (take > 0) {
+      int pos = atomicAdd(counter, take);
+      const int wo = q << 4;
+      while (take > 0) {  // highest bytes first
+        const int b = 31 - __clz(m16);
+        m16 &= ~(1u << b);
+        if (pos < list_cap) list[pos] = kf_entry(T, wo + b - R.a0, min_range_bin, rowbit);
+        pos++;
+        take--;
+      }
+    }
+    carry += __shfl_sync(FULL, suf, 0);
+  }
+  __syncwarp();
+  return min(*counter, list_cap) - start;   // == want
 }
 
 // HI: z_min > 128 (selects the form of the conservative byte compare at compile time: the scan loop carries no branch on it);
-// NG: number of 32-vector groups of a staged row, unrolled at compile time (8: Oxford, 7: MulRan); 0 = run-time loop over n_groups.
-template <bool HI, int NG>
+// NG: number of 32-vector groups of a staged row, unrolled at compile time (8: Oxford, 7: MulRan); 0 = run-time loop over n_groups;
+// CAP: candidate list capacity per row (>= k).
+template <bool HI, int NG, int CAP>
 __global__ void __launch_bounds__(KF_THREADS, 4)
 k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t row_stride, int z_min, int k, int want_peaks, int rowbuf, int n_groups,
-                const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, double range_res, const double2* __restrict__ cs_table, int cap,
-                float* __restrict__ fx, float* __restrict__ fy, uint8_t* __restrict__ fi, uint16_t* __restrict__ faz, uint16_t* __restrict__ frg,
-                int* __restrict__ fcount,
-                float* __restrict__ px, float* __restrict__ py, uint8_t* __restrict__ pi, uint16_t* __restrict__ paz, uint16_t* __restrict__ prg,
-                int* __restrict__ pcount, const double* __restrict__ mot, int ccw) {
-  extern __shared__ __align__(128) uint8_t s_dyn[];               // [KF_WARPS][rowbuf] staged rows
-  __shared__ __align__(16) uint32_t s_list[KF_WARPS][KF_CAP + 4];  // candidates of the row (unordered), zero-padded to a multiple of 4
-  __shared__ __align__(16) uint32_t s_sel[KF_WARPS][KF_CAP];       // P1: queue of flagged vectors (u16); P2: selected entries, ascending
-  __shared__ uint32_t s_idx[KF_WARPS][KF_CAP];                     // P2: per selected entry (index among emitted) | (index among peaks) << 16
-  __shared__ uint32_t s_stkey[KF_WARPS * KF_CAP];                  // P3 staging, output order: entry
-  __shared__ int16_t s_stpp[KF_WARPS * KF_CAP];                    //   position among the chunk's peaks, or -1
-  __shared__ uint8_t s_strow[KF_WARPS * KF_CAP];                   //   row within the chunk
-  __shared__ __align__(8) uint64_t s_bar[KF_WARPS];
-  __shared__ int s_n[KF_WARPS], s_cntf[KF_WARPS], s_cntp[KF_WARPS], s_dn[KF_WARPS];
+                const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, double range_res, const double2* __restrict__ cs_table,
+                const double* __restrict__ th_table, int cap, KfCloud out_f, int* __restrict__ fcount, KfCloud out_p, int* __restrict__ pcount,
+                const double* __restrict__ mot, int ccw) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];                   // [KF_WARPS][2][rowbuf] staged rows, 
+  __shared__ __align__(16) uint32_t s_list[KF_WARPS][2 * CAP + 4];     // candidates of the row pair (unordered, zero-padded to a multiple of 4)
+  __shared__ __align__(16) uint32_t s_sel[KF_WARPS][2 * CAP];          // P1: queue of flagged vectors (u16); P2: selected entries, ascending
+  __shared__ __align__(8) uint64_t s_bar[KF_WARPS][2];
+  __shared__ int s_dn[KF_WARPS];
+  __shared__ int s_chain[KF_WARPS][2];                                 // emitted points / peaks of the scan up to and including this warp's rows
+  __shared__ __align__(8) uint64_t s_chain_bar[KF_WARPS];              // phase c completes when the warp has published its totals of chunk c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned FULL = 0xffffffffu;
   const int scan = blockIdx.x;
@@ -150,372 +299,287 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
   const uint32_t addc = (HI ? (256u - z) : (128u - z)) * 0x01010101u;
   const size_t scan_bytes = (size_t)(n_az - 1) * row_stride + (size_t)n_range;  // addressable bytes of one scan
   const uint8_t* scan_base = polar + (size_t)scan * (size_t)n_az * row_stride;
-  uint8_t* buf = s_dyn + (size_t)warp * rowbuf;
-  const uint4* vbuf = reinterpret_cast<const uint4*>(buf);
+  uint8_t* bufs = s_dyn + (size_t)warp * 2 * rowbuf;   // the warp's two row buffers
   uint32_t* list = s_list[warp];
-  uint64_t* bar = &s_bar[warp];
-  if (lane == 0) mbar_init(bar, 1);
-  // The row buffer starts out zero: the scan loop runs over whole groups of 32 vectors, and the vectors past a row's staged superset are
+  uint32_t* sel = s_sel[warp];
+  if (lane < 2) mbar_init(&s_bar[warp][lane], 1);
+  if (lane == 2) mbar_init(&s_chain_bar[warp], 1);
+  // The row buffers start out zero: the scan loop runs over whole groups of 32 vectors, and the vectors past a row's staged superset are
   // never written by a bulk copy (the one right behind it is re-zeroed per row, see below).
-  for (int o = lane * 16; o < rowbuf; o += 32 * 16) *reinterpret_cast<uint4*>(buf + o) = make_uint4(0, 0, 0, 0);
+  for (int o = lane * 16; o < 2 * rowbuf; o += 32 * 16) *reinterpret_cast<uint4*>(bufs + o) = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   __syncwarp();
-  uint32_t parity = 0;
-  bool in_flight = false;
-  if (warp < n_az) in_flight = stage_row_tma(buf, scan_base + (size_t)warp * row_stride, n_range, buf_lo, buf_hi, bar, lane);
+  uint32_t parity = 0;      // bit x: parity to wait for on the warp's barrier x
+  uint32_t in_flight = 0;   // bit x: a bulk copy into buffer x is under way
+#pragma unroll
+  for (int x = 0; x < 2; x++)
+    if (2 * warp + x < n_az && stage_row_tma(bufs + x * rowbuf, scan_base + (size_t)(2 * warp + x) * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
+      in_flight |= 1u << x;
   double m0 = 0.0, m1 = 0.0, m2 = 0.0;
   if (mot) { m0 = mot[scan * 3 + 0]; m1 = mot[scan * 3 + 1]; m2 = mot[scan * 3 + 2]; }
   const double range_res_half = range_res / 2.0;
   const size_t cbase = (size_t)scan * cap;
-  int base_f = 0, base_p = 0;   // running output offsets of the scan (every thread keeps its own copy)
+  __syncthreads();   // every warp's chain barrier is initialised before a neighbour waits on it
 
-  for (int row0 = 0; row0 < n_az; row0 += KF_WARPS) {
-    // =============================== P1: warp per row ===============================================================================
-    const int row = row0 + warp;
-    int n = 0;
-    int a0 = 0;
-    if (row < n_az) {
-      const uint8_t* rp = scan_base + (size_t)row * row_stride;
-      a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
-      if (in_flight) { mbar_wait(bar, parity); parity ^= 1u; }
-      else stage_row_sync(buf, rp, n_range, lane);
-      const int lo_b = a0, hi_b = a0 + n_range;  // valid buffer byte range [lo_b, hi_b)
-      const int nvec = (hi_b + 15) >> 4;         // 16-byte vectors covering [0, hi_b)
+  // Conservative test "some byte of the 16 may be >= z_min" (never misses one; false positives only next to a byte >= 188):
+  // z <= 128: byte + (128 - z) sets bit 7, or overflows the byte only when the byte itself has bit 7 set; z > 128: bit 7.
+  auto any_ge = [&](const uint4 v) -> bool {
+    if (HI) return ((v.x | v.y | v.z | v.w) & 0x80808080u) != 0;
+    const uint32_t a = (v.x + addc) | v.x, b = (v.y + addc) | v.y, c = (v.z + addc) | v.z, d = (v.w + addc) | v.w;
+    return ((a | b | c | d) & 0x80808080u) != 0;
+  };
+
+  for (int row0 = 0, chunk = 0; row0 < n_az; row0 += 2 * KF_WARPS, chunk++) {
+    // =============================== P1: the warp's two rows ========================================================================
+    const int rowA = row0 + 2 * warp;
+    KfRow R[2];
+    uint32_t bits[2] = {0u, 0u};
+    uint32_t have = 0;
+#pragma unroll
+    for (int x = 0; x < 2; x++) {
+      R[x].buf = bufs + x * rowbuf; R[x].a0 = 0; R[x].nvec = 0;
+      if (rowA + x >= n_az) continue;
+      have |= 1u << x;
+      const uint8_t* rp = scan_base + (size_t)(rowA + x) * row_stride;
+      R[x].a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
+      R[x].nvec = (R[x].a0 + n_range + 15) >> 4;
+      if (in_flight & (1u << x)) { mbar_wait(&s_bar[warp][x], (parity >> x) & 1u); parity ^= 1u << x; }
+      else stage_row_sync(bufs + x * rowbuf, rp, n_range, lane);
       // a previous row with another alignment may have ended one vector later: that vector must not be seen by the guard-free scan
-      if (lane == 0 && (nvec << 4) < rowbuf) *reinterpret_cast<uint4*>(buf + (nvec << 4)) = make_uint4(0, 0, 0, 0);
+      if (lane == 0 && (R[x].nvec << 4) < rowbuf) *reinterpret_cast<uint4*>(bufs + x * rowbuf + (R[x].nvec << 4)) = make_uint4(0, 0, 0, 0);
       __syncwarp();
-      auto valid_mask = [&](int wo) -> uint32_t {   // word at buffer offset wo: 0x80 per byte that belongs to the row
-        uint32_t m = 0x80808080u;
-        if (wo < lo_b) m &= (lo_b - wo >= 4) ? 0u : (0x80808080u << (8 * (lo_b - wo)));
-        if (wo + 4 > hi_b) m &= (hi_b - wo <= 0) ? 0u : (0x80808080u >> (8 * (wo + 4 - hi_b)));
-        return m;
-      };
-      // exact "byte >= t" masks of one vector; the staged superset starts / ends up to 15 bytes outside the row: masked at both ends
-      auto masks = [&](const uint4 v, int wo, uint32_t ac, bool h, uint32_t m[4]) {
-        m[0] = ge_mask(v.x, ac, h); m[1] = ge_mask(v.y, ac, h); m[2] = ge_mask(v.z, ac, h); m[3] = ge_mask(v.w, ac, h);
-        if (wo < lo_b || wo + 16 > hi_b) { m[0] &= valid_mask(wo); m[1] &= valid_mask(wo + 4); m[2] &= valid_mask(wo + 8); m[3] &= valid_mask(wo + 12); }
-      };
-      // Conservative test "some byte of the 16 may be >= z_min" (never misses one; false positives only next to a byte >= 188):
-      // z <= 128: byte + (128 - z) sets bit 7, or overflows the byte only when the byte itself has bit 7 set; z > 128: bit 7.
-      auto any_ge = [&](const uint4 v) -> bool {
-        if (HI) return ((v.x | v.y | v.z | v.w) & 0x80808080u) != 0;
-        const uint32_t a = (v.x + addc) | v.x, b = (v.y + addc) | v.y, c = (v.z + addc) | v.z, d = (v.w + addc) | v.w;
-        return ((a | b | c | d) & 0x80808080u) != 0;
-      };
-      // ---- scan: one flag bit per (lane, group); no ballots, no stores in the loop -----------------------------------------------------
-      bool dense = zero_thr;
-      uint16_t* queue = reinterpret_cast<uint16_t*>(s_sel[warp]);   // <= KF_CAP flagged vector ids
-      int nq = 0;
-      if (!dense) {
-        uint32_t bits = 0;
+      if (!zero_thr) {   // scan: one flag bit per (lane, group); no ballots, no stores in the loop
+        const uint4* vb = reinterpret_cast<const uint4*>(R[x].buf);
+        uint32_t b = 0;
         if (NG > 0) {
 #pragma unroll
           for (int j = 0; j < NG; j++)
-            if (any_ge(vbuf[j * 32 + lane])) bits |= 1u << j;
+            if (any_ge(vb[j * 32 + lane])) b |= 1u << j;
         } else {
 #pragma unroll 4
-          for (int j = 0; j < n_groups; j++) bits |= (any_ge(vbuf[j * 32 + lane]) ? 1u : 0u) << j;
+          for (int j = 0; j < n_groups; j++) b |= (any_ge(vb[j * 32 + lane]) ? 1u : 0u) << j;
         }
-        const int mine = __popc(bits);
-        int incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t2 = __shfl_up_sync(FULL, incl, d);
-          if (lane >= d) incl += t2;
-        }
-        nq = __shfl_sync(FULL, incl, 31);
-        if (nq > KF_CAP) dense = true;
-        else {
-          int q = incl - mine;
-          while (bits) {
-            const int j = __ffs(bits) - 1;
-            bits &= bits - 1;
-            queue[q++] = (uint16_t)(j * 32 + lane);
-          }
-        }
-        __syncwarp();
+        bits[x] = b;
       }
-      // ---- exact masks of the queued vectors, one vector per lane per round; list positions from a warp scan of the per-vector counts ----
-      for (int qb = 0; qb < nq && !dense; qb += 32) {
-        int c = 0, wo = 0;
-        uint32_t m16 = 0;   // bit b: byte b of the vector is a candidate
+    }
+    // flagged vectors per row (packed: first row in the low half), inclusive scan over the lanes
+    const uint32_t mine = (uint32_t)__popc(bits[0]) | ((uint32_t)__popc(bits[1]) << 16);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t2 = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += t2;
+    }
+    const uint32_t totq = __shfl_sync(FULL, incl, 31);
+    const int nq0 = (int)(totq & 0xffffu), nq1 = (int)(totq >> 16);
+    uint32_t dense = zero_thr ? have : (((nq0 > CAP) ? 1u : 0u) | ((nq1 > CAP) ? 2u : 0u));
+    uint16_t* queue = reinterpret_cast<uint16_t*>(sel);   // <= 2 * CAP flagged vectors: bit 15 = second row, bits 0..14 = vector id
+    int n = 0, nrow[2] = {0, 0};
+    for (int attempt = 0; attempt < 3; attempt++) {
+      n = 0; nrow[0] = 0; nrow[1] = 0;
+      if (dense) {
+        if (lane == 0) s_dn[warp] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+          if (dense & have & (1u << x)) {
+            nrow[x] = kf_dense_select(R[x], n_range, z, k, min_range_bin, (uint32_t)x, list, 2 * CAP, &s_dn[warp], lane);
+            n += nrow[x];
+          }
+      }
+      // queue of the sparse rows' flagged vectors, first row first
+      const int q0n = (dense & 1u) ? 0 : nq0, q1n = (dense & 2u) ? 0 : nq1;
+      {
+        int q = (int)((incl & 0xffffu) - (mine & 0xffffu));
+        uint32_t b = (dense & 1u) ? 0u : bits[0];
+        while (b) { const int j = __ffs(b) - 1; b &= b - 1; queue[q++] = (uint16_t)(j * 32 + lane); }
+        q = q0n + (int)((incl >> 16) - (mine >> 16));
+        b = (dense & 2u) ? 0u : bits[1];
+        while (b) { const int j = __ffs(b) - 1; b &= b - 1; queue[q++] = (uint16_t)(0x8000 | (j * 32 + lane)); }
+      }
+      __syncwarp();
+      const int nq = q0n + q1n;
+      uint32_t overflow = 0;
+      // exact masks of the queued vectors, one vector per lane per round; list positions from a warp scan of the per-vector counts
+      for (int qb = 0; qb < nq; qb += 32) {
+        uint32_t m16 = 0, c = 0;
+        int wo = 0, x = 0;
         if (qb + lane < nq) {
           const int t = queue[qb + lane];
-          wo = t << 4;
-          uint32_t m[4];
-          masks(vbuf[t], wo, addc, HI, m);
-          // movemask of 4 bytes: bits 7, 15, 23, 31 -> bits 0..3 (multiply gathers them at bits 21..24; no carries, all partial products distinct)
-          m16 = (((m[0] >> 7) * 0x00204081u) >> 21 & 0xfu) | (((m[1] >> 7) * 0x00204081u) >> 17 & 0xf0u) |
-                (((m[2] >> 7) * 0x00204081u) >> 13 & 0xf00u) | (((m[3] >> 7) * 0x00204081u) >> 9 & 0xf000u);
-          c = __popc(m16);
+          x = t >> 15;
+          wo = (t & 0x7fff) << 4;
+          const KfRow Rx = {x ? R[1].buf : R[0].buf, x ? R[1].a0 : R[0].a0, x ? R[1].nvec : R[0].nvec};   // selects, not indexing: R stays in registers
+          m16 = kf_ge16(Rx, n_range, t & 0x7fff, addc, HI);
+          c = (uint32_t)__popc(m16) << (16 * x);
         }
-        int incl = c;
+        uint32_t ic = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const int t2 = __shfl_up_sync(FULL, incl, d);
-          if (lane >= d) incl += t2;
+          const uint32_t t2 = __shfl_up_sync(FULL, ic, d);
+          if (lane >= d) ic += t2;
         }
-        const int round_total = __shfl_sync(FULL, incl, 31);
-        if (n + round_total > KF_CAP) { dense = true; break; }
-        int pos = n + incl - c;
+        const uint32_t rt = __shfl_sync(FULL, ic, 31);
+        const int t0 = (int)(rt & 0xffffu), t1 = (int)(rt >> 16);
+        if (nrow[0] + t0 > CAP) overflow |= 1u;
+        if (nrow[1] + t1 > CAP) overflow |= 2u;
+        if (overflow) break;
+        const uint32_t ex = ic - c;
+        int pos = n + (int)(ex & 0xffffu) + (int)(ex >> 16);
+        const uint8_t* rb = x ? R[1].buf : R[0].buf;
+        const int ra0 = x ? R[1].a0 : R[0].a0;
         while (m16) {
           const int b = __ffs(m16) - 1;
           m16 &= m16 - 1;
-          list[pos++] = kf_entry(buf[wo + b], wo + b - a0, min_range_bin);
+          list[pos++] = kf_entry(rb[wo + b], wo + b - ra0, min_range_bin, (uint32_t)x);
         }
-        n += round_total;
+        n += t0 + t1; nrow[0] += t0; nrow[1] += t1;
       }
-      if (dense) {
-        // ---- dense row: exact threshold T = k-th largest intensity (bisection over the staged row), everything above T, then the ties at
-        // T from the far end — the largest ranges win, exactly as the reference's erase(begin()) leaves them --------------------------------
-        if (lane == 0) s_dn[warp] = 0;
-        __syncwarp();
-        auto count_ge = [&](uint32_t t) -> int {   // bytes of the row >= t (t in 1..255; t == 0 never asked)
-          const bool h = t > 128;
-          const uint32_t ac = (h ? (256u - t) : (128u - t)) * 0x01010101u;
-          uint32_t c = 0;   // 128 x the count: dp4a sums the four flag bytes (0x80 each) of a word in one instruction
-          for (int q = lane; q < nvec; q += 32) {
-            uint32_t m[4];
-            masks(vbuf[q], q << 4, ac, h, m);
-            c = __dp4a(m[0], 0x01010101u, c); c = __dp4a(m[1], 0x01010101u, c);
-            c = __dp4a(m[2], 0x01010101u, c); c = __dp4a(m[3], 0x01010101u, c);
-          }
-          return (int)(__reduce_add_sync(FULL, c) >> 7);
-        };
-        // T = the k-th largest intensity among the candidates (or z_min when the row holds no more than k candidates: all are taken)
-        auto cnt = [&](uint32_t t) -> int { return t == 0 ? n_range : count_ge(t); };
-        uint32_t T = z;
-        int n_ge = cnt(z), n_gt = -1;
-        if (n_ge > k) {
-          uint32_t lo = z, hi_t = 256;   // count(>= lo) >= k, count(>= hi_t) < k
-          int c_hi = 0;
-          while (hi_t - lo > 1) {
-            const uint32_t mid = (lo + hi_t) >> 1;
-            const int c = count_ge(mid);
-            if (c >= k) { lo = mid; n_ge = c; } else { hi_t = mid; c_hi = c; }
-          }
-          T = lo;
-          n_gt = c_hi;                   // hi_t == T + 1 (0 entries above 255)
-        }
-        if (n_gt < 0) n_gt = (T >= 255) ? 0 : count_ge(T + 1);
-        const int want = n_ge < k ? n_ge : k;
-        const int need = want - n_gt;   // ties to take at T, largest ranges first (>= 0)
-        if (T < 255 && n_gt > 0) {      // (1) everything strictly above the threshold
-          const uint32_t t1 = T + 1;
-          const bool h = t1 > 128;
-          const uint32_t ac = (h ? (256u - t1) : (128u - t1)) * 0x01010101u;
-          for (int q = lane; q < nvec; q += 32) {
-            const int wo = q << 4;
-            uint32_t m[4];
-            masks(vbuf[q], wo, ac, h, m);
-            uint32_t m16 = (((m[0] >> 7) * 0x00204081u) >> 21 & 0xfu) | (((m[1] >> 7) * 0x00204081u) >> 17 & 0xf0u) |
-                           (((m[2] >> 7) * 0x00204081u) >> 13 & 0xf00u) | (((m[3] >> 7) * 0x00204081u) >> 9 & 0xf000u);
-            if (m16) {
-              int pos = atomicAdd(&s_dn[warp], __popc(m16));
-              while (m16) {
-                const int b = __ffs(m16) - 1;
-                m16 &= m16 - 1;
-                if (pos < KF_CAP) list[pos] = kf_entry(buf[wo + b], wo + b - a0, min_range_bin);
-                pos++;
-              }
-            }
-          }
-        }
-        // (2) ties at T, scanning ranges from the far end; 32 vectors (512 bytes) per step
-        const uint32_t T4 = T * 0x01010101u;
-        int carry = 0;
-        for (int base = ((nvec - 1) >> 5) << 5; base >= 0 && carry < need; base -= 32) {
-          const int q = base + lane;
-          uint32_t m16 = 0;
-          if (q < nvec) {
-            const uint4 v = vbuf[q];
-            const int wo = q << 4;
-            const uint32_t e0 = eq_mask(v.x, T4) & valid_mask(wo), e1 = eq_mask(v.y, T4) & valid_mask(wo + 4);
-            const uint32_t e2 = eq_mask(v.z, T4) & valid_mask(wo + 8), e3 = eq_mask(v.w, T4) & valid_mask(wo + 12);
-            m16 = (((e0 >> 7) * 0x00204081u) >> 21 & 0xfu) | (((e1 >> 7) * 0x00204081u) >> 17 & 0xf0u) |
-                  (((e2 >> 7) * 0x00204081u) >> 13 & 0xf00u) | (((e3 >> 7) * 0x00204081u) >> 9 & 0xf000u);
-          }
-          const int c = __popc(m16);
-          int suf = c;  // inclusive suffix sum over lanes (higher lane = larger range)
+      if (!overflow) break;
+      dense |= overflow;   // the overflowing row(s) go through the dense path; at most two more attempts
+      __syncwarp();
+    }
+    __syncwarp();
+    if (lane < 4) list[n + lane] = 0;   // pad to a multiple of 4 with zeros (never greater than an entry)
+    __syncwarp();
+
+    // =============================== P2: rank, non-max suppression, compaction (warp-local) =========================================
+    const int nselA = nrow[0] < k ? nrow[0] : k, nselB = nrow[1] < k ? nrow[1] : k;
+    const int n_sel = nselA + nselB;
+    // all-pairs rank over the pair's list: entries of the second row are larger than all entries of the first, so
+    // rank inside the row = rank in the pair (second row) or rank in the pair - |second row| (first row); selected iff < k
+    for (int e = lane; e < n; e += 32) {
+      const uint32_t me = list[e];
+      int rank = 0;
+      for (int q = 0; q < n; q += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(list + q);
+        rank += (v.x > me) + (v.y > me) + (v.z > me) + (v.w > me);
+      }
+      const bool second = (me >> 26) & 1u;
+      const int rk = second ? rank : rank - nrow[1];
+      if (rk < k) sel[second ? nselA + (nselB - 1 - rk) : (nselA - 1 - rk)] = me;
+    }
+    __syncwarp();
+    // axial non-max suppression of the emitted selected bins (radar_filters.cpp:238-298) on the staged rows
+    if (want_peaks) {
+      for (int e = lane; e < n_sel; e += 32) {
+        const uint32_t ent = sel[e];
+        if (!(ent & 2u)) continue;   // not emitted: its peak flag is never read
+        const int x = (int)((ent >> 26) & 1u);
+        const int rowp = rowA + x;
+        const uint8_t* rb = x ? R[1].buf : R[0].buf;
+        const int ra0 = x ? R[1].a0 : R[0].a0;
+        const int r = (int)((ent >> 2) & 0xffffu);
+        const bool in_band = (r >= 3) && (r < n_range - 3);
+        int B[13];
+        if (r >= 6 && r + 6 < n_range) {
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int v2 = __shfl_down_sync(FULL, suf, d);
-            if (lane + d < 32) suf += v2;
-          }
-          const int after = carry + suf - c;
-          int take = need - after;
-          if (take > c) take = c;
-          if (take > 0) {
-            int pos = atomicAdd(&s_dn[warp], take);
-            const int wo = q << 4;
-            while (take > 0) {  // highest bytes first
-              const int b = 31 - __clz(m16);
-              m16 &= ~(1u << b);
-              if (pos < KF_CAP) list[pos] = kf_entry(T, wo + b - a0, min_range_bin);
-              pos++;
-              take--;
+          for (int t = 0; t < 13; t++) B[t] = rb[ra0 + r - 6 + t];
+        } else {
+          const long long gbase = (long long)rowp * (long long)row_stride;
+#pragma unroll
+          for (int t = 0; t < 13; t++) {
+            const int q = r - 6 + t;
+            if (q >= 0 && q < n_range) B[t] = rb[ra0 + q];
+            else {
+              const long long fidx = gbase + q;  // flat index into the scan buffer, as cv::Mat::at(bearing, r_nn) addresses it
+              B[t] = (fidx >= 0 && fidx < (long long)scan_bytes) ? (int)__ldg(scan_base + fidx) : 0;
             }
           }
-          carry += __shfl_sync(FULL, suf, 0);
         }
-        __syncwarp();
-        n = min(s_dn[warp], KF_CAP);   // == want
+        int s[7];  // s[i] = score at r - 3 + i = sum of the 7 bytes centred there (sliding window)
+        s[0] = B[0] + B[1] + B[2] + B[3] + B[4] + B[5] + B[6];
+#pragma unroll
+        for (int i = 1; i < 7; i++) s[i] = s[i - 1] - B[i - 1] + B[i + 6];
+        if (!in_band) {
+          // a score exists only where some selected in-band bin OF THE SAME ROW lies within 3 of the position
+          const int q_lo = x ? nselA : 0, q_hi = x ? n_sel : nselA;
+#pragma unroll
+          for (int i = 0; i < 7; i++) {
+            const int p = r - 3 + i;
+            bool computed = false;
+            for (int q = q_lo; q < q_hi; q++) {
+              const int r2 = (int)((sel[q] >> 2) & 0xffffu);
+              if (r2 >= 3 && r2 < n_range - 3 && r2 - p <= 3 && p - r2 <= 3) { computed = true; break; }
+            }
+            if (!computed) s[i] = 0;
+          }
+        }
+        bool largest = true;
+#pragma unroll
+        for (int i = 1; i <= 3; i++)
+          if (s[3 - i] > s[3] || s[3] < s[3 + i]) largest = false;
+        if (largest) sel[e] = ent | 1u;   // other lanes read only the range field of this entry
       }
       __syncwarp();
-      if (lane < 4) list[n + lane] = 0;   // pad to a multiple of 4 with zeros (never greater than an entry)
     }
-    if (lane == 0) s_n[warp] = n;
-    __syncthreads();   // ---- (1) lists complete ---------------------------------------------------------------------------------------
+    // request the warp's next two rows now: the copies fly under the emission below and under the other warps
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads / writes of the buffers before the bulk copies into them
+    in_flight = 0;
+#pragma unroll
+    for (int x = 0; x < 2; x++) {
+      const int nrow_next = rowA + 2 * KF_WARPS + x;
+      if (nrow_next < n_az && stage_row_tma(bufs + x * rowbuf, scan_base + (size_t)nrow_next * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
+        in_flight |= 1u << x;
+    }
 
-    // =============================== P2: half-warp per row ==========================================================================
-    if (tid < KF_WARPS * 16) {
-      const int r8 = tid >> 4, hl = tid & 15;
-      const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
-      const int nr = s_n[r8];
-      const int n_sel = nr < k ? nr : k;
-      const uint32_t* lst = s_list[r8];
-      uint32_t* sel = s_sel[r8];
-      // all-pairs rank: rank = number of strictly larger entries; selected iff rank < k; position n_sel - 1 - rank (ascending order)
-      for (int e = hl; e < nr; e += 16) {
-        const uint32_t mine = lst[e];
-        int rank = 0;
-        for (int q = 0; q < nr; q += 4) {
-          const uint4 v = *reinterpret_cast<const uint4*>(lst + q);
-          rank += (v.x > mine) + (v.y > mine) + (v.z > mine) + (v.w > mine);
-        }
-        if (rank < k) sel[n_sel - 1 - rank] = mine;
-      }
-      __syncwarp(hmask);
-      // axial non-max suppression of the emitted selected bins (radar_filters.cpp:238-298) on the staged row of warp r8
-      if (want_peaks) {
-        const int rowp = row0 + r8;
-        const uint8_t* rb = s_dyn + (size_t)r8 * rowbuf;
-        const int ra0 = (int)(reinterpret_cast<uintptr_t>(scan_base + (size_t)rowp * row_stride) & 15u);
-        for (int e = hl; e < n_sel; e += 16) {
-          const uint32_t ent = sel[e];
-          if (!(ent & 2u)) continue;   // not emitted: its peak flag is never read
-          const int r = (int)((ent >> 2) & 0xffffu);
-          const bool in_band = (r >= 3) && (r < n_range - 3);
-          int B[13];
-          if (r >= 6 && r + 6 < n_range) {
-#pragma unroll
-            for (int t = 0; t < 13; t++) B[t] = rb[ra0 + r - 6 + t];
-          } else {
-            const long long gbase = (long long)rowp * (long long)row_stride;
-#pragma unroll
-            for (int t = 0; t < 13; t++) {
-              const int q = r - 6 + t;
-              if (q >= 0 && q < n_range) B[t] = rb[ra0 + q];
-              else {
-                const long long fidx = gbase + q;  // flat index into the scan buffer, as cv::Mat::at(bearing, r_nn) addresses it
-                B[t] = (fidx >= 0 && fidx < (long long)scan_bytes) ? (int)__ldg(scan_base + fidx) : 0;
-              }
-            }
-          }
-          int s[7];  // s[i] = score at r - 3 + i = sum of the 7 bytes centred there (sliding window)
-          s[0] = B[0] + B[1] + B[2] + B[3] + B[4] + B[5] + B[6];
-#pragma unroll
-          for (int i = 1; i < 7; i++) s[i] = s[i - 1] - B[i - 1] + B[i + 6];
-          if (!in_band) {
-            // a score exists only where some selected in-band bin lies within 3 of the position
-#pragma unroll
-            for (int i = 0; i < 7; i++) {
-              const int p = r - 3 + i;
-              bool computed = false;
-              for (int q = 0; q < n_sel; q++) {
-                const int r2 = (int)((sel[q] >> 2) & 0xffffu);
-                if (r2 >= 3 && r2 < n_range - 3 && r2 - p <= 3 && p - r2 <= 3) { computed = true; break; }
-              }
-              if (!computed) s[i] = 0;
-            }
-          }
-          bool largest = true;
-#pragma unroll
-          for (int i = 1; i <= 3; i++)
-            if (s[3 - i] > s[3] || s[3] < s[3 + i]) largest = false;
-          if (largest) sel[e] = ent | 1u;   // other lanes read only the range field of this entry
-        }
-      }
-      __syncwarp(hmask);
-      // output offsets inside the row: ballot prefix over the ascending entries (emitted, emitted peaks)
-      int run_f = 0, run_p = 0;
-      const unsigned lt = (1u << hl) - 1u;
-      for (int b0 = 0; b0 < n_sel; b0 += 16) {
-        const int e = b0 + hl;
+    // =============================== P3: the pair's points, warp-local =================================================================
+    // Output offsets: the clouds are written in row order, so the pair starts where all earlier rows of the scan end.  No CTA barrier:
+    // the running totals travel along a chain warp 0 -> 1 -> ... -> KF_WARPS-1 -> warp 0 of the next chunk through shared memory; a warp
+    // publishes its totals (mbarrier arrive, release) as soon as it has counted, before it computes a single point, and its successor
+    // sleeps on that mbarrier (try_wait, acquire) instead of polling.
+    int run_f = 0, run_p = 0;
+    for (int b0 = 0; b0 < n_sel; b0 += 32) {
+      const int e = b0 + lane;
+      const uint32_t ent = e < n_sel ? sel[e] : 0u;
+      run_f += __popc(__ballot_sync(FULL, (ent & 2u) != 0));
+      run_p += __popc(__ballot_sync(FULL, (ent & 3u) == 3u));
+    }
+    int base_f = 0, base_p = 0;
+    if (chunk > 0 || warp > 0) {
+      const int pred = warp == 0 ? KF_WARPS - 1 : warp - 1;
+      mbar_wait(&s_chain_bar[pred], (uint32_t)((warp == 0 ? chunk - 1 : chunk) & 1));   // the predecessor's totals for this position are in
+      base_f = s_chain[pred][0]; base_p = s_chain[pred][1];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      s_chain[warp][0] = base_f + run_f; s_chain[warp][1] = base_p + run_p;
+      asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&s_chain_bar[warp])) : "memory");
+    }
+    {
+      const unsigned lt = (1u << lane) - 1u;
+      for (int b0 = 0; b0 < n_sel; b0 += 32) {
+        const int e = b0 + lane;
         const uint32_t ent = e < n_sel ? sel[e] : 0u;
         const bool fe = (ent & 2u) != 0, fp = (ent & 3u) == 3u;
-        const unsigned bf = (__ballot_sync(hmask, fe) >> (16 * ((tid >> 4) & 1))) & 0xffffu;
-        const unsigned bp = (__ballot_sync(hmask, fp) >> (16 * ((tid >> 4) & 1))) & 0xffffu;
-        if (e < n_sel) s_idx[r8][e] = (uint32_t)(run_f + __popc(bf & lt)) | ((uint32_t)(run_p + __popc(bp & lt)) << 16);
-        run_f += __popc(bf);
-        run_p += __popc(bp);
-      }
-      if (hl == 0) { s_cntf[r8] = run_f; s_cntp[r8] = run_p; }
-    }
-    __syncthreads();   // ---- (2) rows consumed, per-row counts known ---------------------------------------------------------------------
-
-    // request the next chunk's rows: they fly under the staging and the fp64 work below
-    {
-      const int nrow = row0 + KF_WARPS + warp;
-      in_flight = false;
-      if (nrow < n_az) {
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads / writes of this buffer before the bulk copy into it
-        in_flight = stage_row_tma(buf, scan_base + (size_t)nrow * row_stride, n_range, buf_lo, buf_hi, bar, lane);
-      }
-    }
-    int tot_f = 0, tot_p = 0;
-    if (tid < KF_WARPS * 16) {   // staging in output order (rows ascending, entries ascending inside a row)
-      const int r8 = tid >> 4, hl = tid & 15;
-      int off_f = 0, off_p = 0;
-#pragma unroll
-      for (int j = 0; j < KF_WARPS - 1; j++) { off_f += j < r8 ? s_cntf[j] : 0; off_p += j < r8 ? s_cntp[j] : 0; }
-      const int nr = s_n[r8];
-      const int n_sel = nr < k ? nr : k;
-      for (int e = hl; e < n_sel; e += 16) {
-        const uint32_t ent = s_sel[r8][e];
-        if (ent & 2u) {
-          const uint32_t ix = s_idx[r8][e];
-          const int q = off_f + (int)(ix & 0xffffu);
-          s_stkey[q] = ent;
-          s_strow[q] = (uint8_t)r8;
-          s_stpp[q] = (ent & 1u) ? (int16_t)(off_p + (int)(ix >> 16)) : (int16_t)-1;
+        const unsigned bf = __ballot_sync(FULL, fe), bp = __ballot_sync(FULL, fp);
+        if (fe) {
+          const int q = base_f + __popc(bf & lt);
+          const int az = rowA + (int)((ent >> 26) & 1u);
+          const int r = (int)((ent >> 2) & 0xffffu);
+          const double2 cs = cs_table[az];
+          const double rho = __dadd_rn(range_res_half, __dmul_rn(range_res, (double)r));  // radar_filters.cpp:329-330
+          float x = (float)__dmul_rn(rho, cs.x);
+          float y = (float)__dmul_rn(rho, cs.y);
+          if (mot) compensate_polar_point(x, y, cs.x, cs.y, th_table[az], m0, m1, m2, ccw);
+          const uint8_t inten = (uint8_t)((ent >> 18) & 0xffu);
+          if (q < cap) kf_store(out_f, cbase + q, x, y, inten, az, r);
+          if (fp) {
+            const int qp = base_p + __popc(bp & lt);
+            if (qp < cap) kf_store(out_p, cbase + qp, x, y, inten, az, r);
+          }
         }
+        base_f += __popc(bf);
+        base_p += __popc(bp);
       }
     }
-#pragma unroll
-    for (int j = 0; j < KF_WARPS; j++) { tot_f += s_cntf[j]; tot_p += s_cntp[j]; }
-    __syncthreads();   // ---- (3) staging complete -----------------------------------------------------------------------------------------
-
-    // =============================== P3: one thread per emitted point =================================================================
-    for (int i = tid; i < tot_f; i += KF_THREADS) {
-      const uint32_t ent = s_stkey[i];
-      const int az = row0 + (int)s_strow[i];
-      const int r = (int)((ent >> 2) & 0xffffu);
-      const double2 cs = cs_table[az];
-      const double rho = __dadd_rn(range_res_half, __dmul_rn(range_res, (double)r));  // radar_filters.cpp:329-330
-      float x = (float)__dmul_rn(rho, cs.x);
-      float y = (float)__dmul_rn(rho, cs.y);
-      if (mot) compensate_point(x, y, m0, m1, m2, ccw);
-      const uint8_t inten = (uint8_t)((ent >> 18) & 0xffu);
-      const int q = base_f + i;
-      if (q < cap) {
-        fx[cbase + q] = x; fy[cbase + q] = y; fi[cbase + q] = inten; faz[cbase + q] = (uint16_t)az; frg[cbase + q] = (uint16_t)r;
-      }
-      const int pp = s_stpp[i];
-      if (pp >= 0 && base_p + pp < cap) {
-        const int qp = base_p + pp;
-        px[cbase + qp] = x; py[cbase + qp] = y; pi[cbase + qp] = inten; paz[cbase + qp] = (uint16_t)az; prg[cbase + qp] = (uint16_t)r;
-      }
-    }
-    base_f += tot_f;
-    base_p += tot_p;
-    // no barrier here: the next chunk's P1 touches only the row buffers / lists, and its barrier (1) orders P3's staging reads before the
-    // next staging writes
+    __syncwarp();   // every lane is done with sel before the next chunk reuses it
   }
+  __syncthreads();
   if (tid == 0) {
-    fcount[scan] = base_f < cap ? base_f : cap;
-    if (want_peaks) pcount[scan] = base_p < cap ? base_p : cap;
+    const int tot_f = s_chain[KF_WARPS - 1][0], tot_p = s_chain[KF_WARPS - 1][1];
+    fcount[scan] = tot_f < cap ? tot_f : cap;
+    if (want_peaks) pcount[scan] = tot_p < cap ? tot_p : cap;
   }
 }
 
@@ -542,13 +606,17 @@ int ensure_cs_table(tbv_ctx* ctx, int n_az) {
   if (F.cs_n_az == n_az) return TBV_OK;
   int rc = F.cs_table.reserve(n_az);
   if (rc) return rc;
+  if ((rc = F.th_table.reserve(n_az))) return rc;
   std::vector<double2> h(n_az);
+  std::vector<double> th(n_az);
   for (int b = 0; b < n_az; b++) {
     const double theta = (double(b + 1) / n_az) * 2. * M_PI;  // radar_filters.cpp:317 — glibc cos/sin on the host keeps x,y bit-exact
     h[b].x = std::cos(theta);
     h[b].y = std::sin(theta);
+    th[b] = std::atan2(h[b].y, h[b].x);                       // the azimuth as Compensate's atan2 sees it, in (-pi, pi] (utils.h:28-32)
   }
   TBV_CUDA(cudaMemcpyAsync(F.cs_table.p, h.data(), n_az * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  TBV_CUDA(cudaMemcpyAsync(F.th_table.p, th.data(), n_az * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   F.cs_n_az = n_az;
   return TBV_OK;
@@ -560,7 +628,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
   TBV_REQUIRE(n_range <= 8192, "n_range > 8192 is not supported");
   TBV_REQUIRE(n_az <= 4096, "n_az > 4096 is not supported");
-  TBV_REQUIRE(p->k_strongest >= 1 && p->k_strongest <= KF_CAP, "k_strongest must be in [1,128]");
+  TBV_REQUIRE(p->k_strongest >= 1 && p->k_strongest <= KF_MAX_K, "k_strongest must be in [1,128]");
   const int z_min = (int)p->z_min;  // float -> int as StructuredKStrongest's ctor does (radar_filters.h:86)
   TBV_REQUIRE(z_min >= 0 && z_min <= 255, "z_min must be in [0,255]");
   FilterState& F = ctx->filt;
@@ -575,21 +643,26 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   const int nvec_max = (15 + n_range + 15) >> 4;
   const int n_groups = (nvec_max + 1 + 31) / 32;
   const int rowbuf = n_groups * 512;
-  const size_t k1_smem = (size_t)KF_WARPS * rowbuf;
+  const size_t k1_smem = (size_t)KF_WARPS * 2 * rowbuf;    // two row buffers per warp
   const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
   const int min_range_bin = (int)std::ceil((double)p->min_distance / rr);   // radar_filters.cpp:315
   auto launch = [&](auto kern) -> int {
     const int rc2 = ensure_dyn_smem(ctx, kern, k1_smem);
     if (rc2) return rc2;
+    auto cl = [](DevCloud& c) { return KfCloud{c.x.p, c.y.p, c.inten.p, c.az.p, c.rg.p}; };
     kern<<<batch, KF_THREADS, k1_smem, ctx->stream>>>(polar_dev, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf, n_groups, polar_dev, buf_hi,
-                                                     min_range_bin, rr, F.cs_table.p, n_az * k, F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p,
-                                                     F.filtered.az.p, F.filtered.rg.p, F.filtered.count.p, F.peaks.x.p, F.peaks.y.p, F.peaks.inten.p,
-                                                     F.peaks.az.p, F.peaks.rg.p, F.peaks.count.p, mot_dev, ccw);
+                                                     min_range_bin, rr, F.cs_table.p, F.th_table.p, n_az * k, cl(F.filtered), F.filtered.count.p, cl(F.peaks),
+                                                     F.peaks.count.p, mot_dev, ccw);
     return TBV_OK;
   };
-  if (z_min > 128) rc = n_groups == 8 ? launch(k1_filter_fused<true, 8>) : n_groups == 7 ? launch(k1_filter_fused<true, 7>) : launch(k1_filter_fused<true, 0>);
-  else rc = n_groups == 8 ? launch(k1_filter_fused<false, 8>) : n_groups == 7 ? launch(k1_filter_fused<false, 7>) : launch(k1_filter_fused<false, 0>);
+  // compile-time variants: byte-compare form (z_min > 128), unrolled scan for the two dataset shapes, list capacity 64 (k <= 64) or 128
+  auto pick = [&](auto hi_tag) -> int {
+    constexpr bool H = decltype(hi_tag)::value;
+    if (k <= 64) return n_groups == 8 ? launch(k1_filter_fused<H, 8, 64>) : n_groups == 7 ? launch(k1_filter_fused<H, 7, 64>) : launch(k1_filter_fused<H, 0, 64>);
+    return n_groups == 8 ? launch(k1_filter_fused<H, 8, 128>) : n_groups == 7 ? launch(k1_filter_fused<H, 7, 128>) : launch(k1_filter_fused<H, 0, 128>);
+  };
+  rc = z_min > 128 ? pick(std::true_type{}) : pick(std::false_type{});
   if (rc) return rc;
   launched(ctx, "k1_filter_fused");
   TBV_CUDA(cudaGetLastError());

@@ -105,6 +105,7 @@ struct FilterState {  // device-resident result of the last k-strongest call
   int batch = 0, n_az = 0, n_range = 0, k = 0;
   DevBuf<uint8_t> polar;       // staging for host-input calls
   DevBuf<double2> cs_table;    // [n_az] (cos theta, sin theta) computed on the host with glibc
+  DevBuf<double> th_table;     // [n_az] atan2(sin theta, cos theta), host glibc: the azimuth as Compensate's atan2 sees it
   int cs_n_az = 0;
   DevCloud filtered, peaks;
 };
