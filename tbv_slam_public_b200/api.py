@@ -600,6 +600,20 @@ class PGOParams(C.Structure):
                 ("replace_cov_by_identity", C.c_int), ("loop_cauchy", C.c_double)]
 
 
+class PGOOptions(C.Structure):   # tbv_pgo_options: fields <= 0 -> the reference's values
+    _fields_ = [("max_num_iterations", C.c_int), ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double), ("max_cg_iterations", C.c_int), ("cg_rel_tol", C.c_double)]
+
+
+class PGOSummaryC(C.Structure):  # tbv_pgo_summary
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("iterations", C.c_int), ("successful_steps", C.c_int),
+                ("cg_iterations", C.c_int), ("termination", C.c_int), ("device_ms", C.c_float)]
+
+
+PGO_TERMINATION = ("max_num_iterations", "gradient_tolerance", "parameter_tolerance", "function_tolerance", "min_trust_region_radius",
+                   "failure: consecutive invalid steps")
+
+
 def default_sc_params(**kw) -> SCParams:
     """TBV-8 offline settings (tbv_slam/src/tbv_slam_offline.cpp:81-101): 40 x 120, 80 m, sum / 1000, 3 candidates, augmentations."""
     p = SCParams(40, 120, 80.0, 0.1, 10, 3, 0.05, 1, 1, 0.0, 0, 1000.0, 10.0)
@@ -632,6 +646,10 @@ def _sc_bind():
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.tbv_pgo_solve_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
                                      C.c_double, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.tbv_pgo_solve_damped.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                       C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.tbv_pgo_optimize.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PGOParams), C.c_int,
+                                   C.POINTER(PGOOptions), C.POINTER(PGOSummaryC)]
     L._sc_bound = True
     return L
 
@@ -801,23 +819,45 @@ def pgo_optimize(ctx: Context, nodes, ids, meas, params: PGOParams | None = None
 
 
 def pgo_solve_damped(ctx: Context, ids, H_diag, H_off, g, damping, fixed_node=0, max_iters=20000, rel_tol=1e-12):
-    """(H + diag(damping)) delta = -g with a caller-given damping vector [n, 6] (> 0), on the device.
-
-    tbv_pgo_solve_step derives its damping from the diagonal it is handed (clamp(diag, 1e-6, 1e32) / radius); called with radius = 1 on a
-    copy of H_diag whose diagonal e satisfies e + clamp(e, 1e-6, 1e32) = diag(H) + damping, it solves exactly the system asked for here
-    (off-diagonal entries of the blocks untouched).  An explicit damping argument in the C-ABI is the cleaner form and is planned with the
-    next kernel revision; this wrapper needs no kernel change."""
-    Hd = np.array(H_diag, np.float64).reshape(-1, 6, 6)
-    damping = np.asarray(damping, np.float64).reshape(-1, 6)
+    """(H + diag(damping)) delta = -g with a caller-given damping vector [n, 6] (> 0), on the device (tbv_pgo_solve_damped)."""
+    ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+    Hd = np.ascontiguousarray(H_diag, np.float64).reshape(-1, 36)
+    m = len(ids)
+    Ho = np.ascontiguousarray(H_off, np.float64).reshape(-1, 36)[:m]
+    if m == 0:
+        Ho = np.zeros((1, 36))
+    g = np.ascontiguousarray(g, np.float64).reshape(-1, 6)
     n = len(Hd)
+    damping = np.ascontiguousarray(damping, np.float64).reshape(-1, 6)
     if damping.shape != (n, 6) or not np.all(damping > 0):
         raise ValueError("damping: [n, 6], positive")
-    idx = np.arange(6)
-    total = Hd[:, idx, idx] + damping
-    e = np.where(total / 2.0 >= 1e-6, total / 2.0, total - 1e-6)
-    e = np.where(e > 1e32, total - 1e32, e)
-    Hd[:, idx, idx] = e
-    return pgo_solve_step(ctx, ids, Hd, H_off, g, fixed_node, 1.0, max_iters, rel_tol)
+    delta = np.zeros((n, 6)); it = C.c_int(0); rel = C.c_double(0)
+    _check(_sc_bind().tbv_pgo_solve_damped(ctx.h, n, m, _ptr(ids), _ptr(Hd), _ptr(Ho), _ptr(g), _ptr(damping), fixed_node, 1.0, int(max_iters),
+                                           float(rel_tol), _ptr(delta), C.byref(it), C.byref(rel)))
+    return delta, it.value, rel.value
+
+
+def pgo_optimize_device(ctx: Context, nodes, ids, meas, params: PGOParams | None = None, info=None, fixed_node=0, max_num_iterations=200,
+                        function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8, initial_radius=1e4, cg_rel_tol=1e-10,
+                        cg_max_iters=20000):
+    """CeresLeastSquares::Solve with the whole Levenberg-Marquardt loop on the device (tbv_pgo_optimize): the same iteration rules as
+    pgo_optimize_ceres below, which drives them from the host one device call at a time and is this call's checker.
+    Returns (nodes [n, 7], PGOSummary) — the summary also carries device_ms."""
+    params = params or default_pgo_params()
+    x = np.array(nodes, np.float64).reshape(-1, 7).copy()
+    ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+    meas = np.ascontiguousarray(meas, np.float64).reshape(-1, 7)
+    info = None if info is None else np.ascontiguousarray(info, np.float64).reshape(-1, 36)
+    opt = PGOOptions(int(max_num_iterations), float(function_tolerance), float(gradient_tolerance), float(parameter_tolerance), float(initial_radius),
+                     int(cg_max_iters), float(cg_rel_tol))
+    sc = PGOSummaryC()
+    _check(_sc_bind().tbv_pgo_optimize(ctx.h, len(x), _ptr(x), len(ids), _ptr(ids), _ptr(meas), _ptr(info), C.byref(params), fixed_node, C.byref(opt),
+                                       C.byref(sc)))
+    S = PGOSummary()
+    S.initial_cost, S.final_cost, S.iterations, S.successful_steps, S.cg_iterations = sc.initial_cost, sc.final_cost, sc.iterations, sc.successful_steps, sc.cg_iterations
+    S.termination = PGO_TERMINATION[sc.termination]
+    S.device_ms = float(sc.device_ms)
+    return x, S
 
 
 def pgo_optimize_ceres(ctx: Context, nodes, ids, meas, params: PGOParams | None = None, info=None, fixed_node=0, max_num_iterations=200,

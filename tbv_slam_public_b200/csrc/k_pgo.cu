@@ -218,323 +218,55 @@ pgo_cost(int n_con, const int* __restrict__ order, const double* __restrict__ re
   if (threadIdx.x == 0) *cost = s[0];
 }
 
-// ---- one Levenberg-Marquardt step of the pose graph on the device (first part) ------------------------------------------
+// ---- the linear solve of one Levenberg-Marquardt iteration on the device ----------------------------------------------------
 // Solves (H + D) delta = -g for the block-sparse normal equations tbv_pgo_assemble produces (H_diag: 6x6 per node, H_off: block
-// (begin, end) per constraint, symmetric), D = clamp(diag(H), 1e-6, 1e32) / radius — the system Ceres' LEVENBERG_MARQUARDT strategy
-// hands to SPARSE_NORMAL_CHOLESKY (ceresoptimizer.cpp:50-62) — by conjugate gradients with the 6x6 block-Jacobi preconditioner.
-// ONE persistent CTA: the graph is small (4.5 k nodes, 27 k unknowns, 1.4 MB of blocks: L2-resident), an iteration is a block-sparse
-// product plus two dot products, and keeping it in one CTA makes every reduction a fixed-shape tree (deterministic) with no grid sync.
-constexpr int PCG_THREADS = 1024;
+// (begin, end) per constraint, symmetric), D = the LM damping — the system Ceres' LEVENBERG_MARQUARDT strategy hands to
+// SPARSE_NORMAL_CHOLESKY (ceresoptimizer.cpp:50-62) — by conjugate gradients preconditioned with the ODOMETRY CHAIN: M = the block-tridiagonal
+// part of H + D (diagonal blocks + the blocks coupling nodes i and i + 1).  A pose graph is that chain plus a few hundred weak loop blocks,
+// so CG needs ~5 iterations where block-Jacobi needs ~1 500 (4 500 nodes, radius 1e4) and does not converge at all once the trust region
+// has grown (measured, profiles/r2a_pgo_*.json).  M is factorised and applied by BLOCK CYCLIC REDUCTION: level l eliminates every second
+// of the still active nodes (Schur complements of 6x6 blocks), ceil(log2 n) levels, every level fully parallel over its nodes — an exact
+// tridiagonal solve in 2 log2 n parallel steps instead of 2 n sequential ones.  One thread-block CLUSTER of 8 CTAs runs the whole solve:
+// vectors and blocks stream from L2 through 8 SMs, the levels and the CG reductions are separated by cluster barriers (~0.4 us), per-CTA
+// partial sums are exchanged through distributed shared memory and added in rank order by every CTA (same bits everywhere, so control flow
+// is uniform and the result does not depend on scheduling).  Storage per node: Dinv, ML, MR (36 doubles each) — every node is eliminated
+// exactly once.
+constexpr int PCR_CL = 8;            // portable cluster size
+constexpr int PCR_THREADS = 1024;
 
-__device__ __forceinline__ double pcg_block_sum(double v, double* s_w) {  // fixed tree: lanes, then the 32 warp totals in order
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();            // s_w may still be read from the previous reduction
-  if (lane == 0) s_w[warp] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < PCG_THREADS / 32; w++) t += s_w[w];
-  return t;
+__device__ __forceinline__ void m6_mul(const double* A, const double* B, double* O) {      // O = A B
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) {
+      double v = 0.0;
+      for (int k = 0; k < 6; k++) v += A[6 * a + k] * B[6 * k + b];
+      O[6 * a + b] = v;
+    }
 }
-
-__global__ void __launch_bounds__(PCG_THREADS, 1)
-pgo_pcg(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
-        const double* __restrict__ Ho, const double* __restrict__ g, double radius, int max_iters, double rel_tol, double* __restrict__ x,
-        double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q, double* __restrict__ Minv, double* __restrict__ Dg,
-        int* __restrict__ out_iters, double* __restrict__ out_rel) {
-  __shared__ double s_w[PCG_THREADS / 32];
-  const int tid = threadIdx.x;
-  // ---- damped diagonal blocks and their inverses (Cholesky of the SPD 6x6, then L^-T L^-1) ------------------------------------------
-  for (int i = tid; i < n; i += PCG_THREADS) {
-    double A[6][6], L[6][6], Li[6][6];
-    for (int a = 0; a < 6; a++)
-      for (int b = 0; b < 6; b++) A[a][b] = Hd[36 * (size_t)i + a * 6 + b];
-    bool ok = i != fixed_node;
-    for (int a = 0; a < 6; a++) {
-      const double d = fmin(fmax(A[a][a], 1e-6), 1e32) / radius;
-      Dg[6 * (size_t)i + a] = d;
-      A[a][a] += d;
+__device__ __forceinline__ void m6_mul_tn(const double* A, const double* B, double* O) {   // O = A^T B
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) {
+      double v = 0.0;
+      for (int k = 0; k < 6; k++) v += A[6 * k + a] * B[6 * k + b];
+      O[6 * a + b] = v;
     }
-    for (int a = 0; a < 6; a++)
-      for (int b = 0; b < 6; b++) { L[a][b] = 0.0; Li[a][b] = 0.0; }
-    for (int j = 0; j < 6 && ok; j++) {
-      double d = A[j][j];
-      for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
-      if (!(d > 0.0)) { ok = false; break; }
-      L[j][j] = sqrt(d);
-      for (int a = j + 1; a < 6; a++) {
-        double v = A[a][j];
-        for (int k = 0; k < j; k++) v -= L[a][k] * L[j][k];
-        L[a][j] = v / L[j][j];
-      }
-    }
-    if (ok) {
-      for (int c = 0; c < 6; c++) {            // Li = L^-1 by forward substitution on the identity
-        for (int a = 0; a < 6; a++) {
-          double v = (a == c) ? 1.0 : 0.0;
-          for (int k = 0; k < a; k++) v -= L[a][k] * Li[k][c];
-          Li[a][c] = v / L[a][a];
-        }
-      }
-    }
-    for (int a = 0; a < 6; a++)
-      for (int b = 0; b < 6; b++) {
-        double v = 0.0;
-        if (ok) for (int k = 0; k < 6; k++) v += Li[k][a] * Li[k][b];   // (L L^T)^-1 = L^-T L^-1
-        Minv[36 * (size_t)i + a * 6 + b] = v;
-      }
-  }
-  __syncthreads();
-  auto apply_Minv = [&](const double* v, double* o) {
-    for (int i = tid; i < n; i += PCG_THREADS) {
-      double t[6];
-      for (int a = 0; a < 6; a++) t[a] = v[6 * (size_t)i + a];
-      for (int a = 0; a < 6; a++) {
-        double acc = 0.0;
-        for (int b = 0; b < 6; b++) acc += Minv[36 * (size_t)i + a * 6 + b] * t[b];
-        o[6 * (size_t)i + a] = acc;
-      }
-    }
-  };
-  // q = (H + D) v: the node's own block, then its constraints in the order of `inc` (side 0: this node begins the constraint -> H_off v_end;
-  // side 1: it ends it -> H_off^T v_begin)
-  auto apply_A = [&](const double* v, double* o) {
-    for (int i = tid; i < n; i += PCG_THREADS) {
-      double acc[6] = {0, 0, 0, 0, 0, 0};
-      if (i != fixed_node) {
-        double t[6];
-        for (int a = 0; a < 6; a++) t[a] = v[6 * (size_t)i + a];
-        for (int a = 0; a < 6; a++) {
-          double s0 = Dg[6 * (size_t)i + a] * t[a];
-          for (int b = 0; b < 6; b++) s0 += Hd[36 * (size_t)i + a * 6 + b] * t[b];
-          acc[a] = s0;
-        }
-        for (int e = row[i]; e < row[i + 1]; e++) {
-          const int c = inc[e] >> 1, side = inc[e] & 1;
-          const int other = side ? ids[3 * c] : ids[3 * c + 1];
-          const double* B = Ho + 36 * (size_t)c;
-          double u[6];
-          for (int a = 0; a < 6; a++) u[a] = v[6 * (size_t)other + a];
-          if (side == 0) { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[a * 6 + b] * u[b]; }
-          else           { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[b * 6 + a] * u[b]; }
-        }
-      }
-      for (int a = 0; a < 6; a++) o[6 * (size_t)i + a] = acc[a];
-    }
-  };
-  auto dot = [&](const double* u, const double* v) {
-    double acc = 0.0;
-    for (int i = tid; i < n; i += PCG_THREADS)
-      for (int a = 0; a < 6; a++) acc += u[6 * (size_t)i + a] * v[6 * (size_t)i + a];
-    return pcg_block_sum(acc, s_w);
-  };
-  // ---- x = 0, r = b = -g (the fixed node's rows are zero), z = M^-1 r, p = z ---------------------------------------------------------
-  for (int i = tid; i < n; i += PCG_THREADS)
-    for (int a = 0; a < 6; a++) {
-      x[6 * (size_t)i + a] = 0.0;
-      r[6 * (size_t)i + a] = (i == fixed_node) ? 0.0 : -g[6 * (size_t)i + a];
-    }
-  __syncthreads();
-  apply_Minv(r, z);
-  for (int i = tid; i < n; i += PCG_THREADS)
-    for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a];   // own elements only: no barrier needed before
-  __syncthreads();
-  double rz = dot(r, z);
-  const double bnorm = sqrt(dot(r, r));
-  double rel = bnorm > 0.0 ? 1.0 : 0.0;
-  int it = 0;
-  while (it < max_iters && rel > rel_tol) {
-    apply_A(p, q);
-    __syncthreads();
-    const double pq = dot(p, q);
-    if (!(pq > 0.0)) break;                      // lost positive definiteness (never with D > 0): stop with what we have
-    const double alpha = rz / pq;
-    for (int i = tid; i < n; i += PCG_THREADS)
-      for (int a = 0; a < 6; a++) {
-        x[6 * (size_t)i + a] += alpha * p[6 * (size_t)i + a];
-        r[6 * (size_t)i + a] -= alpha * q[6 * (size_t)i + a];
-      }
-    apply_Minv(r, z);                            // own elements of r: written by this thread just above
-    __syncthreads();
-    const double rz_new = dot(r, z);
-    rel = sqrt(dot(r, r)) / bnorm;
-    const double beta = rz_new / rz;
-    rz = rz_new;
-    for (int i = tid; i < n; i += PCG_THREADS)
-      for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a] + beta * p[6 * (size_t)i + a];
-    __syncthreads();
-    it++;
-  }
-  if (tid == 0) { *out_iters = it; *out_rel = rel; }
 }
-
-// ---- the same solve on a thread-block CLUSTER (opt-in: TBV_PGO_CLUSTER=1; not yet run on a GPU — see DESIGN.md §7b) -----------------------
-// pgo_pcg is bound by one SM's latency chain (35 us per CG iteration measured at 600 nodes).  Here the nodes are split into contiguous ranges over
-// the PCGC_CL CTAs of one cluster, ONE ROW (node, component) PER THREAD, so an iteration is: a block-sparse product whose rows read 6-element
-// slices (blocks and vectors stream from L2, 1/PCGC_CL of them per SM), three cluster barriers (380 cycles each on this part) and two reductions
-// whose per-CTA partials are exchanged through distributed shared memory and summed in rank order by every CTA — the same bits everywhere, so
-// all CTAs take the same branch and the result does not depend on scheduling.  All 6 rows of a node live in one CTA: z = M^-1 r needs only a
-// __syncthreads.
-constexpr int PCGC_CL = 8;          // portable cluster size
-constexpr int PCGC_THREADS = 1024;
-
-__device__ __forceinline__ void pcgc_block_sum2(double& a, double& b, double (*s_w)[2]) {   // fixed tree per CTA; both values at once
-  for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) { s_w[warp][0] = a; s_w[warp][1] = b; }
-  __syncthreads();
-  double ta = 0.0, tb = 0.0;
-  for (int w = 0; w < PCGC_THREADS / 32; w++) { ta += s_w[w][0]; tb += s_w[w][1]; }
-  a = ta; b = tb;
+__device__ __forceinline__ void m6_submul(const double* A, const double* B, double* O) {    // O -= A B
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) {
+      double v = 0.0;
+      for (int k = 0; k < 6; k++) v += A[6 * a + k] * B[6 * k + b];
+      O[6 * a + b] -= v;
+    }
 }
-
-__global__ void __cluster_dims__(PCGC_CL, 1, 1) __launch_bounds__(PCGC_THREADS, 1)
-pgo_pcg_cluster(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
-                const double* __restrict__ Ho, const double* __restrict__ g, double radius, int max_iters, double rel_tol, double* __restrict__ x,
-                double* __restrict__ r, double* __restrict__ z, double* p, double* __restrict__ q, double* __restrict__ Minv, double* __restrict__ Dg,
-                int* __restrict__ out_iters, double* __restrict__ out_rel) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  __shared__ double s_w[PCGC_THREADS / 32][2];
-  __shared__ double s_part[2][2];                    // [0]: (p.q, -)   [1]: (r.z, r.r) — this CTA's partials, read by the whole cluster
-  const int tid = threadIdx.x, rank = (int)cluster.block_rank();
-  const int npc = (n + PCGC_CL - 1) / PCGC_CL;        // nodes per CTA
-  const int n0 = min(rank * npc, n), n1 = min(n0 + npc, n);
-  const int rows0 = 6 * n0, nrows = 6 * (n1 - n0);
-
-  // cluster-wide sums of (a, b): per-CTA fixed tree, then every CTA adds the PCGC_CL partials in rank order (DSMEM reads)
-  auto cluster_sum2 = [&](double& a, double& b, int slot) {
-    pcgc_block_sum2(a, b, s_w);
-    if (tid == 0) { s_part[slot][0] = a; s_part[slot][1] = b; }
-    cluster.sync();
-    double ta = 0.0, tb = 0.0;
-    for (int k = 0; k < PCGC_CL; k++) {
-      const double* remote = cluster.map_shared_rank(&s_part[slot][0], k);
-      ta += remote[0]; tb += remote[1];
+__device__ __forceinline__ void m6_submul_nt(const double* A, const double* B, double* O) { // O -= A B^T
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) {
+      double v = 0.0;
+      for (int k = 0; k < 6; k++) v += A[6 * a + k] * B[6 * b + k];
+      O[6 * a + b] -= v;
     }
-    a = ta; b = tb;
-  };
-
-  // ---- setup, one thread per owned node: damped diagonal block, its inverse, r = -g, z = M^-1 r, p = z, x = 0 --------------------------------------
-  for (int i = n0 + tid; i < n1; i += PCGC_THREADS) {
-    double A[6][6], L[6][6], Li[6][6];
-    for (int a = 0; a < 6; a++)
-      for (int b = 0; b < 6; b++) { A[a][b] = Hd[36 * (size_t)i + a * 6 + b]; L[a][b] = 0.0; Li[a][b] = 0.0; }
-    bool ok = i != fixed_node;
-    for (int a = 0; a < 6; a++) {
-      const double d = fmin(fmax(A[a][a], 1e-6), 1e32) / radius;
-      Dg[6 * (size_t)i + a] = d;
-      A[a][a] += d;
-    }
-    for (int j = 0; j < 6 && ok; j++) {
-      double d = A[j][j];
-      for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
-      if (!(d > 0.0)) { ok = false; break; }
-      L[j][j] = sqrt(d);
-      for (int a = j + 1; a < 6; a++) {
-        double v = A[a][j];
-        for (int k = 0; k < j; k++) v -= L[a][k] * L[j][k];
-        L[a][j] = v / L[j][j];
-      }
-    }
-    if (ok)
-      for (int c = 0; c < 6; c++)
-        for (int a = 0; a < 6; a++) {
-          double v = (a == c) ? 1.0 : 0.0;
-          for (int k = 0; k < a; k++) v -= L[a][k] * Li[k][c];
-          Li[a][c] = v / L[a][a];
-        }
-    double rr[6];
-    for (int a = 0; a < 6; a++) rr[a] = (i == fixed_node) ? 0.0 : -g[6 * (size_t)i + a];
-    for (int a = 0; a < 6; a++) {
-      double zz = 0.0;
-      for (int b = 0; b < 6; b++) {
-        double v = 0.0;
-        if (ok) for (int k = 0; k < 6; k++) v += Li[k][a] * Li[k][b];
-        Minv[36 * (size_t)i + a * 6 + b] = v;
-        zz += v * rr[b];
-      }
-      x[6 * (size_t)i + a] = 0.0;
-      r[6 * (size_t)i + a] = rr[a];
-      z[6 * (size_t)i + a] = zz;
-      p[6 * (size_t)i + a] = zz;
-    }
-  }
-  __syncthreads();
-  double rz = 0.0, bb = 0.0;
-  for (int lr = tid; lr < nrows; lr += PCGC_THREADS) { rz += r[rows0 + lr] * z[rows0 + lr]; bb += r[rows0 + lr] * r[rows0 + lr]; }
-  cluster_sum2(rz, bb, 1);                           // also publishes p to the cluster (barrier.cluster release / acquire)
-  const double bnorm = sqrt(bb);
-  double rel = bnorm > 0.0 ? 1.0 : 0.0;
-  int it = 0;
-  while (it < max_iters && rel > rel_tol) {
-    // q = (H + D) p, own rows; p.q
-    double pq = 0.0, unused = 0.0;
-    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
-      const int R = rows0 + lr, i = R / 6, a = R - 6 * i;
-      double acc = 0.0;
-      if (i != fixed_node) {
-        const double* Hr = Hd + 36 * (size_t)i + 6 * a;
-        const double* pi = p + 6 * (size_t)i;
-        acc = Dg[R] * pi[a];
-        for (int b = 0; b < 6; b++) acc += Hr[b] * pi[b];
-        for (int e = row[i]; e < row[i + 1]; e++) {
-          const int c = inc[e] >> 1, side = inc[e] & 1;
-          const int other = side ? ids[3 * c] : ids[3 * c + 1];
-          const double* B = Ho + 36 * (size_t)c;
-          const double* u = p + 6 * (size_t)other;
-          // the other node may belong to another CTA: read its slice of p from L2 (the cluster barrier orders the writes; no stale L1 line)
-          if (side == 0) { for (int b = 0; b < 6; b++) acc += B[6 * a + b] * __ldcg(u + b); }
-          else           { for (int b = 0; b < 6; b++) acc += B[6 * b + a] * __ldcg(u + b); }
-        }
-      }
-      q[R] = acc;
-      pq += p[R] * acc;
-    }
-    cluster_sum2(pq, unused, 0);
-    if (!(pq > 0.0)) break;                          // same value in every CTA: the whole cluster leaves together
-    const double alpha = rz / pq;
-    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
-      const int R = rows0 + lr;
-      x[R] += alpha * p[R];
-      r[R] -= alpha * q[R];
-    }
-    __syncthreads();                                 // z needs the node's six residual rows (same CTA)
-    double rz_new = 0.0, rr_new = 0.0;
-    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
-      const int R = rows0 + lr, i = R / 6, a = R - 6 * i;
-      const double* Mr = Minv + 36 * (size_t)i + 6 * a;
-      const double* ri = r + 6 * (size_t)i;
-      double acc = 0.0;
-      for (int b = 0; b < 6; b++) acc += Mr[b] * ri[b];
-      z[R] = acc;
-      rz_new += ri[a] * acc;
-      rr_new += ri[a] * ri[a];
-    }
-    cluster_sum2(rz_new, rr_new, 1);
-    rel = sqrt(rr_new) / bnorm;
-    const double beta = rz_new / rz;
-    rz = rz_new;
-    for (int lr = tid; lr < nrows; lr += PCGC_THREADS) {
-      const int R = rows0 + lr;
-      p[R] = z[R] + beta * p[R];
-    }
-    cluster.sync();                                  // the next product reads other CTAs' rows of p
-    it++;
-  }
-  cluster.sync();                                    // no CTA may exit while another still reads its partials through DSMEM
-  if (rank == 0 && tid == 0) { *out_iters = it; *out_rel = rel; }
 }
-
-// ---- the same solve with the ODOMETRY CHAIN as preconditioner (opt-in: TBV_PGO_CHAIN=1; not yet run on a GPU — see DESIGN.md §7b) ----------------
-// M = block-tridiagonal part of (H + D): diagonal blocks + the blocks coupling nodes i and i + 1 (chain[i] = A[i+1][i], summed on the host from the
-// constraints between consecutive nodes), factorised once as M = L S L^T (block Thomas: S_0 = A_00, W_i = chain[i-1] S_{i-1}^-1,
-// S_i = A_ii - W_i chain[i-1]^T).  A pose graph is that chain plus a few weak loop blocks: CG needs ~5 iterations where block-Jacobi needs ~1100
-// (measured with the numpy prototype tests/tools/pgo_chain_prototype.py, which restates this kernel operation by operation and is its checker).
-// First version: factorisation and the two sweeps of every application run on ONE thread (dependent 6x6 recurrences; the blocks stream from L2);
-// the product and the block-diagonal solve use the whole CTA.  Next: 6 lanes per recurrence, then parallel cyclic reduction.
-__device__ void pcgc_inverse_spd6(const double* S, double* Sinv, bool* ok) {   // Cholesky S = L L^T, then S^-1 = L^-T L^-1
+__device__ void m6_inverse_spd(const double* S, double* Sinv, bool* ok) {   // Cholesky S = L L^T, then S^-1 = L^-T L^-1
   double L[6][6], Li[6][6];
   for (int a = 0; a < 6; a++)
     for (int b = 0; b < 6; b++) { L[a][b] = 0.0; Li[a][b] = 0.0; }
@@ -564,157 +296,383 @@ __device__ void pcgc_inverse_spd6(const double* S, double* Sinv, bool* ok) {   /
     }
 }
 
-__global__ void __launch_bounds__(PCG_THREADS, 1)
-pgo_pcg_chain(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
-              const double* __restrict__ Ho, const double* __restrict__ chain, const double* __restrict__ g, double radius, int max_iters, double rel_tol,
-              double* __restrict__ x, double* r, double* z, double* __restrict__ p, double* __restrict__ q, double* Sinv, double* Wb, double* __restrict__ Dg,
-              double* y, int* __restrict__ out_iters, double* __restrict__ out_rel) {
-  __shared__ double s_w[PCG_THREADS / 32];
-  __shared__ int s_bad;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_bad = 0;
-  for (int i = tid; i < n; i += PCG_THREADS)
-    for (int a = 0; a < 6; a++) Dg[6 * (size_t)i + a] = fmin(fmax(Hd[36 * (size_t)i + 7 * a], 1e-6), 1e32) / radius;
-  __syncthreads();
-  // ---- block Thomas factorisation of the chain (sequential in i) -----------------------------------------------------------------------------------
-  if (tid == 0) {
-    double Sp[36];                                        // S_{i-1}^-1
-    for (int i = 0; i < n; i++) {
-      double S[36];
-      for (int e = 0; e < 36; e++) S[e] = (i == fixed_node) ? ((e % 7 == 0) ? 1.0 : 0.0) : Hd[36 * (size_t)i + e];
-      if (i != fixed_node)
-        for (int a = 0; a < 6; a++) S[7 * a] += Dg[6 * (size_t)i + a];
-      if (i > 0) {
-        const double* C = chain + 36 * (size_t)(i - 1);   // A[i][i-1]; zero on both sides of the fixed node (host)
-        double W[36];
-        for (int a = 0; a < 6; a++)
-          for (int b = 0; b < 6; b++) {
-            double v = 0.0;
-            for (int k = 0; k < 6; k++) v += C[6 * a + k] * Sp[6 * k + b];
-            W[6 * a + b] = v;
-          }
-        for (int e = 0; e < 36; e++) Wb[36 * (size_t)(i - 1) + e] = W[e];
-        for (int a = 0; a < 6; a++)
-          for (int b = 0; b < 6; b++) {
-            double v = 0.0;
-            for (int k = 0; k < 6; k++) v += W[6 * a + k] * C[6 * b + k];
-            S[6 * a + b] -= v;
-          }
-      }
-      bool ok;
-      pcgc_inverse_spd6(S, Sp, &ok);
-      if (!ok) s_bad = 1;
-      for (int e = 0; e < 36; e++) Sinv[36 * (size_t)i + e] = Sp[e];
-    }
+// The factorisation runs as ordinary grids, one thread per node of a level with its 6x6 blocks in registers (128 threads per CTA: no
+// spills; inside the 1024-thread cluster kernel the same code is limited to 64 registers and ran 15x slower): 2 launches per level.
+constexpr int PCRF_THREADS = 128;
+
+// the damped chain: Dm_i = H_ii + D_i (identity for the fixed node), Cc_i = A[i+1][i] = sum of the blocks between nodes i and i+1
+__global__ void __launch_bounds__(PCRF_THREADS)
+pgo_cr_setup(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
+             const double* __restrict__ Ho, const double* __restrict__ damping, double radius, double* __restrict__ Dm, double* __restrict__ Cc,
+             double* __restrict__ Dg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double D[36];
+  for (int e = 0; e < 36; e++) D[e] = (i == fixed_node) ? ((e % 7 == 0) ? 1.0 : 0.0) : Hd[36 * (size_t)i + e];
+  for (int a = 0; a < 6; a++) {
+    const double d = damping ? damping[6 * (size_t)i + a] : fmin(fmax(Hd[36 * (size_t)i + 7 * a], 1e-6), 1e32) / radius;
+    Dg[6 * (size_t)i + a] = d;
+    if (i != fixed_node) D[7 * a] += d;
   }
-  __syncthreads();
-  // z = M^-1 v: forward sweep (thread 0), block-diagonal solve (all threads), backward sweep (thread 0)
+  for (int e = 0; e < 36; e++) Dm[36 * (size_t)i + e] = D[e];
+  double C[36];
+  for (int e = 0; e < 36; e++) C[e] = 0.0;
+  if (i + 1 < n && i != fixed_node && i + 1 != fixed_node)      // no coupling across the fixed node
+    for (int e = row[i]; e < row[i + 1]; e++) {
+      const int c = inc[e] >> 1, side = inc[e] & 1;
+      const int other = side ? ids[3 * c] : ids[3 * c + 1];
+      if (other != i + 1) continue;
+      const double* B = Ho + 36 * (size_t)c;                    // block (begin, end)
+      // side 0: i begins the constraint, B = A[i][i+1] -> A[i+1][i] = B^T; side 1: i ends it, B = A[i+1][i]
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) C[6 * a + b] += side ? B[6 * a + b] : B[6 * b + a];
+    }
+  for (int e = 0; e < 36; e++) Cc[36 * (size_t)i + e] = C[e];
+}
+// block cyclic reduction, stride s: active nodes = multiples of s; odd multiples are eliminated.
+// (A) per eliminated node o: Dinv, ML = A[e1][o] Dinv, MR = A[e2][o] Dinv      (n_odd == 0 and s >= n: node 0 alone, Dinv only)
+__global__ void __launch_bounds__(PCRF_THREADS)
+pgo_cr_eliminate(int n, int s, int n_odd, const double* __restrict__ Dm, const double* __restrict__ Cc, double* __restrict__ Dinv, double* __restrict__ ML,
+                 double* __restrict__ MR, int* __restrict__ bad) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_odd == 0) {                                    // the last active node
+    if (j != 0) return;
+    double D[36], Di[36];
+    for (int e = 0; e < 36; e++) D[e] = Dm[e];
+    bool ok;
+    m6_inverse_spd(D, Di, &ok);
+    if (!ok) *bad = 1;
+    for (int e = 0; e < 36; e++) Dinv[e] = Di[e];
+    return;
+  }
+  if (j >= n_odd) return;
+  const int o = s * (2 * j + 1), e1 = o - s, e2 = o + s;
+  double D[36], Di[36], C[36], M[36];
+  for (int e = 0; e < 36; e++) D[e] = Dm[36 * (size_t)o + e];
+  bool ok;
+  m6_inverse_spd(D, Di, &ok);
+  if (!ok) *bad = 1;
+  for (int e = 0; e < 36; e++) Dinv[36 * (size_t)o + e] = Di[e];
+  for (int e = 0; e < 36; e++) C[e] = Cc[36 * (size_t)e1 + e];     // A[o][e1]
+  m6_mul_tn(C, Di, M);                                              // A[e1][o] Dinv = C^T Dinv
+  for (int e = 0; e < 36; e++) ML[36 * (size_t)o + e] = M[e];
+  if (e2 < n) {
+    for (int e = 0; e < 36; e++) C[e] = Cc[36 * (size_t)o + e];    // A[e2][o]
+    m6_mul(C, Di, M);
+  } else {
+    for (int e = 0; e < 36; e++) M[e] = 0.0;
+  }
+  for (int e = 0; e < 36; e++) MR[36 * (size_t)o + e] = M[e];
+}
+// (B) per surviving node e: Schur complement and the new coupling to e + 2s
+__global__ void __launch_bounds__(PCRF_THREADS)
+pgo_cr_update(int n, int s, int n_even, double* __restrict__ Dm, double* __restrict__ Cc, const double* __restrict__ ML, const double* __restrict__ MR) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_even) return;
+  const int e0 = 2 * s * j, ol = e0 - s, orr = e0 + s;
+  if (ol < 0 && orr >= n) return;
+  double D[36], M[36], C[36];
+  for (int e = 0; e < 36; e++) D[e] = Dm[36 * (size_t)e0 + e];
+  if (ol >= 0) {                                       // D -= A[e][ol] Dinv A[ol][e] = MR_ol * Cc[ol]^T
+    for (int e = 0; e < 36; e++) { M[e] = MR[36 * (size_t)ol + e]; C[e] = Cc[36 * (size_t)ol + e]; }
+    m6_submul_nt(M, C, D);
+  }
+  if (orr < n) {                                       // D -= A[e][or] Dinv A[or][e] = ML_or * Cc[e]
+    for (int e = 0; e < 36; e++) { M[e] = ML[36 * (size_t)orr + e]; C[e] = Cc[36 * (size_t)e0 + e]; }
+    m6_submul(M, C, D);
+    double Cn[36];
+    for (int e = 0; e < 36; e++) Cn[e] = 0.0;
+    if (e0 + 2 * s < n) {                              // A'[e + 2s][e] = -A[e + 2s][or] Dinv A[or][e] = -MR_or * Cc[e]
+      for (int e = 0; e < 36; e++) M[e] = MR[36 * (size_t)orr + e];
+      m6_submul(M, C, Cn);
+    }
+    for (int e = 0; e < 36; e++) Cc[36 * (size_t)e0 + e] = Cn[e];
+  }
+  for (int e = 0; e < 36; e++) Dm[36 * (size_t)e0 + e] = D[e];
+}
+
+__global__ void __cluster_dims__(PCR_CL, 1, 1) __launch_bounds__(PCR_THREADS, 1)
+pgo_pcg_cr(int n, int fixed_node, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
+           const double* __restrict__ Ho, const double* __restrict__ g, int max_iters, double rel_tol, double* __restrict__ x, double* r, double* z,
+           double* p, double* __restrict__ q, double* u, const double* __restrict__ Dinv, const double* __restrict__ ML, const double* __restrict__ MR,
+           const double* __restrict__ Dg, const int* __restrict__ bad, int* __restrict__ out_iters, double* __restrict__ out_rel) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double s_w[PCR_THREADS / 32][2];
+  __shared__ double s_part[2][2];                    // [0]: (p.q, -)   [1]: (r.z, r.r) — this CTA's partials, read by the whole cluster
+  const int tid = threadIdx.x, rank = (int)cluster.block_rank();
+  const int gt = rank * PCR_THREADS + tid, GT = PCR_CL * PCR_THREADS;
+  const int npc = (n + PCR_CL - 1) / PCR_CL;          // nodes per CTA for the row-parallel CG work
+  const int n0 = min(rank * npc, n), n1 = min(n0 + npc, n);
+  const int rows0 = 6 * n0, nrows = 6 * (n1 - n0);
+
+  auto block_sum2 = [&](double& a, double& b) {   // fixed tree per CTA; both values at once
+    for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+    const int warp = tid >> 5, lane = tid & 31;
+    __syncthreads();
+    if (lane == 0) { s_w[warp][0] = a; s_w[warp][1] = b; }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < PCR_THREADS / 32; w++) { ta += s_w[w][0]; tb += s_w[w][1]; }
+    a = ta; b = tb;
+  };
+  // cluster-wide sums of (a, b): per-CTA fixed tree, then every CTA adds the PCR_CL partials in rank order (DSMEM reads)
+  auto cluster_sum2 = [&](double& a, double& b, int slot) {
+    block_sum2(a, b);
+    if (tid == 0) { s_part[slot][0] = a; s_part[slot][1] = b; }
+    cluster.sync();
+    double ta = 0.0, tb = 0.0;
+    for (int k = 0; k < PCR_CL; k++) {
+      const double* remote = cluster.map_shared_rank(&s_part[slot][0], k);
+      ta += remote[0]; tb += remote[1];
+    }
+    a = ta; b = tb;
+  };
+
+  // z = M^-1 v by cyclic reduction: forward over the levels (right-hand sides of the surviving nodes), node 0, backward (eliminated nodes).
+  // One (node, component) row per thread; u is the working right-hand side.  Reads of other CTAs' rows go to L2 (__ldcg).
   auto apply_chain = [&](const double* v, double* o) {
-    if (tid == 0) {
-      double prev[6], cur[6];
-      for (int a = 0; a < 6; a++) { prev[a] = v[a]; y[a] = prev[a]; }
-      for (int i = 1; i < n; i++) {
-        const double* W = Wb + 36 * (size_t)(i - 1);
-        for (int a = 0; a < 6; a++) {
-          double acc = v[6 * (size_t)i + a];
-          for (int b = 0; b < 6; b++) acc -= W[6 * a + b] * prev[b];
-          cur[a] = acc;
+    for (int R = gt; R < 6 * n; R += GT) u[R] = __ldcg(v + R);
+    cluster.sync();
+    for (int s = 1; s < n; s <<= 1) {
+      const int n_even = (n - 1) / (2 * s) + 1;
+      for (int t = gt; t < 6 * n_even; t += GT) {
+        const int j = t / 6, a = t - 6 * j, e0 = 2 * s * j, ol = e0 - s, orr = e0 + s;
+        double acc = __ldcg(u + 6 * (size_t)e0 + a);
+        if (ol >= 0) {
+          const double* M = MR + 36 * (size_t)ol + 6 * a;
+          const double* w = u + 6 * (size_t)ol;
+          for (int b = 0; b < 6; b++) acc -= M[b] * __ldcg(w + b);
         }
-        for (int a = 0; a < 6; a++) { prev[a] = cur[a]; y[6 * (size_t)i + a] = cur[a]; }
+        if (orr < n) {
+          const double* M = ML + 36 * (size_t)orr + 6 * a;
+          const double* w = u + 6 * (size_t)orr;
+          for (int b = 0; b < 6; b++) acc -= M[b] * __ldcg(w + b);
+        }
+        u[6 * (size_t)e0 + a] = acc;
       }
+      cluster.sync();
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += PCG_THREADS)
-      for (int a = 0; a < 6; a++) {
+    if (gt < 6) {
+      double acc = 0.0;
+      for (int b = 0; b < 6; b++) acc += Dinv[6 * gt + b] * __ldcg(u + b);
+      o[gt] = acc;
+    }
+    cluster.sync();
+    int s_top = 1;
+    while (s_top * 2 < n) s_top <<= 1;
+    for (int s = s_top; s >= 1; s >>= 1) {
+      if (s >= n) continue;
+      const int n_odd = (n - 1 >= s) ? (n - 1 - s) / (2 * s) + 1 : 0;
+      for (int t = gt; t < 6 * n_odd; t += GT) {
+        const int j = t / 6, a = t - 6 * j, od = s * (2 * j + 1), e1 = od - s, e2 = od + s;
+        const double* Di = Dinv + 36 * (size_t)od + 6 * a;
+        const double* w = u + 6 * (size_t)od;
         double acc = 0.0;
-        for (int b = 0; b < 6; b++) acc += Sinv[36 * (size_t)i + 6 * a + b] * y[6 * (size_t)i + b];
-        o[6 * (size_t)i + a] = acc;
-      }
-    __syncthreads();
-    if (tid == 0) {
-      double nxt[6], cur[6];
-      for (int a = 0; a < 6; a++) nxt[a] = o[6 * (size_t)(n - 1) + a];
-      for (int i = n - 2; i >= 0; i--) {
-        const double* W = Wb + 36 * (size_t)i;            // W_{i+1}: o_i -= W_{i+1}^T o_{i+1}
-        for (int a = 0; a < 6; a++) {
-          double acc = o[6 * (size_t)i + a];
-          for (int b = 0; b < 6; b++) acc -= W[6 * b + a] * nxt[b];
-          cur[a] = acc;
+        for (int b = 0; b < 6; b++) acc += Di[b] * __ldcg(w + b);
+        {                                              // - (ML^T z_e1)[a]
+          const double* M = ML + 36 * (size_t)od;
+          const double* zz = o + 6 * (size_t)e1;
+          for (int b = 0; b < 6; b++) acc -= M[6 * b + a] * __ldcg(zz + b);
         }
-        for (int a = 0; a < 6; a++) { nxt[a] = cur[a]; o[6 * (size_t)i + a] = cur[a]; }
-      }
-      if (fixed_node >= 0 && fixed_node < n)
-        for (int a = 0; a < 6; a++) o[6 * (size_t)fixed_node + a] = 0.0;
-    }
-    __syncthreads();
-  };
-  auto apply_A = [&](const double* v, double* o) {        // as in pgo_pcg
-    for (int i = tid; i < n; i += PCG_THREADS) {
-      double acc[6] = {0, 0, 0, 0, 0, 0};
-      if (i != fixed_node) {
-        double t[6];
-        for (int a = 0; a < 6; a++) t[a] = v[6 * (size_t)i + a];
-        for (int a = 0; a < 6; a++) {
-          double s0 = Dg[6 * (size_t)i + a] * t[a];
-          for (int b = 0; b < 6; b++) s0 += Hd[36 * (size_t)i + a * 6 + b] * t[b];
-          acc[a] = s0;
+        if (e2 < n) {                                  // - (MR^T z_e2)[a]
+          const double* M = MR + 36 * (size_t)od;
+          const double* zz = o + 6 * (size_t)e2;
+          for (int b = 0; b < 6; b++) acc -= M[6 * b + a] * __ldcg(zz + b);
         }
-        for (int e = row[i]; e < row[i + 1]; e++) {
-          const int c = inc[e] >> 1, side = inc[e] & 1;
-          const int other = side ? ids[3 * c] : ids[3 * c + 1];
-          const double* B = Ho + 36 * (size_t)c;
-          double u[6];
-          for (int a = 0; a < 6; a++) u[a] = v[6 * (size_t)other + a];
-          if (side == 0) { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[a * 6 + b] * u[b]; }
-          else           { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) acc[a] += B[b * 6 + a] * u[b]; }
-        }
+        o[6 * (size_t)od + a] = acc;
       }
-      for (int a = 0; a < 6; a++) o[6 * (size_t)i + a] = acc[a];
+      cluster.sync();
     }
   };
-  auto dot = [&](const double* u, const double* v) {
-    double acc = 0.0;
-    for (int i = tid; i < n; i += PCG_THREADS)
-      for (int a = 0; a < 6; a++) acc += u[6 * (size_t)i + a] * v[6 * (size_t)i + a];
-    return pcg_block_sum(acc, s_w);
-  };
-  for (int i = tid; i < n; i += PCG_THREADS)
-    for (int a = 0; a < 6; a++) {
-      x[6 * (size_t)i + a] = 0.0;
-      r[6 * (size_t)i + a] = (i == fixed_node) ? 0.0 : -g[6 * (size_t)i + a];
-    }
-  __syncthreads();
+
+  // ---- x = 0, r = b = -g (the fixed node's rows are zero), z = M^-1 r, p = z ---------------------------------------------------------------------
+  for (int lr = tid; lr < nrows; lr += PCR_THREADS) {
+    const int R = rows0 + lr, i = R / 6;
+    x[R] = 0.0;
+    r[R] = (i == fixed_node) ? 0.0 : -g[R];
+  }
+  cluster.sync();
   apply_chain(r, z);
-  for (int i = tid; i < n; i += PCG_THREADS)
-    for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a];
-  __syncthreads();
-  double rz = dot(r, z);
-  const double bnorm = sqrt(dot(r, r));
+  double rz = 0.0, bb = 0.0;
+  for (int lr = tid; lr < nrows; lr += PCR_THREADS) {
+    const int R = rows0 + lr;
+    const double zr = __ldcg(z + R);
+    p[R] = zr;
+    rz += r[R] * zr; bb += r[R] * r[R];
+  }
+  cluster_sum2(rz, bb, 1);                           // also publishes p to the cluster (barrier.cluster release / acquire)
+  const double bnorm = sqrt(bb);
   double rel = bnorm > 0.0 ? 1.0 : 0.0;
   int it = 0;
   while (it < max_iters && rel > rel_tol) {
-    apply_A(p, q);
-    __syncthreads();
-    const double pq = dot(p, q);
-    if (!(pq > 0.0)) break;
-    const double alpha = rz / pq;
-    for (int i = tid; i < n; i += PCG_THREADS)
-      for (int a = 0; a < 6; a++) {
-        x[6 * (size_t)i + a] += alpha * p[6 * (size_t)i + a];
-        r[6 * (size_t)i + a] -= alpha * q[6 * (size_t)i + a];
+    // q = (H + D) p, own rows; p.q
+    double pq = 0.0, unused = 0.0;
+    for (int lr = tid; lr < nrows; lr += PCR_THREADS) {
+      const int R = rows0 + lr, i = R / 6, a = R - 6 * i;
+      double acc = 0.0;
+      if (i != fixed_node) {
+        const double* Hr = Hd + 36 * (size_t)i + 6 * a;
+        const double* pi = p + 6 * (size_t)i;
+        acc = Dg[R] * pi[a];
+        for (int b = 0; b < 6; b++) acc += Hr[b] * pi[b];
+        for (int e = row[i]; e < row[i + 1]; e++) {
+          const int c = inc[e] >> 1, side = inc[e] & 1;
+          const int other = side ? ids[3 * c] : ids[3 * c + 1];
+          if (other == fixed_node) continue;          // the fixed node's column is not part of the system
+          const double* B = Ho + 36 * (size_t)c;
+          const double* uu = p + 6 * (size_t)other;
+          // the other node may belong to another CTA: read its slice of p from L2 (the cluster barrier orders the writes; no stale L1 line)
+          if (side == 0) { for (int b = 0; b < 6; b++) acc += B[6 * a + b] * __ldcg(uu + b); }
+          else           { for (int b = 0; b < 6; b++) acc += B[6 * b + a] * __ldcg(uu + b); }
+        }
       }
-    __syncthreads();                                     // the sweeps read every row of r
+      q[R] = acc;
+      pq += p[R] * acc;
+    }
+    cluster_sum2(pq, unused, 0);
+    if (!(pq > 0.0)) break;                          // same value in every CTA: the whole cluster leaves together
+    const double alpha = rz / pq;
+    for (int lr = tid; lr < nrows; lr += PCR_THREADS) {
+      const int R = rows0 + lr;
+      x[R] += alpha * p[R];
+      r[R] -= alpha * q[R];
+    }
+    cluster.sync();                                  // the preconditioner reads every row of r
     apply_chain(r, z);
-    const double rz_new = dot(r, z);
-    rel = sqrt(dot(r, r)) / bnorm;
+    double rz_new = 0.0, rr_new = 0.0;
+    for (int lr = tid; lr < nrows; lr += PCR_THREADS) {
+      const int R = rows0 + lr;
+      rz_new += r[R] * __ldcg(z + R);
+      rr_new += r[R] * r[R];
+    }
+    cluster_sum2(rz_new, rr_new, 1);
+    rel = sqrt(rr_new) / bnorm;
     const double beta = rz_new / rz;
     rz = rz_new;
-    for (int i = tid; i < n; i += PCG_THREADS)
-      for (int a = 0; a < 6; a++) p[6 * (size_t)i + a] = z[6 * (size_t)i + a] + beta * p[6 * (size_t)i + a];
-    __syncthreads();
+    for (int lr = tid; lr < nrows; lr += PCR_THREADS) {
+      const int R = rows0 + lr;
+      p[R] = __ldcg(z + R) + beta * p[R];
+    }
+    cluster.sync();                                  // the next product reads other CTAs' rows of p
     it++;
   }
-  if (tid == 0) { *out_iters = s_bad ? -it - 1 : it; *out_rel = rel; }   // negative: a chain pivot block was not positive definite
+  cluster.sync();                                    // no CTA may exit while another still reads its partials through DSMEM
+  // a pivot block of the chain that was not positive definite (factorisation kernels) is reported through the sign of the iteration count
+  if (rank == 0 && tid == 0) { *out_iters = *bad ? -it - 1 : it; *out_rel = rel; }
+}
+
+// ---- trust-region bookkeeping of tbv_pgo_optimize on the device (the vectors never leave HBM between LM iterations) ------------------------------
+// x (+) delta of a node: p += dp; q = exp(dr) * q (ceres::EigenQuaternionParameterization::Plus, q = x y z w)
+__device__ __forceinline__ void pgo_plus_node(const double* nd, const double* d, double* o) {
+  o[0] = nd[0] + d[0]; o[1] = nd[1] + d[1]; o[2] = nd[2] + d[2];
+  const double nrm = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+  const double k = nrm > 0.0 ? sin(nrm) / nrm : 1.0;
+  const double dv[3] = {d[3] * k, d[4] * k, d[5] * k}, dw = cos(nrm);
+  const double* v = nd + 3;
+  const double w = nd[6];
+  o[6] = dw * w - (dv[0] * v[0] + dv[1] * v[1] + dv[2] * v[2]);
+  o[3] = dw * v[0] + w * dv[0] + (dv[1] * v[2] - dv[2] * v[1]);
+  o[4] = dw * v[1] + w * dv[1] + (dv[2] * v[0] - dv[0] * v[2]);
+  o[5] = dw * v[2] + w * dv[2] + (dv[0] * v[1] - dv[1] * v[0]);
+}
+
+constexpr int PGS_THREADS = 1024;
+__device__ __forceinline__ double pgs_block_sum(double v, double* s_w) {   // fixed tree: lanes, then the warp totals in order (deterministic)
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < PGS_THREADS / 32; w++) t += s_w[w];
+  return t;
+}
+__device__ __forceinline__ double pgs_block_max(double v, double* s_w) {
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < PGS_THREADS / 32; w++) t = fmax(t, s_w[w]);
+  return t;
+}
+
+// Jacobi scaling s = 1 / (1 + sqrt(diag H)) of LevenbergMarquardtStrategy (fixed at iteration 0)
+__global__ void pgo_scale(int n, const double* __restrict__ Hd, double* __restrict__ scale) {
+  const int R = blockIdx.x * blockDim.x + threadIdx.x;
+  if (R >= 6 * n) return;
+  const int i = R / 6, a = R - 6 * i;
+  scale[R] = 1.0 / (1.0 + sqrt(fmax(Hd[36 * (size_t)i + 7 * a], 0.0)));
+}
+// LM diagonal clamp(diag(S H S), 1e-6, 1e32) — recomputed after a successful step, reused after a rejected one — and the damping
+// (H + diag / (radius s^2)) delta = -g that is equivalent to (S H S + diag / radius) y = -S g, delta = S y
+__global__ void pgo_damping(int n, int fixed_node, const double* __restrict__ Hd, const double* __restrict__ scale, int reuse, double radius,
+                            double* __restrict__ lm_diag, double* __restrict__ damping) {
+  const int R = blockIdx.x * blockDim.x + threadIdx.x;
+  if (R >= 6 * n) return;
+  const int i = R / 6, a = R - 6 * i;
+  const double s2 = scale[R] * scale[R];
+  double d = lm_diag[R];
+  if (!reuse) { d = fmin(fmax(Hd[36 * (size_t)i + 7 * a] * s2, 1e-6), 1e32); lm_diag[R] = d; }
+  damping[R] = (i == fixed_node) ? 1.0 : d / (radius * s2);
+}
+// candidate = x (+) delta; stats[0] = model change -delta.(g + H delta / 2), [1] = |x - candidate|^2, [2] = |candidate|^2, [3] = 1 if delta is finite
+__global__ void __launch_bounds__(PGS_THREADS, 1)
+pgo_step(int n, const int* __restrict__ ids, const int* __restrict__ row, const int* __restrict__ inc, const double* __restrict__ Hd,
+         const double* __restrict__ Ho, const double* __restrict__ g, const double* __restrict__ delta, const double* __restrict__ nodes,
+         double* __restrict__ cand, double* __restrict__ stats) {
+  __shared__ double s_w[PGS_THREADS / 32];
+  double mc = 0.0, dn = 0.0, cn = 0.0, bad = 0.0;
+  for (int i = threadIdx.x; i < n; i += PGS_THREADS) {
+    double d[6], hd[6];
+    for (int a = 0; a < 6; a++) d[a] = delta[6 * (size_t)i + a];
+    for (int a = 0; a < 6; a++) {
+      double acc = 0.0;
+      for (int b = 0; b < 6; b++) acc += Hd[36 * (size_t)i + 6 * a + b] * d[b];
+      hd[a] = acc;
+    }
+    for (int e = row[i]; e < row[i + 1]; e++) {
+      const int c = inc[e] >> 1, side = inc[e] & 1;
+      const int other = side ? ids[3 * c] : ids[3 * c + 1];
+      const double* B = Ho + 36 * (size_t)c;
+      const double* u = delta + 6 * (size_t)other;
+      if (side == 0) { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) hd[a] += B[6 * a + b] * u[b]; }
+      else           { for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) hd[a] += B[6 * b + a] * u[b]; }
+    }
+    for (int a = 0; a < 6; a++) {
+      mc -= d[a] * (g[6 * (size_t)i + a] + 0.5 * hd[a]);
+      if (!isfinite(d[a])) bad = 1.0;
+    }
+    double o[7];
+    pgo_plus_node(nodes + 7 * (size_t)i, d, o);
+    for (int c = 0; c < 7; c++) {
+      const double df = nodes[7 * (size_t)i + c] - o[c];
+      dn += df * df; cn += o[c] * o[c];
+      cand[7 * (size_t)i + c] = o[c];
+    }
+  }
+  mc = pgs_block_sum(mc, s_w); dn = pgs_block_sum(dn, s_w); cn = pgs_block_sum(cn, s_w); bad = pgs_block_sum(bad, s_w);
+  if (threadIdx.x == 0) { stats[0] = mc; stats[1] = dn; stats[2] = cn; stats[3] = bad > 0.0 ? 0.0 : 1.0; }
+}
+// stats[4] = max |x - Plus(x, -g)| over the free nodes (Ceres' gradient max norm for a manifold), stats[5] = |x|^2
+__global__ void __launch_bounds__(PGS_THREADS, 1)
+pgo_gradmax(int n, int fixed_node, const double* __restrict__ nodes, const double* __restrict__ g, double* __restrict__ stats) {
+  __shared__ double s_w[PGS_THREADS / 32];
+  double gm = 0.0, xn = 0.0;
+  for (int i = threadIdx.x; i < n; i += PGS_THREADS) {
+    double d[6], o[7];
+    for (int a = 0; a < 6; a++) d[a] = (i == fixed_node) ? 0.0 : -g[6 * (size_t)i + a];
+    pgo_plus_node(nodes + 7 * (size_t)i, d, o);
+    for (int c = 0; c < 7; c++) {
+      const double v = nodes[7 * (size_t)i + c];
+      gm = fmax(gm, fabs(v - o[c]));
+      xn += v * v;
+    }
+  }
+  gm = pgs_block_max(gm, s_w); xn = pgs_block_sum(xn, s_w);
+  if (threadIdx.x == 0) { stats[4] = gm; stats[5] = xn; }
 }
 
 }  // namespace tbv
@@ -791,92 +749,290 @@ extern "C" int tbv_pgo_assemble(tbv_ctx* ctx, int n_nodes, const double* nodes, 
 }
 
 
-extern "C" int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const int* ids, const double* H_diag, const double* H_off, const double* g,
-                                  int fixed_node, double radius, int max_iters, double rel_tol, double* delta, int* iters, double* rel_residual) {
-  TBV_ENTER(ctx);
-  TBV_REQUIRE(ctx && ids && H_diag && H_off && g && delta && n_nodes >= 1 && n_con >= 0 && radius > 0 && max_iters >= 0, "bad arguments");
-  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
+namespace {
+
+// Device-resident pose graph: constraint lists, CSR incidence, the assembled blocks and every solver vector.  Built once per call of
+// tbv_pgo_solve_step / tbv_pgo_optimize; all Levenberg-Marquardt iterations of tbv_pgo_optimize run on these buffers.
+struct PgoDev {
+  int n = 0, m = 0, fixed = 0;
+  bool has_info = false;
+  DevBuf<double> nodes, cand, meas, info, rec, cost;          // nodes [n][7] (current / candidate), measurements, records, 1 cost
+  DevBuf<double> Hd, Ho, g, Hd_c, Ho_c, g_c;                  // normal equations at the current point / at the candidate
+  DevBuf<double> x, r, z, p, q, u, Dm, Cc, Dinv, ML, MR, Dg;  // linear solve
+  DevBuf<double> scale, lm_diag, damping, stats;              // trust-region bookkeeping (stats: 8 doubles)
+  DevBuf<int> ids, row, inc, order, err, it;
+  DevBuf<double> rel;
+  void release() {
+    for (DevBuf<double>* b : {&nodes, &cand, &meas, &info, &rec, &cost, &Hd, &Ho, &g, &Hd_c, &Ho_c, &g_c, &x, &r, &z, &p, &q, &u, &Dm, &Cc, &Dinv, &ML, &MR, &Dg,
+                              &scale, &lm_diag, &damping, &stats, &rel})
+      b->release();
+    for (DevBuf<int>* b : {&ids, &row, &inc, &order, &err, &it}) b->release();
+  }
+};
+
+// id list -> CSR incidence (node -> constraints, reference order: all odometry constraints, then all loop constraints) and uploads
+int pgo_upload_graph(tbv_ctx* ctx, PgoDev& G, int n_nodes, int n_con, const int* ids, bool reference_order) {
   for (int c = 0; c < n_con; c++)
     TBV_REQUIRE(ids[3 * c] >= 0 && ids[3 * c] < n_nodes && ids[3 * c + 1] >= 0 && ids[3 * c + 1] < n_nodes, "constraint references a missing node");
+  G.n = n_nodes; G.m = n_con;
+  std::vector<int> order(n_con);
+  std::iota(order.begin(), order.end(), 0);
+  if (reference_order)   // AddConstraintType(odometry) then AddConstraintType(loop) (ceresoptimizer.cpp:34-35)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (ids[3 * a + 2] == 1) < (ids[3 * b + 2] == 1); });
   std::vector<int> row(n_nodes + 1, 0), inc(2 * (size_t)n_con + 1);
   for (int c = 0; c < n_con; c++) { row[ids[3 * c] + 1]++; row[ids[3 * c + 1] + 1]++; }
   for (int i = 0; i < n_nodes; i++) row[i + 1] += row[i];
   {
     std::vector<int> fill(row.begin(), row.end() - 1);
-    for (int c = 0; c < n_con; c++) { inc[fill[ids[3 * c]]++] = (c << 1); inc[fill[ids[3 * c + 1]]++] = (c << 1) | 1; }
+    for (int c : order) { inc[fill[ids[3 * c]]++] = (c << 1); inc[fill[ids[3 * c + 1]]++] = (c << 1) | 1; }
   }
-  const size_t N6 = 6 * (size_t)n_nodes, nc1 = n_con ? n_con : 1;
-  DevBuf<double> dhd, dho, dg, dx, dr, dz, dp, dq, dmi, ddg, drel;
-  DevBuf<int> dids, drow, dinc, dit;
-  auto cleanup = [&]() {
-    dhd.release(); dho.release(); dg.release(); dx.release(); dr.release(); dz.release(); dp.release(); dq.release(); dmi.release(); ddg.release();
-    drel.release(); dids.release(); drow.release(); dinc.release(); dit.release();
-  };
+  const size_t nc1 = n_con ? n_con : 1;
   int rc;
-  if ((rc = dhd.reserve(36 * (size_t)n_nodes)) || (rc = dho.reserve(36 * nc1)) || (rc = dg.reserve(N6)) || (rc = dx.reserve(N6)) || (rc = dr.reserve(N6)) ||
-      (rc = dz.reserve(N6)) || (rc = dp.reserve(N6)) || (rc = dq.reserve(N6)) || (rc = dmi.reserve(36 * (size_t)n_nodes)) || (rc = ddg.reserve(N6)) ||
-      (rc = drel.reserve(1)) || (rc = dids.reserve(3 * nc1)) || (rc = drow.reserve(n_nodes + 1)) || (rc = dinc.reserve(inc.size())) || (rc = dit.reserve(1))) {
-    cleanup();
+  if ((rc = G.ids.reserve(3 * nc1)) || (rc = G.row.reserve(n_nodes + 1)) || (rc = G.inc.reserve(inc.size())) || (rc = G.order.reserve(nc1)) ||
+      (rc = G.err.reserve(2)) || (rc = G.it.reserve(1)) || (rc = G.rel.reserve(1)))
     return rc;
-  }
   cudaStream_t st = ctx->stream;
-  cudaError_t e = cudaMemcpyAsync(dhd.p, H_diag, 36 * (size_t)n_nodes * sizeof(double), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dho.p, H_off, 36 * (size_t)n_con * sizeof(double), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dg.p, g, N6 * sizeof(double), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dids.p, ids, 3 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(drow.p, row.data(), (n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(dinc.p, inc.data(), 2 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    static const bool use_cluster = getenv("TBV_PGO_CLUSTER") != nullptr;   // opt-in until the cluster kernel has been run and timed on a B200
-    static const bool use_chain = getenv("TBV_PGO_CHAIN") != nullptr;       // opt-in: odometry-chain preconditioner (same status)
-    if (use_chain) {
-      // chain[i] = A[i+1][i]: sum over the constraints between nodes i and i+1 of H_off (begin = i+1) or its transpose (begin = i)
-      std::vector<double> chain(36 * (size_t)std::max(n_nodes - 1, 1), 0.0);
-      for (int c = 0; c < n_con; c++) {
-        const int a = ids[3 * c], b = ids[3 * c + 1];
-        if (a - b != 1 && b - a != 1) continue;
-        const int lo = a < b ? a : b;
-        if (lo == fixed_node || lo + 1 == fixed_node) continue;            // no coupling across the fixed node
-        const double* B = H_off + 36 * (size_t)c;
-        double* C = chain.data() + 36 * (size_t)lo;
-        for (int u = 0; u < 6; u++)
-          for (int v = 0; v < 6; v++) C[6 * u + v] += (a > b) ? B[6 * u + v] : B[6 * v + u];
-      }
-      DevBuf<double> dch, dsi, dwb, dy;
-      int rc2;
-      if ((rc2 = dch.reserve(chain.size())) || (rc2 = dsi.reserve(36 * (size_t)n_nodes)) || (rc2 = dwb.reserve(chain.size())) || (rc2 = dy.reserve(N6))) {
-        dch.release(); dsi.release(); dwb.release(); dy.release(); cleanup();
-        return rc2;
-      }
-      e = cudaMemcpyAsync(dch.p, chain.data(), chain.size() * sizeof(double), cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) {
-        pgo_pcg_chain<<<1, PCG_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dch.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p,
-                                                  dz.p, dp.p, dq.p, dsi.p, dwb.p, ddg.p, dy.p, dit.p, drel.p);
-        launched(ctx, "pgo_pcg_chain");
-        e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);               // `chain` (host) and the extra buffers must outlive the kernel
-      }
-      dch.release(); dsi.release(); dwb.release(); dy.release();
-    } else if (use_cluster) {
-      pgo_pcg_cluster<<<PCGC_CL, PCGC_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p,
-                                                         dz.p, dp.p, dq.p, dmi.p, ddg.p, dit.p, drel.p);
-      launched(ctx, "pgo_pcg_cluster");
-    } else {
-      pgo_pcg<<<1, PCG_THREADS, 0, st>>>(n_nodes, fixed_node, dids.p, drow.p, dinc.p, dhd.p, dho.p, dg.p, radius, max_iters, rel_tol, dx.p, dr.p, dz.p, dp.p,
-                                          dq.p, dmi.p, ddg.p, dit.p, drel.p);
-      launched(ctx, "pgo_pcg");
+  if (n_con) TBV_CUDA(cudaMemcpyAsync(G.ids.p, ids, 3 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st));
+  TBV_CUDA(cudaMemcpyAsync(G.row.p, row.data(), (n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n_con) TBV_CUDA(cudaMemcpyAsync(G.inc.p, inc.data(), 2 * (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n_con) TBV_CUDA(cudaMemcpyAsync(G.order.p, order.data(), (size_t)n_con * sizeof(int), cudaMemcpyHostToDevice, st));
+  TBV_CUDA(cudaMemsetAsync(G.err.p, 0, sizeof(int), st));
+  TBV_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope
+  return TBV_OK;
+}
+
+int pgo_reserve_solver(PgoDev& G) {
+  const size_t N6 = 6 * (size_t)G.n, N36 = 36 * (size_t)G.n;
+  int rc;
+  for (DevBuf<double>* b : {&G.x, &G.r, &G.z, &G.p, &G.q, &G.u, &G.Dg})
+    if ((rc = b->reserve(N6))) return rc;
+  for (DevBuf<double>* b : {&G.Dm, &G.Cc, &G.Dinv, &G.ML, &G.MR})
+    if ((rc = b->reserve(N36))) return rc;
+  return TBV_OK;
+}
+
+// enqueue (H + D) delta = -g on the current blocks; D = `damping` (device, [n][6]) or clamp(diag H, 1e-6, 1e32) / radius when null
+int pgo_enqueue_solve(tbv_ctx* ctx, PgoDev& G, const double* Hd, const double* Ho, const double* g, const double* damping, double radius, int max_iters,
+                      double rel_tol) {
+  cudaStream_t st = ctx->stream;
+  const int n = G.n;
+  TBV_CUDA(cudaMemsetAsync(G.err.p + 1, 0, sizeof(int), st));   // err[1]: a chain pivot block was not positive definite
+  pgo_cr_setup<<<(n + PCRF_THREADS - 1) / PCRF_THREADS, PCRF_THREADS, 0, st>>>(n, G.fixed, G.ids.p, G.row.p, G.inc.p, Hd, Ho, damping, radius, G.Dm.p, G.Cc.p,
+                                                                               G.Dg.p);
+  launched(ctx, "pgo_cr_setup");
+  for (int s = 1; s < n; s <<= 1) {
+    const int n_odd = (n - 1 >= s) ? (n - 1 - s) / (2 * s) + 1 : 0, n_even = (n - 1) / (2 * s) + 1;
+    if (n_odd > 0) {
+      pgo_cr_eliminate<<<(n_odd + PCRF_THREADS - 1) / PCRF_THREADS, PCRF_THREADS, 0, st>>>(n, s, n_odd, G.Dm.p, G.Cc.p, G.Dinv.p, G.ML.p, G.MR.p, G.err.p + 1);
+      launched(ctx, "pgo_cr_eliminate");
     }
-    if (e == cudaSuccess) e = cudaGetLastError();
+    pgo_cr_update<<<(n_even + PCRF_THREADS - 1) / PCRF_THREADS, PCRF_THREADS, 0, st>>>(n, s, n_even, G.Dm.p, G.Cc.p, G.ML.p, G.MR.p);
+    launched(ctx, "pgo_cr_update");
   }
+  pgo_cr_eliminate<<<1, PCRF_THREADS, 0, st>>>(n, 0, 0, G.Dm.p, G.Cc.p, G.Dinv.p, G.ML.p, G.MR.p, G.err.p + 1);   // node 0 is what is left
+  launched(ctx, "pgo_cr_eliminate");
+  pgo_pcg_cr<<<PCR_CL, PCR_THREADS, 0, st>>>(n, G.fixed, G.ids.p, G.row.p, G.inc.p, Hd, Ho, g, max_iters, rel_tol, G.x.p, G.r.p, G.z.p, G.p.p, G.q.p, G.u.p,
+                                             G.Dinv.p, G.ML.p, G.MR.p, G.Dg.p, G.err.p + 1, G.it.p, G.rel.p);
+  launched(ctx, "pgo_pcg_cr");
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
+}
+
+}  // namespace
+
+extern "C" int tbv_pgo_solve_step(tbv_ctx* ctx, int n_nodes, int n_con, const int* ids, const double* H_diag, const double* H_off, const double* g,
+                                  int fixed_node, double radius, int max_iters, double rel_tol, double* delta, int* iters, double* rel_residual) {
+  TBV_ENTER(ctx);
+  TBV_REQUIRE(ctx && ids && H_diag && H_off && g && delta && n_nodes >= 1 && n_con >= 0 && radius > 0 && max_iters >= 0, "bad arguments");
+  return tbv_pgo_solve_damped(ctx, n_nodes, n_con, ids, H_diag, H_off, g, nullptr, fixed_node, radius, max_iters, rel_tol, delta, iters, rel_residual);
+}
+
+extern "C" int tbv_pgo_solve_damped(tbv_ctx* ctx, int n_nodes, int n_con, const int* ids, const double* H_diag, const double* H_off, const double* g,
+                                    const double* damping, int fixed_node, double radius, int max_iters, double rel_tol, double* delta, int* iters,
+                                    double* rel_residual) {
+  TBV_ENTER(ctx);
+  TBV_REQUIRE(ctx && ids && H_diag && H_off && g && delta && n_nodes >= 1 && n_con >= 0 && max_iters >= 0 && (damping || radius > 0), "bad arguments");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
+  PgoDev G;
+  G.fixed = fixed_node;
+  int rc = pgo_upload_graph(ctx, G, n_nodes, n_con, ids, false);
+  const size_t N6 = 6 * (size_t)n_nodes, nc1 = n_con ? n_con : 1;
+  if (!rc) rc = pgo_reserve_solver(G);
+  if (!rc && ((rc = G.Hd.reserve(36 * (size_t)n_nodes)) || (rc = G.Ho.reserve(36 * nc1)) || (rc = G.g.reserve(N6)) || (damping && (rc = G.damping.reserve(N6))))) {}
+  if (rc) { G.release(); return rc; }
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaMemcpyAsync(G.Hd.p, H_diag, 36 * (size_t)n_nodes * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(G.Ho.p, H_off, 36 * (size_t)n_con * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(G.g.p, g, N6 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && damping) e = cudaMemcpyAsync(G.damping.p, damping, N6 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) rc = pgo_enqueue_solve(ctx, G, G.Hd.p, G.Ho.p, G.g.p, damping ? G.damping.p : nullptr, radius, max_iters, rel_tol);
   int h_it = 0;
   double h_rel = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(delta, dx.p, N6 * sizeof(double), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_it, dit.p, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_rel, drel.p, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(delta, G.x.p, N6 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(&h_it, G.it.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(&h_rel, G.rel.p, sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cleanup();
-  if (e != cudaSuccess) { set_error("tbv_pgo_solve_step: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
+  G.release();
+  if (rc) return rc;
+  if (e != cudaSuccess) { set_error("tbv_pgo_solve_damped: %s", cudaGetErrorString(e)); return TBV_ERR_CUDA; }
   if (iters) *iters = h_it;
   if (rel_residual) *rel_residual = h_rel;
   return TBV_OK;
 }
+
+namespace {
+// residuals, Jacobians and the block normal equations at `nodes` (device) -> Hd, Ho, g, G.cost (device); enqueued on the context's stream
+int pgo_enqueue_assemble(tbv_ctx* ctx, PgoDev& G, const tbv_pgo_params& P, const double* nodes, double* Hd, double* Ho, double* g) {
+  cudaStream_t st = ctx->stream;
+  if (G.m) {
+    pgo_blocks<<<(G.m + 63) / 64, 64, 0, st>>>(G.m, nodes, G.ids.p, G.meas.p, G.has_info ? G.info.p : nullptr, P, G.fixed, G.rec.p, Ho, nullptr, G.err.p);
+    launched(ctx, "pgo_blocks");
+  }
+  pgo_gather<<<(G.n * 32 + 127) / 128, 128, 0, st>>>(G.n, G.row.p, G.inc.p, G.rec.p, Hd, g);
+  launched(ctx, "pgo_gather");
+  pgo_cost<<<1, 256, 0, st>>>(G.m, G.order.p, G.rec.p, G.cost.p);
+  launched(ctx, "pgo_cost");
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
+}
+}  // namespace
+
+extern "C" int tbv_pgo_optimize(tbv_ctx* ctx, int n_nodes, double* nodes, int n_con, const int* ids, const double* meas, const double* info,
+                                const tbv_pgo_params* params, int fixed_node, const tbv_pgo_options* options, tbv_pgo_summary* summary) {
+  TBV_ENTER(ctx);
+  TBV_REQUIRE(ctx && nodes && ids && meas && params && n_nodes >= 1 && n_con >= 0, "bad arguments");
+  TBV_REQUIRE(params->replace_cov_by_identity || info, "information matrices required when replace_cov_by_identity is 0");
+  AllocScope alloc_scope(ctx->stream);  // temporaries of this call come from the stream-ordered pool
+  tbv_pgo_options O = {200, 1e-6, 1e-10, 1e-8, 1e4, 20000, 1e-10};   // ceresoptimizer.cpp:13-15 (max_num_iterations 200) + Ceres 2.1.0 defaults
+  if (options) {
+    if (options->max_num_iterations > 0) O.max_num_iterations = options->max_num_iterations;
+    if (options->function_tolerance > 0) O.function_tolerance = options->function_tolerance;
+    if (options->gradient_tolerance > 0) O.gradient_tolerance = options->gradient_tolerance;
+    if (options->parameter_tolerance > 0) O.parameter_tolerance = options->parameter_tolerance;
+    if (options->initial_radius > 0) O.initial_radius = options->initial_radius;
+    if (options->max_cg_iterations > 0) O.max_cg_iterations = options->max_cg_iterations;
+    if (options->cg_rel_tol > 0) O.cg_rel_tol = options->cg_rel_tol;
+  }
+  PgoDev G;
+  G.fixed = fixed_node;
+  G.has_info = info != nullptr && !params->replace_cov_by_identity;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  auto fail = [&](int rc) { G.release(); if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); return rc; };
+  int rc = pgo_upload_graph(ctx, G, n_nodes, n_con, ids, true);
+  if (rc) return fail(rc);
+  const size_t N6 = 6 * (size_t)n_nodes, N7 = 7 * (size_t)n_nodes, N36 = 36 * (size_t)n_nodes, nc1 = n_con ? n_con : 1;
+  if ((rc = pgo_reserve_solver(G))) return fail(rc);
+  for (DevBuf<double>* b : {&G.Hd, &G.Hd_c})
+    if ((rc = b->reserve(N36))) return fail(rc);
+  for (DevBuf<double>* b : {&G.Ho, &G.Ho_c})
+    if ((rc = b->reserve(36 * nc1))) return fail(rc);
+  for (DevBuf<double>* b : {&G.g, &G.g_c, &G.scale, &G.lm_diag, &G.damping})
+    if ((rc = b->reserve(N6))) return fail(rc);
+  if ((rc = G.nodes.reserve(N7)) || (rc = G.cand.reserve(N7)) || (rc = G.meas.reserve(7 * nc1)) || (rc = G.info.reserve(G.has_info ? 36 * nc1 : 1)) ||
+      (rc = G.rec.reserve(PGB * nc1)) || (rc = G.cost.reserve(1)) || (rc = G.stats.reserve(8)))
+    return fail(rc);
+  cudaError_t e = cudaMemcpyAsync(G.nodes.p, nodes, N7 * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con) e = cudaMemcpyAsync(G.meas.p, meas, 7 * (size_t)n_con * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_con && G.has_info) e = cudaMemcpyAsync(G.info.p, info, 36 * (size_t)n_con * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+  if (e == cudaSuccess) e = cudaEventRecord(ev0, st);
+  if (e != cudaSuccess) { set_error("tbv_pgo_optimize: %s", cudaGetErrorString(e)); return fail(TBV_ERR_CUDA); }
+
+  double* x = G.nodes.p; double* cand = G.cand.p;
+  double* Hd = G.Hd.p; double* Ho = G.Ho.p; double* g = G.g.p;
+  double* Hd_c = G.Hd_c.p; double* Ho_c = G.Ho_c.p; double* g_c = G.g_c.p;
+  double h_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double h_cost = 0.0;
+  int h_err = 0, h_it = 0;
+  auto read_eval = [&](double* cost_out) -> int {   // cost + gradient max norm + |x|^2 of the point just evaluated
+    TBV_CUDA(cudaMemcpyAsync(&h_cost, G.cost.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TBV_CUDA(cudaMemcpyAsync(&h_err, G.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TBV_CUDA(cudaMemcpyAsync(h_stats + 4, G.stats.p + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TBV_CUDA(cudaStreamSynchronize(st));
+    if (h_err) { set_error("tbv_pgo_optimize: an information matrix is not positive definite"); return TBV_ERR_INVALID; }
+    *cost_out = h_cost;
+    return TBV_OK;
+  };
+  const int rows_grid = (int)((N6 + 255) / 256);
+  tbv_pgo_summary S = {};
+  // ---- iteration 0: evaluate, Jacobi scaling, gradient norm -------------------------------------------------------------------------------------
+  double x_cost = 0.0;
+  if ((rc = pgo_enqueue_assemble(ctx, G, *params, x, Hd, Ho, g))) return fail(rc);
+  pgo_scale<<<rows_grid, 256, 0, st>>>(n_nodes, Hd, G.scale.p);
+  launched(ctx, "pgo_scale");
+  pgo_gradmax<<<1, PGS_THREADS, 0, st>>>(n_nodes, fixed_node, x, g, G.stats.p);
+  launched(ctx, "pgo_gradmax");
+  if ((rc = read_eval(&x_cost))) return fail(rc);
+  S.initial_cost = S.final_cost = x_cost;
+  double gmax = h_stats[4], x_norm = sqrt(h_stats[5]);
+  double radius = O.initial_radius, decrease = 2.0;
+  bool reuse = false, step_ok = true;
+  int invalid = 0, iteration = 0;
+  S.termination = TBV_PGO_MAX_ITERATIONS;
+  const double DBL_BIG = 1.7976931348623157e308;
+  for (;;) {
+    // FinalizeIterationAndCheckIfMinimizerCanContinue
+    if (iteration >= O.max_num_iterations) { S.termination = TBV_PGO_MAX_ITERATIONS; break; }
+    if (step_ok && gmax <= O.gradient_tolerance) { S.termination = TBV_PGO_GRADIENT_TOLERANCE; break; }
+    if (radius < 1e-32) { S.termination = TBV_PGO_MIN_RADIUS; break; }
+    iteration++;
+    S.iterations = iteration;
+    // LevenbergMarquardtStrategy::ComputeStep
+    pgo_damping<<<rows_grid, 256, 0, st>>>(n_nodes, fixed_node, Hd, G.scale.p, reuse ? 1 : 0, radius, G.lm_diag.p, G.damping.p);
+    launched(ctx, "pgo_damping");
+    if ((rc = pgo_enqueue_solve(ctx, G, Hd, Ho, g, G.damping.p, radius, O.max_cg_iterations, O.cg_rel_tol))) return fail(rc);
+    reuse = true;
+    pgo_step<<<1, PGS_THREADS, 0, st>>>(n_nodes, G.ids.p, G.row.p, G.inc.p, Hd, Ho, g, G.x.p, x, cand, G.stats.p);
+    launched(ctx, "pgo_step");
+    // the candidate is evaluated right away (one host synchronisation per iteration); an invalid step simply discards the evaluation
+    if ((rc = pgo_enqueue_assemble(ctx, G, *params, cand, Hd_c, Ho_c, g_c))) return fail(rc);
+    pgo_gradmax<<<1, PGS_THREADS, 0, st>>>(n_nodes, fixed_node, cand, g_c, G.stats.p);
+    launched(ctx, "pgo_gradmax");
+    e = cudaMemcpyAsync(h_stats, G.stats.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_it, G.it.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { set_error("tbv_pgo_optimize: %s", cudaGetErrorString(e)); return fail(TBV_ERR_CUDA); }
+    double cand_cost = 0.0;
+    if ((rc = read_eval(&cand_cost))) return fail(rc);
+    if (h_it < 0) { set_error("tbv_pgo_optimize: a pivot block of the damped odometry chain is not positive definite"); return fail(TBV_ERR_INVALID); }
+    S.cg_iterations += h_it;
+    const double model_change = h_stats[0];
+    if (!(h_stats[3] > 0.5 && model_change > 0.0)) {   // HandleInvalidStep
+      invalid++;
+      step_ok = false;
+      if (invalid >= 5) { S.termination = TBV_PGO_FAILURE; break; }
+      radius /= decrease; decrease *= 2.0;
+      continue;
+    }
+    invalid = 0;
+    if (!std::isfinite(cand_cost)) cand_cost = DBL_BIG;
+    if (sqrt(h_stats[1]) <= O.parameter_tolerance * (x_norm + O.parameter_tolerance)) { S.termination = TBV_PGO_PARAMETER_TOLERANCE; break; }
+    if (std::fabs(x_cost - cand_cost) <= O.function_tolerance * x_cost) { S.termination = TBV_PGO_FUNCTION_TOLERANCE; break; }
+    const double rho = cand_cost < DBL_BIG ? (x_cost - cand_cost) / model_change : -1.0;
+    if (rho > 1e-3) {                                    // HandleSuccessfulStep
+      std::swap(x, cand); std::swap(Hd, Hd_c); std::swap(Ho, Ho_c); std::swap(g, g_c);
+      x_cost = cand_cost;
+      x_norm = sqrt(h_stats[5]);
+      gmax = h_stats[4];
+      step_ok = true;
+      S.successful_steps++;
+      if (x_cost < S.final_cost) S.final_cost = x_cost;
+      const double t = 2.0 * rho - 1.0;
+      radius = std::min(radius / std::max(1.0 / 3.0, 1.0 - t * t * t), 1e16);
+      decrease = 2.0; reuse = false;
+    } else {
+      step_ok = false;
+      radius /= decrease; decrease *= 2.0;
+    }
+  }
+  e = cudaEventRecord(ev1, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nodes, x, N7 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&S.device_ms, ev0, ev1);
+  if (e != cudaSuccess) { set_error("tbv_pgo_optimize: %s", cudaGetErrorString(e)); return fail(TBV_ERR_CUDA); }
+  if (summary) *summary = S;
+  fail(TBV_OK);
+  return TBV_OK;
+}
+

@@ -20,7 +20,7 @@ STAGE_OF_KERNEL = {
     "sc_similarity": "Detect loop", "sc_search": "Detect loop", "sc_distance": "Detect loop",
     "k_pack_constraints": "Register", "k_merge_constraints": "Register", "nccl_all_gather": "Register",
     "k_coral": "Verify loop candidate",
-    "pgo_blocks": "Pose grapgh optimization", "pgo_gather": "Pose grapgh optimization", "pgo_cost": "Pose grapgh optimization", "pgo_pcg": "Pose grapgh optimization", "pgo_pcg_cluster": "Pose grapgh optimization", "pgo_pcg_chain": "Pose grapgh optimization",   # sic: the reference's spelling
+    "pgo_blocks": "Pose grapgh optimization", "pgo_gather": "Pose grapgh optimization", "pgo_cost": "Pose grapgh optimization", "pgo_pcg_cr": "Pose grapgh optimization", "pgo_cr_setup": "Pose grapgh optimization", "pgo_cr_eliminate": "Pose grapgh optimization", "pgo_cr_update": "Pose grapgh optimization", "pgo_scale": "Pose grapgh optimization", "pgo_damping": "Pose grapgh optimization", "pgo_step": "Pose grapgh optimization", "pgo_gradmax": "Pose grapgh optimization",   # sic: the reference's spelling
 }
 
 

@@ -122,7 +122,7 @@ class GpuLoopDevice:
 
     # CeresLeastSquares(...).Solve() (ceresoptimizer.cpp:13-62)
     def optimize(self, nodes, ids, meas, info, pgo_params, **kw):
-        return self.api.pgo_optimize(self.ctx, nodes, ids, meas, pgo_params, info=info, **kw)
+        return self.api.pgo_optimize_device(self.ctx, nodes, ids, meas, pgo_params, info=info, **kw)   # whole LM loop on the device (tbv_pgo_optimize)
 
 
 class ScanLearningInterface:

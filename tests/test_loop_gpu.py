@@ -217,16 +217,22 @@ def _damped_system(ids, Hd, Ho, g, radius, fixed):
     return A[keep][:, keep].tocsc(), -g.reshape(-1)[keep], keep
 
 
-@pytest.mark.parametrize("n,radius,fixed", [(2, 1e4, 0), (30, 1e4, 0), (600, 1e4, 0), (600, 1e2, 17), (4500, 1e4, 0)])
+@pytest.mark.parametrize("n,radius,fixed", [(1, 1e4, 0), (2, 1e4, 0), (3, 1e4, 1), (7, 1e4, 3), (30, 1e4, 0), (600, 1e4, 0), (600, 1e2, 17), (600, 1e8, 17),
+                                            (1025, 1e6, 1024), (4500, 1e4, 0), (4500, 1e8, 0)])
 def test_pgo_solve_step_matches_sparse_direct_solve(ctx, n, radius, fixed):
-    """tbv_pgo_solve_step (block-Jacobi PCG, one CTA) against scipy's sparse LU on the same damped normal equations.
-    Tolerance: relative residual <= 1e-11 (asked: 1e-12), |delta - direct| <= 1e-5 |direct| (CG at 1e-12 reaches ~1e-7 on these graphs)."""
+    """tbv_pgo_solve_step (CG preconditioned with the odometry chain by block cyclic reduction, one 8-CTA cluster) against scipy's sparse LU
+    on the same damped normal equations — including the large trust-region radii at which a block-Jacobi preconditioner does not converge
+    (profiles/r2a_pgo_one_cta.json) and node counts around the powers of two of the reduction.
+    Tolerance: relative residual <= 1e-11 (asked: 1e-12), |delta - direct| <= 1e-5 |direct|."""
     import scipy.sparse.linalg as spl
     rng = np.random.default_rng(n)
     nodes, ids, meas = _graph(n, rng)
     _, Hd, Ho, g, _ = api.pgo_assemble(ctx, nodes, ids, meas, fixed_node=fixed)
     delta, iters, rel = api.pgo_solve_step(ctx, ids, Hd, Ho, g, fixed_node=fixed, radius=radius, max_iters=20000, rel_tol=1e-12)
-    assert 0 < iters < 20000 and rel <= 1e-12
+    if n == 1:                     # only the fixed node: nothing to solve
+        assert iters == 0 and np.all(delta == 0)
+        return
+    assert 0 < iters < 400 and rel <= 1e-12
     assert np.all(delta[fixed] == 0)
     A, b, keep = _damped_system(ids, Hd, Ho, g, radius, fixed)
     ref = spl.spsolve(A, b)
@@ -242,8 +248,8 @@ def test_pgo_solve_step_iteration_cap_and_arguments(ctx):
     rng = np.random.default_rng(3)
     nodes, ids, meas = _graph(200, rng)
     _, Hd, Ho, g, _ = api.pgo_assemble(ctx, nodes, ids, meas)
-    d5, it5, rel5 = api.pgo_solve_step(ctx, ids, Hd, Ho, g, max_iters=5)
-    assert it5 == 5 and 0 < rel5 < 1.0 and np.all(np.isfinite(d5))
+    d5, it5, rel5 = api.pgo_solve_step(ctx, ids, Hd, Ho, g, max_iters=1)
+    assert it5 == 1 and 0 < rel5 < 1.0 and np.all(np.isfinite(d5))
     d0, it0, rel0 = api.pgo_solve_step(ctx, ids, Hd, Ho, g, max_iters=0)
     assert it0 == 0 and np.all(d0 == 0)
     dz, itz, relz = api.pgo_solve_step(ctx, ids, Hd, Ho, np.zeros_like(g))        # zero gradient: nothing to do
@@ -341,7 +347,7 @@ def test_pgo_optimize_reaches_a_stationary_point_of_the_oracle_cost(ctx, oracle,
     c_ref, _, _, g_ref, _ = oracle.pgo_assemble(x, ids, meas, OP)
     c0, _, _, g0, _ = oracle.pgo_assemble(start, ids, meas, OP)
     if loop_scaling == 1.0:      # saturated Cauchy loops: a flat valley, the run ends on function_tolerance = 1e-15 within the 200 iterations
-        assert S.termination in ("gradient_tolerance", "function_tolerance") and S.iterations <= 200
+        assert S.termination in ("gradient_tolerance", "function_tolerance", "parameter_tolerance") and S.iterations <= 200
     else:
         assert S.termination == "gradient_tolerance" and S.iterations < 100
     assert abs(S.final_cost - c_ref) <= 1e-10 * c_ref and abs(S.initial_cost - c0) <= 1e-10 * c0 and c_ref < c0
@@ -352,3 +358,64 @@ def test_pgo_optimize_reaches_a_stationary_point_of_the_oracle_cost(ctx, oracle,
     _, S2 = api.pgo_optimize(ctx, start, ids, meas, P)                      # Ceres defaults
     assert S2.termination in ("function_tolerance", "gradient_tolerance") and S2.iterations <= S.iterations
     assert S2.final_cost <= S.final_cost * (1 + 1e-4)
+
+
+def test_pgo_solve_damped_takes_an_arbitrary_damping(ctx):
+    """tbv_pgo_solve_damped: (H + diag(damping)) delta = -g for ANY positive damping vector (what LevenbergMarquardtStrategy needs: its
+    diagonal is scaled, clamped and reused), against a dense direct solve."""
+    rng = np.random.default_rng(3)
+    nodes, ids, meas = _graph(40, rng)
+    _, Hd, Ho, g, _ = api.pgo_assemble(ctx, nodes, ids, meas)
+    n = len(Hd)
+    H = np.zeros((6 * n, 6 * n))
+    for i in range(n):
+        H[6 * i:6 * i + 6, 6 * i:6 * i + 6] = Hd[i]
+    for c, (a, b, _t) in enumerate(ids):
+        H[6 * a:6 * a + 6, 6 * b:6 * b + 6] += Ho[c]
+        H[6 * b:6 * b + 6, 6 * a:6 * a + 6] += Ho[c].T
+    keep = np.arange(6, 6 * n)
+    for damping in (rng.uniform(0.1, 50.0, size=(n, 6)), np.full((n, 6), 1e-9), rng.uniform(1e-3, 1.0, size=(n, 6)) * Hd[:, np.arange(6), np.arange(6)].clip(1e-3)):
+        delta, iters, rel = api.pgo_solve_damped(ctx, ids, Hd, Ho, g, damping, fixed_node=0)
+        A = (H + np.diag(damping.reshape(-1)))[np.ix_(keep, keep)]
+        want = np.linalg.solve(A, -g.reshape(-1)[keep])
+        assert iters > 0 and np.all(delta[0] == 0) and np.allclose(delta.reshape(-1)[keep], want, rtol=1e-6, atol=1e-9 * np.abs(want).max())
+    with pytest.raises(ValueError):
+        api.pgo_solve_damped(ctx, ids, Hd, Ho, g, np.zeros((n, 6)))
+
+
+@pytest.mark.parametrize("loop_scaling", [500000.0, 1.0])
+def test_pgo_optimize_on_the_device_equals_the_host_driven_loop(ctx, oracle, loop_scaling):
+    """tbv_pgo_optimize (every LM iteration on the device) against api.pgo_optimize_ceres (the same Ceres 2.1.0 iteration rules driven from the
+    host, one device call at a time): same iterations, termination and accepted steps; nodes to 1e-9; and the oracle's gradient vanishes there."""
+    rng = np.random.default_rng(2)
+    truth, start, ids, meas = _ring_graph(300, rng)
+    P, OP = api.default_pgo_params(loop_scaling=loop_scaling), oracle.default_pgo_params(loop_scaling=loop_scaling)
+    kw = dict(function_tolerance=1e-14, gradient_tolerance=1e-9, parameter_tolerance=1e-14) if loop_scaling != 1.0 else {}
+    xh, Sh = api.pgo_optimize_ceres(ctx, start, ids, meas, P, **kw)
+    xd, Sd = api.pgo_optimize_device(ctx, start, ids, meas, P, **kw)
+    assert (Sd.iterations, Sd.successful_steps, Sd.termination) == (Sh.iterations, Sh.successful_steps, Sh.termination)
+    assert abs(Sd.final_cost - Sh.final_cost) <= 1e-9 * Sh.final_cost and abs(Sd.initial_cost - Sh.initial_cost) <= 1e-12 * Sh.initial_cost
+    assert np.abs(xd - xh).max() <= 1e-9 and np.array_equal(xd[0], start[0])
+    c_ref, _, _, g_ref, _ = oracle.pgo_assemble(xd, ids, meas, OP)
+    c0, _, _, g0, _ = oracle.pgo_assemble(start, ids, meas, OP)
+    assert abs(Sd.final_cost - c_ref) <= 1e-10 * c_ref and c_ref < c0
+    if loop_scaling != 1.0:
+        assert np.abs(g_ref).max() <= 1e-6 * np.abs(g0).max()
+    assert Sd.device_ms > 0
+
+
+def test_pgo_optimize_full_sequence_graph_beats_the_reference_time(ctx, oracle):
+    """SURVEY 6 / VERDICT r1: the reference's CeresLeastSquares needs 1.23 s for an Oxford sequence graph (4.5 k nodes, 5.2 k constraints) on one
+    CPU thread.  A same-size graph (noisy odometry chain + a loop every 5th node one lap back, TBV's loop weighting, Ceres' default
+    tolerances) is optimised on the device, whole LM loop included, in less than half of that — and in less than 8 ms per LM iteration
+    (measured on a B200: ~4 ms per iteration, of which ~30 chain-preconditioned CG iterations of ~0.12 ms; profiles/r2c_pgo_bench.json) —
+    and the run must stop on a Ceres tolerance at a point where the oracle's cost equals the summary's."""
+    rng = np.random.default_rng(5)
+    truth, start, ids, meas = _ring_graph(4500, rng)
+    assert len(ids) > 5200
+    x, S = api.pgo_optimize_device(ctx, start, ids, meas)            # warm-up (pool allocations)
+    x, S = api.pgo_optimize_device(ctx, start, ids, meas)
+    assert S.termination in ("function_tolerance", "gradient_tolerance", "parameter_tolerance") and S.final_cost < S.initial_cost
+    c_ref = oracle.pgo_assemble(x, ids, meas)[0]
+    assert abs(S.final_cost - c_ref) <= 1e-9 * c_ref
+    assert S.device_ms < 615.0 and S.device_ms < 8.0 * S.iterations, S

@@ -22,8 +22,7 @@ from test_loop_gpu import _damped_system, _graph  # noqa: E402
 def main():
     import scipy.sparse.linalg as spl
     ctx = api.Context(0)
-    out = {"kernel": "pgo_pcg_chain" if os.environ.get("TBV_PGO_CHAIN") else ("pgo_pcg_cluster" if os.environ.get("TBV_PGO_CLUSTER") else "pgo_pcg"),
-           "cases": []}
+    out = {"kernel": "pgo_pcg_cr", "cases": []}
     ok = True
     for n, radius, fixed in ((2, 1e4, 0), (7, 1e4, 3), (30, 1e4, 0), (600, 1e4, 0), (600, 1e2, 17), (600, 1e8, 17), (4500, 1e4, 0), (4500, 1e2, 0)):
         rng = np.random.default_rng(n)

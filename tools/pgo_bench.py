@@ -54,19 +54,25 @@ def main():
         w, k = timed(ctx, lambda: api.pgo_assemble(ctx, nodes, ids, meas), reps=3)
         _, Hd, Ho, g, _ = api.pgo_assemble(ctx, nodes, ids, meas)
         row = {"constraints": int(len(ids)), "assemble_call_ms": round(w, 3), "assemble_kernel_ms": round(sum(k.values()), 4)}
-        for radius in (1e4, 1e2):
+        for radius in (1e4, 1e2, 1e8):
             res = {}
             def step():
                 res["r"] = api.pgo_solve_step(ctx, ids, Hd, Ho, g, radius=radius, rel_tol=1e-10)
             w, k = timed(ctx, step, reps=3)
             it = res["r"][1]
-            row["solve_step_radius_%g" % radius] = {"cg_iterations": it, "call_ms": round(w, 3), "kernel_ms": round(k.get("pgo_pcg", 0.0), 3),
-                                                    "us_per_cg_iteration": round(1e3 * k.get("pgo_pcg", 0.0) / max(it, 1), 3)}
+            row["solve_step_radius_%g" % radius] = {"cg_iterations": it, "call_ms": round(w, 3), "kernel_ms": round(k.get("pgo_pcg_cr", 0.0), 3),
+                                                    "us_per_cg_iteration": round(1e3 * k.get("pgo_pcg_cr", 0.0) / max(it, 1), 3)}
+        api.pgo_optimize_device(ctx, nodes, ids, meas)    # warm-up
         t0 = time.perf_counter()
-        _, S = api.pgo_optimize(ctx, nodes, ids, meas, max_num_iterations=20)
-        row["optimize_20_lm_iterations"] = {"wall_ms": round(1e3 * (time.perf_counter() - t0), 1), "lm_iterations": S.iterations,
-                                          "cg_iterations": S.cg_iterations, "termination": S.termination,
-                                          "cost": [S.initial_cost, S.final_cost]}
+        _, S = api.pgo_optimize_device(ctx, nodes, ids, meas)                  # Ceres defaults (200 iterations, 1e-6 / 1e-10 / 1e-8), whole loop on the device
+        row["optimize_device"] = {"wall_ms": round(1e3 * (time.perf_counter() - t0), 2), "device_ms": round(S.device_ms, 3), "lm_iterations": S.iterations,
+                                  "successful_steps": S.successful_steps, "cg_iterations": S.cg_iterations, "termination": S.termination,
+                                  "cost": [S.initial_cost, S.final_cost]}
+        t0 = time.perf_counter()
+        _, Sh = api.pgo_optimize_ceres(ctx, nodes, ids, meas)                  # the same rules driven from the host, blocks crossing PCIe every iteration
+        row["optimize_host_driven"] = {"wall_ms": round(1e3 * (time.perf_counter() - t0), 1), "lm_iterations": Sh.iterations, "cg_iterations": Sh.cg_iterations,
+                                       "termination": Sh.termination, "cost": [Sh.initial_cost, Sh.final_cost]}
+        row["reference_cpu_ms"] = "1230 (CeresLeastSquares on a 4.5 k-node Oxford graph, one CPU thread; SURVEY 6)" if n == 4500 else None
         out["%d nodes" % n] = row
         print(json.dumps({"%d nodes" % n: row}), file=sys.stderr, flush=True)
     print(json.dumps(out, indent=1))
