@@ -847,7 +847,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
             ti = -1;
           }
         }
-        assoc[(size_t)fi * slot_cap + j] = ti;
+        if (mode == REG_MODE_EVAL) assoc[(size_t)fi * slot_cap + j] = ti;   // read back only by tbv_pair_normal_eq; the registration loop never needs it
       }
       // the accepted correspondences of this warp, in slot order, go to the warp's own segment of the block arrays (it starts at
       // the warp's first slot): the warp that writes a block is the warp that evaluates it, so no second pass and no barrier
@@ -1115,7 +1115,7 @@ int reg_scratch_reserve(tbv_ctx* ctx, int n_problems, int max_fixed, int slot_ca
   RegScratch& S = *reg_scratch(ctx);
   const size_t slots = (size_t)n_problems * max_fixed * slot_cap;
   int rc;
-  if ((rc = S.assoc.reserve(slots)) || (rc = S.wgt.reserve(slots)) || (rc = S.blocks.reserve(slots * BLK_FIELDS)) || (rc = S.n_blocks.reserve(n_problems)))
+  if ((rc = S.assoc.reserve(slots)) || (rc = S.blocks.reserve(slots * BLK_FIELDS)) || (rc = S.n_blocks.reserve(n_problems)))
     return rc;
   if (want_residuals && (rc = S.residuals.reserve(slots * 2))) return rc;
   return TBV_OK;
@@ -1142,7 +1142,7 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   if ((rc = ensure_dyn_smem(ctx, k_register<4>, RG_STAGE))) return rc;
   k_register<4><<<n_problems, RG_THREADS, RG_STAGE, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, S.wgt.p, dbg, RG_STAGE);
+                                                               want_residuals ? S.residuals.p : nullptr, nullptr, dbg, RG_STAGE);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
 #ifdef TBV_DEV_TIMERS
