@@ -230,6 +230,10 @@ int tbv_odom_step(tbv_odom* od, const uint8_t* polar_host, tbv_odom_out* out);
  * [n_range][n_az] (MulRan and every non-Oxford dataset: radar_driver.cpp:74-90) and is rotated 90 deg CCW on the device as the
  * first launch of the step — cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on receipt.  Default 0: azimuth-major [n_az][n_range] (Oxford). */
 int tbv_odom_set_wire_layout(tbv_odom* od, int range_major);
+/* The step (7 kernel launches) is replayed from a CUDA graph once an input buffer has been seen twice — the upload buffers of
+ * tbv_odom_step / _submit, or a caller's own ring of device buffers passed to tbv_odom_step_dev.  enable = 0 turns that off (direct
+ * launches); default on.  Results are identical either way. */
+int tbv_odom_set_graphs(tbv_odom* od, int enable);
 /* scans already on the device; results stay on the device until tbv_odom_fetch */
 int tbv_odom_step_dev(tbv_odom* od, const uint8_t* polar_dev);
 int tbv_odom_fetch(tbv_odom* od, tbv_odom_out* out);

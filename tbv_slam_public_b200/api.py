@@ -138,6 +138,7 @@ _OPTIONAL = [
     ("tbv_odom_destroy", [C.c_void_p], None),
     ("tbv_odom_reset", [C.c_void_p], None),
     ("tbv_odom_set_wire_layout", [C.c_void_p, C.c_int], None),
+    ("tbv_odom_set_graphs", [C.c_void_p, C.c_int], None),
     ("tbv_odom_step", [C.c_void_p, C.c_void_p, C.c_void_p], None),
     ("tbv_odom_step_dev", [C.c_void_p, C.c_void_p], None),
     ("tbv_odom_fetch", [C.c_void_p, C.c_void_p], None),
@@ -523,6 +524,10 @@ class OdometryKeyframeFuser:
             self.close()
         except Exception:
             pass
+
+    def set_graphs(self, enable: bool):
+        """CUDA-graph replay of the step for input buffers seen before (default on)."""
+        _check(lib().tbv_odom_set_graphs(self.h, int(bool(enable))))
 
     def set_wire_layout(self, range_major: bool):
         """True: scans arrive [n_range][n_az] (MulRan wire layout) and are rotated 90 deg CCW on the device on receipt (radar_driver.cpp:80-84)."""

@@ -964,6 +964,16 @@ void cells_release(tbv_ctx* ctx) {
   ctx->cells_scratch = nullptr;
 }
 
+uint64_t cells_fingerprint(tbv_ctx* ctx) {
+  if (!ctx->cells_scratch) return 0;
+  const CellsScratch& S = *(CellsScratch*)ctx->cells_scratch;
+  uint64_t h = 1;
+  for (const void* p : {(const void*)S.cand.p, (const void*)S.err.p, (const void*)S.sx.p, (const void*)S.sy.p, (const void*)S.si.p, (const void*)S.vidx16.p,
+                        (const void*)S.order16.p, (const void*)S.dbg.p})
+    h = fp_mix(h, p);
+  return h;
+}
+
 int cells_build_dev(tbv_ctx* ctx, const float* x, const float* y, const uint8_t* inten_u8, const float* inten_f32, const int* count_dev,
                     int cap_pts, int batch, const CellsParams& par, int cell_cap, CellStore& out) {
   TBV_REQUIRE(par.radius > 0.f && par.downsample_factor > 0.0, "radius and downsample_factor must be positive");

@@ -223,6 +223,11 @@ struct tbv_odom {
   cudaEvent_t uploaded[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
   tbv_odom_out* outs_host[2] = {nullptr, nullptr};  // pinned
   int n_submitted = 0, n_collected = 0;
+  // CUDA graphs of the step, one per input buffer the caller keeps handing in (the two upload buffers of the submit / collect pipeline, or a
+  // caller's own ring): the second step on a buffer is captured, every later one is a single cudaGraphLaunch instead of 7 kernel launches
+  struct StepGraph { const uint8_t* key = nullptr; cudaGraphExec_t exec = nullptr; int launches = 0; int seen = 0; uint64_t fp = 0; };
+  StepGraph graphs[4];
+  int use_graphs = 1, steps_done = 0;
   int wire_range_major = 0;        // scans arrive [n_range][n_az] (MulRan wire layout) and are rotated on receipt (tbv_odom_set_wire_layout)
   DevBuf<uint8_t> rotated;         // [n_seq][n_az][n_range] azimuth-major copies of the step's scans
 };
@@ -234,6 +239,7 @@ static void odom_free(tbv_odom* od) {
   if (od->copy_stream) cudaStreamSynchronize(od->copy_stream);
   od->state.release(); od->mot.release(); od->fixed_pose.release(); od->problems.release(); od->fixed_set.release();
   od->rotated.release();
+  for (auto& g : od->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   od->results.release(); od->views.release(); od->fused_set.release(); od->kf_grids.release(); od->outs_dev.release(); od->cur.release(); od->kf.release();
   for (int i = 0; i < 2; i++) {
     od->polar[i].release();
@@ -310,6 +316,69 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   return cellgrid_build_launch(ctx, od->views.p, od->fused_set.p, n_seq, n_seq * (od->K + 1), od->cpar.max_extent);
 }
 
+// One step through a cached CUDA graph when the input buffer has been seen before (the launch-bound regime is the online one: one
+// sequence per step, where the 7 launches of the step cost as much as its kernels); direct launches otherwise and while profiling.
+static uint64_t step_fingerprint(tbv_odom* od) {   // every context-level buffer the step's kernels were handed
+  tbv_ctx* ctx = od->ctx;
+  const FilterState& F = ctx->filt;
+  uint64_t h = fp_mix(cells_fingerprint(ctx), (const void*)(uintptr_t)reg_fingerprint(ctx));
+  for (const DevCloud* c : {&F.filtered, &F.peaks})
+    for (const void* p : {(const void*)c->x.p, (const void*)c->y.p, (const void*)c->inten.p, (const void*)c->az.p, (const void*)c->rg.p, (const void*)c->count.p})
+      h = fp_mix(h, p);
+  h = fp_mix(h, F.cs_table.p); h = fp_mix(h, F.th_table.p); h = fp_mix(h, od->rotated.p);
+  return h;
+}
+
+static int odom_enqueue_graphed(tbv_odom* od, const uint8_t* polar_dev) {
+  tbv_ctx* ctx = od->ctx;
+  if (!od->use_graphs || ctx->prof.on || od->steps_done < 1) {   // the first step allocates and sets kernel attributes: never captured
+    od->steps_done++;
+    return odom_enqueue(od, polar_dev);
+  }
+  od->steps_done++;
+  tbv_odom::StepGraph* slot = nullptr;
+  for (auto& g : od->graphs)
+    if (g.key == polar_dev) { slot = &g; break; }
+  if (slot && slot->exec) {
+    if (slot->fp == step_fingerprint(od)) {
+      TBV_CUDA(cudaGraphLaunch(slot->exec, ctx->stream));
+      ctx->launches += slot->launches;
+      return TBV_OK;
+    }
+    cudaGraphExecDestroy(slot->exec);   // a scratch buffer of the context moved since the capture (another caller grew it): capture again
+    slot->exec = nullptr;
+  }
+  if (!slot) {   // first time this buffer is seen: remember it (replacing the least used entry) and launch directly
+    slot = &od->graphs[0];
+    for (auto& g : od->graphs)
+      if (g.seen < slot->seen) slot = &g;
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+    slot->key = polar_dev; slot->seen = 1; slot->launches = 0;
+    return odom_enqueue(od, polar_dev);
+  }
+  // second step on this buffer: capture it
+  slot->seen++;
+  const long long before = ctx->launches;
+  cudaGraph_t graph = nullptr;
+  TBV_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = odom_enqueue(od, polar_dev);
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != TBV_OK || e != cudaSuccess || !graph) {   // not capturable in this state: run directly, stop trying
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    ctx->launches = before;
+    od->use_graphs = 0;
+    return odom_enqueue(od, polar_dev);
+  }
+  slot->fp = step_fingerprint(od);
+  slot->launches = (int)(ctx->launches - before);   // counted once during the capture: that count stands for the launch below
+  cudaError_t ei = cudaGraphInstantiate(&slot->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) { slot->exec = nullptr; cudaGetLastError(); ctx->launches = before; od->use_graphs = 0; return odom_enqueue(od, polar_dev); }
+  TBV_CUDA(cudaGraphLaunch(slot->exec, ctx->stream));
+  return TBV_OK;
+}
+
 extern "C" {
 
 tbv_odom* tbv_odom_create(tbv_ctx* ctx, int n_seq, int n_az, int n_range, const tbv_odom_params* params) {
@@ -355,8 +424,16 @@ int tbv_odom_reset(tbv_odom* od) {
   return TBV_OK;
 }
 
+int tbv_odom_set_graphs(tbv_odom* od, int enable) {
+  TBV_REQUIRE(od, "null handle");
+  od->use_graphs = enable != 0;
+  return TBV_OK;
+}
+
 int tbv_odom_set_wire_layout(tbv_odom* od, int range_major) {
   TBV_REQUIRE(od, "null handle");
+  if (od->wire_range_major != (range_major != 0))
+    for (auto& g : od->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = tbv_odom::StepGraph(); }   // captured steps had the other layout
   od->wire_range_major = range_major != 0;
   return TBV_OK;
 }
@@ -365,7 +442,7 @@ int tbv_odom_step_dev(tbv_odom* od, const uint8_t* polar_dev) {
   TBV_ENTER(od ? od->ctx : nullptr);
   TBV_REQUIRE(od && polar_dev, "null pointer");
   cudaSetDevice(od->ctx->device);
-  return odom_enqueue(od, polar_dev);
+  return odom_enqueue_graphed(od, polar_dev);
 }
 
 int tbv_odom_fetch(tbv_odom* od, tbv_odom_out* out) {
@@ -405,7 +482,7 @@ int tbv_odom_submit(tbv_odom* od, const uint8_t* polar_host) {
   TBV_CUDA(cudaMemcpyAsync(od->polar[b].p, polar_host, bytes, cudaMemcpyHostToDevice, od->copy_stream));
   TBV_CUDA(cudaEventRecord(od->uploaded[b], od->copy_stream));
   TBV_CUDA(cudaStreamWaitEvent(od->ctx->stream, od->uploaded[b], 0));
-  rc = odom_enqueue(od, od->polar[b].p);
+  rc = odom_enqueue_graphed(od, od->polar[b].p);
   if (rc) return rc;
   TBV_CUDA(cudaEventRecord(od->consumed[b], od->ctx->stream));
   TBV_CUDA(cudaMemcpyAsync(od->outs_host[b], od->outs_dev.p, (size_t)od->n_seq * sizeof(tbv_odom_out), cudaMemcpyDeviceToHost, od->ctx->stream));

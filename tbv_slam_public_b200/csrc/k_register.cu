@@ -1104,6 +1104,14 @@ RegScratch* reg_scratch(tbv_ctx* ctx) {
   if (!ctx->reg_scratch) ctx->reg_scratch = new RegScratch();
   return (RegScratch*)ctx->reg_scratch;
 }
+uint64_t reg_fingerprint(tbv_ctx* ctx) {
+  if (!ctx->reg_scratch) return 0;
+  const RegScratch& S = *(RegScratch*)ctx->reg_scratch;
+  uint64_t h = 2;
+  for (const void* p : {(const void*)S.assoc.p, (const void*)S.blocks.p, (const void*)S.n_blocks.p, (const void*)S.residuals.p, (const void*)S.dbg.p})
+    h = fp_mix(h, p);
+  return h;
+}
 void reg_release(tbv_ctx* ctx) {
   if (!ctx->reg_scratch) return;
   RegScratch* s = (RegScratch*)ctx->reg_scratch;

@@ -175,6 +175,11 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
 // batched cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on the device (k_misc.cu): src [batch][rows][cols] -> dst [batch][cols][rows]
 int rotate90ccw_dev(tbv_ctx* ctx, const uint8_t* src_dev, int rows, int cols, int batch, uint8_t* dst_dev);
 int compensate_clouds_dev(tbv_ctx* ctx, DevCloud& cloud, const double* mot_dev /*[batch][3]*/, int ccw);
+// Hash of the device pointers of a context's grow-on-demand scratch (they move when another caller on the same context asks for more):
+// a captured graph of the odometry step is valid only while these are what they were at capture time.
+inline uint64_t fp_mix(uint64_t h, const void* p) { return (h ^ (uint64_t)reinterpret_cast<uintptr_t>(p)) * 0x9E3779B97F4A7C15ull; }
+uint64_t cells_fingerprint(tbv_ctx* ctx);   // k_cells.cu
+uint64_t reg_fingerprint(tbv_ctx* ctx);     // k_register.cu
 void cells_release(tbv_ctx* ctx);
 void reg_release(tbv_ctx* ctx);
 void comm_release(tbv_ctx* ctx);

@@ -166,3 +166,27 @@ def test_pipelined_submit_collect_matches_sync(ctx):
     f2.close()
     for a, b in zip(sync, got):
         assert np.array_equal(a, b)
+
+
+def test_cuda_graph_replay_of_the_step_changes_nothing(ctx, stream8):
+    """The step is replayed from a CUDA graph once an input buffer has been seen twice (tbv_odom_set_graphs, default on): same poses, counts
+    and keyframe decisions, bit for bit, as direct launches — also after another fuser on the same context has grown the context's scratch
+    buffers (the captured graphs are then stale and must be re-captured, not replayed)."""
+    a = api.OdometryKeyframeFuser(ctx, 1, 400, 3768)            # graphs on: host path alternates between its two upload buffers
+    b = api.OdometryKeyframeFuser(ctx, 1, 400, 3768)
+    b.set_graphs(False)
+    l0 = ctx.launch_count()
+    for f in range(6):
+        oa = a.pointcloudCallback(stream8.scans[f][None])
+        ob = b.pointcloudCallback(stream8.scans[f][None])
+        assert np.array_equal(api.poses(oa), api.poses(ob))
+        assert (oa[0].n_points, oa[0].n_cells, oa[0].itrs, oa[0].is_keyframe) == (ob[0].n_points, ob[0].n_cells, ob[0].itrs, ob[0].is_keyframe)
+    per_step = (ctx.launch_count() - l0) / 12
+    assert 6 <= per_step <= 8                                   # replayed steps are counted like launched ones
+    big = api.OdometryKeyframeFuser(ctx, 3, 400, 3768)          # grows the context's filter / cells / registration scratch
+    big.pointcloudCallback(stream8.scans[:3])
+    for f in range(6, 8):
+        oa = a.pointcloudCallback(stream8.scans[f][None])
+        ob = b.pointcloudCallback(stream8.scans[f][None])
+        assert np.array_equal(api.poses(oa), api.poses(ob)) and oa[0].n_cells == ob[0].n_cells
+    a.close(); b.close(); big.close()
