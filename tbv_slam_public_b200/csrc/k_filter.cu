@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(KF_THREADS, 4)
 k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t row_stride, int z_min, int k, int want_peaks, int rowbuf, int n_groups,
                 const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, double range_res, const double2* __restrict__ cs_table,
                 const double* __restrict__ th_table, int cap, KfCloud out_f, int* __restrict__ fcount, KfCloud out_p, int* __restrict__ pcount,
-                const double* __restrict__ mot, int ccw) {
+                const double* __restrict__ mot, int ccw, int split, KfCloud tmp_f, KfCloud tmp_p, int2* __restrict__ seg_tot, int* __restrict__ seg_done) {
   extern __shared__ __align__(128) uint8_t s_dyn[];                   // [KF_WARPS][2][rowbuf] staged rows, 
   __shared__ __align__(16) uint32_t s_list[KF_WARPS][2 * CAP + 4];     // candidates of the row pair (unordered, zero-padded to a multiple of 4)
   __shared__ __align__(16) uint32_t s_sel[KF_WARPS][2 * CAP];          // P1: queue of flagged vectors (u16); P2: selected entries, ascending
@@ -293,7 +293,12 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
   __shared__ __align__(8) uint64_t s_chain_bar[KF_WARPS];              // phase c completes when the warp has published its totals of chunk c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned FULL = 0xffffffffu;
-  const int scan = blockIdx.x;
+  // split == 1: the CTA owns the whole scan.  split > 1 (small batches: fewer scans than the GPU has CTA slots): `split` CTAs share a scan,
+  // each a contiguous block of row pairs [row_lo, row_hi); a block's points go to its own segment of the scratch clouds and the CTA that
+  // finishes last moves the segments behind one another into the final clouds.
+  const int scan = blockIdx.x / split, seg = blockIdx.x - scan * split;
+  const int seg_rows = 2 * ((((n_az + 1) >> 1) + split - 1) / split);
+  const int row_lo = min(n_az, seg * seg_rows), row_hi = min(n_az, row_lo + seg_rows);
   const uint32_t z = (uint32_t)z_min;
   const bool zero_thr = z == 0;   // every byte is a candidate: no sparse pass
   const uint32_t addc = (HI ? (256u - z) : (128u - z)) * 0x01010101u;
@@ -314,12 +319,16 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
   uint32_t in_flight = 0;   // bit x: a bulk copy into buffer x is under way
 #pragma unroll
   for (int x = 0; x < 2; x++)
-    if (2 * warp + x < n_az && stage_row_tma(bufs + x * rowbuf, scan_base + (size_t)(2 * warp + x) * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
+    if (row_lo + 2 * warp + x < row_hi &&
+        stage_row_tma(bufs + x * rowbuf, scan_base + (size_t)(row_lo + 2 * warp + x) * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
       in_flight |= 1u << x;
   double m0 = 0.0, m1 = 0.0, m2 = 0.0;
   if (mot) { m0 = mot[scan * 3 + 0]; m1 = mot[scan * 3 + 1]; m2 = mot[scan * 3 + 2]; }
   const double range_res_half = range_res / 2.0;
   const size_t cbase = (size_t)scan * cap;
+  const KfCloud dst_f = split == 1 ? out_f : tmp_f, dst_p = split == 1 ? out_p : tmp_p;
+  const size_t dbase = split == 1 ? cbase : cbase + (size_t)row_lo * (size_t)k;   // a block of R rows emits at most R * k points
+  __shared__ int s_last;
   __syncthreads();   // every warp's chain barrier is initialised before a neighbour waits on it
 
   // Conservative test "some byte of the 16 may be >= z_min" (never misses one; false positives only next to a byte >= 188):
@@ -330,7 +339,7 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
     return ((a | b | c | d) & 0x80808080u) != 0;
   };
 
-  for (int row0 = 0, chunk = 0; row0 < n_az; row0 += 2 * KF_WARPS, chunk++) {
+  for (int row0 = row_lo, chunk = 0; row0 < row_hi; row0 += 2 * KF_WARPS, chunk++) {
     // =============================== P1: the warp's two rows ========================================================================
     const int rowA = row0 + 2 * warp;
     KfRow R[2];
@@ -339,7 +348,7 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
 #pragma unroll
     for (int x = 0; x < 2; x++) {
       R[x].buf = bufs + x * rowbuf; R[x].a0 = 0; R[x].nvec = 0;
-      if (rowA + x >= n_az) continue;
+      if (rowA + x >= row_hi) continue;
       have |= 1u << x;
       const uint8_t* rp = scan_base + (size_t)(rowA + x) * row_stride;
       R[x].a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
@@ -519,7 +528,7 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
 #pragma unroll
     for (int x = 0; x < 2; x++) {
       const int nrow_next = rowA + 2 * KF_WARPS + x;
-      if (nrow_next < n_az && stage_row_tma(bufs + x * rowbuf, scan_base + (size_t)nrow_next * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
+      if (nrow_next < row_hi && stage_row_tma(bufs + x * rowbuf, scan_base + (size_t)nrow_next * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
         in_flight |= 1u << x;
     }
 
@@ -563,10 +572,10 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
           float y = (float)__dmul_rn(rho, cs.y);
           if (mot) compensate_polar_point(x, y, cs.x, cs.y, th_table[az], m0, m1, m2, ccw);
           const uint8_t inten = (uint8_t)((ent >> 18) & 0xffu);
-          if (q < cap) kf_store(out_f, cbase + q, x, y, inten, az, r);
+          if (q < cap) kf_store(dst_f, dbase + q, x, y, inten, az, r);
           if (fp) {
             const int qp = base_p + __popc(bp & lt);
-            if (qp < cap) kf_store(out_p, cbase + qp, x, y, inten, az, r);
+            if (qp < cap) kf_store(dst_p, dbase + qp, x, y, inten, az, r);
           }
         }
         base_f += __popc(bf);
@@ -576,10 +585,46 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
     __syncwarp();   // every lane is done with sel before the next chunk reuses it
   }
   __syncthreads();
+  const int n_chunks = (row_hi - row_lo + 2 * KF_WARPS - 1) / (2 * KF_WARPS);
+  const int my_f = n_chunks > 0 ? s_chain[KF_WARPS - 1][0] : 0, my_p = n_chunks > 0 ? s_chain[KF_WARPS - 1][1] : 0;
+  if (split == 1) {
+    if (tid == 0) {
+      fcount[scan] = my_f < cap ? my_f : cap;
+      if (want_peaks) pcount[scan] = my_p < cap ? my_p : cap;
+    }
+    return;
+  }
+  // ---- split scans: publish this block's totals; the CTA that arrives last compacts the scan ------------------------------------------------
   if (tid == 0) {
-    const int tot_f = s_chain[KF_WARPS - 1][0], tot_p = s_chain[KF_WARPS - 1][1];
-    fcount[scan] = tot_f < cap ? tot_f : cap;
-    if (want_peaks) pcount[scan] = tot_p < cap ? tot_p : cap;
+    seg_tot[scan * split + seg] = make_int2(my_f, my_p);
+    __threadfence();                                   // totals and scratch points before the arrival
+    s_last = atomicAdd(&seg_done[scan], 1) == split - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  int off_f = 0, off_p = 0;
+  for (int c = 0; c < split; c++) {
+    const int2 t = __ldcg(&seg_tot[scan * split + c]);
+    const size_t src = cbase + (size_t)min(n_az, c * seg_rows) * (size_t)k;
+    for (int i = tid; i < t.x; i += KF_THREADS)
+      if (off_f + i < cap) {
+        const size_t q = cbase + off_f + i;
+        out_f.x[q] = __ldcg(tmp_f.x + src + i); out_f.y[q] = __ldcg(tmp_f.y + src + i); out_f.i[q] = __ldcg(tmp_f.i + src + i);
+        out_f.az[q] = __ldcg(tmp_f.az + src + i); out_f.rg[q] = __ldcg(tmp_f.rg + src + i);
+      }
+    for (int i = tid; i < t.y; i += KF_THREADS)
+      if (off_p + i < cap) {
+        const size_t q = cbase + off_p + i;
+        out_p.x[q] = __ldcg(tmp_p.x + src + i); out_p.y[q] = __ldcg(tmp_p.y + src + i); out_p.i[q] = __ldcg(tmp_p.i + src + i);
+        out_p.az[q] = __ldcg(tmp_p.az + src + i); out_p.rg[q] = __ldcg(tmp_p.rg + src + i);
+      }
+    off_f += t.x; off_p += t.y;
+  }
+  if (tid == 0) {
+    fcount[scan] = off_f < cap ? off_f : cap;
+    if (want_peaks) pcount[scan] = off_p < cap ? off_p : cap;
+    seg_done[scan] = 0;                                // ready for the next launch
   }
 }
 
@@ -644,6 +689,22 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   const int n_groups = (nvec_max + 1 + 31) / 32;
   const int rowbuf = n_groups * 512;
   const size_t k1_smem = (size_t)KF_WARPS * 2 * rowbuf;    // two row buffers per warp
+  // Fewer scans than resident CTA slots (4 per SM): split every scan over several CTAs so that the whole GPU streams (the online node
+  // hands over ONE scan at a time: 32 CTAs of ~12 rows).
+  int split = 1;
+  {
+    const int slots = 4 * ctx->sm_count, n_pairs = (n_az + 1) / 2;
+    while (split < 32 && batch * split * 2 <= slots && n_pairs / (split * 2) >= KF_WARPS) split *= 2;   // a block keeps >= one chunk of rows
+  }
+  if (split > 1) {
+    if ((rc = F.tmp_f.reserve(batch, n_az * k))) return rc;
+    if (want_peaks && (rc = F.tmp_p.reserve(batch, n_az * k))) return rc;
+    if ((rc = F.seg_tot.reserve((size_t)batch * split))) return rc;
+    if (F.seg_done.n < (size_t)batch) {
+      if ((rc = F.seg_done.reserve(batch))) return rc;
+      TBV_CUDA(cudaMemsetAsync(F.seg_done.p, 0, F.seg_done.n * sizeof(int), ctx->stream));   // the kernel leaves the counters at zero
+    }
+  }
   const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
   const double rr = (double)p->range_res;                                   // widened float (radar_filters.h:86)
   const int min_range_bin = (int)std::ceil((double)p->min_distance / rr);   // radar_filters.cpp:315
@@ -651,9 +712,9 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
     const int rc2 = ensure_dyn_smem(ctx, kern, k1_smem);
     if (rc2) return rc2;
     auto cl = [](DevCloud& c) { return KfCloud{c.x.p, c.y.p, c.inten.p, c.az.p, c.rg.p}; };
-    kern<<<batch, KF_THREADS, k1_smem, ctx->stream>>>(polar_dev, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf, n_groups, polar_dev, buf_hi,
+    kern<<<batch * split, KF_THREADS, k1_smem, ctx->stream>>>(polar_dev, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf, n_groups, polar_dev, buf_hi,
                                                      min_range_bin, rr, F.cs_table.p, F.th_table.p, n_az * k, cl(F.filtered), F.filtered.count.p, cl(F.peaks),
-                                                     F.peaks.count.p, mot_dev, ccw);
+                                                     F.peaks.count.p, mot_dev, ccw, split, cl(F.tmp_f), cl(F.tmp_p), F.seg_tot.p, F.seg_done.p);
     return TBV_OK;
   };
   // compile-time variants: byte-compare form (z_min > 128), unrolled scan for the two dataset shapes, list capacity 64 (k <= 64) or 128

@@ -134,7 +134,7 @@ void tbv_destroy(tbv_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   FilterState& F = ctx->filt;
-  F.polar.release(); F.cs_table.release(); F.th_table.release(); F.filtered.release(); F.peaks.release();
+  F.polar.release(); F.cs_table.release(); F.th_table.release(); F.filtered.release(); F.peaks.release(); F.tmp_f.release(); F.tmp_p.release(); F.seg_tot.release(); F.seg_done.release();
   cells_release(ctx);
   reg_release(ctx);
   comm_release(ctx);

@@ -108,6 +108,9 @@ struct FilterState {  // device-resident result of the last k-strongest call
   DevBuf<double> th_table;     // [n_az] atan2(sin theta, cos theta), host glibc: the azimuth as Compensate's atan2 sees it
   int cs_n_az = 0;
   DevCloud filtered, peaks;
+  DevCloud tmp_f, tmp_p;       // split scans only (small batches): per-block segments, moved into filtered / peaks by the scan's last CTA
+  DevBuf<int2> seg_tot;        // [batch][split] points / peaks of every block
+  DevBuf<int> seg_done;        // [batch] arrival counters, zero between launches
 };
 
 struct SmemOptIn {  // largest dynamic shared-memory size a kernel has been opted into on this context's device
