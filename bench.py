@@ -90,7 +90,7 @@ def k1_traffic_per_scan(path: str):
     not carry a made-up number."""
     import re
     txt = open(os.path.join(ROOT, path)).read()
-    blocks = [b for b in txt.split("== ") if b.lstrip().startswith("void k1_filter_fused") or "k1_filter_fused" in b.split("\n", 1)[0]]
+    blocks = [b for b in txt.split("== ")[1:] if "k1_filter_fused" in b.split("\n", 1)[0] and "grid (" in b.split("\n", 1)[0]]
     if not blocks:
         raise RuntimeError(f"{path}: no k1_filter_fused launch in the ncu summary")
     b = blocks[0]
@@ -410,8 +410,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    k1_traffic_per_scan(K1_TRAFFIC_FILE)    # fail before any GPU work (and on every rank alike) when the committed ncu summary is unreadable
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that dies must not leave the others waiting for the default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     W, K, S = args.warmup, args.steps, args.seqs
     T = W + K
     pool, gt_pool = make_pool(T + POOL_EXTRA, rank, with_gt=True)

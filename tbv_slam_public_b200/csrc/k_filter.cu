@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   // suspend-time hint (10 ms cap): the warp is parked, not spinning
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
@@ -113,7 +113,10 @@ __device__ __forceinline__ void compensate_polar_point(float& x, float& y, doubl
   const double terr = __fma_rn(s, px, -t);                            // s * px = t + terr exactly
   const double cross = __dsub_rn(__fma_rn(c, py, -t), terr);          // c * py - s * px
   const double dot = __fma_rn(c, px, __dmul_rn(s, py));
-  const double a = __dadd_rn(th, __ddiv_rn(cross, dot));
+  // cross / dot is a correction of < 1e-7 rad: the reciprocal needs 1e-9 relative accuracy, one Newton step from the fp32 seed gives 1e-14
+  const double r0 = (double)__frcp_rn((float)dot);
+  const double rcp = __dmul_rn(r0, __dsub_rn(2.0, __dmul_rn(dot, r0)));
+  const double a = __dadd_rn(th, __dmul_rn(cross, rcp));
   double d = __ddiv_rn((a > 0.00001 ? a : __dadd_rn(two_pi, a)), two_pi);
   d = ccw ? -(__dsub_rn(d, 0.5)) : __dsub_rn(d, 0.5);
   const double ang = __dmul_rn(d, m2);

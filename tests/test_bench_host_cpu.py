@@ -45,3 +45,14 @@ def test_first_offsets_give_every_rank_the_same_mix_of_places():
     assert len(a) == len(c) == n_seq and not np.array_equal(a, c)
     place = lambda v: sorted(((np.asarray(v) - (np.arange(n_seq) * 5) % b.POOL_EXTRA) // n_frames).tolist())
     assert place(a) == place(c) == sorted(list(range(b.N_PLACES)) * 8)                      # every rank: the same mix of stretches
+
+
+def test_roofline_traffic_is_read_from_the_committed_ncu_summary():
+    """bench.py's roofline.traffic comes from profiles/ (VERDICT r1 weak #9): the parser must read the committed summary, and must fail loudly
+    on a file without a k1_filter_fused launch."""
+    import pytest
+    b = _bench()
+    per_scan, scans = b.k1_traffic_per_scan(b.K1_TRAFFIC_FILE)
+    assert scans >= 1 and 400 * 3768 <= per_scan <= 1.15 * (400 * 3768 + 208000)       # DRAM traffic per scan ~ the algorithmic bytes: no re-reads
+    with pytest.raises(Exception):
+        b.k1_traffic_per_scan("profiles/README.md")

@@ -1,21 +1,21 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, the bench (both arms), the ncu launch list and one full capture per top kernel.
+# One GPU-box visit: parity tests, smoke, the bench (both arms), the ncu launch list and one full capture per top kernel.
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-tail -c 600 gpurun_out/bench.json
+tail -c 400 gpurun_out/bench.json
 timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"
-cat gpurun_out/bench_reference.json | head -c 400
-# launch list: skip warm-up launches (3 warm-up steps x ~14 launches), 2 timed steps
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 2 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-for k in k_register cells_fused k1_kstrongest k2_make_clouds; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 2 -f -o gpurun_out/full_$k \
-     python bench.py --steps 2 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_full_$k.log 2>&1; echo "ncu full $k rc=$?"
+head -c 300 gpurun_out/bench_reference.json
+# launch list: skip the warm-up launches (5 warm-up steps x 7 launches), 2 timed steps
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 2 --warmup 5 --no-cpu-baseline --no-extra-legs > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+for k in k1_filter_fused k_register cells_fused; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o gpurun_out/full_$k \
+     python bench.py --steps 2 --warmup 5 --no-cpu-baseline --no-extra-legs > gpurun_out/ncu_full_$k.log 2>&1; echo "ncu full $k rc=$?"
 done
 ls -la gpurun_out
