@@ -109,6 +109,43 @@ def first_offsets(n_seq: int, n_frames: int, rank: int = 0):
     return (((j + rank) % N_PLACES) * n_frames + (j * 5) % POOL_EXTRA).astype(np.int32)
 
 
+def bind_to_gpu_numa_node(gpu_index: int) -> dict:
+    """Host-side placement for the e2e leg: run this rank's threads on, and take its pinned upload buffers from, the
+    NUMA node the GPU's PCIe root complex hangs off — so that eight ranks do not all pull their scans from node 0 across the socket
+    interconnect.  Reads the GPU's node from sysfs (nvidia-smi gives the PCI bus id); sched_setaffinity to the node's CPUs and
+    set_mempolicy(MPOL_PREFERRED, node) before any pinned allocation.  On a guest that exposes a single node (this pool's 1-GPU boxes do:
+    profiles/r2b_host_topology_1gpu_box.txt) there is nothing to choose and the record says so."""
+    info = {"nodes": 1, "gpu_node": None, "bound": False}
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        info["nodes"] = len(nodes)
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=20).stdout.strip().lower()
+        if bus.startswith("0000") and len(bus) > 12:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        info["gpu_node"] = node
+        if len(nodes) > 1 and node in nodes:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            allowed = os.sched_getaffinity(0) & cpus
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+            import ctypes
+            libc = ctypes.CDLL("libc.so.6", use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238            # x86-64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, mask, 16 * 64)
+            info["bound"] = bool(allowed) and rc == 0
+            info["cpus"] = len(allowed)
+    except Exception as e:  # placement is an optimisation: never fatal
+        info["error"] = str(e)[:120]
+    return info
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (the profiling recipe's clocks line)."""
 
@@ -410,6 +447,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)     # before any pinned allocation
     k1_traffic_per_scan(K1_TRAFFIC_FILE)    # fail before any GPU work (and on every rank alike) when the committed ncu summary is unreadable
     if world > 1:
         import datetime
@@ -640,7 +678,7 @@ def run_ours(args):
         "run": {"sequences_per_gpu": S, "scans_per_step": S * world, "gpus": world},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": S * 80,
                 "ms_per_step": round(e2e_s / K_e2e * 1e3, 4), "steps": K_e2e, "api": "tbv_odom_submit/tbv_odom_collect (pinned host scans, double-buffered)",
-                "h2d_gbs_per_gpu": h2d_gbs,
+                "h2d_gbs_per_gpu": h2d_gbs, "host_placement": numa,
                 "bound": "host->device link: every scan byte crosses PCIe once (1.5 MB per scan); the kernels need ~5 % of the step's copy time"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         # device ms per scan under the reference's timing keys (odometrykeyframefuser.cpp:253-256, radar_driver.cpp:87); compensation is

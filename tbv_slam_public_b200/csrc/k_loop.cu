@@ -296,7 +296,7 @@ int tbv_loopdb_register_sharded(tbv_loopdb* db, int n_cand, const int* from, con
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   int n = *n_all;
   if (n > all_capacity) { set_error("tbv_loopdb_register_sharded: %d constraints accepted, room for %d", n, all_capacity); n = all_capacity; rc = TBV_ERR_CAPACITY; }
-  if (n > 0) TBV_CUDA(cudaMemcpyAsync(all, comm_all(ctx), (size_t)n * sizeof(tbv_constraint), cudaMemcpyDeviceToHost, ctx->stream));
+  if (n > 0) { const int rc2 = comm_fetch_all(ctx, all, n); if (rc2) return rc2; }
   if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[3], ctx->stream));
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   if (timing_ms) {
