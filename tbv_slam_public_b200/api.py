@@ -486,12 +486,12 @@ class LoopDB:
         params = params or loop_reg_params()
         fs, ts, Tf, Tt, _, q = self._cand_args(id_from, id_to, T_from, T_to, None, quality)
         n = len(fs)
-        out = np.zeros(max(n, 1), CONSTRAINT_DTYPE)
+        out = np.empty(max(n, 1), CONSTRAINT_DTYPE)          # the library writes records [0, n_out); the view below is all the caller sees
         n_out = C.c_int(0)
         tm = (C.c_float * 4)() if want_timing else None
         _check(lib().tbv_loopdb_register_sharded(self.h, n, _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), _ptr(q), C.byref(params), float(max_score),
                                                  _ptr(out), n, C.byref(n_out), tm))
-        out = out[:n_out.value].copy()
+        out = out[:n_out.value]
         return (out, [float(v) for v in tm]) if want_timing else out
 
     def register_candidates_dev(self, id_from, id_to, T_from, T_to, out_dev_ptr: int, out_capacity: int, n_out_dev_ptr: int,

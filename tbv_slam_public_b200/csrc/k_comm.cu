@@ -109,20 +109,34 @@ int comm_reserve(tbv_ctx* ctx, int capacity) {
 tbv_constraint* comm_send_records(tbv_ctx* ctx) { return comm_state(ctx, true)->send.p + 1; }
 int* comm_send_count(tbv_ctx* ctx) { return reinterpret_cast<int*>(comm_state(ctx, true)->send.p); }
 tbv_constraint* comm_all(tbv_ctx* ctx) { return comm_state(ctx, true)->all.p; }
-// D2H of the first n merged records into `dst` (any host memory) through the context's pinned staging buffer; synchronises the stream
-int comm_fetch_all(tbv_ctx* ctx, tbv_constraint* dst, int n) {
+// Merged records -> `dst` (any host memory) through the context's pinned staging buffer; synchronises the stream.  The count and the
+// records cross in ONE round when the whole merged area is small (<= 4 MB: every batch the loop-closure flow produces) — one stream
+// synchronisation per call instead of count-then-records; larger areas fetch the count first and then exactly the valid records.
+// *n_out = number of merged records (may exceed dst_capacity: the caller reports TBV_ERR_CAPACITY; only dst_capacity are copied).
+int comm_fetch_all(tbv_ctx* ctx, tbv_constraint* dst, int dst_capacity, int* n_out) {
   CommState* S = comm_state(ctx, true);
-  if (n <= 0) return TBV_OK;
-  if (S->host_stage_n < (size_t)n) {
+  const size_t area = (size_t)S->world * (size_t)S->capacity;       // records the merge can have produced
+  if (S->host_stage_n < area + 1) {
     if (S->host_stage) cudaFreeHost(S->host_stage);
     S->host_stage = nullptr; S->host_stage_n = 0;
-    const size_t want = (size_t)S->world * (size_t)S->capacity > (size_t)n ? (size_t)S->world * (size_t)S->capacity : (size_t)n;
-    TBV_CUDA(cudaHostAlloc((void**)&S->host_stage, want * sizeof(tbv_constraint), cudaHostAllocDefault));
-    S->host_stage_n = want;
+    TBV_CUDA(cudaHostAlloc((void**)&S->host_stage, (area + 1) * sizeof(tbv_constraint), cudaHostAllocDefault));
+    S->host_stage_n = area + 1;
   }
-  TBV_CUDA(cudaMemcpyAsync(S->host_stage, S->all.p, (size_t)n * sizeof(tbv_constraint), cudaMemcpyDeviceToHost, ctx->stream));
+  int* count = reinterpret_cast<int*>(S->host_stage + area);         // the slot after the records holds the count
+  const size_t guess = area < (size_t)dst_capacity ? area : (size_t)dst_capacity;
+  const bool one_round = guess * sizeof(tbv_constraint) <= ((size_t)4 << 20);
+  TBV_CUDA(cudaMemcpyAsync(count, S->n_all.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (one_round && guess > 0) TBV_CUDA(cudaMemcpyAsync(S->host_stage, S->all.p, guess * sizeof(tbv_constraint), cudaMemcpyDeviceToHost, ctx->stream));
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
-  memcpy(dst, S->host_stage, (size_t)n * sizeof(tbv_constraint));
+  const int n = *count;
+  *n_out = n;
+  const size_t take = (size_t)(n < dst_capacity ? n : dst_capacity);
+  if (take == 0) return TBV_OK;
+  if (!one_round) {
+    TBV_CUDA(cudaMemcpyAsync(S->host_stage, S->all.p, take * sizeof(tbv_constraint), cudaMemcpyDeviceToHost, ctx->stream));
+    TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  memcpy(dst, S->host_stage, take * sizeof(tbv_constraint));
   return TBV_OK;
 }
 int* comm_n_all(tbv_ctx* ctx) { return comm_state(ctx, true)->n_all.p; }
@@ -286,14 +300,8 @@ int tbv_allgather_constraints(tbv_ctx* ctx, const tbv_constraint* local_dev, con
   const int* n_all_dev = nullptr;
   int rc = tbv_allgather_constraints_dev(ctx, local_dev, n_local_dev, capacity, &all_dev, &n_all_dev);
   if (rc) return rc;
-  TBV_CUDA(cudaMemcpyAsync(n_all, n_all_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
-  int n = *n_all;
-  if (n > all_capacity) { set_error("tbv_allgather_constraints: %d records gathered, room for %d", n, all_capacity); n = all_capacity; rc = TBV_ERR_CAPACITY; }
-  if (n > 0) {
-    const int rc2 = comm_fetch_all(ctx, all, n);
-    if (rc2) return rc2;
-  }
+  if ((rc = comm_fetch_all(ctx, all, all_capacity, n_all))) return rc;
+  if (*n_all > all_capacity) { set_error("tbv_allgather_constraints: %d records gathered, room for %d", *n_all, all_capacity); rc = TBV_ERR_CAPACITY; }
   return rc;
 }
 

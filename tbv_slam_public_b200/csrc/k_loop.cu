@@ -292,11 +292,8 @@ int tbv_loopdb_register_sharded(tbv_loopdb* db, int n_cand, const int* from, con
   if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[1], ctx->stream));
   if ((rc = comm_allgather_merge(ctx, capacity))) return rc;
   if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[2], ctx->stream));
-  TBV_CUDA(cudaMemcpyAsync(n_all, comm_n_all(ctx), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
-  int n = *n_all;
-  if (n > all_capacity) { set_error("tbv_loopdb_register_sharded: %d constraints accepted, room for %d", n, all_capacity); n = all_capacity; rc = TBV_ERR_CAPACITY; }
-  if (n > 0) { const int rc2 = comm_fetch_all(ctx, all, n); if (rc2) return rc2; }
+  if ((rc = comm_fetch_all(ctx, all, all_capacity, n_all))) return rc;
+  if (*n_all > all_capacity) { set_error("tbv_loopdb_register_sharded: %d constraints accepted, room for %d", *n_all, all_capacity); rc = TBV_ERR_CAPACITY; }
   if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[3], ctx->stream));
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   if (timing_ms) {

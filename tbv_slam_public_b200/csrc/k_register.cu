@@ -31,8 +31,26 @@
 
 namespace tbv {
 
-constexpr int RG_THREADS = 256;
+#ifndef RG_THREADS_V
+#define RG_THREADS_V 256
+#endif
+constexpr int RG_THREADS = RG_THREADS_V;
 constexpr int RG_WARPS = RG_THREADS / 32;
+#ifdef RG_CG_A
+#define RG_LDA(p) __ldcg(p)
+#else
+#define RG_LDA(p) (*(p))
+#endif
+#ifdef RG_CG_S
+#define RG_STA(p, v) __stcg(p, v)
+#else
+#define RG_STA(p, v) (*(p) = (v))
+#endif
+#ifdef RG_CG_B
+#define RG_LDB(p) __ldcg(p)
+#else
+#define RG_LDB(p) (*(p))
+#endif
 constexpr int NACC = 10;  // cost, g0..g2, H00,H01,H02,H11,H12,H22
 
 struct Aff {
@@ -133,8 +151,8 @@ __device__ void scaled_loss(int loss, double limit, double w, double s, double r
 // blk points at field 0 of the block (stride = field stride).
 __device__ __forceinline__ double eval_block(int cost_type, int loss, double limit, const double* __restrict__ blk, size_t stride,
                                              double x0, double x1, double cy, double sy, double f[2], double J[6], int& n, bool want_jac) {
-  const double sx = blk[0], sy_ = blk[stride], tx = blk[2 * stride], ty = blk[3 * stride];
-  const double a4 = blk[4 * stride], a5 = blk[5 * stride], w = blk[7 * stride];
+  const double sx = RG_LDB(blk), sy_ = RG_LDB(blk + stride), tx = RG_LDB(blk + 2 * stride), ty = RG_LDB(blk + 3 * stride);
+  const double a4 = RG_LDB(blk + 4 * stride), a5 = RG_LDB(blk + 5 * stride), w = RG_LDB(blk + 7 * stride);
   const double mx = (cy * sx + (-sy) * sy_) + x0;
   const double my = (sy * sx + cy * sy_) + x1;
   const double dmx = (-sy) * sx + (-cy) * sy_;
@@ -150,7 +168,7 @@ __device__ __forceinline__ double eval_block(int cost_type, int loss, double lim
     J[0] = -1.0; J[1] = 0.0; J[2] = -dmx; J[3] = 0.0; J[4] = -1.0; J[5] = -dmy;
   } else {  // P2D: L = [a4 0; a5 a6]
     n = 2;
-    const double a6 = blk[6 * stride];
+    const double a6 = RG_LDB(blk + 6 * stride);
     const double e0 = mx - tx, e1 = my - ty;
     f[0] = a4 * e0 + 0.0 * e1;
     f[1] = a5 * e0 + a6 * e1;
@@ -222,31 +240,33 @@ __device__ void lm_gradient_norms(LMState& S) {
   S.it_gnorm = sqrt(gn);
 }
 
-__device__ bool chol_solve3(const double H[3][3], const double b[3], double y[3]) {
-  double L[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  for (int j = 0; j < 3; j++) {
-    double d = H[j][j];
-    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
-    if (!(d > 0.0) || !isfinite(d)) return false;
-    L[j][j] = sqrt(d);
-    for (int i = j + 1; i < 3; i++) {
-      double v = H[i][j];
-      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
-      L[i][j] = v / L[j][j];
-    }
-  }
-  double z[3];
-  for (int i = 0; i < 3; i++) {
-    double v = b[i];
-    for (int k = 0; k < i; k++) v -= L[i][k] * z[k];
-    z[i] = v / L[i][i];
-  }
-  for (int i = 2; i >= 0; i--) {
-    double v = z[i];
-    for (int k = i + 1; k < 3; k++) v -= L[k][i] * y[k];
-    y[i] = v / L[i][i];
-  }
-  return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
+// Dense 3x3 Cholesky solve H y = b (lower triangle h00 h10 h11 h20 h21 h22), every operation of the textbook loops in their order, written
+// out on scalars: nothing is indexed at run time, so nothing lives in local memory.
+__device__ __forceinline__ bool chol_solve3(double h00, double h10, double h11, double h20, double h21, double h22, double b0, double b1, double b2,
+                                            double& y0, double& y1, double& y2) {
+  if (!(h00 > 0.0) || !isfinite(h00)) return false;
+  const double l00 = sqrt(h00);
+  const double l10 = h10 / l00;
+  const double l20 = h20 / l00;
+  const double d1 = h11 - l10 * l10;
+  if (!(d1 > 0.0) || !isfinite(d1)) return false;
+  const double l11 = sqrt(d1);
+  const double l21 = (h21 - l20 * l10) / l11;
+  double d2 = h22 - l20 * l20;
+  d2 -= l21 * l21;
+  if (!(d2 > 0.0) || !isfinite(d2)) return false;
+  const double l22 = sqrt(d2);
+  const double z0 = b0 / l00;
+  const double z1 = (b1 - l10 * z0) / l11;
+  double v = b2 - l20 * z0;
+  v -= l21 * z1;
+  const double z2 = v / l22;
+  y2 = z2 / l22;
+  y1 = (z1 - l21 * y2) / l11;
+  v = z0 - l10 * y1;
+  v -= l20 * y2;
+  y0 = v / l00;
+  return isfinite(y0) && isfinite(y1) && isfinite(y2);
 }
 
 // after the evaluation at the initial point (acc = cost, g, H)
@@ -296,37 +316,54 @@ __device__ __noinline__ bool lm_advance(LMState& S, int max_iterations) {
     S.it_successful = false;
     S.it_rel_dec = 0.0;
     S.it_cost = 0.0;
-    const double hd[3] = {S.H[0], S.H[3], S.H[5]};
-    if (!S.reuse_diagonal)
-      for (int c = 0; c < 3; c++) S.diag[c] = fmin(fmax((S.scal[c] * S.scal[c]) * hd[c], 1e-6), 1e32);
-    double lmd[3];
-    for (int c = 0; c < 3; c++) lmd[c] = sqrt(S.diag[c] / S.radius);
-    const double Hf[3][3] = {{S.H[0], S.H[1], S.H[2]}, {S.H[1], S.H[3], S.H[4]}, {S.H[2], S.H[4], S.H[5]}};
-    double Hs[3][3], Hd[3][3], rhs[3];
-    for (int a = 0; a < 3; a++) {
-      rhs[a] = S.scal[a] * S.g[a];
-      for (int c = 0; c < 3; c++) { Hs[a][c] = (S.scal[a] * S.scal[c]) * Hf[a][c]; Hd[a][c] = Hs[a][c]; }
-      Hd[a][a] += lmd[a] * lmd[a];
+    if (!S.reuse_diagonal) {
+      S.diag[0] = fmin(fmax((S.scal[0] * S.scal[0]) * S.H[0], 1e-6), 1e32);
+      S.diag[1] = fmin(fmax((S.scal[1] * S.scal[1]) * S.H[3], 1e-6), 1e32);
+      S.diag[2] = fmin(fmax((S.scal[2] * S.scal[2]) * S.H[5], 1e-6), 1e32);
     }
-    double step[3];
-    const bool solved = chol_solve3(Hd, rhs, step);
+    double st0 = 0.0, st1 = 0.0, st2 = 0.0;
+    bool solved;
+    {
+      // Hs = D H D (symmetric: (c_a c_b) H_ab == (c_b c_a) H_ba bit for bit), rhs = D g, damped diagonal Hs_aa + lmd_a^2
+      const double c0 = S.scal[0], c1 = S.scal[1], c2 = S.scal[2];
+      const double lmd0 = sqrt(S.diag[0] / S.radius), lmd1 = sqrt(S.diag[1] / S.radius), lmd2 = sqrt(S.diag[2] / S.radius);
+      solved = chol_solve3((c0 * c0) * S.H[0] + lmd0 * lmd0, (c0 * c1) * S.H[1], (c1 * c1) * S.H[3] + lmd1 * lmd1, (c0 * c2) * S.H[2],
+                           (c1 * c2) * S.H[4], (c2 * c2) * S.H[5] + lmd2 * lmd2, c0 * S.g[0], c1 * S.g[1], c2 * S.g[2], st0, st1, st2);
+    }
     S.reuse_diagonal = true;
     bool valid = false;
+    const double c0 = S.scal[0], c1 = S.scal[1], c2 = S.scal[2];
     if (solved) {
-      for (int c = 0; c < 3; c++) step[c] *= -1.0;
+      // the scaled system again (the same products, recomputed from shared memory rather than kept in registers across the solve)
+      const double s00 = (c0 * c0) * S.H[0], s01 = (c0 * c1) * S.H[1], s02 = (c0 * c2) * S.H[2];
+      const double s11 = (c1 * c1) * S.H[3], s12 = (c1 * c2) * S.H[4], s22 = (c2 * c2) * S.H[5];
+      const double r0 = c0 * S.g[0], r1 = c1 * S.g[1], r2 = c2 * S.g[2];
+      st0 *= -1.0; st1 *= -1.0; st2 *= -1.0;
       double lin = 0.0, quad = 0.0;
-      for (int a = 0; a < 3; a++) {
-        lin += step[a] * rhs[a];
+      {
+        lin += st0 * r0;
         double hv = 0.0;
-        for (int c = 0; c < 3; c++) hv += Hs[a][c] * step[c];
-        quad += step[a] * hv;
+        hv += s00 * st0; hv += s01 * st1; hv += s02 * st2;
+        quad += st0 * hv;
+      }
+      {
+        lin += st1 * r1;
+        double hv = 0.0;
+        hv += s01 * st0; hv += s11 * st1; hv += s12 * st2;
+        quad += st1 * hv;
+      }
+      {
+        lin += st2 * r2;
+        double hv = 0.0;
+        hv += s02 * st0; hv += s12 * st1; hv += s22 * st2;
+        quad += st2 * hv;
       }
       S.model_cost_change = -(lin + quad / 2.0);
       valid = S.model_cost_change > 0.0;
     }
     if (valid) {
       S.num_consecutive_invalid = 0;
-      for (int c = 0; c < 3; c++) S.cand[c] = S.x[c] + step[c] * S.scal[c];
+      S.cand[0] = S.x[0] + st0 * c0; S.cand[1] = S.x[1] + st1 * c1; S.cand[2] = S.x[2] + st2 * c2;
       return true;
     }
     // ---- HandleInvalidStep
@@ -550,28 +587,50 @@ __device__ __forceinline__ int nn_search(const SetView& t, const CellGrid& g, in
   return (best >= 0 && (double)bestd < R * R) ? best : -1;
 }
 
-// The same search over a copy of the set's grid entries in SHARED memory.  The entries are in bucket order (row-major), so the bucket
-// rows the square [q - R, q + R] touches form ONE contiguous run [row[by0], row[by1 + 1]) — row[r] = first entry of bucket row r.
-// Every entry of the run is tested (a row holds ~5 cells; no per-bucket table is needed): a superset of the buckets nn_search
-// visits, the same accepted neighbour (the closest entry overall, ties to the smaller cell index, kept iff d2 < R*R).
-__device__ __forceinline__ int nn_search_staged(const float4* __restrict__ ent, const uint16_t* __restrict__ row, const CellGrid& g, float qx, float qy,
-                                                double R) {
-  const float Rm = (float)R + 1e-3f;
+// The same search over a copy of the set's grid entries in SHARED memory.  The entries are in bucket order (row-major); per bucket row
+// the copy carries the start offsets of at most RG_NSEG equal runs of buckets ("x segments", 1 << shift buckets each), so a query
+// visits, in every bucket row its square [q - R, q + R] touches, the entries of the one or two segments the square overlaps — a
+// superset of the buckets nn_search visits, hence the same accepted neighbour (the closest entry overall, ties to the smaller cell
+// index, kept iff d2 < R*R; an entry outside the square is farther than R and could not have been accepted).
+#ifndef RG_NSEG_V
+#define RG_NSEG_V 16
+#endif
+constexpr int RG_NSEG = RG_NSEG_V;
+
+struct NNQuery {
+  float qx, qy;
+  int by0, by1, s0, s1;   // bucket rows / x segments to visit; by1 < by0: nothing (query outside the grid + R, NaN, or an idle lane)
+};
+__device__ __forceinline__ NNQuery nn_prepare(const CellGrid& g, int shift, float qx, float qy, float Rm, bool live) {
+  NNQuery q;
+  q.qx = qx; q.qy = qy; q.by0 = 0; q.by1 = -1; q.s0 = 0; q.s1 = 0;
   const float ly = floorf((qy - Rm - g.miny) / GRID_CELL), hy = floorf((qy + Rm - g.miny) / GRID_CELL);
-  if (!(hy >= 0.f) || !(ly <= (float)(g.ny - 1))) return -1;  // the square lies outside the grid rows (or q is NaN)
-  const int by0 = ly > 0.f ? (int)ly : 0, by1 = hy < (float)(g.ny - 1) ? (int)hy : g.ny - 1;
+  const float lx = floorf((qx - Rm - g.minx) / GRID_CELL), hx = floorf((qx + Rm - g.minx) / GRID_CELL);
+  if (live && hy >= 0.f && ly <= (float)(g.ny - 1) && hx >= 0.f && lx <= (float)(g.nx - 1)) {   // every comparison is false for NaN
+    q.by0 = ly > 0.f ? (int)ly : 0;
+    q.by1 = hy < (float)(g.ny - 1) ? (int)hy : g.ny - 1;
+    const int bx0 = lx > 0.f ? (int)lx : 0, bx1 = hx < (float)(g.nx - 1) ? (int)hx : g.nx - 1;
+    q.s0 = bx0 >> shift; q.s1 = bx1 >> shift;
+  }
+  return q;
+}
+__device__ __forceinline__ void nn_visit(const float4 e, float qx, float qy, float& bestd, int& best) {
+  const int i = __float_as_int(e.z);
+  const float dx = qx - e.x, dy = qy - e.y;
+  float dd = dx * dx;   // FLANN L2_Simple, no contraction (-fmad=false)
+  dd = dd + dy * dy;
+  if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
+}
+// tab[row * stride + s] = first entry of x segment s of a bucket row (s == segments: the end of the row).
+__device__ __forceinline__ int nn_search_staged(const float4* __restrict__ ent, const uint16_t* __restrict__ tab, int stride, const NNQuery& Q, double R2) {
   float bestd = FLT_MAX;
   int best = -1;
-  const int j1 = row[by1 + 1];
-  for (int j = row[by0]; j < j1; j++) {
-    const float4 e = ent[j];
-    const int i = __float_as_int(e.z);
-    const float dx = qx - e.x, dy = qy - e.y;
-    float dd = dx * dx;   // FLANN L2_Simple, no contraction (-fmad=false)
-    dd = dd + dy * dy;
-    if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
+  for (int r = Q.by0; r <= Q.by1; r++) {
+    const uint16_t* t = tab + r * stride;
+    const int j1 = t[Q.s1 + 1];
+    for (int j = t[Q.s0]; j < j1; j++) nn_visit(ent[j], Q.qx, Q.qy, bestd, best);
   }
-  return (best >= 0 && (double)bestd < R * R) ? best : -1;
+  return (best >= 0 && (double)bestd < R2) ? best : -1;
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
@@ -615,16 +674,38 @@ __device__ __noinline__ void outer_advance(OuterState& O, const LMState& S, int 
   O.go = (O.itr <= max_itr_association && O.success) ? 1 : 0;
 }
 
+// Per-problem constants, written once by the set-up phase.  Every phase below is its own (not inlined) function that reads what it
+// needs from here: nothing of one phase stays in registers during another, so each phase has the whole 64-register budget of the
+// 4-CTAs-per-SM launch for its own loop and the serial trust-region code is not squeezed out of the register file by loop state
+// it never uses (local-memory traffic on that path costs an L2 round trip per access: the L1 left beside 212 KB of shared memory is tiny).
+constexpr int RG_TILE = BLK_FIELDS * 32;   // doubles per tile of 32 residual blocks (layout: rg_segment below)
+
+struct RegCtx {
+  RegParamsDev P;
+  const double* sf;            // moving set, field-major
+  size_t scap;
+  double* blocks;              // this problem's residual blocks: one segment per warp, tiles of 32 blocks (rg_segment)
+  size_t bstride;              // slots per problem in the assoc / residual scratch
+  int* assoc;                  // evaluation mode: [fixed][source] -> matched target or -1
+  double* residuals;           // evaluation mode, optional
+  const double* fixed_pose;    // poses of this problem's fixed scans
+  double src_pose[3];
+  int n_src, n_fixed, jc, staged, mode, slot_cap, nres_per_block;
+};
+
 struct RegShared {
   double acc[NACC];
   double warp_acc[RG_WARPS][NACC];
   double ex[3], cs[2];
-  int flag, n_blocks, warp_cnt[RG_WARPS], warp_pre[RG_WARPS + 1];   // blocks per warp segment and their exclusive prefix
+  int flag, n_blocks, warp_cnt[RG_WARPS];   // blocks in every warp's segment
+  int cnt[RG_MAX_FIXED][RG_WARPS];          // ... split by fixed scan (evaluation mode: the reference's block order for the residual vector)
   Aff Tst[RG_MAX_FIXED], Ttar[RG_MAX_FIXED];
   SetView tgt[RG_MAX_FIXED];
   CellGrid grid[RG_MAX_FIXED];   // search-grid headers of the fixed sets
   int n_tgt[RG_MAX_FIXED];
-  int staged, ent_off[RG_MAX_FIXED], row_off[RG_MAX_FIXED];   // byte offsets into the dynamic shared memory (staged working set)
+  int ent_off[RG_MAX_FIXED], tab_off[RG_MAX_FIXED];           // byte offsets into the dynamic shared memory (staged working set)
+  int seg_shift[RG_MAX_FIXED], seg_stride[RG_MAX_FIXED];      // x segment = 1 << shift buckets; table row = segments + 1 offsets
+  RegCtx c;
   LMState lm;
   OuterState outer;
 };
@@ -636,8 +717,8 @@ struct RegShared {
 template <int COST, bool HUBER>
 __device__ __forceinline__ void eval_block_simple(const double* __restrict__ blk, size_t stride, double limit, double x0, double x1, double cy,
                                                   double sy, double* __restrict__ a) {
-  const double sx = blk[0], sy_ = blk[stride], tx = blk[2 * stride], ty = blk[3 * stride];
-  const double a4 = blk[4 * stride], a5 = blk[5 * stride], w = blk[7 * stride], sw = blk[8 * stride];
+  const double sx = RG_LDB(blk), sy_ = RG_LDB(blk + stride), tx = RG_LDB(blk + 2 * stride), ty = RG_LDB(blk + 3 * stride);
+  const double a4 = RG_LDB(blk + 4 * stride), a5 = RG_LDB(blk + 5 * stride), w = RG_LDB(blk + 7 * stride), sw = RG_LDB(blk + 8 * stride);
   const double mx = (cy * sx + (-sy) * sy_) + x0;
   const double my = (sy * sx + cy * sy_) + x1;
   const double dmx = (-sy) * sx + (-cy) * sy_;
@@ -652,7 +733,7 @@ __device__ __forceinline__ void eval_block_simple(const double* __restrict__ blk
     f[0] = tx - mx; f[1] = ty - my;
     J[0] = -1.0; J[1] = 0.0; J[2] = -dmx; J[3] = 0.0; J[4] = -1.0; J[5] = -dmy;
   } else {
-    const double a6 = blk[6 * stride];
+    const double a6 = RG_LDB(blk + 6 * stride);
     const double e0 = mx - tx, e1 = my - ty;
     f[0] = a4 * e0 + 0.0 * e1;
     f[1] = a5 * e0 + a6 * e1;
@@ -681,48 +762,250 @@ __device__ __forceinline__ void eval_block_simple(const double* __restrict__ blk
   }
 }
 
-template <int COST, bool HUBER, typename At>
-__device__ __forceinline__ void eval_loop_simple(const double* __restrict__ blocks, size_t bstride, int nblk, At at, double limit, double x0,
-                                                 double x1, double cy, double sy, int tid, double* __restrict__ a) {
-  for (int q = tid; q < nblk; q += RG_THREADS) eval_block_simple<COST, HUBER>(blocks + at(q), bstride, limit, x0, x1, cy, sy, a);
+// the blocks [0, n) of one warp's segment, lane-strided
+template <int COST, bool HUBER>
+__device__ __forceinline__ void eval_loop_simple(const double* __restrict__ seg, size_t bstride, int n, double limit, double x0, double x1, double cy,
+                                                 double sy, int lane, double* __restrict__ a) {
+  for (int k = lane; k < n; k += 32, seg += RG_TILE) eval_block_simple<COST, HUBER>(seg, bstride, limit, x0, x1, cy, sy, a);
 }
 
-// MIN_CTAS: resident CTAs per SM the register budget is set for (3 -> 80 registers, 4 -> 64)
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(RG_THREADS, MIN_CTAS)
-k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
-           const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
-           double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
-           double* __restrict__ residuals_all, double* __restrict__ wgt_all, unsigned long long* __restrict__ dbg, int stage_bytes) {
-  __shared__ RegShared sh;
-  extern __shared__ __align__(16) uint8_t rg_stage[];
-  long long t_assoc = 0, t_eval = 0, t_lm = 0, t_mark = 0;
-  const long long t_start = dbg ? clock64() : 0;
-  const int p = blockIdx.x;
+// Every warp owns the source cells [j_begin, j_end) — an equal share of the moving set — against EVERY fixed scan, and a segment of the
+// block arrays with room for all of them (n_fixed * jc blocks at warp * n_fixed * jc).  The warps therefore carry equal shares of the
+// association whatever the match rates of the individual keyframes, the warp that writes a block is the warp that evaluates it, and
+// an evaluation is a lane-strided sweep over the warp's own contiguous segment.  (The order in which blocks are summed is fixed by
+// this layout, not by the data: results are bit-identical from run to run.  The reference's block order — fixed-scan-major, source
+// index ascending — is only needed for the residual vector of the evaluation mode, which is re-derived from sh.cnt.)
+// Inside a segment the blocks lie in tiles of 32: tile t holds field f of blocks 32t .. 32t+31 at doubles [t * RG_TILE + 32 f, +32) — a lane
+// that sweeps the segment reads all fields of its block at CONSTANT offsets from one pointer (no per-field stride arithmetic, nothing to
+// keep in registers but the pointer), and a warp's accesses stay fully coalesced (32 consecutive doubles per field).
+__device__ __forceinline__ size_t rg_segment_doubles(int n_fixed, int jc) { return (size_t)((n_fixed * jc + 31) >> 5) * RG_TILE; }
+__device__ __forceinline__ double* rg_segment(const RegCtx& c, int warp) { return c.blocks + (size_t)warp * rg_segment_doubles(c.n_fixed, c.jc); }
+
+// ---- association at pose x with search radius R (AddScanPairCost for every fixed scan): the search runs out of shared memory; per
+// accepted slot ONE round trip to the matched target cell's fields (all loads issued together).  One barrier per round.
+// Returns the number of residual blocks of the problem (the same value in every thread).
+__device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __restrict__ rg_stage, const double* x, double R) {
+  const RegCtx& c = sh.c;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned FULL = 0xffffffffu;
-  const RegProblem prob = problems[p];
-  RegResult* out = results + p;
-  if (!prob.active) {
-    if (tid == 0) {
-      RegResult r;
-      memset(&r, 0, sizeof(r));
-      r.pose[0] = prob.src_pose[0]; r.pose[1] = prob.src_pose[1]; r.pose[2] = prob.src_pose[2];
-      *out = r;
-      if (n_blocks_all) n_blocks_all[p] = 0;
-    }
-    return;
-  }
-  const SetView src = sets[prob.src_set];
-  const int n_src = set_count(src);
-  const int n_fixed = min(prob.n_fixed, RG_MAX_FIXED);
-  const size_t bstride = (size_t)max_fixed * slot_cap;
-  int* assoc = assoc_all + (size_t)p * bstride;
-  (void)wgt_all;  // weights now go straight into the residual blocks
-  double* blocks = blocks_all + (size_t)p * BLK_FIELDS * bstride;
-  const int nres_per_block = (P.cost == TBV_P2L) ? 1 : 2;
+  const int n_fixed = c.n_fixed;
   if (tid < n_fixed) {
-    sh.tgt[tid] = sets[fixed_set[prob.fixed_first + tid]];
+    const double* fp = c.fixed_pose + (size_t)tid * 3;
+    const Aff Ttar = vec_to_aff(fp[0], fp[1], fp[2]);
+    sh.Ttar[tid] = Ttar;
+    sh.Tst[tid] = aff_mul(aff_inv(Ttar), vec_to_aff(x[0], x[1], x[2]));
+  }
+  __syncthreads();
+  const float Rm = (float)R + 1e-3f;
+  const double R2 = R * R;
+  const int weight_opt = c.P.weight_opt, cost = c.P.cost, mode = c.mode;
+  const bool weighted = weight_opt != TBV_W_UNIFORM, staged = c.staged != 0;
+  const double angle_outlier = c.P.angle_outlier;
+  const double* __restrict__ sf = c.sf;
+  const size_t scap = c.scap;
+  constexpr size_t bstride = 32;
+  const double2* s_u = reinterpret_cast<const double2*>(rg_stage);
+  const int jc = c.jc, n_src = c.n_src;
+  const int j_begin = min(n_src, warp * jc), j_end = min(n_src, j_begin + jc);
+  double* seg = rg_segment(c, warp);
+  int my_cnt = 0;
+  for (int fi = 0; fi < n_fixed; fi++) {
+    const Aff Tst = sh.Tst[fi];
+    const double* __restrict__ tf = sh.tgt[fi].f;
+    const size_t tcap = (size_t)sh.tgt[fi].cap;
+    const int cnt0 = my_cnt;
+    for (int jb = j_begin; jb < j_end; jb += 32) {
+      const int j = jb + lane;
+      const bool live = j < j_end;
+      double ux = 0.0, uy = 0.0;
+      if (live) {
+        if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
+        else { ux = RG_LDA(sf + (size_t)CF_U0 * scap + j); uy = RG_LDA(sf + (size_t)CF_U1 * scap + j); }
+      }
+      const float qx = (float)((Tst.r00 * ux + Tst.r01 * uy) + Tst.tx), qy = (float)((Tst.r10 * ux + Tst.r11 * uy) + Tst.ty);
+      int ti = -1;
+      if (staged) {
+        const NNQuery Q = nn_prepare(sh.grid[fi], sh.seg_shift[fi], qx, qy, Rm, live);
+        ti = nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]), reinterpret_cast<const uint16_t*>(rg_stage + sh.tab_off[fi]),
+                              sh.seg_stride[fi], Q, R2);
+      } else if (live) {
+        ti = nn_search(sh.tgt[fi], sh.grid[fi], sh.n_tgt[fi], qx, qy, R);
+      }
+      bool ok = false;
+      double w = 1.0, tn0 = 0.0, tn1 = 0.0, tu0 = 0.0, tu1 = 0.0;
+      if (ti >= 0) {
+        // every value the decision, the weight and the block need, in one round trip
+        const double sn0 = RG_LDA(sf + (size_t)CF_N0 * scap + j), sn1 = RG_LDA(sf + (size_t)CF_N1 * scap + j);
+        tn0 = RG_LDA(tf + (size_t)CF_N0 * tcap + ti); tn1 = RG_LDA(tf + (size_t)CF_N1 * tcap + ti);
+        tu0 = RG_LDA(tf + (size_t)CF_U0 * tcap + ti); tu1 = RG_LDA(tf + (size_t)CF_U1 * tcap + ti);
+        double N1 = 0.0, N2 = 0.0, p1 = 0.0, p2 = 0.0;
+        if (weighted) {
+          N1 = RG_LDA(sf + (size_t)CF_NS * scap + j); p1 = RG_LDA(sf + (size_t)CF_SCALE * scap + j);
+          N2 = RG_LDA(tf + (size_t)CF_NS * tcap + ti); p2 = RG_LDA(tf + (size_t)CF_SCALE * tcap + ti);
+        }
+        const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
+        const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
+        const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
+        if (sim > angle_outlier) {
+          ok = true;
+          if (weighted) {
+            const double simN = 2 * fmin(N1, N2) / (N1 + N2);
+            const double simP = 2 * fmin(p1, p2) / (p1 + p2);
+            switch (weight_opt) {   // registration.cpp:67-75
+              case TBV_W_SIM_N: w = simN; break;
+              case TBV_W_SIM_DIRECTION: w = sim; break;
+              case TBV_W_SIM_SCALE: w = simP; break;
+              case TBV_W_COMBINED: w = simN + sim + simP; break;
+              default: w = 1.0;
+            }
+          }
+        } else {
+          ti = -1;
+        }
+      }
+      if (mode == REG_MODE_EVAL && live) c.assoc[(size_t)fi * c.slot_cap + j] = ti;   // read back only by tbv_pair_normal_eq
+      // the accepted correspondences of this warp go to its own segment in (fixed scan, source index) order
+      const unsigned bal = __ballot_sync(FULL, ok);
+      if (ok) {
+        const int m = my_cnt + __popc(bal & ((1u << lane) - 1u));
+        double* b = seg + (size_t)(m >> 5) * RG_TILE + (m & 31);
+        const Aff Ttar = sh.Ttar[fi];
+        RG_STA(b + 0 * bstride, ux);
+        RG_STA(b + 1 * bstride, uy);
+        RG_STA(b + 2 * bstride, (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx);
+        RG_STA(b + 3 * bstride, (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty);
+        if (cost == TBV_P2L) {
+          RG_STA(b + 4 * bstride, Ttar.r00 * tn0 + Ttar.r01 * tn1);
+          RG_STA(b + 5 * bstride, Ttar.r10 * tn0 + Ttar.r11 * tn1);
+        } else if (cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
+          const double regularization = c.P.regularization, cov_scale = c.P.cov_scale;
+          const double c00 = RG_LDA(tf + (size_t)CF_C00 * tcap + ti), c01 = RG_LDA(tf + (size_t)CF_C01 * tcap + ti);
+          const double c10 = RG_LDA(tf + (size_t)CF_C10 * tcap + ti), c11 = RG_LDA(tf + (size_t)CF_C11 * tcap + ti);
+          const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
+          const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
+          const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
+          const double M00 = RC00 * R00 + RC01 * R01, M01 = RC00 * R10 + RC01 * R11;
+          const double M10 = RC10 * R00 + RC11 * R01, M11 = RC10 * R10 + RC11 * R11;
+          const double t00 = (regularization + M00) * cov_scale, t01 = (0.0 + M01) * cov_scale;
+          const double t10 = (0.0 + M10) * cov_scale, t11 = (regularization + M11) * cov_scale;
+          const double det = t00 * t11 - t10 * t01;
+          const double invdet = 1.0 / det;
+          const double i00 = t11 * invdet, i10 = -t10 * invdet, i11 = t00 * invdet;
+          const double l00 = sqrt(i00);
+          const double l10 = i10 / l00;
+          const double l11 = sqrt(i11 - l10 * l10);
+          RG_STA(b + 4 * bstride, l00);
+          RG_STA(b + 5 * bstride, l10);
+          RG_STA(b + 6 * bstride, l11);
+        }
+        RG_STA(b + 7 * bstride, w);
+        RG_STA(b + 8 * bstride, sqrt(w));
+      }
+      my_cnt += __popc(bal);
+    }
+    if (lane == 0) sh.cnt[fi][warp] = my_cnt - cnt0;
+  }
+  if (lane == 0) sh.warp_cnt[warp] = my_cnt;
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int wv = 0; wv < RG_WARPS; wv++) total += sh.warp_cnt[wv];
+  if (tid == 0) sh.n_blocks = total;   // read again by thread 0 only (result record)
+  return total;
+}
+
+// evaluation mode: block k of this warp's segment -> its index in the reference's block order (fixed-scan-major, source index ascending)
+__device__ __forceinline__ int rg_reference_index(const RegShared& sh, int warp, int k) {
+  const int n_fixed = sh.c.n_fixed;
+  int fi = 0, cum = 0;
+  while (fi < n_fixed - 1 && k >= cum + sh.cnt[fi][warp]) { cum += sh.cnt[fi][warp]; fi++; }
+  int q = k - cum;
+  for (int f = 0; f < fi; f++)
+    for (int wv = 0; wv < RG_WARPS; wv++) q += sh.cnt[f][wv];
+  for (int wv = 0; wv < warp; wv++) q += sh.cnt[fi][wv];
+  return q;
+}
+
+// ---- evaluation at sh.ex (cos/sin in sh.cs): per-warp partial sums in sh.warp_acc (fixed shapes: deterministic); ends with a barrier,
+// warp 0 combines them afterwards.
+__device__ __forceinline__ void rg_evaluate(RegShared& sh, int write_residuals) {
+  const RegCtx& c = sh.c;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned FULL = 0xffffffffu;
+  double a[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) a[i] = 0.0;
+  const double x0 = sh.ex[0], x1 = sh.ex[1], cy = sh.cs[0], sy = sh.cs[1];
+  const int n_mine = sh.warp_cnt[warp];
+  const double* seg = rg_segment(c, warp) + lane;   // this lane's block of tile 0; its later blocks follow at RG_TILE doubles each
+  constexpr size_t bstride = 32;
+  const int cost = c.P.cost, loss = c.P.loss;
+  const double limit = c.P.loss_limit;
+  const bool simple_loss = (loss == TBV_LOSS_HUBER || loss == TBV_LOSS_NONE) && c.mode == REG_MODE_REGISTER;
+  if (simple_loss) {
+    if (loss == TBV_LOSS_HUBER) {
+      if (cost == TBV_P2L) eval_loop_simple<TBV_P2L, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+      else if (cost == TBV_P2P) eval_loop_simple<TBV_P2P, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+      else eval_loop_simple<TBV_P2D, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+    } else {
+      if (cost == TBV_P2L) eval_loop_simple<TBV_P2L, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+      else if (cost == TBV_P2P) eval_loop_simple<TBV_P2P, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+      else eval_loop_simple<TBV_P2D, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+    }
+  } else {
+    for (int k = lane; k < n_mine; k += 32, seg += RG_TILE) {
+      double f[2], J[6];
+      int n;
+      a[0] += eval_block(cost, loss, limit, seg, bstride, x0, x1, cy, sy, f, J, n, true);
+      for (int r = 0; r < n; r++) {
+        const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
+        a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
+        a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
+      }
+      if (write_residuals && c.residuals) {
+        const int q = rg_reference_index(sh, warp, k);
+        for (int r = 0; r < n; r++) c.residuals[(size_t)q * n + r] = f[r];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; i++) {
+    double v = a[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    if (lane == 0) sh.warp_acc[warp][i] = v;
+  }
+  __syncthreads();
+}
+
+// warp 0, after rg_evaluate(): cross-warp sums in warp order -> sh.acc (visible to the warp after __syncwarp)
+__device__ __forceinline__ void rg_combine(RegShared& sh, int lane) {
+  if (lane < NACC) {
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < RG_WARPS; wv++) v += sh.warp_acc[wv][lane];
+    sh.acc[lane] = v;
+  }
+  __syncwarp();
+}
+// warp 0: publish the next evaluation point chosen by lane 0 (x in sh.ex); cos and sin are computed by two different lanes
+__device__ __forceinline__ void rg_publish_eval_point(RegShared& sh, int lane, bool go) {
+  const int g = __shfl_sync(0xffffffffu, go ? 1 : 0, 0);
+  if (g) {
+    const double th = sh.ex[2];
+    if (lane == 1) sh.cs[0] = cos(th);
+    if (lane == 2) sh.cs[1] = sin(th);
+  }
+}
+
+// ---- set-up: the problem's constants, L2 prefetch of its working set, staging of what the search reads into shared memory
+__device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg_stage, int stage_bytes, const SetView* __restrict__ sets,
+                                      const int* __restrict__ fixed_set, int fixed_first) {
+  const RegCtx& c = sh.c;
+  const int tid = threadIdx.x;
+  const int n_fixed = c.n_fixed, n_src = c.n_src;
+  if (tid < n_fixed) {
+    sh.tgt[tid] = sets[fixed_set[fixed_first + tid]];
     sh.n_tgt[tid] = set_count(sh.tgt[tid]);
     CellGrid g;
     g.minx = g.miny = 0.f; g.nx = g.ny = 1; g.ok = 0;
@@ -737,8 +1020,8 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   {
     const int pf_fields[6] = {CF_U0, CF_U1, CF_N0, CF_N1, CF_NS, CF_SCALE};
     for (int f = -1; f < n_fixed; f++) {
-      const double* base = (f < 0) ? src.f : sh.tgt[f].f;
-      const size_t cap = (f < 0) ? (size_t)src.cap : (size_t)sh.tgt[f].cap;
+      const double* base = (f < 0) ? c.sf : sh.tgt[f].f;
+      const size_t cap = (f < 0) ? c.scap : (size_t)sh.tgt[f].cap;
       const int cnt = (f < 0) ? n_src : sh.n_tgt[f];
       const int lines = (cnt * 8 + 127) / 128;
 #pragma unroll
@@ -753,250 +1036,132 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       }
     }
   }
-
   // Stage what the nearest-neighbour search reads into shared memory when it fits (it does for the odometry and loop workloads:
-  // ~37 KB for 450-cell sets and four keyframes): the moving set's means and, per fixed set, its grid entries + one start offset
-  // per bucket row.  The search then runs out of shared memory and the association pays ONE global round trip per slot (the
-  // matched target's normal / N / planarity) instead of one per link of query -> bucket rows -> entries -> target fields.
+  // ~40 KB for 450-cell sets and four keyframes): the moving set's means and, per fixed set, its grid entries + the start offsets of
+  // the x segments of every bucket row.  The search then runs out of shared memory and the association pays ONE global round trip per
+  // slot (the matched target's mean / normal / N / planarity) instead of one per link of query -> bucket rows -> entries -> target fields.
   if (tid == 0) {
     int need = n_src * 16, ok = 1;
     for (int f = 0; f < n_fixed; f++) {
       if (!(sh.tgt[f].grid && sh.grid[f].ok)) { ok = 0; break; }
       sh.ent_off[f] = need; need += sh.n_tgt[f] * 16;
-      sh.row_off[f] = need; need += ((sh.grid[f].ny + 2) * 2 + 15) & ~15;
     }
-    sh.staged = (ok && need <= stage_bytes) ? 1 : 0;
+    // segment tables: at most RG_NSEG segments per bucket row, coarsened (all sets together) until the tables fit
+    for (int bump = 0; ok; bump++) {
+      int t = need;
+      for (int f = 0; f < n_fixed; f++) {
+        const int nx = sh.grid[f].nx, ny = sh.grid[f].ny;
+        int shf = 0;
+        while (((nx - 1) >> shf) + 1 > RG_NSEG) shf++;
+        shf += bump;
+        const int stride = ((nx - 1) >> shf) + 2;
+        sh.tab_off[f] = t; sh.seg_shift[f] = shf; sh.seg_stride[f] = stride;
+        t += (ny * stride * 2 + 15) & ~15;
+      }
+      if (t <= stage_bytes) { need = t; break; }
+      if (bump >= 14) ok = 0;   // one segment per row is the smallest table there is
+    }
+    sh.c.staged = (ok && need <= stage_bytes) ? 1 : 0;
   }
   __syncthreads();
-  const bool staged = sh.staged != 0;
-  const double2* s_u = reinterpret_cast<const double2*>(rg_stage);
-  if (staged) {
+  if (c.staged) {
     double2* su = reinterpret_cast<double2*>(rg_stage);
-    for (int j = tid; j < n_src; j += RG_THREADS) su[j] = make_double2(src.f[(size_t)CF_U0 * src.cap + j], src.f[(size_t)CF_U1 * src.cap + j]);
+    for (int j = tid; j < n_src; j += RG_THREADS) su[j] = make_double2(c.sf[(size_t)CF_U0 * c.scap + j], c.sf[(size_t)CF_U1 * c.scap + j]);
     for (int f = 0; f < n_fixed; f++) {
       float4* e = reinterpret_cast<float4*>(rg_stage + sh.ent_off[f]);
-      uint16_t* r = reinterpret_cast<uint16_t*>(rg_stage + sh.row_off[f]);
-      const int nt = sh.n_tgt[f], ny = sh.grid[f].ny, nx = sh.grid[f].nx;
-      for (int j = tid; j < nt; j += RG_THREADS) e[j] = sh.tgt[f].gent[j];
-      for (int k = tid; k <= ny; k += RG_THREADS) r[k] = k < ny ? sh.tgt[f].gstart[k * nx] : (uint16_t)nt;
+      uint16_t* tb = reinterpret_cast<uint16_t*>(rg_stage + sh.tab_off[f]);
+      const int nt = sh.n_tgt[f], ny = sh.grid[f].ny, nx = sh.grid[f].nx, stride = sh.seg_stride[f], shf = sh.seg_shift[f];
+      const float4* __restrict__ gent = sh.tgt[f].gent;
+      const uint16_t* __restrict__ gstart = sh.tgt[f].gstart;
+      for (int j = tid; j < nt; j += RG_THREADS) e[j] = gent[j];
+      for (int k = tid; k < ny * stride; k += RG_THREADS) {
+        const int r = k / stride, sg = k - r * stride;
+        tb[k] = gstart[r * nx + min(sg << shf, nx)];   // sg == segments: the first bucket of the next row (the last row: the entry count)
+      }
     }
   }
   __syncthreads();
+}
 
-  // every warp owns a contiguous range of (fixed scan, source cell) slots — fixed-major, the order the reference adds its residual
-  // blocks in — and the matching segment of the block arrays
-  const int n_slots = n_fixed * n_src;
-  const int chunk = (((n_slots + RG_WARPS - 1) / RG_WARPS) + 31) & ~31;
-  const int s_begin = min(n_slots, warp * chunk), s_end = min(n_slots, s_begin + chunk);
-
-  // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan).  Slot = (fixed scan, source
-  // cell), fixed-major: the order the reference adds its residual blocks in.  Every warp owns a contiguous slot range:
-  // pass 1 searches and counts, one barrier publishes the per-warp counts, pass 2 writes the accepted correspondences of
-  // the warp's range at their final, ordered positions.  Two barriers per association round, whatever the slot count.
-  auto associate = [&](const double x[3], double R) {
-    if (tid < n_fixed) {
-      const double* fp = fixed_pose + (size_t)(prob.fixed_first + tid) * 3;
-      const Aff Ttar = vec_to_aff(fp[0], fp[1], fp[2]);
-      sh.Ttar[tid] = Ttar;
-      sh.Tst[tid] = aff_mul(aff_inv(Ttar), vec_to_aff(x[0], x[1], x[2]));
-    }
-    __syncthreads();
-    int my_cnt = 0;
-    for (int base = s_begin; base < s_end; base += 32) {
-      const int slot = base + lane;
-      bool ok = false;
-      int ti = -1, fi = 0, j = 0;
-      double w = 1.0, tn0 = 0.0, tn1 = 0.0;
-      if (slot < s_end) {
-        fi = slot / n_src;
-        j = slot - fi * n_src;
-        const Aff Tst = sh.Tst[fi];
-        const SetView& tgt = sh.tgt[fi];
-        double ux, uy;
-        if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
-        else { ux = src.f[(size_t)CF_U0 * src.cap + j]; uy = src.f[(size_t)CF_U1 * src.cap + j]; }
-        const double qxd = (Tst.r00 * ux + Tst.r01 * uy) + Tst.tx;
-        const double qyd = (Tst.r10 * ux + Tst.r11 * uy) + Tst.ty;
-        ti = staged ? nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]),
-                                       reinterpret_cast<const uint16_t*>(rg_stage + sh.row_off[fi]), sh.grid[fi], (float)qxd, (float)qyd, R)
-                    : nn_search(tgt, sh.grid[fi], sh.n_tgt[fi], (float)qxd, (float)qyd, R);
-        if (ti >= 0) {
-          // every value the decision and the weight need, in one round trip
-          const bool weighted = P.weight_opt != TBV_W_UNIFORM;
-          const double sn0 = src.f[(size_t)CF_N0 * src.cap + j], sn1 = src.f[(size_t)CF_N1 * src.cap + j];
-          tn0 = tgt.f[(size_t)CF_N0 * tgt.cap + ti]; tn1 = tgt.f[(size_t)CF_N1 * tgt.cap + ti];
-          const double N2 = weighted ? tgt.f[(size_t)CF_NS * tgt.cap + ti] : 0.0, p2 = weighted ? tgt.f[(size_t)CF_SCALE * tgt.cap + ti] : 0.0;
-          const double N1 = weighted ? src.f[(size_t)CF_NS * src.cap + j] : 0.0, p1 = weighted ? src.f[(size_t)CF_SCALE * src.cap + j] : 0.0;
-          const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
-          const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
-          const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
-          if (sim > P.angle_outlier) {
-            ok = true;
-            if (weighted) {
-              const double simN = 2 * fmin(N1, N2) / (N1 + N2);
-              const double simP = 2 * fmin(p1, p2) / (p1 + p2);
-              switch (P.weight_opt) {   // registration.cpp:67-75
-                case TBV_W_SIM_N: w = simN; break;
-                case TBV_W_SIM_DIRECTION: w = sim; break;
-                case TBV_W_SIM_SCALE: w = simP; break;
-                case TBV_W_COMBINED: w = simN + sim + simP; break;
-                default: w = 1.0;
-              }
-            }
-          } else {
-            ti = -1;
-          }
-        }
-        if (mode == REG_MODE_EVAL) assoc[(size_t)fi * slot_cap + j] = ti;   // read back only by tbv_pair_normal_eq; the registration loop never needs it
-      }
-      // the accepted correspondences of this warp, in slot order, go to the warp's own segment of the block arrays (it starts at
-      // the warp's first slot): the warp that writes a block is the warp that evaluates it, so no second pass and no barrier
-      // stand between the search and the first evaluation
-      const unsigned bal = __ballot_sync(FULL, ok);
-      if (ok) {
-        const int q = s_begin + my_cnt + __popc(bal & ((1u << lane) - 1u));
-        const Aff Ttar = sh.Ttar[fi];
-        const SetView& tgt = sh.tgt[fi];
-        const double tu0 = tgt.f[(size_t)CF_U0 * tgt.cap + ti], tu1 = tgt.f[(size_t)CF_U1 * tgt.cap + ti];
-        double ux, uy;
-        if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
-        else { ux = src.f[(size_t)CF_U0 * src.cap + j]; uy = src.f[(size_t)CF_U1 * src.cap + j]; }
-        blocks[0 * bstride + q] = ux;
-        blocks[1 * bstride + q] = uy;
-        blocks[2 * bstride + q] = (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx;
-        blocks[3 * bstride + q] = (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty;
-        if (P.cost == TBV_P2L) {
-          blocks[4 * bstride + q] = Ttar.r00 * tn0 + Ttar.r01 * tn1;
-          blocks[5 * bstride + q] = Ttar.r10 * tn0 + Ttar.r11 * tn1;
-        } else if (P.cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
-          const double c00 = tgt.f[(size_t)CF_C00 * tgt.cap + ti], c01 = tgt.f[(size_t)CF_C01 * tgt.cap + ti];
-          const double c10 = tgt.f[(size_t)CF_C10 * tgt.cap + ti], c11 = tgt.f[(size_t)CF_C11 * tgt.cap + ti];
-          const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
-          const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
-          const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
-          const double M00 = RC00 * R00 + RC01 * R01, M01 = RC00 * R10 + RC01 * R11;
-          const double M10 = RC10 * R00 + RC11 * R01, M11 = RC10 * R10 + RC11 * R11;
-          const double t00 = (P.regularization + M00) * P.cov_scale, t01 = (0.0 + M01) * P.cov_scale;
-          const double t10 = (0.0 + M10) * P.cov_scale, t11 = (P.regularization + M11) * P.cov_scale;
-          const double det = t00 * t11 - t10 * t01;
-          const double invdet = 1.0 / det;
-          const double i00 = t11 * invdet, i10 = -t10 * invdet, i11 = t00 * invdet;
-          const double l00 = sqrt(i00);
-          const double l10 = i10 / l00;
-          const double l11 = sqrt(i11 - l10 * l10);
-          blocks[4 * bstride + q] = l00;
-          blocks[5 * bstride + q] = l10;
-          blocks[6 * bstride + q] = l11;
-        }
-        blocks[7 * bstride + q] = w;
-        blocks[8 * bstride + q] = sqrt(w);
-      }
-      my_cnt += __popc(bal);
-    }
-    if (lane == 0) sh.warp_cnt[warp] = my_cnt;
-    __syncthreads();
+// MIN_CTAS: resident CTAs per SM the register budget is set for (4 -> 64 registers)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(RG_THREADS, MIN_CTAS)
+k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
+           const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
+           double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
+           double* __restrict__ residuals_all, unsigned long long* __restrict__ dbg, int stage_bytes) {
+  __shared__ RegShared sh;
+  extern __shared__ __align__(16) uint8_t rg_stage[];
+#ifdef TBV_DEV_TIMERS   // per-phase cycle counters of development builds; a release build carries none of their registers
+  long long t_assoc = 0, t_eval = 0, t_lm = 0, t_mark = 0, t_s0 = 0, t_s1 = 0, t_s2 = 0, t_s3 = 0, t_sub = 0, n_rounds = 0, n_evals = 0;
+  const long long t_start = clock64();
+#define RG_TIMER_MARK() t_mark = clock64()
+#define RG_TIMER_ADD(acc) { const long long t_now = clock64(); acc += t_now - t_mark; t_mark = t_now; t_sub = t_now; }
+#define RG_TIMER_SUB(acc) { const long long t_now = clock64(); acc += t_now - t_sub; t_sub = t_now; }
+#define RG_TIMER_COUNT(n) n++
+#else
+  (void)dbg;
+#define RG_TIMER_MARK()
+#define RG_TIMER_ADD(acc)
+#define RG_TIMER_SUB(acc)
+#define RG_TIMER_COUNT(n)
+#endif
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (!problems[p].active) {
     if (tid == 0) {
-      int total = 0;
-      for (int wv = 0; wv < RG_WARPS; wv++) { sh.warp_pre[wv] = total; total += sh.warp_cnt[wv]; }
-      sh.warp_pre[RG_WARPS] = total;
-      sh.n_blocks = total;
+      RegResult* out = results + p;
+      out->pose[0] = problems[p].src_pose[0]; out->pose[1] = problems[p].src_pose[1]; out->pose[2] = problems[p].src_pose[2];
+      out->align[0] = out->align[1] = out->align[2] = 0.0;
+      out->pose_updated = 0; out->success = 0; out->itrs = 0; out->lm_iterations = 0; out->num_residuals = 0; out->last_n_iterations = 0;
+      out->termination = 0; out->score = 0.0; out->final_cost = 0.0; out->last_relative_decrease = 0.0;
+      if (n_blocks_all) n_blocks_all[p] = 0;
     }
-    __syncthreads();
-  };
-  // block q of the reference's order (fixed-major, compacted) -> its place in the segmented block arrays.  The evaluation strides all
-  // 256 threads over q: the segments are not equally full (a recent keyframe matches far more cells than an old one), the threads are.
-  auto block_at = [&](int q) -> int {
-    int wv = 0;
-#pragma unroll
-    for (int k = 1; k < RG_WARPS; k++) wv += (q >= sh.warp_pre[k]);
-    return wv * chunk + (q - sh.warp_pre[wv]);
-  };
-
-  // ---- evaluation at sh.ex (cos/sin in sh.cs): per-warp partial sums in sh.warp_acc (fixed shapes: deterministic).
-  // The caller combines them after the barrier at the end.
-  const bool simple_loss = (P.loss == TBV_LOSS_HUBER || P.loss == TBV_LOSS_NONE) && mode == REG_MODE_REGISTER;
-  auto evaluate = [&](int nblk, bool write_residuals) {
-    double a[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; i++) a[i] = 0.0;
-    const double x0 = sh.ex[0], x1 = sh.ex[1], cy = sh.cs[0], sy = sh.cs[1];
-    if (simple_loss) {
-      if (P.loss == TBV_LOSS_HUBER) {
-        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, true>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, true>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else eval_loop_simple<TBV_P2D, true>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
-      } else {
-        if (P.cost == TBV_P2L) eval_loop_simple<TBV_P2L, false>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else if (P.cost == TBV_P2P) eval_loop_simple<TBV_P2P, false>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
-        else eval_loop_simple<TBV_P2D, false>(blocks, bstride, nblk, block_at, P.loss_limit, x0, x1, cy, sy, tid, a);
-      }
-    } else {
-      for (int q = tid; q < nblk; q += RG_THREADS) {
-        double f[2], J[6];
-        int n;
-        a[0] += eval_block(P.cost, P.loss, P.loss_limit, blocks + block_at(q), bstride, x0, x1, cy, sy, f, J, n, true);
-        for (int r = 0; r < n; r++) {
-          const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
-          a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
-          a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
-        }
-        if (write_residuals && residuals_all) {
-          double* ro = residuals_all + (size_t)p * 2 * bstride;
-          for (int r = 0; r < n; r++) ro[(size_t)q * n + r] = f[r];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NACC; i++) {
-      double v = a[i];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-      if (lane == 0) sh.warp_acc[warp][i] = v;
-    }
-    __syncthreads();
-  };
-  // warp 0, after evaluate(): cross-warp sums in warp order -> sh.acc (visible to the warp after __syncwarp)
-  auto combine = [&]() {
-    if (lane < NACC) {
-      double v = 0.0;
-#pragma unroll
-      for (int wv = 0; wv < RG_WARPS; wv++) v += sh.warp_acc[wv][lane];
-      sh.acc[lane] = v;
-    }
-    __syncwarp();
-  };
-  // warp 0: publish the next evaluation point chosen by lane 0 (x in sh.ex); cos and sin are computed by two different lanes
-  auto publish_eval_point = [&](bool go) {
-    const int g = __shfl_sync(FULL, go ? 1 : 0, 0);
-    if (g) {
-      const double th = sh.ex[2];
-      if (lane == 1) sh.cs[0] = cos(th);
-      if (lane == 2) sh.cs[1] = sin(th);
-    }
-  };
+    return;
+  }
+  if (tid == 0) {
+    const RegProblem prob = problems[p];
+    const SetView src = sets[prob.src_set];
+    RegCtx& c = sh.c;
+    c.P = P;
+    c.sf = src.f; c.scap = (size_t)src.cap;
+    c.n_src = set_count(src);
+    c.n_fixed = min(prob.n_fixed, RG_MAX_FIXED);
+    c.jc = (c.n_src + RG_WARPS - 1) / RG_WARPS;
+    c.bstride = (size_t)max_fixed * (slot_cap + RG_WARPS);   // room for every warp's segment: n_fixed * RG_WARPS * jc <= n_fixed * (n_src + RG_WARPS - 1)
+    c.blocks = blocks_all + (size_t)p * BLK_FIELDS * (c.bstride + 32 * RG_WARPS);   // >= RG_WARPS segments rounded up to whole tiles
+    c.assoc = assoc_all + (size_t)p * c.bstride;
+    c.residuals = residuals_all ? residuals_all + (size_t)p * 2 * c.bstride : nullptr;
+    c.fixed_pose = fixed_pose + (size_t)prob.fixed_first * 3;
+    c.src_pose[0] = prob.src_pose[0]; c.src_pose[1] = prob.src_pose[1]; c.src_pose[2] = prob.src_pose[2];
+    c.staged = 0; c.mode = mode; c.slot_cap = slot_cap;
+    c.nres_per_block = (P.cost == TBV_P2L) ? 1 : 2;
+  }
+  __syncthreads();
+  rg_setup(sh, rg_stage, stage_bytes, sets, fixed_set, problems[p].fixed_first);
 
   // =========================================================================================================
   if (mode == REG_MODE_EVAL) {
     const double R = (eval_itr == 1) ? 2 * P.radius : P.radius;
-    associate(prob.src_pose, R);
-    const int nblk = sh.n_blocks;
+    const int nblk = rg_associate(sh, rg_stage, sh.c.src_pose, R);
     if (tid == 0) {
-      sh.ex[0] = prob.src_pose[0]; sh.ex[1] = prob.src_pose[1]; sh.ex[2] = prob.src_pose[2];
-      sh.cs[0] = cos(prob.src_pose[2]); sh.cs[1] = sin(prob.src_pose[2]);
+      sh.ex[0] = sh.c.src_pose[0]; sh.ex[1] = sh.c.src_pose[1]; sh.ex[2] = sh.c.src_pose[2];
+      sh.cs[0] = cos(sh.c.src_pose[2]); sh.cs[1] = sin(sh.c.src_pose[2]);
     }
     __syncthreads();
-    evaluate(nblk, true);
+    rg_evaluate(sh, 1);
     if (warp == 0) {
-      combine();
+      rg_combine(sh, lane);
       if (lane == 0) {
-        RegResult r;
-        memset(&r, 0, sizeof(r));
-        r.pose[0] = prob.src_pose[0]; r.pose[1] = prob.src_pose[1]; r.pose[2] = prob.src_pose[2];
-        r.num_residuals = nblk * nres_per_block;
-        r.success = r.num_residuals > 1;
-        r.final_cost = sh.acc[0];
-        r.score = sh.acc[0] / (double)max(r.num_residuals, 1);
-        *out = r;
+        RegResult* out = results + p;
+        out->pose[0] = sh.c.src_pose[0]; out->pose[1] = sh.c.src_pose[1]; out->pose[2] = sh.c.src_pose[2];
+        out->align[0] = out->align[1] = out->align[2] = 0.0;
+        out->pose_updated = 0; out->itrs = 0; out->lm_iterations = 0; out->last_n_iterations = 0; out->termination = 0;
+        out->last_relative_decrease = 0.0;
+        out->num_residuals = nblk * sh.c.nres_per_block;
+        out->success = out->num_residuals > 1;
+        out->final_cost = sh.acc[0];
+        out->score = sh.acc[0] / (double)max(nblk * sh.c.nres_per_block, 1);
         n_blocks_all[p] = nblk;
         if (eval_out)
           for (int i = 0; i < NACC; i++) eval_out[(size_t)p * NACC + i] = sh.acc[i];
@@ -1011,7 +1176,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
   LMState& S = sh.lm;
   OuterState& O = sh.outer;
   if (tid == 0) {
-    for (int c = 0; c < 3; c++) { O.par[c] = prob.src_pose[c]; O.prev_par[c] = prob.src_pose[c]; O.tsrc[c] = prob.src_pose[c]; }
+    for (int k = 0; k < 3; k++) { O.par[k] = sh.c.src_pose[k]; O.prev_par[k] = sh.c.src_pose[k]; O.tsrc[k] = sh.c.src_pose[k]; }
     O.prev_score = DBL_MAX;
     O.total_lm = 0; O.itr = 1; O.pose_updated = 0; O.success = 1;
     O.num_residuals = 0; O.last_n_iterations = 0; O.termination = 1;
@@ -1024,66 +1189,74 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     if (warp == 0) {   // evaluation point of the first evaluation = parameters.back()
       if (lane == 0) { sh.ex[0] = O.par[0]; sh.ex[1] = O.par[1]; sh.ex[2] = O.par[2]; }
       __syncwarp();
-      publish_eval_point(true);
+      rg_publish_eval_point(sh, lane, true);
     }
-    if (dbg) t_mark = clock64();
-    associate(O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
-    if (dbg) { const long long t = clock64(); t_assoc += t - t_mark; t_mark = t; }
-    const int nblk = sh.n_blocks;
-    if (nblk * nres_per_block <= 1) {  // BuildOptimizationProblem fails (:371-374): Register returns false, itr_ not advanced
-      if (tid == 0) { O.num_residuals = nblk * nres_per_block; O.success = 0; }
+    RG_TIMER_MARK();
+    const int nblk = rg_associate(sh, rg_stage, O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
+    RG_TIMER_ADD(t_assoc);
+    RG_TIMER_COUNT(n_rounds);
+    const int nres = nblk * sh.c.nres_per_block;
+    if (nres <= 1) {  // BuildOptimizationProblem fails (:371-374): Register returns false, itr_ not advanced
+      if (tid == 0) { O.num_residuals = nres; O.success = 0; }
       break;
     }
     // ---- ceres::Solve
     bool first = true;
     for (;;) {
-      evaluate(nblk, false);
-      if (dbg) { const long long t = clock64(); t_eval += t - t_mark; t_mark = t; }
+      rg_evaluate(sh, 0);
+      RG_TIMER_ADD(t_eval);
+      RG_TIMER_COUNT(n_evals);
       if (warp == 0) {
-        combine();
+        rg_combine(sh, lane);
+        RG_TIMER_SUB(t_s0);
         bool go = false;
         if (lane == 0) {
           if (first) lm_begin(S, O.par, sh.acc); else lm_candidate(S, sh.acc);
+          RG_TIMER_SUB(t_s1);
           go = lm_advance(S, P.max_itr_solver);
+          RG_TIMER_SUB(t_s2);
           if (go) { sh.ex[0] = S.cand[0]; sh.ex[1] = S.cand[1]; sh.ex[2] = S.cand[2]; }
-          else outer_advance(O, S, nblk * nres_per_block, P.max_itr_association);
+          else outer_advance(O, S, nres, P.max_itr_association);
           sh.flag = go ? 1 : 0;
         }
         __syncwarp();
-        publish_eval_point(go);
+        rg_publish_eval_point(sh, lane, go);
+        RG_TIMER_SUB(t_s3);
       }
       first = false;
       __syncthreads();
-      if (dbg) { const long long t = clock64(); t_lm += t - t_mark; t_mark = t; }
+      RG_TIMER_ADD(t_lm);
       if (!sh.flag) break;
     }
   }
   __syncthreads();
   if (tid == 0) {
     if (O.success && O.pose_updated) { O.tsrc[0] = O.par[0]; O.tsrc[1] = O.par[1]; O.tsrc[2] = O.par[2]; }
-    RegResult r;
-    memset(&r, 0, sizeof(r));
-    r.pose[0] = O.tsrc[0]; r.pose[1] = O.tsrc[1]; r.pose[2] = O.tsrc[2];
-    r.pose_updated = O.pose_updated;
-    r.success = O.success ? 1 : 0;
-    r.itrs = O.itr;
-    r.lm_iterations = O.total_lm;
-    r.num_residuals = O.num_residuals;
-    r.last_n_iterations = O.last_n_iterations;
-    r.termination = O.termination;
-    r.final_cost = O.final_cost;
-    r.last_relative_decrease = O.last_rel_dec;
-    r.score = O.success ? O.final_cost / (double)O.num_residuals : 0.0;
+    RegResult* out = results + p;
+    out->pose[0] = O.tsrc[0]; out->pose[1] = O.tsrc[1]; out->pose[2] = O.tsrc[2];
+    out->pose_updated = O.pose_updated;
+    out->success = O.success ? 1 : 0;
+    out->itrs = O.itr;
+    out->lm_iterations = O.total_lm;
+    out->num_residuals = O.num_residuals;
+    out->last_n_iterations = O.last_n_iterations;
+    out->termination = O.termination;
+    out->final_cost = O.final_cost;
+    out->last_relative_decrease = O.last_rel_dec;
+    out->score = O.success ? O.final_cost / (double)O.num_residuals : 0.0;
     // Talign = Trevised^-1 * Tto (loopclosure.cpp:73), Trevised = vectorToAffine(parameters)
-    const double* fp = fixed_pose + (size_t)prob.fixed_first * 3;
+    const double* fp = sh.c.fixed_pose;
     const Aff Tal = aff_mul(aff_inv(vec_to_aff(O.tsrc[0], O.tsrc[1], O.tsrc[2])), vec_to_aff(fp[0], fp[1], fp[2]));
-    r.align[0] = Tal.tx; r.align[1] = Tal.ty; r.align[2] = atan2(Tal.r10, Tal.r11);
-    *out = r;
+    out->align[0] = Tal.tx; out->align[1] = Tal.ty; out->align[2] = atan2(Tal.r10, Tal.r11);
     if (n_blocks_all) n_blocks_all[p] = sh.n_blocks;
+#ifdef TBV_DEV_TIMERS
     if (dbg) {
       atomicAdd(&dbg[0], (unsigned long long)t_assoc); atomicAdd(&dbg[1], (unsigned long long)t_eval); atomicAdd(&dbg[2], (unsigned long long)t_lm);
       atomicAdd(&dbg[3], (unsigned long long)(clock64() - t_start)); atomicAdd(&dbg[4], 1ull);
+      atomicAdd(&dbg[5], (unsigned long long)t_s0); atomicAdd(&dbg[6], (unsigned long long)t_s1); atomicAdd(&dbg[7], (unsigned long long)t_s2); atomicAdd(&dbg[8], (unsigned long long)t_s3);
+      atomicAdd(&dbg[9], (unsigned long long)n_rounds); atomicAdd(&dbg[10], (unsigned long long)n_evals);
     }
+#endif
   }
 }
 
@@ -1121,9 +1294,9 @@ void reg_release(tbv_ctx* ctx) {
 }
 int reg_scratch_reserve(tbv_ctx* ctx, int n_problems, int max_fixed, int slot_cap, bool want_residuals) {
   RegScratch& S = *reg_scratch(ctx);
-  const size_t slots = (size_t)n_problems * max_fixed * slot_cap;
+  const size_t slots = (size_t)n_problems * max_fixed * (slot_cap + RG_WARPS);   // the kernel's bstride per problem
   int rc;
-  if ((rc = S.assoc.reserve(slots)) || (rc = S.blocks.reserve(slots * BLK_FIELDS)) || (rc = S.n_blocks.reserve(n_problems)))
+  if ((rc = S.assoc.reserve(slots)) || (rc = S.blocks.reserve((slots + (size_t)n_problems * 32 * RG_WARPS) * BLK_FIELDS)) || (rc = S.n_blocks.reserve(n_problems)))
     return rc;
   if (want_residuals && (rc = S.residuals.reserve(slots * 2))) return rc;
   return TBV_OK;
@@ -1143,23 +1316,23 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   constexpr int RG_STAGE = 48 * 1024;
   unsigned long long* dbg = nullptr;  // per-phase cycle counters: development builds only (-DTBV_DEV_TIMERS)
 #ifdef TBV_DEV_TIMERS
-  if (!S.dbg.p) { if ((rc = S.dbg.reserve(8))) return rc; }
+  if (!S.dbg.p) { if ((rc = S.dbg.reserve(16))) return rc; }
   dbg = S.dbg.p;
-  TBV_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  TBV_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), ctx->stream));
 #endif
   if ((rc = ensure_dyn_smem(ctx, k_register<4>, RG_STAGE))) return rc;
   k_register<4><<<n_problems, RG_THREADS, RG_STAGE, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
                                                                slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, nullptr, dbg, RG_STAGE);
+                                                               want_residuals ? S.residuals.p : nullptr, dbg, RG_STAGE);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
 #ifdef TBV_DEV_TIMERS
   {  // mean cycles per problem spent in association / evaluation / LM + barrier
-    unsigned long long h[8];
+    unsigned long long h[16];
     TBV_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     TBV_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (h[4]) fprintf(stderr, "k_register cycles/problem: associate %.0f  evaluate %.0f  lm+barrier %.0f  total %.0f\n", (double)h[0] / h[4], (double)h[1] / h[4],
-                      (double)h[2] / h[4], (double)h[3] / h[4]);
+    if (h[4]) fprintf(stderr, "k_register cycles/problem: associate %.0f  evaluate %.0f  lm+barrier %.0f  total %.0f | combine %.0f begin/candidate %.0f advance %.0f publish %.0f | rounds %.2f evals %.2f\n", (double)h[0] / h[4], (double)h[1] / h[4],
+                      (double)h[2] / h[4], (double)h[3] / h[4], (double)h[5] / h[4], (double)h[6] / h[4], (double)h[7] / h[4], (double)h[8] / h[4], (double)h[9] / h[4], (double)h[10] / h[4]);
   }
 #endif
   return TBV_OK;

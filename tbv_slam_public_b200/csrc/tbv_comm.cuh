@@ -21,7 +21,8 @@ int* comm_send_count(tbv_ctx* ctx);                // device: header count of th
 int comm_allgather_merge(tbv_ctx* ctx, int capacity);
 tbv_constraint* comm_all(tbv_ctx* ctx);
 int* comm_n_all(tbv_ctx* ctx);
-int comm_fetch_all(tbv_ctx* ctx, tbv_constraint* dst, int n);   // merged records -> host (through pinned staging); synchronises
+// merged records (and their count) -> host through pinned staging, one stream synchronisation; *n_out may exceed dst_capacity
+int comm_fetch_all(tbv_ctx* ctx, tbv_constraint* dst, int dst_capacity, int* n_out);
 void comm_release(tbv_ctx* ctx);
 
 }  // namespace tbv
