@@ -193,7 +193,7 @@ int tbv_loopdb_add(tbv_loopdb* db, int n_sets, const tbv_cell* const* sets, cons
   }
   TBV_CUDA(cudaMemcpyAsync(db->views.p + db->n_kf, hv.data(), n_sets * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));  // hv goes out of scope
-  int rc = cellgrid_build_launch(ctx, db->views.p + db->n_kf, nullptr, n_sets, n_sets);
+  int rc = cellgrid_build_launch(ctx, db->views.p + db->n_kf, nullptr, n_sets, n_sets, db->cell_cap);
   if (rc) return rc;
   db->n_kf += n_sets;
   return TBV_OK;

@@ -113,6 +113,8 @@ tbv_ctx* tbv_create(int device) {
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (ctx->sm_count <= 0) ctx->sm_count = 148;
+  cudaDeviceGetAttribute(&ctx->smem_optin_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (ctx->smem_optin_max <= 0) ctx->smem_optin_max = 232448;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
     delete ctx;

@@ -313,7 +313,7 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   launched(ctx, "k_odom_update");
   TBV_CUDA(cudaGetLastError());
   // new keyframes get their search grid now (used by the registrations of the following frames)
-  return cellgrid_build_launch(ctx, od->views.p, od->fused_set.p, n_seq, n_seq * (od->K + 1), od->cpar.max_extent);
+  return cellgrid_build_launch(ctx, od->views.p, od->fused_set.p, n_seq, n_seq * (od->K + 1), od->cell_cap, od->cpar.max_extent);
 }
 
 // One step through a cached CUDA graph when the input buffer has been seen before (the launch-bound regime is the online one: one

@@ -440,8 +440,9 @@ __device__ __forceinline__ int grid_coord(float v, float mn, int n) {  // bucket
 }
 
 __global__ void __launch_bounds__(256)
-k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which, int n_sets, int bucket_cap) {
-  extern __shared__ int s_cnt[];  // [bucket_cap] <= GRID_CAP: the caller's bound on the buckets of one grid (larger grids: no grid)
+k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which, int n_sets, int bucket_cap, int sort_cap) {
+  extern __shared__ int s_cnt[];  // [bucket_cap] <= GRID_CAP: the caller's bound on the buckets of one grid (larger grids: no grid),
+                                  // then [sort_cap] float4 (16-byte aligned: bucket_cap is a multiple of 4): the entries before their final order
   __shared__ float s_red[4][8];
   __shared__ int s_part[256];
   __shared__ CellGrid s_g;
@@ -514,11 +515,35 @@ k_cellgrid_build(const SetView* __restrict__ sets, const int* __restrict__ which
   }
   if (tid == 0) t.gstart[nb] = (uint16_t)n;
   __syncthreads();
+  // Entries in bucket order (row-major).  When the set fits the staging area they are also put in ascending (x, cell index) order inside
+  // every bucket — buckets of a row ascend in x, so every bucket ROW is then sorted by x, which is what the per-row binary search of
+  // k_register's staged nearest-neighbour search needs (header ok = 2).  Larger sets keep the arbitrary order inside a bucket (ok = 1:
+  // searched bucket by bucket from global memory).
+  const bool sort_rows = n <= sort_cap;
+  float4* s_ent = reinterpret_cast<float4*>(s_cnt + bucket_cap);
   for (int i = tid; i < n; i += 256) {
     const float a = (float)U0[i], b = (float)U1[i];
     const int pos = atomicAdd(&s_cnt[grid_coord(b, g.miny, g.ny) * g.nx + grid_coord(a, g.minx, g.nx)], 1);
-    t.gent[pos] = make_float4(a, b, __int_as_float(i), 0.f);
+    const float4 e = make_float4(a, b, __int_as_float(i), 0.f);
+    if (sort_rows) s_ent[pos] = e; else t.gent[pos] = e;
   }
+  if (!sort_rows) return;
+  __syncthreads();
+  for (int pos = tid; pos < n; pos += 256) {
+    const float4 e = s_ent[pos];
+    const int idx = __float_as_int(e.z);
+    const int b = grid_coord(e.y, g.miny, g.ny) * g.nx + grid_coord(e.x, g.minx, g.nx);
+    const int lo = t.gstart[b], hi = t.gstart[b + 1];          // written by this block before the barrier above
+    const float key = (e.x == e.x) ? e.x : -FLT_MAX;            // a NaN mean (never produced by the cells kernel) sorts first: the order stays total
+    int rank = 0;
+    for (int k = lo; k < hi; k++) {
+      const float4 o = s_ent[k];
+      const float okey = (o.x == o.x) ? o.x : -FLT_MAX;
+      rank += (okey < key || (okey == key && __float_as_int(o.z) < idx)) ? 1 : 0;
+    }
+    t.gent[lo + rank] = e;
+  }
+  if (tid == 0) t.grid->ok = 2;
 }
 
 // MapPointNormal::GetClosestIdx (pointnormal.cpp:238-254): float 1-NN over the cell means, accepted iff d2 < R*R.
@@ -587,33 +612,13 @@ __device__ __forceinline__ int nn_search(const SetView& t, const CellGrid& g, in
   return (best >= 0 && (double)bestd < R * R) ? best : -1;
 }
 
-// The same search over a copy of the set's grid entries in SHARED memory.  The entries are in bucket order (row-major); per bucket row
-// the copy carries the start offsets of at most RG_NSEG equal runs of buckets ("x segments", 1 << shift buckets each), so a query
-// visits, in every bucket row its square [q - R, q + R] touches, the entries of the one or two segments the square overlaps — a
-// superset of the buckets nn_search visits, hence the same accepted neighbour (the closest entry overall, ties to the smaller cell
-// index, kept iff d2 < R*R; an entry outside the square is farther than R and could not have been accepted).
-#ifndef RG_NSEG_V
-#define RG_NSEG_V 16
-#endif
-constexpr int RG_NSEG = RG_NSEG_V;
-
-struct NNQuery {
-  float qx, qy;
-  int by0, by1, s0, s1;   // bucket rows / x segments to visit; by1 < by0: nothing (query outside the grid + R, NaN, or an idle lane)
-};
-__device__ __forceinline__ NNQuery nn_prepare(const CellGrid& g, int shift, float qx, float qy, float Rm, bool live) {
-  NNQuery q;
-  q.qx = qx; q.qy = qy; q.by0 = 0; q.by1 = -1; q.s0 = 0; q.s1 = 0;
-  const float ly = floorf((qy - Rm - g.miny) / GRID_CELL), hy = floorf((qy + Rm - g.miny) / GRID_CELL);
-  const float lx = floorf((qx - Rm - g.minx) / GRID_CELL), hx = floorf((qx + Rm - g.minx) / GRID_CELL);
-  if (live && hy >= 0.f && ly <= (float)(g.ny - 1) && hx >= 0.f && lx <= (float)(g.nx - 1)) {   // every comparison is false for NaN
-    q.by0 = ly > 0.f ? (int)ly : 0;
-    q.by1 = hy < (float)(g.ny - 1) ? (int)hy : g.ny - 1;
-    const int bx0 = lx > 0.f ? (int)lx : 0, bx1 = hx < (float)(g.nx - 1) ? (int)hx : g.nx - 1;
-    q.s0 = bx0 >> shift; q.s1 = bx1 >> shift;
-  }
-  return q;
-}
+// The same search over a copy of the set's grid entries in SHARED memory (grids built with ok == 2: every bucket row ascends in x).
+// row[r] = first entry of bucket row r (row[ny] = number of entries).  In every bucket row the square [q - R, q + R] touches, a binary
+// search finds the first entry with x >= qx - R and the scan stops at the first x > qx + R: a query looks at the handful of cells inside
+// its square, whatever the row holds (a wall along x puts dozens of cells into one bucket row; with one query per lane the warp would
+// otherwise wait for the lane with the longest row).  The entries visited are a superset of those within R of the query — an entry
+// outside the square is farther than R and could not be accepted — so the result is the exhaustive 1-NN + radius test of the
+// reference: the closest entry overall, ties to the smaller cell index, kept iff d2 < R*R.
 __device__ __forceinline__ void nn_visit(const float4 e, float qx, float qy, float& bestd, int& best) {
   const int i = __float_as_int(e.z);
   const float dx = qx - e.x, dy = qy - e.y;
@@ -621,14 +626,27 @@ __device__ __forceinline__ void nn_visit(const float4 e, float qx, float qy, flo
   dd = dd + dy * dy;
   if (dd < bestd || (dd == bestd && i < best)) { bestd = dd; best = i; }
 }
-// tab[row * stride + s] = first entry of x segment s of a bucket row (s == segments: the end of the row).
-__device__ __forceinline__ int nn_search_staged(const float4* __restrict__ ent, const uint16_t* __restrict__ tab, int stride, const NNQuery& Q, double R2) {
+__device__ __forceinline__ int nn_search_staged(const float4* __restrict__ ent, const uint16_t* __restrict__ row, const CellGrid& g, float qx, float qy,
+                                                float Rm, double R2, bool live) {
+  const float ly = floorf((qy - Rm - g.miny) / GRID_CELL), hy = floorf((qy + Rm - g.miny) / GRID_CELL);
+  if (!(live && hy >= 0.f && ly <= (float)(g.ny - 1))) return -1;   // the square lies outside the grid rows, q is NaN, or an idle lane
+  const int by0 = ly > 0.f ? (int)ly : 0, by1 = hy < (float)(g.ny - 1) ? (int)hy : g.ny - 1;
+  const float xlo = qx - Rm, xhi = qx + Rm;
   float bestd = FLT_MAX;
   int best = -1;
-  for (int r = Q.by0; r <= Q.by1; r++) {
-    const uint16_t* t = tab + r * stride;
-    const int j1 = t[Q.s1 + 1];
-    for (int j = t[Q.s0]; j < j1; j++) nn_visit(ent[j], Q.qx, Q.qy, bestd, best);
+  for (int r = by0; r <= by1; r++) {
+    int lo = row[r];
+    const int end = row[r + 1];
+    int n = end - lo;
+    while (n > 0) {   // lower bound of xlo in the row
+      const int half = n >> 1;
+      if (ent[lo + half].x < xlo) { lo += half + 1; n -= half + 1; } else n = half;
+    }
+    for (int j = lo; j < end; j++) {
+      const float4 e = ent[j];
+      if (e.x > xhi) break;
+      nn_visit(e, qx, qy, bestd, best);
+    }
   }
   return (best >= 0 && (double)bestd < R2) ? best : -1;
 }
@@ -703,8 +721,7 @@ struct RegShared {
   SetView tgt[RG_MAX_FIXED];
   CellGrid grid[RG_MAX_FIXED];   // search-grid headers of the fixed sets
   int n_tgt[RG_MAX_FIXED];
-  int ent_off[RG_MAX_FIXED], tab_off[RG_MAX_FIXED];           // byte offsets into the dynamic shared memory (staged working set)
-  int seg_shift[RG_MAX_FIXED], seg_stride[RG_MAX_FIXED];      // x segment = 1 << shift buckets; table row = segments + 1 offsets
+  int ent_off[RG_MAX_FIXED], row_off[RG_MAX_FIXED];           // byte offsets into the dynamic shared memory (staged working set)
   RegCtx c;
   LMState lm;
   OuterState outer;
@@ -825,9 +842,8 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
       const float qx = (float)((Tst.r00 * ux + Tst.r01 * uy) + Tst.tx), qy = (float)((Tst.r10 * ux + Tst.r11 * uy) + Tst.ty);
       int ti = -1;
       if (staged) {
-        const NNQuery Q = nn_prepare(sh.grid[fi], sh.seg_shift[fi], qx, qy, Rm, live);
-        ti = nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]), reinterpret_cast<const uint16_t*>(rg_stage + sh.tab_off[fi]),
-                              sh.seg_stride[fi], Q, R2);
+        ti = nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]), reinterpret_cast<const uint16_t*>(rg_stage + sh.row_off[fi]),
+                              sh.grid[fi], qx, qy, Rm, R2, live);
       } else if (live) {
         ti = nn_search(sh.tgt[fi], sh.grid[fi], sh.n_tgt[fi], qx, qy, R);
       }
@@ -1037,29 +1053,15 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
     }
   }
   // Stage what the nearest-neighbour search reads into shared memory when it fits (it does for the odometry and loop workloads:
-  // ~40 KB for 450-cell sets and four keyframes): the moving set's means and, per fixed set, its grid entries + the start offsets of
-  // the x segments of every bucket row.  The search then runs out of shared memory and the association pays ONE global round trip per
+  // ~38 KB for 450-cell sets and four keyframes): the moving set's means and, per fixed set, its grid entries (x-sorted bucket rows)
+  // + one start offset per bucket row.  The search then runs out of shared memory and the association pays ONE global round trip per
   // slot (the matched target's mean / normal / N / planarity) instead of one per link of query -> bucket rows -> entries -> target fields.
   if (tid == 0) {
     int need = n_src * 16, ok = 1;
     for (int f = 0; f < n_fixed; f++) {
-      if (!(sh.tgt[f].grid && sh.grid[f].ok)) { ok = 0; break; }
+      if (!(sh.tgt[f].grid && sh.grid[f].ok == 2)) { ok = 0; break; }
       sh.ent_off[f] = need; need += sh.n_tgt[f] * 16;
-    }
-    // segment tables: at most RG_NSEG segments per bucket row, coarsened (all sets together) until the tables fit
-    for (int bump = 0; ok; bump++) {
-      int t = need;
-      for (int f = 0; f < n_fixed; f++) {
-        const int nx = sh.grid[f].nx, ny = sh.grid[f].ny;
-        int shf = 0;
-        while (((nx - 1) >> shf) + 1 > RG_NSEG) shf++;
-        shf += bump;
-        const int stride = ((nx - 1) >> shf) + 2;
-        sh.tab_off[f] = t; sh.seg_shift[f] = shf; sh.seg_stride[f] = stride;
-        t += (ny * stride * 2 + 15) & ~15;
-      }
-      if (t <= stage_bytes) { need = t; break; }
-      if (bump >= 14) ok = 0;   // one segment per row is the smallest table there is
+      sh.row_off[f] = need; need += ((sh.grid[f].ny + 1) * 2 + 15) & ~15;
     }
     sh.c.staged = (ok && need <= stage_bytes) ? 1 : 0;
   }
@@ -1069,15 +1071,12 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
     for (int j = tid; j < n_src; j += RG_THREADS) su[j] = make_double2(c.sf[(size_t)CF_U0 * c.scap + j], c.sf[(size_t)CF_U1 * c.scap + j]);
     for (int f = 0; f < n_fixed; f++) {
       float4* e = reinterpret_cast<float4*>(rg_stage + sh.ent_off[f]);
-      uint16_t* tb = reinterpret_cast<uint16_t*>(rg_stage + sh.tab_off[f]);
-      const int nt = sh.n_tgt[f], ny = sh.grid[f].ny, nx = sh.grid[f].nx, stride = sh.seg_stride[f], shf = sh.seg_shift[f];
+      uint16_t* rw = reinterpret_cast<uint16_t*>(rg_stage + sh.row_off[f]);
+      const int nt = sh.n_tgt[f], ny = sh.grid[f].ny, nx = sh.grid[f].nx;
       const float4* __restrict__ gent = sh.tgt[f].gent;
       const uint16_t* __restrict__ gstart = sh.tgt[f].gstart;
       for (int j = tid; j < nt; j += RG_THREADS) e[j] = gent[j];
-      for (int k = tid; k < ny * stride; k += RG_THREADS) {
-        const int r = k / stride, sg = k - r * stride;
-        tb[k] = gstart[r * nx + min(sg << shf, nx)];   // sg == segments: the first bucket of the next row (the last row: the entry count)
-      }
+      for (int k = tid; k <= ny; k += RG_THREADS) rw[k] = k < ny ? gstart[k * nx] : (uint16_t)nt;
     }
   }
   __syncthreads();
@@ -1338,12 +1337,8 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   return TBV_OK;
 }
 
-int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets, double max_extent) {
+int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets, int cell_cap, double max_extent) {
   if (n_launch <= 0) return TBV_OK;
-  {
-    const int rc = ensure_dyn_smem(ctx, k_cellgrid_build, (size_t)GRID_CAP * sizeof(int));
-    if (rc) return rc;
-  }
   // shared-memory counters for as many buckets as a grid over cells within max_extent of the sensor can have (<= GRID_CAP): for the
   // odometry's 181 m that is 33 KB instead of 64 KB, so all 592 CTAs are resident at once instead of running as 1.33 waves
   int bucket_cap = GRID_CAP;
@@ -1351,7 +1346,19 @@ int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* whic
     const long long side = (long long)(2.0 * max_extent / GRID_CELL) + 2;
     if (side * side < GRID_CAP) bucket_cap = (int)(side * side);
   }
-  k_cellgrid_build<<<n_launch, 256, (size_t)bucket_cap * sizeof(int), ctx->stream>>>(sets_dev, which_dev, n_sets, bucket_cap);
+  bucket_cap = (bucket_cap + 3) & ~3;   // the entry staging area behind the counters stays 16-byte aligned
+  // + room to order the entries of a set of up to cell_cap cells inside their buckets (x-sorted bucket rows: the staged search of
+  // k_register needs them); a set that does not fit keeps bucket order only and is searched from global memory
+  const size_t cap_bytes = (size_t)ctx->smem_optin_max > 2048 ? (size_t)ctx->smem_optin_max - 2048 : 0;   // static shared memory of the kernel + reserve
+  int sort_cap = cell_cap > 0 ? cell_cap : 0;
+  if ((size_t)bucket_cap * sizeof(int) + (size_t)sort_cap * sizeof(float4) > cap_bytes)
+    sort_cap = cap_bytes > (size_t)bucket_cap * sizeof(int) ? (int)((cap_bytes - (size_t)bucket_cap * sizeof(int)) / sizeof(float4)) : 0;
+  const size_t smem = (size_t)bucket_cap * sizeof(int) + (size_t)sort_cap * sizeof(float4);
+  {
+    const int rc = ensure_dyn_smem(ctx, k_cellgrid_build, smem);
+    if (rc) return rc;
+  }
+  k_cellgrid_build<<<n_launch, 256, smem, ctx->stream>>>(sets_dev, which_dev, n_sets, bucket_cap, sort_cap);
   launched(ctx, "k_cellgrid_build");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
@@ -1400,7 +1407,7 @@ struct HostProblemSet {  // uploads n_sets cell sets, describes them as SetViews
     if ((rc = views.reserve(n_sets))) return rc;
     TBV_CUDA(cudaMemcpyAsync(views.p, hv.data(), n_sets * sizeof(SetView), cudaMemcpyHostToDevice, ctx->stream));
     TBV_CUDA(cudaStreamSynchronize(ctx->stream));  // hv goes out of scope
-    return cellgrid_build_launch(ctx, views.p, nullptr, n_sets, n_sets);
+    return cellgrid_build_launch(ctx, views.p, nullptr, n_sets, n_sets, max_n);
   }
 };
 

@@ -132,6 +132,7 @@ struct tbv_ctx {
   cudaStream_t stream = nullptr;
   long long launches = 0;
   int sm_count = 148;             // multiprocessors of `device` (queried in tbv_create)
+  int smem_optin_max = 232448;    // largest opt-in shared memory per block of `device` (queried in tbv_create; 227 KB on sm_100)
   tbv::Prof prof;
   std::vector<tbv::SmemOptIn> smem_optin;  // per context (= per device): no process-global launch state
   tbv::FilterState filt;

@@ -6,7 +6,8 @@ namespace tbv {
 
 constexpr int GRID_CAP = 16384;  // buckets of the 4 m search grid over a fixed scan's cell means (128 x 128 = 512 m span)
 
-struct CellGrid {       // header of one search grid; ok == 0: no grid (extent / size outside the limits) -> exhaustive search
+struct CellGrid {       // header of one search grid; ok == 0: no grid (extent / size outside the limits) -> exhaustive search;
+                        // 1: entries in bucket order; 2: and ascending in x inside every bucket row (what k_register stages)
   float minx, miny;
   int nx, ny, ok;
 };
@@ -36,7 +37,8 @@ struct GridStore {      // storage for the grids of n_sets cell sets
 
 // (re)builds the grids of sets which_dev[0..n_launch) (which_dev == nullptr: sets 0..n_launch-1; entries < 0 are skipped)
 // max_extent > 0: bound on |x|, |y| of the cell means (sizes the kernel's shared-memory counters; a larger set simply gets no grid)
-int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets, double max_extent = 0.0);
+// cell_cap: upper bound on the cells of any of those sets (sizes the shared-memory area in which the entries are ordered inside their buckets)
+int cellgrid_build_launch(tbv_ctx* ctx, const SetView* sets_dev, const int* which_dev, int n_launch, int n_sets, int cell_cap, double max_extent = 0.0);
 
 struct RegProblem {     // one n_scan_normal_reg::Register call: fixed scans + one moving scan
   int n_fixed;
@@ -71,12 +73,11 @@ constexpr int BLK_FIELDS = 9;  // per residual block: src(2) tar(2) [nrm(2) | L0
 
 struct RegScratch {            // association / residual-block scratch, [n_problems][...]
   DevBuf<int> assoc;           // [n_problems][max_fixed][slot_cap] target index per (fixed, src) or -1
-  DevBuf<double> wgt;          // [n_problems][max_fixed*slot_cap] loss weight of an accepted slot (between the two association passes)
-  DevBuf<double> blocks;       // [n_problems][BLK_FIELDS][max_fixed*slot_cap] compacted residual blocks, field-major
+  DevBuf<double> blocks;       // [n_problems] x (one segment per warp of tiles of 32 residual blocks, BLK_FIELDS x 32 doubles per tile)
   DevBuf<int> n_blocks;        // [n_problems]
   DevBuf<double> residuals;    // [n_problems][2*max_fixed*slot_cap] (eval mode, optional)
   DevBuf<unsigned long long> dbg;  // development builds only (-DTBV_DEV_TIMERS): per-phase cycle counters
-  void release() { assoc.release(); wgt.release(); blocks.release(); n_blocks.release(); residuals.release(); dbg.release(); }
+  void release() { assoc.release(); blocks.release(); n_blocks.release(); residuals.release(); dbg.release(); }
 };
 
 // Launches one CTA per problem.  All pointers are device pointers.  slot_cap >= number of cells of any moving scan,

@@ -177,8 +177,23 @@ def fake_api(monkeypatch):
         x[keep] = spl.spsolve(A[keep][:, keep].tocsc(), -g.reshape(-1)[keep])
         return x.reshape(n, 6), 1, 0.0
 
+    def pgo_solve_damped(ctx, ids, Hd, Ho, g, damping, fixed_node=0, max_iters=0, rel_tol=0):
+        # (H + diag(damping)) delta = -g through the radius interface: a diagonal chosen so that clamp(e) / 1 adds exactly `damping`
+        n, idx = len(Hd), np.arange(6)
+        Hd2 = np.array(Hd, np.float64).reshape(-1, 6, 6).copy()
+        total = Hd2[:, idx, idx] + np.asarray(damping, np.float64).reshape(-1, 6)
+        e = np.where(total / 2.0 >= 1e-6, total / 2.0, total - 1e-6)
+        Hd2[:, idx, idx] = np.where(e > 1e32, total - 1e32, e)
+        return pgo_solve_step(ctx, ids, Hd2, Ho, g, fixed_node, 1.0)
+
+    def pgo_optimize_device(ctx, *a, **kw):
+        # tbv_pgo_optimize runs the loop of pgo_optimize_ceres on the device; the rehearsal drives the same loop from the host over the fakes
+        return api.pgo_optimize_ceres(ctx, *a, **kw)
+
     monkeypatch.setattr(api, "pgo_assemble", pgo_assemble)
     monkeypatch.setattr(api, "pgo_solve_step", pgo_solve_step)
+    monkeypatch.setattr(api, "pgo_solve_damped", pgo_solve_damped)
+    monkeypatch.setattr(api, "pgo_optimize_device", pgo_optimize_device)
     return FakeCtx()
 
 
