@@ -612,6 +612,12 @@ __device__ __forceinline__ int nn_search(const SetView& t, const CellGrid& g, in
   return (best >= 0 && (double)bestd < R * R) ? best : -1;
 }
 
+// The specialised registration kernels reach the global-memory search only for sets too large to stage: out of line there, so that its
+// state does not compete for registers with the staged loop every problem of the hot path runs.
+__device__ __noinline__ int nn_search_cold(const SetView* t, const CellGrid* g, int n_tgt, float qx, float qy, double R) {
+  return nn_search(*t, *g, n_tgt, qx, qy, R);
+}
+
 // The same search over a copy of the set's grid entries in SHARED memory (grids built with ok == 2: every bucket row ascends in x).
 // row[r] = first entry of bucket row r (row[ny] = number of entries).  In every bucket row the square [q - R, q + R] touches, a binary
 // search finds the first entry with x >= qx - R and the scan stops at the first x > qx + R: a query looks at the handful of cells inside
@@ -801,6 +807,8 @@ __device__ __forceinline__ double* rg_segment(const RegCtx& c, int warp) { retur
 // ---- association at pose x with search radius R (AddScanPairCost for every fixed scan): the search runs out of shared memory; per
 // accepted slot ONE round trip to the matched target cell's fields (all loads issued together).  One barrier per round.
 // Returns the number of residual blocks of the problem (the same value in every thread).
+// COST >= 0: the cost function is fixed at compile time (specialised kernel, registration mode only); COST < 0: read from the parameters.
+template <int COST>
 __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __restrict__ rg_stage, const double* x, double R) {
   const RegCtx& c = sh.c;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -815,7 +823,7 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
   __syncthreads();
   const float Rm = (float)R + 1e-3f;
   const double R2 = R * R;
-  const int weight_opt = c.P.weight_opt, cost = c.P.cost, mode = c.mode;
+  const int weight_opt = c.P.weight_opt, cost = (COST >= 0) ? COST : c.P.cost, mode = (COST >= 0) ? (int)REG_MODE_REGISTER : c.mode;
   const bool weighted = weight_opt != TBV_W_UNIFORM, staged = c.staged != 0;
   const double angle_outlier = c.P.angle_outlier;
   const double* __restrict__ sf = c.sf;
@@ -845,7 +853,7 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
         ti = nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]), reinterpret_cast<const uint16_t*>(rg_stage + sh.row_off[fi]),
                               sh.grid[fi], qx, qy, Rm, R2, live);
       } else if (live) {
-        ti = nn_search(sh.tgt[fi], sh.grid[fi], sh.n_tgt[fi], qx, qy, R);
+        ti = (COST >= 0) ? nn_search_cold(&sh.tgt[fi], &sh.grid[fi], sh.n_tgt[fi], qx, qy, R) : nn_search(sh.tgt[fi], sh.grid[fi], sh.n_tgt[fi], qx, qy, R);
       }
       bool ok = false;
       double w = 1.0, tn0 = 0.0, tn1 = 0.0, tu0 = 0.0, tu1 = 0.0;
@@ -893,7 +901,7 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
         if (cost == TBV_P2L) {
           RG_STA(b + 4 * bstride, Ttar.r00 * tn0 + Ttar.r01 * tn1);
           RG_STA(b + 5 * bstride, Ttar.r10 * tn0 + Ttar.r11 * tn1);
-        } else if (cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
+        } else if ((COST < 0 || COST == TBV_P2D) && cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
           const double regularization = c.P.regularization, cov_scale = c.P.cov_scale;
           const double c00 = RG_LDA(tf + (size_t)CF_C00 * tcap + ti), c01 = RG_LDA(tf + (size_t)CF_C01 * tcap + ti);
           const double c10 = RG_LDA(tf + (size_t)CF_C10 * tcap + ti), c11 = RG_LDA(tf + (size_t)CF_C11 * tcap + ti);
@@ -944,6 +952,7 @@ __device__ __forceinline__ int rg_reference_index(const RegShared& sh, int warp,
 
 // ---- evaluation at sh.ex (cos/sin in sh.cs): per-warp partial sums in sh.warp_acc (fixed shapes: deterministic); ends with a barrier,
 // warp 0 combines them afterwards.
+template <int COST, int LOSS>
 __device__ __forceinline__ void rg_evaluate(RegShared& sh, int write_residuals) {
   const RegCtx& c = sh.c;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -955,32 +964,36 @@ __device__ __forceinline__ void rg_evaluate(RegShared& sh, int write_residuals) 
   const int n_mine = sh.warp_cnt[warp];
   const double* seg = rg_segment(c, warp) + lane;   // this lane's block of tile 0; its later blocks follow at RG_TILE doubles each
   constexpr size_t bstride = 32;
-  const int cost = c.P.cost, loss = c.P.loss;
   const double limit = c.P.loss_limit;
-  const bool simple_loss = (loss == TBV_LOSS_HUBER || loss == TBV_LOSS_NONE) && c.mode == REG_MODE_REGISTER;
-  if (simple_loss) {
-    if (loss == TBV_LOSS_HUBER) {
-      if (cost == TBV_P2L) eval_loop_simple<TBV_P2L, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
-      else if (cost == TBV_P2P) eval_loop_simple<TBV_P2P, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
-      else eval_loop_simple<TBV_P2D, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
-    } else {
-      if (cost == TBV_P2L) eval_loop_simple<TBV_P2L, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
-      else if (cost == TBV_P2P) eval_loop_simple<TBV_P2P, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
-      else eval_loop_simple<TBV_P2D, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
-    }
+  if (COST >= 0) {   // specialised kernel: one loop, nothing else compiled in
+    eval_loop_simple<COST, LOSS == TBV_LOSS_HUBER>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
   } else {
-    for (int k = lane; k < n_mine; k += 32, seg += RG_TILE) {
-      double f[2], J[6];
-      int n;
-      a[0] += eval_block(cost, loss, limit, seg, bstride, x0, x1, cy, sy, f, J, n, true);
-      for (int r = 0; r < n; r++) {
-        const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
-        a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
-        a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
+    const int cost = c.P.cost, loss = c.P.loss;
+    const bool simple_loss = (loss == TBV_LOSS_HUBER || loss == TBV_LOSS_NONE) && c.mode == REG_MODE_REGISTER;
+    if (simple_loss) {
+      if (loss == TBV_LOSS_HUBER) {
+        if (cost == TBV_P2L) eval_loop_simple<TBV_P2L, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+        else if (cost == TBV_P2P) eval_loop_simple<TBV_P2P, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+        else eval_loop_simple<TBV_P2D, true>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+      } else {
+        if (cost == TBV_P2L) eval_loop_simple<TBV_P2L, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+        else if (cost == TBV_P2P) eval_loop_simple<TBV_P2P, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
+        else eval_loop_simple<TBV_P2D, false>(seg, bstride, n_mine, limit, x0, x1, cy, sy, lane, a);
       }
-      if (write_residuals && c.residuals) {
-        const int q = rg_reference_index(sh, warp, k);
-        for (int r = 0; r < n; r++) c.residuals[(size_t)q * n + r] = f[r];
+    } else {
+      for (int k = lane; k < n_mine; k += 32, seg += RG_TILE) {
+        double f[2], J[6];
+        int n;
+        a[0] += eval_block(cost, loss, limit, seg, bstride, x0, x1, cy, sy, f, J, n, true);
+        for (int r = 0; r < n; r++) {
+          const double j0 = J[r * 3 + 0], j1 = J[r * 3 + 1], j2 = J[r * 3 + 2], fr = f[r];
+          a[1] += j0 * fr; a[2] += j1 * fr; a[3] += j2 * fr;
+          a[4] += j0 * j0; a[5] += j0 * j1; a[6] += j0 * j2; a[7] += j1 * j1; a[8] += j1 * j2; a[9] += j2 * j2;
+        }
+        if (write_residuals && c.residuals) {
+          const int q = rg_reference_index(sh, warp, k);
+          for (int r = 0; r < n; r++) c.residuals[(size_t)q * n + r] = f[r];
+        }
       }
     }
   }
@@ -1082,8 +1095,10 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
   __syncthreads();
 }
 
-// MIN_CTAS: resident CTAs per SM the register budget is set for (4 -> 64 registers)
-template <int MIN_CTAS>
+// MIN_CTAS: resident CTAs per SM the register budget is set for (4 -> 64 registers).
+// COST / LOSS >= 0: registration mode with that cost function and loss compiled in (the odometry and loop-closure configuration, P2L +
+// Huber, runs a kernel that carries no other cost function, loss, or the evaluation mode); < 0: everything, selected at run time.
+template <int MIN_CTAS, int COST, int LOSS>
 __global__ void __launch_bounds__(RG_THREADS, MIN_CTAS)
 k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
            const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
@@ -1134,21 +1149,21 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     c.fixed_pose = fixed_pose + (size_t)prob.fixed_first * 3;
     c.src_pose[0] = prob.src_pose[0]; c.src_pose[1] = prob.src_pose[1]; c.src_pose[2] = prob.src_pose[2];
     c.staged = 0; c.mode = mode; c.slot_cap = slot_cap;
-    c.nres_per_block = (P.cost == TBV_P2L) ? 1 : 2;
+    c.nres_per_block = (((COST >= 0) ? COST : P.cost) == TBV_P2L) ? 1 : 2;
   }
   __syncthreads();
   rg_setup(sh, rg_stage, stage_bytes, sets, fixed_set, problems[p].fixed_first);
 
   // =========================================================================================================
-  if (mode == REG_MODE_EVAL) {
+  if (COST < 0 && mode == REG_MODE_EVAL) {
     const double R = (eval_itr == 1) ? 2 * P.radius : P.radius;
-    const int nblk = rg_associate(sh, rg_stage, sh.c.src_pose, R);
+    const int nblk = rg_associate<COST>(sh, rg_stage, sh.c.src_pose, R);
     if (tid == 0) {
       sh.ex[0] = sh.c.src_pose[0]; sh.ex[1] = sh.c.src_pose[1]; sh.ex[2] = sh.c.src_pose[2];
       sh.cs[0] = cos(sh.c.src_pose[2]); sh.cs[1] = sin(sh.c.src_pose[2]);
     }
     __syncthreads();
-    rg_evaluate(sh, 1);
+    rg_evaluate<COST, LOSS>(sh, 1);
     if (warp == 0) {
       rg_combine(sh, lane);
       if (lane == 0) {
@@ -1191,7 +1206,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       rg_publish_eval_point(sh, lane, true);
     }
     RG_TIMER_MARK();
-    const int nblk = rg_associate(sh, rg_stage, O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
+    const int nblk = rg_associate<COST>(sh, rg_stage, O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
     RG_TIMER_ADD(t_assoc);
     RG_TIMER_COUNT(n_rounds);
     const int nres = nblk * sh.c.nres_per_block;
@@ -1202,7 +1217,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     // ---- ceres::Solve
     bool first = true;
     for (;;) {
-      rg_evaluate(sh, 0);
+      rg_evaluate<COST, LOSS>(sh, 0);
       RG_TIMER_ADD(t_eval);
       RG_TIMER_COUNT(n_evals);
       if (warp == 0) {
@@ -1319,10 +1334,13 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   dbg = S.dbg.p;
   TBV_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), ctx->stream));
 #endif
-  if ((rc = ensure_dyn_smem(ctx, k_register<4>, RG_STAGE))) return rc;
-  k_register<4><<<n_problems, RG_THREADS, RG_STAGE, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed,
-                                                               slot_cap, params, results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                               want_residuals ? S.residuals.p : nullptr, dbg, RG_STAGE);
+  // the configuration every caller on the hot path uses (odometry and loop closure: P2L, Huber) has its own kernel
+  auto kernel = k_register<4, -1, -1>;
+  if (mode == REG_MODE_REGISTER && params.cost == TBV_P2L && params.loss == TBV_LOSS_HUBER) kernel = k_register<4, TBV_P2L, TBV_LOSS_HUBER>;
+  if ((rc = ensure_dyn_smem(ctx, kernel, RG_STAGE))) return rc;
+  kernel<<<n_problems, RG_THREADS, RG_STAGE, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed, slot_cap, params,
+                                                        results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
+                                                        want_residuals ? S.residuals.p : nullptr, dbg, RG_STAGE);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
 #ifdef TBV_DEV_TIMERS
