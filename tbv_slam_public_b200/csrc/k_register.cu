@@ -723,7 +723,7 @@ struct RegShared {
   double ex[3], cs[2];
   int flag, n_blocks, warp_cnt[RG_WARPS];   // blocks in every warp's segment
   int cnt[RG_MAX_FIXED][RG_WARPS];          // ... split by fixed scan (evaluation mode: the reference's block order for the residual vector)
-  Aff Tst[RG_MAX_FIXED], Ttar[RG_MAX_FIXED];
+  Aff Tst[RG_MAX_FIXED], Ttar[RG_MAX_FIXED], TtarInv[RG_MAX_FIXED];   // source -> fixed frame at the current pose; fixed -> world (and back)
   SetView tgt[RG_MAX_FIXED];
   CellGrid grid[RG_MAX_FIXED];   // search-grid headers of the fixed sets
   int n_tgt[RG_MAX_FIXED];
@@ -938,6 +938,132 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
   return total;
 }
 
+// The same association for the specialised kernels (registration mode): source-cell-major — the moving cell's own fields are fetched once
+// and held while it is matched against every fixed scan (their latency overlaps the first search) — and the per-round transform
+// Tst = Ttar^-1 * T(x) reuses the cos / sin of x[2] that warp 0 has just published in sh.cs for the evaluation at the same point
+// (vec_to_aff(x) evaluates the same two functions on the same argument) and the inverse fixed poses of the set-up phase: no
+// trigonometry between the barriers of a round.  Blocks of a warp's segment are in (source index, fixed scan) order here; the sums are
+// the same fixed-shape reductions.
+template <int COST>
+__device__ __forceinline__ int rg_associate_fast(RegShared& sh, const uint8_t* __restrict__ rg_stage, const double* x, double R) {
+  const RegCtx& c = sh.c;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned FULL = 0xffffffffu;
+  const int n_fixed = c.n_fixed;
+  if (tid < n_fixed) {
+    Aff Tx;
+    Tx.r00 = sh.cs[0]; Tx.r01 = -sh.cs[1]; Tx.r10 = sh.cs[1]; Tx.r11 = sh.cs[0]; Tx.tx = x[0]; Tx.ty = x[1];
+    sh.Tst[tid] = aff_mul(sh.TtarInv[tid], Tx);
+  }
+  __syncthreads();
+  const float Rm = (float)R + 1e-3f;
+  const double R2 = R * R;
+  const int weight_opt = c.P.weight_opt;
+  const bool weighted = weight_opt != TBV_W_UNIFORM, staged = c.staged != 0;
+  const double angle_outlier = c.P.angle_outlier;
+  const double* __restrict__ sf = c.sf;
+  const size_t scap = c.scap;
+  constexpr size_t bstride = 32;
+  const double2* s_u = reinterpret_cast<const double2*>(rg_stage);
+  const int jc = c.jc, n_src = c.n_src;
+  const int j_begin = min(n_src, warp * jc), j_end = min(n_src, j_begin + jc);
+  double* seg = rg_segment(c, warp);
+  int my_cnt = 0;
+  for (int jb = j_begin; jb < j_end; jb += 32) {
+    const int j = jb + lane;
+    const bool live = j < j_end;
+    double ux = 0.0, uy = 0.0, sn0 = 0.0, sn1 = 0.0, N1 = 0.0, p1 = 0.0;
+    if (live) {
+      if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
+      else { ux = RG_LDA(sf + (size_t)CF_U0 * scap + j); uy = RG_LDA(sf + (size_t)CF_U1 * scap + j); }
+      sn0 = RG_LDA(sf + (size_t)CF_N0 * scap + j); sn1 = RG_LDA(sf + (size_t)CF_N1 * scap + j);
+      if (weighted) { N1 = RG_LDA(sf + (size_t)CF_NS * scap + j); p1 = RG_LDA(sf + (size_t)CF_SCALE * scap + j); }
+    }
+    for (int fi = 0; fi < n_fixed; fi++) {
+      const Aff& Tst = sh.Tst[fi];
+      const double* __restrict__ tf = sh.tgt[fi].f;
+      const size_t tcap = (size_t)sh.tgt[fi].cap;
+      const float qx = (float)((Tst.r00 * ux + Tst.r01 * uy) + Tst.tx), qy = (float)((Tst.r10 * ux + Tst.r11 * uy) + Tst.ty);
+      int ti = -1;
+      if (staged) {
+        ti = nn_search_staged(reinterpret_cast<const float4*>(rg_stage + sh.ent_off[fi]), reinterpret_cast<const uint16_t*>(rg_stage + sh.row_off[fi]),
+                              sh.grid[fi], qx, qy, Rm, R2, live);
+      } else if (live) {
+        ti = nn_search_cold(&sh.tgt[fi], &sh.grid[fi], sh.n_tgt[fi], qx, qy, R);
+      }
+      bool ok = false;
+      double w = 1.0, tn0 = 0.0, tn1 = 0.0, tu0 = 0.0, tu1 = 0.0;
+      if (ti >= 0) {
+        // every value of the target cell the decision, the weight and the block need, in one round trip
+        tn0 = RG_LDA(tf + (size_t)CF_N0 * tcap + ti); tn1 = RG_LDA(tf + (size_t)CF_N1 * tcap + ti);
+        tu0 = RG_LDA(tf + (size_t)CF_U0 * tcap + ti); tu1 = RG_LDA(tf + (size_t)CF_U1 * tcap + ti);
+        double N2 = 0.0, p2 = 0.0;
+        if (weighted) { N2 = RG_LDA(tf + (size_t)CF_NS * tcap + ti); p2 = RG_LDA(tf + (size_t)CF_SCALE * tcap + ti); }
+        const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
+        const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
+        const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
+        if (sim > angle_outlier) {
+          ok = true;
+          if (weighted) {
+            const double simN = 2 * fmin(N1, N2) / (N1 + N2);
+            const double simP = 2 * fmin(p1, p2) / (p1 + p2);
+            switch (weight_opt) {   // registration.cpp:67-75
+              case TBV_W_SIM_N: w = simN; break;
+              case TBV_W_SIM_DIRECTION: w = sim; break;
+              case TBV_W_SIM_SCALE: w = simP; break;
+              case TBV_W_COMBINED: w = simN + sim + simP; break;
+              default: w = 1.0;
+            }
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(FULL, ok);
+      if (ok) {
+        const int m = my_cnt + __popc(bal & ((1u << lane) - 1u));
+        double* b = seg + (size_t)(m >> 5) * RG_TILE + (m & 31);
+        const Aff& Ttar = sh.Ttar[fi];
+        RG_STA(b + 0 * bstride, ux);
+        RG_STA(b + 1 * bstride, uy);
+        RG_STA(b + 2 * bstride, (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx);
+        RG_STA(b + 3 * bstride, (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty);
+        if (COST == TBV_P2L) {
+          RG_STA(b + 4 * bstride, Ttar.r00 * tn0 + Ttar.r01 * tn1);
+          RG_STA(b + 5 * bstride, Ttar.r10 * tn0 + Ttar.r11 * tn1);
+        } else if (COST == TBV_P2D) {  // n_scan_normal.cpp:288-298
+          const double c00 = RG_LDA(tf + (size_t)CF_C00 * tcap + ti), c01 = RG_LDA(tf + (size_t)CF_C01 * tcap + ti);
+          const double c10 = RG_LDA(tf + (size_t)CF_C10 * tcap + ti), c11 = RG_LDA(tf + (size_t)CF_C11 * tcap + ti);
+          const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
+          const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
+          const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
+          const double M00 = RC00 * R00 + RC01 * R01, M01 = RC00 * R10 + RC01 * R11;
+          const double M10 = RC10 * R00 + RC11 * R01, M11 = RC10 * R10 + RC11 * R11;
+          const double t00 = (c.P.regularization + M00) * c.P.cov_scale, t01 = (0.0 + M01) * c.P.cov_scale;
+          const double t10 = (0.0 + M10) * c.P.cov_scale, t11 = (c.P.regularization + M11) * c.P.cov_scale;
+          const double det = t00 * t11 - t10 * t01;
+          const double invdet = 1.0 / det;
+          const double i00 = t11 * invdet, i10 = -t10 * invdet, i11 = t00 * invdet;
+          const double l00 = sqrt(i00);
+          const double l10 = i10 / l00;
+          const double l11 = sqrt(i11 - l10 * l10);
+          RG_STA(b + 4 * bstride, l00);
+          RG_STA(b + 5 * bstride, l10);
+          RG_STA(b + 6 * bstride, l11);
+        }
+        RG_STA(b + 7 * bstride, w);
+        RG_STA(b + 8 * bstride, sqrt(w));
+      }
+      my_cnt += __popc(bal);
+    }
+  }
+  if (lane == 0) sh.warp_cnt[warp] = my_cnt;
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int wv = 0; wv < RG_WARPS; wv++) total += sh.warp_cnt[wv];
+  if (tid == 0) sh.n_blocks = total;   // read again by thread 0 only (result record)
+  return total;
+}
+
 // evaluation mode: block k of this warp's segment -> its index in the reference's block order (fixed-scan-major, source index ascending)
 __device__ __forceinline__ int rg_reference_index(const RegShared& sh, int warp, int k) {
   const int n_fixed = sh.c.n_fixed;
@@ -1040,6 +1166,10 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
     g.minx = g.miny = 0.f; g.nx = g.ny = 1; g.ok = 0;
     if (sh.tgt[tid].grid) g = *sh.tgt[tid].grid;
     sh.grid[tid] = g;
+    const double* fp = c.fixed_pose + (size_t)tid * 3;   // the fixed poses do not change during the call
+    const Aff Ttar = vec_to_aff(fp[0], fp[1], fp[2]);
+    sh.Ttar[tid] = Ttar;
+    sh.TtarInv[tid] = aff_inv(Ttar);
   }
   __syncthreads();
   // Pull the problem's read-only working set into L2 with full-line prefetches (all lines in flight at once): the cell fields
@@ -1204,9 +1334,10 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       if (lane == 0) { sh.ex[0] = O.par[0]; sh.ex[1] = O.par[1]; sh.ex[2] = O.par[2]; }
       __syncwarp();
       rg_publish_eval_point(sh, lane, true);
+      __syncwarp();   // sh.cs is read by the first lanes of this warp at the top of the association (rg_associate_fast)
     }
     RG_TIMER_MARK();
-    const int nblk = rg_associate<COST>(sh, rg_stage, O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
+    const int nblk = (COST >= 0) ? rg_associate_fast<COST>(sh, rg_stage, O.par, R) : rg_associate<COST>(sh, rg_stage, O.par, R);  // ends with a barrier: sh.ex / sh.cs are visible too
     RG_TIMER_ADD(t_assoc);
     RG_TIMER_COUNT(n_rounds);
     const int nres = nblk * sh.c.nres_per_block;
