@@ -11,46 +11,33 @@
 //   * a "problem" = up to max_fixed fixed cell sets (keyframes) + one moving set; the CTA keeps the whole outer
 //     association loop and all LM iterations on chip: no host round trip per iteration, thousands of problems per launch
 //     (odometry: one per sequence; loop closure: one per candidate);
-//   * association: the fixed set's cell means are staged in shared memory as float2 (the reference searches a float
-//     kd-tree, pcl::PointXY); one warp per source cell scans them lane-strided and the warp takes the lexicographic
-//     (distance, index) minimum — the exhaustive 1-NN the kd-tree returns, lowest index on exact ties;
-//   * accepted correspondences are compacted IN ORDER (fixed scan major, source index ascending — the order the
-//     reference adds residual blocks in) into field-major arrays holding exactly what a cost functor captures
-//     (source mean, target mean and normal / sqrt-information pre-transformed to the world frame, loss weight);
-//   * one evaluation = every thread strides over the blocks, accumulates cost, g = J^T r (3) and H = J^T J (6 unique)
+//   * association: every fixed set has a 4 m search grid over its cell means (float: the reference searches a float kd-tree of
+//     pcl::PointXY) whose bucket rows are sorted by x when the grid is built; the CTA stages the grid entries + one offset per bucket
+//     row in shared memory, and a query is, per bucket row its square touches, a binary search for the square's left edge + a scan to
+//     its right edge — the exhaustive 1-NN + radius test the kd-tree answers, lowest cell index on exact ties;
+//   * every warp owns an equal share of the moving cells against ALL fixed sets and writes its accepted correspondences — exactly
+//     what a cost functor captures: source mean, target mean and normal / sqrt-information in the world frame, loss weight — into its
+//     own segment of the block scratch (tiles of 32 blocks, fields at constant offsets); the warp that writes a block evaluates it;
+//   * one evaluation = every warp sweeps its segment lane-strided, accumulates cost, g = J^T r (3) and H = J^T J (6 unique)
 //     of the loss-corrected residuals/Jacobians, fixed-shape warp-shuffle + cross-warp reduction (deterministic);
-//   * thread 0 runs the trust-region logic on the 3x3 system: Jacobi scaling, LM diagonal clamp, Cholesky, model
+//   * lane 0 of warp 0 runs the trust-region logic on the 3x3 system: Jacobi scaling, LM diagonal clamp, Cholesky, model
 //     cost change, step quality, radius update, the three tolerance tests — the same state machine as
-//     ceres::internal::TrustRegionMinimizer with max_consecutive_nonmonotonic_steps = 0.
+//     ceres::internal::TrustRegionMinimizer with max_consecutive_nonmonotonic_steps = 0;
+//   * the configuration every caller on the hot path uses (registration mode, P2L, Huber) has its own instantiation that carries no
+//     other cost function, loss or mode: 64 registers per thread (4 CTAs per SM: one wave for 592 problems) with few spills.
 // fp64 throughout (fp32 only where the reference uses float: the NN search), built with -fmad=false.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "tbv_reg.cuh"
 
 namespace tbv {
 
-#ifndef RG_THREADS_V
-#define RG_THREADS_V 256
-#endif
-constexpr int RG_THREADS = RG_THREADS_V;
+constexpr int RG_THREADS = 256;
 constexpr int RG_WARPS = RG_THREADS / 32;
-#ifdef RG_CG_A
-#define RG_LDA(p) __ldcg(p)
-#else
-#define RG_LDA(p) (*(p))
-#endif
-#ifdef RG_CG_S
-#define RG_STA(p, v) __stcg(p, v)
-#else
-#define RG_STA(p, v) (*(p) = (v))
-#endif
-#ifdef RG_CG_B
-#define RG_LDB(p) __ldcg(p)
-#else
-#define RG_LDB(p) (*(p))
-#endif
 constexpr int NACC = 10;  // cost, g0..g2, H00,H01,H02,H11,H12,H22
 
 struct Aff {
@@ -151,8 +138,8 @@ __device__ void scaled_loss(int loss, double limit, double w, double s, double r
 // blk points at field 0 of the block (stride = field stride).
 __device__ __forceinline__ double eval_block(int cost_type, int loss, double limit, const double* __restrict__ blk, size_t stride,
                                              double x0, double x1, double cy, double sy, double f[2], double J[6], int& n, bool want_jac) {
-  const double sx = RG_LDB(blk), sy_ = RG_LDB(blk + stride), tx = RG_LDB(blk + 2 * stride), ty = RG_LDB(blk + 3 * stride);
-  const double a4 = RG_LDB(blk + 4 * stride), a5 = RG_LDB(blk + 5 * stride), w = RG_LDB(blk + 7 * stride);
+  const double sx = blk[0], sy_ = blk[stride], tx = blk[2 * stride], ty = blk[3 * stride];
+  const double a4 = blk[4 * stride], a5 = blk[5 * stride], w = blk[7 * stride];
   const double mx = (cy * sx + (-sy) * sy_) + x0;
   const double my = (sy * sx + cy * sy_) + x1;
   const double dmx = (-sy) * sx + (-cy) * sy_;
@@ -168,7 +155,7 @@ __device__ __forceinline__ double eval_block(int cost_type, int loss, double lim
     J[0] = -1.0; J[1] = 0.0; J[2] = -dmx; J[3] = 0.0; J[4] = -1.0; J[5] = -dmy;
   } else {  // P2D: L = [a4 0; a5 a6]
     n = 2;
-    const double a6 = RG_LDB(blk + 6 * stride);
+    const double a6 = blk[6 * stride];
     const double e0 = mx - tx, e1 = my - ty;
     f[0] = a4 * e0 + 0.0 * e1;
     f[1] = a5 * e0 + a6 * e1;
@@ -740,8 +727,8 @@ struct RegShared {
 template <int COST, bool HUBER>
 __device__ __forceinline__ void eval_block_simple(const double* __restrict__ blk, size_t stride, double limit, double x0, double x1, double cy,
                                                   double sy, double* __restrict__ a) {
-  const double sx = RG_LDB(blk), sy_ = RG_LDB(blk + stride), tx = RG_LDB(blk + 2 * stride), ty = RG_LDB(blk + 3 * stride);
-  const double a4 = RG_LDB(blk + 4 * stride), a5 = RG_LDB(blk + 5 * stride), w = RG_LDB(blk + 7 * stride), sw = RG_LDB(blk + 8 * stride);
+  const double sx = blk[0], sy_ = blk[stride], tx = blk[2 * stride], ty = blk[3 * stride];
+  const double a4 = blk[4 * stride], a5 = blk[5 * stride], w = blk[7 * stride], sw = blk[8 * stride];
   const double mx = (cy * sx + (-sy) * sy_) + x0;
   const double my = (sy * sx + cy * sy_) + x1;
   const double dmx = (-sy) * sx + (-cy) * sy_;
@@ -756,7 +743,7 @@ __device__ __forceinline__ void eval_block_simple(const double* __restrict__ blk
     f[0] = tx - mx; f[1] = ty - my;
     J[0] = -1.0; J[1] = 0.0; J[2] = -dmx; J[3] = 0.0; J[4] = -1.0; J[5] = -dmy;
   } else {
-    const double a6 = RG_LDB(blk + 6 * stride);
+    const double a6 = blk[6 * stride];
     const double e0 = mx - tx, e1 = my - ty;
     f[0] = a4 * e0 + 0.0 * e1;
     f[1] = a5 * e0 + a6 * e1;
@@ -845,7 +832,7 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
       double ux = 0.0, uy = 0.0;
       if (live) {
         if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
-        else { ux = RG_LDA(sf + (size_t)CF_U0 * scap + j); uy = RG_LDA(sf + (size_t)CF_U1 * scap + j); }
+        else { ux = sf[(size_t)CF_U0 * scap + j]; uy = sf[(size_t)CF_U1 * scap + j]; }
       }
       const float qx = (float)((Tst.r00 * ux + Tst.r01 * uy) + Tst.tx), qy = (float)((Tst.r10 * ux + Tst.r11 * uy) + Tst.ty);
       int ti = -1;
@@ -859,13 +846,13 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
       double w = 1.0, tn0 = 0.0, tn1 = 0.0, tu0 = 0.0, tu1 = 0.0;
       if (ti >= 0) {
         // every value the decision, the weight and the block need, in one round trip
-        const double sn0 = RG_LDA(sf + (size_t)CF_N0 * scap + j), sn1 = RG_LDA(sf + (size_t)CF_N1 * scap + j);
-        tn0 = RG_LDA(tf + (size_t)CF_N0 * tcap + ti); tn1 = RG_LDA(tf + (size_t)CF_N1 * tcap + ti);
-        tu0 = RG_LDA(tf + (size_t)CF_U0 * tcap + ti); tu1 = RG_LDA(tf + (size_t)CF_U1 * tcap + ti);
+        const double sn0 = sf[(size_t)CF_N0 * scap + j], sn1 = sf[(size_t)CF_N1 * scap + j];
+        tn0 = tf[(size_t)CF_N0 * tcap + ti]; tn1 = tf[(size_t)CF_N1 * tcap + ti];
+        tu0 = tf[(size_t)CF_U0 * tcap + ti]; tu1 = tf[(size_t)CF_U1 * tcap + ti];
         double N1 = 0.0, N2 = 0.0, p1 = 0.0, p2 = 0.0;
         if (weighted) {
-          N1 = RG_LDA(sf + (size_t)CF_NS * scap + j); p1 = RG_LDA(sf + (size_t)CF_SCALE * scap + j);
-          N2 = RG_LDA(tf + (size_t)CF_NS * tcap + ti); p2 = RG_LDA(tf + (size_t)CF_SCALE * tcap + ti);
+          N1 = sf[(size_t)CF_NS * scap + j]; p1 = sf[(size_t)CF_SCALE * scap + j];
+          N2 = tf[(size_t)CF_NS * tcap + ti]; p2 = tf[(size_t)CF_SCALE * tcap + ti];
         }
         const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
         const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
@@ -894,17 +881,17 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
         const int m = my_cnt + __popc(bal & ((1u << lane) - 1u));
         double* b = seg + (size_t)(m >> 5) * RG_TILE + (m & 31);
         const Aff Ttar = sh.Ttar[fi];
-        RG_STA(b + 0 * bstride, ux);
-        RG_STA(b + 1 * bstride, uy);
-        RG_STA(b + 2 * bstride, (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx);
-        RG_STA(b + 3 * bstride, (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty);
+        b[0 * bstride] = ux;
+        b[1 * bstride] = uy;
+        b[2 * bstride] = (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx;
+        b[3 * bstride] = (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty;
         if (cost == TBV_P2L) {
-          RG_STA(b + 4 * bstride, Ttar.r00 * tn0 + Ttar.r01 * tn1);
-          RG_STA(b + 5 * bstride, Ttar.r10 * tn0 + Ttar.r11 * tn1);
+          b[4 * bstride] = Ttar.r00 * tn0 + Ttar.r01 * tn1;
+          b[5 * bstride] = Ttar.r10 * tn0 + Ttar.r11 * tn1;
         } else if ((COST < 0 || COST == TBV_P2D) && cost == TBV_P2D) {  // n_scan_normal.cpp:288-298
           const double regularization = c.P.regularization, cov_scale = c.P.cov_scale;
-          const double c00 = RG_LDA(tf + (size_t)CF_C00 * tcap + ti), c01 = RG_LDA(tf + (size_t)CF_C01 * tcap + ti);
-          const double c10 = RG_LDA(tf + (size_t)CF_C10 * tcap + ti), c11 = RG_LDA(tf + (size_t)CF_C11 * tcap + ti);
+          const double c00 = tf[(size_t)CF_C00 * tcap + ti], c01 = tf[(size_t)CF_C01 * tcap + ti];
+          const double c10 = tf[(size_t)CF_C10 * tcap + ti], c11 = tf[(size_t)CF_C11 * tcap + ti];
           const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
           const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
           const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
@@ -918,12 +905,12 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
           const double l00 = sqrt(i00);
           const double l10 = i10 / l00;
           const double l11 = sqrt(i11 - l10 * l10);
-          RG_STA(b + 4 * bstride, l00);
-          RG_STA(b + 5 * bstride, l10);
-          RG_STA(b + 6 * bstride, l11);
+          b[4 * bstride] = l00;
+          b[5 * bstride] = l10;
+          b[6 * bstride] = l11;
         }
-        RG_STA(b + 7 * bstride, w);
-        RG_STA(b + 8 * bstride, sqrt(w));
+        b[7 * bstride] = w;
+        b[8 * bstride] = sqrt(w);
       }
       my_cnt += __popc(bal);
     }
@@ -964,7 +951,6 @@ __device__ __forceinline__ int rg_associate_fast(RegShared& sh, const uint8_t* _
   const double* __restrict__ sf = c.sf;
   const size_t scap = c.scap;
   constexpr size_t bstride = 32;
-  const double2* s_u = reinterpret_cast<const double2*>(rg_stage);
   const int jc = c.jc, n_src = c.n_src;
   const int j_begin = min(n_src, warp * jc), j_end = min(n_src, j_begin + jc);
   double* seg = rg_segment(c, warp);
@@ -974,10 +960,9 @@ __device__ __forceinline__ int rg_associate_fast(RegShared& sh, const uint8_t* _
     const bool live = j < j_end;
     double ux = 0.0, uy = 0.0, sn0 = 0.0, sn1 = 0.0, N1 = 0.0, p1 = 0.0;
     if (live) {
-      if (staged) { const double2 u = s_u[j]; ux = u.x; uy = u.y; }
-      else { ux = RG_LDA(sf + (size_t)CF_U0 * scap + j); uy = RG_LDA(sf + (size_t)CF_U1 * scap + j); }
-      sn0 = RG_LDA(sf + (size_t)CF_N0 * scap + j); sn1 = RG_LDA(sf + (size_t)CF_N1 * scap + j);
-      if (weighted) { N1 = RG_LDA(sf + (size_t)CF_NS * scap + j); p1 = RG_LDA(sf + (size_t)CF_SCALE * scap + j); }
+      ux = sf[(size_t)CF_U0 * scap + j]; uy = sf[(size_t)CF_U1 * scap + j];
+      sn0 = sf[(size_t)CF_N0 * scap + j]; sn1 = sf[(size_t)CF_N1 * scap + j];
+      if (weighted) { N1 = sf[(size_t)CF_NS * scap + j]; p1 = sf[(size_t)CF_SCALE * scap + j]; }
     }
     for (int fi = 0; fi < n_fixed; fi++) {
       const Aff& Tst = sh.Tst[fi];
@@ -995,10 +980,10 @@ __device__ __forceinline__ int rg_associate_fast(RegShared& sh, const uint8_t* _
       double w = 1.0, tn0 = 0.0, tn1 = 0.0, tu0 = 0.0, tu1 = 0.0;
       if (ti >= 0) {
         // every value of the target cell the decision, the weight and the block need, in one round trip
-        tn0 = RG_LDA(tf + (size_t)CF_N0 * tcap + ti); tn1 = RG_LDA(tf + (size_t)CF_N1 * tcap + ti);
-        tu0 = RG_LDA(tf + (size_t)CF_U0 * tcap + ti); tu1 = RG_LDA(tf + (size_t)CF_U1 * tcap + ti);
+        tn0 = tf[(size_t)CF_N0 * tcap + ti]; tn1 = tf[(size_t)CF_N1 * tcap + ti];
+        tu0 = tf[(size_t)CF_U0 * tcap + ti]; tu1 = tf[(size_t)CF_U1 * tcap + ti];
         double N2 = 0.0, p2 = 0.0;
-        if (weighted) { N2 = RG_LDA(tf + (size_t)CF_NS * tcap + ti); p2 = RG_LDA(tf + (size_t)CF_SCALE * tcap + ti); }
+        if (weighted) { N2 = tf[(size_t)CF_NS * tcap + ti]; p2 = tf[(size_t)CF_SCALE * tcap + ti]; }
         const double snx = Tst.r00 * sn0 + Tst.r01 * sn1;
         const double sny = Tst.r10 * sn0 + Tst.r11 * sn1;
         const double sim = fmax(snx * tn0 + sny * tn1, 0.0);
@@ -1022,16 +1007,16 @@ __device__ __forceinline__ int rg_associate_fast(RegShared& sh, const uint8_t* _
         const int m = my_cnt + __popc(bal & ((1u << lane) - 1u));
         double* b = seg + (size_t)(m >> 5) * RG_TILE + (m & 31);
         const Aff& Ttar = sh.Ttar[fi];
-        RG_STA(b + 0 * bstride, ux);
-        RG_STA(b + 1 * bstride, uy);
-        RG_STA(b + 2 * bstride, (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx);
-        RG_STA(b + 3 * bstride, (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty);
+        b[0 * bstride] = ux;
+        b[1 * bstride] = uy;
+        b[2 * bstride] = (Ttar.r00 * tu0 + Ttar.r01 * tu1) + Ttar.tx;
+        b[3 * bstride] = (Ttar.r10 * tu0 + Ttar.r11 * tu1) + Ttar.ty;
         if (COST == TBV_P2L) {
-          RG_STA(b + 4 * bstride, Ttar.r00 * tn0 + Ttar.r01 * tn1);
-          RG_STA(b + 5 * bstride, Ttar.r10 * tn0 + Ttar.r11 * tn1);
+          b[4 * bstride] = Ttar.r00 * tn0 + Ttar.r01 * tn1;
+          b[5 * bstride] = Ttar.r10 * tn0 + Ttar.r11 * tn1;
         } else if (COST == TBV_P2D) {  // n_scan_normal.cpp:288-298
-          const double c00 = RG_LDA(tf + (size_t)CF_C00 * tcap + ti), c01 = RG_LDA(tf + (size_t)CF_C01 * tcap + ti);
-          const double c10 = RG_LDA(tf + (size_t)CF_C10 * tcap + ti), c11 = RG_LDA(tf + (size_t)CF_C11 * tcap + ti);
+          const double c00 = tf[(size_t)CF_C00 * tcap + ti], c01 = tf[(size_t)CF_C01 * tcap + ti];
+          const double c10 = tf[(size_t)CF_C10 * tcap + ti], c11 = tf[(size_t)CF_C11 * tcap + ti];
           const double R00 = Ttar.r00, R01 = Ttar.r01, R10 = Ttar.r10, R11 = Ttar.r11;
           const double RC00 = R00 * c00 + R01 * c10, RC01 = R00 * c01 + R01 * c11;
           const double RC10 = R10 * c00 + R11 * c10, RC11 = R10 * c01 + R11 * c11;
@@ -1045,12 +1030,12 @@ __device__ __forceinline__ int rg_associate_fast(RegShared& sh, const uint8_t* _
           const double l00 = sqrt(i00);
           const double l10 = i10 / l00;
           const double l11 = sqrt(i11 - l10 * l10);
-          RG_STA(b + 4 * bstride, l00);
-          RG_STA(b + 5 * bstride, l10);
-          RG_STA(b + 6 * bstride, l11);
+          b[4 * bstride] = l00;
+          b[5 * bstride] = l10;
+          b[6 * bstride] = l11;
         }
-        RG_STA(b + 7 * bstride, w);
-        RG_STA(b + 8 * bstride, sqrt(w));
+        b[7 * bstride] = w;
+        b[8 * bstride] = sqrt(w);
       }
       my_cnt += __popc(bal);
     }
@@ -1154,6 +1139,9 @@ __device__ __forceinline__ void rg_publish_eval_point(RegShared& sh, int lane, b
 }
 
 // ---- set-up: the problem's constants, L2 prefetch of its working set, staging of what the search reads into shared memory
+// STAGE_SRC: also stage the moving set's means (the fixed-scan-major association of the generic kernel re-reads them for every fixed scan;
+// the source-major association of the specialised kernels reads them once from global memory and leaves the room to the L1 cache).
+template <bool STAGE_SRC>
 __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg_stage, int stage_bytes, const SetView* __restrict__ sets,
                                       const int* __restrict__ fixed_set, int fixed_first) {
   const RegCtx& c = sh.c;
@@ -1200,7 +1188,7 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
   // + one start offset per bucket row.  The search then runs out of shared memory and the association pays ONE global round trip per
   // slot (the matched target's mean / normal / N / planarity) instead of one per link of query -> bucket rows -> entries -> target fields.
   if (tid == 0) {
-    int need = n_src * 16, ok = 1;
+    int need = STAGE_SRC ? n_src * 16 : 0, ok = 1;
     for (int f = 0; f < n_fixed; f++) {
       if (!(sh.tgt[f].grid && sh.grid[f].ok == 2)) { ok = 0; break; }
       sh.ent_off[f] = need; need += sh.n_tgt[f] * 16;
@@ -1211,7 +1199,8 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
   __syncthreads();
   if (c.staged) {
     double2* su = reinterpret_cast<double2*>(rg_stage);
-    for (int j = tid; j < n_src; j += RG_THREADS) su[j] = make_double2(c.sf[(size_t)CF_U0 * c.scap + j], c.sf[(size_t)CF_U1 * c.scap + j]);
+    if (STAGE_SRC)
+      for (int j = tid; j < n_src; j += RG_THREADS) su[j] = make_double2(c.sf[(size_t)CF_U0 * c.scap + j], c.sf[(size_t)CF_U1 * c.scap + j]);
     for (int f = 0; f < n_fixed; f++) {
       float4* e = reinterpret_cast<float4*>(rg_stage + sh.ent_off[f]);
       uint16_t* rw = reinterpret_cast<uint16_t*>(rg_stage + sh.row_off[f]);
@@ -1282,7 +1271,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     c.nres_per_block = (((COST >= 0) ? COST : P.cost) == TBV_P2L) ? 1 : 2;
   }
   __syncthreads();
-  rg_setup(sh, rg_stage, stage_bytes, sets, fixed_set, problems[p].fixed_first);
+  rg_setup<(COST < 0)>(sh, rg_stage, stage_bytes, sets, fixed_set, problems[p].fixed_first);
 
   // =========================================================================================================
   if (COST < 0 && mode == REG_MODE_EVAL) {
@@ -1400,6 +1389,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
       atomicAdd(&dbg[3], (unsigned long long)(clock64() - t_start)); atomicAdd(&dbg[4], 1ull);
       atomicAdd(&dbg[5], (unsigned long long)t_s0); atomicAdd(&dbg[6], (unsigned long long)t_s1); atomicAdd(&dbg[7], (unsigned long long)t_s2); atomicAdd(&dbg[8], (unsigned long long)t_s3);
       atomicAdd(&dbg[9], (unsigned long long)n_rounds); atomicAdd(&dbg[10], (unsigned long long)n_evals);
+      if (p < 2048) { dbg[16 + 4 * p] = (unsigned long long)(clock64() - t_start); dbg[17 + 4 * p] = (unsigned long long)n_evals; dbg[18 + 4 * p] = (unsigned long long)sh.c.n_src; dbg[19 + 4 * p] = (unsigned long long)sh.n_blocks; }
     }
 #endif
   }
@@ -1461,26 +1451,41 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   constexpr int RG_STAGE = 48 * 1024;
   unsigned long long* dbg = nullptr;  // per-phase cycle counters: development builds only (-DTBV_DEV_TIMERS)
 #ifdef TBV_DEV_TIMERS
-  if (!S.dbg.p) { if ((rc = S.dbg.reserve(16))) return rc; }
+  if (!S.dbg.p) { if ((rc = S.dbg.reserve(16 + 4 * 2048))) return rc; }
   dbg = S.dbg.p;
-  TBV_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  TBV_CUDA(cudaMemsetAsync(dbg, 0, (16 + 4 * 2048) * sizeof(unsigned long long), ctx->stream));
 #endif
-  // the configuration every caller on the hot path uses (odometry and loop closure: P2L, Huber) has its own kernel
+  // the configuration every caller on the hot path uses (odometry and loop closure: P2L, Huber) has its own kernel; it stages the fixed
+  // scans' grids only (42 KB: 4 CTAs x (42 KB + 5.2 KB static + 1 KB reserved) stay under the 196 KB shared-memory configuration, which
+  // leaves 60 KB of L1 to the stack lines instead of 28 KB)
   auto kernel = k_register<4, -1, -1>;
-  if (mode == REG_MODE_REGISTER && params.cost == TBV_P2L && params.loss == TBV_LOSS_HUBER) kernel = k_register<4, TBV_P2L, TBV_LOSS_HUBER>;
-  if ((rc = ensure_dyn_smem(ctx, kernel, RG_STAGE))) return rc;
-  kernel<<<n_problems, RG_THREADS, RG_STAGE, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed, slot_cap, params,
-                                                        results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
-                                                        want_residuals ? S.residuals.p : nullptr, dbg, RG_STAGE);
+  int stage = RG_STAGE;
+  if (mode == REG_MODE_REGISTER && params.cost == TBV_P2L && params.loss == TBV_LOSS_HUBER) { kernel = k_register<4, TBV_P2L, TBV_LOSS_HUBER>; stage = 42 * 1024; }
+  if ((rc = ensure_dyn_smem(ctx, kernel, stage))) return rc;
+  kernel<<<n_problems, RG_THREADS, stage, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed, slot_cap, params,
+                                                     results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
+                                                     want_residuals ? S.residuals.p : nullptr, dbg, stage);
   launched(ctx, "k_register");
   TBV_CUDA(cudaGetLastError());
 #ifdef TBV_DEV_TIMERS
   {  // mean cycles per problem spent in association / evaluation / LM + barrier
-    unsigned long long h[16];
+    static unsigned long long h[16 + 4 * 2048];
     TBV_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     TBV_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h[4]) fprintf(stderr, "k_register cycles/problem: associate %.0f  evaluate %.0f  lm+barrier %.0f  total %.0f | combine %.0f begin/candidate %.0f advance %.0f publish %.0f | rounds %.2f evals %.2f\n", (double)h[0] / h[4], (double)h[1] / h[4],
                       (double)h[2] / h[4], (double)h[3] / h[4], (double)h[5] / h[4], (double)h[6] / h[4], (double)h[7] / h[4], (double)h[8] / h[4], (double)h[9] / h[4], (double)h[10] / h[4]);
+    if (h[4] && n_problems <= 2048) {   // distribution over the problems of the launch: who is the slowest, and why
+      std::vector<int> idx(n_problems);
+      for (int i = 0; i < n_problems; i++) idx[i] = i;
+      std::sort(idx.begin(), idx.end(), [&](int a, int b) { return h[16 + 4 * a] < h[16 + 4 * b]; });
+      auto row = [&](int i) { fprintf(stderr, " [cyc %llu evals %llu n_src %llu blocks %llu]", h[16 + 4 * i], h[17 + 4 * i], h[18 + 4 * i], h[19 + 4 * i]); };
+      fprintf(stderr, "k_register distribution: min"); row(idx[0]);
+      fprintf(stderr, " p50"); row(idx[n_problems / 2]);
+      fprintf(stderr, " p90"); row(idx[n_problems * 9 / 10]);
+      fprintf(stderr, " p99"); row(idx[n_problems * 99 / 100]);
+      fprintf(stderr, " max"); row(idx[n_problems - 1]);
+      fprintf(stderr, "\n");
+    }
   }
 #endif
   return TBV_OK;

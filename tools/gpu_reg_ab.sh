@@ -17,7 +17,7 @@ try:
 except Exception as e:
     print(n, "parse failed", e)
 PY
-  grep "cycles/problem" gpurun_out/ab_$n.err | tail -2
+  grep "cycles/problem\|distribution" gpurun_out/ab_$n.err | tail -4
   for q in ${AB_SEQS:-}; do
     timeout 300 python bench.py --no-cpu-baseline --no-extra-legs --steps 6 --warmup 3 --seqs $q > gpurun_out/ab_${n}_$q.json 2> gpurun_out/ab_${n}_$q.err
     echo "  seqs=$q: $(python -c "import json;d=json.loads(open('gpurun_out/ab_${n}_$q.json').read().strip().splitlines()[-1]);print('k_register',d['kernels']['k_register']['ms_per_step'],'ms/step',d['ms_per_step'])" 2>&1 | tail -1)"
