@@ -36,8 +36,9 @@
 
 namespace tbv {
 
-constexpr int RG_THREADS = 256;
-constexpr int RG_WARPS = RG_THREADS / 32;
+constexpr int RG_THREADS = 256;            // threads per problem (CTA) of the standard launch; the single-fixed-scan launch uses RG_THREADS_SMALL
+constexpr int RG_WARPS = RG_THREADS / 32;  // = the largest number of warps a CTA of this kernel has (sizes of the per-warp tables)
+constexpr int RG_THREADS_SMALL = 128;
 constexpr int NACC = 10;  // cost, g0..g2, H00,H01,H02,H11,H12,H22
 
 struct Aff {
@@ -920,7 +921,7 @@ __device__ __forceinline__ int rg_associate(RegShared& sh, const uint8_t* __rest
   __syncthreads();
   int total = 0;
 #pragma unroll
-  for (int wv = 0; wv < RG_WARPS; wv++) total += sh.warp_cnt[wv];
+  for (int wv = 0; wv < RG_WARPS; wv++) total += (wv < (int)(blockDim.x >> 5)) ? sh.warp_cnt[wv] : 0;
   if (tid == 0) sh.n_blocks = total;   // read again by thread 0 only (result record)
   return total;
 }
@@ -1044,7 +1045,7 @@ __device__ __forceinline__ int rg_associate_fast(RegShared& sh, const uint8_t* _
   __syncthreads();
   int total = 0;
 #pragma unroll
-  for (int wv = 0; wv < RG_WARPS; wv++) total += sh.warp_cnt[wv];
+  for (int wv = 0; wv < RG_WARPS; wv++) total += (wv < (int)(blockDim.x >> 5)) ? sh.warp_cnt[wv] : 0;
   if (tid == 0) sh.n_blocks = total;   // read again by thread 0 only (result record)
   return total;
 }
@@ -1056,7 +1057,7 @@ __device__ __forceinline__ int rg_reference_index(const RegShared& sh, int warp,
   while (fi < n_fixed - 1 && k >= cum + sh.cnt[fi][warp]) { cum += sh.cnt[fi][warp]; fi++; }
   int q = k - cum;
   for (int f = 0; f < fi; f++)
-    for (int wv = 0; wv < RG_WARPS; wv++) q += sh.cnt[f][wv];
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) q += sh.cnt[f][wv];
   for (int wv = 0; wv < warp; wv++) q += sh.cnt[fi][wv];
   return q;
 }
@@ -1123,7 +1124,7 @@ __device__ __forceinline__ void rg_combine(RegShared& sh, int lane) {
   if (lane < NACC) {
     double v = 0.0;
 #pragma unroll
-    for (int wv = 0; wv < RG_WARPS; wv++) v += sh.warp_acc[wv][lane];
+    for (int wv = 0; wv < RG_WARPS; wv++) v += (wv < (int)(blockDim.x >> 5)) ? sh.warp_acc[wv][lane] : 0.0;
     sh.acc[lane] = v;
   }
   __syncwarp();
@@ -1174,12 +1175,12 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const char* ptr = reinterpret_cast<const char*>(base + (size_t)pf_fields[k] * cap);
-        for (int l = tid; l < lines; l += RG_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (size_t)l * 128));
+        for (int l = tid; l < lines; l += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (size_t)l * 128));
       }
       if (f >= 0 && sh.tgt[f].gent) {
         const char* ptr = reinterpret_cast<const char*>(sh.tgt[f].gent);
         const int elines = (cnt * 16 + 127) / 128;
-        for (int l = tid; l < elines; l += RG_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (size_t)l * 128));
+        for (int l = tid; l < elines; l += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (size_t)l * 128));
       }
     }
   }
@@ -1200,15 +1201,15 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
   if (c.staged) {
     double2* su = reinterpret_cast<double2*>(rg_stage);
     if (STAGE_SRC)
-      for (int j = tid; j < n_src; j += RG_THREADS) su[j] = make_double2(c.sf[(size_t)CF_U0 * c.scap + j], c.sf[(size_t)CF_U1 * c.scap + j]);
+      for (int j = tid; j < n_src; j += blockDim.x) su[j] = make_double2(c.sf[(size_t)CF_U0 * c.scap + j], c.sf[(size_t)CF_U1 * c.scap + j]);
     for (int f = 0; f < n_fixed; f++) {
       float4* e = reinterpret_cast<float4*>(rg_stage + sh.ent_off[f]);
       uint16_t* rw = reinterpret_cast<uint16_t*>(rg_stage + sh.row_off[f]);
       const int nt = sh.n_tgt[f], ny = sh.grid[f].ny, nx = sh.grid[f].nx;
       const float4* __restrict__ gent = sh.tgt[f].gent;
       const uint16_t* __restrict__ gstart = sh.tgt[f].gstart;
-      for (int j = tid; j < nt; j += RG_THREADS) e[j] = gent[j];
-      for (int k = tid; k <= ny; k += RG_THREADS) rw[k] = k < ny ? gstart[k * nx] : (uint16_t)nt;
+      for (int j = tid; j < nt; j += blockDim.x) e[j] = gent[j];
+      for (int k = tid; k <= ny; k += blockDim.x) rw[k] = k < ny ? gstart[k * nx] : (uint16_t)nt;
     }
   }
   __syncthreads();
@@ -1217,8 +1218,10 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
 // MIN_CTAS: resident CTAs per SM the register budget is set for (4 -> 64 registers).
 // COST / LOSS >= 0: registration mode with that cost function and loss compiled in (the odometry and loop-closure configuration, P2L +
 // Huber, runs a kernel that carries no other cost function, loss, or the evaluation mode); < 0: everything, selected at run time.
-template <int MIN_CTAS, int COST, int LOSS>
-__global__ void __launch_bounds__(RG_THREADS, MIN_CTAS)
+// THREADS: CTA size (RG_THREADS, or RG_THREADS_SMALL for launches of single-fixed-scan problems — loop-closure candidates — where
+// eight 4-warp CTAs per SM keep 1 184 problems resident at once instead of 592).
+template <int THREADS, int MIN_CTAS, int COST, int LOSS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegProblem* __restrict__ problems, const int* __restrict__ fixed_set,
            const double* __restrict__ fixed_pose, int max_fixed, int slot_cap, RegParamsDev P, RegResult* __restrict__ results,
            double* __restrict__ eval_out, int* __restrict__ assoc_all, double* __restrict__ blocks_all, int* __restrict__ n_blocks_all,
@@ -1260,7 +1263,7 @@ k_register(int mode, int eval_itr, const SetView* __restrict__ sets, const RegPr
     c.sf = src.f; c.scap = (size_t)src.cap;
     c.n_src = set_count(src);
     c.n_fixed = min(prob.n_fixed, RG_MAX_FIXED);
-    c.jc = (c.n_src + RG_WARPS - 1) / RG_WARPS;
+    c.jc = (c.n_src + (THREADS / 32) - 1) / (THREADS / 32);
     c.bstride = (size_t)max_fixed * (slot_cap + RG_WARPS);   // room for every warp's segment: n_fixed * RG_WARPS * jc <= n_fixed * (n_src + RG_WARPS - 1)
     c.blocks = blocks_all + (size_t)p * BLK_FIELDS * (c.bstride + 32 * RG_WARPS);   // >= RG_WARPS segments rounded up to whole tiles
     c.assoc = assoc_all + (size_t)p * c.bstride;
@@ -1446,7 +1449,6 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   if (rc) return rc;
   RegScratch& S = *reg_scratch(ctx);
   TBV_REQUIRE(max_fixed <= RG_MAX_FIXED, "too many fixed scans per problem (at most 16)");
-  (void)tgt_cap;
   // dynamic shared memory for the staged working set: 4 CTAs x (48 KB + 4.2 KB static + 1 KB reserved) fit one SM's 228 KB
   constexpr int RG_STAGE = 48 * 1024;
   unsigned long long* dbg = nullptr;  // per-phase cycle counters: development builds only (-DTBV_DEV_TIMERS)
@@ -1458,11 +1460,18 @@ int register_launch(tbv_ctx* ctx, int mode, int eval_itr, const SetView* sets_de
   // the configuration every caller on the hot path uses (odometry and loop closure: P2L, Huber) has its own kernel; it stages the fixed
   // scans' grids only (42 KB: 4 CTAs x (42 KB + 5.2 KB static + 1 KB reserved) stay under the 196 KB shared-memory configuration, which
   // leaves 60 KB of L1 to the stack lines instead of 28 KB)
-  auto kernel = k_register<4, -1, -1>;
-  int stage = RG_STAGE;
-  if (mode == REG_MODE_REGISTER && params.cost == TBV_P2L && params.loss == TBV_LOSS_HUBER) { kernel = k_register<4, TBV_P2L, TBV_LOSS_HUBER>; stage = 42 * 1024; }
+  auto kernel = k_register<RG_THREADS, 4, -1, -1>;
+  int stage = RG_STAGE, threads = RG_THREADS;
+  if (mode == REG_MODE_REGISTER && params.cost == TBV_P2L && params.loss == TBV_LOSS_HUBER) {
+    kernel = k_register<RG_THREADS, 4, TBV_P2L, TBV_LOSS_HUBER>; stage = 42 * 1024;
+    // single-fixed-scan problems (loop-closure candidates) in numbers that would not be resident at 4 CTAs per SM: 4-warp CTAs, 8 per SM
+    // (8 x (20 KB + 5.2 KB + 1 KB) of shared memory, 8 x 128 x 64 registers), one wave for up to 8 problems per SM
+    if (max_fixed == 1 && n_problems > 4 * ctx->sm_count && (size_t)tgt_cap * 16 + 4096 <= 20 * 1024) {
+      kernel = k_register<RG_THREADS_SMALL, 8, TBV_P2L, TBV_LOSS_HUBER>; stage = 20 * 1024; threads = RG_THREADS_SMALL;
+    }
+  }
   if ((rc = ensure_dyn_smem(ctx, kernel, stage))) return rc;
-  kernel<<<n_problems, RG_THREADS, stage, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed, slot_cap, params,
+  kernel<<<n_problems, threads, stage, ctx->stream>>>(mode, eval_itr, sets_dev, problems_dev, fixed_set_dev, fixed_pose_dev, max_fixed, slot_cap, params,
                                                      results_dev, eval_out_dev, S.assoc.p, S.blocks.p, S.n_blocks.p,
                                                      want_residuals ? S.residuals.p : nullptr, dbg, stage);
   launched(ctx, "k_register");
