@@ -273,10 +273,10 @@ def build_loop_sets(ctx, pool, kf_rows):
     return sets
 
 
-def run_loop_leg(api, ctx, db, sets, gt_kf, world, rank, barrier, reduce_max, want_cpu: bool, iters: int = 10, warmup: int = 2):
+def run_loop_leg(api, ctx, db, sets, gt_kf, world, rank, barrier, reduce_max, want_cpu: bool, iters: int = 40, warmup: int = 3):
     out = {"metric": "loop-closure candidate registrations/sec (P2L, Huber 0.1, SetParameters(4,10))", "unit": "pairs/s", "scaling": "weak",
            "keyframes": len(sets), "mean_cells": round(float(np.mean([len(c) for c in sets])), 1),
-           "sharding": f"candidates by id_from mod {world}; database replicated; ONE ncclAllGather of 128-byte constraint records + device merge per iteration, inside tbv_loopdb_register_sharded",
+           "sharding": f"candidates by id_from mod {world}; database replicated; ONE ncclAllGather of 128-byte constraint records + device merge per batch inside the library; two batches in flight (tbv_loopdb_submit_sharded / _collect_sharded), every batch's records collected on the host",
            "batches": {}}
     for P in LOOP_PAIRS_PER_GPU:
         fr, to, Tf, Tt = loop_candidates(gt_kf, P * world, world)
@@ -287,9 +287,14 @@ def run_loop_leg(api, ctx, db, sets, gt_kf, world, rank, barrier, reduce_max, wa
         l0 = ctx.launch_count()
         ph = np.zeros(4)
         t0 = time.perf_counter()
-        for _ in range(iters):
-            rec, tm = db.register_sharded(fr, to, Tf, Tt, want_timing=True)
+        # two batches in flight (tbv_loopdb_submit_sharded / _collect_sharded): the exchange of a batch runs under the registration of the next
+        db.submit_sharded(fr, to, Tf, Tt)
+        for _ in range(iters - 1):
+            db.submit_sharded(fr, to, Tf, Tt)
+            rec, tm = db.collect_sharded(want_timing=True)
             ph += tm
+        rec, tm = db.collect_sharded(want_timing=True)
+        ph += tm
         ctx.synchronize()
         sec = reduce_max(time.perf_counter() - t0)
         launches = ctx.launch_count() - l0
@@ -404,8 +409,11 @@ def run_mulran_leg(api, parallel, torch, ctx, sets, gt_kf, world, rank, local, b
     ctx.synchronize(); ctx2.synchronize(); barrier()
     t0 = time.perf_counter()
     for t in range(W, T):
-        fuser.step_dev(dev[t].data_ptr())          # asynchronous: the odometry step runs while the loop batch below is registered
-        rec = db2.register_sharded(fr, to, Tf, Tt)
+        fuser.step_dev(dev[t].data_ptr())          # asynchronous: the odometry step runs while the loop batches below are registered
+        db2.submit_sharded(fr, to, Tf, Tt)         # two loop batches in flight: the one submitted in the previous step is collected now
+        if t > W:
+            rec = db2.collect_sharded()
+    rec = db2.collect_sharded()
     ctx.synchronize(); ctx2.synchronize()
     sec_mixed = reduce_max(time.perf_counter() - t0)
     barrier()

@@ -444,6 +444,16 @@ int tbv_loopdb_register_sharded(tbv_loopdb* db, int n_cand, const int* from, con
                                 const double* quality, const tbv_reg_params* params, double max_score, tbv_constraint* all,
                                 int all_capacity, int* n_all, float* timing_ms);
 
+/* The same in two halves, so that a host with a stream of candidate batches (one per new keyframe, loopclosure.cpp:658-724) keeps two
+ * in flight: submit enqueues ONE H2D copy of the rank's share (pinned staging), the registration launch and the packing on the
+ * context's stream and the exchange (ncclAllGather + merge + D2H of the merged records into pinned memory) on a second stream of the
+ * database, and returns without waiting; collect blocks until the OLDEST submitted batch is on the host and copies it out.  Batches are
+ * collected in submission order; at most two may be in flight (TBV_ERR_INVALID on a third submit).  Every rank submits the same batches
+ * in the same order.  The exchange of batch i overlaps the registration of batch i + 1.  tbv_loopdb_register_sharded = submit + collect. */
+int tbv_loopdb_submit_sharded(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
+                              const double* quality, const tbv_reg_params* params, double max_score);
+int tbv_loopdb_collect_sharded(tbv_loopdb* db, tbv_constraint* all, int all_capacity, int* n_all, float* timing_ms);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
 void* tbv_host_alloc(size_t bytes);
 void tbv_host_free(void* p);

@@ -156,6 +156,9 @@ _OPTIONAL = [
                                  C.POINTER(RegParams), C.c_double, C.c_void_p, C.c_int, C.c_void_p], None),
     ("tbv_loopdb_register_sharded", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RegParams),
                                      C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
+    ("tbv_loopdb_submit_sharded", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RegParams),
+                                   C.c_double], None),
+    ("tbv_loopdb_collect_sharded", [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
     ("tbv_comm_unique_id", [C.c_void_p], None),
     ("tbv_comm_init_rank", [C.c_void_p, C.c_void_p, C.c_int, C.c_int], None),
     ("tbv_comm_init", [C.c_void_p, C.c_void_p], None),
@@ -491,6 +494,27 @@ class LoopDB:
         tm = (C.c_float * 4)() if want_timing else None
         _check(lib().tbv_loopdb_register_sharded(self.h, n, _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), _ptr(q), C.byref(params), float(max_score),
                                                  _ptr(out), n, C.byref(n_out), tm))
+        out = out[:n_out.value]
+        return (out, [float(v) for v in tm]) if want_timing else out
+
+    def submit_sharded(self, id_from, id_to, T_from, T_to, quality=None, params: RegParams | None = None, max_score=0.0):
+        """tbv_loopdb_submit_sharded: enqueue one sharded batch and return at once (at most two in flight; every rank submits the same
+        batches in the same order).  The exchange of a batch overlaps the registration of the next one."""
+        params = params or loop_reg_params()
+        fs, ts, Tf, Tt, _, q = self._cand_args(id_from, id_to, T_from, T_to, None, quality)
+        _check(lib().tbv_loopdb_submit_sharded(self.h, len(fs), _ptr(fs), _ptr(ts), _ptr(Tf), _ptr(Tt), _ptr(q), C.byref(params), float(max_score)))
+        self._pending = getattr(self, "_pending", []) + [len(fs)]
+
+    def collect_sharded(self, want_timing=False):
+        """tbv_loopdb_collect_sharded: the accepted constraints of the OLDEST batch in flight, global candidate order (blocks until they
+        are on the host)."""
+        pending = getattr(self, "_pending", [])
+        n = pending[0] if pending else 0
+        self._pending = pending[1:]
+        out = np.empty(max(n, 1), CONSTRAINT_DTYPE)
+        n_out = C.c_int(0)
+        tm = (C.c_float * 4)() if want_timing else None
+        _check(lib().tbv_loopdb_collect_sharded(self.h, _ptr(out), n, C.byref(n_out), tm))
         out = out[:n_out.value]
         return (out, [float(v) for v in tm]) if want_timing else out
 

@@ -192,27 +192,38 @@ k_merge_constraints(const tbv_constraint* __restrict__ blocks, int world, int st
   }
 }
 
-int comm_allgather_merge(tbv_ctx* ctx, int capacity) {
+// The exchange on explicit buffers and an explicit stream: send [capacity + 1] (header + records), recv [world][capacity + 1],
+// all [world * capacity], n_all [1].  tbv_loopdb_submit_sharded gives every batch in flight its own set and runs the exchange on a
+// second stream, so that the collective of one batch overlaps the registration of the next.
+int comm_allgather_merge_on(tbv_ctx* ctx, cudaStream_t stream, const tbv_constraint* send, tbv_constraint* recv, tbv_constraint* all,
+                            int* n_all, int capacity) {
   CommState* S = comm_state(ctx, true);
-  TBV_REQUIRE(capacity >= 1 && capacity <= S->capacity, "exchange buffers are smaller than the requested capacity");
+  TBV_REQUIRE(capacity >= 1 && send && all && n_all, "bad exchange buffers");
   TBV_REQUIRE(S->world <= 64, "more than 64 ranks");
   // Only the used part of a block travels: header + `capacity` records; the receive blocks lie back to back with that stride.
   const int stride = capacity + 1;
-  const tbv_constraint* blocks = S->send.p;
+  const tbv_constraint* blocks = send;
   if (S->world > 1) {
     const NcclApi* api = nccl_api();
-    TBV_REQUIRE(api && S->comm, "no NCCL communicator on this context (tbv_comm_init / tbv_comm_init_rank)");
-    TBV_NCCL(api, api->AllGather(S->send.p, S->recv.p, (size_t)stride * sizeof(tbv_constraint), ncclChar, S->comm, ctx->stream));
-    if (ctx->prof.on) prof_mark(ctx, "nccl_all_gather");   // not one of this library's kernels: timed, not counted as a launch
-    blocks = S->recv.p;
+    TBV_REQUIRE(api && S->comm && recv, "no NCCL communicator on this context (tbv_comm_init / tbv_comm_init_rank)");
+    TBV_NCCL(api, api->AllGather(send, recv, (size_t)stride * sizeof(tbv_constraint), ncclChar, S->comm, stream));
+    if (ctx->prof.on && stream == ctx->stream) prof_mark(ctx, "nccl_all_gather");   // not one of this library's kernels: timed, not counted as a launch
+    blocks = recv;
   }
   int grid = (S->world * capacity + 31) / 32;
   if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;
   if (grid < 1) grid = 1;
-  k_merge_constraints<<<grid, 256, 0, ctx->stream>>>(blocks, S->world, stride, capacity, S->all.p, S->n_all.p);
-  launched(ctx, "k_merge_constraints");
+  k_merge_constraints<<<grid, 256, 0, stream>>>(blocks, S->world, stride, capacity, all, n_all);
+  ctx->launches++;
+  if (ctx->prof.on && stream == ctx->stream) prof_mark(ctx, "k_merge_constraints");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
+}
+
+int comm_allgather_merge(tbv_ctx* ctx, int capacity) {
+  CommState* S = comm_state(ctx, true);
+  TBV_REQUIRE(capacity >= 1 && capacity <= S->capacity, "exchange buffers are smaller than the requested capacity");
+  return comm_allgather_merge_on(ctx, ctx->stream, S->send.p, S->recv.p, S->all.p, S->n_all.p, capacity);
 }
 
 }  // namespace tbv

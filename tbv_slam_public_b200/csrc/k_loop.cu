@@ -79,6 +79,33 @@ k_pack_constraints(const RegResult* __restrict__ res, const Candidate* __restric
 
 using namespace tbv;
 
+// One batch in flight of the pipelined sharded registration (tbv_loopdb_submit_sharded / tbv_loopdb_collect_sharded).  Every slot owns
+// all the memory its batch touches, so that batch i + 1 can be uploaded and registered while batch i is still in its exchange.
+struct LoopSlot {
+  uint8_t* up_host = nullptr;        // pinned: [problems | fixed_set | fixed_pose | candidates] of this rank's share, ONE H2D copy
+  size_t up_host_bytes = 0;
+  DevBuf<uint8_t> up_dev;            // the same block on the device
+  DevBuf<RegResult> results;
+  DevBuf<tbv_constraint> send;       // [capacity + 1]: header (count) + this rank's accepted records
+  DevBuf<tbv_constraint> recv;       // [world][capacity + 1]
+  DevBuf<tbv_constraint> all;        // [world * capacity] merged, global candidate order
+  DevBuf<int> n_all;
+  tbv_constraint* down_host = nullptr;   // pinned: merged records, then one record-sized slot holding the count
+  size_t down_host_n = 0;
+  int capacity = 0;                  // records per rank the exchange buffers are sized for
+  int area = 0;                      // world * capacity of the batch in flight
+  bool busy = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, registered + packed, merged, on the host
+  void release() {
+    for (cudaEvent_t& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    if (up_host) cudaFreeHost(up_host);
+    if (down_host) cudaFreeHost(down_host);
+    up_host = nullptr; down_host = nullptr; up_host_bytes = 0; down_host_n = 0; capacity = 0; busy = false;
+    up_dev.release(); results.release(); send.release(); recv.release(); all.release(); n_all.release();
+  }
+};
+constexpr int LOOP_SLOTS = 2;
+
 struct tbv_loopdb {
   tbv_ctx* ctx = nullptr;
   int max_kf = 0, cell_cap = 0, n_kf = 0;
@@ -94,9 +121,14 @@ struct tbv_loopdb {
   DevBuf<Candidate> cand;
   DevBuf<tbv_constraint> out;
   DevBuf<int> n_out;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // tbv_loopdb_register_sharded's optional phase timing
+  // pipelined sharded registration: LOOP_SLOTS batches in flight, submitted and collected in order
+  LoopSlot slot[LOOP_SLOTS];
+  long long n_submitted = 0, n_collected = 0;
+  cudaStream_t xstream = nullptr;   // the exchange (all-gather, merge, D2H) of a batch runs here, behind its registration on the context's stream
   void release() {
-    for (cudaEvent_t& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    for (LoopSlot& sl : slot) sl.release();
+    if (xstream) cudaStreamDestroy(xstream);
+    xstream = nullptr;
     store.release(); grids.release(); views.release(); problems.release(); fixed_set.release(); fixed_pose.release();
     results.release(); cand.release(); out.release(); n_out.release();
   }
@@ -244,67 +276,142 @@ int tbv_loopdb_register(tbv_loopdb* db, int n_cand, const int* from, const int* 
   return TBV_OK;
 }
 
+int tbv_loopdb_submit_sharded(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
+                              const double* quality, const tbv_reg_params* params, double max_score) {
+  TBV_ENTER(db ? db->ctx : nullptr);
+  TBV_REQUIRE(db && n_cand >= 0 && params, "bad arguments");
+  TBV_REQUIRE(n_cand == 0 || (from && to && T_from && T_to), "bad arguments");
+  TBV_REQUIRE(db->n_submitted - db->n_collected < LOOP_SLOTS, "two batches are in flight already: collect one first");
+  tbv_ctx* ctx = db->ctx;
+  const int world = comm_world(ctx), rank = comm_rank(ctx);
+  LoopSlot& sl = db->slot[db->n_submitted % LOOP_SLOTS];
+  // this rank's share: from mod world == rank (SURVEY 8e), ascending global index; capacity = the largest share over ranks, which
+  // every rank computes from the replicated list
+  int share[64] = {0};
+  for (int p = 0; p < n_cand; p++) {
+    TBV_REQUIRE(from[p] >= 0 && from[p] < db->n_kf && to[p] >= 0 && to[p] < db->n_kf, "candidate indexes a keyframe that is not in the database");
+    share[from[p] % world]++;
+  }
+  int capacity = 1;
+  for (int r = 0; r < world; r++) capacity = std::max(capacity, share[r]);
+  const int n_mine = share[rank];
+  // upload block: [RegProblem | fixed_set | fixed_pose | Candidate] x n_mine, sections 16-byte aligned
+  auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t o_prob = 0, o_fs = al16(o_prob + (size_t)n_mine * sizeof(RegProblem)), o_fp = al16(o_fs + (size_t)n_mine * sizeof(int)),
+               o_cand = al16(o_fp + (size_t)n_mine * 3 * sizeof(double)), up_bytes = al16(o_cand + (size_t)n_mine * sizeof(Candidate)) + 16;
+  int rc;
+  if (sl.up_host_bytes < up_bytes) {
+    if (sl.up_host) cudaFreeHost(sl.up_host);
+    sl.up_host = nullptr; sl.up_host_bytes = 0;
+    TBV_CUDA(cudaHostAlloc((void**)&sl.up_host, up_bytes, cudaHostAllocDefault));
+    sl.up_host_bytes = up_bytes;
+  }
+  if ((rc = sl.up_dev.reserve(up_bytes)) || (rc = sl.results.reserve(n_mine > 0 ? n_mine : 1)) || (rc = sl.n_all.reserve(1))) return rc;
+  if (capacity > sl.capacity) {   // the three exchange buffers are sized together: the merge addresses recv as [world][capacity + 1]
+    sl.capacity = 0;
+    if ((rc = sl.send.reserve((size_t)capacity + 1)) || (rc = sl.recv.reserve((size_t)world * ((size_t)capacity + 1))) ||
+        (rc = sl.all.reserve((size_t)world * capacity)))
+      return rc;
+    sl.capacity = capacity;
+  }
+  const size_t area = (size_t)world * (size_t)capacity;
+  if (sl.down_host_n < area + 1) {
+    if (sl.down_host) cudaFreeHost(sl.down_host);
+    sl.down_host = nullptr; sl.down_host_n = 0;
+    TBV_CUDA(cudaHostAlloc((void**)&sl.down_host, (area + 1) * sizeof(tbv_constraint), cudaHostAllocDefault));
+    sl.down_host_n = area + 1;
+  }
+  for (cudaEvent_t& e : sl.ev)
+    if (!e) TBV_CUDA(cudaEventCreate(&e));
+  if (!db->xstream) TBV_CUDA(cudaStreamCreateWithFlags(&db->xstream, cudaStreamNonBlocking));
+  RegProblem* hp = reinterpret_cast<RegProblem*>(sl.up_host + o_prob);
+  int* hfs = reinterpret_cast<int*>(sl.up_host + o_fs);
+  double* hfp = reinterpret_cast<double*>(sl.up_host + o_fp);
+  Candidate* hc = reinterpret_cast<Candidate*>(sl.up_host + o_cand);
+  int slot_cap = 1;
+  for (int p = 0, i = 0; p < n_cand; p++) {
+    if (from[p] % world != rank) continue;
+    hp[i].n_fixed = 1; hp[i].fixed_first = i; hp[i].src_set = from[p]; hp[i].active = 1;
+    hfs[i] = to[p];
+    for (int c = 0; c < 3; c++) { hp[i].src_pose[c] = T_from[3 * (size_t)p + c]; hfp[3 * (size_t)i + c] = T_to[3 * (size_t)p + c]; }
+    hc[i].from = from[p]; hc[i].to = to[p]; hc[i].index = p;
+    hc[i].quality[0] = quality ? quality[2 * (size_t)p] : 0.0;
+    hc[i].quality[1] = quality ? quality[2 * (size_t)p + 1] : 0.0;
+    if (db->n_cells[from[p]] > slot_cap) slot_cap = db->n_cells[from[p]];
+    i++;
+  }
+  // ---- registration + packing on the context's stream ---------------------------------------------------------------------------------
+  TBV_CUDA(cudaEventRecord(sl.ev[0], ctx->stream));
+  if (n_mine > 0) {
+    TBV_CUDA(cudaMemcpyAsync(sl.up_dev.p, sl.up_host, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const RegProblem* dp = reinterpret_cast<const RegProblem*>(sl.up_dev.p + o_prob);
+    rc = register_launch(ctx, REG_MODE_REGISTER, 0, db->views.p, dp, reinterpret_cast<const int*>(sl.up_dev.p + o_fs),
+                         reinterpret_cast<const double*>(sl.up_dev.p + o_fp), n_mine, 1, slot_cap, db->cell_cap, to_dev(*params), sl.results.p,
+                         nullptr, false);
+    if (rc) return rc;
+    k_pack_constraints<<<1, 256, 0, ctx->stream>>>(sl.results.p, reinterpret_cast<const Candidate*>(sl.up_dev.p + o_cand), n_mine, max_score,
+                                                   sl.send.p + 1, capacity, reinterpret_cast<int*>(sl.send.p));
+    launched(ctx, "k_pack_constraints");
+    TBV_CUDA(cudaGetLastError());
+  } else {
+    TBV_CUDA(cudaMemsetAsync(sl.send.p, 0, sizeof(int), ctx->stream));
+  }
+  TBV_CUDA(cudaEventRecord(sl.ev[1], ctx->stream));
+  // ---- exchange + return of the merged records on the exchange stream (the context's own stream while a profile is being taken, so that
+  //      the per-launch events of tbv_profile_begin/_end see it) -----------------------------------------------------------------------------
+  cudaStream_t xs = ctx->prof.on ? ctx->stream : db->xstream;
+  if (xs != ctx->stream) TBV_CUDA(cudaStreamWaitEvent(xs, sl.ev[1], 0));
+  if ((rc = comm_allgather_merge_on(ctx, xs, sl.send.p, sl.recv.p, sl.all.p, sl.n_all.p, capacity))) return rc;
+  TBV_CUDA(cudaEventRecord(sl.ev[2], xs));
+  // The count and the records cross in ONE round (the merged area is what the ranks can have accepted: a few hundred KB); a caller
+  // whose array is smaller than the number of accepted records gets TBV_ERR_CAPACITY from the collect.
+  int* count = reinterpret_cast<int*>(sl.down_host + area);
+  TBV_CUDA(cudaMemcpyAsync(count, sl.n_all.p, sizeof(int), cudaMemcpyDeviceToHost, xs));
+  TBV_CUDA(cudaMemcpyAsync(sl.down_host, sl.all.p, area * sizeof(tbv_constraint), cudaMemcpyDeviceToHost, xs));
+  TBV_CUDA(cudaEventRecord(sl.ev[3], xs));
+  sl.area = (int)area;
+  sl.busy = true;
+  db->n_submitted++;
+  return TBV_OK;
+}
+
+int tbv_loopdb_collect_sharded(tbv_loopdb* db, tbv_constraint* all, int all_capacity, int* n_all, float* timing_ms) {
+  TBV_ENTER(db ? db->ctx : nullptr);
+  TBV_REQUIRE(db && n_all && all_capacity >= 0 && (all || all_capacity == 0), "bad arguments");
+  *n_all = 0;
+  TBV_REQUIRE(db->n_collected < db->n_submitted, "no batch in flight");
+  LoopSlot& sl = db->slot[db->n_collected % LOOP_SLOTS];
+  TBV_CUDA(cudaEventSynchronize(sl.ev[3]));
+  sl.busy = false;
+  db->n_collected++;
+  const int n = *reinterpret_cast<const int*>(sl.down_host + sl.area);
+  *n_all = n;
+  const size_t take = (size_t)std::max(0, std::min(n, all_capacity));
+  if (take) memcpy(all, sl.down_host, take * sizeof(tbv_constraint));
+  if (timing_ms) {
+    // {H2D of the share + registration + packing, all-gather + merge, D2H of the merged records, whole batch}; the collective and the
+    // merge kernel are timed together here, their split is available through tbv_profile_begin/_end ("nccl_all_gather", "k_merge_constraints")
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[0], sl.ev[0], sl.ev[1]));
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[1], sl.ev[1], sl.ev[2]));
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[2], sl.ev[2], sl.ev[3]));
+    TBV_CUDA(cudaEventElapsedTime(&timing_ms[3], sl.ev[0], sl.ev[3]));
+  }
+  if (n > all_capacity) { set_error("tbv_loopdb_collect_sharded: %d constraints accepted, room for %d", n, all_capacity); return TBV_ERR_CAPACITY; }
+  return TBV_OK;
+}
+
 int tbv_loopdb_register_sharded(tbv_loopdb* db, int n_cand, const int* from, const int* to, const double* T_from, const double* T_to,
                                 const double* quality, const tbv_reg_params* params, double max_score, tbv_constraint* all,
                                 int all_capacity, int* n_all, float* timing_ms) {
   TBV_ENTER(db ? db->ctx : nullptr);
   TBV_REQUIRE(db && n_cand >= 0 && params && n_all && all_capacity >= 0 && (all || all_capacity == 0), "bad arguments");
-  TBV_REQUIRE(n_cand == 0 || (from && to && T_from && T_to), "bad arguments");
-  tbv_ctx* ctx = db->ctx;
-  const int world = comm_world(ctx), rank = comm_rank(ctx);
   *n_all = 0;
   if (timing_ms) for (int i = 0; i < 4; i++) timing_ms[i] = 0.f;
+  TBV_REQUIRE(db->n_submitted == db->n_collected, "a submitted batch is still in flight: collect it first");
   if (n_cand == 0) return TBV_OK;
-  // this rank's share: from mod world == rank (SURVEY 8e), ascending global index; capacity = the largest share over ranks, which
-  // every rank computes from the replicated list
-  std::vector<int> share(world, 0), mine;
-  for (int p = 0; p < n_cand; p++) {
-    TBV_REQUIRE(from[p] >= 0, "candidate indexes a keyframe that is not in the database");
-    const int r = from[p] % world;
-    share[r]++;
-    if (r == rank) mine.push_back(p);
-  }
-  int capacity = 1;
-  for (int r = 0; r < world; r++) capacity = std::max(capacity, share[r]);
-  const int n_mine = (int)mine.size();
-  std::vector<int> f(n_mine), t(n_mine);
-  std::vector<double> Tf((size_t)n_mine * 3), Tt((size_t)n_mine * 3), q;
-  if (quality) q.resize((size_t)n_mine * 2);
-  for (int i = 0; i < n_mine; i++) {
-    const int p = mine[i];
-    f[i] = from[p]; t[i] = to[p];
-    for (int c = 0; c < 3; c++) { Tf[3 * (size_t)i + c] = T_from[3 * (size_t)p + c]; Tt[3 * (size_t)i + c] = T_to[3 * (size_t)p + c]; }
-    if (quality) { q[2 * (size_t)i] = quality[2 * (size_t)p]; q[2 * (size_t)i + 1] = quality[2 * (size_t)p + 1]; }
-  }
-  int rc = comm_reserve(ctx, capacity);
+  int rc = tbv_loopdb_submit_sharded(db, n_cand, from, to, T_from, T_to, quality, params, max_score);
   if (rc) return rc;
-  if (timing_ms)
-    for (cudaEvent_t& e : db->ev)
-      if (!e) TBV_CUDA(cudaEventCreate(&e));
-  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[0], ctx->stream));
-  if (n_mine > 0) {
-    rc = loopdb_enqueue(db, n_mine, f.data(), t.data(), Tf.data(), Tt.data(), mine.data(), quality ? q.data() : nullptr, params, max_score,
-                        comm_send_records(ctx), capacity, comm_send_count(ctx));
-    if (rc) return rc;
-  } else {
-    TBV_CUDA(cudaMemsetAsync(comm_send_count(ctx), 0, sizeof(int), ctx->stream));
-  }
-  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[1], ctx->stream));
-  if ((rc = comm_allgather_merge(ctx, capacity))) return rc;
-  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[2], ctx->stream));
-  if ((rc = comm_fetch_all(ctx, all, all_capacity, n_all))) return rc;
-  if (*n_all > all_capacity) { set_error("tbv_loopdb_register_sharded: %d constraints accepted, room for %d", *n_all, all_capacity); rc = TBV_ERR_CAPACITY; }
-  if (timing_ms) TBV_CUDA(cudaEventRecord(db->ev[3], ctx->stream));
-  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (timing_ms) {
-    // {registration + packing, all-gather + merge, -, whole call}: the collective and the merge kernel are timed together here; their
-    // split is available through tbv_profile_begin/_end ("nccl_all_gather", "k_merge_constraints")
-    TBV_CUDA(cudaEventElapsedTime(&timing_ms[0], db->ev[0], db->ev[1]));
-    TBV_CUDA(cudaEventElapsedTime(&timing_ms[1], db->ev[1], db->ev[2]));
-    TBV_CUDA(cudaEventElapsedTime(&timing_ms[2], db->ev[2], db->ev[3]));
-    TBV_CUDA(cudaEventElapsedTime(&timing_ms[3], db->ev[0], db->ev[3]));
-  }
-  return rc;
+  return tbv_loopdb_collect_sharded(db, all, all_capacity, n_all, timing_ms);
 }
 
 }  // extern "C"

@@ -21,6 +21,10 @@ int* comm_send_count(tbv_ctx* ctx);                // device: header count of th
 int comm_allgather_merge(tbv_ctx* ctx, int capacity);
 tbv_constraint* comm_all(tbv_ctx* ctx);
 int* comm_n_all(tbv_ctx* ctx);
+// The same exchange on the caller's buffers and stream: send [capacity + 1] (header + records), recv [world][capacity + 1] (unused at
+// world 1), all [world * capacity], n_all [1].  The collectives of one communicator must be enqueued in the same order on every rank.
+int comm_allgather_merge_on(tbv_ctx* ctx, cudaStream_t stream, const tbv_constraint* send, tbv_constraint* recv, tbv_constraint* all,
+                            int* n_all, int capacity);
 // merged records (and their count) -> host through pinned staging, one stream synchronisation; *n_out may exceed dst_capacity
 int comm_fetch_all(tbv_ctx* ctx, tbv_constraint* dst, int dst_capacity, int* n_out);
 void comm_release(tbv_ctx* ctx);

@@ -213,6 +213,21 @@ int main(int argc, char** argv) {
            "tbv_loopdb_register_sharded: %s", tbv_last_error());
     EXPECT(n_got == n_ref && std::memcmp(got.data(), ref.data(), (size_t)n_ref * sizeof(tbv_constraint)) == 0, "sharded registration differs from the single-GPU call (%d vs %d)", n_got, n_ref);
     EXPECT(ms[3] > 0.f && ms[0] > 0.f, "phase timing missing");
+    // the pipelined form: two batches in flight, a third refused, collected in submission order
+    {
+      std::vector<tbv_constraint> p0(n_cand), p1(n_cand);
+      int n0 = 0, n1 = 0;
+      EXPECT(tbv_loopdb_submit_sharded(db, n_cand, from.data(), to.data(), Tf.data(), Tt.data(), nullptr, &lp, 0.0) == TBV_OK, "submit 0: %s", tbv_last_error());
+      EXPECT(tbv_loopdb_submit_sharded(db, n_cand / 2, from.data(), to.data(), Tf.data(), Tt.data(), nullptr, &lp, 0.0) == TBV_OK, "submit 1: %s", tbv_last_error());
+      EXPECT(tbv_loopdb_submit_sharded(db, n_cand, from.data(), to.data(), Tf.data(), Tt.data(), nullptr, &lp, 0.0) == TBV_ERR_INVALID, "a third batch in flight was accepted");
+      EXPECT(tbv_loopdb_collect_sharded(db, p0.data(), n_cand, &n0, nullptr) == TBV_OK, "collect 0: %s", tbv_last_error());
+      EXPECT(tbv_loopdb_collect_sharded(db, p1.data(), n_cand, &n1, ms) == TBV_OK, "collect 1: %s", tbv_last_error());
+      EXPECT(n0 == n_ref && std::memcmp(p0.data(), ref.data(), (size_t)n_ref * sizeof(tbv_constraint)) == 0, "pipelined batch 0 differs (%d vs %d)", n0, n_ref);
+      int n_half = 0;
+      for (int i = 0; i < n_ref; i++) n_half += ref[i].candidate < n_cand / 2;
+      EXPECT(n1 == n_half && std::memcmp(p1.data(), ref.data(), (size_t)n_half * sizeof(tbv_constraint)) == 0, "pipelined batch 1 differs (%d vs %d)", n1, n_half);
+      EXPECT(tbv_loopdb_collect_sharded(db, p1.data(), n_cand, &n1, nullptr) == TBV_ERR_INVALID, "collect without a batch in flight");
+    }
     // the low-level export: records left on the device by tbv_loopdb_register_dev, then the exchange
     tbv_constraint* d_rec = nullptr;
     int* d_n = nullptr;

@@ -54,6 +54,20 @@ def test_register_sharded_without_and_with_a_one_rank_communicator(stream8, cell
     got, timing = db.register_sharded(fr, to, Tf, Tt, want_timing=True)
     assert got.tobytes() == ref.tobytes() and len(timing) == 4 and timing[3] >= timing[0] > 0
     assert len(db.register_sharded([], [], np.zeros((0, 3)), np.zeros((0, 3)))) == 0
+    # pipelined form (tbv_loopdb_submit_sharded / _collect_sharded): two batches in flight, collected in order, a third is refused
+    ref5 = db.register_candidates(fr[:5], to[:5], Tf[:5], Tt[:5])
+    for _ in range(3):
+        db.submit_sharded(fr, to, Tf, Tt)
+        db.submit_sharded(fr[:5], to[:5], Tf[:5], Tt[:5])
+        with pytest.raises(api.TbvError):
+            db.submit_sharded(fr, to, Tf, Tt)
+        assert db.collect_sharded().tobytes() == ref.tobytes()
+        db.submit_sharded(fr, to, Tf, Tt)
+        assert db.collect_sharded().tobytes() == ref5.tobytes()
+        got, timing = db.collect_sharded(want_timing=True)
+        assert got.tobytes() == ref.tobytes() and timing[3] >= timing[0] > 0
+    with pytest.raises(api.TbvError):
+        db.collect_sharded()                                                   # nothing in flight
     # low-level export on caller-owned device buffers
     buf = torch.zeros((len(fr), 128), dtype=torch.uint8, device="cuda")
     cnt = torch.zeros((1,), dtype=torch.int32, device="cuda")
@@ -127,7 +141,8 @@ def test_register_sharded_world2_nccl(tmp_path):
     assert len(ref) > 40 * 128
     for k in range(2):
         assert d[k]["single"].tobytes() == ref
-        for key in ("got", "again", "low"):
+        for key in ("got", "again", "low", "pipe0", "pipe2"):
             assert d[k][key].tobytes() == ref, (k, key)
+        assert d[k]["pipe1"].tobytes() == d[k]["small_ref"].tobytes()
         assert d[k]["small"].tobytes() == d[k]["small_ref"].tobytes() and d[k]["lop"].tobytes() == d[k]["lop_ref"].tobytes()
         assert d[k]["timing"][3] > 0

@@ -42,6 +42,20 @@ def main(out_dir, n_cand=96):
     zeros = np.zeros(7, np.int32)                                       # every candidate has from = 0 -> all on rank 0
     lop = db.register_sharded(zeros, to[:7] % 7 + 1, st.gt[zeros] + err[:7], st.gt[to[:7] % 7 + 1])
     lop_ref = db.register_candidates(zeros, to[:7] % 7 + 1, st.gt[zeros] + err[:7], st.gt[to[:7] % 7 + 1])
+    # pipelined form: two batches in flight (different sizes), collected in submission order; a third submit is refused
+    db.submit_sharded(fr, to, Tf, Tt, quality=quality)
+    db.submit_sharded(fr[:5], to[:5], Tf[:5], Tt[:5])
+    try:
+        db.submit_sharded(fr[:5], to[:5], Tf[:5], Tt[:5])
+        refused = False
+    except api.TbvError:
+        refused = True
+    assert refused
+    pipe0 = db.collect_sharded()
+    db.submit_sharded(fr, to, Tf, Tt, quality=quality)                  # slot 0 again while the 5-candidate batch is in flight
+    pipe1 = db.collect_sharded()
+    pipe2, ptiming = db.collect_sharded(want_timing=True)
+    assert ptiming[3] > 0
     # the low-level export: this rank's share packed on the device, then tbv_allgather_constraints
     mine = parallel.shard_candidates(fr, world, rank)
     cap = parallel.shard_capacity(fr, world)
@@ -53,7 +67,8 @@ def main(out_dir, n_cand=96):
     low = ctx.allgather_constraints(buf.data_ptr(), cnt.data_ptr(), cap)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), single=single.view(np.uint8), got=got.view(np.uint8), again=again.view(np.uint8),
              small=small.view(np.uint8), small_ref=db.register_candidates(fr[:5], to[:5], Tf[:5], Tt[:5]).view(np.uint8),
-             lop=lop.view(np.uint8), lop_ref=lop_ref.view(np.uint8), low=low.view(np.uint8), timing=np.array(timing), launches=ctx.launch_count())
+             lop=lop.view(np.uint8), lop_ref=lop_ref.view(np.uint8),
+             pipe0=pipe0.view(np.uint8), pipe1=pipe1.view(np.uint8), pipe2=pipe2.view(np.uint8), low=low.view(np.uint8), timing=np.array(timing), launches=ctx.launch_count())
     dist.barrier()
     ctx.comm_destroy()
     dist.destroy_process_group()
