@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(KF_THREADS, 4)
 k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t row_stride, int z_min, int k, int want_peaks, int rowbuf, int n_groups,
                 const uint8_t* buf_lo, const uint8_t* buf_hi, int min_range_bin, double range_res, const double2* __restrict__ cs_table,
                 const double* __restrict__ th_table, int cap, KfCloud out_f, int* __restrict__ fcount, KfCloud out_p, int* __restrict__ pcount,
-                const double* __restrict__ mot, int ccw, int split, KfCloud tmp_f, KfCloud tmp_p, int2* __restrict__ seg_tot, int* __restrict__ seg_done) {
+                const double* __restrict__ mot, int ccw, int split, KfCloud tmp_f, KfCloud tmp_p, int2* __restrict__ seg_tot, int* __restrict__ seg_done,
+                const KfCloud dst_f, const KfCloud dst_p /* where the rows' points go: the final clouds (split == 1) or the scratch clouds */) {
   extern __shared__ __align__(128) uint8_t s_dyn[];                   // [KF_WARPS][2][rowbuf] staged rows, 
   __shared__ __align__(16) uint32_t s_list[KF_WARPS][2 * CAP + 4];     // candidates of the row pair (unordered, zero-padded to a multiple of 4)
   __shared__ __align__(16) uint32_t s_sel[KF_WARPS][2 * CAP];          // P1: queue of flagged vectors (u16); P2: selected entries, ascending
@@ -329,7 +330,6 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
   if (mot) { m0 = mot[scan * 3 + 0]; m1 = mot[scan * 3 + 1]; m2 = mot[scan * 3 + 2]; }
   const double range_res_half = range_res / 2.0;
   const size_t cbase = (size_t)scan * cap;
-  const KfCloud dst_f = split == 1 ? out_f : tmp_f, dst_p = split == 1 ? out_p : tmp_p;
   const size_t dbase = split == 1 ? cbase : cbase + (size_t)row_lo * (size_t)k;   // a block of R rows emits at most R * k points
   __shared__ int s_last;
   __syncthreads();   // every warp's chain barrier is initialised before a neighbour waits on it
@@ -342,9 +342,12 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
     return ((a | b | c | d) & 0x80808080u) != 0;
   };
 
+  const uint8_t* const row_base = scan_base + (size_t)(row_lo + 2 * warp) * row_stride;
+  const size_t chunk_stride = (size_t)(2 * KF_WARPS) * row_stride;
   for (int row0 = row_lo, chunk = 0; row0 < row_hi; row0 += 2 * KF_WARPS, chunk++) {
     // =============================== P1: the warp's two rows ========================================================================
     const int rowA = row0 + 2 * warp;
+    const uint8_t* const row_ptr = row_base + (size_t)chunk * chunk_stride;   // first row of the warp's pair
     KfRow R[2];
     uint32_t bits[2] = {0u, 0u};
     uint32_t have = 0;
@@ -353,7 +356,7 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
       R[x].buf = bufs + x * rowbuf; R[x].a0 = 0; R[x].nvec = 0;
       if (rowA + x >= row_hi) continue;
       have |= 1u << x;
-      const uint8_t* rp = scan_base + (size_t)(rowA + x) * row_stride;
+      const uint8_t* rp = row_ptr + (size_t)x * row_stride;
       R[x].a0 = (int)(reinterpret_cast<uintptr_t>(rp) & 15u);
       R[x].nvec = (R[x].a0 + n_range + 15) >> 4;
       if (in_flight & (1u << x)) { mbar_wait(&s_bar[warp][x], (parity >> x) & 1u); parity ^= 1u << x; }
@@ -531,7 +534,7 @@ k1_filter_fused(const uint8_t* __restrict__ polar, int n_az, int n_range, size_t
 #pragma unroll
     for (int x = 0; x < 2; x++) {
       const int nrow_next = rowA + 2 * KF_WARPS + x;
-      if (nrow_next < row_hi && stage_row_tma(bufs + x * rowbuf, scan_base + (size_t)nrow_next * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
+      if (nrow_next < row_hi && stage_row_tma(bufs + x * rowbuf, row_ptr + (size_t)(2 * KF_WARPS + x) * row_stride, n_range, buf_lo, buf_hi, &s_bar[warp][x], lane))
         in_flight |= 1u << x;
     }
 
@@ -717,7 +720,8 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
     auto cl = [](DevCloud& c) { return KfCloud{c.x.p, c.y.p, c.inten.p, c.az.p, c.rg.p}; };
     kern<<<batch * split, KF_THREADS, k1_smem, ctx->stream>>>(polar_dev, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf, n_groups, polar_dev, buf_hi,
                                                      min_range_bin, rr, F.cs_table.p, F.th_table.p, n_az * k, cl(F.filtered), F.filtered.count.p, cl(F.peaks),
-                                                     F.peaks.count.p, mot_dev, ccw, split, cl(F.tmp_f), cl(F.tmp_p), F.seg_tot.p, F.seg_done.p);
+                                                     F.peaks.count.p, mot_dev, ccw, split, cl(F.tmp_f), cl(F.tmp_p), F.seg_tot.p, F.seg_done.p,
+                                                     split == 1 ? cl(F.filtered) : cl(F.tmp_f), split == 1 ? cl(F.peaks) : cl(F.tmp_p));
     return TBV_OK;
   };
   // compile-time variants: byte-compare form (z_min > 128), unrolled scan for the two dataset shapes, list capacity 64 (k <= 64) or 128

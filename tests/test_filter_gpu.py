@@ -66,6 +66,21 @@ def test_zero_threshold_rows_shorter_and_longer_than_the_list(ctx, oracle, shape
     _check_scan(ctx, oracle, np.zeros(shape, np.uint8), z_min=0.0, k_strongest=k, min_distance=0.0)
 
 
+@pytest.mark.parametrize("n_real", [0, 5, 12, 13, 300])
+def test_high_threshold_rows_flagged_everywhere_but_holding_few_candidates(ctx, oracle, n_real):
+    """z_min > 128: the conservative vector test flags every byte >= 128, so rows full of values in [128, z_min) overflow the queue of
+    flagged vectors and take the dense path although they hold fewer than k real candidates (count(>= z_min) < k at the start of the
+    threshold search) — or exactly k, or more."""
+    rng = np.random.default_rng(100 + n_real)
+    img = rng.integers(130, 200, size=(6, 3768), dtype=np.uint8)
+    for b in range(6):
+        at = rng.choice(3768, n_real, replace=False)
+        img[b, at] = rng.integers(200, 256, n_real)
+    img[5, :] = 199                                          # all-equal row just below the threshold
+    _check_scan(ctx, oracle, img, z_min=200.0, k_strongest=12, min_distance=0.0)
+    _check_scan(ctx, oracle, img, z_min=200.0, k_strongest=40, min_distance=0.0)
+
+
 def test_edge_bins_and_row_crossing(ctx, oracle):
     """Kept bins within 6 of either row end: NMS reads across the row edge (flat cv::Mat indexing)."""
     img = np.full((6, 128), 20, np.uint8)
