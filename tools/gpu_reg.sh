@@ -22,5 +22,5 @@ PY
 tail -3 gpurun_out/bench_reg.err
 if [ "${NCU:-0}" = "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_register -s 6 -c 1 -f -o gpurun_out/full_k_register \
-     python bench.py --no-cpu-baseline --no-extra-legs --steps 3 --warmup 3 > gpurun_out/ncu_full_k_register.log 2>&1; echo "ncu rc=$?"
+     python bench.py --no-cpu-baseline --no-extra-legs --steps 2 --warmup 5 > gpurun_out/ncu_full_k_register.log 2>&1; echo "ncu rc=$?"
 fi
