@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences in the cpu_baseline sample (0: sized for ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the loop_batch and mulran legs (profiling runs)")
+    ap.add_argument("--no-overlap", action="store_true", help="single-stream steps with the compensation fused into the filter kernel (tbv_odom_set_overlap off)")
     return ap.parse_args()
 
 
@@ -224,6 +225,8 @@ def algorithmic_bytes(kernel: str, n_seq: int, st: dict) -> float | None:
         # fused filter kernel: scan bytes in, the two clouds out (x,y f32, I u8, az,rg u16 = 13 B/pt; peaks ~ a third of the points)
         "k1_filter_fused": SCAN_BYTES + 13 * npts * 1.33,
         "k_compensate": 2 * 8 * npts,
+        # compensation of an overlapped step: x, y, azimuth in, x, y out, both clouds
+        "k_compensate_polar": 18 * npts * 1.33,
         # fused cells kernel: points (x,y f32 + I u8) in, one 16-double record per valid cell out (all tables in shared memory)
         "cells_fused": 9 * npts + 128 * ncell,
         # legacy multi-kernel cells path (fine voxel grids only)
@@ -365,6 +368,7 @@ def run_mulran_leg(api, parallel, torch, ctx, sets, gt_kf, world, rank, local, b
     torch.cuda.synchronize()
     fuser = api.OdometryKeyframeFuser(ctx, S, N_AZ, MU_N_RANGE, mulran_params(api))
     fuser.set_wire_layout(True)
+    fuser.set_overlap(OVERLAP)
     stream = torch.cuda.ExternalStream(ctx.stream)
     # ---- odometry alone, scans resident in HBM ------------------------------------------------------------------------------------------
     for t in range(W):
@@ -446,7 +450,12 @@ def run_mulran_leg(api, parallel, torch, ctx, sets, gt_kf, world, rank, local, b
     return out
 
 
+OVERLAP = True   # set from --no-overlap in run_ours
+
+
 def run_ours(args):
+    global OVERLAP
+    OVERLAP = not args.no_overlap
     import torch
     import torch.distributed as dist
     from tbv_slam_public_b200 import api, parallel, statistics
@@ -469,6 +478,7 @@ def run_ours(args):
     ctx = api.Context(local)
     par = api.default_odom_params()
     fuser = api.OdometryKeyframeFuser(ctx, S, N_AZ, N_RANGE, par)
+    fuser.set_overlap(OVERLAP)   # the filter of step t + 1 on a second stream under the registration of step t (scans are resident / uploaded)
     stream = torch.cuda.ExternalStream(ctx.stream)
 
     # host side: the scans of the steps the e2e leg replays, in pinned memory (what a sensor-facing producer would hand over).
@@ -683,7 +693,10 @@ def run_ours(args):
         "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 scan bytes -> f32 points -> f64 cells / normal equations / LM", "data": "synthetic",
         "config": bench_config(),
-        "run": {"sequences_per_gpu": S, "scans_per_step": S * world, "gpus": world},
+        "run": {"sequences_per_gpu": S, "scans_per_step": S * world, "gpus": world,
+                "step_overlap": ("filter of step t+1 on a second stream under the registration of step t, compensation as its own launch (tbv_odom_set_overlap); "
+                                 "per-kernel times come from a serialised pass, so their sum exceeds ms_per_step") if OVERLAP else
+                                "off: single-stream steps, compensation fused into the filter kernel"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": S * 80,
                 "ms_per_step": round(e2e_s / K_e2e * 1e3, 4), "steps": K_e2e, "api": "tbv_odom_submit/tbv_odom_collect (pinned host scans, double-buffered)",
                 "h2d_gbs_per_gpu": h2d_gbs, "host_placement": numa,

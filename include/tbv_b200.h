@@ -230,6 +230,13 @@ int tbv_odom_step(tbv_odom* od, const uint8_t* polar_host, tbv_odom_out* out);
  * [n_range][n_az] (MulRan and every non-Oxford dataset: radar_driver.cpp:74-90) and is rotated 90 deg CCW on the device as the
  * first launch of the step — cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on receipt.  Default 0: azimuth-major [n_az][n_range] (Oxford). */
 int tbv_odom_set_wire_layout(tbv_odom* od, int range_major);
+/* enable != 0: overlapped steps for large batches.  The filter of a step (rotate on receipt + k-strongest + NMS + polar -> Cartesian)
+ * depends on nothing but the step's scans, so it is launched on a second, low-priority stream into a second set of clouds and runs while
+ * the registration of the PREVIOUS step drains; the motion compensation (which needs the previous step's pose) becomes its own small
+ * launch on the context's stream — same arithmetic on the same floats, identical results.  Steps are not replayed from CUDA graphs in
+ * this mode.  Contract for tbv_odom_step_dev: the scans handed over must be COMPLETE in device memory when the call is made (not merely
+ * enqueued on the context's stream); tbv_odom_submit orders its own uploads.  Default 0. */
+int tbv_odom_set_overlap(tbv_odom* od, int enable);
 /* The step (7 kernel launches) is replayed from a CUDA graph once an input buffer has been seen twice — the upload buffers of
  * tbv_odom_step / _submit, or a caller's own ring of device buffers passed to tbv_odom_step_dev.  enable = 0 turns that off (direct
  * launches); default on.  Results are identical either way. */

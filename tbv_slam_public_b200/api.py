@@ -139,6 +139,7 @@ _OPTIONAL = [
     ("tbv_odom_reset", [C.c_void_p], None),
     ("tbv_odom_set_wire_layout", [C.c_void_p, C.c_int], None),
     ("tbv_odom_set_graphs", [C.c_void_p, C.c_int], None),
+    ("tbv_odom_set_overlap", [C.c_void_p, C.c_int], None),
     ("tbv_odom_step", [C.c_void_p, C.c_void_p, C.c_void_p], None),
     ("tbv_odom_step_dev", [C.c_void_p, C.c_void_p], None),
     ("tbv_odom_fetch", [C.c_void_p, C.c_void_p], None),
@@ -552,6 +553,11 @@ class OdometryKeyframeFuser:
     def set_graphs(self, enable: bool):
         """CUDA-graph replay of the step for input buffers seen before (default on)."""
         _check(lib().tbv_odom_set_graphs(self.h, int(bool(enable))))
+
+    def set_overlap(self, enable: bool):
+        """Overlapped steps for large batches: the filter of a step runs on a second stream under the registration of the previous step
+        (identical results; scans given to step_dev must be complete in device memory when the call is made)."""
+        _check(lib().tbv_odom_set_overlap(self.h, int(bool(enable))))
 
     def set_wire_layout(self, range_major: bool):
         """True: scans arrive [n_range][n_az] (MulRan wire layout) and are rotated 90 deg CCW on the device on receipt (radar_driver.cpp:80-84)."""

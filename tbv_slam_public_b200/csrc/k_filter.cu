@@ -674,7 +674,8 @@ int ensure_cs_table(tbv_ctx* ctx, int n_az) {
 }
 
 int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
-                          const tbv_filter_params* p, int want_peaks, const double* mot_dev, int ccw) {
+                          const tbv_filter_params* p, int want_peaks, const double* mot_dev, int ccw, cudaStream_t stream) {
+  cudaStream_t st = stream ? stream : ctx->stream;
   TBV_REQUIRE(ctx && polar_dev && p, "null pointer");
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
   TBV_REQUIRE(n_range <= 8192, "n_range > 8192 is not supported");
@@ -708,7 +709,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
     if ((rc = F.seg_tot.reserve((size_t)batch * split))) return rc;
     if (F.seg_done.n < (size_t)batch) {
       if ((rc = F.seg_done.reserve(batch))) return rc;
-      TBV_CUDA(cudaMemsetAsync(F.seg_done.p, 0, F.seg_done.n * sizeof(int), ctx->stream));   // the kernel leaves the counters at zero
+      TBV_CUDA(cudaMemsetAsync(F.seg_done.p, 0, F.seg_done.n * sizeof(int), st));   // the kernel leaves the counters at zero
     }
   }
   const uint8_t* buf_hi = polar_dev + (size_t)(batch - 1) * n_az * row_stride + (size_t)(n_az - 1) * row_stride + (size_t)n_range;
@@ -718,7 +719,7 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
     const int rc2 = ensure_dyn_smem(ctx, kern, k1_smem);
     if (rc2) return rc2;
     auto cl = [](DevCloud& c) { return KfCloud{c.x.p, c.y.p, c.inten.p, c.az.p, c.rg.p}; };
-    kern<<<batch * split, KF_THREADS, k1_smem, ctx->stream>>>(polar_dev, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf, n_groups, polar_dev, buf_hi,
+    kern<<<batch * split, KF_THREADS, k1_smem, st>>>(polar_dev, n_az, n_range, row_stride, z_min, k, want_peaks, rowbuf, n_groups, polar_dev, buf_hi,
                                                      min_range_bin, rr, F.cs_table.p, F.th_table.p, n_az * k, cl(F.filtered), F.filtered.count.p, cl(F.peaks),
                                                      F.peaks.count.p, mot_dev, ccw, split, cl(F.tmp_f), cl(F.tmp_p), F.seg_tot.p, F.seg_done.p,
                                                      split == 1 ? cl(F.filtered) : cl(F.tmp_f), split == 1 ? cl(F.peaks) : cl(F.tmp_p));
@@ -733,6 +734,37 @@ int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int 
   rc = z_min > 128 ? pick(std::true_type{}) : pick(std::false_type{});
   if (rc) return rc;
   launched(ctx, "k1_filter_fused");
+  TBV_CUDA(cudaGetLastError());
+  return TBV_OK;
+}
+
+// The fused filter's compensation as a separate launch: one thread per point of both clouds; (cos, sin, theta) of the point's azimuth from
+// the host tables, i.e. the very operations of compensate_polar_point on the very floats the filter stored.
+__global__ void __launch_bounds__(256)
+k_compensate_polar(KfCloud cf, const int* __restrict__ fcount, KfCloud cp, const int* __restrict__ pcount, int cap, const double2* __restrict__ cs_table,
+                   const double* __restrict__ th_table, const double* __restrict__ mot, int ccw) {
+  const int scan = blockIdx.y;
+  const KfCloud c = blockIdx.z ? cp : cf;
+  const int n = min((blockIdx.z ? pcount : fcount)[scan], cap);
+  const double m0 = mot[scan * 3 + 0], m1 = mot[scan * 3 + 1], m2 = mot[scan * 3 + 2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t q = (size_t)scan * cap + i;
+    float x = c.x[q], y = c.y[q];
+    const int az = c.az[q];
+    const double2 cs = cs_table[az];
+    compensate_polar_point(x, y, cs.x, cs.y, th_table[az], m0, m1, m2, ccw);
+    c.x[q] = x; c.y[q] = y;
+  }
+}
+
+int compensate_polar_clouds_dev(tbv_ctx* ctx, const double* mot_dev, int ccw, int want_peaks) {
+  FilterState& F = ctx->filt;
+  TBV_REQUIRE(F.batch > 0 && mot_dev, "no filter result on the device");
+  auto cl = [](DevCloud& c) { return KfCloud{c.x.p, c.y.p, c.inten.p, c.az.p, c.rg.p}; };
+  dim3 grid(8, F.batch, want_peaks ? 2 : 1);
+  k_compensate_polar<<<grid, 256, 0, ctx->stream>>>(cl(F.filtered), F.filtered.count.p, cl(F.peaks), F.peaks.count.p, F.filtered.cap, F.cs_table.p, F.th_table.p,
+                                                    mot_dev, ccw);
+  launched(ctx, "k_compensate_polar");
   TBV_CUDA(cudaGetLastError());
   return TBV_OK;
 }

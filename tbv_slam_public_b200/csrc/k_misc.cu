@@ -69,16 +69,17 @@ __global__ void __launch_bounds__(256) k_rotate90ccw_v4(const uint8_t* __restric
   }
 }
 
-int rotate90ccw_dev(tbv_ctx* ctx, const uint8_t* src_dev, int rows, int cols, int batch, uint8_t* dst_dev) {
+int rotate90ccw_dev(tbv_ctx* ctx, const uint8_t* src_dev, int rows, int cols, int batch, uint8_t* dst_dev, cudaStream_t stream) {
+  cudaStream_t st = stream ? stream : ctx->stream;
   const bool v4 = rows % 4 == 0 && cols % 4 == 0 && ((reinterpret_cast<uintptr_t>(src_dev) | reinterpret_cast<uintptr_t>(dst_dev)) & 3u) == 0;
   for (int b0 = 0; b0 < batch; b0 += 65535) {   // gridDim.z limit
     const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
     const uint8_t* s = src_dev + (size_t)b0 * rows * cols;
     uint8_t* d = dst_dev + (size_t)b0 * rows * cols;
     if (v4) {
-      k_rotate90ccw_v4<<<dim3((cols + 63) / 64, (rows + 63) / 64, nb), 256, 0, ctx->stream>>>(s, rows, cols, d);
+      k_rotate90ccw_v4<<<dim3((cols + 63) / 64, (rows + 63) / 64, nb), 256, 0, st>>>(s, rows, cols, d);
     } else {
-      k_rotate90ccw<<<dim3((cols + 31) / 32, (rows + 31) / 32, nb), dim3(32, 8), 0, ctx->stream>>>(s, rows, cols, d);
+      k_rotate90ccw<<<dim3((cols + 31) / 32, (rows + 31) / 32, nb), dim3(32, 8), 0, st>>>(s, rows, cols, d);
     }
     launched(ctx, "k_rotate90ccw");
   }
@@ -115,7 +116,11 @@ tbv_ctx* tbv_create(int device) {
   if (ctx->sm_count <= 0) ctx->sm_count = 148;
   cudaDeviceGetAttribute(&ctx->smem_optin_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (ctx->smem_optin_max <= 0) ctx->smem_optin_max = 232448;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // the context's stream takes the highest priority: side streams of the library (the filter stream of an overlapped odometry step) fill
+  // the gaps its kernels leave instead of competing with them
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
     delete ctx;
     return nullptr;

@@ -230,6 +230,17 @@ struct tbv_odom {
   int use_graphs = 1, steps_done = 0;
   int wire_range_major = 0;        // scans arrive [n_range][n_az] (MulRan wire layout) and are rotated on receipt (tbv_odom_set_wire_layout)
   DevBuf<uint8_t> rotated;         // [n_seq][n_az][n_range] azimuth-major copies of the step's scans
+  // Overlapped steps (tbv_odom_set_overlap): the filter of step t + 1 does not depend on step t (only its compensation does), so it runs
+  // on a second, low-priority stream into a second set of clouds and fills the SMs the registration of step t leaves idle as its CTAs
+  // retire; the compensation is then its own small launch on the context's stream (same arithmetic, same bits).
+  int overlap = 0, parity = 0;
+  cudaStream_t filter_stream = nullptr;
+  DevCloud alt_f, alt_p;                                  // the clouds the context's filter state does NOT point at right now
+  cudaEvent_t ev_filtered[2] = {nullptr, nullptr};        // [parity] the filter of the step has written its clouds
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};            // [parity] the step that used these clouds has read them for the last time
+  bool free_valid[2] = {false, false};
+  cudaEvent_t input_ready = nullptr;                      // set by tbv_odom_submit for the step being enqueued: its scans are uploaded
+  cudaStream_t input_consumer = nullptr;                  // the stream on which that step read its scans (for the upload ring's reuse event)
 };
 
 static void odom_free(tbv_odom* od) {
@@ -237,6 +248,12 @@ static void odom_free(tbv_odom* od) {
   cudaSetDevice(od->ctx->device);
   cudaStreamSynchronize(od->ctx->stream);
   if (od->copy_stream) cudaStreamSynchronize(od->copy_stream);
+  if (od->filter_stream) { cudaStreamSynchronize(od->filter_stream); cudaStreamDestroy(od->filter_stream); }
+  for (int i = 0; i < 2; i++) {
+    if (od->ev_filtered[i]) cudaEventDestroy(od->ev_filtered[i]);
+    if (od->ev_free[i]) cudaEventDestroy(od->ev_free[i]);
+  }
+  od->alt_f.release(); od->alt_p.release();
   od->state.release(); od->mot.release(); od->fixed_pose.release(); od->problems.release(); od->fixed_set.release();
   od->rotated.release();
   for (auto& g : od->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
@@ -287,6 +304,37 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   cudaStream_t st = ctx->stream;
   // previous frame-to-frame motion first: K2 compensates the points as it emits them (odometrykeyframefuser.cpp:146-150)
   int rc;
+  od->input_consumer = st;
+  if (od->overlap) {
+    // ---- the filter on its own stream, into the other set of clouds; nothing in it depends on the previous step --------------------------
+    FilterState& Fs = ctx->filt;
+    std::swap(Fs.filtered, od->alt_f); std::swap(Fs.peaks, od->alt_p);
+    const int pr = od->parity; od->parity ^= 1;
+    cudaStream_t fs = ctx->prof.on ? st : od->filter_stream;   // a profile is taken with every launch on the context's stream
+    od->input_consumer = fs;
+    if (fs != st) {
+      if (od->free_valid[pr]) TBV_CUDA(cudaStreamWaitEvent(fs, od->ev_free[pr], 0));        // step t - 2 has read these clouds for the last time
+      if (od->input_ready) TBV_CUDA(cudaStreamWaitEvent(fs, od->input_ready, 0));           // host-input pipeline: the scans are uploaded
+    } else if (od->input_ready) {
+      TBV_CUDA(cudaStreamWaitEvent(st, od->input_ready, 0));
+    }
+    if (od->wire_range_major) {   // radar_driver.cpp:80-84: cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on receipt
+      if ((rc = od->rotated.reserve((size_t)n_seq * od->n_az * od->n_range))) return rc;
+      if ((rc = rotate90ccw_dev(ctx, polar_dev, od->n_range, od->n_az, n_seq, od->rotated.p, fs))) return rc;
+      polar_dev = od->rotated.p;
+    }
+    if ((rc = filter_kstrongest_dev(ctx, polar_dev, od->n_az, od->n_range, (size_t)od->n_range, n_seq, &od->par.filter, 1, nullptr, od->par.radar_ccw, fs)))
+      return rc;
+    if (fs != st) {
+      TBV_CUDA(cudaEventRecord(od->ev_filtered[pr], fs));
+      TBV_CUDA(cudaStreamWaitEvent(st, od->ev_filtered[pr], 0));
+    }
+    if (od->par.compensate) {   // previous frame-to-frame motion (odometrykeyframefuser.cpp:146-150), then the compensation of both clouds
+      k_odom_motion<<<(n_seq + 127) / 128, 128, 0, st>>>(od->state.p, n_seq, od->mot.p);
+      launched(ctx, "k_odom_motion");
+      if ((rc = compensate_polar_clouds_dev(ctx, od->mot.p, od->par.radar_ccw, 1))) return rc;
+    }
+  } else {
   if (od->wire_range_major) {   // radar_driver.cpp:80-84: cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on receipt
     if ((rc = od->rotated.reserve((size_t)n_seq * od->n_az * od->n_range))) return rc;
     if ((rc = rotate90ccw_dev(ctx, polar_dev, od->n_range, od->n_az, n_seq, od->rotated.p))) return rc;
@@ -299,6 +347,7 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
   if ((rc = filter_kstrongest_dev(ctx, polar_dev, od->n_az, od->n_range, (size_t)od->n_range, n_seq, &od->par.filter, 1,
                                   od->par.compensate ? od->mot.p : nullptr, od->par.radar_ccw)))
     return rc;
+  }
   FilterState& F = ctx->filt;
   if ((rc = cells_build_dev(ctx, F.filtered.x.p, F.filtered.y.p, F.filtered.inten.p, nullptr, F.filtered.count.p, F.filtered.cap, n_seq, od->cpar,
                             od->cell_cap, od->cur)))
@@ -312,6 +361,11 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
                                        od->kf.f64.p, od->kf.count.p, cells_err_dev(ctx), od->cur.n_samples.p, od->outs_dev.p, od->fused_set.p);
   launched(ctx, "k_odom_update");
   TBV_CUDA(cudaGetLastError());
+  if (od->overlap) {   // the step's clouds have been read for the last time (cells: points, update: counts)
+    const int pr = od->parity ^ 1;
+    TBV_CUDA(cudaEventRecord(od->ev_free[pr], st));
+    od->free_valid[pr] = true;
+  }
   // new keyframes get their search grid now (used by the registrations of the following frames)
   return cellgrid_build_launch(ctx, od->views.p, od->fused_set.p, n_seq, n_seq * (od->K + 1), od->cell_cap, od->cpar.max_extent);
 }
@@ -331,7 +385,9 @@ static uint64_t step_fingerprint(tbv_odom* od) {   // every context-level buffer
 
 static int odom_enqueue_graphed(tbv_odom* od, const uint8_t* polar_dev) {
   tbv_ctx* ctx = od->ctx;
-  if (!od->use_graphs || ctx->prof.on || od->steps_done < 1) {   // the first step allocates and sets kernel attributes: never captured
+  od->input_consumer = ctx->stream;
+  if (!od->use_graphs || od->overlap || ctx->prof.on || od->steps_done < 1) {   // the first step allocates and sets kernel attributes: never captured;
+                                                                                 // an overlapped step spans two streams that must not be joined per step
     od->steps_done++;
     return odom_enqueue(od, polar_dev);
   }
@@ -415,6 +471,8 @@ int tbv_odom_reset(tbv_odom* od) {
   cudaSetDevice(ctx->device);
   TBV_CUDA(cudaStreamSynchronize(ctx->stream));
   if (od->copy_stream) TBV_CUDA(cudaStreamSynchronize(od->copy_stream));
+  if (od->filter_stream) TBV_CUDA(cudaStreamSynchronize(od->filter_stream));
+  od->free_valid[0] = od->free_valid[1] = false;
   od->n_submitted = od->n_collected = 0;
   TBV_CUDA(cudaMemsetAsync(od->kf.count.p, 0, (size_t)od->n_seq * od->K * sizeof(int), ctx->stream));
   k_odom_reset<<<(od->n_seq + 127) / 128, 128, 0, ctx->stream>>>(od->state.p, od->n_seq);
@@ -427,6 +485,26 @@ int tbv_odom_reset(tbv_odom* od) {
 int tbv_odom_set_graphs(tbv_odom* od, int enable) {
   TBV_REQUIRE(od, "null handle");
   od->use_graphs = enable != 0;
+  return TBV_OK;
+}
+
+int tbv_odom_set_overlap(tbv_odom* od, int enable) {
+  TBV_ENTER(od ? od->ctx : nullptr);
+  TBV_REQUIRE(od, "null handle");
+  tbv_ctx* ctx = od->ctx;
+  TBV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (od->filter_stream) TBV_CUDA(cudaStreamSynchronize(od->filter_stream));
+  if (enable && !od->filter_stream) {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    TBV_CUDA(cudaStreamCreateWithPriority(&od->filter_stream, cudaStreamNonBlocking, least));
+    for (int i = 0; i < 2; i++) {
+      TBV_CUDA(cudaEventCreateWithFlags(&od->ev_filtered[i], cudaEventDisableTiming));
+      TBV_CUDA(cudaEventCreateWithFlags(&od->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  od->free_valid[0] = od->free_valid[1] = false;
+  od->overlap = enable != 0;
   return TBV_OK;
 }
 
@@ -481,10 +559,12 @@ int tbv_odom_submit(tbv_odom* od, const uint8_t* polar_host) {
   if (od->n_submitted >= 2) TBV_CUDA(cudaStreamWaitEvent(od->copy_stream, od->consumed[b], 0));
   TBV_CUDA(cudaMemcpyAsync(od->polar[b].p, polar_host, bytes, cudaMemcpyHostToDevice, od->copy_stream));
   TBV_CUDA(cudaEventRecord(od->uploaded[b], od->copy_stream));
-  TBV_CUDA(cudaStreamWaitEvent(od->ctx->stream, od->uploaded[b], 0));
+  if (od->overlap) od->input_ready = od->uploaded[b];   // awaited by the stream that reads the scans (the filter stream of an overlapped step)
+  else TBV_CUDA(cudaStreamWaitEvent(od->ctx->stream, od->uploaded[b], 0));
   rc = odom_enqueue_graphed(od, od->polar[b].p);
+  od->input_ready = nullptr;
   if (rc) return rc;
-  TBV_CUDA(cudaEventRecord(od->consumed[b], od->ctx->stream));
+  TBV_CUDA(cudaEventRecord(od->consumed[b], od->input_consumer));
   TBV_CUDA(cudaMemcpyAsync(od->outs_host[b], od->outs_dev.p, (size_t)od->n_seq * sizeof(tbv_odom_out), cudaMemcpyDeviceToHost, od->ctx->stream));
   TBV_CUDA(cudaEventRecord(od->done[b], od->ctx->stream));
   od->n_submitted++;

@@ -174,10 +174,13 @@ inline void launched(tbv_ctx* ctx, const char* name) {  // bookkeeping after eve
 }
 // implemented in k_filter.cu
 // mot_dev != nullptr ([batch][3] previous frame-to-frame motion): both clouds are motion-compensated as they are emitted
+// stream != nullptr: the kernel is launched there instead of on the context's stream (the caller orders it)
 int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
-                          const tbv_filter_params* params, int want_peaks, const double* mot_dev = nullptr, int ccw = 0);
+                          const tbv_filter_params* params, int want_peaks, const double* mot_dev = nullptr, int ccw = 0, cudaStream_t stream = nullptr);
+// the compensation of the fused filter as its own launch (same arithmetic, same bits): both clouds of the last filter call, in place
+int compensate_polar_clouds_dev(tbv_ctx* ctx, const double* mot_dev /*[batch][3]*/, int ccw, int want_peaks);
 // batched cv::rotate(ROTATE_90_COUNTERCLOCKWISE) on the device (k_misc.cu): src [batch][rows][cols] -> dst [batch][cols][rows]
-int rotate90ccw_dev(tbv_ctx* ctx, const uint8_t* src_dev, int rows, int cols, int batch, uint8_t* dst_dev);
+int rotate90ccw_dev(tbv_ctx* ctx, const uint8_t* src_dev, int rows, int cols, int batch, uint8_t* dst_dev, cudaStream_t stream = nullptr);
 int compensate_clouds_dev(tbv_ctx* ctx, DevCloud& cloud, const double* mot_dev /*[batch][3]*/, int ccw);
 // Hash of the device pointers of a context's grow-on-demand scratch (they move when another caller on the same context asks for more):
 // a captured graph of the odometry step is valid only while these are what they were at capture time.

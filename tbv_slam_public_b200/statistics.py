@@ -11,7 +11,7 @@ from __future__ import annotations
 # kernel -> the reference's timing key (radar_driver.cpp:87,111; odometrykeyframefuser.cpp:253-256; loopclosure.cpp:647-731; posegraph.cpp:126)
 STAGE_OF_KERNEL = {
     "k1_filter_fused": "Filtering", "cfar_rows": "Filtering", "cfar_emit": "Filtering", "k_rotate90ccw": "Filtering",
-    "k_compensate": "compensate",
+    "k_compensate": "compensate", "k_compensate_polar": "compensate",
     "cells_fused": "build_normals", "c1_grid": "build_normals", "c2_scan": "build_normals", "c3_scatter": "build_normals", "c4_centroids": "build_normals",
     "c5_cells": "build_normals", "c6_compact": "build_normals",
     "k_register": "register", "k_odom_problems": "register",

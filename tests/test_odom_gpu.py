@@ -168,6 +168,58 @@ def test_pipelined_submit_collect_matches_sync(ctx):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("wire", [False, True])
+def test_overlapped_steps_change_nothing(ctx, wire):
+    """tbv_odom_set_overlap: the filter of a step on a second stream (into a second set of clouds) under the previous step's registration,
+    compensation as its own launch — poses, counts and keyframe decisions bit for bit those of the fused single-stream step, through the
+    device-input call, the host-input pipeline and with the rotate-on-receipt wire layout; the step's clouds stay fetchable."""
+    import torch
+    st = synth.make_stream(8)
+    n_seq, n_az, n_range = 3, 400, 3768
+    p = api.default_odom_params()
+    frames = [np.stack([st.scans[(f + s) % 8] for s in range(n_seq)]) for f in range(8)]
+    if wire:
+        frames = [np.ascontiguousarray(np.rot90(b, -1, axes=(1, 2))) for b in frames]     # [n_range][n_az] per scan, as the driver receives them
+    dev = [torch.from_numpy(b.reshape(-1)).cuda() for b in frames]
+    torch.cuda.synchronize()
+
+    def run(overlap, host):
+        fu = api.OdometryKeyframeFuser(ctx, n_seq, n_az, n_range, p)
+        fu.set_wire_layout(wire)
+        fu.set_overlap(overlap)
+        outs = []
+        if host:
+            bufs = [api.PinnedBuffer(n_seq * n_az * n_range) for _ in range(2)]
+            for f in range(8):
+                bufs[f & 1].array[:] = frames[f].reshape(-1)
+                fu.submit(bufs[f & 1].ptr)
+                if f >= 1:
+                    outs.append(fu.collect())
+            outs.append(fu.collect())
+            rec = [[(o.n_points, o.n_cells, o.itrs, o.is_keyframe) for o in out] for out in outs]
+            poses = [api.poses(out).copy() for out in outs]
+        else:
+            rec, poses = [], []
+            for f in range(8):
+                fu.step_dev(dev[f].data_ptr())
+                out = fu.fetch()
+                rec.append([(o.n_points, o.n_cells, o.itrs, o.is_keyframe) for o in out])
+                poses.append(api.poses(out).copy())
+        filt, _ = ctx.filter_fetch(n_seq, n_az, p.filter.k_strongest)      # the last step's (compensated) clouds
+        fu.close()
+        return rec, poses, filt
+
+    ref_rec, ref_poses, ref_filt = run(False, False)
+    for overlap, host in ((True, False), (True, True), (False, True)):
+        rec, poses, filt = run(overlap, host)
+        assert rec == ref_rec, (overlap, host)
+        for a, b in zip(poses, ref_poses):
+            assert np.array_equal(a, b), (overlap, host)
+        for b in range(n_seq):
+            for x, y in zip(filt.scan(b), ref_filt.scan(b)):
+                assert np.array_equal(x, y), (overlap, host, b)
+
+
 def test_cuda_graph_replay_of_the_step_changes_nothing(ctx, stream8):
     """The step is replayed from a CUDA graph once an input buffer has been seen twice (tbv_odom_set_graphs, default on): same poses, counts
     and keyframe decisions, bit for bit, as direct launches — also after another fuser on the same context has grown the context's scratch
