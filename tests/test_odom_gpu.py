@@ -187,24 +187,24 @@ def test_overlapped_steps_change_nothing(ctx, wire):
         fu = api.OdometryKeyframeFuser(ctx, n_seq, n_az, n_range, p)
         fu.set_wire_layout(wire)
         fu.set_overlap(overlap)
-        outs = []
+        rec, poses = [], []
+
+        def take(out):   # the fuser hands out the same record array every time: copy what is compared
+            rec.append([(o.n_points, o.n_cells, o.itrs, o.is_keyframe) for o in out])
+            poses.append(api.poses(out).copy())
+
         if host:
             bufs = [api.PinnedBuffer(n_seq * n_az * n_range) for _ in range(2)]
             for f in range(8):
                 bufs[f & 1].array[:] = frames[f].reshape(-1)
                 fu.submit(bufs[f & 1].ptr)
                 if f >= 1:
-                    outs.append(fu.collect())
-            outs.append(fu.collect())
-            rec = [[(o.n_points, o.n_cells, o.itrs, o.is_keyframe) for o in out] for out in outs]
-            poses = [api.poses(out).copy() for out in outs]
+                    take(fu.collect())
+            take(fu.collect())
         else:
-            rec, poses = [], []
             for f in range(8):
                 fu.step_dev(dev[f].data_ptr())
-                out = fu.fetch()
-                rec.append([(o.n_points, o.n_cells, o.itrs, o.is_keyframe) for o in out])
-                poses.append(api.poses(out).copy())
+                take(fu.fetch())
         filt, _ = ctx.filter_fetch(n_seq, n_az, p.filter.k_strongest)      # the last step's (compensated) clouds
         fu.close()
         return rec, poses, filt
