@@ -675,8 +675,9 @@ int ensure_cs_table(tbv_ctx* ctx, int n_az) {
 
 int filter_kstrongest_dev(tbv_ctx* ctx, const uint8_t* polar_dev, int n_az, int n_range, size_t row_stride, int batch,
                           const tbv_filter_params* p, int want_peaks, const double* mot_dev, int ccw, cudaStream_t stream) {
-  cudaStream_t st = stream ? stream : ctx->stream;
   TBV_REQUIRE(ctx && polar_dev && p, "null pointer");
+  cudaStream_t st = stream ? stream : ctx->stream;
+  if (!stream) ctx->filt_epoch++;   // an ordinary user of the context's clouds (an overlapped odometry step orders itself against these)
   TBV_REQUIRE(n_az > 0 && n_range > 0 && batch > 0 && row_stride >= (size_t)n_range, "bad image shape");
   TBV_REQUIRE(n_range <= 8192, "n_range > 8192 is not supported");
   TBV_REQUIRE(n_az <= 4096, "n_az > 4096 is not supported");

@@ -239,6 +239,8 @@ struct tbv_odom {
   cudaEvent_t ev_filtered[2] = {nullptr, nullptr};        // [parity] the filter of the step has written its clouds
   cudaEvent_t ev_free[2] = {nullptr, nullptr};            // [parity] the step that used these clouds has read them for the last time
   bool free_valid[2] = {false, false};
+  cudaEvent_t ev_sync = nullptr;                          // orders the filter stream behind other users of the context's clouds
+  unsigned long long seen_epoch = 0;                      // ctx->filt_epoch at this fuser's last step
   cudaEvent_t input_ready = nullptr;                      // set by tbv_odom_submit for the step being enqueued: its scans are uploaded
   cudaStream_t input_consumer = nullptr;                  // the stream on which that step read its scans (for the upload ring's reuse event)
 };
@@ -253,6 +255,7 @@ static void odom_free(tbv_odom* od) {
     if (od->ev_filtered[i]) cudaEventDestroy(od->ev_filtered[i]);
     if (od->ev_free[i]) cudaEventDestroy(od->ev_free[i]);
   }
+  if (od->ev_sync) cudaEventDestroy(od->ev_sync);
   od->alt_f.release(); od->alt_p.release();
   od->state.release(); od->mot.release(); od->fixed_pose.release(); od->problems.release(); od->fixed_set.release();
   od->rotated.release();
@@ -313,6 +316,11 @@ static int odom_enqueue(tbv_odom* od, const uint8_t* polar_dev) {
     cudaStream_t fs = ctx->prof.on ? st : od->filter_stream;   // a profile is taken with every launch on the context's stream
     od->input_consumer = fs;
     if (fs != st) {
+      if (ctx->filt_epoch != od->seen_epoch) {   // somebody else filtered on this context since the last step: its clouds are one of the two sets
+        TBV_CUDA(cudaEventRecord(od->ev_sync, st));                                          // this step is about to overwrite — wait for whatever
+        TBV_CUDA(cudaStreamWaitEvent(fs, od->ev_sync, 0));                                   // reads them on the context's stream (one step without overlap)
+        od->seen_epoch = ctx->filt_epoch;
+      }
       if (od->free_valid[pr]) TBV_CUDA(cudaStreamWaitEvent(fs, od->ev_free[pr], 0));        // step t - 2 has read these clouds for the last time
       if (od->input_ready) TBV_CUDA(cudaStreamWaitEvent(fs, od->input_ready, 0));           // host-input pipeline: the scans are uploaded
     } else if (od->input_ready) {
@@ -502,7 +510,9 @@ int tbv_odom_set_overlap(tbv_odom* od, int enable) {
       TBV_CUDA(cudaEventCreateWithFlags(&od->ev_filtered[i], cudaEventDisableTiming));
       TBV_CUDA(cudaEventCreateWithFlags(&od->ev_free[i], cudaEventDisableTiming));
     }
+    TBV_CUDA(cudaEventCreateWithFlags(&od->ev_sync, cudaEventDisableTiming));
   }
+  od->seen_epoch = ctx->filt_epoch;
   od->free_valid[0] = od->free_valid[1] = false;
   od->overlap = enable != 0;
   return TBV_OK;

@@ -136,6 +136,7 @@ struct tbv_ctx {
   tbv::Prof prof;
   std::vector<tbv::SmemOptIn> smem_optin;  // per context (= per device): no process-global launch state
   tbv::FilterState filt;
+  unsigned long long filt_epoch = 0;   // bumped by every filter call that writes the context's clouds on the context's stream (see tbv_odom_set_overlap)
   void* cells_scratch = nullptr;  // tbv::CellsScratch (k_cells.cu)
   void* reg_scratch = nullptr;    // tbv::RegScratch (k_register.cu)
   void* comm = nullptr;           // tbv::CommState (k_comm.cu): NCCL communicator + exchange buffers, or null

@@ -200,10 +200,14 @@ def test_overlapped_steps_change_nothing(ctx, wire):
                 fu.submit(bufs[f & 1].ptr)
                 if f >= 1:
                     take(fu.collect())
+                if f == 3:
+                    ctx.StructuredKStrongest(st.scans[:2])        # another user of the context's clouds between two overlapped steps
             take(fu.collect())
         else:
             for f in range(8):
                 fu.step_dev(dev[f].data_ptr())
+                if f == 3:
+                    ctx.StructuredKStrongest(st.scans[:2])        # (enqueued behind the step, before its results are fetched)
                 take(fu.fetch())
         filt, _ = ctx.filter_fetch(n_seq, n_az, p.filter.k_strongest)      # the last step's (compensated) clouds
         fu.close()
