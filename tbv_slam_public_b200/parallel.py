@@ -12,7 +12,8 @@ What shards and how
     is what PoseGraph::AddConstraintThSafe would have seen in the serial program.
 
 The exchange itself lives behind the C-ABI (tbv_comm_init_rank / tbv_loopdb_register_sharded / tbv_allgather_constraints:
-ncclAllGather on the context's stream + a device merge, csrc/k_comm.cu) so that a C++/ROS host can run it; on GPUs this module
+ncclAllGather + a device merge, csrc/k_comm.cu; tbv_loopdb_submit_sharded / _collect_sharded keep two batches in flight with the exchange
+on a second stream) so that a C++/ROS host can run it; on GPUs this module
 only hands the library an ncclUniqueId through torch.distributed's store (`init_comm`).  `all_gather_constraints` below is the
 same record exchange over a torch.distributed group and exists for the gloo / world-2 CPU tests of the host logic.
 """

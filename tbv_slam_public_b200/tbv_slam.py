@@ -72,7 +72,9 @@ class GpuLoopDevice:
     def __init__(self, ctx, max_keyframes: int, cell_capacity: int = 1024, sc_params=None, sharded: bool = False, group=None):
         """sharded: register candidates through parallel.ShardedLoopClosure — every rank of the torch.distributed group holds the whole
         keyframe database and registers the candidates with id_from mod world == rank; the accepted constraints are all-gathered.
-        All ranks must then run the same search (same graph, same calls); useful with SearchAndAddConstraintBatched."""
+        All ranks must then run the same search (same graph, same calls); useful with SearchAndAddConstraintBatched.
+        Only ACCEPTED candidates are exchanged (128 bytes each): a rejected candidate's record carries score 0.0 in this mode, where the
+        single-GPU path reports the score its failed registration ended with (a log column; no decision reads it)."""
         from . import api
         self.api, self.ctx = api, ctx
         self.rsc = api.RSCManager(ctx, sc_params)
