@@ -706,6 +706,7 @@ struct RegCtx {
 };
 
 struct RegShared {
+  unsigned long long stage_bar;   // mbarrier: completion of the bulk copies (TMA) that stage the fixed sets' grid entries
   double acc[NACC];
   double warp_acc[RG_WARPS][NACC];
   double ex[3], cs[2];
@@ -1142,6 +1143,28 @@ __device__ __forceinline__ void rg_publish_eval_point(RegShared& sh, int lane, b
 // ---- set-up: the problem's constants, L2 prefetch of its working set, staging of what the search reads into shared memory
 // STAGE_SRC: also stage the moving set's means (the fixed-scan-major association of the generic kernel re-reads them for every fixed scan;
 // the source-major association of the specialised kernels reads them once from global memory and leaves the room to the L1 cache).
+// TMA bulk copy global -> shared memory with completion on an mbarrier (cp.async.bulk, SASS UBLKCP): source, destination and size are
+// multiples of 16 bytes.
+__device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rg_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(rg_smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(rg_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void rg_bar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RG_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RG_WAIT_DONE;\n"
+      "bra RG_WAIT_LOOP;\n"
+      "RG_WAIT_DONE:\n"
+      "}\n" ::"r"(rg_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 template <bool STAGE_SRC>
 __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg_stage, int stage_bytes, const SetView* __restrict__ sets,
                                       const int* __restrict__ fixed_set, int fixed_first) {
@@ -1196,21 +1219,29 @@ __device__ __forceinline__ void rg_setup(RegShared& sh, uint8_t* __restrict__ rg
       sh.row_off[f] = need; need += ((sh.grid[f].ny + 1) * 2 + 15) & ~15;
     }
     sh.c.staged = (ok && need <= stage_bytes) ? 1 : 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(rg_smem_u32(&sh.stage_bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
   if (c.staged) {
+    // the grid entries of every fixed set: ONE bulk copy (TMA) per set, all in flight together, completion on one mbarrier
+    uint32_t bulk_bytes = 0;
+    for (int f = 0; f < n_fixed; f++) bulk_bytes += (uint32_t)sh.n_tgt[f] * 16u;
+    if (tid == 0 && bulk_bytes > 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(rg_smem_u32(&sh.stage_bar)), "r"(bulk_bytes) : "memory");
+      for (int f = 0; f < n_fixed; f++)
+        if (sh.n_tgt[f] > 0) rg_bulk_load(rg_stage + sh.ent_off[f], sh.tgt[f].gent, (uint32_t)sh.n_tgt[f] * 16u, &sh.stage_bar);
+    }
     double2* su = reinterpret_cast<double2*>(rg_stage);
     if (STAGE_SRC)
       for (int j = tid; j < n_src; j += blockDim.x) su[j] = make_double2(c.sf[(size_t)CF_U0 * c.scap + j], c.sf[(size_t)CF_U1 * c.scap + j]);
     for (int f = 0; f < n_fixed; f++) {
-      float4* e = reinterpret_cast<float4*>(rg_stage + sh.ent_off[f]);
       uint16_t* rw = reinterpret_cast<uint16_t*>(rg_stage + sh.row_off[f]);
       const int nt = sh.n_tgt[f], ny = sh.grid[f].ny, nx = sh.grid[f].nx;
-      const float4* __restrict__ gent = sh.tgt[f].gent;
       const uint16_t* __restrict__ gstart = sh.tgt[f].gstart;
-      for (int j = tid; j < nt; j += blockDim.x) e[j] = gent[j];
-      for (int k = tid; k <= ny; k += blockDim.x) rw[k] = k < ny ? gstart[k * nx] : (uint16_t)nt;
+      for (int k = tid; k <= ny; k += blockDim.x) rw[k] = k < ny ? gstart[k * nx] : (uint16_t)nt;   // one offset per bucket row (a strided gather)
     }
+    if (bulk_bytes > 0) rg_bar_wait(&sh.stage_bar, 0);
   }
   __syncthreads();
 }
